@@ -1,0 +1,115 @@
+"""CPU: pin oracle/flamo_oracle.py against the golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py).  Bit-level agreement is expected when the oracle
+reproduces the reference's float32 internals; the full-precision oracle must stay within
+the reference's own float32 noise recorded in each fixture."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+from oracle import flamo_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def params_of(g, dtype=torch.float64):
+    out, i = [], 0
+    while f"param_{i}" in g:
+        out.append(torch.tensor(g[f"param_{i}"], dtype=dtype))
+        i += 1
+    return out
+
+
+def rel_err(Y, Yref):
+    den = np.maximum(np.abs(Yref), 1e-3 * np.abs(Yref).max())
+    return (np.abs(Y - Yref) / den).max()
+
+
+@pytest.mark.parametrize("name", list(C.CASES))
+def test_oracle_matches_reference(name):
+    case, g = C.CASES[name], load(name)
+    node = O.from_desc(case["desc"])
+    M = case["nfft"] // 2 + 1
+    n_in = g["Y"].shape  # noqa
+    params = params_of(g)
+    # requires_grad flags come from which grads the reference produced
+    for i, p in enumerate(params):
+        p.requires_grad_(f"grad_{i}" in g)
+    X = C.make_input(case["B"], M, _n_in(case["desc"]), case["C"])
+    O.REF_FP32_INTERNALS = True
+    try:
+        Y = O.forward(node, X, params, case["nfft"], case["alias"])
+        assert rel_err(Y.detach()[:, g["bins"]].numpy(), g["Y"]) < 1e-11
+        gp = [p for p in params if p.requires_grad]
+        if gp:
+            loss = C.golden_loss(Y)
+            assert abs(loss.item() - float(g["loss"])) <= 1e-11 * max(1.0, abs(float(g["loss"])))
+            grads = torch.autograd.grad(loss, gp)
+            k = 0
+            for i, p in enumerate(params):
+                if p.requires_grad:
+                    ref = g[f"grad_{i}"]
+                    assert np.abs(grads[k].numpy() - ref).max() <= 1e-10 * (np.abs(ref).max() + 1e-30), (name, i)
+                    k += 1
+    finally:
+        O.REF_FP32_INTERNALS = False
+    # full-precision oracle: within the reference's own float32 noise
+    with torch.no_grad():
+        Yt = O.forward(node, X, [p.detach() for p in params], case["nfft"], case["alias"])
+    assert rel_err(Yt[:, g["bins"]].numpy(), g["Y"]) <= max(1e-11, 1.01 * float(g["ref_fp32_noise"]))
+
+
+def _n_in(desc):
+    name = desc[0]
+    if name == "Series":
+        return _n_in(desc[1][0])
+    if name == "Recursion":
+        return _n_in(desc[1])
+    size = desc[1]["size"]
+    return size[-1]
+
+
+def test_known_answer_probe():
+    """examples/e10_probe.py:149-157: z-plane probe == bin sweep (< 5e-3) for the 4x4 FDN."""
+    g = load("kat_probe_fdn4")
+    node = O.from_desc(C.probe_fdn_desc())
+    nfft = 2**15
+    M = nfft // 2 + 1
+    X = torch.ones(1, M, 1, dtype=torch.complex128)
+    Y = O.forward(node, X, params_of(g), nfft, 0.0)[0, g["bins"]].numpy()
+    assert np.abs(Y - g["Y"][0]).max() < 1e-11
+    assert np.abs(Y - g["probe"][:, :, 0]).max() < 5e-3
+
+
+def test_train_trace():
+    """Three reference Trainer.train_step calls (Adam, mse + 0.2*sparsity) reproduced by the oracle."""
+    g = np.load(os.path.join(GOLD, "train_trace_fdn8.npz"))
+    from flamo_b200 import workloads as W
+
+    node = O.from_desc(W.fdn(8))
+    nfft = 4096
+    params, i = [], 0
+    while f"param0_{i}" in g:
+        params.append(torch.tensor(g[f"param0_{i}"]))
+        i += 1
+    for p, flag in zip(params, (True, False, True, True)):
+        p.requires_grad_(flag)
+    fb_node = node.children[1].children[1]
+    crit = [
+        (1, lambda est, tgt, ps: O.mse_loss(est, tgt)),
+        (0.2, lambda est, tgt, ps: O.sparsity_loss(O.mapped_matrix(fb_node, ps[2]))),
+    ]
+    tr = O.OracleTrainer(node, params, nfft, W.ALIAS_DECAY_DB, crit, lr=1e-3)
+    x = torch.zeros(1, nfft // 2 + 1, 1, dtype=torch.float64)
+    x[:, 0, :] = 1
+    y = torch.ones(1, nfft // 2 + 1, 1, dtype=torch.float64)
+    losses = [tr.train_step(x, y) for _ in range(3)]
+    assert np.allclose(losses, g["losses"], rtol=1e-10, atol=0)
+    for i, p in enumerate(params):
+        assert np.allclose(p.detach().numpy(), g[f"param3_{i}"], rtol=1e-9, atol=1e-12)
