@@ -1,0 +1,137 @@
+"""ctypes binding of libfsweep.so (include/fsweep.h).  No torch types cross this boundary:
+only raw device pointers, sizes and the CUDA stream handle.
+
+The library is built in-tree by `make -C flamo_b200/csrc` (see __graft_entry__.build()).  If it
+is missing the import of any compute entry point fails loudly — there is no CPU or PyTorch
+fallback for the sweep.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfsweep.so")
+
+OK, E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_CUDA = 0, -1, -2, -3, -4
+C64, C128 = 0, 1
+EPI_NONE, EPI_ABS = 0, 1
+OP_GAIN, OP_PGAIN, OP_SOS, OP_PSOS, OP_DELAY, OP_PDELAY, OP_TABLE, OP_PTABLE, OP_RECURSION = range(1, 10)
+F_ISINT, F_GRAD = 1, 2
+
+EXPORTS = [
+    "fsweep_version", "fsweep_last_error", "fsweep_plan_create", "fsweep_plan_destroy",
+    "fsweep_plan_num_coeffs", "fsweep_plan_coeff_numel", "fsweep_workspace_bytes",
+    "fsweep_forward", "fsweep_backward", "fsweep_last_launch_count",
+]
+
+
+class Op(C.Structure):
+    """fsweep_op_t"""
+    _fields_ = [
+        ("kind", C.c_int32), ("n_out", C.c_int32), ("n_in", C.c_int32), ("n_sections", C.c_int32),
+        ("flags", C.c_uint32), ("n_ff", C.c_int32), ("n_fb", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class SweepError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libfsweep error {code}: {msg}")
+        self.code = code
+
+
+class Unsupported(SweepError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libfsweep.so once; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA sweep library is not built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C flamo_b200/csrc -j8`. "
+            "flamo_b200 has no CPU fallback for the frequency sweep."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.fsweep_version.restype = i32
+    L.fsweep_last_error.restype = C.c_char_p
+    L.fsweep_last_launch_count.restype = i32
+    L.fsweep_plan_create.restype = i32
+    L.fsweep_plan_create.argtypes = [C.POINTER(Op), i32, i64, C.c_double, i32, C.POINTER(vp)]
+    L.fsweep_plan_destroy.restype = i32
+    L.fsweep_plan_destroy.argtypes = [vp]
+    L.fsweep_plan_num_coeffs.restype = i32
+    L.fsweep_plan_num_coeffs.argtypes = [vp]
+    L.fsweep_plan_coeff_numel.restype = i64
+    L.fsweep_plan_coeff_numel.argtypes = [vp, i32, i64]
+    L.fsweep_workspace_bytes.restype = C.c_size_t
+    L.fsweep_workspace_bytes.argtypes = [vp, i64, i64, i64]
+    L.fsweep_forward.restype = i32
+    L.fsweep_forward.argtypes = [vp, C.POINTER(vp), vp, i64, vp, i64, i64, i64, i64, i64, i32, vp]
+    L.fsweep_backward.restype = i32
+    L.fsweep_backward.argtypes = [vp, C.POINTER(vp), vp, i64, vp, i64, C.POINTER(vp), vp, i64, i64, i64, i64, i64,
+                                  i32, vp, C.c_size_t, vp]
+    _lib = L
+    return L
+
+
+def check(code):
+    if code == OK:
+        return
+    msg = lib().fsweep_last_error().decode()
+    raise (Unsupported if code == E_UNSUPPORTED else SweepError)(code, msg)
+
+
+class Plan:
+    """Owns one fsweep_plan_t."""
+
+    def __init__(self, ops, nfft, alias_decay_db, dtype):
+        L = lib()
+        arr = (Op * len(ops))(*ops)
+        h = C.c_void_p()
+        check(L.fsweep_plan_create(arr, len(ops), int(nfft), float(alias_decay_db), int(dtype), C.byref(h)))
+        self.handle = h
+        self.dtype = dtype
+        self.n_coeffs = L.fsweep_plan_num_coeffs(h)
+        self.launches = 0
+
+    def coeff_numel(self, slot, M):
+        return lib().fsweep_plan_coeff_numel(self.handle, slot, M)
+
+    def workspace_bytes(self, batch, cols, n_bins):
+        return lib().fsweep_workspace_bytes(self.handle, batch, cols, n_bins)
+
+    def forward(self, coef_ptrs, x_ptr, xbs, y_ptr, ybs, batch, cols, bin_begin, n_bins, epilogue, stream):
+        L = lib()
+        cp = (C.c_void_p * len(coef_ptrs))(*coef_ptrs)
+        check(L.fsweep_forward(self.handle, cp, x_ptr, xbs, y_ptr, ybs, batch, cols, bin_begin, n_bins, epilogue,
+                               stream))
+        n = L.fsweep_last_launch_count()
+        self.launches += n
+        return n
+
+    def backward(self, coef_ptrs, x_ptr, xbs, gy_ptr, gybs, grad_ptrs, gx_ptr, gxbs, batch, cols, bin_begin, n_bins,
+                 epilogue, ws_ptr, ws_bytes, stream):
+        L = lib()
+        cp = (C.c_void_p * len(coef_ptrs))(*coef_ptrs)
+        gp = (C.c_void_p * len(grad_ptrs))(*grad_ptrs)
+        check(L.fsweep_backward(self.handle, cp, x_ptr, xbs, gy_ptr, gybs, gp, gx_ptr, gxbs, batch, cols, bin_begin,
+                                n_bins, epilogue, ws_ptr, ws_bytes, stream))
+        n = L.fsweep_last_launch_count()
+        self.launches += n
+        return n
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().fsweep_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

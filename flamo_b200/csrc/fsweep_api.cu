@@ -1,0 +1,518 @@
+// fsweep_api.cu — the C ABI declared in include/fsweep.h: plan validation / lowering to step
+// tables, workspace sizing, and the forward / backward launches.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <type_traits>
+#include <vector>
+
+#include "fsweep_kernels.cuh"
+
+using namespace fsweep;
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+bool kind_is_diag(int k) {
+  return k == FSWEEP_OP_PGAIN || k == FSWEEP_OP_PSOS || k == FSWEEP_OP_PDELAY || k == FSWEEP_OP_PTABLE;
+}
+bool kind_is_table(int k) { return k == FSWEEP_OP_TABLE || k == FSWEEP_OP_PTABLE; }
+bool kind_is_leaf(int k) { return k >= FSWEEP_OP_GAIN && k <= FSWEEP_OP_PTABLE; }
+
+int row_len_of(const fsweep_op_t& o) {
+  switch (o.kind) {
+    case FSWEEP_OP_GAIN:
+    case FSWEEP_OP_DELAY:
+      return o.n_in;
+    case FSWEEP_OP_PGAIN:
+    case FSWEEP_OP_PDELAY:
+      return 1;
+    case FSWEEP_OP_SOS:
+      return o.n_sections * o.n_in * 8;
+    case FSWEEP_OP_PSOS:
+      return o.n_sections * 8;
+    default:
+      return 0;
+  }
+}
+
+constexpr int MAX_GRID = 2048;
+constexpr size_t SMEM_ACC_BUDGET = 64 * 1024;
+
+}  // namespace
+
+struct fsweep_plan {
+  int dtype;
+  int G;
+  ProgK prog;         // template: everything but pointers and the gx-dependent flag
+  int first_pre_rstep;  // index in rsteps of op 0's reverse step when it is a top-level op (-1 otherwise)
+  int n_coeffs;
+  std::vector<fsweep_op_t> leaf;  // leaf ops in slot order == ProgK::ops order
+  bool any_global, any_acc;
+  // lazily filled launch geometry: [cc index 0:1, 1:4][fwd, bwd]
+  std::mutex mu;
+  int blocks_per_sm[2][2] = {{0, 0}, {0, 0}};
+  int num_sms = 0;
+};
+
+extern "C" int fsweep_version(void) { return FSWEEP_VERSION; }
+extern "C" const char* fsweep_last_error(void) { return g_err; }
+extern "C" int fsweep_last_launch_count(void) { return g_launches; }
+
+extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nfft, double alias_decay_db, int dtype,
+                                  fsweep_plan_t** out) {
+  if (!ops || !out || n_ops <= 0) return fail(FSWEEP_E_BADARG, "null or empty program");
+  if (dtype != FSWEEP_C64 && dtype != FSWEEP_C128) return fail(FSWEEP_E_BADARG, "bad dtype %d", dtype);
+  if (nfft < 2) return fail(FSWEEP_E_BADARG, "bad nfft %lld", (long long)nfft);
+
+  // ---- split into pre | ff | fb | post and validate
+  std::vector<int> pre, ff, fb, post;
+  int rec = -1;
+  for (int i = 0; i < n_ops;) {
+    const fsweep_op_t& o = ops[i];
+    if (o.kind == FSWEEP_OP_RECURSION) {
+      if (rec >= 0) return fail(FSWEEP_E_UNSUPPORTED, "more than one RECURSION in one program (split the series)");
+      if (o.n_ff < 1 || o.n_fb < 1)
+        return fail(FSWEEP_E_BADARG, "RECURSION at %d: bad chain lengths (%d, %d)", i, o.n_ff, o.n_fb);
+      if (i + 1 + o.n_ff + o.n_fb > n_ops) return fail(FSWEEP_E_BADARG, "RECURSION at %d: chains run past the end", i);
+      rec = i;
+      for (int j = 0; j < o.n_ff; ++j) ff.push_back(i + 1 + j);
+      for (int j = 0; j < o.n_fb; ++j) fb.push_back(i + 1 + o.n_ff + j);
+      i += 1 + o.n_ff + o.n_fb;
+    } else {
+      (rec < 0 ? pre : post).push_back(i);
+      ++i;
+    }
+  }
+  int width = 0;
+  auto check_leaf = [&](int i) -> int {
+    const fsweep_op_t& o = ops[i];
+    if (!kind_is_leaf(o.kind))
+      return fail(o.kind == FSWEEP_OP_RECURSION ? FSWEEP_E_UNSUPPORTED : FSWEEP_E_BADARG,
+                  "op %d: kind %d not allowed here (nested recursion is unsupported)", i, o.kind);
+    if (o.n_in < 1 || o.n_out < 1) return fail(FSWEEP_E_BADARG, "op %d: bad channel counts", i);
+    if (kind_is_diag(o.kind) && o.n_in != o.n_out) return fail(FSWEEP_E_BADARG, "op %d: diagonal kind needs n_in == n_out", i);
+    if ((o.kind == FSWEEP_OP_SOS || o.kind == FSWEEP_OP_PSOS) && o.n_sections < 1)
+      return fail(FSWEEP_E_BADARG, "op %d: SOS needs n_sections >= 1", i);
+    width = std::max(width, std::max(o.n_in, o.n_out));
+    return FSWEEP_OK;
+  };
+  auto check_chain = [&](const std::vector<int>& c, const char* what) -> int {
+    for (size_t j = 0; j < c.size(); ++j) {
+      int r = check_leaf(c[j]);
+      if (r) return r;
+      if (j > 0 && ops[c[j]].n_in != ops[c[j - 1]].n_out)
+        return fail(FSWEEP_E_BADARG, "%s chain: op %d has %d inputs but op %d has %d outputs", what, c[j], ops[c[j]].n_in,
+                    c[j - 1], ops[c[j - 1]].n_out);
+    }
+    return FSWEEP_OK;
+  };
+  int r;
+  if ((r = check_chain(pre, "series"))) return r;
+  if ((r = check_chain(post, "series"))) return r;
+  int rec_n = 0, rec_in = 0;
+  if (rec >= 0) {
+    if ((r = check_chain(ff, "feedforward"))) return r;
+    if ((r = check_chain(fb, "feedback"))) return r;
+    rec_in = ops[ff.front()].n_in;
+    rec_n = ops[ff.back()].n_out;
+    if (ops[fb.front()].n_in != rec_n || ops[fb.back()].n_out != rec_in)
+      return fail(FSWEEP_E_BADARG, "recursion: feedforward is %d->%d but feedback is %d->%d", rec_in, rec_n,
+                  ops[fb.front()].n_in, ops[fb.back()].n_out);
+    if (!pre.empty() && ops[pre.back()].n_out != rec_in)
+      return fail(FSWEEP_E_BADARG, "recursion input has %d channels but the preceding op outputs %d", rec_in,
+                  ops[pre.back()].n_out);
+    if (!post.empty() && ops[post.front()].n_in != rec_n)
+      return fail(FSWEEP_E_BADARG, "recursion output has %d channels but the next op takes %d", rec_n,
+                  ops[post.front()].n_in);
+  }
+  if (width > 32)
+    return fail(FSWEEP_E_UNSUPPORTED, "channel width %d > 32: not supported by the register-resident sweep", width);
+  const int n_leaf = (int)(pre.size() + ff.size() + fb.size() + post.size());
+  if (n_leaf > MAX_OPS) return fail(FSWEEP_E_UNSUPPORTED, "program has %d ops (max %d): split the series", n_leaf, MAX_OPS);
+
+  fsweep_plan* p = new (std::nothrow) fsweep_plan();
+  if (!p) return fail(FSWEEP_E_BADARG, "out of host memory");
+  p->dtype = dtype;
+  int G = 1;
+  while (G < width) G <<= 1;
+  p->G = G;
+
+  ProgK& P = p->prog;
+  memset(&P, 0, sizeof(P));
+  P.nfft = nfft;
+  const double lng = -std::fabs(alias_decay_db) / (double)nfft / 20.0 * std::log(10.0);
+  P.lng = lng;
+  P.gm1 = std::expm1(lng);
+  P.g2m1 = std::expm1(2.0 * lng);
+  P.rec_n = rec_n;
+
+  // kernel op order == coefficient slot order == order of appearance in the flat program
+  std::vector<int> order;  // flat index of every leaf, ascending
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind != FSWEEP_OP_RECURSION) order.push_back(i);
+  std::vector<int> slot_of(n_ops, -1);
+  for (size_t s = 0; s < order.size(); ++s) slot_of[order[s]] = (int)s;
+  p->n_coeffs = (int)order.size();
+  P.n_ops = p->n_coeffs;
+  const size_t real_sz = dtype == FSWEEP_C64 ? 4 : 8;
+
+  int acc_per_lane = 0, acc_total = 0;
+  p->any_global = p->any_acc = false;
+  for (size_t s = 0; s < order.size(); ++s) {
+    const fsweep_op_t& o = ops[order[s]];
+    p->leaf.push_back(o);
+    OpK& k = P.ops[s];
+    k.kind = o.kind;
+    k.n_out = o.n_out;
+    k.n_in = o.n_in;
+    k.K = o.n_sections;
+    k.flags = o.flags;
+    k.row_len = row_len_of(o);
+    k.acc_off = acc_total;
+    k.row_off = 0;
+    k.acc_mode = ACC_NONE;
+    if (o.flags & FSWEEP_F_GRAD) {
+      if (kind_is_table(o.kind)) {
+        k.acc_mode = ACC_TABLE;
+      } else {
+        k.acc_mode = ACC_SMEM;
+        acc_total += o.n_out * k.row_len;
+      }
+    }
+  }
+  // shared-memory accumulator budget: spill the largest rows to global atomics until it fits
+  for (;;) {
+    acc_per_lane = 0;
+    int big = -1;
+    for (int s = 0; s < P.n_ops; ++s)
+      if (P.ops[s].acc_mode == ACC_SMEM) {
+        P.ops[s].row_off = acc_per_lane;
+        acc_per_lane += P.ops[s].row_len;
+        if (big < 0 || P.ops[s].row_len > P.ops[big].row_len) big = s;
+      }
+    if ((size_t)acc_per_lane * BLOCK * real_sz <= SMEM_ACC_BUDGET || big < 0) break;
+    P.ops[big].acc_mode = ACC_GLOBAL;
+  }
+  for (int s = 0; s < P.n_ops; ++s) {
+    if (P.ops[s].acc_mode == ACC_GLOBAL) p->any_global = true;
+    if (P.ops[s].acc_mode == ACC_SMEM || P.ops[s].acc_mode == ACC_GLOBAL) p->any_acc = true;
+  }
+  P.acc_per_lane = acc_per_lane;
+  P.acc_total = acc_total;
+
+  const std::vector<int>& first_chain = !pre.empty() ? pre : (rec >= 0 ? ff : post);
+  const std::vector<int>& last_chain = !post.empty() ? post : (rec >= 0 ? ff : pre);
+  P.in_ch = ops[first_chain.front()].n_in;
+  P.out_ch = ops[last_chain.back()].n_out;
+
+  // ---- step tables
+  auto S = [&](int flat, unsigned fl) {
+    Step s;
+    s.op = (unsigned char)slot_of[flat];
+    s.flags = (unsigned char)fl;
+    return s;
+  };
+  int nf = 0, nm = 0, nb = 0, nr = 0, saves = 0;
+  for (int i : pre) P.fsteps[nf++] = S(i, 0);
+  for (size_t j = 0; j < ff.size(); ++j) P.fsteps[nf++] = S(ff[j], j + 1 == ff.size() ? ST_SOLVE : 0);
+  for (int i : post) P.fsteps[nf++] = S(i, 0);
+  for (size_t j = 0; j < fb.size(); ++j)
+    P.msteps[nm++] = S(fb[j], (j == 0 && !kind_is_diag(ops[fb[j]].kind)) ? ST_IDENT : 0);
+  for (int i : ff) P.msteps[nm++] = S(i, 0);
+
+  for (int i : pre) P.bsteps[nb++] = S(i, ST_SAVE), ++saves;
+  for (size_t j = 0; j < ff.size(); ++j)
+    P.bsteps[nb++] = S(ff[j], (j == 0 ? ST_SAVE_X : 0) | (j + 1 == ff.size() ? ST_SOLVE : 0));
+  for (size_t j = 0; j < fb.size(); ++j) P.bsteps[nb++] = S(fb[j], ST_SAVE | (j + 1 == fb.size() ? ST_ADD_X : 0)), ++saves;
+  for (int i : ff) P.bsteps[nb++] = S(i, ST_SAVE), ++saves;
+  for (int i : post) P.bsteps[nb++] = S(i, ST_SAVE), ++saves;
+
+  for (int j = (int)post.size() - 1; j >= 0; --j) P.rsteps[nr++] = S(post[j], RS_NEED_GIN);
+  for (int j = (int)ff.size() - 1; j >= 0; --j)
+    P.rsteps[nr++] = S(ff[j], RS_NEED_GIN | (j + 1 == (int)ff.size() ? RS_ADJ : 0) | (j == 0 ? RS_SAVE_G : 0));
+  for (int j = (int)fb.size() - 1; j >= 0; --j) P.rsteps[nr++] = S(fb[j], (j > 0 ? RS_NEED_GIN : 0) | (j == 0 ? RS_RESTORE_G : 0));
+  p->first_pre_rstep = -1;
+  for (int j = (int)pre.size() - 1; j >= 0; --j) {
+    if (j == 0) p->first_pre_rstep = nr;
+    P.rsteps[nr++] = S(pre[j], j > 0 ? RS_NEED_GIN : 0);
+  }
+  P.n_fsteps = nf;
+  P.n_msteps = nm;
+  P.n_bsteps = nb;
+  P.n_rsteps = nr;
+  P.n_slots = saves + 1;
+
+  *out = p;
+  return FSWEEP_OK;
+}
+
+extern "C" int fsweep_plan_destroy(fsweep_plan_t* plan) {
+  delete plan;
+  return FSWEEP_OK;
+}
+
+extern "C" int fsweep_plan_num_coeffs(const fsweep_plan_t* plan) { return plan ? plan->n_coeffs : 0; }
+
+extern "C" int64_t fsweep_plan_coeff_numel(const fsweep_plan_t* plan, int slot, int64_t M) {
+  if (!plan || slot < 0 || slot >= plan->n_coeffs) return -1;
+  const fsweep_op_t& o = plan->leaf[slot];
+  switch (o.kind) {
+    case FSWEEP_OP_GAIN:
+    case FSWEEP_OP_DELAY:
+      return (int64_t)o.n_out * o.n_in;
+    case FSWEEP_OP_PGAIN:
+    case FSWEEP_OP_PDELAY:
+      return o.n_out;
+    case FSWEEP_OP_SOS:
+      return (int64_t)o.n_sections * o.n_in * o.n_out * 8;
+    case FSWEEP_OP_PSOS:
+      return (int64_t)o.n_sections * o.n_out * 8;
+    case FSWEEP_OP_TABLE:
+      return M * o.n_out * o.n_in;
+    case FSWEEP_OP_PTABLE:
+      return M * o.n_out;
+    default:
+      return -1;
+  }
+}
+
+namespace {
+
+int cc_of(int64_t ncols) { return ncols == 1 ? 1 : 4; }
+
+size_t smem_fwd(const fsweep_plan* p) { return (size_t)p->G * BLOCK * 2 * (p->dtype == FSWEEP_C64 ? 4 : 8); }
+size_t smem_bwd(const fsweep_plan* p, int cc) {
+  const size_t rs = p->dtype == FSWEEP_C64 ? 4 : 8;
+  return smem_fwd(p) + (size_t)p->prog.n_slots * cc * BLOCK * 2 * rs + (size_t)p->prog.acc_per_lane * BLOCK * rs;
+}
+
+int grid_cap(int64_t n_bins, int G) {
+  const int64_t per_block = BLOCK / G;
+  int64_t need = (n_bins + per_block - 1) / per_block;
+  return (int)std::min<int64_t>(need, MAX_GRID);
+}
+
+template <typename F>
+cudaError_t by_group(int G, F&& f) {
+  switch (G) {
+    case 1: return f(std::integral_constant<int, 1>());
+    case 2: return f(std::integral_constant<int, 2>());
+    case 4: return f(std::integral_constant<int, 4>());
+    case 8: return f(std::integral_constant<int, 8>());
+    case 16: return f(std::integral_constant<int, 16>());
+    default: return f(std::integral_constant<int, 32>());
+  }
+}
+
+// persistent grid: resident blocks per SM (occupancy query, cached) x SM count, capped by the work
+int pick_grid(fsweep_plan* p, int cc, bool bwd, size_t smem, int64_t n_bins, cudaError_t* err) {
+  const int ci = cc == 1 ? 0 : 1;
+  *err = cudaSuccess;
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (p->num_sms == 0) {
+      int dev = 0;
+      if ((*err = cudaGetDevice(&dev)) != cudaSuccess) return 0;
+      if ((*err = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return 0;
+    }
+    if (p->blocks_per_sm[ci][bwd] == 0) {
+      int n = 0;
+      const int dtype = p->dtype;
+      *err = by_group(p->G, [&](auto g) { return occupancy<decltype(g)::value>(dtype, cc, bwd, smem, &n); });
+      if (*err != cudaSuccess) return 0;
+      if (n < 1) {
+        *err = cudaErrorLaunchOutOfResources;
+        return 0;
+      }
+      p->blocks_per_sm[ci][bwd] = n;
+    }
+  }
+  int64_t resident = (int64_t)p->blocks_per_sm[ci][bwd] * p->num_sms;
+  return (int)std::min<int64_t>(resident, grid_cap(n_bins, p->G));
+}
+
+int check_common(const fsweep_plan* plan, const void* const* coeffs, const void* x, int64_t batch, int64_t cols,
+                 int64_t bin_begin, int64_t n_bins, int epilogue) {
+  if (!plan || !coeffs || !x) return fail(FSWEEP_E_BADARG, "null plan / coeffs / x");
+  if (batch < 1 || cols < 1 || n_bins < 0 || bin_begin < 0) return fail(FSWEEP_E_BADARG, "bad batch/cols/bins");
+  if (batch * cols > (1 << 20)) return fail(FSWEEP_E_BADARG, "batch*cols too large");
+  if (bin_begin + n_bins > plan->prog.nfft / 2 + 1)
+    return fail(FSWEEP_E_BADARG, "bin range [%lld, %lld) exceeds nfft/2+1", (long long)bin_begin, (long long)(bin_begin + n_bins));
+  if (epilogue != FSWEEP_EPI_NONE && epilogue != FSWEEP_EPI_ABS) return fail(FSWEEP_E_BADARG, "bad epilogue %d", epilogue);
+  for (int s = 0; s < plan->n_coeffs; ++s)
+    if (!coeffs[s]) return fail(FSWEEP_E_BADARG, "coefficient slot %d is null", s);
+  return FSWEEP_OK;
+}
+
+}  // namespace
+
+extern "C" size_t fsweep_workspace_bytes(const fsweep_plan_t* plan, int64_t batch, int64_t cols, int64_t n_bins) {
+  (void)batch;
+  (void)cols;
+  if (!plan) return 0;
+  const size_t rs = plan->dtype == FSWEEP_C64 ? 4 : 8;
+  const size_t grid = (size_t)grid_cap(n_bins, plan->G);
+  size_t partial = grid * (size_t)plan->prog.acc_per_lane * plan->G * rs;
+  size_t gacc = (size_t)plan->prog.acc_total * rs;
+  return ((partial + 255) / 256) * 256 + ((gacc + 255) / 256) * 256 + 256;
+}
+
+extern "C" int fsweep_forward(const fsweep_plan_t* plan_c, const void* const* coeffs, const void* x,
+                              int64_t x_batch_stride, void* y, int64_t y_batch_stride, int64_t batch, int64_t cols,
+                              int64_t bin_begin, int64_t n_bins, int epilogue, void* stream) {
+  g_launches = 0;
+  fsweep_plan* plan = const_cast<fsweep_plan*>(plan_c);
+  int r = check_common(plan, coeffs, x, batch, cols, bin_begin, n_bins, epilogue);
+  if (r) return r;
+  if (!y) return fail(FSWEEP_E_BADARG, "null y");
+  if (n_bins == 0) return FSWEEP_OK;
+  ProgK P = plan->prog;
+  for (int s = 0; s < plan->n_coeffs; ++s) P.ops[s].coef = coeffs[s];
+  SweepArgs A;
+  memset(&A, 0, sizeof(A));
+  A.x = x;
+  A.xbs = x_batch_stride;
+  A.y = y;
+  A.ybs = y_batch_stride;
+  A.batch = (int)batch;
+  A.cols = (int)cols;
+  A.bin_begin = bin_begin;
+  A.n_bins = n_bins;
+  A.epilogue = epilogue;
+  const int cc = cc_of(batch * cols);
+  LaunchCfg cfg;
+  cfg.smem = smem_fwd(plan);
+  cfg.stream = (cudaStream_t)stream;
+  cudaError_t e;
+  cfg.grid = pick_grid(plan, cc, false, cfg.smem, n_bins, &e);
+  if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+  const int dtype = plan->dtype;
+  e = by_group(plan->G, [&](auto g) { return launch_fwd<decltype(g)::value>(dtype, cc, cfg, P, A); });
+  if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "forward launch: %s", cudaGetErrorString(e));
+  g_launches = 1;
+  return FSWEEP_OK;
+}
+
+extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* coeffs, const void* x,
+                               int64_t x_batch_stride, const void* grad_y, int64_t gy_batch_stride,
+                               void* const* grad_coeffs, void* grad_x, int64_t gx_batch_stride, int64_t batch,
+                               int64_t cols, int64_t bin_begin, int64_t n_bins, int epilogue, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  fsweep_plan* plan = const_cast<fsweep_plan*>(plan_c);
+  int r = check_common(plan, coeffs, x, batch, cols, bin_begin, n_bins, epilogue);
+  if (r) return r;
+  if (!grad_y) return fail(FSWEEP_E_BADARG, "null grad_y");
+  if (n_bins == 0) return fail(FSWEEP_E_BADARG, "empty bin range in backward");
+  const size_t need = fsweep_workspace_bytes(plan, batch, cols, n_bins);
+  if (need > 256 && (!workspace || workspace_bytes < need))
+    return fail(FSWEEP_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rs = plan->dtype == FSWEEP_C64 ? 4 : 8;
+
+  ProgK P = plan->prog;
+  bool any_acc_wanted = false;
+  for (int s = 0; s < plan->n_coeffs; ++s) {
+    P.ops[s].coef = coeffs[s];
+    void* gp = grad_coeffs ? grad_coeffs[s] : nullptr;
+    if (P.ops[s].acc_mode == ACC_TABLE) {
+      P.ops[s].gtab = gp;
+      if (!gp) P.ops[s].acc_mode = ACC_NONE;
+    } else if (P.ops[s].acc_mode != ACC_NONE) {
+      if (gp) any_acc_wanted = true;
+    }
+  }
+  if (grad_x && plan->first_pre_rstep >= 0) P.rsteps[plan->first_pre_rstep].flags |= RS_NEED_GIN;
+
+  const int cc = cc_of(batch * cols);
+  LaunchCfg cfg;
+  cfg.smem = smem_bwd(plan, cc);
+  if (cfg.smem > 200 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "backward needs %zu bytes of shared memory", cfg.smem);
+  cfg.stream = st;
+  cudaError_t e;
+  cfg.grid = pick_grid(plan, cc, true, cfg.smem, n_bins, &e);
+  if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+
+  const size_t partial_bytes = (((size_t)grid_cap(n_bins, plan->G) * P.acc_per_lane * plan->G * rs + 255) / 256) * 256;
+  char* ws = reinterpret_cast<char*>(workspace);
+  void* partial = ws;
+  void* gacc = ws ? ws + partial_bytes : nullptr;
+
+  SweepArgs A;
+  memset(&A, 0, sizeof(A));
+  A.x = x;
+  A.xbs = x_batch_stride;
+  A.gy = grad_y;
+  A.gybs = gy_batch_stride;
+  A.gx = grad_x;
+  A.gxbs = gx_batch_stride;
+  A.batch = (int)batch;
+  A.cols = (int)cols;
+  A.bin_begin = bin_begin;
+  A.n_bins = n_bins;
+  A.epilogue = epilogue;
+  A.partial = partial;
+  A.gacc = gacc;
+
+  int launches = 0;
+  if (plan->any_global) {
+    e = cudaMemsetAsync(gacc, 0, (size_t)P.acc_total * rs, st);
+    if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "memset: %s", cudaGetErrorString(e));
+    ++launches;
+  }
+  const int dtype = plan->dtype;
+  e = by_group(plan->G, [&](auto g) { return launch_bwd<decltype(g)::value>(dtype, cc, cfg, P, A); });
+  if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "backward launch: %s", cudaGetErrorString(e));
+  ++launches;
+
+  if (any_acc_wanted) {
+    FinalizeArgs F;
+    memset(&F, 0, sizeof(F));
+    F.n_ops = P.n_ops;
+    F.G = plan->G;
+    F.acc_per_lane = P.acc_per_lane;
+    F.n_blocks = cfg.grid;
+    F.partial = partial;
+    F.gacc = gacc;
+    int max_total = 1;
+    for (int s = 0; s < P.n_ops; ++s) {
+      FinalizeOp& o = F.ops[s];
+      o.kind = P.ops[s].kind;
+      o.n_out = P.ops[s].n_out;
+      o.n_in = P.ops[s].n_in;
+      o.K = P.ops[s].K;
+      o.acc_mode = P.ops[s].acc_mode;
+      o.row_off = P.ops[s].row_off;
+      o.row_len = P.ops[s].row_len;
+      o.acc_off = P.ops[s].acc_off;
+      o.grad = grad_coeffs[s];
+      if (o.grad && (o.acc_mode == ACC_SMEM || o.acc_mode == ACC_GLOBAL))
+        max_total = std::max(max_total, o.n_out * o.row_len);
+    }
+    dim3 grid((unsigned)std::min(64, (max_total + 127) / 128), (unsigned)P.n_ops);
+    if (dtype == FSWEEP_C64)
+      fsweep_finalize_kernel<float><<<grid, 128, 0, st>>>(F);
+    else
+      fsweep_finalize_kernel<double><<<grid, 128, 0, st>>>(F);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "finalize launch: %s", cudaGetErrorString(e));
+    ++launches;
+  }
+  g_launches = launches;
+  return FSWEEP_OK;
+}

@@ -1,0 +1,1027 @@
+// fsweep_kernels.cuh — the bin-sweep kernels (sm_100a), register-resident path for loop widths <= 32.
+//
+// Mapping: one GROUP of G lanes (G = 1,2,4,...,32, a power of two >= the widest channel count of
+// the program) owns one frequency bin; lane r of the group owns ROW r of every per-bin matrix and
+// element r of every per-bin vector.  Dense "H x" products broadcast x_n from lane n with
+// __shfl_sync(width=G); adjoint products "H^H g" are butterfly reductions.  The closed loop
+// (I - F*Fb) is built row-distributed in registers, LU-factored with implicit partial pivoting
+// (pivot lane chosen by an arg-max butterfly; rows never move), and reused for every batch item
+// and trailing column of that bin.  Nothing per-bin is ever written to HBM except y (or g_x).
+//
+// Backward = recompute-in-backward: the forward states are re-derived per bin, parked in
+// thread-private shared-memory slots, and walked in reverse.  The recursion adjoint uses
+//   lambda = A^-H g_y,  u = x + Fb*y,  g_F = lambda u^H,  g_Fb = (F^H lambda) y^H,  g_x = F^H lambda
+// (SURVEY.md appendix A), i.e. two vector-valued chain back-propagations and one adjoint solve with
+// the same LU.  Coefficient gradients are accumulated in thread-private shared-memory columns
+// (no atomics, fixed order -> deterministic), reduced per block, and summed over blocks in float64
+// by fsweep_finalize_kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fsweep.h"
+
+#include <type_traits>
+
+namespace fsweep {
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E) — guarantees static register
+// indices where `#pragma unroll` of nested loops is only a hint
+template <int B, int E, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+// descending: I = E-1 ... B
+template <int B, int E, typename F>
+__device__ __forceinline__ void static_rfor(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, E - 1>{});
+    static_rfor<B, E - 1>(f);
+  }
+}
+
+constexpr int MAX_OPS = 24;
+constexpr int BLOCK = 128;
+constexpr unsigned FULL = 0xffffffffu;
+
+// accumulator placement for one op's coefficient gradient
+constexpr int ACC_NONE = 0;    // no gradient wanted
+constexpr int ACC_SMEM = 1;    // thread-private shared-memory column, reduced at kernel end
+constexpr int ACC_GLOBAL = 2;  // too large for shared memory: atomicAdd straight into the global accumulator
+constexpr int ACC_TABLE = 3;   // TABLE kinds: per-bin gradient written directly
+
+struct OpK {
+  int kind, n_out, n_in, K;
+  unsigned flags;
+  int acc_mode;
+  int row_off;  // ACC_SMEM: offset of this op's per-lane accumulator row
+  int row_len;  // accumulators per row (per lane)
+  int acc_off;  // offset of this op in the flat accumulator / partial buffers (row-major [row][row_len])
+  int pad_;
+  const void* coef;
+  void* gtab;  // ACC_TABLE: gradient table
+};
+
+// The host lowers the op list into small step tables so that every kernel has exactly ONE call
+// site of apply_op / backprop_op (keeps code size and compile time bounded).
+struct Step {
+  unsigned char op;     // index into ProgK::ops
+  unsigned char flags;  // ST_* (forward tables) or RS_* (reverse table)
+};
+// forward-direction step flags
+constexpr unsigned ST_SAVE = 1;    // park the op input in the next saved-state slot (backward only)
+constexpr unsigned ST_SAVE_X = 2;  // before the op: park the state in slot X (recursion input x)
+constexpr unsigned ST_SOLVE = 4;   // after the op: state <- A^-1 state
+constexpr unsigned ST_ADD_X = 8;   // after the op: state += slot X            (u = x + Fb y)
+constexpr unsigned ST_IDENT = 16;  // matrix build: the state is still the identity
+// reverse-direction step flags
+constexpr unsigned RS_NEED_GIN = 1;   // propagate the gradient to the op input
+constexpr unsigned RS_ADJ = 2;        // before the op: g <- A^-H g
+constexpr unsigned RS_SAVE_G = 4;     // after the op: park g in slot X          (g_u)
+constexpr unsigned RS_RESTORE_G = 8;  // after the op: g <- slot X
+
+constexpr int MAX_STEPS = 2 * MAX_OPS;
+
+struct ProgK {
+  int n_ops;
+  int rec_n;  // loop width (0: no recursion)
+  int in_ch, out_ch;
+  int n_slots;       // backward: saved-state slots (the last one is slot X)
+  int acc_per_lane;  // backward: shared-memory accumulators per lane
+  int acc_total;     // backward: flat accumulator count (sum over ops of rows*row_len)
+  int n_fsteps, n_msteps, n_bsteps, n_rsteps;
+  long long nfft;
+  double lng;   // ln(gamma)
+  double gm1;   // gamma - 1
+  double g2m1;  // gamma^2 - 1
+  OpK ops[MAX_OPS];
+  Step fsteps[MAX_OPS];    // forward kernel: signal path
+  Step msteps[MAX_OPS];    // loop-matrix build: Fb chain then F chain, applied to the identity
+  Step bsteps[MAX_STEPS];  // backward kernel: forward recompute with saves
+  Step rsteps[MAX_STEPS];  // backward kernel: reverse sweep
+};
+
+// ------------------------------------------------------------------------------------------ complex
+template <typename T>
+struct cx {
+  T x, y;
+};
+template <typename T>
+__device__ __forceinline__ cx<T> mk(T a, T b) {
+  cx<T> r;
+  r.x = a;
+  r.y = b;
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ cx<T> cmul(cx<T> a, cx<T> b) {
+  return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+template <typename T>
+__device__ __forceinline__ cx<T> cmulc(cx<T> a, cx<T> b) {  // a * conj(b)
+  return mk<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+template <typename T>
+__device__ __forceinline__ void cfma(cx<T>& acc, cx<T> a, cx<T> b) {  // acc += a*b
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+template <typename T>
+__device__ __forceinline__ void cfnma(cx<T>& acc, cx<T> a, cx<T> b) {  // acc -= a*b
+  acc.x = fma(-a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(-a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
+}
+template <typename T>
+__device__ __forceinline__ void cfmac(cx<T>& acc, cx<T> a, cx<T> b) {  // acc += a*conj(b)
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.y, b.x, acc.y);
+  acc.y = fma(-a.x, b.y, acc.y);
+}
+template <typename T>
+__device__ __forceinline__ void cfmacj(cx<T>& acc, cx<T> a, cx<T> b) {  // acc += conj(a)*b
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
+}
+template <typename T>
+__device__ __forceinline__ cx<T> crcp(cx<T> a) {
+  T d = T(1) / (a.x * a.x + a.y * a.y);
+  return mk<T>(a.x * d, -a.y * d);
+}
+template <typename T>
+__device__ __forceinline__ bool czero(cx<T> a) {
+  return a.x == T(0) && a.y == T(0);
+}
+
+template <int G, typename T>
+__device__ __forceinline__ cx<T> shfl(cx<T> v, int src) {
+  return mk<T>(__shfl_sync(FULL, v.x, src, G), __shfl_sync(FULL, v.y, src, G));
+}
+template <int G, typename T>
+__device__ __forceinline__ cx<T> group_sum(cx<T> v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(FULL, v.x, o, G);
+    v.y += __shfl_xor_sync(FULL, v.y, o, G);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void sincospi_t(float a, float* s, float* c) { sincospif(a, s, c); }
+__device__ __forceinline__ void sincospi_t(double a, double* s, double* c) { sincospi(a, s, c); }
+template <typename T>
+__device__ __forceinline__ T eps_of();
+template <>
+__device__ __forceinline__ float eps_of<float>() {
+  return 1.1920928955078125e-07f;
+}
+template <>
+__device__ __forceinline__ double eps_of<double>() {
+  return 2.220446049250313e-16;
+}
+
+// ------------------------------------------------------------------------------- per-bin context
+template <typename T>
+struct Ctx {
+  long long k;   // absolute bin index
+  T omega;       // 2*pi*k/nfft
+  cx<T> u1;      // gamma*z^-1 -/+ 1   (expansion point +1 if plus else -1)
+  cx<T> u2;      // gamma^2*z^-2 - 1
+  bool plus;     // low half of the spectrum: expand section quadratics around w = +1
+  long long nfft;
+  double lng;
+  double inv_nfft;
+};
+
+template <typename T>
+__device__ __forceinline__ Ctx<T> make_ctx(const ProgK& P, long long k) {
+  Ctx<T> c;
+  c.k = k;
+  c.nfft = P.nfft;
+  c.lng = P.lng;
+  c.inv_nfft = 1.0 / (double)P.nfft;
+  double fr = (double)(2 * k) * c.inv_nfft;  // omega/pi in [0,1]
+  T f = (T)fr;
+  T s, co, sh, ch;
+  sincospi_t(f, &s, &co);
+  sincospi_t(f * T(0.5), &sh, &ch);
+  c.omega = (T)(fr * 3.141592653589793238462643383279502884);
+  T g = (T)(P.gm1 + 1.0), g2 = (T)(P.g2m1 + 1.0);
+  c.plus = co >= T(0);
+  // w - 1 = (g-1) - 2 g sin^2(w/2) - j g sin w ;  w + 1 = 2 g cos^2(w/2) - (g-1) - j g sin w
+  if (c.plus)
+    c.u1 = mk<T>((T)P.gm1 - T(2) * g * sh * sh, -g * s);
+  else
+    c.u1 = mk<T>(T(2) * g * ch * ch - (T)P.gm1, -g * s);
+  // w^2 - 1 = (g^2-1) - 2 g^2 sin^2 w - j 2 g^2 sin w cos w
+  c.u2 = mk<T>((T)P.g2m1 - T(2) * g2 * s * s, -T(2) * g2 * s * co);
+  return c;
+}
+
+// ---------------------------------------------------------------------------------- op responses
+__device__ __forceinline__ bool is_dense(int kind) {
+  return kind == FSWEEP_OP_GAIN || kind == FSWEEP_OP_SOS || kind == FSWEEP_OP_DELAY || kind == FSWEEP_OP_TABLE;
+}
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, T (&c)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&c)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w;
+  c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<double>(const double* p, double (&c)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double2 a = __ldg(reinterpret_cast<const double2*>(p) + i);
+    c[2 * i] = a.x;
+    c[2 * i + 1] = a.y;
+  }
+}
+
+// one packed section -> B(w), A(w)
+template <typename T>
+__device__ __forceinline__ void section_eval(const T (&c)[8], const Ctx<T>& ctx, cx<T>& Bv, cx<T>& Av) {
+  T sb = ctx.plus ? c[0] : c[3];
+  T sa = ctx.plus ? c[4] : c[7];
+  Bv = mk<T>(fma(c[2], ctx.u2.x, fma(c[1], ctx.u1.x, sb)), fma(c[2], ctx.u2.y, c[1] * ctx.u1.y));
+  Av = mk<T>(fma(c[6], ctx.u2.x, fma(c[5], ctx.u1.x, sa)), fma(c[6], ctx.u2.y, c[5] * ctx.u1.y));
+}
+
+// H = prod B / prod A with the reference's zero guard (dsp.py:1524-1525)
+template <typename T>
+__device__ __forceinline__ cx<T> sos_eval(const T* p, int K, long stride, const Ctx<T>& ctx, bool& guarded,
+                                          cx<T>& den_out) {
+  cx<T> num = mk<T>(1, 0), den = mk<T>(1, 0);
+  for (int s = 0; s < K; ++s, p += stride) {
+    T c[8];
+    load8<T>(p, c);
+    cx<T> Bv, Av;
+    section_eval<T>(c, ctx, Bv, Av);
+    num = cmul(num, Bv);
+    den = cmul(den, Av);
+  }
+  den_out = den;
+  guarded = czero(den);
+  if (guarded) return mk<T>(eps_of<T>(), T(0));
+  return cmul(num, crcp(den));
+}
+
+// numerator product with section `skip` left out (rare path: a section is exactly zero at this bin)
+template <typename T>
+__device__ __forceinline__ cx<T> sos_num_without(const T* p, int K, long stride, const Ctx<T>& ctx, int skip) {
+  cx<T> num = mk<T>(1, 0);
+  for (int s = 0; s < K; ++s, p += stride) {
+    if (s == skip) continue;
+    T c[8];
+    load8<T>(p, c);
+    cx<T> Bv, Av;
+    section_eval<T>(c, ctx, Bv, Av);
+    num = cmul(num, Bv);
+  }
+  return num;
+}
+
+__device__ __forceinline__ float exp_t(float a) { return expf(a); }
+__device__ __forceinline__ double exp_t(double a) { return exp(a); }
+__device__ __forceinline__ float abs_t(float a, float b) { return hypotf(a, b); }
+__device__ __forceinline__ double abs_t(double a, double b) { return hypot(a, b); }
+
+// H = gamma^d * exp(-j omega_k d).  Integer delays: phase index (k*d mod nfft) formed exactly
+// (in float64 while k*d < 2^53, else in 64-bit integers); fractional: k*d/nfft range-reduced in float64.
+template <typename T>
+__device__ __forceinline__ cx<T> delay_eval(double d, unsigned flags, const Ctx<T>& ctx) {
+  double fr;
+  double dd = d;
+  if (flags & FSWEEP_F_ISINT) {
+    dd = rint(d);
+    double t = (double)ctx.k * dd;
+    if (fabs(t) < 4.0e15) {
+      double q = floor(t * ctx.inv_nfft);
+      double r = fma(-q, (double)ctx.nfft, t);  // exact: t and q*nfft are integers < 2^53
+      if (r < 0.0) r += (double)ctx.nfft;
+      if (r >= (double)ctx.nfft) r -= (double)ctx.nfft;
+      fr = 2.0 * r * ctx.inv_nfft;
+    } else {
+      long long di = llrint(d);
+      unsigned long long a = (unsigned long long)(di < 0 ? -di : di);
+      long long idx = (long long)(((unsigned long long)ctx.k * a) % (unsigned long long)ctx.nfft);
+      fr = (di < 0 ? -2.0 : 2.0) * (double)idx * ctx.inv_nfft;
+    }
+  } else {
+    double t = (double)ctx.k * d * ctx.inv_nfft;
+    t -= floor(t);
+    fr = 2.0 * t;
+  }
+  T s, c;
+  sincospi_t((T)fr, &s, &c);
+  T mag = exp_t((T)(ctx.lng * dd));
+  return mk<T>(mag * c, -mag * s);
+}
+
+// accumulator sink handed to the gradient routines
+template <typename T>
+struct Acc {
+  T* sacc;   // shared: [acc_per_lane][BLOCK]
+  T* gacc;   // global flat accumulator (ACC_GLOBAL ops)
+  int tid;
+  bool valid;  // this group holds a real bin
+  __device__ __forceinline__ void add(const OpK& op, int row, int e, T v) const {
+    if (!valid) return;
+    if (op.acc_mode == ACC_SMEM) {
+      T* p = sacc + (size_t)(op.row_off + e) * BLOCK + tid;
+      *p += v;
+    } else if (op.acc_mode == ACC_GLOBAL) {
+      atomicAdd(gacc + op.acc_off + (size_t)row * op.row_len + e, v);
+    }
+  }
+};
+
+// gradient of one (pair) cascade: gh = dL/dH (complex), H the cascade value
+template <typename T>
+__device__ __forceinline__ void sos_grad(const OpK& op, const T* p, long stride, const Ctx<T>& ctx, cx<T> H,
+                                         cx<T> gh, const Acc<T>& acc, int row, int e0) {
+  const int K = op.K;
+  const T* p0 = p;
+  for (int s = 0; s < K; ++s, p += stride) {
+    T c[8];
+    load8<T>(p, c);
+    cx<T> Bv, Av;
+    section_eval<T>(c, ctx, Bv, Av);
+    cx<T> qb;
+    if (czero(Bv)) {
+      // dH/dB_s = prod_{t != s} B_t / prod A  (H itself is 0 at this bin)
+      bool gd;
+      cx<T> den;
+      (void)sos_eval<T>(p0, K, stride, ctx, gd, den);
+      qb = cmul(sos_num_without<T>(p0, K, stride, ctx, s), crcp(den));
+    } else {
+      qb = cmul(H, crcp(Bv));
+    }
+    cx<T> qa = cmul(H, crcp(Av));
+    qa.x = -qa.x;
+    qa.y = -qa.y;
+    cx<T> rb = cmulc(gh, qb), ra = cmulc(gh, qa);
+    int e = e0 + s * op.row_len / K;  // row_len = K * per-section stride of this row
+    acc.add(op, row, e + (ctx.plus ? 0 : 3), rb.x);
+    acc.add(op, row, e + 1, rb.x * ctx.u1.x + rb.y * ctx.u1.y);
+    acc.add(op, row, e + 2, rb.x * ctx.u2.x + rb.y * ctx.u2.y);
+    acc.add(op, row, e + (ctx.plus ? 4 : 7), ra.x);
+    acc.add(op, row, e + 5, ra.x * ctx.u1.x + ra.y * ctx.u1.y);
+    acc.add(op, row, e + 6, ra.x * ctx.u2.x + ra.y * ctx.u2.y);
+  }
+}
+
+// One entry H[m][n] of a dense op's response (single switch; called from runtime loops over n).
+template <typename T>
+__device__ __forceinline__ cx<T> op_entry(const OpK& op, const Ctx<T>& ctx, int m, int n, bool& guard) {
+  guard = false;
+  switch (op.kind) {
+    case FSWEEP_OP_GAIN:
+      return mk<T>(__ldg(reinterpret_cast<const T*>(op.coef) + m * op.n_in + n), T(0));
+    case FSWEEP_OP_DELAY:
+      return delay_eval<T>(__ldg(reinterpret_cast<const double*>(op.coef) + m * op.n_in + n), op.flags, ctx);
+    case FSWEEP_OP_SOS: {
+      cx<T> den;
+      return sos_eval<T>(reinterpret_cast<const T*>(op.coef) + ((size_t)n * op.n_out + m) * 8, op.K,
+                         (long)op.n_in * op.n_out * 8, ctx, guard, den);
+    }
+    case FSWEEP_OP_TABLE: {
+      const T* t = reinterpret_cast<const T*>(op.coef) + 2 * (((size_t)ctx.k * op.n_out + m) * op.n_in + n);
+      return mk<T>(__ldg(t), __ldg(t + 1));
+    }
+    default:
+      return mk<T>(0, 0);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ cx<T> op_diag(const OpK& op, const Ctx<T>& ctx, int m, bool& guard) {
+  guard = false;
+  if (m >= op.n_out) return mk<T>(0, 0);
+  switch (op.kind) {
+    case FSWEEP_OP_PGAIN:
+      return mk<T>(__ldg(reinterpret_cast<const T*>(op.coef) + m), T(0));
+    case FSWEEP_OP_PDELAY:
+      return delay_eval<T>(__ldg(reinterpret_cast<const double*>(op.coef) + m), op.flags, ctx);
+    case FSWEEP_OP_PSOS: {
+      cx<T> den;
+      return sos_eval<T>(reinterpret_cast<const T*>(op.coef) + (size_t)m * 8, op.K, (long)op.n_out * 8, ctx, guard,
+                         den);
+    }
+    case FSWEEP_OP_PTABLE: {
+      const T* t = reinterpret_cast<const T*>(op.coef) + 2 * ((size_t)ctx.k * op.n_out + m);
+      return mk<T>(__ldg(t), __ldg(t + 1));
+    }
+    default:
+      return mk<T>(0, 0);
+  }
+}
+
+// Row `lane` of a dense response, staged in this thread's private shared-memory column
+// hrow[n*BLOCK + tid]; returns the bit mask of guarded (|prod A| == 0) entries.
+template <typename T>
+__device__ __forceinline__ unsigned stage_row(const OpK& op, const Ctx<T>& ctx, int lane, cx<T>* hrow, int tid) {
+  unsigned gmask = 0;
+  const bool live = lane < op.n_out;
+  for (int n = 0; n < op.n_in; ++n) {
+    bool gd = false;
+    cx<T> h = mk<T>(0, 0);
+    if (live) h = op_entry<T>(op, ctx, lane, n, gd);
+    if (gd) gmask |= 1u << n;
+    hrow[(size_t)n * BLOCK + tid] = h;
+  }
+  return gmask;
+}
+
+// S <- H S for NC columns (row-distributed).  `ident`: S is the identity, so H S = H (dense only).
+template <typename T, int G, int NC>
+__device__ __forceinline__ void apply_op(const OpK& op, const Ctx<T>& ctx, int lane, cx<T> (&S)[NC], int ncols,
+                                         bool ident, cx<T>* hrow, int tid) {
+  if (is_dense(op.kind)) {
+    (void)stage_row<T>(op, ctx, lane, hrow, tid);
+    if (ident) {
+      static_for<0, NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        S[c] = (c < op.n_in) ? hrow[(size_t)c * BLOCK + tid] : mk<T>(0, 0);
+      });
+      return;
+    }
+    // n outer (runtime), c inner (static register indices): columns >= ncols are dead weight only in
+    // the NC == G matrix build, where ncols == loop width
+    cx<T> acc[NC];
+    static_for<0, NC>([&](auto cc) { acc[decltype(cc)::value] = mk<T>(0, 0); });
+    for (int n = 0; n < op.n_in; ++n) {
+      const cx<T> h = hrow[(size_t)n * BLOCK + tid];
+      static_for<0, NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        cx<T> v = shfl<G>(S[c], n);
+        cfma(acc[c], h, v);
+      });
+    }
+    static_for<0, NC>([&](auto cc) { S[decltype(cc)::value] = acc[decltype(cc)::value]; });
+  } else {
+    bool gd;
+    cx<T> h = op_diag<T>(op, ctx, lane, gd);
+    static_for<0, NC>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      if (c < ncols) S[c] = cmul(h, S[c]);
+    });
+  }
+}
+
+// Back-propagate through one op: accumulate its coefficient gradient from (Sin, g) and replace g by
+// H^H g (if need_gin).  Sin = the op's forward input, g = dL/d(output), both row-distributed.
+template <typename T, int G, int NC>
+__device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, int lane, const cx<T> (&Sin)[NC],
+                                            cx<T> (&g)[NC], bool need_gin, const Acc<T>& acc, bool first_chunk,
+                                            cx<T>* hrow, int tid) {
+  const bool want = op.acc_mode != ACC_NONE;
+  if (is_dense(op.kind)) {
+    const unsigned gmask = stage_row<T>(op, ctx, lane, hrow, tid);
+    if (want) {
+      for (int n = 0; n < op.n_in; ++n) {
+        cx<T> gh = mk<T>(0, 0);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          cx<T> v = shfl<G>(Sin[c], n);
+          cfmac(gh, g[c], v);
+        }
+        if (lane < op.n_out) {
+          const cx<T> h = hrow[(size_t)n * BLOCK + tid];
+          switch (op.kind) {
+            case FSWEEP_OP_GAIN:
+              acc.add(op, lane, n, gh.x);
+              break;
+            case FSWEEP_OP_DELAY:
+              if (!(op.flags & FSWEEP_F_ISINT)) {
+                // dH/dd = (ln g - j w) H
+                cx<T> t = cmul(mk<T>((T)ctx.lng, -ctx.omega), h);
+                acc.add(op, lane, n, gh.x * t.x + gh.y * t.y);
+              }
+              break;
+            case FSWEEP_OP_SOS:
+              if (!((gmask >> n) & 1u))
+                sos_grad<T>(op, reinterpret_cast<const T*>(op.coef) + ((size_t)n * op.n_out + lane) * 8,
+                            (long)op.n_in * op.n_out * 8, ctx, h, gh, acc, lane, n * 8);
+              break;
+            case FSWEEP_OP_TABLE:
+              if (acc.valid && op.gtab) {
+                T* t = reinterpret_cast<T*>(op.gtab) + 2 * (((size_t)ctx.k * op.n_out + lane) * op.n_in + n);
+                if (first_chunk) {
+                  t[0] = gh.x;
+                  t[1] = gh.y;
+                } else {
+                  t[0] += gh.x;
+                  t[1] += gh.y;
+                }
+              }
+              break;
+            default:
+              break;
+          }
+        }
+      }
+    }
+    if (need_gin) {
+      cx<T> gin[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) gin[c] = mk<T>(0, 0);
+      for (int n = 0; n < op.n_in; ++n) {
+        const cx<T> h = hrow[(size_t)n * BLOCK + tid];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          cx<T> t = mk<T>(0, 0);
+          cfmacj(t, h, g[c]);  // conj(h) * g
+          t = group_sum<G>(t);
+          if (lane == n) gin[c] = t;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) g[c] = gin[c];
+    }
+  } else {
+    bool gd;
+    cx<T> h = op_diag<T>(op, ctx, lane, gd);
+    if (want && lane < op.n_out) {
+      cx<T> gh = mk<T>(0, 0);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) cfmac(gh, g[c], Sin[c]);
+      switch (op.kind) {
+        case FSWEEP_OP_PGAIN:
+          acc.add(op, lane, 0, gh.x);
+          break;
+        case FSWEEP_OP_PDELAY:
+          if (!(op.flags & FSWEEP_F_ISINT)) {
+            cx<T> t = cmul(mk<T>((T)ctx.lng, -ctx.omega), h);
+            acc.add(op, lane, 0, gh.x * t.x + gh.y * t.y);
+          }
+          break;
+        case FSWEEP_OP_PSOS:
+          if (!gd)
+            sos_grad<T>(op, reinterpret_cast<const T*>(op.coef) + (size_t)lane * 8, (long)op.n_out * 8, ctx, h, gh,
+                        acc, lane, 0);
+          break;
+        case FSWEEP_OP_PTABLE:
+          if (acc.valid && op.gtab) {
+            T* t = reinterpret_cast<T*>(op.gtab) + 2 * ((size_t)ctx.k * op.n_out + lane);
+            if (first_chunk) {
+              t[0] = gh.x;
+              t[1] = gh.y;
+            } else {
+              t[0] += gh.x;
+              t[1] += gh.y;
+            }
+          }
+          break;
+        default:
+          break;
+      }
+    }
+    if (need_gin) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        cx<T> t = mk<T>(0, 0);
+        cfmacj(t, h, g[c]);
+        g[c] = t;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- LU
+constexpr int STEP_PAD = 1 << 20;  // "mystep" of padding lanes (rows >= N)
+
+template <int G>
+__device__ __forceinline__ int lane_with_step(int mystep, int k) {
+  unsigned m = __ballot_sync(FULL, mystep == k);
+  if constexpr (G < 32) {
+    int base = (threadIdx.x & 31) & ~(G - 1);
+    m = (m >> base) & ((1u << G) - 1u);
+  }
+  return __ffs(m) - 1;
+}
+
+template <typename T, int G>
+struct LU {
+  cx<T> a[G];   // row `lane` of A, overwritten by L multipliers (cols < mystep) and U (cols >= mystep)
+  cx<T> dinv;   // 1 / U[mystep][mystep]
+  int mystep;   // elimination step at which this row was the pivot row
+
+  // Gaussian elimination with implicit partial pivoting; N = live rows/cols.
+  __device__ __forceinline__ void factor(int lane, int N) {
+    mystep = (lane < N) ? -1 : STEP_PAD;
+    dinv = mk<T>(1, 0);
+    static_for<0, G>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      if (k < N) {
+        T mag = (mystep < 0) ? (a[k].x * a[k].x + a[k].y * a[k].y) : T(-1);
+        int who = lane;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+          T om = __shfl_xor_sync(FULL, mag, o, G);
+          int ow = __shfl_xor_sync(FULL, who, o, G);
+          if (om > mag || (om == mag && ow < who)) {
+            mag = om;
+            who = ow;
+          }
+        }
+        cx<T> pk = shfl<G>(a[k], who);
+        cx<T> inv = crcp(pk);
+        const bool act = (mystep < 0) && (lane != who);
+        cx<T> l = cmul(a[k], inv);
+        if (lane == who) {
+          mystep = k;
+          dinv = inv;
+        }
+        static_for<k + 1, G>([&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          if (j < N) {
+            cx<T> pj = shfl<G>(a[j], who);
+            if (act) cfnma(a[j], l, pj);
+          }
+        });
+        if (act) a[k] = l;
+      }
+    });
+  }
+
+  // A x = b for NC right-hand sides; b in natural row order on entry, x in natural order on exit.
+  template <int NC>
+  __device__ __forceinline__ void solve(int lane, int N, cx<T> (&b)[NC]) const {
+    static_for<0, G>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      if (k < N) {
+        int p = lane_with_step<G>(mystep, k);
+        static_for<0, NC>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          cx<T> bk = shfl<G>(b[c], p);
+          if (mystep > k && mystep != STEP_PAD) cfnma(b[c], a[k], bk);
+        });
+      }
+    });
+    cx<T> x[NC];
+    static_for<0, NC>([&](auto cc) { x[decltype(cc)::value] = mk<T>(0, 0); });
+    static_rfor<0, G>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      if (k < N) {
+        int p = lane_with_step<G>(mystep, k);
+        static_for<0, NC>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          cx<T> xk = shfl<G>(cmul(b[c], dinv), p);
+          if (mystep < k) cfnma(b[c], a[k], xk);
+          if (lane == k) x[c] = xk;
+        });
+      }
+    });
+    static_for<0, NC>([&](auto cc) { b[decltype(cc)::value] = x[decltype(cc)::value]; });
+  }
+
+  // A^H lam = g for NC right-hand sides (natural order in and out), reusing the same factors:
+  // A = P^T L U  =>  U^H w = g ,  L^H v = w ,  lam = P^T v.
+  template <int NC>
+  __device__ __forceinline__ void solve_adj(int lane, int N, cx<T> (&g)[NC]) const {
+    const bool live = mystep != STEP_PAD;
+    cx<T> w[NC];
+    static_for<0, NC>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      cx<T> gp = shfl<G>(g[c], live ? mystep : lane);
+      w[c] = live ? gp : mk<T>(0, 0);
+    });
+    // forward substitution with U^H (lower triangular): w_i = (g_i - sum_{j<i} conj(U[j][i]) w_j) / conj(U[i][i])
+    static_for<0, G>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      if (i < N) {
+        static_for<0, NC>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          cx<T> t = mk<T>(0, 0);
+          if (live && mystep < i) cfmacj(t, a[i], w[c]);
+          t = group_sum<G>(t);
+          if (mystep == i) {
+            cx<T> d = mk<T>(w[c].x - t.x, w[c].y - t.y);
+            w[c] = cmulc(d, dinv);  // d * conj(1/U_ii)
+          }
+        });
+      }
+    });
+    // back substitution with L^H (unit upper triangular): v_j = w_j - sum_{i>j} conj(L[i][j]) v_i
+    static_rfor<0, G>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      if (j < N) {
+        static_for<0, NC>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          cx<T> t = mk<T>(0, 0);
+          if (live && mystep > j) cfmacj(t, a[j], w[c]);
+          t = group_sum<G>(t);
+          if (mystep == j) {
+            w[c].x -= t.x;
+            w[c].y -= t.y;
+          }
+        });
+      }
+    });
+    static_for<0, NC>([&](auto cc) { g[decltype(cc)::value] = w[decltype(cc)::value]; });
+  }
+};
+
+// Build A = I - F*Fb for this bin (row-distributed) and factor it.
+template <typename T, int G>
+__device__ __forceinline__ void build_loop(const ProgK& P, const Ctx<T>& ctx, int lane, LU<T, G>& lu, cx<T>* hrow,
+                                           int tid) {
+  const int N = P.rec_n;
+  static_for<0, G>([&](auto cc) {
+    constexpr int c = decltype(cc)::value;
+    lu.a[c] = mk<T>(c == lane ? T(1) : T(0), T(0));
+  });
+  for (int i = 0; i < P.n_msteps; ++i) {
+    const Step st = P.msteps[i];
+    apply_op<T, G, G>(P.ops[st.op], ctx, lane, lu.a, N, (st.flags & ST_IDENT) != 0, hrow, tid);
+  }
+  static_for<0, G>([&](auto cc) {
+    constexpr int c = decltype(cc)::value;
+    lu.a[c].x = (c == lane ? T(1) : T(0)) - lu.a[c].x;
+    lu.a[c].y = -lu.a[c].y;
+  });
+  lu.factor(lane, N);
+}
+
+// ------------------------------------------------------------------------------- kernel arguments
+struct SweepArgs {
+  const void* x;
+  long long xbs;
+  void* y;  // forward: output; backward: unused
+  long long ybs;
+  const void* gy;  // backward
+  long long gybs;
+  void* gx;  // backward, may be null
+  long long gxbs;
+  int batch, cols;
+  long long bin_begin, n_bins;
+  int epilogue;
+  void* partial;  // backward: [grid][acc_per_lane * G]
+  void* gacc;     // backward: [acc_total] (ACC_GLOBAL ops), zeroed by the host wrapper
+};
+
+template <typename T, int G, int CC>
+__device__ __forceinline__ void load_cols(const cx<T>* x, long long xbs, long long bl, int nch, int cols, int q0,
+                                          int ncols_total, int lane, cx<T> (&S)[CC]) {
+#pragma unroll
+  for (int c = 0; c < CC; ++c) {
+    int q = q0 + c;
+    S[c] = mk<T>(0, 0);
+    if (q < ncols_total && lane < nch) {
+      int b = q / cols, cc = q - b * cols;
+      const T* p = reinterpret_cast<const T*>(x + (size_t)b * xbs + ((size_t)bl * nch + lane) * cols + cc);
+      S[c] = mk<T>(__ldg(p), __ldg(p + 1));
+    }
+  }
+}
+
+// shared memory: [hrow: G*BLOCK cx] [save: n_slots*CC*BLOCK cx] [sacc: acc_per_lane*BLOCK T]
+// ------------------------------------------------------------------------------------ forward
+template <typename T, int G, int CC>
+__global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant__ ProgK P, const SweepArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* hrow = reinterpret_cast<cx<T>*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & (G - 1);
+  const long long groups_total = (long long)gridDim.x * (BLOCK / G);
+  const long long gg = (long long)blockIdx.x * (BLOCK / G) + tid / G;
+  const long long n_iter = (A.n_bins + groups_total - 1) / groups_total;
+  const int ncols_total = A.batch * A.cols;
+  const cx<T>* x = reinterpret_cast<const cx<T>*>(A.x);
+
+  for (long long it = 0; it < n_iter; ++it) {
+    long long bl = it * groups_total + gg;
+    const bool valid = bl < A.n_bins;
+    if (!valid) bl = A.n_bins - 1;
+    const Ctx<T> ctx = make_ctx<T>(P, A.bin_begin + bl);
+    LU<T, G> lu;
+    if (P.rec_n > 0) build_loop<T, G>(P, ctx, lane, lu, hrow, tid);
+
+    for (int q0 = 0; q0 < ncols_total; q0 += CC) {
+      cx<T> S[CC];
+      load_cols<T, G, CC>(x, A.xbs, bl, P.in_ch, A.cols, q0, ncols_total, lane, S);
+      for (int i = 0; i < P.n_fsteps; ++i) {
+        const Step st = P.fsteps[i];
+        apply_op<T, G, CC>(P.ops[st.op], ctx, lane, S, CC, false, hrow, tid);
+        if (st.flags & ST_SOLVE) lu.template solve<CC>(lane, P.rec_n, S);
+      }
+      if (valid && lane < P.out_ch) {
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          int q = q0 + c;
+          if (q < ncols_total) {
+            int b = q / A.cols, cc = q - b * A.cols;
+            size_t off = (size_t)b * A.ybs + ((size_t)bl * P.out_ch + lane) * A.cols + cc;
+            if (A.epilogue == FSWEEP_EPI_ABS) {
+              reinterpret_cast<T*>(A.y)[off] = abs_t(S[c].x, S[c].y);
+            } else {
+              T* p = reinterpret_cast<T*>(A.y) + 2 * off;
+              p[0] = S[c].x;
+              p[1] = S[c].y;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ backward
+template <typename T, int G, int CC>
+__global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant__ ProgK P, const SweepArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* hrow = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* save = hrow + (size_t)G * BLOCK;                                 // [n_slots][CC][BLOCK]
+  T* sacc = reinterpret_cast<T*>(save + (size_t)P.n_slots * CC * BLOCK);  // [acc_per_lane][BLOCK]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & (G - 1);
+  const long long groups_total = (long long)gridDim.x * (BLOCK / G);
+  const long long gg = (long long)blockIdx.x * (BLOCK / G) + tid / G;
+  const long long n_iter = (A.n_bins + groups_total - 1) / groups_total;
+  const int ncols_total = A.batch * A.cols;
+  const cx<T>* x = reinterpret_cast<const cx<T>*>(A.x);
+  const int slot_x = P.n_slots - 1;
+
+  for (int i = 0; i < P.acc_per_lane; ++i) sacc[(size_t)i * BLOCK + tid] = T(0);
+
+  Acc<T> acc;
+  acc.sacc = sacc;
+  acc.gacc = reinterpret_cast<T*>(A.gacc);
+  acc.tid = tid;
+
+  auto put = [&](int slot, const cx<T>(&S)[CC]) {
+#pragma unroll
+    for (int c = 0; c < CC; ++c) save[((size_t)slot * CC + c) * BLOCK + tid] = S[c];
+  };
+  auto get = [&](int slot, cx<T>(&S)[CC]) {
+#pragma unroll
+    for (int c = 0; c < CC; ++c) S[c] = save[((size_t)slot * CC + c) * BLOCK + tid];
+  };
+
+  for (long long it = 0; it < n_iter; ++it) {
+    long long bl = it * groups_total + gg;
+    const bool valid = bl < A.n_bins;
+    if (!valid) bl = A.n_bins - 1;
+    acc.valid = valid;
+    const Ctx<T> ctx = make_ctx<T>(P, A.bin_begin + bl);
+    LU<T, G> lu;
+    if (P.rec_n > 0) build_loop<T, G>(P, ctx, lane, lu, hrow, tid);
+
+    for (int q0 = 0; q0 < ncols_total; q0 += CC) {
+      const bool first_chunk = q0 == 0;
+      cx<T> S[CC];
+      load_cols<T, G, CC>(x, A.xbs, bl, P.in_ch, A.cols, q0, ncols_total, lane, S);
+      int slot = 0;
+      // ---- forward recompute, parking every op input
+      for (int i = 0; i < P.n_bsteps; ++i) {
+        const Step st = P.bsteps[i];
+        if (st.flags & ST_SAVE_X) put(slot_x, S);
+        if (st.flags & ST_SAVE) put(slot++, S);
+        apply_op<T, G, CC>(P.ops[st.op], ctx, lane, S, CC, false, hrow, tid);
+        if (st.flags & ST_SOLVE) lu.template solve<CC>(lane, P.rec_n, S);
+        if (st.flags & ST_ADD_X) {
+          cx<T> X[CC];
+          get(slot_x, X);
+#pragma unroll
+          for (int c = 0; c < CC; ++c) {
+            S[c].x += X[c].x;
+            S[c].y += X[c].y;
+          }
+        }
+      }
+      // ---- output gradient
+      cx<T> g[CC];
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        int q = q0 + c;
+        g[c] = mk<T>(0, 0);
+        if (q < ncols_total && lane < P.out_ch) {
+          int b = q / A.cols, cc = q - b * A.cols;
+          size_t off = (size_t)b * A.gybs + ((size_t)bl * P.out_ch + lane) * A.cols + cc;
+          if (A.epilogue == FSWEEP_EPI_ABS) {
+            T ga = __ldg(reinterpret_cast<const T*>(A.gy) + off);
+            T mag = abs_t(S[c].x, S[c].y);
+            if (mag > T(0)) g[c] = mk<T>(ga * S[c].x / mag, ga * S[c].y / mag);
+          } else {
+            const T* p = reinterpret_cast<const T*>(A.gy) + 2 * off;
+            g[c] = mk<T>(__ldg(p), __ldg(p + 1));
+          }
+        }
+      }
+      // ---- reverse sweep
+      for (int i = 0; i < P.n_rsteps; ++i) {
+        const Step st = P.rsteps[i];
+        if (st.flags & RS_ADJ) lu.template solve_adj<CC>(lane, P.rec_n, g);
+        cx<T> Sin[CC];
+        get(--slot, Sin);
+        backprop_op<T, G, CC>(P.ops[st.op], ctx, lane, Sin, g, (st.flags & RS_NEED_GIN) != 0, acc, first_chunk, hrow,
+                              tid);
+        if (st.flags & RS_SAVE_G) put(slot_x, g);
+        if (st.flags & RS_RESTORE_G) get(slot_x, g);
+      }
+      if (A.gx != nullptr && valid && lane < P.in_ch) {
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          int q = q0 + c;
+          if (q < ncols_total) {
+            int b = q / A.cols, cc = q - b * A.cols;
+            T* p = reinterpret_cast<T*>(A.gx) + 2 * ((size_t)b * A.gxbs + ((size_t)bl * P.in_ch + lane) * A.cols + cc);
+            p[0] = g[c].x;
+            p[1] = g[c].y;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- block reduction of the thread-private accumulator columns: partial[block][i][row]
+  __syncthreads();
+  T* partial = reinterpret_cast<T*>(A.partial) + (size_t)blockIdx.x * P.acc_per_lane * G;
+  for (int e = tid; e < P.acc_per_lane * G; e += BLOCK) {
+    int i = e / G, row = e - i * G;
+    T s = T(0);
+    for (int j = 0; j < BLOCK / G; ++j) s += sacc[(size_t)i * BLOCK + j * G + row];
+    partial[e] = s;
+  }
+}
+
+// Sum the per-block partials (float64) and scatter into the caller's gradient buffers.
+struct FinalizeOp {
+  int kind, n_out, n_in, K;
+  int acc_mode, row_off, row_len, acc_off;
+  void* grad;  // caller buffer or null
+};
+struct FinalizeArgs {
+  int n_ops, G, acc_per_lane, n_blocks;
+  const void* partial;
+  const void* gacc;
+  FinalizeOp ops[MAX_OPS];
+};
+
+template <typename T>
+__global__ void fsweep_finalize_kernel(const __grid_constant__ FinalizeArgs F) {
+  const int opi = blockIdx.y;
+  const FinalizeOp& op = F.ops[opi];
+  if (op.grad == nullptr || (op.acc_mode != ACC_SMEM && op.acc_mode != ACC_GLOBAL)) return;
+  const bool diag = !(op.kind == FSWEEP_OP_GAIN || op.kind == FSWEEP_OP_SOS || op.kind == FSWEEP_OP_DELAY);
+  const int rows = op.n_out;
+  const int total = rows * op.row_len;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int row = e / op.row_len, i = e - row * op.row_len;
+    double s = 0.0;
+    if (op.acc_mode == ACC_SMEM) {
+      const T* p = reinterpret_cast<const T*>(F.partial) + (size_t)(op.row_off + i) * F.G + row;
+      for (int b = 0; b < F.n_blocks; ++b) s += (double)p[(size_t)b * F.acc_per_lane * F.G];
+    } else {
+      s = (double)reinterpret_cast<const T*>(F.gacc)[op.acc_off + e];
+    }
+    // map (row, i) -> index in the caller's layout
+    size_t o;
+    if (op.kind == FSWEEP_OP_SOS) {
+      // i = (s * n_in + n) * 8 + slot  ->  ((s * n_in + n) * n_out + row) * 8 + slot
+      int slot = i & 7, sn = i >> 3;
+      o = ((size_t)sn * op.n_out + row) * 8 + slot;
+    } else if (op.kind == FSWEEP_OP_PSOS) {
+      int slot = i & 7, sidx = i >> 3;
+      o = ((size_t)sidx * op.n_out + row) * 8 + slot;
+    } else if (diag) {
+      o = row;
+    } else {
+      o = (size_t)row * op.n_in + i;
+    }
+    if (op.kind == FSWEEP_OP_DELAY || op.kind == FSWEEP_OP_PDELAY)
+      reinterpret_cast<double*>(op.grad)[o] = s;
+    else
+      reinterpret_cast<T*>(op.grad)[o] = (T)s;
+  }
+}
+
+// launch thunks, one translation unit per G (fsweep_inst.cu compiled with -DFSWEEP_G=...)
+struct LaunchCfg {
+  int grid;
+  size_t smem;
+  cudaStream_t stream;
+};
+template <int G>
+cudaError_t launch_fwd(int dtype, int cc, const LaunchCfg& cfg, const ProgK& P, const SweepArgs& A);
+template <int G>
+cudaError_t launch_bwd(int dtype, int cc, const LaunchCfg& cfg, const ProgK& P, const SweepArgs& A);
+template <int G>
+cudaError_t occupancy(int dtype, int cc, bool bwd, size_t smem, int* blocks_per_sm);
+
+}  // namespace fsweep

@@ -1,0 +1,208 @@
+"""Trainer with the interface of flamo.optimize.trainer.Trainer (reference trainer.py:9-313).
+
+`train_step` is the unit BASELINE.json's metric is quoted on: zero_grad -> net(inputs) -> weighted
+criteria -> backward -> Adam step.  On a CUDA device the whole step can be captured once into a CUDA
+graph (`graph=True`, the default when the device is CUDA): the step then costs one graph launch, one
+host<->device copy of the inputs if they live on the host, and ONE device->host read of the
+per-criterion losses (the reference pays one sync per criterion, trainer.py:184-192).  The arithmetic
+is identical in both modes.
+"""
+from __future__ import annotations
+
+import os
+import time
+import warnings
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+try:
+    from tqdm import trange
+except Exception:  # pragma: no cover
+    trange = range
+
+
+class Trainer:
+    def __init__(self, net: nn.Module, max_epochs: int = 10, lr: float = 1e-3, patience: int = 5,
+                 patience_delta: float = 0.01, step_size: int = 50, step_factor: float = 0.1, log: bool = True,
+                 train_dir: str = None, device: str = "cpu", graph: Optional[bool] = None):
+        self.device = device
+        self.log = log
+        self.net = net.to(device)
+        self.max_epochs, self.lr = max_epochs, lr
+        self.patience, self.patience_delta = patience, patience_delta
+        self.min_val_loss = float("inf")
+        on_cuda = torch.device(device).type == "cuda"
+        self.use_graph = on_cuda if graph is None else (graph and on_cuda)
+        params = list(self.net.parameters())
+        if self.use_graph:
+            # capturable Adam keeps `step` and `lr` on the device so a captured step can be replayed
+            self.optimizer = torch.optim.Adam(params, lr=torch.tensor(float(lr), device=device), capturable=True)
+        else:
+            self.optimizer = torch.optim.Adam(params, lr=self.lr)
+        self.n_loss = 0
+        if self.log:
+            assert os.path.isdir(train_dir), "The directory specified in train_dir does not exist."
+        self.train_dir = train_dir
+        self.criterion, self.alpha, self.requires_model = [], [], []
+        self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=step_size, gamma=step_factor)
+        self.train_loss_log, self.valid_loss_log = {}, {}
+        self._graphs = {}
+        self._warm = {}
+
+    def register_criterion(self, criterion: nn.Module, alpha: int = 1, requires_model: bool = False):
+        self.criterion.append(criterion.to(self.device))
+        self.alpha.append(alpha)
+        self.requires_model.append(requires_model)
+        self.n_loss += 1
+        self._graphs.clear()
+
+    # -- loops -----------------------------------------------------------------------------------
+    def train(self, train_dataset, valid_dataset):
+        self.train_loss, self.valid_loss = [], []
+        self.train_loss_log, self.valid_loss_log = {}, {}
+        for c in self.criterion:
+            self.train_loss_log[c.__class__.__name__] = []
+            self.valid_loss_log[c.__class__.__name__] = []
+        st = time.time()
+        for epoch in trange(self.max_epochs, desc="Training"):
+            st_epoch = time.time()
+            total = 0
+            for data in train_dataset:
+                total += self.train_step(data)
+            self.scheduler.step()
+            self.train_loss.append(total / len(train_dataset))
+            total = 0
+            for data in valid_dataset:
+                total += self.valid_step(data)
+            self.valid_loss.append(total / len(valid_dataset))
+            self.print_results(epoch, time.time() - st_epoch)
+            if self.log:
+                self.save_model(epoch)
+            if self.early_stop():
+                print("Early stopping at epoch: {}".format(epoch))
+                break
+        print("Training time: {:.3f}s".format(time.time() - st))
+
+    def move_to_device(self, data):
+        if isinstance(data, list):
+            return [x.to(self.device) for x in data]
+        return data.to(self.device)
+
+    def _log(self, log, values):
+        for c, v in zip(self.criterion, values):
+            log.setdefault(c.__class__.__name__, []).append(v)
+
+    def _losses(self, inputs, targets):
+        """Forward + criteria: returns (total, [per-criterion tensors])."""
+        est = self.net(inputs)
+        parts, total = [], 0
+        for alpha, crit, needs_model in zip(self.alpha, self.criterion, self.requires_model):
+            t = crit(est, targets, self.net) if needs_model else crit(est, targets)
+            parts.append(t)
+            total = total + alpha * t
+        return total, parts
+
+    # -- eager step (any device) -----------------------------------------------------------------
+    def _eager_train_step(self, inputs, targets):
+        self.optimizer.zero_grad()
+        loss, parts = self._losses(inputs, targets)
+        loss.backward()
+        self.optimizer.step()
+        vals = torch.stack([p.detach().reshape(()) for p in parts] + [loss.detach().reshape(())]).tolist()
+        self._log(self.train_loss_log, vals[:-1])
+        return vals[-1]
+
+    # -- captured step (CUDA) --------------------------------------------------------------------
+    def _graph_for(self, inputs, targets):
+        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), targets.dtype)
+        g = self._graphs.get(key)
+        if g is not None:
+            return g
+        n_warm = self._warm.get(key, 0)
+        if n_warm < 3:  # eager warm-up: lazy state (Adam moments, plans, cuFFT plans, caches) must exist
+            self._warm[key] = n_warm + 1
+            return None
+        static_in, static_tg = inputs.clone(), targets.clone()
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        try:
+            with torch.cuda.graph(graph):
+                loss, parts = self._losses(static_in, static_tg)
+                loss.backward()
+                self.optimizer.step()
+                out = torch.stack([p.detach().reshape(()) for p in parts] + [loss.detach().reshape(())])
+        except Exception as e:  # keep training eagerly (still on the CUDA sweep) if capture is impossible
+            warnings.warn(f"CUDA-graph capture of the training step failed ({e}); continuing without graph.")
+            self.use_graph = False
+            torch.cuda.synchronize()
+            return None
+        g = (graph, static_in, static_tg, out)
+        self._graphs[key] = g
+        return g
+
+    def train_step(self, data):
+        inputs, targets = data
+        inputs = self.move_to_device(inputs)
+        targets = self.move_to_device(targets)
+        if self.use_graph:
+            g = self._graph_for(inputs, targets)
+            if g is not None:
+                graph, static_in, static_tg, out = g
+                static_in.copy_(inputs, non_blocking=True)
+                static_tg.copy_(targets, non_blocking=True)
+                graph.replay()
+                vals = out.tolist()  # the step's single device->host read
+                self._log(self.train_loss_log, vals[:-1])
+                return vals[-1]
+        return self._eager_train_step(inputs, targets)
+
+    @torch.no_grad()
+    def valid_step(self, data):
+        inputs, targets = data
+        inputs = self.move_to_device(inputs)
+        targets = self.move_to_device(targets)
+        loss, parts = self._losses(inputs, targets)
+        vals = torch.stack([p.reshape(()) for p in parts] + [loss.reshape(())]).tolist()
+        self._log(self.valid_loss_log, vals[:-1])
+        return vals[-1]
+
+    # -- bookkeeping -----------------------------------------------------------------------------
+    def print_results(self, e: int, e_time: float):
+        print(get_str_results(epoch=e, train_loss=self.train_loss, valid_loss=self.valid_loss, time=e_time))
+
+    def get_train_dir(self):
+        if self.train_dir is not None:
+            os.makedirs(self.train_dir, exist_ok=True)
+        else:
+            self.train_dir = os.path.join("output", time.strftime("%Y%m%d-%H%M%S"))
+            os.makedirs(self.train_dir)
+
+    def save_model(self, e: int):
+        d = os.path.join(self.train_dir, "checkpoints")
+        os.makedirs(d, exist_ok=True)
+        torch.save(self.net.state_dict(), os.path.join(d, "model_e" + str(e) + ".pt"))
+
+    def early_stop(self):
+        if self.valid_loss[-1] < (self.min_val_loss - self.patience_delta):
+            self.min_val_loss = self.valid_loss[-1]
+            self.counter = 0
+        elif (self.min_val_loss - self.patience_delta) < self.valid_loss[-1] < (self.min_val_loss + self.patience_delta):
+            self.counter += 1
+            if self.counter >= self.patience:
+                return True
+        return False
+
+
+def get_str_results(epoch=None, train_loss=None, valid_loss=None, time=None):
+    s = ""
+    if epoch is not None:
+        s += "epoch: {:3d} ".format(epoch)
+    if train_loss is not None:
+        s += "- train_loss: {:6.4f} ".format(train_loss[-1])
+    if valid_loss is not None:
+        s += "- test_loss: {:6.4f} ".format(valid_loss[-1])
+    if time is not None:
+        s += "- time: {:6.4f} s".format(time)
+    return s

@@ -1,0 +1,702 @@
+"""flamo.processor.dsp — same classes, constructor signatures, parameter shapes and attributes as the
+reference (gdalsanto/flamo, flamo/processor/dsp.py), with every per-bin evaluation lowered to the
+CUDA sweep (flamo_b200.sweep -> libfsweep.so).
+
+What stays PyTorch: the O(#params) maps from raw `param` to coefficients (`map`, RBJ / SVF / GEQ
+designers, softplus of delays, matrix exponential).  They are evaluated in float64 (free at this
+size, removes the reference's float32 rounding of delays and section taps — SURVEY.md finding 4) and
+handed to the kernel in its compute dtype.
+
+`freq_response(param)` / `get_poly_coeff(...)` remain available as plain-PyTorch closed forms for
+callers that want the response tensor itself (plots, probes, subclasses); they are not used by
+`forward`.  A subclass or instance that overrides them is lowered as a TABLE op fed by its own
+`freq_response(param)`.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import sweep
+from .._lib import OP_DELAY, OP_GAIN, OP_PDELAY, OP_PGAIN, OP_PSOS, OP_PTABLE, OP_SOS, OP_TABLE
+from ..auxiliary.eq import eq_freqs, geq
+from ..functional import (HadamardMatrix, RotationMatrix, bandpass_filter, highpass_filter, lowpass_filter,
+                          skew_matrix)
+from ..utils import to_complex
+
+# ======================================================================================= transforms
+
+
+class Transform(nn.Module):
+    """Callable wrapper used as Shell input / output layer (reference dsp.py:27-66)."""
+
+    def __init__(self, transform: callable = lambda x: x, device: Optional[str] = None,
+                 dtype: torch.dtype = torch.float32):
+        super().__init__()
+        self.transform = transform
+        self.device = device
+        self.dtype = dtype
+
+    def forward(self, x):
+        return self.transform(x)
+
+    def probe(self, z):
+        return None
+
+
+class FFT(Transform):
+    """rfft along dim 1 with n = nfft (reference dsp.py:69-93); cuFFT when x is on the GPU."""
+
+    def __init__(self, nfft: int = 2 ** 11, norm: str = "backward", dtype: torch.dtype = torch.float32):
+        self.nfft, self.norm = nfft, norm
+        super().__init__(transform=self._apply, dtype=dtype)
+
+    def _apply(self, x):
+        return torch.fft.rfft(x, n=self.nfft, dim=1, norm=self.norm)
+
+
+class iFFT(Transform):
+    """irfft along dim 1 with n = nfft (reference dsp.py:96-119)."""
+
+    def __init__(self, nfft: int = 2 ** 11, norm: str = "backward", dtype: torch.dtype = torch.float32):
+        self.nfft, self.norm = nfft, norm
+        super().__init__(transform=self._apply, dtype=dtype)
+
+    def _apply(self, x):
+        return torch.fft.irfft(x, n=self.nfft, dim=1, norm=self.norm)
+
+
+def _alias_envelope(nfft, alias_decay_db, device, dtype):
+    gamma = 10 ** (-torch.abs(torch.tensor(alias_decay_db, device=device, dtype=dtype)) / nfft / 20)
+    return gamma ** torch.arange(0, -nfft, -1, device=device, dtype=dtype)
+
+
+class FFTAntiAlias(Transform):
+    """rfft of x(n) * gamma^-n (reference dsp.py:122-163)."""
+
+    def __init__(self, nfft: int = 2 ** 11, norm: str = "backward", alias_decay_db: float = 0.0,
+                 device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        self.nfft, self.norm = nfft, norm
+        self.alias_envelope = _alias_envelope(nfft, alias_decay_db, device, dtype)
+        super().__init__(transform=self._apply, device=device, dtype=dtype)
+
+    def _apply(self, x):
+        return torch.fft.rfft(x * self.alias_envelope.view(1, -1, 1), n=self.nfft, dim=1, norm=self.norm)
+
+
+class iFFTAntiAlias(Transform):
+    """irfft followed by the gamma^-n envelope (reference dsp.py:166-206)."""
+
+    def __init__(self, nfft: int = 2 ** 11, norm: str = "backward", alias_decay_db: float = 0.0,
+                 device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        self.nfft, self.norm = nfft, norm
+        self.alias_envelope = _alias_envelope(nfft, alias_decay_db, device, dtype)
+        super().__init__(transform=self._apply, device=device, dtype=dtype)
+
+    def _apply(self, x):
+        return torch.fft.irfft(x, n=self.nfft, dim=1, norm=self.norm) * self.alias_envelope.view(1, -1, 1)
+
+
+# ============================================================================================= core
+
+
+def _identity(x):
+    return x
+
+
+class DSP(nn.Module):
+    """Base of every LTI module: raw `param`, a `map` to a stable parameterisation, a closed-form
+    response on the nfft/2+1 rFFT bins (reference dsp.py:212-352)."""
+
+    _parallel = False  # 1-D (per-channel) variant
+
+    def __init__(self, size: tuple, nfft: int = 2 ** 11, map: callable = _identity, requires_grad: bool = False,
+                 alias_decay_db: float = 0.0, device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        super().__init__()
+        assert isinstance(size, tuple), "Size must be a tuple."
+        self.size = size
+        self.nfft = nfft
+        self.map = map
+        self.new_value = 0
+        self.requires_grad = requires_grad
+        self.device = device
+        self.dtype = dtype
+        self.param = nn.Parameter(torch.empty(self.size, device=device, dtype=dtype), requires_grad=requires_grad)
+        self.fft = lambda x: torch.fft.rfft(x, n=self.nfft, dim=0)
+        self.ifft = lambda x: torch.fft.irfft(x, n=self.nfft, dim=0)
+        self.alias_decay_db = torch.tensor(alias_decay_db, device=device, dtype=dtype)
+        self._alias_db = float(alias_decay_db)  # host copy: lowering never reads the device tensor back
+        self._consts = {}
+        self.init_param()
+        self.get_gamma()
+
+    def _const(self, key, values, like):
+        """Small constant tensor cached per (device, dtype): maps must not create device tensors from
+        host data at call time (that would synchronise and is illegal under CUDA-graph capture)."""
+        k = (key, like.device, like.dtype)
+        t = self._consts.get(k)
+        if t is None:
+            t = torch.as_tensor(values).to(device=like.device, dtype=like.dtype)
+            self._consts[k] = t
+        return t
+
+    # -- parameters ------------------------------------------------------------------------------
+    def init_param(self):
+        torch.nn.init.normal_(self.param)
+
+    def get_gamma(self):
+        self.gamma = 10 ** (-torch.abs(self.alias_decay_db) / self.nfft / 20)
+
+    def assign_value(self, new_value: torch.Tensor, indx: tuple = tuple([slice(None)])):
+        assert self.param[indx].shape == new_value.shape, (
+            f"New values shape {new_value.shape} is not compatible with the parameter shape {self.param[indx].shape}.")
+        with torch.no_grad():
+            self.param[indx].copy_(new_value)
+            self.new_value = 1
+
+    # -- evaluation ------------------------------------------------------------------------------
+    def forward(self, x, ext_param=None):
+        """x: (B, M, N_in, ...) complex -> (B, M, N_out, ...).  `ext_param` replaces `param` on the
+        gradient path after being logged into it (reference dsp.py:415-432)."""
+        self.check_input_shape(x)
+        return self.freq_convolve(x, self._select_param(ext_param))
+
+    def _select_param(self, ext_param):
+        if ext_param is None:
+            return self.param
+        with torch.no_grad():
+            self.assign_value(ext_param)
+        return ext_param
+
+    def _sweep(self, x, param):
+        prog = sweep.Program(self.nfft, self._alias_db, x.dtype, x.device)
+        self._emit(prog, param)
+        return prog.run(x)
+
+    def _lower(self, prog, ext_param=None):
+        self._emit(prog, self._select_param(ext_param))
+
+    def _emit(self, prog, param):
+        raise NotImplementedError
+
+    def _up(self, param):
+        """Raw parameter in float64 for the maps."""
+        return param.to(torch.float64)
+
+    def _omega(self, dtype=torch.float64, device=None):
+        return 2 * math.pi * torch.arange(0, self.nfft // 2 + 1, dtype=dtype, device=device) / self.nfft
+
+    def _bins_ok(self, x):
+        return x.shape[1] == int(self.nfft / 2 + 1)
+
+    def probe(self, z):
+        raise NotImplementedError(f"probe() not implemented for {self.__class__.__name__}")
+
+    def probe_w(self, w):
+        return self.probe(1 / w)
+
+
+# ============================================================================================ gains
+
+
+class Gain(DSP):
+    """y[b,f,m,...] = sum_n map(param)[m,n] x[b,f,n,...]   (reference dsp.py:357-496)."""
+
+    def __init__(self, size: tuple = (1, 1), nfft: int = 2 ** 11, map: callable = _identity,
+                 requires_grad: bool = False, alias_decay_db: float = 0.0, device: Optional[str] = None,
+                 dtype: torch.dtype = torch.float32):
+        super().__init__(size=size, nfft=nfft, map=map, requires_grad=requires_grad, alias_decay_db=alias_decay_db,
+                         device=device, dtype=dtype)
+        self.initialize_class()
+
+    def initialize_class(self):
+        self.check_param_shape()
+        self.get_io()
+        self.get_freq_convolve()
+
+    def check_param_shape(self):
+        assert len(self.size) == 2, "gains must be 2D. For 1D (parallel) gains use parallelGain module."
+
+    def check_input_shape(self, x):
+        if self.input_channels != x.shape[2]:
+            raise ValueError(f"parameter shape = {self.size} not compatible with input signal of shape = ({x.shape}).")
+
+    def get_io(self):
+        self.input_channels = self.size[-1]
+        self.output_channels = self.size[-2] if len(self.size) > 1 else self.size[-1]
+
+    def get_freq_convolve(self):
+        self.freq_convolve = lambda x, param: self._sweep(x, param)
+
+    def _emit(self, prog, param):
+        W = self.map(self._up(param))
+        if self._parallel:
+            prog.leaf(OP_PGAIN, self.output_channels, self.input_channels, W.reshape(-1))
+        else:
+            prog.leaf(OP_GAIN, self.output_channels, self.input_channels, W)
+
+    def probe(self, z):
+        h = to_complex(self.map(self.param))
+        return torch.diag(h) if self._parallel else h
+
+
+class parallelGain(Gain):
+    """Per-channel gains, param (N,) (reference dsp.py:499-573)."""
+
+    _parallel = True
+
+    def __init__(self, size: tuple = (1,), **kwargs):
+        super().__init__(size=size, **kwargs)
+
+    def check_param_shape(self):
+        assert len(self.size) == 1, "gains must be 1D, for 2D gains use Gain module."
+
+
+class Matrix(Gain):
+    """Gain whose map builds a structured matrix: random | orthogonal | hadamard | rotation
+    (reference dsp.py:579-676)."""
+
+    def __init__(self, size: tuple = (1, 1), nfft: int = 2 ** 11, map: callable = _identity,
+                 matrix_type: str = "random", iter: int = 1, requires_grad: bool = False,
+                 alias_decay_db: float = 0.0, device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        self.matrix_type = matrix_type
+        self.iter = iter
+        super().__init__(size=size, nfft=nfft, map=map, requires_grad=requires_grad, alias_decay_db=alias_decay_db,
+                         device=device, dtype=dtype)
+
+    def matrix_gallery(self):
+        N = self.size[0]
+        t = self.matrix_type
+        if t == "random":
+            self.map = _identity
+        elif t == "orthogonal":
+            assert N == self.size[1], "Matrix must be square to be orthogonal"
+            self.map = lambda x: torch.matrix_exp(skew_matrix(x))
+        elif t == "hadamard":
+            assert N == self.size[1], "Matrix must be square to be Hadamard"
+            assert N % 2 == 0, "Matrix must have even dimensions to be Hadamard"
+            self.map = lambda x: HadamardMatrix(N, device=x.device, dtype=x.dtype)(x)
+        elif t == "rotation":
+            assert N == self.size[1], "Matrix must be square to be a rotation matrix"
+            assert N % 2 == 0, "Matrix must have even dimensions to be a rotation matrix"
+            self.map = lambda x: RotationMatrix(N, self.iter, device=x.device, dtype=x.dtype)([x[0][0]])
+        else:
+            raise ValueError(f"unknown matrix_type {t}")
+
+    def initialize_class(self):
+        self.check_param_shape()
+        self.get_io()
+        self.matrix_gallery()
+        self.get_freq_convolve()
+
+
+# ========================================================================================== filters
+
+
+class Filter(DSP):
+    """FIR filter bank: param (taps, N_out, N_in); H = rfft(map(param) * gamma^n) (reference
+    dsp.py:788-962).  Lowered as a TABLE op: the response is built once per call by cuFFT and
+    streamed by the sweep."""
+
+    _native_response = True
+
+    def __init__(self, size: tuple = (1, 1, 1), nfft: int = 2 ** 11, map: callable = _identity,
+                 requires_grad: bool = False, alias_decay_db: float = 0.0, device: Optional[str] = None,
+                 dtype: torch.dtype = torch.float32):
+        super().__init__(size=size, nfft=nfft, map=map, requires_grad=requires_grad, alias_decay_db=alias_decay_db,
+                         device=device, dtype=dtype)
+        self.initialize_class()
+
+    def initialize_class(self):
+        self.check_param_shape()
+        self.get_io()
+        self.get_freq_response()
+        self.get_freq_convolve()
+        self._stock_freq_response = self.freq_response
+
+    def check_param_shape(self):
+        assert len(self.size) == 3, "Filter must be 3D, for 2D (parallel) filters use ParallelFilter module."
+
+    def check_input_shape(self, x):
+        if (int(self.nfft / 2 + 1), self.input_channels) != (x.shape[1], x.shape[2]):
+            raise ValueError(f"parameter shape not compatible with input signal of shape = ({x.shape}).")
+
+    def get_io(self):
+        self.input_channels = self.size[-1]
+        self.output_channels = self.size[-1] if self._parallel else self.size[-2]
+
+    def get_freq_response(self):
+        self.ir = lambda x: self.map(x)
+        self.freq_response = self._fir_response
+
+    def _fir_response(self, param):
+        ir = self.map(param)
+        env = (10 ** (-abs(self._alias_db) / self.nfft / 20)) ** torch.arange(0, ir.shape[0], device=ir.device,
+                                                                               dtype=ir.dtype)
+        return torch.fft.rfft(ir * env.view(-1, *([1] * (ir.dim() - 1))), n=self.nfft, dim=0)
+
+    def get_freq_convolve(self):
+        self.freq_convolve = lambda x, param: self._sweep(x, param)
+
+    def _emit_table(self, prog, param, upcast=True):
+        H = self.freq_response(self._up(param) if upcast else param)
+        prog.leaf(OP_PTABLE if self._parallel else OP_TABLE, self.output_channels, self.input_channels, H)
+
+    def _emit(self, prog, param):
+        self._emit_table(prog, param)
+
+    def probe(self, z):
+        coeff = self.map(self.param)
+        k = torch.arange(coeff.shape[0], device=coeff.device, dtype=coeff.dtype)
+        w = (self.gamma ** k) * z ** (-k)
+        H = (to_complex(coeff) * w.view(-1, *([1] * (coeff.dim() - 1)))).sum(dim=0)
+        return torch.diag(H) if self._parallel else H
+
+
+class parallelFilter(Filter):
+    """Per-channel FIR filters, param (taps, N) (reference dsp.py:965-1049)."""
+
+    _parallel = True
+
+    def __init__(self, size: tuple = (1, 1), **kwargs):
+        super().__init__(size=size, **kwargs)
+
+    def check_param_shape(self):
+        assert len(self.size) == 2, "Filter must be 1D, for 2D filters use Filter module."
+
+
+class _SectionFilter(Filter):
+    """Shared machinery of Biquad / SVF / GEQ: a cascade of second-order sections per channel pair.
+    Subclasses provide `_taps(mapped) -> (b, a)` of shape (3, K, ...)."""
+
+    def initialize_class(self):
+        self.check_param_shape()
+        self.get_io()
+        self.get_freq_response()
+        self.get_freq_convolve()
+        self._stock_freq_response = self.freq_response
+
+    def _envelope(self, device, dtype):
+        gamma = 10 ** (-abs(self._alias_db) / self.nfft / 20)
+        return gamma ** torch.arange(0, 3, device=device, dtype=dtype)
+
+    def get_freq_response(self):
+        self.freq_response = lambda param: self.get_poly_coeff(self.map(param))[0]
+
+    def get_poly_coeff(self, param):
+        """(H, B, A) with B, A the per-section responses (M, K, ...), as the reference returns them
+        (dsp.py:1464-1526); evaluated in closed form on the bin grid instead of zero-padded FFTs."""
+        b, a = self._taps(param)
+        env = self._envelope(b.device, b.dtype)
+        shape = (3,) + (1,) * (b.dim() - 1)
+        om = self._omega(b.dtype, b.device)
+        zs = torch.exp(-1j * om.view(-1, 1) * torch.arange(3, device=b.device, dtype=b.dtype).view(1, 3))  # (M, 3)
+        B = torch.einsum("fp,p...->f...", zs, to_complex(b * env.view(shape)))
+        A = torch.einsum("fp,p...->f...", zs, to_complex(a * env.view(shape)))
+        num, den = torch.prod(B, dim=1), torch.prod(A, dim=1)
+        H = torch.where(torch.abs(den) != 0, num / den, torch.finfo(num.dtype).eps * torch.ones_like(num))
+        return H, B, A
+
+    def _overridden(self):
+        return (self.freq_response is not self._stock_freq_response
+                or type(self).get_poly_coeff is not _SectionFilter.get_poly_coeff)
+
+    def _emit(self, prog, param):
+        if self._overridden():  # user / subclass supplies its own response: stream it as a table
+            self._emit_table(prog, param, upcast=False)
+            return
+        b, a = self._taps(self.map(self._up(param)))
+        coef = sweep.pack_sections(b, a, self._parallel, prog.real)
+        prog.leaf(OP_PSOS if self._parallel else OP_SOS, self.output_channels, self.input_channels, coef,
+                  K=b.shape[1])
+
+    def probe(self, z):
+        b, a = self._taps(self.map(self.param))
+        env = self._envelope(b.device, b.dtype).view(3, *([1] * (b.dim() - 1)))
+        zs = (z ** (-torch.arange(3, device=b.device, dtype=b.dtype))).view(3, *([1] * (b.dim() - 1)))
+        H = torch.prod((to_complex(b * env) * zs).sum(0), dim=0) / torch.prod((to_complex(a * env) * zs).sum(0), dim=0)
+        return torch.diag(H) if self._parallel else H
+
+
+class Biquad(_SectionFilter):
+    """Cascade of RBJ low/high/band-pass sections; param (K, 2|3, N_out, N_in) = normalised cut-off(s)
+    and linear gain (reference dsp.py:1353-1603)."""
+
+    def __init__(self, size: tuple = (1, 1), n_sections: int = 1, filter_type: str = "lowpass",
+                 nfft: int = 2 ** 11, fs: int = 48000, requires_grad: bool = False, alias_decay_db: float = 0.0,
+                 device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        assert filter_type in ["lowpass", "highpass", "bandpass"], "Invalid filter type"
+        self.n_sections, self.filter_type, self.fs = n_sections, filter_type, fs
+        self.device, self.dtype = device, dtype
+        self.get_map()
+        self.alias_envelope_dcy = _alias_envelope(nfft, alias_decay_db, device, dtype)[:3].reciprocal()
+        DSP.__init__(self, size=(n_sections, *self.get_size(), *size), nfft=nfft, map=self.map,
+                     requires_grad=requires_grad, alias_decay_db=alias_decay_db, device=device, dtype=dtype)
+        self.initialize_class()
+
+    def get_size(self):
+        return (3,) if self.filter_type == "bandpass" else (2,)
+
+    def get_map(self):
+        self.map = self._bounded_map
+
+    def _bounded_map(self, x):
+        """clamp([fc..., 20 log10 |g|]) to [0,1] / [-60,60] dB (reference dsp.py:1528-1563)."""
+        gain_db = 20 * torch.log10(torch.abs(x[:, -1]))
+        tail = (1,) * (x.dim() - 2)
+        if self.filter_type == "bandpass":
+            e = torch.finfo(self.dtype).eps
+            v = torch.stack((x[:, 0], x[:, 1], gain_db), dim=1)
+            lo, hi = [e, e, -60.0], [1 - e, 1 - e, 60.0]
+        else:
+            v = torch.stack((x[:, 0], gain_db), dim=1)
+            lo, hi = [0.0, -60.0], [1.0, 60.0]
+        lo = self._const("lo", lo, x).view(-1, *tail)
+        hi = self._const("hi", hi, x).view(-1, *tail)
+        return torch.clamp(v, min=lo, max=hi)
+
+    def init_param(self):
+        with torch.no_grad():
+            torch.nn.init.uniform_(self.param[:, 0], a=0, b=0.5)
+            if self.filter_type == "bandpass":
+                torch.nn.init.uniform_(self.param[:, 1], a=self.param[:, 0].max().item(), b=1)
+            torch.nn.init.uniform_(self.param[:, -1], a=-1, b=1)
+
+    def check_param_shape(self):
+        assert len(self.size) == 4, "Parameter size must be 4D, for 3D (parallel) biquads use parallelBiquad module."
+
+    def _taps(self, p):
+        half_fs = self.fs / 2  # rad2hertz(param * pi)
+        kw = dict(fs=self.fs, device=p.device, dtype=p.dtype)
+        if self.filter_type == "lowpass":
+            return lowpass_filter(fc=p[:, 0] * half_fs, gain=p[:, 1], **kw)
+        if self.filter_type == "highpass":
+            return highpass_filter(fc=p[:, 0] * half_fs, gain=p[:, 1], **kw)
+        return bandpass_filter(fc1=p[:, 0] * half_fs, fc2=p[:, 1] * half_fs, gain=p[:, 2], **kw)
+
+
+class parallelBiquad(Biquad):
+    """param (K, 2|3, N) (reference dsp.py:1607-1764)."""
+
+    _parallel = True
+
+    def __init__(self, size: tuple = (1,), **kwargs):
+        super().__init__(size=size, **kwargs)
+
+    def check_param_shape(self):
+        assert len(self.size) == 3, "Parameter size must be 3D, for 3D sapce use Biquad module."
+
+
+class SVF(_SectionFilter):
+    """State-variable filter sections; param (5, K, N_out, N_in) = (f, R, mLP, mBP, mHP) before their
+    activations (reference dsp.py:2076-2373)."""
+
+    _TYPES = ["lowpass", "highpass", "bandpass", "lowshelf", "highshelf", "peaking", "notch", None]
+
+    def __init__(self, size: tuple = (1, 1), n_sections: int = 1, filter_type: str = None, nfft: int = 2 ** 11,
+                 fs: int = 48000, requires_grad: bool = False, alias_decay_db: float = 0.0,
+                 device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        assert filter_type in self._TYPES, "Invalid filter type"
+        self.fs, self.n_sections, self.filter_type = fs, n_sections, filter_type
+        self.alias_envelope_dcy = _alias_envelope(nfft, alias_decay_db, device, dtype)[:3].reciprocal()
+        DSP.__init__(self, size=(5, n_sections, *size), nfft=nfft, map=self.map_param2svf,
+                     requires_grad=requires_grad, alias_decay_db=alias_decay_db, device=device, dtype=dtype)
+        self.initialize_class()
+
+    def check_param_shape(self):
+        assert len(self.size) == 4, "Filter parameter space must be 4D, for 3D (parallel) filters use parallelSVF module."
+
+    # activations (reference dsp.py:2234-2364)
+    def param2freq(self, param):
+        return torch.tan(math.pi * torch.sigmoid(param) * 0.5)
+
+    def param2R(self, param):
+        return F.softplus(param) / math.log(2.0)
+
+    def param2mix(self, param, R=None):
+        G = 10 ** (-F.softplus(param[0]))
+        one, zero = torch.ones_like(G), torch.zeros_like(G)
+        t = self.filter_type
+        if t == "lowpass":
+            m = (one, zero, zero)
+        elif t == "highpass":
+            m = (zero, zero, one)
+        elif t == "bandpass":
+            m = (zero, one, zero)
+        elif t == "lowshelf":
+            m = (one, 2 * R * torch.sqrt(G), G)
+        elif t == "highshelf":
+            m = (G, 2 * R * torch.sqrt(G), one)
+        elif t in ("peaking", "notch"):
+            m = (one, 2 * R * torch.sqrt(G), one)
+        else:
+            m = (param[0] + 1, param[1] + 2, param[2] + 1)
+        return torch.stack(m, dim=0)
+
+    def map_param2svf(self, param):
+        f = self.param2freq(param[0])
+        r = self.param2R(param[1])
+        R = 1 / r if self.filter_type == "peaking" else r
+        m = self.param2mix(param[2:], r)
+        return f, R, m[0], m[1], m[2]
+
+    def _taps(self, mapped):
+        f, R, mLP, mBP, mHP = mapped
+        f2 = f * f
+        b = torch.stack((f2 * mLP + f * mBP + mHP, 2 * f2 * mLP - 2 * mHP, f2 * mLP - f * mBP + mHP))
+        a = torch.stack((f2 + 2 * R * f + 1, 2 * f2 - 2, f2 - 2 * R * f + 1))
+        return b, a
+
+
+class parallelSVF(SVF):
+    """param (5, K, N) (reference dsp.py:2377-2464)."""
+
+    _parallel = True
+
+    def __init__(self, size: tuple = (1,), **kwargs):
+        super().__init__(size=size, **kwargs)
+
+    def check_param_shape(self):
+        assert len(self.size) == 3, "Filter parameter space must be 3D, for 4D filters use SVF module."
+
+
+class GEQ(_SectionFilter):
+    """Graphic equaliser: param (n_gains, N_out, N_in) linear command gains; `map` -> dB
+    (reference dsp.py:2467-2611, auxiliary/eq.py:57-111)."""
+
+    def __init__(self, size: tuple = (1, 1), octave_interval: int = 1, nfft: int = 2 ** 11, fs: int = 48000,
+                 map: callable = lambda x: 20 * torch.log10(torch.abs(x)), requires_grad: bool = False,
+                 alias_decay_db: float = 0.0, device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        self.octave_interval, self.fs = octave_interval, fs
+        self.center_freq, self.shelving_crossover = eq_freqs(interval=octave_interval)
+        self.n_gains = len(self.center_freq) + 3
+        self._R = float(torch.tensor(2.7))  # the reference's float32 constant (dsp.py:2575)
+        self.alias_envelope_dcy = _alias_envelope(nfft, alias_decay_db, device, dtype)[:3].reciprocal()
+        DSP.__init__(self, size=(self.n_gains, *size), nfft=nfft, map=map, requires_grad=requires_grad,
+                     alias_decay_db=alias_decay_db, device=device, dtype=dtype)
+        self.initialize_class()
+
+    def init_param(self):
+        torch.nn.init.uniform_(self.param, a=10 ** (-6 / 20), b=10 ** (6 / 20))
+
+    def check_param_shape(self):
+        assert len(self.size) == 3, "Filter must be 3D, for 2D (parallel) filters use ParallelGEQ module."
+
+    def _taps(self, gain_db):
+        cf = self._const("cf", self.center_freq, gain_db)
+        sf = self._const("sf", self.shelving_crossover, gain_db)
+        return geq(center_freq=cf, shelving_freq=sf, R=self._R, gain_db=gain_db, fs=self.fs,
+                   device=gain_db.device, dtype=gain_db.dtype)
+
+
+class parallelGEQ(GEQ):
+    """param (n_gains, N) (reference dsp.py:2614-2692)."""
+
+    _parallel = True
+
+    def __init__(self, size: tuple = (1,), **kwargs):
+        super().__init__(size=size, **kwargs)
+
+    def check_param_shape(self):
+        assert len(self.size) == 2, "Filter must be 2D, for 3D filters use GEQ module."
+
+
+# =========================================================================================== delays
+
+
+class Delay(DSP):
+    """Delay lines: H = gamma^m exp(-j omega m), m = map(param) * fs / unit samples, rounded when
+    `isint` (reference dsp.py:3226-3450).  Learnable delays use a softplus map."""
+
+    def __init__(self, size: tuple = (1, 1), max_len: int = 2000, isint: bool = False, unit: int = 100,
+                 nfft: int = 2 ** 11, fs: int = 48000, requires_grad: bool = False, alias_decay_db: float = 0.0,
+                 device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        self.fs, self.max_len, self.unit, self.isint = fs, max_len, unit, isint
+        super().__init__(size=size, nfft=nfft, requires_grad=requires_grad, alias_decay_db=alias_decay_db,
+                         device=device, dtype=dtype)
+        self.initialize_class()
+
+    def init_param(self):
+        if self.isint:
+            delay_len = torch.randint(1, int(self.max_len), self.size, device=self.device)
+        else:
+            delay_len = torch.rand(self.size, device=self.device) * self.max_len
+        self.assign_value(self.sample2s(delay_len).to(self.param.dtype))
+        self.order = delay_len.max() + 1
+
+    def s2sample(self, delay):
+        return delay * self.fs / self.unit
+
+    def sample2s(self, delay):
+        return delay / self.fs * self.unit
+
+    def initialize_class(self):
+        self.check_param_shape()
+        self.get_io()
+        if self.requires_grad:
+            self.map = lambda x: F.softplus(x)
+        self.omega = self._omega(self.dtype, self.device).unsqueeze(1)
+        self.get_freq_response()
+        self.get_freq_convolve()
+
+    def check_param_shape(self):
+        assert len(self.size) == 2, "delay must be 2D, for 1D (parallel) delay use parallelDelay module."
+
+    def check_input_shape(self, x):
+        if (int(self.nfft / 2 + 1), self.input_channels) != (x.shape[1], x.shape[2]):
+            raise ValueError(
+                f"parameter shape = {self.param.shape} not compatible with input signal of shape = ({x.shape}).")
+
+    def get_io(self):
+        self.input_channels = self.size[-1]
+        self.output_channels = self.size[-1] if self._parallel else self.size[-2]
+
+    def get_delays(self):
+        return lambda param: self.s2sample(self.map(param))
+
+    def get_freq_response(self):
+        self.freq_response = self._delay_response
+
+    def _delay_response(self, param):
+        m = self.s2sample(self.map(param))
+        if self.isint:
+            m = m.round()
+        om = self._omega(m.dtype, m.device).view(-1, *([1] * m.dim()))
+        return ((10 ** (-abs(self._alias_db) / self.nfft / 20)) ** m) * torch.exp(-1j * om * m.unsqueeze(0))
+
+    def get_freq_convolve(self):
+        self.freq_convolve = lambda x, param: self._sweep(x, param)
+
+    def _emit(self, prog, param):
+        m = self.s2sample(self.map(self._up(param)))
+        if self._parallel:
+            prog.leaf(OP_PDELAY, self.output_channels, self.input_channels, m.reshape(-1), isint=self.isint)
+        else:
+            prog.leaf(OP_DELAY, self.output_channels, self.input_channels, m, isint=self.isint)
+
+    def probe(self, z):
+        m = self.s2sample(self.map(self.param))
+        if self.isint:
+            m = m.round()
+        H = (self.gamma ** m) * (1.0 / z) ** m
+        return torch.diag_embed(H) if self._parallel else H
+
+
+class parallelDelay(Delay):
+    """param (N,) (reference dsp.py:3453-3551)."""
+
+    _parallel = True
+
+    def __init__(self, size: tuple = (1,), max_len: int = 2000, unit: int = 100, isint: bool = False, nfft=2 ** 11,
+                 fs: int = 48000, requires_grad: bool = False, alias_decay_db: float = 0.0,
+                 device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        super().__init__(size=size, max_len=max_len, isint=isint, unit=unit, nfft=nfft, fs=fs,
+                         requires_grad=requires_grad, alias_decay_db=alias_decay_db, device=device, dtype=dtype)
+
+    def check_param_shape(self):
+        assert len(self.size) == 1, "delays must be 1D, for 2D delays use Delay module."

@@ -1,0 +1,443 @@
+"""flamo.processor.system — Series, Recursion and Shell with the reference's interface
+(gdalsanto/flamo, flamo/processor/system.py), evaluated as ONE fused sweep launch per container.
+
+A container does not call its children one by one: it asks each child to append its ops to a flat
+sweep program (`_lower`) and runs the program through flamo_b200.sweep.  The closed loop of a
+Recursion, y = (I - F Fb)^-1 F x (reference system.py:417-425), becomes a RECURSION op solved per bin
+in registers; the (B, M, N, N) tensors the reference materialises never exist.
+"""
+from __future__ import annotations
+
+import warnings
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from .. import sweep
+from .._lib import EPI_ABS, EPI_NONE
+from ..functional import signal_gallery
+from .dsp import FFT, Transform, iFFT
+
+# ============================================================================================ series
+
+
+def _flatten(modules, taken):
+    """Flatten nested Sequential / dict containers into an OrderedDict with the reference's key rules
+    (system.py:127-209): integer-like keys are renumbered by position, custom keys must be unique."""
+    out = OrderedDict()
+
+    def position():
+        return str(len(out) + len(taken))
+
+    def visit(obj, key=None):
+        if isinstance(obj, nn.Sequential):
+            visit(obj._modules)
+        elif isinstance(obj, (OrderedDict, dict)):
+            for k, v in obj.items():
+                if isinstance(v, (nn.Sequential, OrderedDict, dict)):
+                    visit(v)
+                else:
+                    visit(v, k)
+        elif isinstance(obj, nn.Module):
+            if key is None:
+                out[position()] = obj
+                return
+            try:
+                int(key)
+                numeric = True
+            except (TypeError, ValueError):
+                numeric = False
+            if numeric:
+                new_key = position()
+                out[new_key] = obj
+                if key != new_key:
+                    warnings.warn(f"Key {key} is an integer, it will be overwritten.")
+            else:
+                if key in taken or key in out:
+                    raise ValueError(f"Key {key} is already present in the Series.")
+                out[key] = obj
+        else:
+            raise ValueError("Modules must be nn.Module, nn.Sequential, or OrderedDict.")
+
+    for m in modules:
+        visit(m)
+    return out
+
+
+def _common_attribute(modules, attr):
+    """Value of `attr` shared by every module that has it (system.py:211-240)."""
+    value, found = None, False
+    for m in modules:
+        if hasattr(m, attr):
+            value, found = getattr(m, attr), True
+            break
+    if not found or value is None:
+        warnings.warn(f"Attribute {attr} not found in any of the modules.")
+        return None
+    for i, m in enumerate(modules):
+        if hasattr(m, attr) and getattr(m, attr) != value:
+            raise ValueError(
+                f"All modules must have the same {attr} value. Module {m.__class__.__name__} at index {i} is "
+                "incoherent with the part of the Series preceding it.")
+    return value
+
+
+def _chain_io(modules):
+    """Input channels of the first module that declares them and output channels of the last,
+    asserting that consecutive declarations match (system.py:242-277)."""
+    first_in, prev_out, prev_name, prev_idx = None, None, None, None
+    for j, m in enumerate(modules):
+        if not hasattr(m, "input_channels"):
+            continue
+        if first_in is None:
+            first_in = m.input_channels
+        else:
+            assert m.input_channels == prev_out, (
+                f"Module {prev_name} at index {prev_idx} has {prev_out} output channels, but module "
+                f"{m.__class__.__name__} at index {j} has {m.input_channels} input_channels.")
+        prev_out, prev_name, prev_idx = getattr(m, "output_channels", None), m.__class__.__name__, j
+    return first_in, prev_out
+
+
+def _alias_of(module) -> float:
+    a = getattr(module, "_alias_db", None)
+    if a is None:
+        a = getattr(module, "alias_decay_db", 0.0)
+        a = float(a) if a is not None else 0.0
+    return a
+
+
+class Series(nn.Sequential):
+    """Modules applied one after the other (reference system.py:11-329)."""
+
+    def __init__(self, *args):
+        super().__init__(_flatten(args, []))
+        self._refresh()
+
+    def _refresh(self):
+        mods = list(self)
+        self.nfft = _common_attribute(mods, "nfft")
+        self.alias_decay_db = _common_attribute(mods, "alias_decay_db")
+        self.dtype = _common_attribute(mods, "dtype")
+        self.input_channels, self.output_channels = _chain_io(mods)
+        self._alias_db = _alias_of(self)
+
+    def prepend(self, new_module):
+        return self.insert(0, new_module)
+
+    def append(self, new_module):
+        for k, v in _flatten((new_module,), list(self._modules.keys())).items():
+            self.add_module(k, v)
+        self._refresh()
+        return self
+
+    def insert(self, index: int, new_module):
+        n = len(self._modules)
+        if not (-n <= index <= n):
+            raise IndexError("Index out of range.")
+        if index < 0:
+            index += n
+        items = list(self._modules.items())
+        items[index:index] = list(_flatten((new_module,), list(self._modules.keys())).items())
+        self._modules.clear()
+        self._modules.update(items)
+        self._refresh()
+        return self
+
+    # -- evaluation ------------------------------------------------------------------------------
+    def _lower(self, prog, ext_param=None):
+        for key, module in self._modules.items():
+            ext = ext_param[key] if (ext_param is not None and key in ext_param) else None
+            if hasattr(module, "_lower"):
+                module._lower(prog, ext)
+            elif ext is not None:
+                prog.eager(lambda t, m=module, e=ext: m(t, e))
+            else:
+                prog.eager(module)
+
+    def forward(self, input, ext_param=None):
+        if not (torch.is_tensor(input) and input.is_complex()) or self.nfft is None:
+            # not a bin-domain signal (e.g. a Series used as a time-domain layer): plain sequential
+            for key, module in self._modules.items():
+                if ext_param is not None and key in ext_param:
+                    input = module(input, ext_param[key])
+                else:
+                    input = module(input)
+            return input
+        for m in self:
+            if hasattr(m, "check_input_shape"):
+                m.check_input_shape(input)
+                break
+        prog = sweep.Program(self.nfft, self._alias_db, input.dtype, input.device)
+        self._lower(prog, ext_param)
+        return prog.run(input)
+
+    def probe(self, z):
+        H = None
+        for m in self:
+            Hi = m.probe(z)
+            H = Hi if H is None else Hi @ H
+        return H
+
+    def probe_w(self, w):
+        H = None
+        for m in self:
+            Hi = m.probe_w(w)
+            H = Hi if H is None else Hi @ H
+        return H
+
+
+# ========================================================================================= recursion
+
+
+class Recursion(nn.Module):
+    """Closed loop with feedforward path fF and feedback path fB (reference system.py:335-565)."""
+
+    def __init__(self, fF, fB):
+        super().__init__()
+        self.feedforward = self._as_path(fF, "Feedforward")
+        self.feedback = self._as_path(fB, "Feedback")
+        self.nfft = self._shared("nfft")
+        self.alias_decay_db = self._shared("alias_decay_db")
+        self.dtype = self._shared("dtype")
+        self.input_channels, self.output_channels = self._check_io()
+        self._alias_db = _alias_of(self.feedforward)
+        self._eye = None
+
+    @staticmethod
+    def _as_path(p, name):
+        if isinstance(p, (nn.Sequential, OrderedDict)) and not isinstance(p, Series):
+            warnings.warn(f"{name} path has been converted to a Series class instance.")
+            return Series(p)
+        return p
+
+    def _shared(self, attr):
+        a, b = getattr(self.feedforward, attr, None), getattr(self.feedback, attr, None)
+        if a is None:
+            warnings.warn(f"The feedforward pass does not possess the attribute {attr}.")
+        if b is None:
+            warnings.warn(f"The feedback pass does not possess the attribute {attr}.")
+        if a is not None and b is not None:
+            assert a == b, (f"The feedforward pass has {attr} = {a} and feedback pass has {attr} = {b}. "
+                            "They must have the same value.")
+        return a if a is not None else b
+
+    def _check_io(self):
+        io = {}
+        for name, path in (("feedforward", self.feedforward), ("feedback", self.feedback)):
+            for side in ("input_channels", "output_channels"):
+                v = getattr(path, side, None)
+                if v is None:
+                    raise ValueError(f"The {name} pass does not possess the attribute {side}.")
+                io[name, side] = v
+        ff_in, ff_out = io["feedforward", "input_channels"], io["feedforward", "output_channels"]
+        fb_in, fb_out = io["feedback", "input_channels"], io["feedback", "output_channels"]
+        assert ff_out == fb_in, (f"Feedforward pass has {ff_out} output channels, but feedback pass has {fb_in} "
+                                 "input channels. They must be the same.")
+        assert fb_out == ff_in, (f"Feedforward pass {ff_in} input channels, but the feedback pass has {fb_out} "
+                                 "output channels. They must be the same.")
+        return ff_in, ff_out
+
+    @property
+    def I(self):
+        """(M, N, N) complex identity, built on first use (the reference allocates it eagerly,
+        system.py:427-438; the sweep never needs it)."""
+        if self._eye is None:
+            n, M = self.output_channels, self.nfft // 2 + 1
+            dev = self.alias_decay_db.device if torch.is_tensor(self.alias_decay_db) else None
+            self._eye = torch.eye(n, dtype=self.dtype, device=dev).to(torch.complex64 if self.dtype == torch.float32
+                                                                       else torch.complex128).expand(M, n, n)
+        return self._eye
+
+    def _lower(self, prog, ext_param=None):
+        ext_ff = ext_fb = None
+        if ext_param is not None:
+            for key, p in ext_param.items():
+                if "feedback" in key:
+                    ext_fb = p
+                elif "feedforward" in key:
+                    ext_ff = p
+        for path in (self.feedforward, self.feedback):
+            if not hasattr(path, "_lower"):
+                raise sweep._lib.Unsupported(sweep._lib.E_UNSUPPORTED,
+                                             f"{path.__class__.__name__} cannot be lowered inside a Recursion")
+        prog.recursion(lambda: self.feedforward._lower(prog, ext_ff), lambda: self.feedback._lower(prog, ext_fb))
+
+    def forward(self, X, ext_param=None):
+        prog = sweep.Program(self.nfft, self._alias_db, X.dtype, X.device)
+        self._lower(prog, ext_param)
+        return prog.run(X)
+
+    def probe(self, z):
+        Fm, Bm = self.feedforward.probe(z), self.feedback.probe(z)
+        A = torch.eye(Fm.shape[-2], dtype=Fm.dtype, device=Fm.device) - Fm @ Bm
+        return torch.linalg.solve(A, Fm)
+
+    def probe_recursion(self, z, include_shell_io: bool = False, **kwargs):
+        Fm, Bm = self.feedforward.probe(z), self.feedback.probe(z)
+        return torch.eye(Fm.shape[0], dtype=Fm.dtype, device=Fm.device) - Fm @ Bm
+
+    def probe_recursion_w(self, w):
+        Fm, Bm = self.feedforward.probe_w(w), self.feedback.probe_w(w)
+        return torch.eye(Fm.shape[0], dtype=Fm.dtype, device=Fm.device) - Fm @ Bm
+
+
+# ============================================================================================= shell
+
+
+def _is_abs_layer(layer) -> bool:
+    """True if `layer` is a Transform computing |x| (the output layer of every frequency-domain
+    example).  Decided once per layer object by probing it on a tiny CPU tensor."""
+    if not isinstance(layer, Transform) or type(layer) is not Transform:
+        return False
+    flag = getattr(layer, "_fsweep_is_abs", None)
+    if flag is None:
+        flag = False
+        try:
+            t = torch.tensor([[[3.0 + 4.0j], [-1.0 - 1.0j], [0.0 + 0.0j], [0.5j]]], dtype=torch.complex64)
+            r = layer.transform(t)
+            flag = bool(torch.is_tensor(r) and not r.is_complex() and r.shape == t.shape
+                        and torch.allclose(r, torch.abs(t)))
+        except Exception:
+            flag = False
+        layer._fsweep_is_abs = flag
+    return flag
+
+
+class Shell(nn.Module):
+    """input_layer -> core -> output_layer (reference system.py:776-1153)."""
+
+    def __init__(self, core, input_layer=nn.Identity(), output_layer=nn.Identity()):
+        super().__init__()
+        self.__core = self._wrap(core, "Core")
+        self.__input_layer = self._wrap(input_layer, "Input layer")
+        self.__output_layer = self._wrap(output_layer, "Output layer")
+        self.nfft = self._shared("nfft")
+        self.alias_decay_db = self._shared("alias_decay_db")
+        self.dtype = self._shared("dtype")
+        self.input_channels, self.output_channels = self._check_io()
+        self.fuse_output = True  # fold an |.| output layer into the sweep epilogue
+
+    @staticmethod
+    def _wrap(m, name):
+        if isinstance(m, (nn.Sequential, OrderedDict)) and not isinstance(m, Series):
+            warnings.warn(f"{name} has been converted to a Series class instance.")
+            return Series(m)
+        return m
+
+    def _shared(self, attr):
+        core = getattr(self.__core, attr, None)
+        if core is None:
+            raise ValueError(f"The core does not possess the attribute {attr}.")
+        for name, layer in (("input layer", self.__input_layer), ("output layer", self.__output_layer)):
+            v = getattr(layer, attr, None)
+            if v is not None:
+                assert core == v, (f"The {name} has {attr} = {v} and the core has {attr} = {core}. "
+                                   "They must have the same value.")
+        return core
+
+    def _check_io(self):
+        c_in, c_out = getattr(self.__core, "input_channels", None), getattr(self.__core, "output_channels", None)
+        if c_in is None:
+            raise ValueError("The core does not possess the attribute input_channels.")
+        if c_out is None:
+            raise ValueError("The core does not possess the attribute output_channels.")
+        l_out = getattr(self.__input_layer, "output_channels", None)
+        if l_out is not None:
+            assert c_in == l_out, (f"The core should receive {c_in} input channels, but {l_out} channels arrive "
+                                   "from the input layer.")
+        o_in = getattr(self.__output_layer, "input_channels", None)
+        if o_in is not None:
+            assert c_out == o_in, (f"The core sends {c_out} output channels, but the output layer can only "
+                                   f"receive {o_in} channels.")
+        in_ch = getattr(self.__input_layer, "input_channels", None)
+        out_ch = getattr(self.__output_layer, "output_channels", None)
+        return (in_ch if in_ch is not None else c_in), (out_ch if out_ch is not None else c_out)
+
+    # -- evaluation ------------------------------------------------------------------------------
+    def forward(self, x, ext_param=None):
+        x = self.__input_layer(x)
+        core, out = self.__core, self.__output_layer
+        if hasattr(core, "_lower") and torch.is_tensor(x) and x.is_complex():
+            if hasattr(core, "check_input_shape"):
+                core.check_input_shape(x)
+            prog = sweep.Program(self.nfft, _alias_of(core), x.dtype, x.device)
+            core._lower(prog, ext_param)
+            if self.fuse_output and _is_abs_layer(out):
+                return prog.run(x, epilogue=EPI_ABS)
+            return out(prog.run(x, epilogue=EPI_NONE))
+        x = core(x, ext_param) if ext_param is not None else core(x)
+        return out(x)
+
+    # -- accessors -------------------------------------------------------------------------------
+    def get_inputLayer(self):
+        return self.__input_layer
+
+    def set_inputLayer(self, input_layer=None):
+        self.__input_layer = input_layer
+
+    def get_outputLayer(self):
+        return self.__output_layer
+
+    def set_outputLayer(self, output_layer=None):
+        self.__output_layer = output_layer
+
+    def get_core(self):
+        return self.__core
+
+    def set_core(self, core):
+        self.__core = core
+
+    def probe(self, z, include_shell_io: bool = False):
+        H = self.__core.probe(z)
+        if include_shell_io:
+            for layer, left in ((self.__input_layer, False), (self.__output_layer, True)):
+                Hl = layer.probe(z) if hasattr(layer, "probe") else None
+                if Hl is not None:
+                    H = Hl if H is None else (Hl @ H if left else H @ Hl)
+        return H
+
+    # -- responses -------------------------------------------------------------------------------
+    def _device(self):
+        return self.alias_decay_db.device if torch.is_tensor(self.alias_decay_db) else None
+
+    def _impulse(self, fs, identity):
+        x = signal_gallery(batch_size=1, n_samples=self.nfft, n=self.input_channels, signal_type="impulse", fs=fs,
+                           device=self._device(), dtype=self.dtype)
+        if identity and self.input_channels > 1:
+            x = x.diag_embed()
+        return x
+
+    def _rising_envelope(self, identity):
+        a = _alias_of(self.__core)
+        gamma = 10 ** (-abs(a) / self.nfft / 20)
+        env = gamma ** torch.arange(0, -self.nfft, -1, device=self._device(), dtype=self.dtype)
+        env = env.view(1, -1, 1)
+        if identity and self.input_channels > 1:
+            env = env.unsqueeze(-1)
+        return env
+
+    def _with_layers(self, input_layer, output_layer, x):
+        saved = (self.__input_layer, self.__output_layer)
+        self.__input_layer, self.__output_layer = input_layer, output_layer
+        try:
+            with torch.no_grad():
+                return self.forward(x)
+        finally:
+            self.__input_layer, self.__output_layer = saved
+
+    def get_time_response(self, fs: int = 48000, identity: bool = False):
+        """Impulse response (1, nfft, N_out[, N_in]) with the anti-aliasing envelope undone
+        (reference system.py:1012-1079)."""
+        env = self._rising_envelope(identity)
+        out = nn.Sequential(iFFT(self.nfft, dtype=self.dtype), Transform(lambda y: y * env))
+        return self._with_layers(FFT(self.nfft, dtype=self.dtype), out, self._impulse(fs, identity))
+
+    def get_freq_response(self, fs: int = 48000, identity: bool = False):
+        """Frequency response on the unit circle (1, M, N_out[, N_in]): core response evaluated at
+        radius gamma, brought back by iFFT -> rising envelope -> FFT (reference system.py:1081-1153)."""
+        env = self._rising_envelope(identity)
+        out = nn.Sequential(iFFT(self.nfft, dtype=self.dtype), Transform(lambda y: y * env),
+                            FFT(self.nfft, dtype=self.dtype))
+        return self._with_layers(FFT(self.nfft, dtype=self.dtype), out, self._impulse(fs, identity))

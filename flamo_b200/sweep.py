@@ -1,0 +1,264 @@
+"""Lowering of a flamo module tree to a flat sweep program + the autograd seam over libfsweep.
+
+    module tree ──_lower()──► Program(ops, coefficient tensors) ──run()──► SweepFunction
+                                                                          │ forward  → fsweep_forward
+                                                                          │ backward → fsweep_backward
+
+The coefficient tensors are produced by the modules' own `map`s in plain PyTorch (O(#params),
+differentiable, user-overridable — SURVEY.md §7); everything that is O(M) happens inside the two
+C-ABI calls.  Gradients come back w.r.t. the coefficients and autograd chains them through the maps.
+"""
+from __future__ import annotations
+
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_ABS, EPI_NONE, F_GRAD, F_ISINT, OP_DELAY, OP_GAIN, OP_PDELAY, OP_PGAIN, OP_PSOS, OP_PTABLE,
+                   OP_RECURSION, OP_SOS, OP_TABLE, Op, Plan)
+
+MAX_OPS_PER_LAUNCH = 24
+_DIAG = (OP_PGAIN, OP_PSOS, OP_PDELAY, OP_PTABLE)
+_TABLE = (OP_TABLE, OP_PTABLE)
+
+# ---------------------------------------------------------------------------------------------
+# bin sharding (multi-GPU): inside `bin_shard(begin, end)` every sweep processes only that range
+# of rFFT bins and returns tensors with end-begin bins.
+_tls = threading.local()
+
+
+class bin_shard:
+    def __init__(self, begin: int, end: int):
+        self.range = (int(begin), int(end))
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "shard", None)
+        _tls.shard = self.range
+        return self
+
+    def __exit__(self, *a):
+        _tls.shard = self.prev
+
+
+def current_shard() -> Optional[Tuple[int, int]]:
+    return getattr(_tls, "shard", None)
+
+
+# ---------------------------------------------------------------------------------------------
+class CudaBackend:
+    """The product backend: ctypes calls into libfsweep.so on the current CUDA stream."""
+
+    name = "cuda"
+
+    def plan(self, ops: Sequence[tuple], nfft: int, alias_decay_db: float, dtype: int):
+        return Plan([Op(*o) for o in ops], nfft, alias_decay_db, dtype)
+
+    @staticmethod
+    def _stream(t: torch.Tensor):
+        return torch.cuda.current_stream(t.device).cuda_stream
+
+    def forward(self, plan, ops, coefs, x, y, cols, bin_begin, epilogue):
+        B, nb = x.shape[0], x.shape[1]
+        plan.forward([c.data_ptr() for c in coefs], x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), B, cols,
+                     bin_begin, nb, epilogue, self._stream(x))
+
+    def backward(self, plan, ops, coefs, x, gy, grads, gx, cols, bin_begin, epilogue):
+        B, nb = x.shape[0], x.shape[1]
+        ws_bytes = plan.workspace_bytes(B, cols, nb)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        plan.backward([c.data_ptr() for c in coefs], x.data_ptr(), x.stride(0), gy.data_ptr(), gy.stride(0),
+                      [g.data_ptr() if g is not None else None for g in grads],
+                      gx.data_ptr() if gx is not None else None, gx.stride(0) if gx is not None else 0, B, cols,
+                      bin_begin, nb, epilogue, ws.data_ptr(), ws_bytes, self._stream(x))
+
+
+_BACKEND = CudaBackend()  # tests/ may swap this for a CPU emulator to exercise the host logic without a GPU
+_PLANS = {}
+_PLANS_LOCK = threading.Lock()
+launch_count = 0  # kernels enqueued by this process through the sweep (bench bookkeeping)
+
+
+def _get_plan(ops: Tuple[tuple, ...], nfft: int, alias_decay_db: float, dtype: int):
+    key = (_BACKEND.name, ops, int(nfft), float(alias_decay_db), dtype)
+    with _PLANS_LOCK:
+        p = _PLANS.get(key)
+        if p is None:
+            p = _BACKEND.plan(ops, nfft, alias_decay_db, dtype)
+            _PLANS[key] = p
+        return p
+
+
+def _batch_view(t: torch.Tensor) -> torch.Tensor:
+    """Kernel layout: dims 1.. contiguous, arbitrary batch stride."""
+    if t.shape[0] == 1 or t[0].is_contiguous():
+        if t.shape[0] == 1 and not t[0].is_contiguous():
+            return t.contiguous()
+        return t
+    return t.contiguous()
+
+
+class SweepFunction(torch.autograd.Function):
+    """y = program(x); x: (B, n_bins, N_in, cols) complex, already restricted to the processed bins."""
+
+    @staticmethod
+    def forward(ctx, x, plan, ops, epilogue, bin_begin, n_out, *coefs):
+        global launch_count
+        x = _batch_view(x)
+        B, nb, _, cols = x.shape
+        real = torch.float32 if x.dtype == torch.complex64 else torch.float64
+        y = torch.empty((B, nb, n_out, cols), dtype=real if epilogue == EPI_ABS else x.dtype, device=x.device)
+        coefs = tuple(c.contiguous() for c in coefs)
+        if nb > 0:
+            _BACKEND.forward(plan, ops, coefs, x, y, cols, bin_begin, epilogue)
+            launch_count += 1
+        ctx.plan, ctx.ops, ctx.epilogue, ctx.bin_begin = plan, ops, epilogue, bin_begin
+        ctx.save_for_backward(x, *coefs)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        global launch_count
+        x, *coefs = ctx.saved_tensors
+        B, nb, _, cols = x.shape
+        gy = _batch_view(gy)
+        need = ctx.needs_input_grad
+        leaf_ops = [o for o in ctx.ops if o[0] != OP_RECURSION]
+        grads: List[Optional[torch.Tensor]] = []
+        for i, c in enumerate(coefs):
+            if need[6 + i] and (leaf_ops[i][4] & F_GRAD):
+                # TABLE gradients are only written inside the processed bin range
+                grads.append(torch.zeros_like(c) if leaf_ops[i][0] in _TABLE else torch.empty_like(c))
+            else:
+                grads.append(None)
+        gx = torch.empty_like(x, memory_format=torch.contiguous_format) if need[0] else None
+        if nb > 0:
+            _BACKEND.backward(ctx.plan, ctx.ops, coefs, x, gy, grads, gx, cols, ctx.bin_begin, ctx.epilogue)
+            launch_count += 2
+        else:
+            grads = [None if g is None else torch.zeros_like(g) for g in grads]
+        return (gx, None, None, None, None, None, *grads)
+
+
+# ---------------------------------------------------------------------------------------------
+class Program:
+    """Flat sweep program under construction.  Leaves are (kind, n_out, n_in, K, flags, 0, 0, 0) tuples
+    paired with a coefficient tensor; a recursion is a marker tuple followed by its two chains."""
+
+    def __init__(self, nfft: int, alias_decay_db: float, cdtype: torch.dtype, device):
+        self.nfft, self.alias_decay_db = int(nfft), float(alias_decay_db)
+        self.cdtype = cdtype
+        self.real = torch.float32 if cdtype == torch.complex64 else torch.float64
+        self.device = device
+        self.items: List[tuple] = []  # ("leaf", op, coef) | ("rec", n_out, n_in, [leaf...], [leaf...]) | ("eager", fn)
+        self._chain: Optional[list] = None
+
+    # -- construction ------------------------------------------------------------------------
+    def leaf(self, kind: int, n_out: int, n_in: int, coef: torch.Tensor, K: int = 0, isint: bool = False):
+        want = kind in (OP_GAIN, OP_PGAIN, OP_SOS, OP_PSOS, OP_TABLE, OP_PTABLE) or not isint
+        flags = (F_ISINT if isint else 0) | (F_GRAD if (coef.requires_grad and torch.is_grad_enabled() and want) else 0)
+        if kind in (OP_DELAY, OP_PDELAY):
+            coef = coef.to(torch.float64)
+        elif kind in _TABLE:
+            coef = coef.to(self.cdtype)
+        else:
+            coef = coef.to(self.real)
+        item = ("leaf", (kind, int(n_out), int(n_in), int(K), flags, 0, 0, 0), coef)
+        (self._chain if self._chain is not None else self.items).append(item)
+
+    def eager(self, fn):
+        """A module the sweep cannot express: run it in PyTorch between two launches."""
+        if self._chain is not None:
+            raise _lib.Unsupported(_lib.E_UNSUPPORTED, "non-DSP module inside a Recursion path")
+        self.items.append(("eager", fn))
+
+    def recursion(self, lower_ff, lower_fb):
+        if self._chain is not None:
+            raise _lib.Unsupported(_lib.E_UNSUPPORTED, "nested Recursion")
+        self._chain = ff = []
+        lower_ff()
+        self._chain = fb = []
+        lower_fb()
+        self._chain = None
+        if not ff or not fb:
+            raise ValueError("Recursion needs non-empty feedforward and feedback paths")
+        self.items.append(("rec", ff[-1][1][1], ff[0][1][2], ff, fb))
+
+    # -- execution ---------------------------------------------------------------------------
+    def _segments(self):
+        seg, n_leaf, has_rec = [], 0, False
+        for it in self.items:
+            if it[0] == "eager":
+                if seg:
+                    yield ("sweep", seg)
+                yield it
+                seg, n_leaf, has_rec = [], 0, False
+                continue
+            n = 1 if it[0] == "leaf" else len(it[3]) + len(it[4])
+            if seg and (n_leaf + n > MAX_OPS_PER_LAUNCH or (it[0] == "rec" and has_rec)):
+                yield ("sweep", seg)
+                seg, n_leaf, has_rec = [], 0, False
+            seg.append(it)
+            n_leaf += n
+            has_rec |= it[0] == "rec"
+        if seg:
+            yield ("sweep", seg)
+
+    def run(self, x: torch.Tensor, epilogue: int = EPI_NONE) -> torch.Tensor:
+        if not x.is_complex():
+            raise TypeError("sweep input must be complex (bin-domain) — put a dsp.FFT input layer in front")
+        if x.device.type != "cuda" and _BACKEND.name == "cuda":
+            raise RuntimeError(
+                "flamo_b200 evaluates the frequency sweep with hand-written CUDA kernels only; got a "
+                f"{x.device.type} tensor. Move the model and data to a CUDA device (no CPU fallback exists).")
+        trail = tuple(x.shape[3:])
+        cols = 1
+        for d in trail:
+            cols *= d
+        x4 = x.reshape(x.shape[0], x.shape[1], x.shape[2], cols)
+        shard = current_shard()
+        M = self.nfft // 2 + 1
+        bin_begin = 0
+        if shard is not None and x4.shape[1] == M:
+            bin_begin = shard[0]
+            x4 = x4[:, shard[0]:shard[1]]
+        elif shard is not None:
+            bin_begin = shard[0]  # already restricted by an earlier launch of the same series
+        segs = list(self._segments())
+        dtype = _lib.C64 if x.dtype == torch.complex64 else _lib.C128
+        for si, (tag, payload) in enumerate(segs):
+            if tag == "eager":
+                x4 = payload(x4.reshape(x4.shape[:3] + trail)).reshape(x4.shape[0], x4.shape[1], -1, cols)
+                continue
+            ops, coefs = [], []
+            for it in payload:
+                if it[0] == "leaf":
+                    ops.append(it[1])
+                    coefs.append(it[2])
+                else:
+                    _, n_out, n_in, ff, fb = it
+                    ops.append((OP_RECURSION, n_out, n_in, 0, 0, len(ff), len(fb), 0))
+                    for l in ff + fb:
+                        ops.append(l[1])
+                        coefs.append(l[2])
+            ops = tuple(ops)
+            last = payload[-1]
+            n_out = last[1][1] if last[0] == "leaf" else last[1]
+            epi = epilogue if si == len(segs) - 1 else EPI_NONE
+            plan = _get_plan(ops, self.nfft, self.alias_decay_db, dtype)
+            x4 = SweepFunction.apply(x4, plan, ops, epi, bin_begin, n_out, *coefs)
+        if epilogue == EPI_ABS and segs and segs[-1][0] == "eager":
+            x4 = torch.abs(x4)
+        return x4.reshape(x4.shape[:3] + trail)
+
+
+def pack_sections(b: torch.Tensor, a: torch.Tensor, parallel: bool, real: torch.dtype) -> torch.Tensor:
+    """(3, K, N_out, N_in) taps (or (3, K, N) for parallel) -> kernel layout [K][N_in][N_out][8]
+    ([K][N][8]) of {b0+b1+b2, b1, b2, b0-b1+b2, a0+a1+a2, a1, a2, a0-a1+a2} (include/fsweep.h).
+    Done in the taps' own (float64) precision, then cast; differentiable."""
+    packed = torch.stack((b[0] + b[1] + b[2], b[1], b[2], b[0] - b[1] + b[2],
+                          a[0] + a[1] + a[2], a[1], a[2], a[0] - a[1] + a[2]), dim=-1)
+    if not parallel:
+        packed = packed.permute(0, 2, 1, 3)  # (K, N_out, N_in, 8) -> (K, N_in, N_out, 8)
+    return packed.to(real).contiguous()

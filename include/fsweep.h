@@ -1,0 +1,162 @@
+/*
+ * fsweep.h — C ABI of libfsweep.so: the B200-native frequency-bin sweep engine.
+ *
+ * The reference (gdalsanto/flamo, pure Python/PyTorch) has no FFI; its boundary for this
+ * path is the Python class API.  This header is the single new seam underneath that API:
+ * the host-side mirror (flamo_b200/processor/{dsp,system}.py) lowers a module tree into a
+ * flat "sweep program" and calls the two entry points below through ctypes.  Each op kind
+ * cites the reference code it replaces (paths relative to /root/reference/flamo/).
+ *
+ *   fsweep_forward   replaces  Series.forward (processor/system.py:279-301),
+ *                              Recursion.forward (system.py:397-425) and every
+ *                              freq_response/freq_convolve lambda it reaches
+ *                              (processor/dsp.py:466-468, 552-554, 922-924, 1520-1526,
+ *                               2226-2232, 2587-2593, 3356-3374, 3406-3408, 3504-3530)
+ *   fsweep_backward  replaces  the autograd graph torch builds through those same calls
+ *                              (einsum / rfft / prod / div / where / exp / linalg.solve
+ *                              backward), as driven by loss.backward() in
+ *                              optimize/trainer.py:190
+ *
+ * Conventions
+ *   - plain C, no C++ exceptions cross the boundary; every pointer marked "device" is a CUDA
+ *     device pointer owned by the caller; the library allocates nothing on the device and
+ *     creates no streams; all work is enqueued on the caller's stream and is CUDA-graph
+ *     capture safe (no sync, no allocation, no host callback).
+ *   - dtype: FSWEEP_C64 computes in float32 / complex64, FSWEEP_C128 in float64 / complex128.
+ *     "real" below means float or double accordingly; "cplx" is interleaved (re, im) of real.
+ *   - a bin k is the rFFT bin index, omega_k = 2*pi*k/nfft, z^-1 = exp(-j*omega_k); the
+ *     anti-aliasing radius gamma = 10^(-|alias_decay_db| / (20*nfft)) (dsp.py:294-307).
+ *   - signals: x is (batch, n_bins, n_in, cols) cplx, y is (batch, n_bins, n_out, cols) cplx
+ *     (or real when the epilogue is FSWEEP_EPI_ABS); the last three dims are contiguous, the
+ *     batch stride is given in elements so bin-range slices of a larger tensor can be passed
+ *     without a copy.  x and y address the FIRST PROCESSED bin (absolute index bin_begin).
+ */
+#ifndef FSWEEP_H
+#define FSWEEP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FSWEEP_API __attribute__((visibility("default")))
+#else
+#define FSWEEP_API
+#endif
+
+#define FSWEEP_VERSION 1
+
+/* return codes */
+#define FSWEEP_OK 0
+#define FSWEEP_E_BADARG (-1)
+#define FSWEEP_E_UNSUPPORTED (-2)
+#define FSWEEP_E_WORKSPACE (-3)
+#define FSWEEP_E_CUDA (-4)
+
+/* dtypes */
+#define FSWEEP_C64 0
+#define FSWEEP_C128 1
+
+/* epilogues (output layer fused into the sweep) */
+#define FSWEEP_EPI_NONE 0 /* y = Y                      (cplx out)                           */
+#define FSWEEP_EPI_ABS 1  /* y = |Y|                    (real out)  Transform(torch.abs)      */
+
+/* op kinds.  Coefficient layout per kind ("coef"), and the gradient buffer layout ("grad",
+ * same shape and dtype as coef unless noted).  Delays are ALWAYS float64. */
+enum fsweep_op_kind {
+  /* dense real matrix, constant over bins: y = W x.  dsp.Gain / dsp.Matrix after `map`
+   * (dsp.py:466-468, 642-665).  coef: real[n_out][n_in]. */
+  FSWEEP_OP_GAIN = 1,
+  /* diagonal real gain: y_n = w_n x_n.  dsp.parallelGain (dsp.py:552-554).  coef: real[n]. */
+  FSWEEP_OP_PGAIN = 2,
+  /* dense cascade of K second-order sections per (out,in) pair:
+   *   H[m][n] = prod_s B_s / prod_s A_s,  B_s = b0 + b1*g*z^-1 + b2*g^2*z^-2  (g = gamma),
+   *   H = eps if |prod A| == 0   (dsp.py:1520-1526 = 2226-2232 = 2587-2593: Biquad, SVF, GEQ
+   *   after their maps; equals the reference's zero-padded rfft of the 3 taps).
+   * coef: real[K][n_in][n_out][8] "packed sections":
+   *   {b0+b1+b2, b1, b2, b0-b1+b2, a0+a1+a2, a1, a2, a0-a1+a2}
+   * The tap sums let the kernel expand each quadratic around w=+1 (low bins) or w=-1 (high
+   * bins) without cancellation; grad has the same packed layout (chain rule through the
+   * linear packing is done by the caller). */
+  FSWEEP_OP_SOS = 3,
+  /* diagonal cascade (parallelBiquad / parallelSVF / parallelGEQ).  coef: real[K][n][8]. */
+  FSWEEP_OP_PSOS = 4,
+  /* dense delays: H[m][n] = gamma^d * exp(-j*omega_k*d), d = coef[m][n] samples
+   * (dsp.py:3356-3374).  With FSWEEP_F_ISINT d is rounded and the phase index (k*d mod nfft)
+   * is formed in integers; otherwise k*d/nfft is range-reduced in float64.
+   * coef: double[n_out][n_in]; grad: double[n_out][n_in] (dL/dd; zero for ISINT). */
+  FSWEEP_OP_DELAY = 5,
+  /* diagonal delays (dsp.parallelDelay, dsp.py:3504-3530).  coef: double[n]. */
+  FSWEEP_OP_PDELAY = 6,
+  /* dense precomputed response streamed from HBM (generic dsp.Filter, dsp.py:901-924):
+   * coef: cplx[M][n_out][n_in] indexed by ABSOLUTE bin; grad: same (dL/dH, PyTorch
+   * convention dL/dRe + j dL/dIm). */
+  FSWEEP_OP_TABLE = 7,
+  /* diagonal table (dsp.parallelFilter, dsp.py:1021-1023).  coef: cplx[M][n]. */
+  FSWEEP_OP_PTABLE = 8,
+  /* closed loop y = (I - F*Fb)^-1 F x (system.py:417-425).  The next n_ff ops form the
+   * feedforward chain F (applied left to right), the n_fb ops after them the feedback chain
+   * Fb.  Owns no coefficient slot.  n_out = loop width, n_in = input channels of F. */
+  FSWEEP_OP_RECURSION = 9
+};
+
+/* op flags */
+#define FSWEEP_F_ISINT 1u /* DELAY/PDELAY: integer delays, exact integer phase          */
+#define FSWEEP_F_GRAD 2u  /* a coefficient gradient is wanted for this op in backward   */
+
+typedef struct fsweep_op {
+  int32_t kind;       /* enum fsweep_op_kind                                               */
+  int32_t n_out;      /* output channels (rows of H)                                       */
+  int32_t n_in;       /* input channels  (cols of H); == n_out for diagonal kinds          */
+  int32_t n_sections; /* K for SOS/PSOS, else 0                                            */
+  uint32_t flags;
+  int32_t n_ff;       /* RECURSION only                                                    */
+  int32_t n_fb;       /* RECURSION only                                                    */
+  int32_t reserved;
+} fsweep_op_t;
+
+typedef struct fsweep_plan fsweep_plan_t; /* opaque, immutable after create, host memory only */
+
+FSWEEP_API int fsweep_version(void);
+FSWEEP_API const char* fsweep_last_error(void); /* thread-local message of the last failing call */
+
+/* ops: flat pre-order program (top-level series; at most one RECURSION, whose chains follow
+ * it).  Every non-RECURSION op owns coefficient slot i = its rank among non-RECURSION ops. */
+FSWEEP_API int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nfft, double alias_decay_db,
+                       int dtype, fsweep_plan_t** out);
+FSWEEP_API int fsweep_plan_destroy(fsweep_plan_t* plan);
+FSWEEP_API int fsweep_plan_num_coeffs(const fsweep_plan_t* plan);
+/* number of reals (for TABLE kinds: of cplx) in slot `slot`'s coefficient / gradient buffer
+ * given the total bin count M (only TABLE kinds depend on M). */
+FSWEEP_API int64_t fsweep_plan_coeff_numel(const fsweep_plan_t* plan, int slot, int64_t M);
+
+/* scratch the caller must provide to fsweep_backward (forward needs none) */
+FSWEEP_API size_t fsweep_workspace_bytes(const fsweep_plan_t* plan, int64_t batch, int64_t cols, int64_t n_bins);
+
+FSWEEP_API int fsweep_forward(const fsweep_plan_t* plan,
+                   const void* const* coeffs,      /* host array [num_coeffs] of device pointers */
+                   const void* x, int64_t x_batch_stride, /* device; stride in cplx elements */
+                   void* y, int64_t y_batch_stride,       /* device; stride in output elements */
+                   int64_t batch, int64_t cols, int64_t bin_begin, int64_t n_bins,
+                   int epilogue, void* stream /* cudaStream_t */);
+
+FSWEEP_API int fsweep_backward(const fsweep_plan_t* plan, const void* const* coeffs,
+                    const void* x, int64_t x_batch_stride,
+                    const void* grad_y, int64_t gy_batch_stride, /* device; dL/dy, layout of y */
+                    void* const* grad_coeffs, /* host array [num_coeffs]; NULL entries skipped;
+                                                 buffers are OVERWRITTEN (TABLE kinds: only the
+                                                 processed bin range is written) */
+                    void* grad_x, int64_t gx_batch_stride, /* device or NULL */
+                    int64_t batch, int64_t cols, int64_t bin_begin, int64_t n_bins,
+                    int epilogue, void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of kernels the last forward / backward call of this thread enqueued (bench bookkeeping) */
+FSWEEP_API int fsweep_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSWEEP_H */

@@ -22,3 +22,15 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def emulated_backend():
+    """Swap the CUDA backend for the float64 CPU emulator of the ABI (tests/cpu_emulator.py)."""
+    import cpu_emulator
+
+    prev = cpu_emulator.install()
+    try:
+        yield
+    finally:
+        cpu_emulator.uninstall(prev)
