@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+metric   freq-bins*channels/sec of one Trainer.train_step  =  B * M * N_ch / t_step
+workload configs[1]: examples/e8_colorless_fdn.py restated with N = 8 delay lines
+         (Gain(8,1) -> Recursion(parallelDelay(8), Matrix(8,8, orthogonal)) -> Gain(1,8)),
+         nfft = 96000 (M = 48001 bins), batch 1, alias_decay_db = 30, float32 modules,
+         Shell(FFT, core, |.|), criteria mse_loss + 0.2 * sparsity_loss, Adam lr 1e-3
+         (SURVEY.md §8d config 2).  A "step" is one full train_step: forward, both criteria,
+         backward, Adam.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA engine
+    python bench.py --impl reference [...]                         the reference algorithm on the host CPU
+    torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU (weak scaling: every
+                                                                   rank trains its own batch item, gradients
+                                                                   are all-reduced over NCCL each step)
+
+The reference is pure Python and cannot travel to the GPU box, so the reference arm times
+oracle/flamo_oracle.py — the bit-exact restatement of the reference's algorithm and cost structure
+(zero-padded rffts, materialised (B,M,N,N) loop matrices, torch.linalg.solve, autograd) — on all
+host cores, in float32 like the modules of the GPU arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NFFT = 96000
+N_DELAYS = 8
+BATCH = 1
+ALIAS_DB = 30.0
+SEED = 130709
+METRIC = "freq-bins*channels/sec (Trainer.train_step)"
+UNIT = "bins*ch/s"
+WORKLOAD = "cfg2: e8_colorless_fdn 8x8 FDN (Gain->Recursion(parallelDelay,Matrix orthogonal)->Gain), nfft=96000, B=1"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU with NVML every `period` s in a thread."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        self.period, self.samples, self.reasons, self.max_mhz = period, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# ------------------------------------------------------------------------------------- model
+def build_gpu_model(device, dtype=torch.float32):
+    from flamo_b200 import workloads as W
+    from flamo_b200.optimize.dataset import DatasetColorless
+    from flamo_b200.optimize.loss import mse_loss, sparsity_loss
+    from flamo_b200.optimize.trainer import Trainer
+    from flamo_b200.processor import dsp, system
+
+    torch.manual_seed(SEED)
+    core = W.build(W.fdn(N_DELAYS), dsp, system, NFFT, ALIAS_DB, dtype=dtype, device=device)
+    model = system.Shell(core=core, input_layer=dsp.FFT(NFFT, dtype=dtype),
+                         output_layer=dsp.Transform(lambda x: torch.abs(x), dtype=dtype))
+    M = NFFT // 2 + 1
+    ds = DatasetColorless(input_shape=(1, M, 1), target_shape=(1, M, 1), expand=BATCH, device="cpu", dtype=dtype)
+    return model, ds, Trainer, mse_loss, sparsity_loss
+
+
+def cpu_reference_trainer(dtype=torch.float32):
+    """The reference algorithm (oracle port) for the same workload, float32 like the GPU arm."""
+    from flamo_b200 import workloads as W
+    from flamo_b200.processor import dsp, system
+    from oracle import flamo_oracle as O
+
+    torch.manual_seed(SEED)
+    core = W.build(W.fdn(N_DELAYS), dsp, system, NFFT, ALIAS_DB, dtype=dtype, device="cpu")
+    params = [p.detach().clone().requires_grad_(p.requires_grad) for p in core.parameters()]
+    node = O.from_desc(W.fdn(N_DELAYS))
+    fb = node.children[1].children[1]
+    crit = [(1, lambda est, tgt, ps: O.mse_loss(est, tgt)),
+            (0.2, lambda est, tgt, ps: O.sparsity_loss(O.mapped_matrix(fb, ps[2])))]
+    tr = O.OracleTrainer(node, params, NFFT, ALIAS_DB, crit, lr=1e-3)
+    M = NFFT // 2 + 1
+    x = torch.zeros(BATCH, M, 1, dtype=dtype)
+    x[:, 0, :] = 1
+    y = torch.ones(BATCH, M, 1, dtype=dtype)
+    return tr, x, y
+
+
+def time_cpu_reference(steps: int, warmup: int):
+    torch.set_num_threads(os.cpu_count())
+    tr, x, y = cpu_reference_trainer()
+    for _ in range(warmup):
+        tr.train_step(x, y)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tr.train_step(x, y)
+        ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    M = NFFT // 2 + 1
+    return BATCH * M * N_DELAYS / t, t
+
+
+def reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    steps = min(steps, 100)  # ~150 ms per step on 8 cores: keep the run within a few minutes
+    value, t = time_cpu_reference(steps, min(warmup, 10))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(warmup, 10), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "device": "host cpu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{steps} full train_step calls of the whole workload (oracle port of the "
+                                   "reference algorithm, torch CPU, all host threads)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def gpu_arm(args):
+    rank, world, local = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    from flamo_b200 import sweep
+
+    model, ds, Trainer, mse_loss, sparsity_loss = build_gpu_model(device)
+    if world > 1:
+        from flamo_b200.parallel import DataParallelTrainer as TrainerCls
+    else:
+        TrainerCls = Trainer
+    trainer = TrainerCls(model, max_epochs=1, lr=1e-3, log=False, device=device, graph=not args.no_graph)
+    trainer.register_criterion(mse_loss(nfft=NFFT, device=device), 1)
+    trainer.register_criterion(sparsity_loss(), 0.2, requires_model=True)
+
+    M = NFFT // 2 + 1
+    x_host = ds.input[:BATCH].contiguous().pin_memory()
+    y_host = ds.target[:BATCH].contiguous().pin_memory()
+    x_dev, y_dev = x_host.to(device), y_host.to(device)
+
+    # L2 flush between timed iterations: write a buffer larger than the 126 MB L2
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(steps, data, timed=True):
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        loss = None
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            starts[i].record()
+            loss = trainer.train_step(data)
+            ends[i].record()
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3, loss
+
+    # lazy state + graph capture happen in the first few calls; they are not part of W
+    for _ in range(6):
+        trainer.train_step((x_dev, y_dev))
+    warmup = max(3, args.warmup)
+    run(warmup, (x_dev, y_dev))
+
+    sampler = ClockSampler(local)
+    barrier()
+    launches0 = sweep.launch_count
+    sampler.start()
+    t_dev, loss = run(args.steps, (x_dev, y_dev))
+    barrier()
+    launches = sweep.launch_count - launches0
+    # keep the GPU under the same load long enough for at least a few clock samples
+    t_probe0 = time.time()
+    while time.time() - t_probe0 < 0.3:
+        run(20, (x_dev, y_dev))
+    clocks = sampler.stop()
+
+    # end to end: inputs in pinned host memory, H2D inside the timed region, loss read back
+    run(warmup, (x_host, y_host))
+    barrier()
+    t_e2e, _ = run(args.steps, (x_host, y_host))
+    barrier()
+
+    def reduce_max(t):
+        if world == 1:
+            return t
+        import torch.distributed as dist
+
+        v = torch.tensor([t], device=device, dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    t_dev, t_e2e = reduce_max(t_dev), reduce_max(t_e2e)
+    units_per_step = world * BATCH * M * N_DELAYS
+    value = units_per_step * args.steps / t_dev
+    e2e_value = units_per_step * args.steps / t_e2e
+
+    roof = kernel_roofline(model, x_dev, flush) if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, t = time_cpu_reference(steps=40, warmup=3)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": "40 full train_step calls of the whole workload (oracle port of the reference "
+                         f"algorithm, torch CPU float32, all host threads): {t * 1e3:.1f} ms/step"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "nfft": NFFT, "bins": M,
+                       "channels": N_DELAYS, "parallelism": f"dp{world}" if world > 1 else "single",
+                       "cuda_graph": bool(trainer.use_graph), "l2": "flushed between timed steps (192 MB fill)",
+                       "final_loss": loss},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": t_e2e / args.steps * 1e3,
+                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),
+                    "d2h_bytes_per_step": 4 * (trainer.n_loss + 1)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def kernel_roofline(model, x_dev, flush, reps=30):
+    """Duration of the dominant kernel (the backward sweep) and of the forward sweep, each launched
+    alone behind an L2 flush, CUDA events on the launching stream; algorithmic bytes per launch =
+    B*M*(8*N_in + 4*N_out) (x read as complex64, |Y| or dL/d|Y| as float32)."""
+    from flamo_b200 import sweep
+    from flamo_b200._lib import EPI_ABS
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    core = model.get_core()
+    with torch.enable_grad():  # lowered with grad enabled so the ops carry FSWEEP_F_GRAD like a real step
+        X = model.get_inputLayer()(x_dev)
+        prog = sweep.Program(NFFT, ALIAS_DB, X.dtype, X.device)
+        core._lower(prog, None)
+        segs = list(prog._segments())
+        assert len(segs) == 1 and segs[0][0] == "sweep"
+        ops, coefs, n_out = prog.flatten_segment(segs[0][1])
+    coefs = [c.detach().contiguous() for c in coefs]
+    plan = prog.plan_for(ops)
+    x4 = X.detach().reshape(X.shape[0], X.shape[1], X.shape[2], 1).contiguous()
+    y = torch.empty((x4.shape[0], x4.shape[1], n_out, 1), dtype=torch.float32, device=X.device)
+    gy = torch.ones_like(y)
+    M = X.shape[1]
+    bytes_per_launch = BATCH * M * (8 * 1 + 4 * 1)
+    backend = sweep._BACKEND
+
+    def timed(call):
+        ts = []
+        for i in range(reps + 5):
+            flush.fill_(i & 0xFF)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            call()
+            e.record()
+            torch.cuda.synchronize()
+            if i >= 5:
+                ts.append(s.elapsed_time(e) * 1e-3)
+        return statistics.mean(ts)
+
+    t_fwd = timed(lambda: backend.forward(plan, ops, coefs, x4, y, 1, 0, EPI_ABS))
+
+    def bwd():  # main backward kernel alone: no gradient buffers -> no finalize launch
+        backend.backward(plan, ops, coefs, x4, gy, [None] * len(coefs), None, 1, 0, EPI_ABS)
+
+    t_bwd = timed(bwd)
+    ach = bytes_per_launch / t_bwd / 1e9
+    return {"bound": "hbm", "kernel": "fsweep_bwd_kernel<float,8,1>", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else which,
+            "traffic": None, "us_per_launch": t_bwd * 1e6, "algorithmic_bytes_per_launch": bytes_per_launch,
+            "forward_kernel": {"kernel": "fsweep_fwd_kernel<float,8,1>", "us_per_launch": t_fwd * 1e6,
+                               "achieved": bytes_per_launch / t_fwd / 1e9, "frac": bytes_per_launch / t_fwd / 1e9 / peak},
+            "note": "config 2 moves 0.58 MB per launch and does ~2-4 kflop per bin: it is latency/FP32 bound, "
+                    "not HBM bound (SURVEY.md §8d); the HBM fraction is reported as the contract asks"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-graph", action="store_true", help="run train_step eagerly (profiling)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@ EXPORTS = [
     "fsweep_version", "fsweep_last_error", "fsweep_plan_create", "fsweep_plan_destroy",
     "fsweep_plan_num_coeffs", "fsweep_plan_coeff_numel", "fsweep_workspace_bytes",
     "fsweep_forward", "fsweep_backward", "fsweep_last_launch_count",
+    "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward",
 ]
 
 
@@ -78,6 +79,11 @@ def lib():
     L.fsweep_backward.restype = i32
     L.fsweep_backward.argtypes = [vp, C.POINTER(vp), vp, i64, vp, i64, C.POINTER(vp), vp, i64, i64, i64, i64, i64,
                                   i32, vp, C.c_size_t, vp]
+    L.fsweep_expm_max_n.restype = i32
+    L.fsweep_expm_forward.restype = i32
+    L.fsweep_expm_forward.argtypes = [vp, vp, i32, i32, vp]
+    L.fsweep_expm_backward.restype = i32
+    L.fsweep_expm_backward.argtypes = [vp, vp, vp, i32, i32, vp]
     _lib = L
     return L
 

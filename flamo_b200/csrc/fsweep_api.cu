@@ -42,9 +42,9 @@ int row_len_of(const fsweep_op_t& o) {
     case FSWEEP_OP_PDELAY:
       return 1;
     case FSWEEP_OP_SOS:
-      return o.n_sections * o.n_in * 8;
+      return o.n_sections * o.n_in * 16;
     case FSWEEP_OP_PSOS:
-      return o.n_sections * 8;
+      return o.n_sections * 16;
     default:
       return 0;
   }
@@ -279,9 +279,9 @@ extern "C" int64_t fsweep_plan_coeff_numel(const fsweep_plan_t* plan, int slot, 
     case FSWEEP_OP_PDELAY:
       return o.n_out;
     case FSWEEP_OP_SOS:
-      return (int64_t)o.n_sections * o.n_in * o.n_out * 8;
+      return (int64_t)o.n_sections * o.n_in * o.n_out * 16;
     case FSWEEP_OP_PSOS:
-      return (int64_t)o.n_sections * o.n_out * 8;
+      return (int64_t)o.n_sections * o.n_out * 16;
     case FSWEEP_OP_TABLE:
       return M * o.n_out * o.n_in;
     case FSWEEP_OP_PTABLE:

@@ -194,8 +194,8 @@ template <typename T>
 struct Ctx {
   long long k;   // absolute bin index
   T omega;       // 2*pi*k/nfft
-  cx<T> u1;      // gamma*z^-1 -/+ 1   (expansion point +1 if plus else -1)
-  cx<T> u2;      // gamma^2*z^-2 - 1
+  cx<T> u1;      // v  = gamma*z^-1 -/+ 1   (expansion point w = +1 if plus else -1)
+  cx<T> u2;      // v^2
   bool plus;     // low half of the spectrum: expand section quadratics around w = +1
   long long nfft;
   double lng;
@@ -222,8 +222,8 @@ __device__ __forceinline__ Ctx<T> make_ctx(const ProgK& P, long long k) {
     c.u1 = mk<T>((T)P.gm1 - T(2) * g * sh * sh, -g * s);
   else
     c.u1 = mk<T>(T(2) * g * ch * ch - (T)P.gm1, -g * s);
-  // w^2 - 1 = (g^2-1) - 2 g^2 sin^2 w - j 2 g^2 sin w cos w
-  c.u2 = mk<T>((T)P.g2m1 - T(2) * g2 * s * s, -T(2) * g2 * s * co);
+  c.u2 = cmul(c.u1, c.u1);
+  (void)g2;
   return c;
 }
 
@@ -251,47 +251,48 @@ __device__ __forceinline__ void load8<double>(const double* p, double (&c)[8]) {
   }
 }
 
-// one packed section -> B(w), A(w)
+// one packed section block {B(w0), B'(w0), b2, -, A(w0), A'(w0), a2, -} -> B(w), A(w) with
+// B(w) = B(w0) + B'(w0) v + b2 v^2, v = w - w0, w0 = +1 | -1: no cancellation between large terms
 template <typename T>
 __device__ __forceinline__ void section_eval(const T (&c)[8], const Ctx<T>& ctx, cx<T>& Bv, cx<T>& Av) {
-  T sb = ctx.plus ? c[0] : c[3];
-  T sa = ctx.plus ? c[4] : c[7];
-  Bv = mk<T>(fma(c[2], ctx.u2.x, fma(c[1], ctx.u1.x, sb)), fma(c[2], ctx.u2.y, c[1] * ctx.u1.y));
-  Av = mk<T>(fma(c[6], ctx.u2.x, fma(c[5], ctx.u1.x, sa)), fma(c[6], ctx.u2.y, c[5] * ctx.u1.y));
+  Bv = mk<T>(fma(c[2], ctx.u2.x, fma(c[1], ctx.u1.x, c[0])), fma(c[2], ctx.u2.y, c[1] * ctx.u1.y));
+  Av = mk<T>(fma(c[6], ctx.u2.x, fma(c[5], ctx.u1.x, c[4])), fma(c[6], ctx.u2.y, c[5] * ctx.u1.y));
 }
 
-// H = prod B / prod A with the reference's zero guard (dsp.py:1524-1525)
+// H = prod B / prod A with the reference's zero guard (dsp.py:1524-1525).  Accumulated as a product
+// of per-section ratios B_s/A_s (each O(1)) — the plain products under/overflow float32 for long
+// cascades (30-band GEQ: prod A ~ 1e-60 at DC).  prod A == 0 exactly iff some A_s == 0.
 template <typename T>
-__device__ __forceinline__ cx<T> sos_eval(const T* p, int K, long stride, const Ctx<T>& ctx, bool& guarded,
-                                          cx<T>& den_out) {
-  cx<T> num = mk<T>(1, 0), den = mk<T>(1, 0);
+__device__ __forceinline__ cx<T> sos_eval(const T* p, int K, long stride, const Ctx<T>& ctx, bool& guarded) {
+  cx<T> H = mk<T>(1, 0);
+  guarded = false;
+  p += ctx.plus ? 0 : 8;
   for (int s = 0; s < K; ++s, p += stride) {
     T c[8];
     load8<T>(p, c);
     cx<T> Bv, Av;
     section_eval<T>(c, ctx, Bv, Av);
-    num = cmul(num, Bv);
-    den = cmul(den, Av);
+    guarded |= czero(Av);
+    H = cmul(H, cmul(Bv, crcp(Av)));
   }
-  den_out = den;
-  guarded = czero(den);
   if (guarded) return mk<T>(eps_of<T>(), T(0));
-  return cmul(num, crcp(den));
+  return H;
 }
 
-// numerator product with section `skip` left out (rare path: a section is exactly zero at this bin)
+// cascade with section `skip` left out (rare path: a numerator section is exactly zero at this bin)
 template <typename T>
-__device__ __forceinline__ cx<T> sos_num_without(const T* p, int K, long stride, const Ctx<T>& ctx, int skip) {
-  cx<T> num = mk<T>(1, 0);
+__device__ __forceinline__ cx<T> sos_eval_without(const T* p, int K, long stride, const Ctx<T>& ctx, int skip) {
+  cx<T> H = mk<T>(1, 0);
+  p += ctx.plus ? 0 : 8;
   for (int s = 0; s < K; ++s, p += stride) {
     if (s == skip) continue;
     T c[8];
     load8<T>(p, c);
     cx<T> Bv, Av;
     section_eval<T>(c, ctx, Bv, Av);
-    num = cmul(num, Bv);
+    H = cmul(H, cmul(Bv, crcp(Av)));
   }
-  return num;
+  return H;
 }
 
 __device__ __forceinline__ float exp_t(float a) { return expf(a); }
@@ -355,6 +356,8 @@ __device__ __forceinline__ void sos_grad(const OpK& op, const T* p, long stride,
                                          cx<T> gh, const Acc<T>& acc, int row, int e0) {
   const int K = op.K;
   const T* p0 = p;
+  p += ctx.plus ? 0 : 8;
+  const int blk = ctx.plus ? 0 : 8;
   for (int s = 0; s < K; ++s, p += stride) {
     T c[8];
     load8<T>(p, c);
@@ -362,11 +365,8 @@ __device__ __forceinline__ void sos_grad(const OpK& op, const T* p, long stride,
     section_eval<T>(c, ctx, Bv, Av);
     cx<T> qb;
     if (czero(Bv)) {
-      // dH/dB_s = prod_{t != s} B_t / prod A  (H itself is 0 at this bin)
-      bool gd;
-      cx<T> den;
-      (void)sos_eval<T>(p0, K, stride, ctx, gd, den);
-      qb = cmul(sos_num_without<T>(p0, K, stride, ctx, s), crcp(den));
+      // dH/dB_s = prod_{t != s} (B_t/A_t) / A_s  (H itself is 0 at this bin)
+      qb = cmul(sos_eval_without<T>(p0, K, stride, ctx, s), crcp(Av));
     } else {
       qb = cmul(H, crcp(Bv));
     }
@@ -374,11 +374,11 @@ __device__ __forceinline__ void sos_grad(const OpK& op, const T* p, long stride,
     qa.x = -qa.x;
     qa.y = -qa.y;
     cx<T> rb = cmulc(gh, qb), ra = cmulc(gh, qa);
-    int e = e0 + s * op.row_len / K;  // row_len = K * per-section stride of this row
-    acc.add(op, row, e + (ctx.plus ? 0 : 3), rb.x);
+    int e = e0 + s * (op.row_len / K) + blk;  // row_len = K * per-section stride of this row
+    acc.add(op, row, e + 0, rb.x);
     acc.add(op, row, e + 1, rb.x * ctx.u1.x + rb.y * ctx.u1.y);
     acc.add(op, row, e + 2, rb.x * ctx.u2.x + rb.y * ctx.u2.y);
-    acc.add(op, row, e + (ctx.plus ? 4 : 7), ra.x);
+    acc.add(op, row, e + 4, ra.x);
     acc.add(op, row, e + 5, ra.x * ctx.u1.x + ra.y * ctx.u1.y);
     acc.add(op, row, e + 6, ra.x * ctx.u2.x + ra.y * ctx.u2.y);
   }
@@ -393,11 +393,9 @@ __device__ __forceinline__ cx<T> op_entry(const OpK& op, const Ctx<T>& ctx, int 
       return mk<T>(__ldg(reinterpret_cast<const T*>(op.coef) + m * op.n_in + n), T(0));
     case FSWEEP_OP_DELAY:
       return delay_eval<T>(__ldg(reinterpret_cast<const double*>(op.coef) + m * op.n_in + n), op.flags, ctx);
-    case FSWEEP_OP_SOS: {
-      cx<T> den;
-      return sos_eval<T>(reinterpret_cast<const T*>(op.coef) + ((size_t)n * op.n_out + m) * 8, op.K,
-                         (long)op.n_in * op.n_out * 8, ctx, guard, den);
-    }
+    case FSWEEP_OP_SOS:
+      return sos_eval<T>(reinterpret_cast<const T*>(op.coef) + ((size_t)n * op.n_out + m) * 16, op.K,
+                         (long)op.n_in * op.n_out * 16, ctx, guard);
     case FSWEEP_OP_TABLE: {
       const T* t = reinterpret_cast<const T*>(op.coef) + 2 * (((size_t)ctx.k * op.n_out + m) * op.n_in + n);
       return mk<T>(__ldg(t), __ldg(t + 1));
@@ -416,11 +414,8 @@ __device__ __forceinline__ cx<T> op_diag(const OpK& op, const Ctx<T>& ctx, int m
       return mk<T>(__ldg(reinterpret_cast<const T*>(op.coef) + m), T(0));
     case FSWEEP_OP_PDELAY:
       return delay_eval<T>(__ldg(reinterpret_cast<const double*>(op.coef) + m), op.flags, ctx);
-    case FSWEEP_OP_PSOS: {
-      cx<T> den;
-      return sos_eval<T>(reinterpret_cast<const T*>(op.coef) + (size_t)m * 8, op.K, (long)op.n_out * 8, ctx, guard,
-                         den);
-    }
+    case FSWEEP_OP_PSOS:
+      return sos_eval<T>(reinterpret_cast<const T*>(op.coef) + (size_t)m * 16, op.K, (long)op.n_out * 16, ctx, guard);
     case FSWEEP_OP_PTABLE: {
       const T* t = reinterpret_cast<const T*>(op.coef) + 2 * ((size_t)ctx.k * op.n_out + m);
       return mk<T>(__ldg(t), __ldg(t + 1));
@@ -514,8 +509,8 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
               break;
             case FSWEEP_OP_SOS:
               if (!((gmask >> n) & 1u))
-                sos_grad<T>(op, reinterpret_cast<const T*>(op.coef) + ((size_t)n * op.n_out + lane) * 8,
-                            (long)op.n_in * op.n_out * 8, ctx, h, gh, acc, lane, n * 8);
+                sos_grad<T>(op, reinterpret_cast<const T*>(op.coef) + ((size_t)n * op.n_out + lane) * 16,
+                            (long)op.n_in * op.n_out * 16, ctx, h, gh, acc, lane, n * 16);
               break;
             case FSWEEP_OP_TABLE:
               if (acc.valid && op.gtab) {
@@ -571,7 +566,7 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
           break;
         case FSWEEP_OP_PSOS:
           if (!gd)
-            sos_grad<T>(op, reinterpret_cast<const T*>(op.coef) + (size_t)lane * 8, (long)op.n_out * 8, ctx, h, gh,
+            sos_grad<T>(op, reinterpret_cast<const T*>(op.coef) + (size_t)lane * 16, (long)op.n_out * 16, ctx, h, gh,
                         acc, lane, 0);
           break;
         case FSWEEP_OP_PTABLE:
@@ -993,12 +988,12 @@ __global__ void fsweep_finalize_kernel(const __grid_constant__ FinalizeArgs F) {
     // map (row, i) -> index in the caller's layout
     size_t o;
     if (op.kind == FSWEEP_OP_SOS) {
-      // i = (s * n_in + n) * 8 + slot  ->  ((s * n_in + n) * n_out + row) * 8 + slot
-      int slot = i & 7, sn = i >> 3;
-      o = ((size_t)sn * op.n_out + row) * 8 + slot;
+      // i = (s * n_in + n) * 16 + slot  ->  ((s * n_in + n) * n_out + row) * 16 + slot
+      int slot = i & 15, sn = i >> 4;
+      o = ((size_t)sn * op.n_out + row) * 16 + slot;
     } else if (op.kind == FSWEEP_OP_PSOS) {
-      int slot = i & 7, sidx = i >> 3;
-      o = ((size_t)sidx * op.n_out + row) * 8 + slot;
+      int slot = i & 15, sidx = i >> 4;
+      o = ((size_t)sidx * op.n_out + row) * 16 + slot;
     } else if (diag) {
       o = row;
     } else {

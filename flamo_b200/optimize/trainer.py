@@ -38,7 +38,8 @@ class Trainer:
         params = list(self.net.parameters())
         if self.use_graph:
             # capturable Adam keeps `step` and `lr` on the device so a captured step can be replayed
-            self.optimizer = torch.optim.Adam(params, lr=torch.tensor(float(lr), device=device), capturable=True)
+            self.optimizer = torch.optim.Adam(params, lr=torch.tensor(float(lr), device=device, dtype=torch.float64),
+                                              capturable=True)
         else:
             self.optimizer = torch.optim.Adam(params, lr=self.lr)
         self.n_loss = 0
@@ -104,13 +105,25 @@ class Trainer:
             total = total + alpha * t
         return total, parts
 
-    # -- eager step (any device) -----------------------------------------------------------------
-    def _eager_train_step(self, inputs, targets):
-        self.optimizer.zero_grad()
+    # -- one optimisation step, as a pure device-side function (captured or eager) --------------------
+    def _zero_grad(self):
+        self.optimizer.zero_grad(set_to_none=True)
+
+    def _sync(self, vals):
+        """Hook between backward and the optimizer step (multi-GPU trainers all-reduce here)."""
+        return vals
+
+    def _train_core(self, inputs, targets):
         loss, parts = self._losses(inputs, targets)
         loss.backward()
+        vals = torch.stack([p.detach().reshape(()) for p in parts] + [loss.detach().reshape(())])
+        vals = self._sync(vals)
         self.optimizer.step()
-        vals = torch.stack([p.detach().reshape(()) for p in parts] + [loss.detach().reshape(())]).tolist()
+        return vals
+
+    def _eager_train_step(self, inputs, targets):
+        self._zero_grad()
+        vals = self._train_core(inputs, targets).tolist()
         self._log(self.train_loss_log, vals[:-1])
         return vals[-1]
 
@@ -124,23 +137,27 @@ class Trainer:
         if n_warm < 3:  # eager warm-up: lazy state (Adam moments, plans, cuFFT plans, caches) must exist
             self._warm[key] = n_warm + 1
             return None
+        from .. import sweep
+
         static_in, static_tg = inputs.clone(), targets.clone()
         graph = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
+        self._zero_grad()
+        n0 = sweep.launch_count
         try:
             with torch.cuda.graph(graph):
-                loss, parts = self._losses(static_in, static_tg)
-                loss.backward()
-                self.optimizer.step()
-                out = torch.stack([p.detach().reshape(()) for p in parts] + [loss.detach().reshape(())])
+                self._zero_grad_captured()
+                out = self._train_core(static_in, static_tg)
         except Exception as e:  # keep training eagerly (still on the CUDA sweep) if capture is impossible
             warnings.warn(f"CUDA-graph capture of the training step failed ({e}); continuing without graph.")
             self.use_graph = False
             torch.cuda.synchronize()
             return None
-        g = (graph, static_in, static_tg, out)
+        g = (graph, static_in, static_tg, out, sweep.launch_count - n0)  # sweep kernels per replay
         self._graphs[key] = g
         return g
+
+    def _zero_grad_captured(self):
+        """Inside the captured region: nothing to do when grads are (re)allocated by backward."""
 
     def train_step(self, data):
         inputs, targets = data
@@ -149,10 +166,16 @@ class Trainer:
         if self.use_graph:
             g = self._graph_for(inputs, targets)
             if g is not None:
-                graph, static_in, static_tg, out = g
+                from .. import sweep
+
+                graph, static_in, static_tg, out, n_kernels = g
                 static_in.copy_(inputs, non_blocking=True)
                 static_tg.copy_(targets, non_blocking=True)
                 graph.replay()
+                sweep.launch_count += n_kernels
+                inval = getattr(self.net, "_invalidate_caches", None)
+                if inval is not None:  # parameters changed on the device without a version bump
+                    inval()
                 vals = out.tolist()  # the step's single device->host read
                 self._log(self.train_loss_log, vals[:-1])
                 return vals[-1]

@@ -54,9 +54,9 @@ class FFT(Transform):
 
     def __init__(self, nfft: int = 2 ** 11, norm: str = "backward", dtype: torch.dtype = torch.float32):
         self.nfft, self.norm = nfft, norm
-        super().__init__(transform=self._apply, dtype=dtype)
+        super().__init__(transform=self._transform, dtype=dtype)
 
-    def _apply(self, x):
+    def _transform(self, x):
         return torch.fft.rfft(x, n=self.nfft, dim=1, norm=self.norm)
 
 
@@ -65,9 +65,9 @@ class iFFT(Transform):
 
     def __init__(self, nfft: int = 2 ** 11, norm: str = "backward", dtype: torch.dtype = torch.float32):
         self.nfft, self.norm = nfft, norm
-        super().__init__(transform=self._apply, dtype=dtype)
+        super().__init__(transform=self._transform, dtype=dtype)
 
-    def _apply(self, x):
+    def _transform(self, x):
         return torch.fft.irfft(x, n=self.nfft, dim=1, norm=self.norm)
 
 
@@ -83,9 +83,9 @@ class FFTAntiAlias(Transform):
                  device: Optional[str] = None, dtype: torch.dtype = torch.float32):
         self.nfft, self.norm = nfft, norm
         self.alias_envelope = _alias_envelope(nfft, alias_decay_db, device, dtype)
-        super().__init__(transform=self._apply, device=device, dtype=dtype)
+        super().__init__(transform=self._transform, device=device, dtype=dtype)
 
-    def _apply(self, x):
+    def _transform(self, x):
         return torch.fft.rfft(x * self.alias_envelope.view(1, -1, 1), n=self.nfft, dim=1, norm=self.norm)
 
 
@@ -96,9 +96,9 @@ class iFFTAntiAlias(Transform):
                  device: Optional[str] = None, dtype: torch.dtype = torch.float32):
         self.nfft, self.norm = nfft, norm
         self.alias_envelope = _alias_envelope(nfft, alias_decay_db, device, dtype)
-        super().__init__(transform=self._apply, device=device, dtype=dtype)
+        super().__init__(transform=self._transform, device=device, dtype=dtype)
 
-    def _apply(self, x):
+    def _transform(self, x):
         return torch.fft.irfft(x, n=self.nfft, dim=1, norm=self.norm) * self.alias_envelope.view(1, -1, 1)
 
 
@@ -276,7 +276,7 @@ class Matrix(Gain):
             self.map = _identity
         elif t == "orthogonal":
             assert N == self.size[1], "Matrix must be square to be orthogonal"
-            self.map = lambda x: torch.matrix_exp(skew_matrix(x))
+            self.map = self._orthogonal_map
         elif t == "hadamard":
             assert N == self.size[1], "Matrix must be square to be Hadamard"
             assert N % 2 == 0, "Matrix must have even dimensions to be Hadamard"
@@ -288,7 +288,34 @@ class Matrix(Gain):
         else:
             raise ValueError(f"unknown matrix_type {t}")
 
+    def _orthogonal_map(self, x):
+        """matrix_exp(skew(x)).  On CUDA the library's capture-safe kernel is used; the result is
+        memoised per parameter version so that the sweep and parameter-only criteria (sparsity_loss
+        calls map(param) again, reference loss.py:41-42) share one evaluation per step."""
+        if not sweep.OrthogonalMap.supported(x):
+            return torch.matrix_exp(skew_matrix(x))
+        key = (x._version, torch.is_grad_enabled() and x.requires_grad)
+        if x is self.param:
+            hit = self._expm_cache
+            if hit is not None and hit[0] == key:
+                return hit[1]
+        out = sweep.OrthogonalMap.apply(x)
+        if x is self.param:
+            self._expm_cache = (key, out)
+        return out
+
+    def _up(self, param):
+        # the orthogonal map upcasts internally; handing it `param` itself lets the memo above hit
+        if self.matrix_type == "orthogonal" and sweep.OrthogonalMap.supported(param):
+            return param
+        return super()._up(param)
+
+    def invalidate_cache(self):
+        """Drop the memoised map (parameters changed without a version bump, e.g. by a graph replay)."""
+        self._expm_cache = None
+
     def initialize_class(self):
+        self._expm_cache = None
         self.check_param_shape()
         self.get_io()
         self.matrix_gallery()

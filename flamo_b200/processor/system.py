@@ -356,7 +356,14 @@ class Shell(nn.Module):
         return (in_ch if in_ch is not None else c_in), (out_ch if out_ch is not None else c_out)
 
     # -- evaluation ------------------------------------------------------------------------------
+    def _invalidate_caches(self):
+        for m in self.modules():
+            f = getattr(m, "invalidate_cache", None)
+            if f is not None:
+                f()
+
     def forward(self, x, ext_param=None):
+        self._invalidate_caches()  # memoised maps live for one forward (+ its criteria) only
         x = self.__input_layer(x)
         core, out = self.__core, self.__output_layer
         if hasattr(core, "_lower") and torch.is_tensor(x) and x.is_complex():

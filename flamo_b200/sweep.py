@@ -61,17 +61,17 @@ class CudaBackend:
 
     def forward(self, plan, ops, coefs, x, y, cols, bin_begin, epilogue):
         B, nb = x.shape[0], x.shape[1]
-        plan.forward([c.data_ptr() for c in coefs], x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), B, cols,
-                     bin_begin, nb, epilogue, self._stream(x))
+        return plan.forward([c.data_ptr() for c in coefs], x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), B,
+                            cols, bin_begin, nb, epilogue, self._stream(x))
 
     def backward(self, plan, ops, coefs, x, gy, grads, gx, cols, bin_begin, epilogue):
         B, nb = x.shape[0], x.shape[1]
         ws_bytes = plan.workspace_bytes(B, cols, nb)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        plan.backward([c.data_ptr() for c in coefs], x.data_ptr(), x.stride(0), gy.data_ptr(), gy.stride(0),
-                      [g.data_ptr() if g is not None else None for g in grads],
-                      gx.data_ptr() if gx is not None else None, gx.stride(0) if gx is not None else 0, B, cols,
-                      bin_begin, nb, epilogue, ws.data_ptr(), ws_bytes, self._stream(x))
+        return plan.backward([c.data_ptr() for c in coefs], x.data_ptr(), x.stride(0), gy.data_ptr(), gy.stride(0),
+                             [g.data_ptr() if g is not None else None for g in grads],
+                             gx.data_ptr() if gx is not None else None, gx.stride(0) if gx is not None else 0, B,
+                             cols, bin_begin, nb, epilogue, ws.data_ptr(), ws_bytes, self._stream(x))
 
 
 _BACKEND = CudaBackend()  # tests/ may swap this for a CPU emulator to exercise the host logic without a GPU
@@ -111,8 +111,7 @@ class SweepFunction(torch.autograd.Function):
         y = torch.empty((B, nb, n_out, cols), dtype=real if epilogue == EPI_ABS else x.dtype, device=x.device)
         coefs = tuple(c.contiguous() for c in coefs)
         if nb > 0:
-            _BACKEND.forward(plan, ops, coefs, x, y, cols, bin_begin, epilogue)
-            launch_count += 1
+            launch_count += _BACKEND.forward(plan, ops, coefs, x, y, cols, bin_begin, epilogue) or 0
         ctx.plan, ctx.ops, ctx.epilogue, ctx.bin_begin = plan, ops, epilogue, bin_begin
         ctx.save_for_backward(x, *coefs)
         return y
@@ -134,8 +133,8 @@ class SweepFunction(torch.autograd.Function):
                 grads.append(None)
         gx = torch.empty_like(x, memory_format=torch.contiguous_format) if need[0] else None
         if nb > 0:
-            _BACKEND.backward(ctx.plan, ctx.ops, coefs, x, gy, grads, gx, cols, ctx.bin_begin, ctx.epilogue)
-            launch_count += 2
+            launch_count += _BACKEND.backward(ctx.plan, ctx.ops, coefs, x, gy, grads, gx, cols, ctx.bin_begin,
+                                              ctx.epilogue) or 0
         else:
             grads = [None if g is None else torch.zeros_like(g) for g in grads]
         return (gx, None, None, None, None, None, *grads)
@@ -205,6 +204,28 @@ class Program:
         if seg:
             yield ("sweep", seg)
 
+    @staticmethod
+    def flatten_segment(payload):
+        """One launch worth of items -> (flat op tuples, coefficient tensors in slot order, n_out)."""
+        ops, coefs = [], []
+        for it in payload:
+            if it[0] == "leaf":
+                ops.append(it[1])
+                coefs.append(it[2])
+            else:
+                _, n_out, n_in, ff, fb = it
+                ops.append((OP_RECURSION, n_out, n_in, 0, 0, len(ff), len(fb), 0))
+                for l in ff + fb:
+                    ops.append(l[1])
+                    coefs.append(l[2])
+        last = payload[-1]
+        n_out = last[1][1] if last[0] == "leaf" else last[1]
+        return tuple(ops), coefs, n_out
+
+    def plan_for(self, ops, cdtype=None):
+        cdtype = cdtype or self.cdtype
+        return _get_plan(ops, self.nfft, self.alias_decay_db, _lib.C64 if cdtype == torch.complex64 else _lib.C128)
+
     def run(self, x: torch.Tensor, epilogue: int = EPI_NONE) -> torch.Tensor:
         if not x.is_complex():
             raise TypeError("sweep input must be complex (bin-domain) — put a dsp.FFT input layer in front")
@@ -231,20 +252,7 @@ class Program:
             if tag == "eager":
                 x4 = payload(x4.reshape(x4.shape[:3] + trail)).reshape(x4.shape[0], x4.shape[1], -1, cols)
                 continue
-            ops, coefs = [], []
-            for it in payload:
-                if it[0] == "leaf":
-                    ops.append(it[1])
-                    coefs.append(it[2])
-                else:
-                    _, n_out, n_in, ff, fb = it
-                    ops.append((OP_RECURSION, n_out, n_in, 0, 0, len(ff), len(fb), 0))
-                    for l in ff + fb:
-                        ops.append(l[1])
-                        coefs.append(l[2])
-            ops = tuple(ops)
-            last = payload[-1]
-            n_out = last[1][1] if last[0] == "leaf" else last[1]
+            ops, coefs, n_out = self.flatten_segment(payload)
             epi = epilogue if si == len(segs) - 1 else EPI_NONE
             plan = _get_plan(ops, self.nfft, self.alias_decay_db, dtype)
             x4 = SweepFunction.apply(x4, plan, ops, epi, bin_begin, n_out, *coefs)
@@ -253,12 +261,48 @@ class Program:
         return x4.reshape(x4.shape[:3] + trail)
 
 
+class OrthogonalMap(torch.autograd.Function):
+    """exp(triu(P,1) - triu(P,1)^T) on the device without a host read-back (libfsweep fsweep_expm_*),
+    the orthogonal map of dsp.Matrix (reference dsp.py:649)."""
+
+    @staticmethod
+    def supported(P: torch.Tensor) -> bool:
+        return (P.is_cuda and P.dim() == 2 and P.shape[0] == P.shape[1]
+                and P.shape[0] <= _lib.lib().fsweep_expm_max_n())
+
+    @staticmethod
+    def forward(ctx, P):
+        global launch_count
+        P64 = P.detach().to(torch.float64).contiguous()
+        E = torch.empty_like(P64)
+        _lib.check(_lib.lib().fsweep_expm_forward(P64.data_ptr(), E.data_ptr(), P64.shape[0], 1,
+                                                   torch.cuda.current_stream(P.device).cuda_stream))
+        launch_count += 1
+        ctx.save_for_backward(P64)
+        ctx.in_dtype = P.dtype
+        return E.to(P.dtype)
+
+    @staticmethod
+    def backward(ctx, G):
+        global launch_count
+        (P64,) = ctx.saved_tensors
+        G64 = G.to(torch.float64).contiguous()
+        gP = torch.empty_like(P64)
+        _lib.check(_lib.lib().fsweep_expm_backward(P64.data_ptr(), G64.data_ptr(), gP.data_ptr(), P64.shape[0], 1,
+                                                    torch.cuda.current_stream(G.device).cuda_stream))
+        launch_count += 1
+        return gP.to(ctx.in_dtype)
+
+
 def pack_sections(b: torch.Tensor, a: torch.Tensor, parallel: bool, real: torch.dtype) -> torch.Tensor:
-    """(3, K, N_out, N_in) taps (or (3, K, N) for parallel) -> kernel layout [K][N_in][N_out][8]
-    ([K][N][8]) of {b0+b1+b2, b1, b2, b0-b1+b2, a0+a1+a2, a1, a2, a0-a1+a2} (include/fsweep.h).
-    Done in the taps' own (float64) precision, then cast; differentiable."""
-    packed = torch.stack((b[0] + b[1] + b[2], b[1], b[2], b[0] - b[1] + b[2],
-                          a[0] + a[1] + a[2], a[1], a[2], a[0] - a[1] + a[2]), dim=-1)
+    """(3, K, N_out, N_in) taps (or (3, K, N) for parallel) -> kernel layout [K][N_in][N_out][2][8]
+    ([K][N][2][8]): per section the Taylor coefficients of B and A around w0 = +1 and w0 = -1
+    (include/fsweep.h, FSWEEP_OP_SOS).  Formed in the taps' own (float64) precision, then cast;
+    differentiable, so autograd maps the kernel's packed gradient back onto (b, a)."""
+    z = torch.zeros_like(b[0])
+    plus = torch.stack((b[0] + b[1] + b[2], b[1] + 2 * b[2], b[2], z, a[0] + a[1] + a[2], a[1] + 2 * a[2], a[2], z), -1)
+    minus = torch.stack((b[0] - b[1] + b[2], b[1] - 2 * b[2], b[2], z, a[0] - a[1] + a[2], a[1] - 2 * a[2], a[2], z), -1)
+    packed = torch.stack((plus, minus), dim=-2)  # (K, ..., 2, 8)
     if not parallel:
-        packed = packed.permute(0, 2, 1, 3)  # (K, N_out, N_in, 8) -> (K, N_in, N_out, 8)
+        packed = packed.permute(0, 2, 1, 3, 4)  # (K, N_out, N_in, 2, 8) -> (K, N_in, N_out, 2, 8)
     return packed.to(real).contiguous()

@@ -76,13 +76,17 @@ enum fsweep_op_kind {
    *   H[m][n] = prod_s B_s / prod_s A_s,  B_s = b0 + b1*g*z^-1 + b2*g^2*z^-2  (g = gamma),
    *   H = eps if |prod A| == 0   (dsp.py:1520-1526 = 2226-2232 = 2587-2593: Biquad, SVF, GEQ
    *   after their maps; equals the reference's zero-padded rfft of the 3 taps).
-   * coef: real[K][n_in][n_out][8] "packed sections":
-   *   {b0+b1+b2, b1, b2, b0-b1+b2, a0+a1+a2, a1, a2, a0-a1+a2}
-   * The tap sums let the kernel expand each quadratic around w=+1 (low bins) or w=-1 (high
-   * bins) without cancellation; grad has the same packed layout (chain rule through the
-   * linear packing is done by the caller). */
+   * coef: real[K][n_in][n_out][2][8] "packed sections": two Taylor blocks per section,
+   *   block 0 (used for bins with cos(omega_k) >= 0, expansion point w0 = +1):
+   *     {b0+b1+b2, b1+2*b2, b2, 0,  a0+a1+a2, a1+2*a2, a2, 0}
+   *   block 1 (cos(omega_k) < 0, w0 = -1):
+   *     {b0-b1+b2, b1-2*b2, b2, 0,  a0-a1+a2, a1-2*a2, a2, 0}
+   * so that B(w) = B(w0) + B'(w0) v + b2 v^2 with v = w - w0 formed without cancellation
+   * (w = gamma*z^-1).  The caller forms the sums in float64.  grad has the same layout: each bin
+   * contributes d/d{B(w0), B'(w0), b2, A(w0), A'(w0), a2} to its block; the chain rule through the
+   * (linear) packing is the caller's. */
   FSWEEP_OP_SOS = 3,
-  /* diagonal cascade (parallelBiquad / parallelSVF / parallelGEQ).  coef: real[K][n][8]. */
+  /* diagonal cascade (parallelBiquad / parallelSVF / parallelGEQ).  coef: real[K][n][2][8]. */
   FSWEEP_OP_PSOS = 4,
   /* dense delays: H[m][n] = gamma^d * exp(-j*omega_k*d), d = coef[m][n] samples
    * (dsp.py:3356-3374).  With FSWEEP_F_ISINT d is rounded and the phase index (k*d mod nfft)
@@ -152,6 +156,15 @@ FSWEEP_API int fsweep_backward(const fsweep_plan_t* plan, const void* const* coe
                     void* grad_x, int64_t gx_batch_stride, /* device or NULL */
                     int64_t batch, int64_t cols, int64_t bin_begin, int64_t n_bins,
                     int epilogue, void* workspace, size_t workspace_bytes, void* stream);
+
+/* E = exp(S) for the orthogonal map of dsp.Matrix (reference dsp.py:649, functional.py:42-56):
+ * skew != 0: S = triu(P,1) - triu(P,1)^T, else S = P.  P, E, G, gP: device double[n][n] row-major.
+ * backward: gP = dL/dP given G = dL/dE.  One CTA, float64, entirely on the device (torch.matrix_exp
+ * reads the norm back to the host, which cannot be captured in a CUDA graph).
+ * n <= 2*fsweep_expm_max_n() for forward, n <= fsweep_expm_max_n() for backward. */
+FSWEEP_API int fsweep_expm_max_n(void);
+FSWEEP_API int fsweep_expm_forward(const double* P, double* E, int n, int skew, void* stream);
+FSWEEP_API int fsweep_expm_backward(const double* P, const double* G, double* gP, int n, int skew, void* stream);
 
 /* number of kernels the last forward / backward call of this thread enqueued (bench bookkeeping) */
 FSWEEP_API int fsweep_last_launch_count(void);

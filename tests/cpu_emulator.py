@@ -46,20 +46,17 @@ def _response(op, coef, k, nfft, lng):
         else:
             ph = om.view(-1, *[1] * d.dim()) * d.unsqueeze(0)
         return torch.exp(lng * d).unsqueeze(0) * torch.exp(-1j * ph)
-    # SOS / PSOS: packed sections [K][n_in][n_out][8] / [K][n][8]
+    # SOS / PSOS: packed sections [K][n_in][n_out][2][8] / [K][n][2][8]
     c = coef.double()
     g = math.exp(lng)
     w = g * torch.exp(-1j * om)
     plus = torch.cos(om) >= 0
-    u1 = torch.where(plus, w - 1, w + 1)
-    u2 = w * w - 1
-    shape = (-1,) + (1,) * (c.dim() - 1)
-    u1, u2, plus = u1.view(shape), u2.view(shape), plus.view(shape)
-    cc = c.unsqueeze(0)
-    sb = torch.where(plus, cc[..., 0], cc[..., 3])
-    sa = torch.where(plus, cc[..., 4], cc[..., 7])
-    B = sb + cc[..., 1] * u1 + cc[..., 2] * u2  # (nb, K, n_in, n_out) | (nb, K, n)
-    A = sa + cc[..., 5] * u1 + cc[..., 6] * u2
+    v = torch.where(plus, w - 1, w + 1)
+    shape = (-1,) + (1,) * (c.dim() - 2)
+    v, plus = v.view(shape), plus.view(shape)
+    cc = torch.where(plus.unsqueeze(-1), c[..., 0, :].unsqueeze(0), c[..., 1, :].unsqueeze(0))  # (nb, K, ..., 8)
+    B = cc[..., 0] + cc[..., 1] * v + cc[..., 2] * v * v  # (nb, K, n_in, n_out) | (nb, K, n)
+    A = cc[..., 4] + cc[..., 5] * v + cc[..., 6] * v * v
     num, den = B.prod(dim=1), A.prod(dim=1)
     H = torch.where(den.abs() != 0, num / den, torch.full_like(num, torch.finfo(torch.float64).eps))
     if kind == OP_SOS:

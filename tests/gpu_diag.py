@@ -5,7 +5,11 @@ import traceback
 
 import torch
 
-sys.path.insert(0, "tests")
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases as C  # noqa: E402
 from test_gpu_parity import WIDE, run_case  # noqa: E402
 
@@ -20,7 +24,7 @@ for dtype in (torch.float32, torch.float64):
         try:
             case, g, Y, ferr, gerrs, missing = run_case(name, dtype)
             worst = max(gerrs.values()) if gerrs else 0.0
-            print(f"{str(dtype)[6:]:8s} {name:26s} fwd {ferr:.2e}  grad {worst:.2e} {dict((k, float(f'{v:.1e}')) for k, v in gerrs.items())}"
+            print(f"{str(dtype)[6:]:8s} {name:26s} fwd {ferr:.2e} |mag| {run_case.mag_err:.2e}  grad {worst:.2e} {dict((k, float(f'{v:.1e}')) for k, v in gerrs.items())}"
                   f" missing={missing}  ({time.time() - t0:.1f}s)", flush=True)
         except Exception as e:
             print(f"{str(dtype)[6:]:8s} {name:26s} EXC {type(e).__name__}: {e}", flush=True)

@@ -1,0 +1,50 @@
+"""GPU: the capture-safe expm(skew(P)) kernel against torch.matrix_exp and its autograd."""
+import pytest
+import torch
+
+from flamo_b200 import sweep
+from flamo_b200.functional import skew_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [1, 2, 6, 8, 13, 16, 32, 48])
+@pytest.mark.parametrize("scale", [0.05, 1.0, 7.0])
+def test_expm_matches_torch(n, scale):
+    torch.manual_seed(n)
+    P = (scale * torch.randn(n, n, dtype=torch.float64, device="cuda")).requires_grad_(True)
+    Q = P.detach().clone().requires_grad_(True)
+    E = sweep.OrthogonalMap.apply(P)
+    Er = torch.matrix_exp(skew_matrix(Q))
+    import scipy.linalg
+
+    Es = torch.tensor(scipy.linalg.expm(skew_matrix(Q.detach()).cpu().numpy()), device="cuda")
+    assert torch.allclose(E, Es, rtol=0, atol=2e-13 * max(1.0, scale * n))
+    assert torch.allclose(E, Er, rtol=0, atol=1e-9)  # sanity only: torch picks a low Taylor degree for small norms
+    assert torch.allclose(E @ E.T, torch.eye(n, dtype=torch.float64, device="cuda"), atol=1e-11)
+    G = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    (E * G).sum().backward()
+    (Er * G).sum().backward()
+    assert torch.allclose(P.grad, Q.grad, rtol=1e-10, atol=1e-11 * float(Q.grad.abs().max() + 1))
+    assert float(P.grad.tril().abs().max()) == 0.0  # only the strict upper triangle is a free parameter
+
+
+def test_expm_float32_parameter_and_capture():
+    P = torch.randn(8, 8, device="cuda", requires_grad=True)
+    E = sweep.OrthogonalMap.apply(P)
+    assert E.dtype == torch.float32
+    assert torch.allclose(E, torch.matrix_exp(skew_matrix(P.detach().double())).float(), atol=1e-6)
+    del E  # an autograd graph kept alive from before the capture would pin P's AccumulateGrad to the default stream
+    for _ in range(2):  # warm-up on the current stream, like Trainer._graph_for
+        sweep.OrthogonalMap.apply(P).sum().backward()
+    P.grad = None
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = sweep.OrthogonalMap.apply(P)
+        out.square().sum().backward()
+    with torch.no_grad():
+        P.add_(0.1)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.allclose(out, torch.matrix_exp(skew_matrix(P.detach().double())).float(), atol=1e-6)
+    assert P.grad is not None and torch.isfinite(P.grad).all()
