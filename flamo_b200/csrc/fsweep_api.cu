@@ -171,8 +171,9 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   P.n_ops = p->n_coeffs;
   const size_t real_sz = dtype == FSWEEP_C64 ? 4 : 8;
 
-  int acc_per_lane = 0, acc_total = 0;
+  int acc_per_lane = 0, acc_total = 0, h_total = 0;
   p->any_global = p->any_acc = false;
+  P.needs_ctx = 0;
   for (size_t s = 0; s < order.size(); ++s) {
     const fsweep_op_t& o = ops[order[s]];
     p->leaf.push_back(o);
@@ -183,6 +184,9 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
     k.K = o.n_sections;
     k.flags = o.flags;
     k.row_len = row_len_of(o);
+    k.h_off = h_total;
+    h_total += kind_is_diag(o.kind) ? 1 : o.n_in;
+    if (o.kind == FSWEEP_OP_SOS || o.kind == FSWEEP_OP_PSOS) P.needs_ctx = 1;
     k.acc_off = acc_total;
     k.row_off = 0;
     k.acc_mode = ACC_NONE;
@@ -214,6 +218,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   }
   P.acc_per_lane = acc_per_lane;
   P.acc_total = acc_total;
+  P.h_total = h_total;
 
   const std::vector<int>& first_chain = !pre.empty() ? pre : (rec >= 0 ? ff : post);
   const std::vector<int>& last_chain = !post.empty() ? post : (rec >= 0 ? ff : pre);
@@ -295,7 +300,9 @@ namespace {
 
 int cc_of(int64_t ncols) { return ncols == 1 ? 1 : 4; }
 
-size_t smem_fwd(const fsweep_plan* p) { return (size_t)p->G * BLOCK * 2 * (p->dtype == FSWEEP_C64 ? 4 : 8); }
+size_t smem_fwd(const fsweep_plan* p) {
+  return (size_t)p->prog.h_total * BLOCK * 2 * (p->dtype == FSWEEP_C64 ? 4 : 8) + (size_t)p->prog.n_ops * BLOCK * 4;
+}
 size_t smem_bwd(const fsweep_plan* p, int cc) {
   const size_t rs = p->dtype == FSWEEP_C64 ? 4 : 8;
   return smem_fwd(p) + (size_t)p->prog.n_slots * cc * BLOCK * 2 * rs + (size_t)p->prog.acc_per_lane * BLOCK * rs;
@@ -397,6 +404,7 @@ extern "C" int fsweep_forward(const fsweep_plan_t* plan_c, const void* const* co
   const int cc = cc_of(batch * cols);
   LaunchCfg cfg;
   cfg.smem = smem_fwd(plan);
+  if (cfg.smem > 200 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "forward needs %zu bytes of shared memory", cfg.smem);
   cfg.stream = (cudaStream_t)stream;
   cudaError_t e;
   cfg.grid = pick_grid(plan, cc, false, cfg.smem, n_bins, &e);
@@ -504,7 +512,7 @@ extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* c
       if (o.grad && (o.acc_mode == ACC_SMEM || o.acc_mode == ACC_GLOBAL))
         max_total = std::max(max_total, o.n_out * o.row_len);
     }
-    dim3 grid((unsigned)std::min(64, (max_total + 127) / 128), (unsigned)P.n_ops);
+    dim3 grid((unsigned)std::min(1024, (max_total + 3) / 4), (unsigned)P.n_ops);  // 4 warps per block, 1 warp per element
     if (dtype == FSWEEP_C64)
       fsweep_finalize_kernel<float><<<grid, 128, 0, st>>>(F);
     else

@@ -60,7 +60,7 @@ struct OpK {
   int row_off;  // ACC_SMEM: offset of this op's per-lane accumulator row
   int row_len;  // accumulators per row (per lane)
   int acc_off;  // offset of this op in the flat accumulator / partial buffers (row-major [row][row_len])
-  int pad_;
+  int h_off;    // offset (complex elements per thread) of this op's response row in the per-thread cache
   const void* coef;
   void* gtab;  // ACC_TABLE: gradient table
 };
@@ -93,6 +93,8 @@ struct ProgK {
   int acc_per_lane;  // backward: shared-memory accumulators per lane
   int acc_total;     // backward: flat accumulator count (sum over ops of rows*row_len)
   int n_fsteps, n_msteps, n_bsteps, n_rsteps;
+  int h_total;     // complex elements per thread in the response cache
+  int needs_ctx;   // some op is a section cascade: the Taylor context (v, v^2) is needed
   long long nfft;
   double lng;   // ln(gamma)
   double gm1;   // gamma - 1
@@ -152,9 +154,11 @@ __device__ __forceinline__ void cfmacj(cx<T>& acc, cx<T> a, cx<T> b) {  // acc +
   acc.y = fma(a.x, b.y, acc.y);
   acc.y = fma(-a.y, b.x, acc.y);
 }
+__device__ __forceinline__ float rcp_t(float d) { return __frcp_rn(d); }
+__device__ __forceinline__ double rcp_t(double d) { return 1.0 / d; }
 template <typename T>
 __device__ __forceinline__ cx<T> crcp(cx<T> a) {
-  T d = T(1) / (a.x * a.x + a.y * a.y);
+  T d = rcp_t(a.x * a.x + a.y * a.y);
   return mk<T>(a.x * d, -a.y * d);
 }
 template <typename T>
@@ -210,20 +214,24 @@ __device__ __forceinline__ Ctx<T> make_ctx(const ProgK& P, long long k) {
   c.lng = P.lng;
   c.inv_nfft = 1.0 / (double)P.nfft;
   double fr = (double)(2 * k) * c.inv_nfft;  // omega/pi in [0,1]
-  T f = (T)fr;
-  T s, co, sh, ch;
-  sincospi_t(f, &s, &co);
-  sincospi_t(f * T(0.5), &sh, &ch);
   c.omega = (T)(fr * 3.141592653589793238462643383279502884);
-  T g = (T)(P.gm1 + 1.0), g2 = (T)(P.g2m1 + 1.0);
-  c.plus = co >= T(0);
-  // w - 1 = (g-1) - 2 g sin^2(w/2) - j g sin w ;  w + 1 = 2 g cos^2(w/2) - (g-1) - j g sin w
-  if (c.plus)
-    c.u1 = mk<T>((T)P.gm1 - T(2) * g * sh * sh, -g * s);
-  else
-    c.u1 = mk<T>(T(2) * g * ch * ch - (T)P.gm1, -g * s);
-  c.u2 = cmul(c.u1, c.u1);
-  (void)g2;
+  c.plus = true;
+  c.u1 = mk<T>(0, 0);
+  c.u2 = mk<T>(0, 0);
+  if (P.needs_ctx) {
+    T f = (T)fr;
+    T s, co, sh, ch;
+    sincospi_t(f, &s, &co);
+    sincospi_t(f * T(0.5), &sh, &ch);
+    T g = (T)(P.gm1 + 1.0);
+    c.plus = co >= T(0);
+    // w - 1 = (g-1) - 2 g sin^2(w/2) - j g sin w ;  w + 1 = 2 g cos^2(w/2) - (g-1) - j g sin w
+    if (c.plus)
+      c.u1 = mk<T>((T)P.gm1 - T(2) * g * sh * sh, -g * s);
+    else
+      c.u1 = mk<T>(T(2) * g * ch * ch - (T)P.gm1, -g * s);
+    c.u2 = cmul(c.u1, c.u1);
+  }
   return c;
 }
 
@@ -297,7 +305,7 @@ __device__ __forceinline__ cx<T> sos_eval_without(const T* p, int K, long stride
 
 __device__ __forceinline__ float exp_t(float a) { return expf(a); }
 __device__ __forceinline__ double exp_t(double a) { return exp(a); }
-__device__ __forceinline__ float abs_t(float a, float b) { return hypotf(a, b); }
+__device__ __forceinline__ float abs_t(float a, float b) { return sqrtf(fmaf(a, a, b * b)); }
 __device__ __forceinline__ double abs_t(double a, double b) { return hypot(a, b); }
 
 // H = gamma^d * exp(-j omega_k d).  Integer delays: phase index (k*d mod nfft) formed exactly
@@ -425,41 +433,56 @@ __device__ __forceinline__ cx<T> op_diag(const OpK& op, const Ctx<T>& ctx, int m
   }
 }
 
-// Row `lane` of a dense response, staged in this thread's private shared-memory column
-// hrow[n*BLOCK + tid]; returns the bit mask of guarded (|prod A| == 0) entries.
+__device__ __forceinline__ bool bin_invariant(int kind) { return kind == FSWEEP_OP_GAIN || kind == FSWEEP_OP_PGAIN; }
+
+// Per-thread response cache in shared memory: hc[(op.h_off + n) * BLOCK + tid] = H[lane][n] of the
+// current bin (diagonal kinds: one entry).  Bin-invariant ops (GAIN, PGAIN) are staged once per
+// kernel, everything else once per bin; apply / backprop then only read the cache.
 template <typename T>
-__device__ __forceinline__ unsigned stage_row(const OpK& op, const Ctx<T>& ctx, int lane, cx<T>* hrow, int tid) {
-  unsigned gmask = 0;
+__device__ __forceinline__ void stage_op(const OpK& op, const Ctx<T>& ctx, int lane, cx<T>* hc, unsigned* gmask,
+                                         int opi, int tid) {
+  unsigned gm = 0;
   const bool live = lane < op.n_out;
-  for (int n = 0; n < op.n_in; ++n) {
+  if (is_dense(op.kind)) {
+    for (int n = 0; n < op.n_in; ++n) {
+      bool gd = false;
+      cx<T> h = mk<T>(0, 0);
+      if (live) h = op_entry<T>(op, ctx, lane, n, gd);
+      if (gd) gm |= 1u << n;
+      hc[(size_t)(op.h_off + n) * BLOCK + tid] = h;
+    }
+  } else {
     bool gd = false;
-    cx<T> h = mk<T>(0, 0);
-    if (live) h = op_entry<T>(op, ctx, lane, n, gd);
-    if (gd) gmask |= 1u << n;
-    hrow[(size_t)n * BLOCK + tid] = h;
+    hc[(size_t)op.h_off * BLOCK + tid] = op_diag<T>(op, ctx, lane, gd);
+    gm = gd ? 1u : 0u;
   }
-  return gmask;
+  gmask[opi * BLOCK + tid] = gm;
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_ops(const ProgK& P, const Ctx<T>& ctx, int lane, cx<T>* hc, unsigned* gmask,
+                                          int tid, bool invariant_pass) {
+  for (int i = 0; i < P.n_ops; ++i)
+    if (bin_invariant(P.ops[i].kind) == invariant_pass) stage_op<T>(P.ops[i], ctx, lane, hc, gmask, i, tid);
 }
 
 // S <- H S for NC columns (row-distributed).  `ident`: S is the identity, so H S = H (dense only).
 template <typename T, int G, int NC>
-__device__ __forceinline__ void apply_op(const OpK& op, const Ctx<T>& ctx, int lane, cx<T> (&S)[NC], int ncols,
-                                         bool ident, cx<T>* hrow, int tid) {
+__device__ __forceinline__ void apply_op(const OpK& op, int lane, cx<T> (&S)[NC], int ncols, bool ident,
+                                         const cx<T>* hc, int tid) {
+  const cx<T>* hrow = hc + (size_t)op.h_off * BLOCK + tid;
   if (is_dense(op.kind)) {
-    (void)stage_row<T>(op, ctx, lane, hrow, tid);
     if (ident) {
       static_for<0, NC>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        S[c] = (c < op.n_in) ? hrow[(size_t)c * BLOCK + tid] : mk<T>(0, 0);
+        S[c] = (c < op.n_in) ? hrow[(size_t)c * BLOCK] : mk<T>(0, 0);
       });
       return;
     }
-    // n outer (runtime), c inner (static register indices): columns >= ncols are dead weight only in
-    // the NC == G matrix build, where ncols == loop width
     cx<T> acc[NC];
     static_for<0, NC>([&](auto cc) { acc[decltype(cc)::value] = mk<T>(0, 0); });
     for (int n = 0; n < op.n_in; ++n) {
-      const cx<T> h = hrow[(size_t)n * BLOCK + tid];
+      const cx<T> h = hrow[(size_t)n * BLOCK];
       static_for<0, NC>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
         cx<T> v = shfl<G>(S[c], n);
@@ -468,8 +491,7 @@ __device__ __forceinline__ void apply_op(const OpK& op, const Ctx<T>& ctx, int l
     }
     static_for<0, NC>([&](auto cc) { S[decltype(cc)::value] = acc[decltype(cc)::value]; });
   } else {
-    bool gd;
-    cx<T> h = op_diag<T>(op, ctx, lane, gd);
+    const cx<T> h = hrow[0];
     static_for<0, NC>([&](auto cc) {
       constexpr int c = decltype(cc)::value;
       if (c < ncols) S[c] = cmul(h, S[c]);
@@ -482,20 +504,19 @@ __device__ __forceinline__ void apply_op(const OpK& op, const Ctx<T>& ctx, int l
 template <typename T, int G, int NC>
 __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, int lane, const cx<T> (&Sin)[NC],
                                             cx<T> (&g)[NC], bool need_gin, const Acc<T>& acc, bool first_chunk,
-                                            cx<T>* hrow, int tid) {
+                                            const cx<T>* hc, unsigned gmask, int tid) {
   const bool want = op.acc_mode != ACC_NONE;
+  const cx<T>* hrow = hc + (size_t)op.h_off * BLOCK + tid;
   if (is_dense(op.kind)) {
-    const unsigned gmask = stage_row<T>(op, ctx, lane, hrow, tid);
     if (want) {
       for (int n = 0; n < op.n_in; ++n) {
         cx<T> gh = mk<T>(0, 0);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
+        static_for<0, NC>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
           cx<T> v = shfl<G>(Sin[c], n);
           cfmac(gh, g[c], v);
-        }
+        });
         if (lane < op.n_out) {
-          const cx<T> h = hrow[(size_t)n * BLOCK + tid];
           switch (op.kind) {
             case FSWEEP_OP_GAIN:
               acc.add(op, lane, n, gh.x);
@@ -503,14 +524,14 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
             case FSWEEP_OP_DELAY:
               if (!(op.flags & FSWEEP_F_ISINT)) {
                 // dH/dd = (ln g - j w) H
-                cx<T> t = cmul(mk<T>((T)ctx.lng, -ctx.omega), h);
+                cx<T> t = cmul(mk<T>((T)ctx.lng, -ctx.omega), hrow[(size_t)n * BLOCK]);
                 acc.add(op, lane, n, gh.x * t.x + gh.y * t.y);
               }
               break;
             case FSWEEP_OP_SOS:
               if (!((gmask >> n) & 1u))
                 sos_grad<T>(op, reinterpret_cast<const T*>(op.coef) + ((size_t)n * op.n_out + lane) * 16,
-                            (long)op.n_in * op.n_out * 16, ctx, h, gh, acc, lane, n * 16);
+                            (long)op.n_in * op.n_out * 16, ctx, hrow[(size_t)n * BLOCK], gh, acc, lane, n * 16);
               break;
             case FSWEEP_OP_TABLE:
               if (acc.valid && op.gtab) {
@@ -532,28 +553,27 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
     }
     if (need_gin) {
       cx<T> gin[NC];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) gin[c] = mk<T>(0, 0);
+      static_for<0, NC>([&](auto cc) { gin[decltype(cc)::value] = mk<T>(0, 0); });
       for (int n = 0; n < op.n_in; ++n) {
-        const cx<T> h = hrow[(size_t)n * BLOCK + tid];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
+        const cx<T> h = hrow[(size_t)n * BLOCK];
+        static_for<0, NC>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
           cx<T> t = mk<T>(0, 0);
           cfmacj(t, h, g[c]);  // conj(h) * g
           t = group_sum<G>(t);
           if (lane == n) gin[c] = t;
-        }
+        });
       }
-#pragma unroll
-      for (int c = 0; c < NC; ++c) g[c] = gin[c];
+      static_for<0, NC>([&](auto cc) { g[decltype(cc)::value] = gin[decltype(cc)::value]; });
     }
   } else {
-    bool gd;
-    cx<T> h = op_diag<T>(op, ctx, lane, gd);
+    const cx<T> h = hrow[0];
     if (want && lane < op.n_out) {
       cx<T> gh = mk<T>(0, 0);
-#pragma unroll
-      for (int c = 0; c < NC; ++c) cfmac(gh, g[c], Sin[c]);
+      static_for<0, NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        cfmac(gh, g[c], Sin[c]);
+      });
       switch (op.kind) {
         case FSWEEP_OP_PGAIN:
           acc.add(op, lane, 0, gh.x);
@@ -565,7 +585,7 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
           }
           break;
         case FSWEEP_OP_PSOS:
-          if (!gd)
+          if (!(gmask & 1u))
             sos_grad<T>(op, reinterpret_cast<const T*>(op.coef) + (size_t)lane * 16, (long)op.n_out * 16, ctx, h, gh,
                         acc, lane, 0);
           break;
@@ -586,12 +606,12 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
       }
     }
     if (need_gin) {
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
+      static_for<0, NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
         cx<T> t = mk<T>(0, 0);
         cfmacj(t, h, g[c]);
         g[c] = t;
-      }
+      });
     }
   }
 }
@@ -599,14 +619,15 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
 // ------------------------------------------------------------------------------------------- LU
 constexpr int STEP_PAD = 1 << 20;  // "mystep" of padding lanes (rows >= N)
 
+__device__ __forceinline__ unsigned mag_key(float m) { return __float_as_uint(m); }
+__device__ __forceinline__ unsigned mag_key(double m) { return __float_as_uint((float)fmin(m, 3.0e38)); }
+
 template <int G>
-__device__ __forceinline__ int lane_with_step(int mystep, int k) {
-  unsigned m = __ballot_sync(FULL, mystep == k);
-  if constexpr (G < 32) {
-    int base = (threadIdx.x & 31) & ~(G - 1);
-    m = (m >> base) & ((1u << G) - 1u);
-  }
-  return __ffs(m) - 1;
+__device__ __forceinline__ unsigned group_mask() {
+  if constexpr (G == 32)
+    return FULL;
+  else
+    return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
 }
 
 template <typename T, int G>
@@ -614,25 +635,32 @@ struct LU {
   cx<T> a[G];   // row `lane` of A, overwritten by L multipliers (cols < mystep) and U (cols >= mystep)
   cx<T> dinv;   // 1 / U[mystep][mystep]
   int mystep;   // elimination step at which this row was the pivot row
+  unsigned piv[(G + 3) / 4];  // pivot lane of every step, 8 bits each
 
-  // Gaussian elimination with implicit partial pivoting; N = live rows/cols.
+  template <int K>
+  __device__ __forceinline__ int pivot_lane() const {
+    return (int)((piv[K / 4] >> (8 * (K % 4))) & 0xffu);
+  }
+
+  // Gaussian elimination with implicit partial pivoting; N = live rows/cols.  The arg-max over the
+  // candidate rows is one REDUX: key = |a|^2 bits with the low log2(G) bits replaced by G-1-lane.
   __device__ __forceinline__ void factor(int lane, int N) {
     mystep = (lane < N) ? -1 : STEP_PAD;
     dinv = mk<T>(1, 0);
+    static_for<0, (G + 3) / 4>([&](auto i) { piv[decltype(i)::value] = 0u; });
+    const unsigned gm = group_mask<G>();
     static_for<0, G>([&](auto kc) {
       constexpr int k = decltype(kc)::value;
       if (k < N) {
-        T mag = (mystep < 0) ? (a[k].x * a[k].x + a[k].y * a[k].y) : T(-1);
-        int who = lane;
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-          T om = __shfl_xor_sync(FULL, mag, o, G);
-          int ow = __shfl_xor_sync(FULL, who, o, G);
-          if (om > mag || (om == mag && ow < who)) {
-            mag = om;
-            who = ow;
-          }
+        int who = 0;
+        if constexpr (G > 1) {
+          unsigned key = 0u;
+          if (mystep < 0)
+            key = (mag_key(a[k].x * a[k].x + a[k].y * a[k].y) & ~(unsigned)(G - 1)) | (unsigned)(G - 1 - lane);
+          key = __reduce_max_sync(gm, key);
+          who = G - 1 - (int)(key & (unsigned)(G - 1));
         }
+        piv[k / 4] |= (unsigned)who << (8 * (k % 4));
         cx<T> pk = shfl<G>(a[k], who);
         cx<T> inv = crcp(pk);
         const bool act = (mystep < 0) && (lane != who);
@@ -659,7 +687,7 @@ struct LU {
     static_for<0, G>([&](auto kc) {
       constexpr int k = decltype(kc)::value;
       if (k < N) {
-        int p = lane_with_step<G>(mystep, k);
+        const int p = pivot_lane<k>();
         static_for<0, NC>([&](auto cc) {
           constexpr int c = decltype(cc)::value;
           cx<T> bk = shfl<G>(b[c], p);
@@ -672,7 +700,7 @@ struct LU {
     static_rfor<0, G>([&](auto kc) {
       constexpr int k = decltype(kc)::value;
       if (k < N) {
-        int p = lane_with_step<G>(mystep, k);
+        const int p = pivot_lane<k>();
         static_for<0, NC>([&](auto cc) {
           constexpr int c = decltype(cc)::value;
           cx<T> xk = shfl<G>(cmul(b[c], dinv), p);
@@ -733,8 +761,7 @@ struct LU {
 
 // Build A = I - F*Fb for this bin (row-distributed) and factor it.
 template <typename T, int G>
-__device__ __forceinline__ void build_loop(const ProgK& P, const Ctx<T>& ctx, int lane, LU<T, G>& lu, cx<T>* hrow,
-                                           int tid) {
+__device__ __forceinline__ void build_loop(const ProgK& P, int lane, LU<T, G>& lu, const cx<T>* hc, int tid) {
   const int N = P.rec_n;
   static_for<0, G>([&](auto cc) {
     constexpr int c = decltype(cc)::value;
@@ -742,7 +769,7 @@ __device__ __forceinline__ void build_loop(const ProgK& P, const Ctx<T>& ctx, in
   });
   for (int i = 0; i < P.n_msteps; ++i) {
     const Step st = P.msteps[i];
-    apply_op<T, G, G>(P.ops[st.op], ctx, lane, lu.a, N, (st.flags & ST_IDENT) != 0, hrow, tid);
+    apply_op<T, G, G>(P.ops[st.op], lane, lu.a, N, (st.flags & ST_IDENT) != 0, hc, tid);
   }
   static_for<0, G>([&](auto cc) {
     constexpr int c = decltype(cc)::value;
@@ -769,6 +796,19 @@ struct SweepArgs {
   void* gacc;     // backward: [acc_total] (ACC_GLOBAL ops), zeroed by the host wrapper
 };
 
+__device__ __forceinline__ cx<float> ld_cx(const cx<float>* p) {
+  float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return mk<float>(v.x, v.y);
+}
+__device__ __forceinline__ cx<double> ld_cx(const cx<double>* p) {
+  double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return mk<double>(v.x, v.y);
+}
+__device__ __forceinline__ void st_cx(cx<float>* p, cx<float> v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+__device__ __forceinline__ void st_cx(cx<double>* p, cx<double> v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
+}
+
 template <typename T, int G, int CC>
 __device__ __forceinline__ void load_cols(const cx<T>* x, long long xbs, long long bl, int nch, int cols, int q0,
                                           int ncols_total, int lane, cx<T> (&S)[CC]) {
@@ -777,19 +817,20 @@ __device__ __forceinline__ void load_cols(const cx<T>* x, long long xbs, long lo
     int q = q0 + c;
     S[c] = mk<T>(0, 0);
     if (q < ncols_total && lane < nch) {
-      int b = q / cols, cc = q - b * cols;
-      const T* p = reinterpret_cast<const T*>(x + (size_t)b * xbs + ((size_t)bl * nch + lane) * cols + cc);
-      S[c] = mk<T>(__ldg(p), __ldg(p + 1));
+      int b = (CC == 1 && cols == 1) ? q : q / cols;
+      int cc = q - b * cols;
+      S[c] = ld_cx(x + (size_t)b * xbs + ((size_t)bl * nch + lane) * cols + cc);
     }
   }
 }
 
-// shared memory: [hrow: G*BLOCK cx] [save: n_slots*CC*BLOCK cx] [sacc: acc_per_lane*BLOCK T]
+// shared memory: [hc: h_total*BLOCK cx] [gmask: n_ops*BLOCK u32] [save: n_slots*CC*BLOCK cx] [sacc: acc_per_lane*BLOCK T]
 // ------------------------------------------------------------------------------------ forward
 template <typename T, int G, int CC>
 __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant__ ProgK P, const SweepArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx<T>* hrow = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* hc = reinterpret_cast<cx<T>*>(smem_raw);
+  unsigned* gmask = reinterpret_cast<unsigned*>(hc + (size_t)P.h_total * BLOCK);
   const int tid = threadIdx.x;
   const int lane = tid & (G - 1);
   const long long groups_total = (long long)gridDim.x * (BLOCK / G);
@@ -798,20 +839,25 @@ __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant
   const int ncols_total = A.batch * A.cols;
   const cx<T>* x = reinterpret_cast<const cx<T>*>(A.x);
 
+  {
+    const Ctx<T> c0 = make_ctx<T>(P, A.bin_begin);
+    stage_ops<T>(P, c0, lane, hc, gmask, tid, true);  // bin-invariant rows, once per kernel
+  }
   for (long long it = 0; it < n_iter; ++it) {
     long long bl = it * groups_total + gg;
     const bool valid = bl < A.n_bins;
     if (!valid) bl = A.n_bins - 1;
     const Ctx<T> ctx = make_ctx<T>(P, A.bin_begin + bl);
+    stage_ops<T>(P, ctx, lane, hc, gmask, tid, false);
     LU<T, G> lu;
-    if (P.rec_n > 0) build_loop<T, G>(P, ctx, lane, lu, hrow, tid);
+    if (P.rec_n > 0) build_loop<T, G>(P, lane, lu, hc, tid);
 
     for (int q0 = 0; q0 < ncols_total; q0 += CC) {
       cx<T> S[CC];
       load_cols<T, G, CC>(x, A.xbs, bl, P.in_ch, A.cols, q0, ncols_total, lane, S);
       for (int i = 0; i < P.n_fsteps; ++i) {
         const Step st = P.fsteps[i];
-        apply_op<T, G, CC>(P.ops[st.op], ctx, lane, S, CC, false, hrow, tid);
+        apply_op<T, G, CC>(P.ops[st.op], lane, S, CC, false, hc, tid);
         if (st.flags & ST_SOLVE) lu.template solve<CC>(lane, P.rec_n, S);
       }
       if (valid && lane < P.out_ch) {
@@ -821,13 +867,10 @@ __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant
           if (q < ncols_total) {
             int b = q / A.cols, cc = q - b * A.cols;
             size_t off = (size_t)b * A.ybs + ((size_t)bl * P.out_ch + lane) * A.cols + cc;
-            if (A.epilogue == FSWEEP_EPI_ABS) {
+            if (A.epilogue == FSWEEP_EPI_ABS)
               reinterpret_cast<T*>(A.y)[off] = abs_t(S[c].x, S[c].y);
-            } else {
-              T* p = reinterpret_cast<T*>(A.y) + 2 * off;
-              p[0] = S[c].x;
-              p[1] = S[c].y;
-            }
+            else
+              st_cx(reinterpret_cast<cx<T>*>(A.y) + off, S[c]);
           }
         }
       }
@@ -839,9 +882,10 @@ __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant
 template <typename T, int G, int CC>
 __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant__ ProgK P, const SweepArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx<T>* hrow = reinterpret_cast<cx<T>*>(smem_raw);
-  cx<T>* save = hrow + (size_t)G * BLOCK;                                 // [n_slots][CC][BLOCK]
+  cx<T>* hc = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* save = hc + (size_t)P.h_total * BLOCK;                           // [n_slots][CC][BLOCK]
   T* sacc = reinterpret_cast<T*>(save + (size_t)P.n_slots * CC * BLOCK);  // [acc_per_lane][BLOCK]
+  unsigned* gmask = reinterpret_cast<unsigned*>(sacc + (size_t)P.acc_per_lane * BLOCK);
 
   const int tid = threadIdx.x;
   const int lane = tid & (G - 1);
@@ -868,14 +912,19 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
     for (int c = 0; c < CC; ++c) S[c] = save[((size_t)slot * CC + c) * BLOCK + tid];
   };
 
+  {
+    const Ctx<T> c0 = make_ctx<T>(P, A.bin_begin);
+    stage_ops<T>(P, c0, lane, hc, gmask, tid, true);
+  }
   for (long long it = 0; it < n_iter; ++it) {
     long long bl = it * groups_total + gg;
     const bool valid = bl < A.n_bins;
     if (!valid) bl = A.n_bins - 1;
     acc.valid = valid;
     const Ctx<T> ctx = make_ctx<T>(P, A.bin_begin + bl);
+    stage_ops<T>(P, ctx, lane, hc, gmask, tid, false);
     LU<T, G> lu;
-    if (P.rec_n > 0) build_loop<T, G>(P, ctx, lane, lu, hrow, tid);
+    if (P.rec_n > 0) build_loop<T, G>(P, lane, lu, hc, tid);
 
     for (int q0 = 0; q0 < ncols_total; q0 += CC) {
       const bool first_chunk = q0 == 0;
@@ -887,7 +936,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
         const Step st = P.bsteps[i];
         if (st.flags & ST_SAVE_X) put(slot_x, S);
         if (st.flags & ST_SAVE) put(slot++, S);
-        apply_op<T, G, CC>(P.ops[st.op], ctx, lane, S, CC, false, hrow, tid);
+        apply_op<T, G, CC>(P.ops[st.op], lane, S, CC, false, hc, tid);
         if (st.flags & ST_SOLVE) lu.template solve<CC>(lane, P.rec_n, S);
         if (st.flags & ST_ADD_X) {
           cx<T> X[CC];
@@ -911,10 +960,12 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
           if (A.epilogue == FSWEEP_EPI_ABS) {
             T ga = __ldg(reinterpret_cast<const T*>(A.gy) + off);
             T mag = abs_t(S[c].x, S[c].y);
-            if (mag > T(0)) g[c] = mk<T>(ga * S[c].x / mag, ga * S[c].y / mag);
+            if (mag > T(0)) {
+              T r = ga * rcp_t(mag);
+              g[c] = mk<T>(r * S[c].x, r * S[c].y);
+            }
           } else {
-            const T* p = reinterpret_cast<const T*>(A.gy) + 2 * off;
-            g[c] = mk<T>(__ldg(p), __ldg(p + 1));
+            g[c] = ld_cx(reinterpret_cast<const cx<T>*>(A.gy) + off);
           }
         }
       }
@@ -924,8 +975,8 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
         if (st.flags & RS_ADJ) lu.template solve_adj<CC>(lane, P.rec_n, g);
         cx<T> Sin[CC];
         get(--slot, Sin);
-        backprop_op<T, G, CC>(P.ops[st.op], ctx, lane, Sin, g, (st.flags & RS_NEED_GIN) != 0, acc, first_chunk, hrow,
-                              tid);
+        backprop_op<T, G, CC>(P.ops[st.op], ctx, lane, Sin, g, (st.flags & RS_NEED_GIN) != 0, acc, first_chunk, hc,
+                              gmask[st.op * BLOCK + tid], tid);
         if (st.flags & RS_SAVE_G) put(slot_x, g);
         if (st.flags & RS_RESTORE_G) get(slot_x, g);
       }
@@ -935,9 +986,8 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
           int q = q0 + c;
           if (q < ncols_total) {
             int b = q / A.cols, cc = q - b * A.cols;
-            T* p = reinterpret_cast<T*>(A.gx) + 2 * ((size_t)b * A.gxbs + ((size_t)bl * P.in_ch + lane) * A.cols + cc);
-            p[0] = g[c].x;
-            p[1] = g[c].y;
+            st_cx(reinterpret_cast<cx<T>*>(A.gx) + (size_t)b * A.gxbs + ((size_t)bl * P.in_ch + lane) * A.cols + cc,
+                  g[c]);
           }
         }
       }
@@ -968,23 +1018,29 @@ struct FinalizeArgs {
   FinalizeOp ops[MAX_OPS];
 };
 
+// One WARP per output element: lanes stride over the per-block partials, shuffle-reduce in float64.
 template <typename T>
-__global__ void fsweep_finalize_kernel(const __grid_constant__ FinalizeArgs F) {
+__global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_constant__ FinalizeArgs F) {
   const int opi = blockIdx.y;
   const FinalizeOp& op = F.ops[opi];
   if (op.grad == nullptr || (op.acc_mode != ACC_SMEM && op.acc_mode != ACC_GLOBAL)) return;
   const bool diag = !(op.kind == FSWEEP_OP_GAIN || op.kind == FSWEEP_OP_SOS || op.kind == FSWEEP_OP_DELAY);
-  const int rows = op.n_out;
-  const int total = rows * op.row_len;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+  const int total = op.n_out * op.row_len;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < total; e += gridDim.x * warps_per_block) {
     int row = e / op.row_len, i = e - row * op.row_len;
     double s = 0.0;
     if (op.acc_mode == ACC_SMEM) {
       const T* p = reinterpret_cast<const T*>(F.partial) + (size_t)(op.row_off + i) * F.G + row;
-      for (int b = 0; b < F.n_blocks; ++b) s += (double)p[(size_t)b * F.acc_per_lane * F.G];
+      const size_t stride = (size_t)F.acc_per_lane * F.G;
+      for (int b = lane; b < F.n_blocks; b += 32) s += (double)p[(size_t)b * stride];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     } else {
       s = (double)reinterpret_cast<const T*>(F.gacc)[op.acc_off + e];
     }
+    if (lane != 0) continue;
     // map (row, i) -> index in the caller's layout
     size_t o;
     if (op.kind == FSWEEP_OP_SOS) {

@@ -38,8 +38,9 @@ class Trainer:
         params = list(self.net.parameters())
         if self.use_graph:
             # capturable Adam keeps `step` and `lr` on the device so a captured step can be replayed
-            self.optimizer = torch.optim.Adam(params, lr=torch.tensor(float(lr), device=device, dtype=torch.float64),
-                                              capturable=True)
+            # and `fused` folds the whole update into one multi-tensor kernel (same arithmetic)
+            self.optimizer = torch.optim.Adam(params, lr=torch.tensor(float(lr), device=device, dtype=torch.float32),
+                                              capturable=True, fused=True)
         else:
             self.optimizer = torch.optim.Adam(params, lr=self.lr)
         self.n_loss = 0

@@ -132,6 +132,7 @@ class DSP(nn.Module):
         self.alias_decay_db = torch.tensor(alias_decay_db, device=device, dtype=dtype)
         self._alias_db = float(alias_decay_db)  # host copy: lowering never reads the device tensor back
         self._consts = {}
+        self._coef_cache = None
         self.init_param()
         self.get_gamma()
 
@@ -179,7 +180,22 @@ class DSP(nn.Module):
         return prog.run(x)
 
     def _lower(self, prog, ext_param=None):
-        self._emit(prog, self._select_param(ext_param))
+        param = self._select_param(ext_param)
+        if param is self.param and not param.requires_grad:
+            # frozen parameters: the mapped coefficient tensor is reused until the parameter is
+            # written again (assign_value / load_state_dict bump `_version`); the optimizer never
+            # touches it, so this also holds across CUDA-graph replays
+            key = (param._version, param.data_ptr(), prog.real, self.map)
+            if self._coef_cache is not None and self._coef_cache[0] == key:
+                prog.items_target().append(self._coef_cache[1])
+                return
+            n0 = len(prog.items_target())
+            with torch.no_grad():
+                self._emit(prog, param)
+            if len(prog.items_target()) == n0 + 1:
+                self._coef_cache = (key, prog.items_target()[-1])
+            return
+        self._emit(prog, param)
 
     def _emit(self, prog, param):
         raise NotImplementedError
@@ -234,7 +250,8 @@ class Gain(DSP):
         self.freq_convolve = lambda x, param: self._sweep(x, param)
 
     def _emit(self, prog, param):
-        W = self.map(self._up(param))
+        # the default identity map needs no float64 detour
+        W = param if self.map is _identity else self.map(self._up(param))
         if self._parallel:
             prog.leaf(OP_PGAIN, self.output_channels, self.input_channels, W.reshape(-1))
         else:

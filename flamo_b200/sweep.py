@@ -166,6 +166,10 @@ class Program:
         item = ("leaf", (kind, int(n_out), int(n_in), int(K), flags, 0, 0, 0), coef)
         (self._chain if self._chain is not None else self.items).append(item)
 
+    def items_target(self) -> list:
+        """The list new leaves are appended to (the open recursion chain, or the top level)."""
+        return self._chain if self._chain is not None else self.items
+
     def eager(self, fn):
         """A module the sweep cannot express: run it in PyTorch between two launches."""
         if self._chain is not None:

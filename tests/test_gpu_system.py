@@ -65,7 +65,8 @@ def test_graph_replay_equals_eager(dtype):
     la = [ta.train_step((x, y)) for _ in range(10)]
     lb = [tb.train_step((x, y)) for _ in range(10)]
     assert tb.use_graph and len(tb._graphs) == 1, "the step was not captured"
-    tol = 1e-5 if dtype == torch.float32 else 1e-10
+    # the captured step uses fused capturable Adam with a float32 learning-rate tensor (1e-3 rounds by 5e-8)
+    tol = 1e-5 if dtype == torch.float32 else 1e-6
     assert np.allclose(la, lb, rtol=tol)
     for pa, pb in zip(ma.parameters(), mb.parameters()):
         assert torch.allclose(pa, pb, rtol=tol * 10, atol=tol)
