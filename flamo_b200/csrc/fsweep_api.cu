@@ -4,13 +4,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <type_traits>
 #include <vector>
 
-#include "fsweep_kernels.cuh"
+#include "fsweep_loop.cuh"
 
 using namespace fsweep;
 
@@ -63,9 +64,11 @@ struct fsweep_plan {
   int n_coeffs;
   std::vector<fsweep_op_t> leaf;  // leaf ops in slot order == ProgK::ops order
   bool any_global, any_acc;
-  // lazily filled launch geometry: [cc index 0:1, 1:4][fwd, bwd]
+  bool loop_fast = false;  // program matches the FDN-loop pattern of fsweep_loop.cuh
+  LoopInfo loop;
+  // lazily filled launch geometry: [cc index 0:1, 1:4, 2:loop kernels][fwd, bwd]
   std::mutex mu;
-  int blocks_per_sm[2][2] = {{0, 0}, {0, 0}};
+  int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};
   int num_sms = 0;
 };
 
@@ -157,6 +160,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   P.nfft = nfft;
   const double lng = -std::fabs(alias_decay_db) / (double)nfft / 20.0 * std::log(10.0);
   P.lng = lng;
+  P.inv_nfft = 1.0 / (double)nfft;
   P.gm1 = std::expm1(lng);
   P.g2m1 = std::expm1(2.0 * lng);
   P.rec_n = rec_n;
@@ -262,6 +266,26 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   P.n_rsteps = nr;
   P.n_slots = saves + 1;
 
+  // ---- FDN-loop pattern: [GAIN] RECURSION(ff: diagonal ops, fb: one GAIN) [GAIN]
+  const char* no_loop = getenv("FSWEEP_DISABLE_LOOP_KERNEL");  // tests: force the generic interpreter
+  if (!(no_loop && no_loop[0] == '1') && rec >= 0 && pre.size() <= 1 && post.size() <= 1 && fb.size() == 1 &&
+      ops[fb[0]].kind == FSWEEP_OP_GAIN &&
+      (pre.empty() || ops[pre[0]].kind == FSWEEP_OP_GAIN) && (post.empty() || ops[post[0]].kind == FSWEEP_OP_GAIN) &&
+      (dtype == FSWEEP_C64 || G <= 16)) {
+    bool ok = true;
+    for (int i : ff) ok = ok && kind_is_diag(ops[i].kind);
+    for (int s2 = 0; s2 < P.n_ops; ++s2) ok = ok && P.ops[s2].acc_mode != ACC_GLOBAL;
+    if (ok) {
+      p->loop_fast = true;
+      memset(&p->loop, 0, sizeof(p->loop));
+      p->loop.pre = pre.empty() ? -1 : slot_of[pre[0]];
+      p->loop.ff_begin = slot_of[ff[0]];
+      p->loop.n_ff = (int)ff.size();
+      p->loop.fb = slot_of[fb[0]];
+      p->loop.post = post.empty() ? -1 : slot_of[post[0]];
+    }
+  }
+
   *out = p;
   return FSWEEP_OK;
 }
@@ -327,8 +351,8 @@ cudaError_t by_group(int G, F&& f) {
 }
 
 // persistent grid: resident blocks per SM (occupancy query, cached) x SM count, capped by the work
-int pick_grid(fsweep_plan* p, int cc, bool bwd, size_t smem, int64_t n_bins, cudaError_t* err) {
-  const int ci = cc == 1 ? 0 : 1;
+int pick_grid(fsweep_plan* p, int cc, bool bwd, size_t smem, int64_t n_bins, cudaError_t* err, bool loop = false) {
+  const int ci = loop ? 2 : (cc == 1 ? 0 : 1);
   *err = cudaSuccess;
   {
     std::lock_guard<std::mutex> lk(p->mu);
@@ -340,7 +364,10 @@ int pick_grid(fsweep_plan* p, int cc, bool bwd, size_t smem, int64_t n_bins, cud
     if (p->blocks_per_sm[ci][bwd] == 0) {
       int n = 0;
       const int dtype = p->dtype;
-      *err = by_group(p->G, [&](auto g) { return occupancy<decltype(g)::value>(dtype, cc, bwd, smem, &n); });
+      if (loop)
+        *err = by_group(p->G, [&](auto g) { return occupancy_loop<decltype(g)::value>(dtype, bwd, smem, &n); });
+      else
+        *err = by_group(p->G, [&](auto g) { return occupancy<decltype(g)::value>(dtype, cc, bwd, smem, &n); });
       if (*err != cudaSuccess) return 0;
       if (n < 1) {
         *err = cudaErrorLaunchOutOfResources;
@@ -402,15 +429,21 @@ extern "C" int fsweep_forward(const fsweep_plan_t* plan_c, const void* const* co
   A.n_bins = n_bins;
   A.epilogue = epilogue;
   const int cc = cc_of(batch * cols);
+  const bool loop = plan->loop_fast;
   LaunchCfg cfg;
   cfg.smem = smem_fwd(plan);
   if (cfg.smem > 200 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "forward needs %zu bytes of shared memory", cfg.smem);
   cfg.stream = (cudaStream_t)stream;
   cudaError_t e;
-  cfg.grid = pick_grid(plan, cc, false, cfg.smem, n_bins, &e);
+  cfg.grid = pick_grid(plan, cc, false, cfg.smem, n_bins, &e, loop);
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
   const int dtype = plan->dtype;
-  e = by_group(plan->G, [&](auto g) { return launch_fwd<decltype(g)::value>(dtype, cc, cfg, P, A); });
+  if (loop) {
+    const LoopInfo L = plan->loop;
+    e = by_group(plan->G, [&](auto g) { return launch_loop_fwd<decltype(g)::value>(dtype, cfg, P, L, A); });
+  } else {
+    e = by_group(plan->G, [&](auto g) { return launch_fwd<decltype(g)::value>(dtype, cc, cfg, P, A); });
+  }
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "forward launch: %s", cudaGetErrorString(e));
   g_launches = 1;
   return FSWEEP_OK;
@@ -447,13 +480,14 @@ extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* c
   }
   if (grad_x && plan->first_pre_rstep >= 0) P.rsteps[plan->first_pre_rstep].flags |= RS_NEED_GIN;
 
-  const int cc = cc_of(batch * cols);
+  const bool loop = plan->loop_fast;
+  const int cc = loop ? 1 : cc_of(batch * cols);
   LaunchCfg cfg;
   cfg.smem = smem_bwd(plan, cc);
   if (cfg.smem > 200 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "backward needs %zu bytes of shared memory", cfg.smem);
   cfg.stream = st;
   cudaError_t e;
-  cfg.grid = pick_grid(plan, cc, true, cfg.smem, n_bins, &e);
+  cfg.grid = pick_grid(plan, cc, true, cfg.smem, n_bins, &e, loop);
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
 
   const size_t partial_bytes = (((size_t)grid_cap(n_bins, plan->G) * P.acc_per_lane * plan->G * rs + 255) / 256) * 256;
@@ -484,7 +518,12 @@ extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* c
     ++launches;
   }
   const int dtype = plan->dtype;
-  e = by_group(plan->G, [&](auto g) { return launch_bwd<decltype(g)::value>(dtype, cc, cfg, P, A); });
+  if (loop) {
+    const LoopInfo L = plan->loop;
+    e = by_group(plan->G, [&](auto g) { return launch_loop_bwd<decltype(g)::value>(dtype, cfg, P, L, A); });
+  } else {
+    e = by_group(plan->G, [&](auto g) { return launch_bwd<decltype(g)::value>(dtype, cc, cfg, P, A); });
+  }
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "backward launch: %s", cudaGetErrorString(e));
   ++launches;
 

@@ -1,6 +1,6 @@
 // fsweep_inst.cu — explicit instantiations of the sweep kernels for one group size.
 // Compiled once per G with -DFSWEEP_G=<1|2|4|8|16|32> so the six widths build in parallel.
-#include "fsweep_kernels.cuh"
+#include "fsweep_loop.cuh"
 
 #ifndef FSWEEP_G
 #error "compile with -DFSWEEP_G=<group size>"
@@ -68,6 +68,52 @@ cudaError_t launch_bwd<FSWEEP_G>(int dtype, int cc, const LaunchCfg& cfg, const 
 template <>
 cudaError_t occupancy<FSWEEP_G>(int dtype, int cc, bool bwd, size_t smem, int* blocks_per_sm) {
   FSWEEP_DISPATCH(occ_t, bwd, smem, blocks_per_sm)
+}
+
+// ---- pattern-specialised FDN-loop kernels (float for every G; double up to G = 16: registers)
+constexpr bool kLoopDouble = FSWEEP_G <= 16;
+
+template <typename T, int G, bool BWD>
+static cudaError_t launch_loop_t(const LaunchCfg& cfg, const ProgK& P, const LoopInfo& L, const SweepArgs& A) {
+  auto k = BWD ? fsweep_loop_bwd_kernel<T, G> : fsweep_loop_fwd_kernel<T, G>;
+  if (cfg.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<cfg.grid, BLOCK, cfg.smem, cfg.stream>>>(P, L, A);
+  return cudaGetLastError();
+}
+
+template <typename T, int G, bool BWD>
+static cudaError_t occ_loop_t(size_t smem, int* n) {
+  auto k = BWD ? fsweep_loop_bwd_kernel<T, G> : fsweep_loop_fwd_kernel<T, G>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, k, BLOCK, smem);
+}
+
+template <>
+cudaError_t launch_loop_fwd<FSWEEP_G>(int dtype, const LaunchCfg& cfg, const ProgK& P, const LoopInfo& L,
+                                      const SweepArgs& A) {
+  if (dtype == FSWEEP_C64) return launch_loop_t<float, FSWEEP_G, false>(cfg, P, L, A);
+  if constexpr (kLoopDouble) return launch_loop_t<double, FSWEEP_G, false>(cfg, P, L, A);
+  return cudaErrorNotSupported;
+}
+template <>
+cudaError_t launch_loop_bwd<FSWEEP_G>(int dtype, const LaunchCfg& cfg, const ProgK& P, const LoopInfo& L,
+                                      const SweepArgs& A) {
+  if (dtype == FSWEEP_C64) return launch_loop_t<float, FSWEEP_G, true>(cfg, P, L, A);
+  if constexpr (kLoopDouble) return launch_loop_t<double, FSWEEP_G, true>(cfg, P, L, A);
+  return cudaErrorNotSupported;
+}
+template <>
+cudaError_t occupancy_loop<FSWEEP_G>(int dtype, bool bwd, size_t smem, int* n) {
+  if (dtype == FSWEEP_C64) return bwd ? occ_loop_t<float, FSWEEP_G, true>(smem, n) : occ_loop_t<float, FSWEEP_G, false>(smem, n);
+  if constexpr (kLoopDouble)
+    return bwd ? occ_loop_t<double, FSWEEP_G, true>(smem, n) : occ_loop_t<double, FSWEEP_G, false>(smem, n);
+  return cudaErrorNotSupported;
 }
 
 }  // namespace fsweep

@@ -97,6 +97,7 @@ struct ProgK {
   int needs_ctx;   // some op is a section cascade: the Taylor context (v, v^2) is needed
   long long nfft;
   double lng;   // ln(gamma)
+  double inv_nfft;
   double gm1;   // gamma - 1
   double g2m1;  // gamma^2 - 1
   OpK ops[MAX_OPS];
@@ -154,11 +155,16 @@ __device__ __forceinline__ void cfmacj(cx<T>& acc, cx<T> a, cx<T> b) {  // acc +
   acc.y = fma(a.x, b.y, acc.y);
   acc.y = fma(-a.y, b.x, acc.y);
 }
-__device__ __forceinline__ float rcp_t(float d) { return __frcp_rn(d); }
+__device__ __forceinline__ float rcp_t(float d) { return __fdividef(1.0f, d); }  // MUFU.RCP, <= 2 ulp
 __device__ __forceinline__ double rcp_t(double d) { return 1.0 / d; }
 template <typename T>
 __device__ __forceinline__ cx<T> crcp(cx<T> a) {
   T d = rcp_t(a.x * a.x + a.y * a.y);
+  return mk<T>(a.x * d, -a.y * d);
+}
+template <typename T>
+__device__ __forceinline__ cx<T> crcp_exact(cx<T> a) {  // correctly rounded reciprocal: section cascades multiply 30 of these
+  T d = T(1) / (a.x * a.x + a.y * a.y);
   return mk<T>(a.x * d, -a.y * d);
 }
 template <typename T>
@@ -212,7 +218,7 @@ __device__ __forceinline__ Ctx<T> make_ctx(const ProgK& P, long long k) {
   c.k = k;
   c.nfft = P.nfft;
   c.lng = P.lng;
-  c.inv_nfft = 1.0 / (double)P.nfft;
+  c.inv_nfft = P.inv_nfft;
   double fr = (double)(2 * k) * c.inv_nfft;  // omega/pi in [0,1]
   c.omega = (T)(fr * 3.141592653589793238462643383279502884);
   c.plus = true;
@@ -281,7 +287,7 @@ __device__ __forceinline__ cx<T> sos_eval(const T* p, int K, long stride, const 
     cx<T> Bv, Av;
     section_eval<T>(c, ctx, Bv, Av);
     guarded |= czero(Av);
-    H = cmul(H, cmul(Bv, crcp(Av)));
+    H = cmul(H, cmul(Bv, crcp_exact(Av)));
   }
   if (guarded) return mk<T>(eps_of<T>(), T(0));
   return H;
@@ -298,7 +304,7 @@ __device__ __forceinline__ cx<T> sos_eval_without(const T* p, int K, long stride
     load8<T>(p, c);
     cx<T> Bv, Av;
     section_eval<T>(c, ctx, Bv, Av);
-    H = cmul(H, cmul(Bv, crcp(Av)));
+    H = cmul(H, cmul(Bv, crcp_exact(Av)));
   }
   return H;
 }
@@ -374,11 +380,11 @@ __device__ __forceinline__ void sos_grad(const OpK& op, const T* p, long stride,
     cx<T> qb;
     if (czero(Bv)) {
       // dH/dB_s = prod_{t != s} (B_t/A_t) / A_s  (H itself is 0 at this bin)
-      qb = cmul(sos_eval_without<T>(p0, K, stride, ctx, s), crcp(Av));
+      qb = cmul(sos_eval_without<T>(p0, K, stride, ctx, s), crcp_exact(Av));
     } else {
-      qb = cmul(H, crcp(Bv));
+      qb = cmul(H, crcp_exact(Bv));
     }
-    cx<T> qa = cmul(H, crcp(Av));
+    cx<T> qa = cmul(H, crcp_exact(Av));
     qa.x = -qa.x;
     qa.y = -qa.y;
     cx<T> rb = cmulc(gh, qb), ra = cmulc(gh, qa);
@@ -461,9 +467,9 @@ __device__ __forceinline__ void stage_op(const OpK& op, const Ctx<T>& ctx, int l
 
 template <typename T>
 __device__ __forceinline__ void stage_ops(const ProgK& P, const Ctx<T>& ctx, int lane, cx<T>* hc, unsigned* gmask,
-                                          int tid, bool invariant_pass) {
+                                          int tid, bool invariant_pass, int skip = -1) {
   for (int i = 0; i < P.n_ops; ++i)
-    if (bin_invariant(P.ops[i].kind) == invariant_pass) stage_op<T>(P.ops[i], ctx, lane, hc, gmask, i, tid);
+    if (i != skip && bin_invariant(P.ops[i].kind) == invariant_pass) stage_op<T>(P.ops[i], ctx, lane, hc, gmask, i, tid);
 }
 
 // S <- H S for NC columns (row-distributed).  `ident`: S is the identity, so H S = H (dense only).
@@ -617,8 +623,6 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
 }
 
 // ------------------------------------------------------------------------------------------- LU
-constexpr int STEP_PAD = 1 << 20;  // "mystep" of padding lanes (rows >= N)
-
 __device__ __forceinline__ unsigned mag_key(float m) { return __float_as_uint(m); }
 __device__ __forceinline__ unsigned mag_key(double m) { return __float_as_uint((float)fmin(m, 3.0e38)); }
 
@@ -630,6 +634,13 @@ __device__ __forceinline__ unsigned group_mask() {
     return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
 }
 
+template <typename T>
+__device__ __forceinline__ cx<T> csel(bool p, cx<T> a) {  // p ? a : 0, branch-free
+  return mk<T>(p ? a.x : T(0), p ? a.y : T(0));
+}
+
+// G x G complex LU, row `lane` per lane.  Rows / columns beyond the live width are identity (the
+// caller pads A that way), so all G steps always run: no width guards, no divergent branches.
 template <typename T, int G>
 struct LU {
   cx<T> a[G];   // row `lane` of A, overwritten by L multipliers (cols < mystep) and U (cols >= mystep)
@@ -642,72 +653,68 @@ struct LU {
     return (int)((piv[K / 4] >> (8 * (K % 4))) & 0xffu);
   }
 
-  // Gaussian elimination with implicit partial pivoting; N = live rows/cols.  The arg-max over the
+  // Gaussian elimination with implicit partial pivoting (rows never move).  The arg-max over the
   // candidate rows is one REDUX: key = |a|^2 bits with the low log2(G) bits replaced by G-1-lane.
-  __device__ __forceinline__ void factor(int lane, int N) {
-    mystep = (lane < N) ? -1 : STEP_PAD;
+  __device__ __forceinline__ void factor(int lane) {
+    mystep = -1;
     dinv = mk<T>(1, 0);
     static_for<0, (G + 3) / 4>([&](auto i) { piv[decltype(i)::value] = 0u; });
-    const unsigned gm = group_mask<G>();
     static_for<0, G>([&](auto kc) {
       constexpr int k = decltype(kc)::value;
-      if (k < N) {
-        int who = 0;
-        if constexpr (G > 1) {
-          unsigned key = 0u;
-          if (mystep < 0)
-            key = (mag_key(a[k].x * a[k].x + a[k].y * a[k].y) & ~(unsigned)(G - 1)) | (unsigned)(G - 1 - lane);
-          key = __reduce_max_sync(gm, key);
-          who = G - 1 - (int)(key & (unsigned)(G - 1));
+      int who = 0;
+      if constexpr (G > 1) {
+        unsigned key = (mag_key(a[k].x * a[k].x + a[k].y * a[k].y) & ~(unsigned)(G - 1)) | (unsigned)(G - 1 - lane);
+        key = (mystep < 0) ? key : 0u;
+        if constexpr (G == 32) {
+          key = __reduce_max_sync(FULL, key);  // one REDUX when the group is the whole warp
+        } else {
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(FULL, key, o, G));
         }
-        piv[k / 4] |= (unsigned)who << (8 * (k % 4));
-        cx<T> pk = shfl<G>(a[k], who);
-        cx<T> inv = crcp(pk);
-        const bool act = (mystep < 0) && (lane != who);
-        cx<T> l = cmul(a[k], inv);
-        if (lane == who) {
-          mystep = k;
-          dinv = inv;
-        }
-        static_for<k + 1, G>([&](auto jc) {
-          constexpr int j = decltype(jc)::value;
-          if (j < N) {
-            cx<T> pj = shfl<G>(a[j], who);
-            if (act) cfnma(a[j], l, pj);
-          }
-        });
-        if (act) a[k] = l;
+        who = G - 1 - (int)(key & (unsigned)(G - 1));
       }
+      piv[k / 4] |= (unsigned)who << (8 * (k % 4));
+      const cx<T> inv = crcp(shfl<G>(a[k], who));
+      const bool act = (mystep < 0) && (lane != who);
+      const cx<T> l = csel(act, cmul(a[k], inv));  // multiplier; 0 for the pivot row and finished rows
+      if (lane == who) {
+        mystep = k;
+        dinv = inv;
+      }
+      static_for<k + 1, G>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        cfnma(a[j], l, shfl<G>(a[j], who));
+      });
+      a[k].x = act ? l.x : a[k].x;
+      a[k].y = act ? l.y : a[k].y;
     });
   }
 
   // A x = b for NC right-hand sides; b in natural row order on entry, x in natural order on exit.
   template <int NC>
-  __device__ __forceinline__ void solve(int lane, int N, cx<T> (&b)[NC]) const {
+  __device__ __forceinline__ void solve(int lane, cx<T> (&b)[NC]) const {
     static_for<0, G>([&](auto kc) {
       constexpr int k = decltype(kc)::value;
-      if (k < N) {
-        const int p = pivot_lane<k>();
-        static_for<0, NC>([&](auto cc) {
-          constexpr int c = decltype(cc)::value;
-          cx<T> bk = shfl<G>(b[c], p);
-          if (mystep > k && mystep != STEP_PAD) cfnma(b[c], a[k], bk);
-        });
-      }
+      const int p = pivot_lane<k>();
+      const cx<T> lk = csel(mystep > k, a[k]);
+      static_for<0, NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        cfnma(b[c], lk, shfl<G>(b[c], p));
+      });
     });
     cx<T> x[NC];
     static_for<0, NC>([&](auto cc) { x[decltype(cc)::value] = mk<T>(0, 0); });
     static_rfor<0, G>([&](auto kc) {
       constexpr int k = decltype(kc)::value;
-      if (k < N) {
-        const int p = pivot_lane<k>();
-        static_for<0, NC>([&](auto cc) {
-          constexpr int c = decltype(cc)::value;
-          cx<T> xk = shfl<G>(cmul(b[c], dinv), p);
-          if (mystep < k) cfnma(b[c], a[k], xk);
-          if (lane == k) x[c] = xk;
-        });
-      }
+      const int p = pivot_lane<k>();
+      const cx<T> uk = csel(mystep < k, a[k]);
+      static_for<0, NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const cx<T> xk = shfl<G>(cmul(b[c], dinv), p);
+        cfnma(b[c], uk, xk);
+        x[c].x = (lane == k) ? xk.x : x[c].x;
+        x[c].y = (lane == k) ? xk.y : x[c].y;
+      });
     });
     static_for<0, NC>([&](auto cc) { b[decltype(cc)::value] = x[decltype(cc)::value]; });
   }
@@ -715,45 +722,35 @@ struct LU {
   // A^H lam = g for NC right-hand sides (natural order in and out), reusing the same factors:
   // A = P^T L U  =>  U^H w = g ,  L^H v = w ,  lam = P^T v.
   template <int NC>
-  __device__ __forceinline__ void solve_adj(int lane, int N, cx<T> (&g)[NC]) const {
-    const bool live = mystep != STEP_PAD;
+  __device__ __forceinline__ void solve_adj(int lane, cx<T> (&g)[NC]) const {
     cx<T> w[NC];
     static_for<0, NC>([&](auto cc) {
       constexpr int c = decltype(cc)::value;
-      cx<T> gp = shfl<G>(g[c], live ? mystep : lane);
-      w[c] = live ? gp : mk<T>(0, 0);
+      w[c] = shfl<G>(g[c], mystep);
     });
+    const cx<T> dinvc = mk<T>(dinv.x, -dinv.y);
     // forward substitution with U^H (lower triangular): w_i = (g_i - sum_{j<i} conj(U[j][i]) w_j) / conj(U[i][i])
     static_for<0, G>([&](auto ic) {
       constexpr int i = decltype(ic)::value;
-      if (i < N) {
-        static_for<0, NC>([&](auto cc) {
-          constexpr int c = decltype(cc)::value;
-          cx<T> t = mk<T>(0, 0);
-          if (live && mystep < i) cfmacj(t, a[i], w[c]);
-          t = group_sum<G>(t);
-          if (mystep == i) {
-            cx<T> d = mk<T>(w[c].x - t.x, w[c].y - t.y);
-            w[c] = cmulc(d, dinv);  // d * conj(1/U_ii)
-          }
-        });
-      }
+      const cx<T> ui = csel(mystep < i, mk<T>(a[i].x, -a[i].y));
+      static_for<0, NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const cx<T> t = group_sum<G>(cmul(ui, w[c]));
+        const cx<T> d = cmul(mk<T>(w[c].x - t.x, w[c].y - t.y), dinvc);
+        w[c].x = (mystep == i) ? d.x : w[c].x;
+        w[c].y = (mystep == i) ? d.y : w[c].y;
+      });
     });
     // back substitution with L^H (unit upper triangular): v_j = w_j - sum_{i>j} conj(L[i][j]) v_i
     static_rfor<0, G>([&](auto jc) {
       constexpr int j = decltype(jc)::value;
-      if (j < N) {
-        static_for<0, NC>([&](auto cc) {
-          constexpr int c = decltype(cc)::value;
-          cx<T> t = mk<T>(0, 0);
-          if (live && mystep > j) cfmacj(t, a[j], w[c]);
-          t = group_sum<G>(t);
-          if (mystep == j) {
-            w[c].x -= t.x;
-            w[c].y -= t.y;
-          }
-        });
-      }
+      const cx<T> lj = csel(mystep > j, mk<T>(a[j].x, -a[j].y));
+      static_for<0, NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const cx<T> t = group_sum<G>(cmul(lj, w[c]));
+        w[c].x = (mystep == j) ? w[c].x - t.x : w[c].x;
+        w[c].y = (mystep == j) ? w[c].y - t.y : w[c].y;
+      });
     });
     static_for<0, NC>([&](auto cc) { g[decltype(cc)::value] = w[decltype(cc)::value]; });
   }
@@ -765,18 +762,18 @@ __device__ __forceinline__ void build_loop(const ProgK& P, int lane, LU<T, G>& l
   const int N = P.rec_n;
   static_for<0, G>([&](auto cc) {
     constexpr int c = decltype(cc)::value;
-    lu.a[c] = mk<T>(c == lane ? T(1) : T(0), T(0));
+    lu.a[c] = mk<T>((c == lane && lane < N) ? T(1) : T(0), T(0));  // identity over the live width only
   });
   for (int i = 0; i < P.n_msteps; ++i) {
     const Step st = P.msteps[i];
-    apply_op<T, G, G>(P.ops[st.op], lane, lu.a, N, (st.flags & ST_IDENT) != 0, hc, tid);
+    apply_op<T, G, G>(P.ops[st.op], lane, lu.a, G, (st.flags & ST_IDENT) != 0, hc, tid);
   }
   static_for<0, G>([&](auto cc) {
     constexpr int c = decltype(cc)::value;
     lu.a[c].x = (c == lane ? T(1) : T(0)) - lu.a[c].x;
     lu.a[c].y = -lu.a[c].y;
   });
-  lu.factor(lane, N);
+  lu.factor(lane);  // rows / columns >= N of A are identity
 }
 
 // ------------------------------------------------------------------------------- kernel arguments
@@ -858,7 +855,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant
       for (int i = 0; i < P.n_fsteps; ++i) {
         const Step st = P.fsteps[i];
         apply_op<T, G, CC>(P.ops[st.op], lane, S, CC, false, hc, tid);
-        if (st.flags & ST_SOLVE) lu.template solve<CC>(lane, P.rec_n, S);
+        if (st.flags & ST_SOLVE) lu.template solve<CC>(lane, S);
       }
       if (valid && lane < P.out_ch) {
 #pragma unroll
@@ -937,7 +934,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
         if (st.flags & ST_SAVE_X) put(slot_x, S);
         if (st.flags & ST_SAVE) put(slot++, S);
         apply_op<T, G, CC>(P.ops[st.op], lane, S, CC, false, hc, tid);
-        if (st.flags & ST_SOLVE) lu.template solve<CC>(lane, P.rec_n, S);
+        if (st.flags & ST_SOLVE) lu.template solve<CC>(lane, S);
         if (st.flags & ST_ADD_X) {
           cx<T> X[CC];
           get(slot_x, X);
@@ -972,7 +969,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
       // ---- reverse sweep
       for (int i = 0; i < P.n_rsteps; ++i) {
         const Step st = P.rsteps[i];
-        if (st.flags & RS_ADJ) lu.template solve_adj<CC>(lane, P.rec_n, g);
+        if (st.flags & RS_ADJ) lu.template solve_adj<CC>(lane, g);
         cx<T> Sin[CC];
         get(--slot, Sin);
         backprop_op<T, G, CC>(P.ops[st.op], ctx, lane, Sin, g, (st.flags & RS_NEED_GIN) != 0, acc, first_chunk, hc,

@@ -98,3 +98,26 @@ def test_c128_vs_oracle_and_golden(name):
     # and directly against the reference's stored outputs (its own float32 internals allowed for)
     ref_tol = max(10 * tol, 1.05 * float(g["ref_fp32_noise"]))
     assert rel_err(Y.detach().cpu().numpy()[:, g["bins"]], g["Y"]) <= ref_tol
+
+
+FDN_CASES = ["cfg2_fdn8_full", "fdn6_example", "fdn8_batch3", "fdn16", "fdn32", "fdn8_fracdelay", "recursion_filters"]
+
+
+@pytest.mark.parametrize("name", FDN_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_generic_interpreter_on_fdn_cases(name, dtype, monkeypatch):
+    """FDN-shaped programs normally take the pattern-specialised loop kernels (fsweep_loop.cuh); the
+    generic step-table interpreter must give the same answers on them."""
+    monkeypatch.setenv("FSWEEP_DISABLE_LOOP_KERNEL", "1")
+    saved = dict(sweep._PLANS)
+    sweep._PLANS.clear()
+    try:
+        case, g, Y, ferr, gerrs, missing = run_case(name, dtype)
+    finally:
+        sweep._PLANS.clear()
+        sweep._PLANS.update(saved)
+    assert not missing
+    if dtype == torch.float32:
+        assert run_case.mag_err <= 1e-4 and all(e <= 1e-3 for e in gerrs.values())
+    else:
+        assert ferr <= 1e-9 and all(e <= 1e-6 for e in gerrs.values())
