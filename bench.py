@@ -247,10 +247,9 @@ def gpu_arm(args):
     t_dev, loss = run(args.steps, (x_dev, y_dev))
     barrier()
     launches = sweep.launch_count - launches0
-    # keep the GPU under the same load long enough for at least a few clock samples
-    t_probe0 = time.time()
-    while time.time() - t_probe0 < 0.3:
-        run(20, (x_dev, y_dev))
+    # keep the GPU under the same load long enough for a few clock samples; a FIXED number of steps,
+    # because every step is a collective when world > 1
+    run(max(300, args.steps), (x_dev, y_dev))
     clocks = sampler.stop()
 
     # end to end: inputs in pinned host memory, H2D inside the timed region, loss read back
@@ -299,9 +298,16 @@ def gpu_arm(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # a captured graph that contains NCCL work keeps the communicator busy: ProcessGroupNCCL's teardown
+        # (destroy_process_group, or its destructor at interpreter exit) then blocks.  Drop the graphs, sync,
+        # meet at a last barrier and leave without running the destructors.
         import torch.distributed as dist
 
-        dist.destroy_process_group()
+        trainer._graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def kernel_roofline(model, x_dev, flush, reps=30):
@@ -356,10 +362,10 @@ def kernel_roofline(model, x_dev, flush, reps=30):
 
     t_bwd = timed(bwd)
     ach = bytes_per_launch / t_bwd / 1e9
-    return {"bound": "hbm", "kernel": "fsweep_bwd_kernel<float,8,1>", "achieved": ach, "peak": peak, "unit": "GB/s",
+    return {"bound": "hbm", "kernel": "fsweep_loop_bwd_kernel<float,8>", "achieved": ach, "peak": peak, "unit": "GB/s",
             "frac": ach / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else which,
             "traffic": None, "us_per_launch": t_bwd * 1e6, "algorithmic_bytes_per_launch": bytes_per_launch,
-            "forward_kernel": {"kernel": "fsweep_fwd_kernel<float,8,1>", "us_per_launch": t_fwd * 1e6,
+            "forward_kernel": {"kernel": "fsweep_loop_fwd_kernel<float,8>", "us_per_launch": t_fwd * 1e6,
                                "achieved": bytes_per_launch / t_fwd / 1e9, "frac": bytes_per_launch / t_fwd / 1e9 / peak},
             "note": "config 2 moves 0.58 MB per launch and does ~2-4 kflop per bin: it is latency/FP32 bound, "
                     "not HBM bound (SURVEY.md §8d); the HBM fraction is reported as the contract asks"}

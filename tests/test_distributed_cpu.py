@@ -1,0 +1,92 @@
+"""CPU, world_size = 2, gloo: the multi-GPU host logic (bin-range / batch sharding, one all-reduce of
+the flat gradient buffer with the losses in its tail) gives the same training trajectory as a single
+process.  The sweep itself runs through the float64 ABI emulator (tests/cpu_emulator.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NFFT, N, STEPS = 1024, 4, 3
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _build(batch):
+    from flamo_b200 import workloads as W
+    from flamo_b200.optimize.loss import mse_loss, sparsity_loss
+    from flamo_b200.processor import dsp, system
+
+    torch.manual_seed(7)
+    core = W.build(W.fdn(N, delays=[101, 157, 211, 263]), dsp, system, NFFT, 30.0, dtype=torch.float64)
+    model = system.Shell(core, dsp.FFT(NFFT, dtype=torch.float64),
+                         dsp.Transform(lambda x: torch.abs(x), dtype=torch.float64))
+    M = NFFT // 2 + 1
+    g = torch.Generator().manual_seed(3)
+    x = torch.zeros(batch, M, 1, dtype=torch.float64)
+    x[:, 0, :] = 1.0 + 0.1 * torch.arange(batch, dtype=torch.float64).view(-1, 1)  # items differ
+    y = 1.0 + 0.05 * torch.rand(batch, M, 1, generator=g, dtype=torch.float64)
+    return model, x, y, mse_loss, sparsity_loss
+
+
+def _train(trainer_cls, model, x, y, mse_loss, sparsity_loss, **kw):
+    tr = trainer_cls(model, max_epochs=1, lr=1e-2, log=False, device="cpu", **kw)
+    tr.register_criterion(mse_loss(nfft=NFFT), 1)
+    tr.register_criterion(sparsity_loss(), 0.2, requires_model=True)
+    losses = [tr.train_step((x, y)) for _ in range(STEPS)]
+    return losses, [p.detach().clone() for p in model.parameters()]
+
+
+def _worker(rank, world, port, shard, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_emulator
+    from flamo_b200.parallel import DataParallelTrainer
+
+    cpu_emulator.install()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        model, x, y, mse_loss, sparsity_loss = _build(batch=2)
+        if shard == "batch":
+            x, y = x[rank:rank + 1], y[rank:rank + 1]  # each rank trains its own item
+        losses, params = _train(DataParallelTrainer, model, x, y, mse_loss, sparsity_loss, shard=shard)
+        if rank == 0:
+            torch.save({"losses": losses, "params": params}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shard", ["bins", "batch"])
+def test_two_ranks_match_single_process(shard, tmp_path, emulated_backend):
+    from flamo_b200.optimize.trainer import Trainer
+
+    model, x, y, mse_loss, sparsity_loss = _build(batch=2)
+    ref_losses, ref_params = _train(Trainer, model, x, y, mse_loss, sparsity_loss)
+    out = str(tmp_path / "rank0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), shard, out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert np.allclose(got["losses"], ref_losses, rtol=1e-9), (got["losses"], ref_losses)
+    for a, b in zip(got["params"], ref_params):
+        assert torch.allclose(a, b, rtol=1e-8, atol=1e-10)
+
+
+def test_bin_range_partition():
+    from flamo_b200.parallel import bin_range
+
+    for M, W in ((48001, 8), (513, 4), (7, 3), (5, 8)):
+        cuts = [bin_range(M, r, W) for r in range(W)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == M
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        sizes = [b - a for a, b in cuts]
+        assert max(sizes) - min(sizes) <= 1
