@@ -143,8 +143,10 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
       return fail(FSWEEP_E_BADARG, "recursion output has %d channels but the next op takes %d", rec_n,
                   ops[post.front()].n_in);
   }
-  if (width > 32)
-    return fail(FSWEEP_E_UNSUPPORTED, "channel width %d > 32: not supported by the register-resident sweep", width);
+  if (width > 64)
+    return fail(FSWEEP_E_UNSUPPORTED, "channel width %d > 64: not supported by the register-resident sweep", width);
+  if (width > 32 && dtype != FSWEEP_C64)
+    return fail(FSWEEP_E_UNSUPPORTED, "channel width %d > 32 is float32-only (complex128 rows exceed the register file)", width);
   const int n_leaf = (int)(pre.size() + ff.size() + fb.size() + post.size());
   if (n_leaf > MAX_OPS) return fail(FSWEEP_E_UNSUPPORTED, "program has %d ops (max %d): split the series", n_leaf, MAX_OPS);
 
@@ -271,7 +273,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   if (!(no_loop && no_loop[0] == '1') && rec >= 0 && pre.size() <= 1 && post.size() <= 1 && fb.size() == 1 &&
       ops[fb[0]].kind == FSWEEP_OP_GAIN &&
       (pre.empty() || ops[pre[0]].kind == FSWEEP_OP_GAIN) && (post.empty() || ops[post[0]].kind == FSWEEP_OP_GAIN) &&
-      (dtype == FSWEEP_C64 || G <= 16)) {
+      G <= 32 && (dtype == FSWEEP_C64 || G <= 16)) {
     bool ok = true;
     for (int i : ff) ok = ok && kind_is_diag(ops[i].kind);
     for (int s2 = 0; s2 < P.n_ops; ++s2) ok = ok && P.ops[s2].acc_mode != ACC_GLOBAL;
@@ -346,7 +348,8 @@ cudaError_t by_group(int G, F&& f) {
     case 4: return f(std::integral_constant<int, 4>());
     case 8: return f(std::integral_constant<int, 8>());
     case 16: return f(std::integral_constant<int, 16>());
-    default: return f(std::integral_constant<int, 32>());
+    case 32: return f(std::integral_constant<int, 32>());
+    default: return f(std::integral_constant<int, 64>());
   }
 }
 
@@ -432,7 +435,7 @@ extern "C" int fsweep_forward(const fsweep_plan_t* plan_c, const void* const* co
   const bool loop = plan->loop_fast;
   LaunchCfg cfg;
   cfg.smem = smem_fwd(plan);
-  if (cfg.smem > 200 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "forward needs %zu bytes of shared memory", cfg.smem);
+  if (cfg.smem > 220 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "forward needs %zu bytes of shared memory", cfg.smem);
   cfg.stream = (cudaStream_t)stream;
   cudaError_t e;
   cfg.grid = pick_grid(plan, cc, false, cfg.smem, n_bins, &e, loop);
@@ -484,7 +487,7 @@ extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* c
   const int cc = loop ? 1 : cc_of(batch * cols);
   LaunchCfg cfg;
   cfg.smem = smem_bwd(plan, cc);
-  if (cfg.smem > 200 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "backward needs %zu bytes of shared memory", cfg.smem);
+  if (cfg.smem > 220 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "backward needs %zu bytes of shared memory", cfg.smem);
   cfg.stream = st;
   cudaError_t e;
   cfg.grid = pick_grid(plan, cc, true, cfg.smem, n_bins, &e, loop);

@@ -48,6 +48,7 @@ static cudaError_t occ_t(bool bwd, size_t smem, int* n) {
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, k, BLOCK, smem);
 }
 
+#if FSWEEP_G <= 32
 #define FSWEEP_DISPATCH(fn, ...)                                         \
   if (dtype == FSWEEP_C64) {                                             \
     if (cc == 1) return fn<float, FSWEEP_G, 1>(__VA_ARGS__);             \
@@ -56,6 +57,14 @@ static cudaError_t occ_t(bool bwd, size_t smem, int* n) {
     if (cc == 1) return fn<double, FSWEEP_G, 1>(__VA_ARGS__);            \
     return fn<double, FSWEEP_G, 4>(__VA_ARGS__);                         \
   }
+#else  // two warps per bin: float32 only (a row of 64 complex128 does not fit the register file)
+#define FSWEEP_DISPATCH(fn, ...)                                         \
+  if (dtype == FSWEEP_C64) {                                             \
+    if (cc == 1) return fn<float, FSWEEP_G, 1>(__VA_ARGS__);             \
+    return fn<float, FSWEEP_G, 4>(__VA_ARGS__);                          \
+  }                                                                      \
+  return cudaErrorNotSupported;
+#endif
 
 template <>
 cudaError_t launch_fwd<FSWEEP_G>(int dtype, int cc, const LaunchCfg& cfg, const ProgK& P, const SweepArgs& A) {
@@ -70,7 +79,8 @@ cudaError_t occupancy<FSWEEP_G>(int dtype, int cc, bool bwd, size_t smem, int* b
   FSWEEP_DISPATCH(occ_t, bwd, smem, blocks_per_sm)
 }
 
-// ---- pattern-specialised FDN-loop kernels (float for every G; double up to G = 16: registers)
+// ---- pattern-specialised FDN-loop kernels (float for every G <= 32; double up to G = 16: registers)
+#if FSWEEP_G <= 32
 constexpr bool kLoopDouble = FSWEEP_G <= 16;
 
 template <typename T, int G, bool BWD>
@@ -115,5 +125,19 @@ cudaError_t occupancy_loop<FSWEEP_G>(int dtype, bool bwd, size_t smem, int* n) {
     return bwd ? occ_loop_t<double, FSWEEP_G, true>(smem, n) : occ_loop_t<double, FSWEEP_G, false>(smem, n);
   return cudaErrorNotSupported;
 }
+#else
+template <>
+cudaError_t launch_loop_fwd<FSWEEP_G>(int, const LaunchCfg&, const ProgK&, const LoopInfo&, const SweepArgs&) {
+  return cudaErrorNotSupported;
+}
+template <>
+cudaError_t launch_loop_bwd<FSWEEP_G>(int, const LaunchCfg&, const ProgK&, const LoopInfo&, const SweepArgs&) {
+  return cudaErrorNotSupported;
+}
+template <>
+cudaError_t occupancy_loop<FSWEEP_G>(int, bool, size_t, int*) {
+  return cudaErrorNotSupported;
+}
+#endif
 
 }  // namespace fsweep

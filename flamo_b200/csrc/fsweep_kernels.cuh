@@ -172,18 +172,108 @@ __device__ __forceinline__ bool czero(cx<T> a) {
   return a.x == T(0) && a.y == T(0);
 }
 
+// ---- group exchange.  G <= 32: warp shuffles.  G == 64: the group is two warps of the same CTA (threads
+// 64g .. 64g+63); values cross through a static shared-memory buffer, ordered by a 64-thread named barrier
+// (id 1 + g).  All callers keep control flow uniform inside a group, so the barriers always match up.
+constexpr int XV = 4;  // widest vector exchanged at once
+__device__ __forceinline__ void gbar64() { asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory"); }
+template <typename T>
+__device__ __forceinline__ cx<T>* xbuf64() {
+  __shared__ double2 buf[BLOCK / 64][XV][64];
+  return reinterpret_cast<cx<T>*>(&buf[threadIdx.x >> 6][0][0]);
+}
+
 template <int G, typename T>
 __device__ __forceinline__ cx<T> shfl(cx<T> v, int src) {
-  return mk<T>(__shfl_sync(FULL, v.x, src, G), __shfl_sync(FULL, v.y, src, G));
+  if constexpr (G == 64) {
+    cx<T>* b = xbuf64<T>();
+    b[threadIdx.x & 63] = v;
+    gbar64();
+    cx<T> r = b[src & 63];
+    gbar64();
+    return r;
+  } else {
+    return mk<T>(__shfl_sync(FULL, v.x, src, G), __shfl_sync(FULL, v.y, src, G));
+  }
+}
+// NC values from lane `src` in one exchange
+template <int G, typename T, int NC>
+__device__ __forceinline__ void shflv(const cx<T> (&v)[NC], int src, cx<T> (&out)[NC]) {
+  if constexpr (G == 64) {
+    static_assert(NC <= XV, "vector exchange too wide");
+    cx<T>* b = xbuf64<T>();
+    static_for<0, NC>([&](auto cc) { b[decltype(cc)::value * 64 + (threadIdx.x & 63)] = v[decltype(cc)::value]; });
+    gbar64();
+    static_for<0, NC>([&](auto cc) { out[decltype(cc)::value] = b[decltype(cc)::value * 64 + (src & 63)]; });
+    gbar64();
+  } else {
+    static_for<0, NC>([&](auto cc) { out[decltype(cc)::value] = shfl<G>(v[decltype(cc)::value], src); });
+  }
 }
 template <int G, typename T>
 __device__ __forceinline__ cx<T> group_sum(cx<T> v) {
+  if constexpr (G == 64) {
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) {
-    v.x += __shfl_xor_sync(FULL, v.x, o, G);
-    v.y += __shfl_xor_sync(FULL, v.y, o, G);
+    for (int o = 16; o > 0; o >>= 1) {
+      v.x += __shfl_xor_sync(FULL, v.x, o);
+      v.y += __shfl_xor_sync(FULL, v.y, o);
+    }
+    cx<T>* b = xbuf64<T>();
+    if ((threadIdx.x & 31) == 0) b[(threadIdx.x >> 5) & 1] = v;
+    gbar64();
+    cx<T> r = mk<T>(b[0].x + b[1].x, b[0].y + b[1].y);
+    gbar64();
+    return r;
+  } else {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      v.x += __shfl_xor_sync(FULL, v.x, o, G);
+      v.y += __shfl_xor_sync(FULL, v.y, o, G);
+    }
+    return v;
   }
-  return v;
+}
+template <int G, typename T, int NC>
+__device__ __forceinline__ void group_sumv(cx<T> (&v)[NC]) {
+  if constexpr (G == 64) {
+    static_assert(NC <= XV, "vector reduction too wide");
+    static_for<0, NC>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v[c].x += __shfl_xor_sync(FULL, v[c].x, o);
+        v[c].y += __shfl_xor_sync(FULL, v[c].y, o);
+      }
+    });
+    cx<T>* b = xbuf64<T>();
+    if ((threadIdx.x & 31) == 0) static_for<0, NC>([&](auto cc) { b[decltype(cc)::value * 64 + ((threadIdx.x >> 5) & 1)] = v[decltype(cc)::value]; });
+    gbar64();
+    static_for<0, NC>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      v[c] = mk<T>(b[c * 64].x + b[c * 64 + 1].x, b[c * 64].y + b[c * 64 + 1].y);
+    });
+    gbar64();
+  } else {
+    static_for<0, NC>([&](auto cc) { v[decltype(cc)::value] = group_sum<G>(v[decltype(cc)::value]); });
+  }
+}
+template <int G>
+__device__ __forceinline__ unsigned group_max(unsigned key) {
+  if constexpr (G == 64) {
+    key = __reduce_max_sync(FULL, key);
+    __shared__ unsigned kb[BLOCK / 64][2];
+    if ((threadIdx.x & 31) == 0) kb[threadIdx.x >> 6][(threadIdx.x >> 5) & 1] = key;
+    gbar64();
+    key = max(kb[threadIdx.x >> 6][0], kb[threadIdx.x >> 6][1]);
+    gbar64();
+    return key;
+  } else if constexpr (G == 32) {
+    return __reduce_max_sync(FULL, key);  // one REDUX when the group is the whole warp
+  } else {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(FULL, key, o, G));
+    return key;
+  }
 }
 
 __device__ __forceinline__ void sincospi_t(float a, float* s, float* c) { sincospif(a, s, c); }
@@ -485,17 +575,23 @@ __device__ __forceinline__ void apply_op(const OpK& op, int lane, cx<T> (&S)[NC]
       });
       return;
     }
-    cx<T> acc[NC];
-    static_for<0, NC>([&](auto cc) { acc[decltype(cc)::value] = mk<T>(0, 0); });
-    for (int n = 0; n < op.n_in; ++n) {
-      const cx<T> h = hrow[(size_t)n * BLOCK];
-      static_for<0, NC>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        cx<T> v = shfl<G>(S[c], n);
-        cfma(acc[c], h, v);
+    // column c of H S depends on column c of S only, so the columns are processed in place, CB at a time
+    // (keeps the accumulators at CB registers even for the NC == G matrix build)
+    constexpr int CB = NC < XV ? NC : XV;
+    static_for<0, NC / CB>([&](auto bc) {
+      constexpr int c0 = decltype(bc)::value * CB;
+      cx<T> acc[CB], blk[CB], v[CB];
+      static_for<0, CB>([&](auto cc) {
+        acc[decltype(cc)::value] = mk<T>(0, 0);
+        blk[decltype(cc)::value] = S[c0 + decltype(cc)::value];
       });
-    }
-    static_for<0, NC>([&](auto cc) { S[decltype(cc)::value] = acc[decltype(cc)::value]; });
+      for (int n = 0; n < op.n_in; ++n) {
+        const cx<T> h = hrow[(size_t)n * BLOCK];
+        shflv<G>(blk, n, v);
+        static_for<0, CB>([&](auto cc) { cfma(acc[decltype(cc)::value], h, v[decltype(cc)::value]); });
+      }
+      static_for<0, CB>([&](auto cc) { S[c0 + decltype(cc)::value] = acc[decltype(cc)::value]; });
+    });
   } else {
     const cx<T> h = hrow[0];
     static_for<0, NC>([&](auto cc) {
@@ -517,11 +613,11 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
     if (want) {
       for (int n = 0; n < op.n_in; ++n) {
         cx<T> gh = mk<T>(0, 0);
-        static_for<0, NC>([&](auto cc) {
-          constexpr int c = decltype(cc)::value;
-          cx<T> v = shfl<G>(Sin[c], n);
-          cfmac(gh, g[c], v);
-        });
+        {
+          cx<T> v[NC];
+          shflv<G>(Sin, n, v);
+          static_for<0, NC>([&](auto cc) { cfmac(gh, g[decltype(cc)::value], v[decltype(cc)::value]); });
+        }
         if (lane < op.n_out) {
           switch (op.kind) {
             case FSWEEP_OP_GAIN:
@@ -562,12 +658,17 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
       static_for<0, NC>([&](auto cc) { gin[decltype(cc)::value] = mk<T>(0, 0); });
       for (int n = 0; n < op.n_in; ++n) {
         const cx<T> h = hrow[(size_t)n * BLOCK];
+        cx<T> t[NC];
         static_for<0, NC>([&](auto cc) {
           constexpr int c = decltype(cc)::value;
-          cx<T> t = mk<T>(0, 0);
-          cfmacj(t, h, g[c]);  // conj(h) * g
-          t = group_sum<G>(t);
-          if (lane == n) gin[c] = t;
+          t[c] = mk<T>(0, 0);
+          cfmacj(t[c], h, g[c]);  // conj(h) * g
+        });
+        group_sumv<G>(t);
+        static_for<0, NC>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          gin[c].x = (lane == n) ? t[c].x : gin[c].x;
+          gin[c].y = (lane == n) ? t[c].y : gin[c].y;
         });
       }
       static_for<0, NC>([&](auto cc) { g[decltype(cc)::value] = gin[decltype(cc)::value]; });
@@ -659,21 +760,38 @@ struct LU {
     mystep = -1;
     dinv = mk<T>(1, 0);
     static_for<0, (G + 3) / 4>([&](auto i) { piv[decltype(i)::value] = 0u; });
+    __shared__ double2 rowbuf_raw[(G == 64) ? BLOCK / 64 : 1][(G == 64) ? 64 : 1];  // G == 64 pivot-row broadcast
+    cx<T>* rowbuf = reinterpret_cast<cx<T>*>(&rowbuf_raw[(G == 64) ? (threadIdx.x >> 6) : 0][0]);
+    (void)rowbuf;
     static_for<0, G>([&](auto kc) {
       constexpr int k = decltype(kc)::value;
       int who = 0;
       if constexpr (G > 1) {
         unsigned key = (mag_key(a[k].x * a[k].x + a[k].y * a[k].y) & ~(unsigned)(G - 1)) | (unsigned)(G - 1 - lane);
         key = (mystep < 0) ? key : 0u;
-        if constexpr (G == 32) {
-          key = __reduce_max_sync(FULL, key);  // one REDUX when the group is the whole warp
-        } else {
-#pragma unroll
-          for (int o = G / 2; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(FULL, key, o, G));
-        }
+        key = group_max<G>(key);
         who = G - 1 - (int)(key & (unsigned)(G - 1));
       }
       piv[k / 4] |= (unsigned)who << (8 * (k % 4));
+      if constexpr (G == 64) {
+        // the pivot row crosses through shared memory once per step instead of one exchange per entry
+        if (lane == who) static_for<k, G>([&](auto jc) { rowbuf[decltype(jc)::value] = a[decltype(jc)::value]; });
+        gbar64();
+        const cx<T> inv = crcp(rowbuf[k]);
+        const bool act = (mystep < 0) && (lane != who);
+        const cx<T> l = csel(act, cmul(a[k], inv));
+        if (lane == who) {
+          mystep = k;
+          dinv = inv;
+        }
+        static_for<k + 1, G>([&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          cfnma(a[j], l, rowbuf[j]);
+        });
+        gbar64();
+        a[k].x = act ? l.x : a[k].x;
+        a[k].y = act ? l.y : a[k].y;
+      } else {
       const cx<T> inv = crcp(shfl<G>(a[k], who));
       const bool act = (mystep < 0) && (lane != who);
       const cx<T> l = csel(act, cmul(a[k], inv));  // multiplier; 0 for the pivot row and finished rows
@@ -687,6 +805,7 @@ struct LU {
       });
       a[k].x = act ? l.x : a[k].x;
       a[k].y = act ? l.y : a[k].y;
+      }
     });
   }
 
@@ -697,10 +816,9 @@ struct LU {
       constexpr int k = decltype(kc)::value;
       const int p = pivot_lane<k>();
       const cx<T> lk = csel(mystep > k, a[k]);
-      static_for<0, NC>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        cfnma(b[c], lk, shfl<G>(b[c], p));
-      });
+      cx<T> bk[NC];
+      shflv<G>(b, p, bk);
+      static_for<0, NC>([&](auto cc) { cfnma(b[decltype(cc)::value], lk, bk[decltype(cc)::value]); });
     });
     cx<T> x[NC];
     static_for<0, NC>([&](auto cc) { x[decltype(cc)::value] = mk<T>(0, 0); });
@@ -708,12 +826,14 @@ struct LU {
       constexpr int k = decltype(kc)::value;
       const int p = pivot_lane<k>();
       const cx<T> uk = csel(mystep < k, a[k]);
+      cx<T> t[NC], xk[NC];
+      static_for<0, NC>([&](auto cc) { t[decltype(cc)::value] = cmul(b[decltype(cc)::value], dinv); });
+      shflv<G>(t, p, xk);
       static_for<0, NC>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        const cx<T> xk = shfl<G>(cmul(b[c], dinv), p);
-        cfnma(b[c], uk, xk);
-        x[c].x = (lane == k) ? xk.x : x[c].x;
-        x[c].y = (lane == k) ? xk.y : x[c].y;
+        cfnma(b[c], uk, xk[c]);
+        x[c].x = (lane == k) ? xk[c].x : x[c].x;
+        x[c].y = (lane == k) ? xk[c].y : x[c].y;
       });
     });
     static_for<0, NC>([&](auto cc) { b[decltype(cc)::value] = x[decltype(cc)::value]; });
@@ -724,19 +844,18 @@ struct LU {
   template <int NC>
   __device__ __forceinline__ void solve_adj(int lane, cx<T> (&g)[NC]) const {
     cx<T> w[NC];
-    static_for<0, NC>([&](auto cc) {
-      constexpr int c = decltype(cc)::value;
-      w[c] = shfl<G>(g[c], mystep);
-    });
+    shflv<G>(g, mystep, w);
     const cx<T> dinvc = mk<T>(dinv.x, -dinv.y);
     // forward substitution with U^H (lower triangular): w_i = (g_i - sum_{j<i} conj(U[j][i]) w_j) / conj(U[i][i])
     static_for<0, G>([&](auto ic) {
       constexpr int i = decltype(ic)::value;
       const cx<T> ui = csel(mystep < i, mk<T>(a[i].x, -a[i].y));
+      cx<T> t[NC];
+      static_for<0, NC>([&](auto cc) { t[decltype(cc)::value] = cmul(ui, w[decltype(cc)::value]); });
+      group_sumv<G>(t);
       static_for<0, NC>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        const cx<T> t = group_sum<G>(cmul(ui, w[c]));
-        const cx<T> d = cmul(mk<T>(w[c].x - t.x, w[c].y - t.y), dinvc);
+        const cx<T> d = cmul(mk<T>(w[c].x - t[c].x, w[c].y - t[c].y), dinvc);
         w[c].x = (mystep == i) ? d.x : w[c].x;
         w[c].y = (mystep == i) ? d.y : w[c].y;
       });
@@ -745,11 +864,13 @@ struct LU {
     static_rfor<0, G>([&](auto jc) {
       constexpr int j = decltype(jc)::value;
       const cx<T> lj = csel(mystep > j, mk<T>(a[j].x, -a[j].y));
+      cx<T> t[NC];
+      static_for<0, NC>([&](auto cc) { t[decltype(cc)::value] = cmul(lj, w[decltype(cc)::value]); });
+      group_sumv<G>(t);
       static_for<0, NC>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        const cx<T> t = group_sum<G>(cmul(lj, w[c]));
-        w[c].x = (mystep == j) ? w[c].x - t.x : w[c].x;
-        w[c].y = (mystep == j) ? w[c].y - t.y : w[c].y;
+        w[c].x = (mystep == j) ? w[c].x - t[c].x : w[c].x;
+        w[c].y = (mystep == j) ? w[c].y - t[c].y : w[c].y;
       });
     });
     static_for<0, NC>([&](auto cc) { g[decltype(cc)::value] = w[decltype(cc)::value]; });
