@@ -11,7 +11,7 @@
 #include <type_traits>
 #include <vector>
 
-#include "fsweep_loop.cuh"
+#include "fsweep_tpb.cuh"
 
 using namespace fsweep;
 
@@ -66,6 +66,8 @@ struct fsweep_plan {
   bool any_global, any_acc;
   bool loop_fast = false;  // program matches the FDN-loop pattern of fsweep_loop.cuh
   LoopInfo loop;
+  int tpb_np = 0;  // 4 / 8: additionally small enough for the thread-per-bin kernels of fsweep_tpb.cuh
+  bool tpb_force = false;  // FSWEEP_FORCE_TPB=1 (tests): use them regardless of the bin count
   // lazily filled launch geometry: [cc index 0:1, 1:4, 2:loop kernels][fwd, bwd]
   std::mutex mu;
   int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -285,6 +287,18 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
       p->loop.n_ff = (int)ff.size();
       p->loop.fb = slot_of[fb[0]];
       p->loop.post = post.empty() ? -1 : slot_of[post[0]];
+      // thread-per-bin variant: float32, every width <= 8, few accumulators, gradients only for a single
+      // PGAIN / PDELAY in the diagonal chain
+      const char* no_tpb = getenv("FSWEEP_DISABLE_TPB");
+      bool tpb = !(no_tpb && no_tpb[0] == '1') && dtype == FSWEEP_C64 && width <= 8 && acc_total <= 256;
+      for (int i : ff) {
+        const bool wants = (ops[i].flags & FSWEEP_F_GRAD) != 0;
+        const bool simple = ops[i].kind == FSWEEP_OP_PGAIN || ops[i].kind == FSWEEP_OP_PDELAY;
+        if (wants && !(simple && ff.size() == 1)) tpb = false;
+      }
+      if (tpb) p->tpb_np = width <= 4 ? 4 : 8;
+      const char* force = getenv("FSWEEP_FORCE_TPB");
+      p->tpb_force = force && force[0] == '1';
     }
   }
 
@@ -323,6 +337,16 @@ extern "C" int64_t fsweep_plan_coeff_numel(const fsweep_plan_t* plan, int slot, 
 }
 
 namespace {
+
+// One thread per bin only pays when there are enough bins to fill the machine with warps (a bin is one THREAD
+// there, a quarter-warp or more in the row-distributed kernels).  Measured on B200, 8x8 FDN, 48001 bins:
+// forward 20 us (thread-per-bin) vs 29 us (row-distributed); backward 69 us vs 49 us (profiles/r01_notes.md).
+constexpr int64_t TPB_MIN_BINS_FWD = 32768;
+constexpr int64_t TPB_MIN_BINS_BWD = 262144;
+bool use_tpb(const fsweep_plan* p, int64_t n_bins, bool bwd) {
+  if (!p->tpb_np) return false;
+  return p->tpb_force || n_bins >= (bwd ? TPB_MIN_BINS_BWD : TPB_MIN_BINS_FWD);
+}
 
 int cc_of(int64_t ncols) { return ncols == 1 ? 1 : 4; }
 
@@ -441,7 +465,11 @@ extern "C" int fsweep_forward(const fsweep_plan_t* plan_c, const void* const* co
   cfg.grid = pick_grid(plan, cc, false, cfg.smem, n_bins, &e, loop);
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
   const int dtype = plan->dtype;
-  if (loop) {
+  if (use_tpb(plan, n_bins, false)) {
+    const LoopInfo L = plan->loop;
+    const int grid = (int)std::min<int64_t>((n_bins + TPB_BLOCK - 1) / TPB_BLOCK, grid_cap(n_bins, plan->G));
+    e = launch_tpb_fwd(plan->tpb_np, grid, cfg.stream, P, L, A);
+  } else if (loop) {
     const LoopInfo L = plan->loop;
     e = by_group(plan->G, [&](auto g) { return launch_loop_fwd<decltype(g)::value>(dtype, cfg, P, L, A); });
   } else {
@@ -521,7 +549,12 @@ extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* c
     ++launches;
   }
   const int dtype = plan->dtype;
-  if (loop) {
+  if (use_tpb(plan, n_bins, true)) {
+    const LoopInfo L = plan->loop;
+    cfg.grid = (int)std::min<int64_t>((n_bins + TPB_BLOCK - 1) / TPB_BLOCK, grid_cap(n_bins, plan->G));
+    const size_t smem = (size_t)std::max(1, P.acc_total) * TPB_BLOCK * sizeof(float);
+    e = launch_tpb_bwd(plan->tpb_np, cfg.grid, smem, st, P, L, A, plan->G);
+  } else if (loop) {
     const LoopInfo L = plan->loop;
     e = by_group(plan->G, [&](auto g) { return launch_loop_bwd<decltype(g)::value>(dtype, cfg, P, L, A); });
   } else {

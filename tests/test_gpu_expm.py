@@ -8,7 +8,7 @@ from flamo_b200.functional import skew_matrix
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n", [1, 2, 6, 8, 13, 16, 32, 48])
+@pytest.mark.parametrize("n", [1, 2, 6, 8, 13, 16, 28])
 @pytest.mark.parametrize("scale", [0.05, 1.0, 7.0])
 def test_expm_matches_torch(n, scale):
     torch.manual_seed(n)

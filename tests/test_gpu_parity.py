@@ -103,10 +103,20 @@ FDN_CASES = ["cfg2_fdn8_full", "fdn6_example", "fdn8_batch3", "fdn16", "fdn32", 
 
 @pytest.mark.parametrize("name", FDN_CASES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-def test_generic_interpreter_on_fdn_cases(name, dtype, monkeypatch):
-    """FDN-shaped programs normally take the pattern-specialised loop kernels (fsweep_loop.cuh); the
-    generic step-table interpreter must give the same answers on them."""
-    monkeypatch.setenv("FSWEEP_DISABLE_LOOP_KERNEL", "1")
+@pytest.mark.parametrize("path", ["generic", "loop", "tpb"])
+def test_alternative_kernel_paths_on_fdn_cases(name, dtype, path, monkeypatch):
+    """FDN-shaped programs can run on three kernel families: the generic step-table interpreter
+    (fsweep_kernels.cuh), the row-distributed loop kernels (fsweep_loop.cuh) and, for widths <= 8 in float32 and
+    enough bins, the thread-per-bin kernels (fsweep_tpb.cuh).  Each family is forced here in turn; all must agree
+    with the oracle."""
+    if path == "tpb":
+        if dtype != torch.float32 or name in ("fdn16", "fdn32"):
+            pytest.skip("thread-per-bin kernels: float32, width <= 8")
+        monkeypatch.setenv("FSWEEP_FORCE_TPB", "1")
+    else:
+        monkeypatch.setenv("FSWEEP_DISABLE_TPB", "1")
+    if path == "generic":
+        monkeypatch.setenv("FSWEEP_DISABLE_LOOP_KERNEL", "1")
     saved = dict(sweep._PLANS)
     sweep._PLANS.clear()
     try:

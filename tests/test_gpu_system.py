@@ -184,7 +184,11 @@ def test_full_size_properties(name):
             a = m32(X.to(torch.complex64))
         with sweep.bin_shard(half, M):
             b = m32(X.to(torch.complex64))
-        assert torch.equal(torch.cat((a, b), dim=1), y32)
+        # (the kernel family is chosen from the number of bins in the launch, so the two halves may run on a
+        #  different family than the whole: equal to float32 rounding, not bit for bit -- bit-identity within
+        #  one family is asserted in test_bin_sharding_is_exact)
+        ab = torch.cat((a, b), dim=1)
+        assert float((ab - y32).abs().max() / y32.abs().max()) < 2e-6
 
 
 def test_config5_full_size_properties():
