@@ -42,6 +42,10 @@ ALIAS_DB = 30.0
 SEED = 130709
 METRIC = "freq-bins*channels/sec (Trainer.train_step)"
 UNIT = "bins*ch/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of the backward sweep kernel, one launch, from the committed
+# `ncu --set full` capture (profiles/r01e_ncu_full_sweep_kernels.md)
+NCU_TRAFFIC_BYTES = 661504
+NCU_TRAFFIC_SOURCE = "profiles/r01e_ncu_full_sweep_kernels.md (ncu --set full, fsweep_loop_bwd_kernel<float,8>)"
 WORKLOAD = "cfg2: e8_colorless_fdn 8x8 FDN (Gain->Recursion(parallelDelay,Matrix orthogonal)->Gain), nfft=96000, B=1"
 
 
@@ -357,18 +361,29 @@ def kernel_roofline(model, x_dev, flush, reps=30):
 
     t_fwd = timed(lambda: backend.forward(plan, ops, coefs, x4, y, 1, 0, EPI_ABS))
 
-    def bwd():  # main backward kernel alone: no gradient buffers -> no finalize launch
-        backend.backward(plan, ops, coefs, x4, gy, [None] * len(coefs), None, 1, 0, EPI_ABS)
+    # The training step's ONE sweep launch: backward kernel with the fused |.| + mse_loss criterion (it recomputes
+    # the forward states, forms dL/d|Y| from the target and sums the loss).  No gradient buffers are passed, so the
+    # only other launch inside the timed call is the one-warp loss finalize.
+    from flamo_b200._lib import CRIT_MSE_CHSUM
+
+    tgt = torch.ones((x4.shape[0], M), dtype=torch.float32, device=X.device)
+    loss = torch.empty((), dtype=torch.float32, device=X.device)
+
+    def bwd():
+        backend.loss(plan, ops, coefs, x4, tgt, CRIT_MSE_CHSUM, 1.0 / tgt.numel(), loss, [None] * len(coefs), None, 0)
 
     t_bwd = timed(bwd)
     ach = bytes_per_launch / t_bwd / 1e9
-    return {"bound": "hbm", "kernel": "fsweep_loop_bwd_kernel<float,8>", "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else which,
-            "traffic": None, "us_per_launch": t_bwd * 1e6, "algorithmic_bytes_per_launch": bytes_per_launch,
-            "forward_kernel": {"kernel": "fsweep_loop_fwd_kernel<float,8>", "us_per_launch": t_fwd * 1e6,
+    return {"bound": "hbm", "kernel": "fsweep_loop_bwd_kernel<float,8> (fused |.|+MSE criterion)", "achieved": ach,
+            "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else which,
+            "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
+            "us_per_launch": t_bwd * 1e6, "algorithmic_bytes_per_launch": bytes_per_launch,
+            "forward_kernel": {"kernel": "fsweep_tpb_fwd_kernel<8> (validation / inference only; not in the training step)",
+                               "us_per_launch": t_fwd * 1e6,
                                "achieved": bytes_per_launch / t_fwd / 1e9, "frac": bytes_per_launch / t_fwd / 1e9 / peak},
-            "note": "config 2 moves 0.58 MB per launch and does ~2-4 kflop per bin: it is latency/FP32 bound, "
-                    "not HBM bound (SURVEY.md §8d); the HBM fraction is reported as the contract asks"}
+            "note": "config 2 moves 0.58 MB per launch and does ~2-4 kflop per bin: it is instruction-issue / latency "
+                    "bound, not HBM bound (SURVEY.md §8d; profiles/); the HBM fraction is reported as the contract asks"}
 
 
 def main():

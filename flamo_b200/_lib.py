@@ -16,13 +16,14 @@ LIB_PATH = os.path.join(_HERE, "libfsweep.so")
 OK, E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_CUDA = 0, -1, -2, -3, -4
 C64, C128 = 0, 1
 EPI_NONE, EPI_ABS = 0, 1
+CRIT_MSE, CRIT_MSE_CHSUM = 1, 2
 OP_GAIN, OP_PGAIN, OP_SOS, OP_PSOS, OP_DELAY, OP_PDELAY, OP_TABLE, OP_PTABLE, OP_RECURSION = range(1, 10)
 F_ISINT, F_GRAD = 1, 2
 
 EXPORTS = [
     "fsweep_version", "fsweep_last_error", "fsweep_plan_create", "fsweep_plan_destroy",
     "fsweep_plan_num_coeffs", "fsweep_plan_coeff_numel", "fsweep_workspace_bytes",
-    "fsweep_forward", "fsweep_backward", "fsweep_last_launch_count",
+    "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward",
 ]
 
@@ -32,6 +33,14 @@ class Op(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("n_out", C.c_int32), ("n_in", C.c_int32), ("n_sections", C.c_int32),
         ("flags", C.c_uint32), ("n_ff", C.c_int32), ("n_fb", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Criterion(C.Structure):
+    """fsweep_criterion_t"""
+    _fields_ = [
+        ("kind", C.c_int32), ("reserved", C.c_int32), ("target", C.c_void_p), ("target_batch_stride", C.c_int64),
+        ("scale", C.c_double), ("loss", C.c_void_p),
     ]
 
 
@@ -79,6 +88,11 @@ def lib():
     L.fsweep_backward.restype = i32
     L.fsweep_backward.argtypes = [vp, C.POINTER(vp), vp, i64, vp, i64, C.POINTER(vp), vp, i64, i64, i64, i64, i64,
                                   i32, vp, C.c_size_t, vp]
+    L.fsweep_forward_loss.restype = i32
+    L.fsweep_forward_loss.argtypes = [vp, C.POINTER(vp), vp, i64, C.POINTER(Criterion), i64, i64, i64, vp, C.c_size_t, vp]
+    L.fsweep_backward_loss.restype = i32
+    L.fsweep_backward_loss.argtypes = [vp, C.POINTER(vp), vp, i64, C.POINTER(Criterion), C.POINTER(vp), vp, i64, i64,
+                                       i64, i64, vp, C.c_size_t, vp]
     L.fsweep_expm_max_n.restype = i32
     L.fsweep_expm_forward.restype = i32
     L.fsweep_expm_forward.argtypes = [vp, vp, i32, i32, vp]
@@ -130,6 +144,26 @@ class Plan:
         gp = (C.c_void_p * len(grad_ptrs))(*grad_ptrs)
         check(L.fsweep_backward(self.handle, cp, x_ptr, xbs, gy_ptr, gybs, gp, gx_ptr, gxbs, batch, cols, bin_begin,
                                 n_bins, epilogue, ws_ptr, ws_bytes, stream))
+        n = L.fsweep_last_launch_count()
+        self.launches += n
+        return n
+
+    def forward_loss(self, coef_ptrs, x_ptr, xbs, crit, batch, bin_begin, n_bins, ws_ptr, ws_bytes, stream):
+        L = lib()
+        cp = (C.c_void_p * len(coef_ptrs))(*coef_ptrs)
+        check(L.fsweep_forward_loss(self.handle, cp, x_ptr, xbs, C.byref(crit), batch, bin_begin, n_bins, ws_ptr,
+                                    ws_bytes, stream))
+        n = L.fsweep_last_launch_count()
+        self.launches += n
+        return n
+
+    def backward_loss(self, coef_ptrs, x_ptr, xbs, crit, grad_ptrs, gx_ptr, gxbs, batch, bin_begin, n_bins, ws_ptr,
+                      ws_bytes, stream):
+        L = lib()
+        cp = (C.c_void_p * len(coef_ptrs))(*coef_ptrs)
+        gp = (C.c_void_p * len(grad_ptrs))(*grad_ptrs)
+        check(L.fsweep_backward_loss(self.handle, cp, x_ptr, xbs, C.byref(crit), gp, gx_ptr, gxbs, batch, bin_begin,
+                                     n_bins, ws_ptr, ws_bytes, stream))
         n = L.fsweep_last_launch_count()
         self.launches += n
         return n

@@ -52,6 +52,7 @@ int row_len_of(const fsweep_op_t& o) {
 }
 
 constexpr int MAX_GRID = 2048;
+constexpr size_t LOSS_PARTIAL_BYTES = (size_t)MAX_GRID * sizeof(double);  // fused criterion: per-block error sums
 constexpr size_t SMEM_ACC_BUDGET = 64 * 1024;
 
 }  // namespace
@@ -430,17 +431,76 @@ extern "C" size_t fsweep_workspace_bytes(const fsweep_plan_t* plan, int64_t batc
   const size_t grid = (size_t)grid_cap(n_bins, plan->G);
   size_t partial = grid * (size_t)plan->prog.acc_per_lane * plan->G * rs;
   size_t gacc = (size_t)plan->prog.acc_total * rs;
-  return ((partial + 255) / 256) * 256 + ((gacc + 255) / 256) * 256 + 256;
+  return ((partial + 255) / 256) * 256 + ((gacc + 255) / 256) * 256 + 256 + LOSS_PARTIAL_BYTES;
 }
+
+namespace {
+
+// validates a fused criterion and fills the kernel-side fields; returns the internal epilogue code in *epi
+int setup_criterion(const fsweep_plan* plan, const fsweep_criterion_t* crit, int64_t n_bins, void* workspace,
+                    size_t workspace_bytes, SweepArgs& A, int* epi) {
+  if (!crit) return fail(FSWEEP_E_BADARG, "null criterion");
+  if (crit->kind != FSWEEP_CRIT_MSE && crit->kind != FSWEEP_CRIT_MSE_CHSUM)
+    return fail(FSWEEP_E_BADARG, "bad criterion kind %d", crit->kind);
+  if (!crit->target || !crit->loss) return fail(FSWEEP_E_BADARG, "criterion: null target / loss");
+  const size_t need = fsweep_workspace_bytes(plan, 1, 1, n_bins);
+  if (!workspace || workspace_bytes < need)
+    return fail(FSWEEP_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+  *epi = crit->kind == FSWEEP_CRIT_MSE ? EPI_ABS_MSE : EPI_ABSSUM_MSE;
+  A.tgt = crit->target;
+  A.tbs = crit->target_batch_stride;
+  A.crit_scale = crit->scale;
+  A.loss_partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + (need - LOSS_PARTIAL_BYTES));
+  return FSWEEP_OK;
+}
+
+void launch_loss_finalize(int dtype, int n_blocks, const SweepArgs& A, void* loss, cudaStream_t st) {
+  FinalizeArgs F;
+  memset(&F, 0, sizeof(F));
+  F.n_ops = 0;
+  F.n_blocks = n_blocks;
+  F.loss_partial = A.loss_partial;
+  F.loss = loss;
+  F.crit_scale = A.crit_scale;
+  if (dtype == FSWEEP_C64)
+    fsweep_finalize_kernel<float><<<dim3(1, 1), 128, 0, st>>>(F);
+  else
+    fsweep_finalize_kernel<double><<<dim3(1, 1), 128, 0, st>>>(F);
+}
+
+int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const void* x, int64_t x_batch_stride, void* y,
+                 int64_t y_batch_stride, int64_t batch, int64_t cols, int64_t bin_begin, int64_t n_bins, int epilogue,
+                 const fsweep_criterion_t* crit, void* workspace, size_t workspace_bytes, void* stream);
+
+}  // namespace
 
 extern "C" int fsweep_forward(const fsweep_plan_t* plan_c, const void* const* coeffs, const void* x,
                               int64_t x_batch_stride, void* y, int64_t y_batch_stride, int64_t batch, int64_t cols,
                               int64_t bin_begin, int64_t n_bins, int epilogue, void* stream) {
+  if (epilogue != FSWEEP_EPI_NONE && epilogue != FSWEEP_EPI_ABS) return fail(FSWEEP_E_BADARG, "bad epilogue %d", epilogue);
+  return forward_impl(plan_c, coeffs, x, x_batch_stride, y, y_batch_stride, batch, cols, bin_begin, n_bins, epilogue,
+                      nullptr, nullptr, 0, stream);
+}
+
+extern "C" int fsweep_forward_loss(const fsweep_plan_t* plan_c, const void* const* coeffs, const void* x,
+                                   int64_t x_batch_stride, const fsweep_criterion_t* crit, int64_t batch,
+                                   int64_t bin_begin, int64_t n_bins, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  if (!crit) return fail(FSWEEP_E_BADARG, "null criterion");
+  if (n_bins <= 0) return fail(FSWEEP_E_BADARG, "empty bin range in a fused criterion");
+  return forward_impl(plan_c, coeffs, x, x_batch_stride, nullptr, 0, batch, 1, bin_begin, n_bins, FSWEEP_EPI_ABS, crit,
+                      workspace, workspace_bytes, stream);
+}
+
+namespace {
+int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const void* x, int64_t x_batch_stride, void* y,
+                 int64_t y_batch_stride, int64_t batch, int64_t cols, int64_t bin_begin, int64_t n_bins, int epilogue,
+                 const fsweep_criterion_t* crit, void* workspace, size_t workspace_bytes, void* stream) {
   g_launches = 0;
   fsweep_plan* plan = const_cast<fsweep_plan*>(plan_c);
   int r = check_common(plan, coeffs, x, batch, cols, bin_begin, n_bins, epilogue);
   if (r) return r;
-  if (!y) return fail(FSWEEP_E_BADARG, "null y");
+  if (!y && !crit) return fail(FSWEEP_E_BADARG, "null y");
   if (n_bins == 0) return FSWEEP_OK;
   ProgK P = plan->prog;
   for (int s = 0; s < plan->n_coeffs; ++s) P.ops[s].coef = coeffs[s];
@@ -455,6 +515,7 @@ extern "C" int fsweep_forward(const fsweep_plan_t* plan_c, const void* const* co
   A.bin_begin = bin_begin;
   A.n_bins = n_bins;
   A.epilogue = epilogue;
+  if (crit && (r = setup_criterion(plan, crit, n_bins, workspace, workspace_bytes, A, &A.epilogue))) return r;
   const int cc = cc_of(batch * cols);
   const bool loop = plan->loop_fast;
   LaunchCfg cfg;
@@ -467,8 +528,8 @@ extern "C" int fsweep_forward(const fsweep_plan_t* plan_c, const void* const* co
   const int dtype = plan->dtype;
   if (use_tpb(plan, n_bins, false)) {
     const LoopInfo L = plan->loop;
-    const int grid = (int)std::min<int64_t>((n_bins + TPB_BLOCK - 1) / TPB_BLOCK, grid_cap(n_bins, plan->G));
-    e = launch_tpb_fwd(plan->tpb_np, grid, cfg.stream, P, L, A);
+    cfg.grid = (int)std::min<int64_t>((n_bins + TPB_BLOCK - 1) / TPB_BLOCK, grid_cap(n_bins, plan->G));
+    e = launch_tpb_fwd(plan->tpb_np, cfg.grid, cfg.stream, P, L, A);
   } else if (loop) {
     const LoopInfo L = plan->loop;
     e = by_group(plan->G, [&](auto g) { return launch_loop_fwd<decltype(g)::value>(dtype, cfg, P, L, A); });
@@ -477,7 +538,20 @@ extern "C" int fsweep_forward(const fsweep_plan_t* plan_c, const void* const* co
   }
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "forward launch: %s", cudaGetErrorString(e));
   g_launches = 1;
+  if (crit) {
+    launch_loss_finalize(dtype, cfg.grid, A, crit->loss, cfg.stream);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(FSWEEP_E_CUDA, "loss finalize launch: %s", cudaGetErrorString(e));
+    g_launches = 2;
+  }
   return FSWEEP_OK;
+}
+}  // namespace
+
+namespace {
+int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const void* x, int64_t x_batch_stride,
+                  const void* grad_y, int64_t gy_batch_stride, void* const* grad_coeffs, void* grad_x,
+                  int64_t gx_batch_stride, int64_t batch, int64_t cols, int64_t bin_begin, int64_t n_bins, int epilogue,
+                  const fsweep_criterion_t* crit, void* workspace, size_t workspace_bytes, void* stream);
 }
 
 extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* coeffs, const void* x,
@@ -485,14 +559,33 @@ extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* c
                                void* const* grad_coeffs, void* grad_x, int64_t gx_batch_stride, int64_t batch,
                                int64_t cols, int64_t bin_begin, int64_t n_bins, int epilogue, void* workspace,
                                size_t workspace_bytes, void* stream) {
+  if (epilogue != FSWEEP_EPI_NONE && epilogue != FSWEEP_EPI_ABS) return fail(FSWEEP_E_BADARG, "bad epilogue %d", epilogue);
+  return backward_impl(plan_c, coeffs, x, x_batch_stride, grad_y, gy_batch_stride, grad_coeffs, grad_x, gx_batch_stride,
+                       batch, cols, bin_begin, n_bins, epilogue, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int fsweep_backward_loss(const fsweep_plan_t* plan_c, const void* const* coeffs, const void* x,
+                                    int64_t x_batch_stride, const fsweep_criterion_t* crit, void* const* grad_coeffs,
+                                    void* grad_x, int64_t gx_batch_stride, int64_t batch, int64_t bin_begin,
+                                    int64_t n_bins, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!crit) return fail(FSWEEP_E_BADARG, "null criterion");
+  return backward_impl(plan_c, coeffs, x, x_batch_stride, nullptr, 0, grad_coeffs, grad_x, gx_batch_stride, batch, 1,
+                       bin_begin, n_bins, FSWEEP_EPI_ABS, crit, workspace, workspace_bytes, stream);
+}
+
+namespace {
+int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const void* x, int64_t x_batch_stride,
+                  const void* grad_y, int64_t gy_batch_stride, void* const* grad_coeffs, void* grad_x,
+                  int64_t gx_batch_stride, int64_t batch, int64_t cols, int64_t bin_begin, int64_t n_bins, int epilogue,
+                  const fsweep_criterion_t* crit, void* workspace, size_t workspace_bytes, void* stream) {
   g_launches = 0;
   fsweep_plan* plan = const_cast<fsweep_plan*>(plan_c);
   int r = check_common(plan, coeffs, x, batch, cols, bin_begin, n_bins, epilogue);
   if (r) return r;
-  if (!grad_y) return fail(FSWEEP_E_BADARG, "null grad_y");
+  if (!grad_y && !crit) return fail(FSWEEP_E_BADARG, "null grad_y");
   if (n_bins == 0) return fail(FSWEEP_E_BADARG, "empty bin range in backward");
   const size_t need = fsweep_workspace_bytes(plan, batch, cols, n_bins);
-  if (need > 256 && (!workspace || workspace_bytes < need))
+  if (need > 256 + LOSS_PARTIAL_BYTES && (!workspace || workspace_bytes < need))
     return fail(FSWEEP_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t rs = plan->dtype == FSWEEP_C64 ? 4 : 8;
@@ -541,6 +634,7 @@ extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* c
   A.epilogue = epilogue;
   A.partial = partial;
   A.gacc = gacc;
+  if (crit && (r = setup_criterion(plan, crit, n_bins, workspace, workspace_bytes, A, &A.epilogue))) return r;
 
   int launches = 0;
   if (plan->any_global) {
@@ -566,6 +660,11 @@ extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* c
   if (any_acc_wanted) {
     FinalizeArgs F;
     memset(&F, 0, sizeof(F));
+    if (crit) {
+      F.loss_partial = A.loss_partial;
+      F.loss = crit->loss;
+      F.crit_scale = A.crit_scale;
+    }
     F.n_ops = P.n_ops;
     F.G = plan->G;
     F.acc_per_lane = P.acc_per_lane;
@@ -587,7 +686,8 @@ extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* c
       if (o.grad && (o.acc_mode == ACC_SMEM || o.acc_mode == ACC_GLOBAL))
         max_total = std::max(max_total, o.n_out * o.row_len);
     }
-    dim3 grid((unsigned)std::min(1024, (max_total + 3) / 4), (unsigned)P.n_ops);  // 4 warps per block, 1 warp per element
+    // 4 warps per block, 1 warp per element; row n_ops of the grid sums the fused criterion's loss
+    dim3 grid((unsigned)std::min(1024, (max_total + 3) / 4), (unsigned)P.n_ops + (crit ? 1u : 0u));
     if (dtype == FSWEEP_C64)
       fsweep_finalize_kernel<float><<<grid, 128, 0, st>>>(F);
     else
@@ -595,7 +695,12 @@ extern "C" int fsweep_backward(const fsweep_plan_t* plan_c, const void* const* c
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "finalize launch: %s", cudaGetErrorString(e));
     ++launches;
+  } else if (crit) {
+    launch_loss_finalize(dtype, cfg.grid, A, crit->loss, st);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(FSWEEP_E_CUDA, "loss finalize launch: %s", cudaGetErrorString(e));
+    ++launches;
   }
   g_launches = launches;
   return FSWEEP_OK;
 }
+}  // namespace

@@ -912,7 +912,51 @@ struct SweepArgs {
   int epilogue;
   void* partial;  // backward: [grid][acc_per_lane * G]
   void* gacc;     // backward: [acc_total] (ACC_GLOBAL ops), zeroed by the host wrapper
+  // fused criterion (epilogue EPI_ABS_MSE / EPI_ABSSUM_MSE, cols == 1): y / gy are unused, dL/d|Y| is formed in
+  // the kernel from the target and the squared errors are summed per block
+  const void* tgt;       // real (batch, n_bins, out_ch) or (batch, n_bins); first processed bin
+  long long tbs;         // target batch stride in elements
+  double crit_scale;     // loss = crit_scale * sum e^2
+  double* loss_partial;  // [grid]
 };
+
+// internal epilogue codes of the fused criteria (the ABI passes an fsweep_criterion_t instead)
+constexpr int EPI_ABS_MSE = 2;     // e = |Y_r| - t_r          (nn.MSELoss on the magnitudes)
+constexpr int EPI_ABSSUM_MSE = 3;  // e = sum_r |Y_r| - t      (optimize/loss.py mse_loss)
+__device__ __forceinline__ bool epi_fused(int e) { return e >= EPI_ABS_MSE; }
+
+// Row-distributed fused criterion: `mag` = |Y_row| on lanes holding an output row (`live`), anything elsewhere.
+// Returns dL/d|Y_row| (upstream gradient 1) and adds this lane's share of the squared error to lacc.
+// Called with uniform control flow inside the group (the channel sum is a group reduction).
+template <typename T, int G>
+__device__ __forceinline__ T crit_rowdist(const SweepArgs& A, T mag, bool live, int row, int out_rows, long long bl,
+                                          int b, int lane, bool count, double& lacc) {
+  const T* tg = reinterpret_cast<const T*>(A.tgt) + (size_t)b * A.tbs;
+  T e;
+  if (A.epilogue == EPI_ABSSUM_MSE) {
+    const T tot = group_sum<G>(mk<T>(live ? mag : T(0), T(0))).x;
+    e = tot - __ldg(tg + bl);
+    if (count && lane == 0) lacc += (double)e * (double)e;
+  } else {
+    e = live ? mag - __ldg(tg + (size_t)bl * out_rows + row) : T(0);
+    if (count && live) lacc += (double)e * (double)e;
+  }
+  return (T)(2.0 * A.crit_scale) * e;
+}
+
+template <typename T>
+__device__ __forceinline__ void block_loss_store(double lacc, double* loss_partial) {
+  __shared__ double red[BLOCK / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lacc += __shfl_xor_sync(FULL, lacc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) s += red[w];
+    loss_partial[blockIdx.x] = s;
+  }
+}
 
 __device__ __forceinline__ cx<float> ld_cx(const cx<float>* p) {
   float2 v = __ldg(reinterpret_cast<const float2*>(p));
@@ -956,6 +1000,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant
   const long long n_iter = (A.n_bins + groups_total - 1) / groups_total;
   const int ncols_total = A.batch * A.cols;
   const cx<T>* x = reinterpret_cast<const cx<T>*>(A.x);
+  double lacc = 0.0;
 
   {
     const Ctx<T> c0 = make_ctx<T>(P, A.bin_begin);
@@ -978,7 +1023,14 @@ __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant
         apply_op<T, G, CC>(P.ops[st.op], lane, S, CC, false, hc, tid);
         if (st.flags & ST_SOLVE) lu.template solve<CC>(lane, S);
       }
-      if (valid && lane < P.out_ch) {
+      if (epi_fused(A.epilogue)) {  // cols == 1: q is the batch item
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          const int q = q0 + c < ncols_total ? q0 + c : ncols_total - 1;
+          crit_rowdist<T, G>(A, abs_t(S[c].x, S[c].y), lane < P.out_ch, lane, P.out_ch, bl, q, lane,
+                             valid && q0 + c < ncols_total, lacc);
+        }
+      } else if (valid && lane < P.out_ch) {
 #pragma unroll
         for (int c = 0; c < CC; ++c) {
           int q = q0 + c;
@@ -994,6 +1046,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant
       }
     }
   }
+  if (epi_fused(A.epilogue)) block_loss_store<T>(lacc, A.loss_partial);
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -1013,6 +1066,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
   const int ncols_total = A.batch * A.cols;
   const cx<T>* x = reinterpret_cast<const cx<T>*>(A.x);
   const int slot_x = P.n_slots - 1;
+  double lacc = 0.0;
 
   for (int i = 0; i < P.acc_per_lane; ++i) sacc[(size_t)i * BLOCK + tid] = T(0);
 
@@ -1072,7 +1126,16 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
       for (int c = 0; c < CC; ++c) {
         int q = q0 + c;
         g[c] = mk<T>(0, 0);
-        if (q < ncols_total && lane < P.out_ch) {
+        if (epi_fused(A.epilogue)) {
+          const bool inr = q < ncols_total;
+          const T mag = abs_t(S[c].x, S[c].y);
+          const T ga = crit_rowdist<T, G>(A, mag, lane < P.out_ch, lane, P.out_ch, bl, inr ? q : ncols_total - 1, lane,
+                                          valid && inr, lacc);
+          if (inr && lane < P.out_ch && mag > T(0)) {
+            const T r = ga * rcp_t(mag);
+            g[c] = mk<T>(r * S[c].x, r * S[c].y);
+          }
+        } else if (q < ncols_total && lane < P.out_ch) {
           int b = q / A.cols, cc = q - b * A.cols;
           size_t off = (size_t)b * A.gybs + ((size_t)bl * P.out_ch + lane) * A.cols + cc;
           if (A.epilogue == FSWEEP_EPI_ABS) {
@@ -1121,6 +1184,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
     for (int j = 0; j < BLOCK / G; ++j) s += sacc[(size_t)i * BLOCK + j * G + row];
     partial[e] = s;
   }
+  if (epi_fused(A.epilogue)) block_loss_store<T>(lacc, A.loss_partial);
 }
 
 // Sum the per-block partials (float64) and scatter into the caller's gradient buffers.
@@ -1133,6 +1197,10 @@ struct FinalizeArgs {
   int n_ops, G, acc_per_lane, n_blocks;
   const void* partial;
   const void* gacc;
+  // fused criterion: blockIdx.y == n_ops sums the per-block squared-error sums into *loss (real T)
+  const double* loss_partial;
+  void* loss;
+  double crit_scale;
   FinalizeOp ops[MAX_OPS];
 };
 
@@ -1140,6 +1208,15 @@ struct FinalizeArgs {
 template <typename T>
 __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_constant__ FinalizeArgs F) {
   const int opi = blockIdx.y;
+  if (opi == F.n_ops) {
+    if (F.loss == nullptr || blockIdx.x != 0 || threadIdx.x >= 32) return;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < F.n_blocks; b += 32) s += F.loss_partial[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *reinterpret_cast<T*>(F.loss) = (T)(F.crit_scale * s);
+    return;
+  }
   const FinalizeOp& op = F.ops[opi];
   if (op.grad == nullptr || (op.acc_mode != ACC_SMEM && op.acc_mode != ACC_GLOBAL)) return;
   const bool diag = !(op.kind == FSWEEP_OP_GAIN || op.kind == FSWEEP_OP_SOS || op.kind == FSWEEP_OP_DELAY);

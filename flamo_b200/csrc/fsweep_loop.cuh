@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_loop_fwd_kernel(const __grid_con
       wpc = __ldg(reinterpret_cast<const T*>(P.ops[L.post].coef) + lane);
   }
   const int out_rows = P.out_ch;
+  double lacc = 0.0;
 
   for (long long it = 0; it < n_iter; ++it) {
     long long bl = it * groups_total + gg;
@@ -152,7 +153,9 @@ __global__ void __launch_bounds__(BLOCK) fsweep_loop_fwd_kernel(const __grid_con
       cx<T> y[1] = {cmul(D, s)};
       lu.template solve<1>(lane, y);
       const cx<T> o = loop_output<T, G>(P, L, y[0], lane, wpc, hc, tid);
-      if (valid && lane < out_rows) {
+      if (epi_fused(A.epilogue)) {
+        crit_rowdist<T, G>(A, abs_t(o.x, o.y), lane < out_rows, lane, out_rows, bl, b, lane, valid, lacc);
+      } else if (valid && lane < out_rows) {
         size_t off = (size_t)b * A.ybs + ((size_t)bl * out_rows + lane) * A.cols + cc;
         if (A.epilogue == FSWEEP_EPI_ABS)
           reinterpret_cast<T*>(A.y)[off] = abs_t(o.x, o.y);
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_loop_fwd_kernel(const __grid_con
       }
     }
   }
+  if (epi_fused(A.epilogue)) block_loss_store<T>(lacc, A.loss_partial);
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -203,6 +207,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_loop_bwd_kernel(const __grid_con
   const bool want_fb = fbop.acc_mode == ACC_SMEM;
   const bool want_pre = L.pre >= 0 && P.ops[L.pre].acc_mode == ACC_SMEM;
   const bool want_post = L.post >= 0 && P.ops[L.post].acc_mode == ACC_SMEM;
+  double lacc = 0.0;
 
   for (long long it = 0; it < n_iter; ++it) {
     long long bl = it * groups_total + gg;
@@ -228,7 +233,17 @@ __global__ void __launch_bounds__(BLOCK) fsweep_loop_bwd_kernel(const __grid_con
       const cx<T> o = loop_output<T, G>(P, L, y, lane, wpc, hc, tid);
       // ---- output gradient (row-distributed over out_rows; replicated on all lanes when post1)
       cx<T> go = mk<T>(0, 0);
-      if (lane < out_rows || post1) {
+      if (epi_fused(A.epilogue)) {
+        // post1: o (row 0) is replicated on every lane of the group; only lane 0 counts the error
+        const T mag = abs_t(o.x, o.y);
+        const T ga = crit_rowdist<T, G>(A, mag, post1 ? lane == 0 : lane < out_rows, post1 ? 0 : lane, out_rows, bl, b,
+                                        lane, valid, lacc);
+        const T gab = post1 ? __shfl_sync(FULL, ga, 0, G > 32 ? 32 : G) : ga;
+        if ((lane < out_rows || post1) && mag > T(0)) {
+          const T r = gab * rcp_t(mag);
+          go = mk<T>(r * o.x, r * o.y);
+        }
+      } else if (lane < out_rows || post1) {
         const int row = post1 ? 0 : lane;
         size_t off = (size_t)b * A.gybs + ((size_t)bl * out_rows + row) * A.cols + cc;
         if (A.epilogue == FSWEEP_EPI_ABS) {
@@ -345,6 +360,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_loop_bwd_kernel(const __grid_con
     for (int j = 0; j < BLOCK / G; ++j) s += sacc[(size_t)i * BLOCK + j * G + row];
     partial[e] = s;
   }
+  if (epi_fused(A.epilogue)) block_loss_store<T>(lacc, A.loss_partial);
 }
 
 template <int G>

@@ -207,6 +207,35 @@ __device__ __forceinline__ void tpb_output(const ProgK& P, const LoopInfo& L, co
   });
 }
 
+// fused criterion, one thread per bin: e over this bin's output rows; returns dL/d|Y_r| per row in ga[]
+template <int NP>
+__device__ __forceinline__ void tpb_crit(const SweepArgs& A, const cx<float> (&o)[NP], int n_out, long long bl, int b,
+                                         float (&mag)[NP], float (&ga)[NP], double& lacc) {
+  const float* tg = reinterpret_cast<const float*>(A.tgt) + (size_t)b * A.tbs;
+  const float sc = (float)(2.0 * A.crit_scale);
+  float tot = 0.f;
+  static_for<0, NP>([&](auto rc) {
+    constexpr int r = decltype(rc)::value;
+    mag[r] = (r < n_out) ? abs_t(o[r].x, o[r].y) : 0.f;
+    tot += mag[r];
+  });
+  if (A.epilogue == EPI_ABSSUM_MSE) {
+    const float e = tot - __ldg(tg + bl);
+    lacc += (double)e * (double)e;
+    static_for<0, NP>([&](auto rc) { ga[decltype(rc)::value] = sc * e; });
+  } else {
+    static_for<0, NP>([&](auto rc) {
+      constexpr int r = decltype(rc)::value;
+      ga[r] = 0.f;
+      if (r < n_out) {
+        const float e = mag[r] - __ldg(tg + (size_t)bl * n_out + r);
+        lacc += (double)e * (double)e;
+        ga[r] = sc * e;
+      }
+    });
+  }
+}
+
 // ------------------------------------------------------------------------------------ forward
 template <int NP>
 __global__ void __launch_bounds__(TPB_BLOCK, 5) fsweep_tpb_fwd_kernel(const __grid_constant__ ProgK P,
@@ -217,6 +246,7 @@ __global__ void __launch_bounds__(TPB_BLOCK, 5) fsweep_tpb_fwd_kernel(const __gr
   const int ncols_total = A.batch * A.cols;
   const cx<float>* x = reinterpret_cast<const cx<float>*>(A.x);
   const int n_out = P.out_ch;
+  double lacc = 0.0;
 
   for (long long bl = (long long)blockIdx.x * TPB_BLOCK + threadIdx.x; bl < A.n_bins;
        bl += (long long)gridDim.x * TPB_BLOCK) {
@@ -232,6 +262,11 @@ __global__ void __launch_bounds__(TPB_BLOCK, 5) fsweep_tpb_fwd_kernel(const __gr
       static_for<0, NP>([&](auto mc) { y[decltype(mc)::value] = cmul(D[decltype(mc)::value], y[decltype(mc)::value]); });
       lu.solve(y);
       tpb_output<NP>(P, L, wpost, y, o);
+      if (epi_fused(A.epilogue)) {
+        float mag[NP], ga[NP];
+        tpb_crit<NP>(A, o, n_out, bl, b, mag, ga, lacc);
+        continue;
+      }
       static_for<0, NP>([&](auto rc) {
         constexpr int r = decltype(rc)::value;
         if (r < n_out) {
@@ -244,6 +279,7 @@ __global__ void __launch_bounds__(TPB_BLOCK, 5) fsweep_tpb_fwd_kernel(const __gr
       });
     }
   }
+  if (epi_fused(A.epilogue)) block_loss_store<float>(lacc, A.loss_partial);
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -267,6 +303,7 @@ __global__ void __launch_bounds__(TPB_BLOCK, 4) fsweep_tpb_bwd_kernel(const __gr
   const OpK& ffop = P.ops[L.ff_begin];  // gradient supported for a single-op chain only (host-checked)
   const bool want_ff = L.n_ff == 1 && ffop.acc_mode == ACC_SMEM;
   auto accp = [&](const OpK& op, int row, int e, float v) { sacc[(op.acc_off + row * op.row_len + e) * TPB_BLOCK + tid] += v; };
+  double lacc = 0.0;
 
   for (long long bl = (long long)blockIdx.x * TPB_BLOCK + tid; bl < A.n_bins; bl += (long long)gridDim.x * TPB_BLOCK) {
     const Ctx<float> ctx = make_ctx<float>(P, A.bin_begin + bl);
@@ -283,6 +320,18 @@ __global__ void __launch_bounds__(TPB_BLOCK, 4) fsweep_tpb_bwd_kernel(const __gr
       tpb_output<NP>(P, L, wpost, y, o);
       // ---- output gradient
       cx<float> go[NP];
+      if (epi_fused(A.epilogue)) {
+        float mag[NP], ga[NP];
+        tpb_crit<NP>(A, o, n_out, bl, b, mag, ga, lacc);
+        static_for<0, NP>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          go[r] = mk<float>(0.f, 0.f);
+          if (r < n_out && mag[r] > 0.f) {
+            const float t = ga[r] * rcp_t(mag[r]);
+            go[r] = mk<float>(t * o[r].x, t * o[r].y);
+          }
+        });
+      } else
       static_for<0, NP>([&](auto rc) {
         constexpr int r = decltype(rc)::value;
         go[r] = mk<float>(0.f, 0.f);
@@ -406,6 +455,7 @@ __global__ void __launch_bounds__(TPB_BLOCK, 4) fsweep_tpb_bwd_kernel(const __gr
       partial[(op.row_off + i) * G + row] = sum;
     }
   }
+  if (epi_fused(A.epilogue)) block_loss_store<float>(lacc, A.loss_partial);
 }
 
 cudaError_t launch_tpb_fwd(int np, int grid, cudaStream_t st, const ProgK& P, const LoopInfo& L, const SweepArgs& A);

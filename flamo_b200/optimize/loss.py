@@ -8,6 +8,8 @@ import torch.nn as nn
 class sparsity_loss(nn.Module):
     """-(sum|A| - N sqrt N) / (N (sqrt N - 1)) of the mapped feedback matrix (loss.py:36-63)."""
 
+    uses_prediction = False  # depends on the model only: the Trainer may skip materialising y_pred for it
+
     def forward(self, y_pred, y_target, model):
         core = model.get_core()
         mm = None

@@ -26,8 +26,11 @@ except Exception:  # pragma: no cover
 class Trainer:
     def __init__(self, net: nn.Module, max_epochs: int = 10, lr: float = 1e-3, patience: int = 5,
                  patience_delta: float = 0.01, step_size: int = 50, step_factor: float = 0.1, log: bool = True,
-                 train_dir: str = None, device: str = "cpu", graph: Optional[bool] = None):
+                 train_dir: str = None, device: str = "cpu", graph: Optional[bool] = None,
+                 fuse_criterion: bool = True):
         self.device = device
+        self.fuse_criterion = fuse_criterion  # evaluate a lone MSE criterion inside the sweep kernel when possible
+        self._unfusable = set()
         self.log = log
         self.net = net.to(device)
         self.max_epochs, self.lr = max_epochs, lr
@@ -96,15 +99,52 @@ class Trainer:
         for c, v in zip(self.criterion, values):
             log.setdefault(c.__class__.__name__, []).append(v)
 
+    # -- forward + criteria --------------------------------------------------------------------------
+    def _fused_kind(self, crit):
+        """ABI criterion kind when `crit` is one the sweep kernels evaluate themselves, else None."""
+        from .._lib import CRIT_MSE, CRIT_MSE_CHSUM
+        from .loss import mse_loss
+
+        if type(crit) is mse_loss:
+            return CRIT_MSE_CHSUM
+        if type(crit) is nn.MSELoss and crit.reduction == "mean":
+            return CRIT_MSE
+        return None
+
+    def _predict(self, inputs, targets):
+        """Returns (est, fused): the network output for the criteria, or — when exactly ONE registered criterion
+        consumes the prediction and it is an MSE the kernels can fuse with the |.| output layer — est = None and
+        fused = (criterion index, loss tensor) computed without materialising the prediction."""
+        users = [i for i, c in enumerate(self.criterion) if getattr(c, "uses_prediction", True)]
+        if self.fuse_criterion and len(users) == 1 and hasattr(self.net, "forward_loss"):
+            i = users[0]
+            kind = self._fused_kind(self.criterion[i])
+            key = (i, tuple(inputs.shape), tuple(targets.shape))
+            if kind is not None and not self.requires_model[i] and key not in self._unfusable:
+                loss = self.net.forward_loss(inputs, targets, kind)
+                if loss is not None:
+                    return None, (i, loss)
+                self._unfusable.add(key)
+        return self.net(inputs), None
+
+    def _criteria(self, est, fused, targets, weight=None):
+        parts, total = [], None
+        for i, (alpha, crit, needs_model) in enumerate(zip(self.alpha, self.criterion, self.requires_model)):
+            if fused is not None and fused[0] == i:
+                t = fused[1]
+            else:
+                t = crit(est, targets, self.net) if needs_model else crit(est, targets)
+            if weight is not None:
+                t = weight(i, t)
+            parts.append(t)
+            term = t if alpha == 1 else alpha * t
+            total = term if total is None else total + term
+        return total, parts
+
     def _losses(self, inputs, targets):
         """Forward + criteria: returns (total, [per-criterion tensors])."""
-        est = self.net(inputs)
-        parts, total = [], 0
-        for alpha, crit, needs_model in zip(self.alpha, self.criterion, self.requires_model):
-            t = crit(est, targets, self.net) if needs_model else crit(est, targets)
-            parts.append(t)
-            total = total + alpha * t
-        return total, parts
+        est, fused = self._predict(inputs, targets)
+        return self._criteria(est, fused, targets)
 
     # -- one optimisation step, as a pure device-side function (captured or eager) --------------------
     def _zero_grad(self):

@@ -65,17 +65,10 @@ class DataParallelTrainer(Trainer):
         M = self.net.nfft // 2 + 1
         b0, b1 = bin_range(M, self.rank, self.world)
         with sweep.bin_shard(b0, b1):
-            est = self.net(inputs)
+            est, fused = self._predict(inputs, targets)  # a fused criterion slices the target itself
         tg = targets[:, b0:b1] if targets.shape[1] == M else targets
-        parts, total = [], 0
-        for alpha, crit, needs_model in zip(self.alpha, self.criterion, self.requires_model):
-            if needs_model:
-                t = crit(est, tg, self.net) / self.world
-            else:
-                t = crit(est, tg) * ((b1 - b0) / M)
-            parts.append(t)
-            total = total + alpha * t
-        return total, parts
+        return self._criteria(est, fused, tg, weight=lambda i, t: t / self.world if self.requires_model[i]
+                              else t * ((b1 - b0) / M))
 
     def _sync(self, vals):
         if self.world == 1:

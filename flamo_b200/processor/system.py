@@ -377,6 +377,24 @@ class Shell(nn.Module):
         x = core(x, ext_param) if ext_param is not None else core(x)
         return out(x)
 
+    def forward_loss(self, x, target, kind: int, ext_param=None):
+        """criterion(self(x), target) with the |.| output layer and the criterion fused into the sweep kernel
+        (sweep.SweepLossFunction; kind = _lib.CRIT_MSE | CRIT_MSE_CHSUM).  Returns None when this Shell cannot be
+        fused (output layer is not |.|, core is not a single sweep launch, unexpected shapes): the caller then
+        evaluates self(x) and the criterion separately."""
+        core, out = self.__core, self.__output_layer
+        if not (self.fuse_output and _is_abs_layer(out) and hasattr(core, "_lower")):
+            return None
+        self._invalidate_caches()
+        x = self.__input_layer(x)
+        if not (torch.is_tensor(x) and x.is_complex()):
+            return None
+        if hasattr(core, "check_input_shape"):
+            core.check_input_shape(x)
+        prog = sweep.Program(self.nfft, _alias_of(core), x.dtype, x.device)
+        core._lower(prog, ext_param)
+        return prog.run_loss(x, target, kind)
+
     # -- accessors -------------------------------------------------------------------------------
     def get_inputLayer(self):
         return self.__input_layer

@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_ABS, EPI_NONE, F_GRAD, F_ISINT, OP_DELAY, OP_GAIN, OP_PDELAY, OP_PGAIN, OP_PSOS, OP_PTABLE,
+from ._lib import (CRIT_MSE, CRIT_MSE_CHSUM, EPI_ABS, EPI_NONE, F_GRAD, F_ISINT, OP_DELAY, OP_GAIN, OP_PDELAY, OP_PGAIN, OP_PSOS, OP_PTABLE,
                    OP_RECURSION, OP_SOS, OP_TABLE, Op, Plan)
 
 MAX_OPS_PER_LAUNCH = 24
@@ -72,6 +72,23 @@ class CudaBackend:
                              [g.data_ptr() if g is not None else None for g in grads],
                              gx.data_ptr() if gx is not None else None, gx.stride(0) if gx is not None else 0, B,
                              cols, bin_begin, nb, epilogue, ws.data_ptr(), ws_bytes, self._stream(x))
+
+
+    def loss(self, plan, ops, coefs, x, target, kind, scale, loss, grads, gx, bin_begin):
+        """Fused |.| + MSE criterion.  grads is None: loss only (one forward launch); else loss and its
+        gradients from ONE backward launch (+ the finalize kernel)."""
+        B, nb = x.shape[0], x.shape[1]
+        ws_bytes = plan.workspace_bytes(B, 1, nb)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        crit = _lib.Criterion(kind, 0, target.data_ptr(), target.stride(0), float(scale), loss.data_ptr())
+        cp = [c.data_ptr() for c in coefs]
+        if grads is None:
+            return plan.forward_loss(cp, x.data_ptr(), x.stride(0), crit, B, bin_begin, nb, ws.data_ptr(), ws_bytes,
+                                     self._stream(x))
+        return plan.backward_loss(cp, x.data_ptr(), x.stride(0), crit,
+                                  [g.data_ptr() if g is not None else None for g in grads],
+                                  gx.data_ptr() if gx is not None else None, gx.stride(0) if gx is not None else 0, B,
+                                  bin_begin, nb, ws.data_ptr(), ws_bytes, self._stream(x))
 
 
 _BACKEND = CudaBackend()  # tests/ may swap this for a CPU emulator to exercise the host logic without a GPU
@@ -138,6 +155,48 @@ class SweepFunction(torch.autograd.Function):
         else:
             grads = [None if g is None else torch.zeros_like(g) for g in grads]
         return (gx, None, None, None, None, None, *grads)
+
+
+class SweepLossFunction(torch.autograd.Function):
+    """loss = criterion(|program(x)|, target) with the output layer and the criterion evaluated inside the sweep
+    kernel (include/fsweep.h, fsweep_*_loss).  When a gradient will be needed, the forward call already runs the
+    backward kernel — it recomputes the forward states anyway — and keeps d loss / d coefficients; autograd's
+    backward only scales them by the upstream gradient.  No forward sweep, no |Y| / dL/d|Y| round trip."""
+
+    @staticmethod
+    def forward(ctx, x, target, plan, ops, kind, scale, bin_begin, *coefs):
+        global launch_count
+        x = _batch_view(x)
+        target = _batch_view(target)
+        real = torch.float32 if x.dtype == torch.complex64 else torch.float64
+        coefs = tuple(c.contiguous() for c in coefs)
+        loss = torch.empty((), dtype=real, device=x.device)
+        need = ctx.needs_input_grad
+        leaf_ops = [o for o in ops if o[0] != OP_RECURSION]
+        want = [need[7 + i] and bool(leaf_ops[i][4] & F_GRAD) for i in range(len(coefs))]
+        if not (any(want) or need[0]):
+            launch_count += _BACKEND.loss(plan, ops, coefs, x, target, kind, scale, loss, None, None, bin_begin) or 0
+            return loss
+        grads = [(torch.zeros_like(c) if leaf_ops[i][0] in _TABLE else torch.empty_like(c)) if want[i] else None
+                 for i, c in enumerate(coefs)]
+        gx = torch.empty_like(x, memory_format=torch.contiguous_format) if need[0] else None
+        launch_count += _BACKEND.loss(plan, ops, coefs, x, target, kind, scale, loss, grads, gx, bin_begin) or 0
+        ctx.grads, ctx.gx = grads, gx
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        live = [t for t in ctx.grads if t is not None] + ([ctx.gx] if ctx.gx is not None else [])
+        by_dtype = {}
+        for t in live:
+            by_dtype.setdefault(t.dtype, []).append(t)
+        scaled = {}
+        for dt, ts in by_dtype.items():
+            gs = g.to(dt) if not dt.is_complex else g.to(torch.float32 if dt == torch.complex64 else torch.float64)
+            for t, r in zip(ts, torch._foreach_mul(ts, gs)):
+                scaled[id(t)] = r
+        pick = lambda t: None if t is None else scaled[id(t)]
+        return (pick(ctx.gx), None, None, None, None, None, None, *[pick(t) for t in ctx.grads])
 
 
 # ---------------------------------------------------------------------------------------------
@@ -263,6 +322,46 @@ class Program:
         if epilogue == EPI_ABS and segs and segs[-1][0] == "eager":
             x4 = torch.abs(x4)
         return x4.reshape(x4.shape[:3] + trail)
+
+
+    def run_loss(self, x: torch.Tensor, target: torch.Tensor, kind: int) -> Optional[torch.Tensor]:
+        """criterion(|program(x)|, target) through the fused kernels, or None when this program / these shapes
+        cannot be fused (more than one launch, trailing columns, eager modules, a target that is not the plain
+        (B, M[, N_out]) magnitude tensor) — the caller then takes the unfused path."""
+        if not x.is_complex() or x.dim() != 3:
+            return None
+        if x.device.type != "cuda" and _BACKEND.name == "cuda":
+            return None
+        segs = list(self._segments())
+        if len(segs) != 1 or segs[0][0] != "sweep":
+            return None
+        ops, coefs, n_out = self.flatten_segment(segs[0][1])
+        B, M = x.shape[0], x.shape[1]
+        real = torch.float32 if x.dtype == torch.complex64 else torch.float64
+        if kind == CRIT_MSE_CHSUM:  # mse_loss: MSE(sum_r |Y_r|, target.squeeze(-1))
+            tgt = target.squeeze(-1) if target.dim() == 3 else target
+            if tuple(tgt.shape) != (B, M):
+                return None
+        else:
+            tgt = target
+            if tuple(tgt.shape) != (B, M, n_out):
+                return None
+        if tgt.dtype != real or tgt.device != x.device:
+            return None
+        scale = 1.0 / tgt.numel()
+        shard = current_shard()
+        x4 = x.unsqueeze(-1)
+        bin_begin = 0
+        if shard is not None:
+            if M != self.nfft // 2 + 1:
+                return None
+            bin_begin = shard[0]
+            x4, tgt = x4[:, shard[0]:shard[1]], tgt[:, shard[0]:shard[1]]
+            scale = 1.0 / tgt.numel()  # mean over the shard, as the unfused path computes it
+        if x4.shape[1] == 0:
+            return None
+        plan = _get_plan(ops, self.nfft, self.alias_decay_db, _lib.C64 if x.dtype == torch.complex64 else _lib.C128)
+        return SweepLossFunction.apply(x4, tgt, plan, ops, kind, scale, bin_begin, *coefs)
 
 
 class OrthogonalMap(torch.autograd.Function):

@@ -137,7 +137,7 @@ FSWEEP_API int fsweep_plan_num_coeffs(const fsweep_plan_t* plan);
  * given the total bin count M (only TABLE kinds depend on M). */
 FSWEEP_API int64_t fsweep_plan_coeff_numel(const fsweep_plan_t* plan, int slot, int64_t M);
 
-/* scratch the caller must provide to fsweep_backward (forward needs none) */
+/* scratch the caller must provide to fsweep_backward / fsweep_*_loss (fsweep_forward needs none) */
 FSWEEP_API size_t fsweep_workspace_bytes(const fsweep_plan_t* plan, int64_t batch, int64_t cols, int64_t n_bins);
 
 FSWEEP_API int fsweep_forward(const fsweep_plan_t* plan,
@@ -156,6 +156,37 @@ FSWEEP_API int fsweep_backward(const fsweep_plan_t* plan, const void* const* coe
                     void* grad_x, int64_t gx_batch_stride, /* device or NULL */
                     int64_t batch, int64_t cols, int64_t bin_begin, int64_t n_bins,
                     int epilogue, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- criteria fused into the sweep -----------------------------------------------------------------
+ * The |.| output layer (Transform(torch.abs), every BASELINE config) and an MSE criterion are evaluated
+ * inside the sweep kernel: neither |Y| nor dL/d|Y| touches HBM, and because the backward kernel
+ * recomputes the forward states anyway, ONE launch of fsweep_backward_loss yields the loss AND its
+ * gradients (upstream gradient 1; the caller scales them by dL/dloss).  Replaces, in one training step
+ * (optimize/trainer.py:177-190): the output layer, the criterion forward (optimize/loss.py:90-103 or
+ * torch.nn.MSELoss), its autograd backward and the forward sweep.  Only for programs with cols == 1. */
+#define FSWEEP_CRIT_MSE 1       /* nn.MSELoss()(|Y|, t): e = |Y[b,k,r]| - t[b,k,r]   (examples/e7_biquad.py:67) */
+#define FSWEEP_CRIT_MSE_CHSUM 2 /* mse_loss (optimize/loss.py:90-103): e = sum_r |Y[b,k,r]| - t[b,k]           */
+
+typedef struct fsweep_criterion {
+  int32_t kind;
+  int32_t reserved;
+  const void* target;          /* device real: (batch, n_bins, n_out) [MSE] or (batch, n_bins) [MSE_CHSUM];
+                                  addresses the FIRST PROCESSED bin like x */
+  int64_t target_batch_stride; /* in elements */
+  double scale;                /* loss = scale * sum e^2 over the processed range; for the reference's mean the
+                                  caller passes 1 / (number of elements of the FULL target) */
+  void* loss;                  /* device real[1], overwritten */
+} fsweep_criterion_t;
+
+/* loss only (validation) */
+FSWEEP_API int fsweep_forward_loss(const fsweep_plan_t* plan, const void* const* coeffs, const void* x,
+                        int64_t x_batch_stride, const fsweep_criterion_t* crit, int64_t batch,
+                        int64_t bin_begin, int64_t n_bins, void* workspace, size_t workspace_bytes, void* stream);
+/* loss and d loss / d coeffs (and d loss / d x when grad_x != NULL); buffers as in fsweep_backward */
+FSWEEP_API int fsweep_backward_loss(const fsweep_plan_t* plan, const void* const* coeffs, const void* x,
+                         int64_t x_batch_stride, const fsweep_criterion_t* crit, void* const* grad_coeffs,
+                         void* grad_x, int64_t gx_batch_stride, int64_t batch, int64_t bin_begin, int64_t n_bins,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* E = exp(S) for the orthogonal map of dsp.Matrix (reference dsp.py:649, functional.py:42-56):
  * skew != 0: S = triu(P,1) - triu(P,1)^T, else S = P.  P, E, G, gP: device double[n][n] row-major.

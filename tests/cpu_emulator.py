@@ -109,6 +109,7 @@ class EmulatedBackend:
     def forward(self, plan, ops, coefs, x, y, cols, bin_begin, epilogue):
         with torch.no_grad():
             y.copy_(_run(ops, coefs, x, bin_begin, plan.nfft, plan.alias, epilogue).to(y.dtype))
+        return 1
 
     def backward(self, plan, ops, coefs, x, gy, grads, gx, cols, bin_begin, epilogue):
         with torch.enable_grad():
@@ -124,6 +125,29 @@ class EmulatedBackend:
                 g.copy_(torch.zeros_like(g) if v is None else v.to(g.dtype))
         if gx is not None:
             gx.copy_(next(it).to(gx.dtype))
+        return 2  # the sweep kernel + the gradient finalize
+
+    def loss(self, plan, ops, coefs, x, target, kind, scale, loss, grads, gx, bin_begin):
+        want = grads is not None
+        with torch.enable_grad():
+            cs = [c.detach().clone().requires_grad_(want and grads[i] is not None) for i, c in enumerate(coefs)]
+            xs = x.detach().clone().requires_grad_(want and gx is not None)
+            mag = _run(ops, cs, xs, bin_begin, plan.nfft, plan.alias, EPI_ABS)[..., 0]
+            e = (mag.sum(-1) if kind == _lib.CRIT_MSE_CHSUM else mag) - target.double()
+            val = scale * (e * e).sum()
+            loss.copy_(val.detach().to(loss.dtype))
+            if not want:
+                return 1
+            wanted = [c for c, g in zip(cs, grads) if g is not None] + ([xs] if gx is not None else [])
+            got = torch.autograd.grad(val, wanted, allow_unused=True) if wanted else []
+        it = iter(got)
+        for c, g in zip(cs, grads):
+            if g is not None:
+                v = next(it)
+                g.copy_(torch.zeros_like(g) if v is None else v.to(g.dtype))
+        if gx is not None:
+            gx.copy_(next(it).to(gx.dtype))
+        return 2
 
 
 def install():

@@ -28,3 +28,43 @@ def test_case_matches_reference(name):
             if f"grad_{i}" in g.files:
                 assert p.grad is not None, (name, i)
                 assert grad_err(p.grad.numpy(), g[f"grad_{i}"]) <= max(1e-8, 20 * float(g["ref_fp32_noise"])), (name, i)
+
+
+@pytest.mark.parametrize("crit_kind", ["mse_loss", "MSELoss"])
+def test_trainer_fused_criterion_equals_unfused(crit_kind):
+    """Trainer.train_step with the criterion fused into the sweep (one backward_loss call) takes the same steps
+    as the unfused path (forward, criterion in PyTorch, backward) — host logic, through the ABI emulator."""
+    from flamo_b200 import sweep, workloads as W
+    from flamo_b200.optimize.loss import mse_loss, sparsity_loss
+    from flamo_b200.optimize.trainer import Trainer
+    from flamo_b200.processor import dsp, system
+
+    nfft, M = 512, 257
+
+    def run(fuse):
+        torch.manual_seed(5)
+        core = W.build(W.fdn(4, delays=[11, 17, 23, 31]), dsp, system, nfft, 30.0, dtype=torch.float64, device="cpu")
+        model = system.Shell(core, dsp.FFT(nfft, dtype=torch.float64),
+                             dsp.Transform(lambda x: torch.abs(x), dtype=torch.float64))
+        tr = Trainer(model, max_epochs=1, lr=1e-2, log=False, device="cpu", fuse_criterion=fuse)
+        if crit_kind == "mse_loss":
+            tr.register_criterion(mse_loss(nfft=nfft), 1)
+            tgt = torch.ones(2, M, 1, dtype=torch.float64)
+        else:
+            tr.register_criterion(torch.nn.MSELoss(), 0.7)
+            tgt = torch.full((2, M, 1), 0.8, dtype=torch.float64)
+        tr.register_criterion(sparsity_loss(), 0.2, requires_model=True)
+        x = torch.zeros(2, nfft, 1, dtype=torch.float64)
+        x[:, 0] = 1
+        x[1, 3] = 0.5
+        n0 = sweep.launch_count
+        losses = [tr.train_step((x, tgt)) for _ in range(3)]
+        return losses, [p.detach().clone() for p in model.parameters()], sweep.launch_count - n0, tr
+
+    lf, pf, nf, trf = run(True)
+    lu, pu, nu, tru = run(False)
+    assert np.allclose(lf, lu, rtol=1e-10)
+    for a, b in zip(pf, pu):
+        assert torch.allclose(a, b, rtol=1e-9, atol=1e-12)
+    assert nf < nu  # the fused step makes fewer sweep launches (no forward sweep)
+    assert np.allclose(list(trf.train_loss_log.values())[0], list(tru.train_loss_log.values())[0], rtol=1e-10)
