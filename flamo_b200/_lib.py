@@ -25,6 +25,7 @@ EXPORTS = [
     "fsweep_plan_num_coeffs", "fsweep_plan_coeff_numel", "fsweep_workspace_bytes",
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward",
+    "fsweep_sparsity_forward", "fsweep_sparsity_backward",
 ]
 
 
@@ -95,9 +96,13 @@ def lib():
                                        i64, i64, vp, C.c_size_t, vp]
     L.fsweep_expm_max_n.restype = i32
     L.fsweep_expm_forward.restype = i32
-    L.fsweep_expm_forward.argtypes = [vp, vp, i32, i32, vp]
+    L.fsweep_expm_forward.argtypes = [vp, vp, i32, i32, i32, vp]
     L.fsweep_expm_backward.restype = i32
-    L.fsweep_expm_backward.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.fsweep_expm_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.fsweep_sparsity_forward.restype = i32
+    L.fsweep_sparsity_forward.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.fsweep_sparsity_backward.restype = i32
+    L.fsweep_sparsity_backward.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     _lib = L
     return L
 

@@ -11,7 +11,7 @@
 #include <type_traits>
 #include <vector>
 
-#include "fsweep_tpb.cuh"
+#include "fsweep_tpc.cuh"
 
 using namespace fsweep;
 
@@ -69,6 +69,8 @@ struct fsweep_plan {
   LoopInfo loop;
   int tpb_np = 0;  // 4 / 8: additionally small enough for the thread-per-bin kernels of fsweep_tpb.cuh
   bool tpb_force = false;  // FSWEEP_FORCE_TPB=1 (tests): use them regardless of the bin count
+  int tpc_np = 0;  // 4 / 8: the flagship shape (N x 1 gain, loop width <= 8, 1 x N gain) -> compact kernels, fsweep_tpc.cuh
+  bool tpc_force = false;  // FSWEEP_FORCE_TPC=1 (tests)
   // lazily filled launch geometry: [cc index 0:1, 1:4, 2:loop kernels][fwd, bwd]
   std::mutex mu;
   int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -300,6 +302,16 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
       if (tpb) p->tpb_np = width <= 4 ? 4 : 8;
       const char* force = getenv("FSWEEP_FORCE_TPB");
       p->tpb_force = force && force[0] == '1';
+      // compact thread-per-bin variant: additionally one input and one output channel through N x 1 / 1 x N gains,
+      // and every accumulator must fit the register-resident set the kernel stages (NP*NP + 3*NP slots)
+      const char* no_tpc = getenv("FSWEEP_DISABLE_TPC");
+      const int np = width <= 4 ? 4 : 8;
+      if (tpb && !(no_tpc && no_tpc[0] == '1') && pre.size() == 1 && post.size() == 1 && ops[pre[0]].n_in == 1 &&
+          ops[post[0]].n_out == 1 && ops[pre[0]].n_out == rec_n && ops[post[0]].n_in == rec_n && rec_in == rec_n &&
+          acc_total <= np * np + 3 * np)
+        p->tpc_np = np;
+      const char* forcec = getenv("FSWEEP_FORCE_TPC");
+      p->tpc_force = forcec && forcec[0] == '1';
     }
   }
 
@@ -348,6 +360,14 @@ bool use_tpb(const fsweep_plan* p, int64_t n_bins, bool bwd) {
   if (!p->tpb_np) return false;
   return p->tpb_force || n_bins >= (bwd ? TPB_MIN_BINS_BWD : TPB_MIN_BINS_FWD);
 }
+
+// The compact kernels are the better choice as soon as there is about one bin per resident thread.
+constexpr int64_t TPC_MIN_BINS = 16384;
+bool use_tpc(const fsweep_plan* p, int64_t n_bins) {
+  if (!p->tpc_np || p->tpb_force) return false;
+  return p->tpc_force || n_bins >= TPC_MIN_BINS;
+}
+int tpc_grid(int64_t n_bins) { return (int)std::min<int64_t>((n_bins + TPC_BLOCK - 1) / TPC_BLOCK, MAX_GRID); }
 
 int cc_of(int64_t ncols) { return ncols == 1 ? 1 : 4; }
 
@@ -526,7 +546,10 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
   cfg.grid = pick_grid(plan, cc, false, cfg.smem, n_bins, &e, loop);
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
   const int dtype = plan->dtype;
-  if (use_tpb(plan, n_bins, false)) {
+  if (use_tpc(plan, n_bins)) {
+    cfg.grid = tpc_grid(n_bins);
+    e = launch_tpc(plan->tpc_np, false, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
+  } else if (use_tpb(plan, n_bins, false)) {
     const LoopInfo L = plan->loop;
     cfg.grid = (int)std::min<int64_t>((n_bins + TPB_BLOCK - 1) / TPB_BLOCK, grid_cap(n_bins, plan->G));
     e = launch_tpb_fwd(plan->tpb_np, cfg.grid, cfg.stream, P, L, A);
@@ -643,7 +666,10 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     ++launches;
   }
   const int dtype = plan->dtype;
-  if (use_tpb(plan, n_bins, true)) {
+  if (use_tpc(plan, n_bins)) {
+    cfg.grid = tpc_grid(n_bins);
+    e = launch_tpc(plan->tpc_np, true, cfg.grid, st, P, plan->loop, A, plan->G);
+  } else if (use_tpb(plan, n_bins, true)) {
     const LoopInfo L = plan->loop;
     cfg.grid = (int)std::min<int64_t>((n_bins + TPB_BLOCK - 1) / TPB_BLOCK, grid_cap(n_bins, plan->G));
     const size_t smem = (size_t)std::max(1, P.acc_total) * TPB_BLOCK * sizeof(float);

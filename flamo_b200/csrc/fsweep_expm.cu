@@ -102,24 +102,26 @@ __device__ double* expm_inplace(double* X, double* W, int n, double* red) {
   return cur;
 }
 
-__global__ void __launch_bounds__(EXPM_THREADS) expm_fwd_kernel(const double* __restrict__ Pin, double* __restrict__ E,
+// IO type T (float | double) is the caller's parameter dtype; the arithmetic is float64 throughout.
+template <typename T>
+__global__ void __launch_bounds__(EXPM_THREADS) expm_fwd_kernel(const T* __restrict__ Pin, T* __restrict__ E,
                                                                int n, int skew) {
   extern __shared__ double sm[];
   double *X = sm, *W = sm + n * n, *red = sm + 8 * n * n;
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     int r = e / n, c = e - r * n;
-    double v = Pin[e];
-    if (skew) v = (c > r) ? Pin[r * n + c] : ((c < r) ? -Pin[c * n + r] : 0.0);
+    double v = (double)Pin[e];
+    if (skew) v = (c > r) ? (double)Pin[r * n + c] : ((c < r) ? -(double)Pin[c * n + r] : 0.0);
     X[e] = v;
   }
   __syncthreads();
   double* R = expm_inplace(X, W, n, red);
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) E[e] = R[e];
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) E[e] = (T)R[e];
 }
 
-__global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const double* __restrict__ Pin,
-                                                               const double* __restrict__ G,
-                                                               double* __restrict__ gP, int n, int skew) {
+template <typename T>
+__global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const T* __restrict__ Pin, const T* __restrict__ G,
+                                                               T* __restrict__ gP, int n, int skew) {
   extern __shared__ double sm[];
   const int m = 2 * n;
   double *X = sm, *W = sm + m * m, *red = sm + 8 * m * m;
@@ -127,13 +129,13 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const double* __
     int r = e / m, c = e - r * m;
     double v = 0.0;
     if (r < n && c >= n) {
-      v = G[r * n + (c - n)];
+      v = (double)G[r * n + (c - n)];
     } else if ((r < n) == (c < n)) {
       int i = r % n, j = c % n;  // block (i, j) of S^T = S[j][i]
       if (skew)
-        v = (i > j) ? Pin[j * n + i] : ((i < j) ? -Pin[i * n + j] : 0.0);
+        v = (i > j) ? (double)Pin[j * n + i] : ((i < j) ? -(double)Pin[i * n + j] : 0.0);
       else
-        v = Pin[j * n + i];
+        v = (double)Pin[j * n + i];
     }
     X[e] = v;
   }
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const double* __
     int i = e / n, j = e - i * n;
     double d = R[i * m + n + j];
     if (skew) d = (i < j) ? d - R[j * m + n + i] : 0.0;
-    gP[e] = d;
+    gP[e] = (T)d;
   }
 }
 
@@ -152,26 +154,107 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const double* __
 
 extern "C" FSWEEP_API int fsweep_expm_max_n(void) { return 28; }  // 8 matrices of (2n)^2 doubles in shared memory
 
-extern "C" FSWEEP_API int fsweep_expm_forward(const double* P, double* E, int n, int skew, void* stream) {
-  if (!P || !E || n < 1 || n > 2 * fsweep_expm_max_n()) return FSWEEP_E_BADARG;
+template <typename T>
+static int expm_forward_t(const T* P, T* E, int n, int skew, cudaStream_t st) {
   size_t smem = (size_t)(8 * n * n + n + 8) * sizeof(double);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(expm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(expm_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return FSWEEP_E_CUDA;
   }
-  expm_fwd_kernel<<<1, EXPM_THREADS, smem, (cudaStream_t)stream>>>(P, E, n, skew);
+  expm_fwd_kernel<T><<<1, EXPM_THREADS, smem, st>>>(P, E, n, skew);
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
 
-extern "C" FSWEEP_API int fsweep_expm_backward(const double* P, const double* G, double* gP, int n, int skew,
-                                               void* stream) {
-  if (!P || !G || !gP || n < 1 || n > fsweep_expm_max_n()) return FSWEEP_E_BADARG;
+template <typename T>
+static int expm_backward_t(const T* P, const T* G, T* gP, int n, int skew, cudaStream_t st) {
   const int m = 2 * n;
   size_t smem = (size_t)(8 * m * m + m + 8) * sizeof(double);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(expm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(expm_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return FSWEEP_E_CUDA;
   }
-  expm_bwd_kernel<<<1, EXPM_THREADS, smem, (cudaStream_t)stream>>>(P, G, gP, n, skew);
+  expm_bwd_kernel<T><<<1, EXPM_THREADS, smem, st>>>(P, G, gP, n, skew);
+  return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}
+
+extern "C" FSWEEP_API int fsweep_expm_forward(const void* P, void* E, int n, int skew, int dtype, void* stream) {
+  if (!P || !E || n < 1 || n > 2 * fsweep_expm_max_n()) return FSWEEP_E_BADARG;
+  if (dtype == FSWEEP_C64) return expm_forward_t<float>((const float*)P, (float*)E, n, skew, (cudaStream_t)stream);
+  if (dtype == FSWEEP_C128) return expm_forward_t<double>((const double*)P, (double*)E, n, skew, (cudaStream_t)stream);
+  return FSWEEP_E_BADARG;
+}
+
+extern "C" FSWEEP_API int fsweep_expm_backward(const void* P, const void* G, void* gP, int n, int skew, int dtype,
+                                               void* stream) {
+  if (!P || !G || !gP || n < 1 || n > fsweep_expm_max_n()) return FSWEEP_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSWEEP_C64) return expm_backward_t<float>((const float*)P, (const float*)G, (float*)gP, n, skew, st);
+  if (dtype == FSWEEP_C128) return expm_backward_t<double>((const double*)P, (const double*)G, (double*)gP, n, skew, st);
+  return FSWEEP_E_BADARG;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sparsity_loss (reference flamo/optimize/loss.py:36-63) of the mapped feedback matrix A (n_mats x n x n):
+//   loss = mean_i ( (sum |A_i| - n sqrt n) / (n (1 - sqrt n)) ),   dloss/dA = sign(A) / (n (1 - sqrt n) n_mats)
+// One launch each way instead of ~6 elementwise / reduction launches of a few microseconds each — inside a
+// captured training step the launch count is what these parameter-sized ops cost.
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256) sparsity_fwd_kernel(const T* __restrict__ A, int n_mats, int n, T* loss) {
+  __shared__ double red[8];
+  const long long total = (long long)n_mats * n * n;
+  double s = 0.0;
+  for (long long e = threadIdx.x; e < total; e += blockDim.x) s += fabs((double)A[e]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const double rn = sqrt((double)n);
+    *loss = (T)((t / n_mats - n * rn) / (n * (1.0 - rn)));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sparsity_bwd_kernel(const T* __restrict__ A, const T* __restrict__ gloss,
+                                                           int n_mats, int n, T* __restrict__ gA) {
+  const long long total = (long long)n_mats * n * n;
+  const double rn = sqrt((double)n);
+  const double k = (double)*gloss / (n * (1.0 - rn) * n_mats);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const T a = A[e];
+    gA[e] = (T)(a > T(0) ? k : (a < T(0) ? -k : 0.0));
+  }
+}
+
+}  // namespace
+
+extern "C" FSWEEP_API int fsweep_sparsity_forward(const void* A, int n_mats, int n, int dtype, void* loss, void* stream) {
+  if (!A || !loss || n_mats < 1 || n < 2) return FSWEEP_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSWEEP_C64)
+    sparsity_fwd_kernel<float><<<1, 256, 0, st>>>((const float*)A, n_mats, n, (float*)loss);
+  else if (dtype == FSWEEP_C128)
+    sparsity_fwd_kernel<double><<<1, 256, 0, st>>>((const double*)A, n_mats, n, (double*)loss);
+  else
+    return FSWEEP_E_BADARG;
+  return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}
+
+extern "C" FSWEEP_API int fsweep_sparsity_backward(const void* A, const void* gloss, int n_mats, int n, int dtype,
+                                                   void* gA, void* stream) {
+  if (!A || !gloss || !gA || n_mats < 1 || n < 2) return FSWEEP_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n_mats * n * n;
+  const int grid = (int)((total + 255) / 256 > 1024 ? 1024 : (total + 255) / 256);
+  if (dtype == FSWEEP_C64)
+    sparsity_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)A, (const float*)gloss, n_mats, n, (float*)gA);
+  else if (dtype == FSWEEP_C128)
+    sparsity_bwd_kernel<double><<<grid, 256, 0, st>>>((const double*)A, (const double*)gloss, n_mats, n, (double*)gA);
+  else
+    return FSWEEP_E_BADARG;
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }

@@ -370,31 +370,70 @@ class OrthogonalMap(torch.autograd.Function):
 
     @staticmethod
     def supported(P: torch.Tensor) -> bool:
-        return (P.is_cuda and P.dim() == 2 and P.shape[0] == P.shape[1]
+        return (P.is_cuda and P.dim() == 2 and P.shape[0] == P.shape[1] and P.dtype in (torch.float32, torch.float64)
                 and P.shape[0] <= _lib.lib().fsweep_expm_max_n())
 
     @staticmethod
     def forward(ctx, P):
         global launch_count
-        P64 = P.detach().to(torch.float64).contiguous()
-        E = torch.empty_like(P64)
-        _lib.check(_lib.lib().fsweep_expm_forward(P64.data_ptr(), E.data_ptr(), P64.shape[0], 1,
+        Pc = P.detach().contiguous()
+        E = torch.empty_like(Pc)
+        _lib.check(_lib.lib().fsweep_expm_forward(Pc.data_ptr(), E.data_ptr(), Pc.shape[0], 1, _real_code(Pc.dtype),
                                                    torch.cuda.current_stream(P.device).cuda_stream))
         launch_count += 1
-        ctx.save_for_backward(P64)
-        ctx.in_dtype = P.dtype
-        return E.to(P.dtype)
+        ctx.save_for_backward(Pc)
+        return E
 
     @staticmethod
     def backward(ctx, G):
         global launch_count
-        (P64,) = ctx.saved_tensors
-        G64 = G.to(torch.float64).contiguous()
-        gP = torch.empty_like(P64)
-        _lib.check(_lib.lib().fsweep_expm_backward(P64.data_ptr(), G64.data_ptr(), gP.data_ptr(), P64.shape[0], 1,
+        (Pc,) = ctx.saved_tensors
+        Gc = G.to(Pc.dtype).contiguous()
+        gP = torch.empty_like(Pc)
+        _lib.check(_lib.lib().fsweep_expm_backward(Pc.data_ptr(), Gc.data_ptr(), gP.data_ptr(), Pc.shape[0], 1,
+                                                    _real_code(Pc.dtype),
                                                     torch.cuda.current_stream(G.device).cuda_stream))
         launch_count += 1
-        return gP.to(ctx.in_dtype)
+        return gP
+
+
+def _real_code(dtype: torch.dtype) -> int:
+    return _lib.C64 if dtype == torch.float32 else _lib.C128
+
+
+class SparsityFunction(torch.autograd.Function):
+    """sparsity_loss of a mapped (N, N) or (B, N, N) matrix (reference optimize/loss.py:36-63) as one launch each
+    way (libfsweep fsweep_sparsity_*) instead of half a dozen parameter-sized PyTorch kernels."""
+
+    @staticmethod
+    def supported(A: torch.Tensor) -> bool:
+        return (A.is_cuda and A.dim() in (2, 3) and A.shape[-1] == A.shape[-2] and A.shape[-1] >= 2
+                and A.dtype in (torch.float32, torch.float64) and _BACKEND.name == "cuda")
+
+    @staticmethod
+    def forward(ctx, A):
+        global launch_count
+        Ac = A.detach().contiguous()
+        loss = torch.empty((), dtype=Ac.dtype, device=Ac.device)
+        n_mats = Ac.shape[0] if Ac.dim() == 3 else 1
+        _lib.check(_lib.lib().fsweep_sparsity_forward(Ac.data_ptr(), n_mats, Ac.shape[-1], _real_code(Ac.dtype),
+                                                       loss.data_ptr(), torch.cuda.current_stream(A.device).cuda_stream))
+        launch_count += 1
+        ctx.save_for_backward(Ac)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        global launch_count
+        (Ac,) = ctx.saved_tensors
+        gc = g.to(Ac.dtype).contiguous()
+        gA = torch.empty_like(Ac)
+        n_mats = Ac.shape[0] if Ac.dim() == 3 else 1
+        _lib.check(_lib.lib().fsweep_sparsity_backward(Ac.data_ptr(), gc.data_ptr(), n_mats, Ac.shape[-1],
+                                                        _real_code(Ac.dtype), gA.data_ptr(),
+                                                        torch.cuda.current_stream(g.device).cuda_stream))
+        launch_count += 1
+        return gA
 
 
 def pack_sections(b: torch.Tensor, a: torch.Tensor, parallel: bool, real: torch.dtype) -> torch.Tensor:

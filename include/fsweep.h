@@ -47,7 +47,7 @@ extern "C" {
 #define FSWEEP_API
 #endif
 
-#define FSWEEP_VERSION 1
+#define FSWEEP_VERSION 2
 
 /* return codes */
 #define FSWEEP_OK 0
@@ -189,13 +189,22 @@ FSWEEP_API int fsweep_backward_loss(const fsweep_plan_t* plan, const void* const
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* E = exp(S) for the orthogonal map of dsp.Matrix (reference dsp.py:649, functional.py:42-56):
- * skew != 0: S = triu(P,1) - triu(P,1)^T, else S = P.  P, E, G, gP: device double[n][n] row-major.
- * backward: gP = dL/dP given G = dL/dE.  One CTA, float64, entirely on the device (torch.matrix_exp
- * reads the norm back to the host, which cannot be captured in a CUDA graph).
+ * skew != 0: S = triu(P,1) - triu(P,1)^T, else S = P.  P, E, G, gP: device real[n][n] row-major, real = float
+ * for dtype FSWEEP_C64 and double for FSWEEP_C128 (the parameter's own dtype: no cast kernels around the call);
+ * the arithmetic is float64 either way.
+ * backward: gP = dL/dP given G = dL/dE.  One CTA, entirely on the device (torch.matrix_exp reads its norm
+ * back to the host, which cannot be captured in a CUDA graph).
  * n <= 2*fsweep_expm_max_n() for forward, n <= fsweep_expm_max_n() for backward. */
 FSWEEP_API int fsweep_expm_max_n(void);
-FSWEEP_API int fsweep_expm_forward(const double* P, double* E, int n, int skew, void* stream);
-FSWEEP_API int fsweep_expm_backward(const double* P, const double* G, double* gP, int n, int skew, void* stream);
+FSWEEP_API int fsweep_expm_forward(const void* P, void* E, int n, int skew, int dtype, void* stream);
+FSWEEP_API int fsweep_expm_backward(const void* P, const void* G, void* gP, int n, int skew, int dtype, void* stream);
+
+/* sparsity_loss of the mapped feedback matrix (reference optimize/loss.py:36-63), A: device real[n_mats][n][n]:
+ *   loss = mean_i ((sum |A_i| - n sqrt n) / (n (1 - sqrt n)));  backward: gA = gloss * dloss/dA (gloss: device real[1]).
+ * One launch each way, capture safe. */
+FSWEEP_API int fsweep_sparsity_forward(const void* A, int n_mats, int n, int dtype, void* loss, void* stream);
+FSWEEP_API int fsweep_sparsity_backward(const void* A, const void* gloss, int n_mats, int n, int dtype, void* gA,
+                                        void* stream);
 
 /* number of kernels the last forward / backward call of this thread enqueued (bench bookkeeping) */
 FSWEEP_API int fsweep_last_launch_count(void);

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().fsweep_version() == 1
+    assert _lib.lib().fsweep_version() == 2
 
 
 def _op(kind, n_out, n_in, K=0, flags=0, n_ff=0, n_fb=0):

@@ -1,4 +1,5 @@
 """GPU: the capture-safe expm(skew(P)) kernel against torch.matrix_exp and its autograd."""
+import numpy as np
 import pytest
 import torch
 
@@ -48,3 +49,25 @@ def test_expm_float32_parameter_and_capture():
     torch.cuda.synchronize()
     assert torch.allclose(out, torch.matrix_exp(skew_matrix(P.detach().double())).float(), atol=1e-6)
     assert P.grad is not None and torch.isfinite(P.grad).all()
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (3, 6, 6), (64, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_sparsity_kernels_match_reference_formula(shape, dtype):
+    """fsweep_sparsity_* against the reference's expression (optimize/loss.py:36-63) and its autograd."""
+    from flamo_b200 import sweep
+
+    torch.manual_seed(1)
+    A = torch.randn(*shape, device="cuda", dtype=dtype, requires_grad=True)
+    N = shape[-1]
+    if A.dim() == 3:
+        ref = torch.mean((torch.sum(torch.abs(A), dim=(-2, -1)) - N * np.sqrt(N)) / (N * (1 - np.sqrt(N))))
+    else:
+        ref = -(torch.sum(torch.abs(A)) - N * np.sqrt(N)) / (N * (np.sqrt(N) - 1))
+    (gr,) = torch.autograd.grad(1.7 * ref, A)
+    assert sweep.SparsityFunction.supported(A)
+    out = sweep.SparsityFunction.apply(A)
+    (go,) = torch.autograd.grad(1.7 * out, A)
+    tol = 1e-6 if dtype == torch.float32 else 1e-13
+    assert abs(float(out.detach()) - float(ref.detach())) <= tol * max(1.0, abs(float(ref.detach())))
+    assert torch.allclose(go, gr, rtol=tol * 10, atol=tol)

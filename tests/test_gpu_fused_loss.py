@@ -71,12 +71,12 @@ def test_fused_equals_unfused_c128(name, kind):
             assert grad_err(b.cpu().numpy() / 2.5, a.cpu().numpy()) <= gtol
 
 
-@pytest.mark.parametrize("path", ["generic", "loop", "tpb"])
+@pytest.mark.parametrize("path", ["generic", "loop", "tpb", "tpc"])
 @pytest.mark.parametrize("kind", [_lib.CRIT_MSE, _lib.CRIT_MSE_CHSUM])
 @pytest.mark.parametrize("B", [1, 5])
 def test_fused_on_every_kernel_family(path, kind, B, monkeypatch):
-    if path == "tpb":
-        monkeypatch.setenv("FSWEEP_FORCE_TPB", "1")
+    if path in ("tpb", "tpc"):
+        monkeypatch.setenv("FSWEEP_FORCE_TPB" if path == "tpb" else "FSWEEP_FORCE_TPC", "1")
     else:
         monkeypatch.setenv("FSWEEP_DISABLE_TPB", "1")
     if path == "generic":

@@ -103,16 +103,18 @@ FDN_CASES = ["cfg2_fdn8_full", "fdn6_example", "fdn8_batch3", "fdn16", "fdn32", 
 
 @pytest.mark.parametrize("name", FDN_CASES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("path", ["generic", "loop", "tpb"])
+@pytest.mark.parametrize("path", ["generic", "loop", "tpb", "tpc"])
 def test_alternative_kernel_paths_on_fdn_cases(name, dtype, path, monkeypatch):
-    """FDN-shaped programs can run on three kernel families: the generic step-table interpreter
+    """FDN-shaped programs can run on four kernel families: the generic step-table interpreter
     (fsweep_kernels.cuh), the row-distributed loop kernels (fsweep_loop.cuh) and, for widths <= 8 in float32 and
-    enough bins, the thread-per-bin kernels (fsweep_tpb.cuh).  Each family is forced here in turn; all must agree
-    with the oracle."""
-    if path == "tpb":
+    enough bins, the unrolled (fsweep_tpb.cuh) and the compact (fsweep_tpc.cuh) thread-per-bin kernels.  Each
+    family is forced here in turn; all must agree with the oracle."""
+    if path in ("tpb", "tpc"):
         if dtype != torch.float32 or name in ("fdn16", "fdn32"):
             pytest.skip("thread-per-bin kernels: float32, width <= 8")
-        monkeypatch.setenv("FSWEEP_FORCE_TPB", "1")
+        if path == "tpc" and name == "recursion_filters":
+            pytest.skip("compact thread-per-bin kernels: N x 1 and 1 x N gains around the loop only")
+        monkeypatch.setenv("FSWEEP_FORCE_TPB" if path == "tpb" else "FSWEEP_FORCE_TPC", "1")
     else:
         monkeypatch.setenv("FSWEEP_DISABLE_TPB", "1")
     if path == "generic":
