@@ -374,12 +374,12 @@ def kernel_roofline(model, x_dev, flush, reps=30):
 
     t_bwd = timed(bwd)
     ach = bytes_per_launch / t_bwd / 1e9
-    return {"bound": "hbm", "kernel": "fsweep_loop_bwd_kernel<float,8> (fused |.|+MSE criterion)", "achieved": ach,
+    return {"bound": "hbm", "kernel": plan.kernel_family(M, True) + " (fused |.|+MSE criterion)", "achieved": ach,
             "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else which,
             "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
             "us_per_launch": t_bwd * 1e6, "algorithmic_bytes_per_launch": bytes_per_launch,
-            "forward_kernel": {"kernel": "fsweep_tpb_fwd_kernel<8> (validation / inference only; not in the training step)",
+            "forward_kernel": {"kernel": plan.kernel_family(M, False) + " (validation / inference only; not in the training step)",
                                "us_per_launch": t_fwd * 1e6,
                                "achieved": bytes_per_launch / t_fwd / 1e9, "frac": bytes_per_launch / t_fwd / 1e9 / peak},
             "note": "config 2 moves 0.58 MB per launch and does ~2-4 kflop per bin: it is instruction-issue / latency "

@@ -22,10 +22,10 @@ F_ISINT, F_GRAD = 1, 2
 
 EXPORTS = [
     "fsweep_version", "fsweep_last_error", "fsweep_plan_create", "fsweep_plan_destroy",
-    "fsweep_plan_num_coeffs", "fsweep_plan_coeff_numel", "fsweep_workspace_bytes",
+    "fsweep_plan_num_coeffs", "fsweep_plan_coeff_numel", "fsweep_plan_kernel_family", "fsweep_workspace_bytes",
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward",
-    "fsweep_sparsity_forward", "fsweep_sparsity_backward",
+    "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total",
 ]
 
 
@@ -82,6 +82,8 @@ def lib():
     L.fsweep_plan_num_coeffs.argtypes = [vp]
     L.fsweep_plan_coeff_numel.restype = i64
     L.fsweep_plan_coeff_numel.argtypes = [vp, i32, i64]
+    L.fsweep_plan_kernel_family.restype = C.c_char_p
+    L.fsweep_plan_kernel_family.argtypes = [vp, i64, i32]
     L.fsweep_workspace_bytes.restype = C.c_size_t
     L.fsweep_workspace_bytes.argtypes = [vp, i64, i64, i64]
     L.fsweep_forward.restype = i32
@@ -103,6 +105,8 @@ def lib():
     L.fsweep_sparsity_forward.argtypes = [vp, i32, i32, i32, vp, vp]
     L.fsweep_sparsity_backward.restype = i32
     L.fsweep_sparsity_backward.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.fsweep_weighted_total.restype = i32
+    L.fsweep_weighted_total.argtypes = [C.POINTER(vp), C.POINTER(C.c_double), C.POINTER(C.c_double), i32, i32, vp, vp]
     _lib = L
     return L
 
@@ -129,6 +133,9 @@ class Plan:
 
     def coeff_numel(self, slot, M):
         return lib().fsweep_plan_coeff_numel(self.handle, slot, M)
+
+    def kernel_family(self, n_bins, backward):
+        return lib().fsweep_plan_kernel_family(self.handle, int(n_bins), int(bool(backward))).decode()
 
     def workspace_bytes(self, batch, cols, n_bins):
         return lib().fsweep_workspace_bytes(self.handle, batch, cols, n_bins)

@@ -443,6 +443,14 @@ int check_common(const fsweep_plan* plan, const void* const* coeffs, const void*
 
 }  // namespace
 
+extern "C" const char* fsweep_plan_kernel_family(const fsweep_plan_t* plan, int64_t n_bins, int backward) {
+  if (!plan) return "";
+  if (use_tpc(plan, n_bins)) return backward ? "fsweep_tpc_kernel<NP,bwd>" : "fsweep_tpc_kernel<NP,fwd>";
+  if (use_tpb(plan, n_bins, backward != 0)) return backward ? "fsweep_tpb_bwd_kernel" : "fsweep_tpb_fwd_kernel";
+  if (plan->loop_fast) return backward ? "fsweep_loop_bwd_kernel" : "fsweep_loop_fwd_kernel";
+  return backward ? "fsweep_bwd_kernel" : "fsweep_fwd_kernel";
+}
+
 extern "C" size_t fsweep_workspace_bytes(const fsweep_plan_t* plan, int64_t batch, int64_t cols, int64_t n_bins) {
   (void)batch;
   (void)cols;

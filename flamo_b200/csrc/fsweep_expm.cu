@@ -258,3 +258,50 @@ extern "C" FSWEEP_API int fsweep_sparsity_backward(const void* A, const void* gl
     return FSWEEP_E_BADARG;
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Weighted total of the step's criteria (reference optimize/trainer.py:184-188: loss += alpha * criterion):
+//   vals[i] = scale_i * part_i  (i < n),   vals[n] = sum_i alpha_i * vals[i]
+// (scale_i: the multi-GPU trainer's shard weights; 1 otherwise)
+// in ONE launch instead of a mul + add per criterion and a stack; the values land in the buffer the Trainer reads
+// back once per step.
+namespace {
+struct TotalArgs {
+  const void* part[FSWEEP_MAX_CRITERIA];
+  double alpha[FSWEEP_MAX_CRITERIA];
+  double scale[FSWEEP_MAX_CRITERIA];
+  int n;
+};
+template <typename T>
+__global__ void weighted_total_kernel(const __grid_constant__ TotalArgs a, T* vals) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  T tot = T(0);
+  for (int i = 0; i < a.n; ++i) {
+    const T v = (T)a.scale[i] * *reinterpret_cast<const T*>(a.part[i]);
+    vals[i] = v;
+    tot += (T)a.alpha[i] * v;
+  }
+  vals[a.n] = tot;
+}
+}  // namespace
+
+extern "C" FSWEEP_API int fsweep_weighted_total(const void* const* parts, const double* alphas, const double* scales,
+                                                int n, int dtype, void* vals, void* stream) {
+  if (!parts || !alphas || !scales || !vals || n < 1 || n > FSWEEP_MAX_CRITERIA) return FSWEEP_E_BADARG;
+  TotalArgs a;
+  a.n = n;
+  for (int i = 0; i < n; ++i) {
+    if (!parts[i]) return FSWEEP_E_BADARG;
+    a.part[i] = parts[i];
+    a.alpha[i] = alphas[i];
+    a.scale[i] = scales[i];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSWEEP_C64)
+    weighted_total_kernel<float><<<1, 32, 0, st>>>(a, (float*)vals);
+  else if (dtype == FSWEEP_C128)
+    weighted_total_kernel<double><<<1, 32, 0, st>>>(a, (double*)vals);
+  else
+    return FSWEEP_E_BADARG;
+  return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}

@@ -7,17 +7,18 @@
 // of the kernel is executed once per warp, cold, and the kernel runs at the speed of INSTRUCTION FETCH
 // (131 - 217 KB of unrolled SASS, `stalled_no_instruction` = 70 % of the time).  Here
 //   * the per-bin matrix A = I - D(w) W lives in thread-private SHARED-MEMORY columns (A[i][j] of thread t at
-//     float2 index (i*NP + j)*BLOCK + t: conflict-free), so that the LU factorisation and the four triangular
-//     solves are RUNTIME loops — a few hundred SASS instructions that stay in the instruction cache;
+//     float2 index (i*NP + j)*BLOCK + t: conflict-free), so that the LU factorisation is a RUNTIME loop over the
+//     elimination steps and no row ever has to be addressed through a select chain;
 //   * 576 B of shared memory per thread and <= 168 registers let 6 blocks of 64 threads live on an SM:
 //     56 832 resident threads cover the 48 001 bins of the headline config in ONE wave (the unrolled backward
 //     kernel needed 255 registers -> 4 blocks -> a two-wave tail);
 //   * gradient accumulators (W_fb: N x N, the two gain vectors, the diagonal op) stay in registers across bins and
 //     are reduced once per block through the then-idle matrix storage into the `partial` layout shared with the
 //     other kernel families (fsweep_finalize_kernel).
-// LU convention (LINPACK, as fsweep_tpb.cuh): at step k rows k and p_k are swapped in columns >= k only, the
-// multipliers stay where they were produced, 1/U_kk is stored on the diagonal, and the solves replay the
-// interchanges progressively.
+// LU convention: P A = L U with full row interchanges, 1/U_kk stored on the diagonal; the row map is one packed
+// word, applied by the solves as a gather / scatter through the shared-memory vector slot.  The k loop of the
+// factorisation is a runtime loop, the triangular solves are fully static (vector in registers, every matrix
+// element one LDS at a constant offset: independent loads that issue back to back).
 #pragma once
 #include "fsweep_tpb.cuh"
 
@@ -51,91 +52,95 @@ struct TpcMat {
   __device__ __forceinline__ float2& at(int i, int j) const { return a[(i * NP + j) * TPC_BLOCK]; }
   __device__ __forceinline__ float2& vec(int i) const { return v[i * TPC_BLOCK]; }
 
-  // in-place LU with partial pivoting; returns the packed interchange word (3 bits per step)
+  // In-place P A = L U with partial pivoting and FULL row interchanges (multipliers move with their rows), unit-lower
+  // L below the diagonal, U above, 1/U_kk on the diagonal.  Returns the row map packed 3 bits per row:
+  // row i of P A is row ((pvec >> 3i) & 7) of A.  The k loop stays a runtime loop (compact code); the work inside is
+  // written with static inner loops so that the loads of one step are independent and issue back to back.
   __device__ __forceinline__ unsigned factor() const {
-    unsigned perm = 0u;
+    unsigned pvec = 0u;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) pvec |= (unsigned)i << (3 * i);
 #pragma unroll 1
     for (int k = 0; k < NP; ++k) {
-      float2 d = at(k, k);
-      float best = d.x * d.x + d.y * d.y;
+      float2* colk = a + k * TPC_BLOCK;  // (r, k) at colk[r*NP*TPC_BLOCK]
+      float best = -1.f;
       int pr = k;
-#pragma unroll 1
-      for (int r = k + 1; r < NP; ++r) {
-        const float2 c = at(r, k);
-        const float m = c.x * c.x + c.y * c.y;
-        if (m > best) {
-          best = m;
-          pr = r;
-        }
-      }
-      perm |= (unsigned)pr << (3 * k);
-      if (pr != k) {
-#pragma unroll 1
-        for (int j = k; j < NP; ++j) {
-          const float2 t = at(k, j);
-          at(k, j) = at(pr, j);
-          at(pr, j) = t;
-        }
-      }
-      float2 prow[NP];  // pivot row in registers (entries j <= k are loaded but unused)
 #pragma unroll
-      for (int j = 0; j < NP; ++j) prow[j] = at(k, j);
-      d = at(k, k);
+      for (int r = 0; r < NP; ++r) {
+        if (r >= k) {
+          const float2 c = colk[r * NP * TPC_BLOCK];
+          const float m = c.x * c.x + c.y * c.y;
+          if (m > best) {
+            best = m;
+            pr = r;
+          }
+        }
+      }
+      float2* rowk = a + k * NP * TPC_BLOCK;
+      if (pr != k) {
+        float2* rowp = a + pr * NP * TPC_BLOCK;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const float2 t = rowk[j * TPC_BLOCK];
+          rowk[j * TPC_BLOCK] = rowp[j * TPC_BLOCK];
+          rowp[j * TPC_BLOCK] = t;
+        }
+        const unsigned fx = ((pvec >> (3 * k)) ^ (pvec >> (3 * pr))) & 7u;
+        pvec ^= (fx << (3 * k)) | (fx << (3 * pr));
+      }
+      float2 prow[NP];  // pivot row in registers (entries j < k are loaded but unused)
+#pragma unroll
+      for (int j = 0; j < NP; ++j) prow[j] = rowk[j * TPC_BLOCK];
+      const float2 d = colk[k * NP * TPC_BLOCK];
       const float id = rcp_t(d.x * d.x + d.y * d.y);
       const float2 inv = f2(d.x * id, -d.y * id);
-      at(k, k) = inv;
+      colk[k * NP * TPC_BLOCK] = inv;
 #pragma unroll 1
       for (int r = k + 1; r < NP; ++r) {
-        const float2 l = cmul2(at(r, k), inv);
-        at(r, k) = l;
+        float2* rowr = a + r * NP * TPC_BLOCK;
+        const float2 l = cmul2(rowr[k * TPC_BLOCK], inv);
+        rowr[k * TPC_BLOCK] = l;
 #pragma unroll
         for (int j = 1; j < NP; ++j)
-          if (j > k) at(r, j) = cnma2(at(r, j), l, prow[j]);
+          if (j > k) rowr[j * TPC_BLOCK] = cnma2(rowr[j * TPC_BLOCK], l, prow[j]);
       }
     }
-    return perm;
+    return pvec;
   }
 
-  // A x = b, b and x in the vector slot
-  __device__ __forceinline__ void solve(unsigned perm) const {
-#pragma unroll 1
-    for (int k = 0; k < NP; ++k) {
-      const int pr = (int)((perm >> (3 * k)) & 7u);
-      const float2 vk = vec(pr);
-      vec(pr) = vec(k);
-      vec(k) = vk;
-#pragma unroll 1
-      for (int r = k + 1; r < NP; ++r) vec(r) = cnma2(vec(r), at(r, k), vk);
-    }
-#pragma unroll 1
-    for (int k = NP - 1; k >= 0; --k) {
-      float2 acc = vec(k);
-#pragma unroll 1
-      for (int j = k + 1; j < NP; ++j) acc = cnma2(acc, at(k, j), vec(j));
-      vec(k) = cmul2(acc, at(k, k));
+  // A x = b.  b is in the vector slot on entry; x is returned in registers.  Fully static: every matrix element is
+  // one LDS at a constant offset, the row permutation is a gather through the vector slot.
+  __device__ __forceinline__ void solve(unsigned pvec, float2 (&x)[NP]) const {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) x[i] = vec((int)((pvec >> (3 * i)) & 7u));
+#pragma unroll
+    for (int i = 1; i < NP; ++i)
+#pragma unroll
+      for (int j = 0; j < i; ++j) x[i] = cnma2(x[i], at(i, j), x[j]);
+#pragma unroll
+    for (int i = NP - 1; i >= 0; --i) {
+#pragma unroll
+      for (int j = i + 1; j < NP; ++j) x[i] = cnma2(x[i], at(i, j), x[j]);
+      x[i] = cmul2(x[i], at(i, i));
     }
   }
 
-  // A^H x = g:  w = U^-H g, then for k = n-1 .. 0:  w <- P_k (M_k^H w)
-  __device__ __forceinline__ void solve_adj(unsigned perm) const {
-#pragma unroll 1
+  // A^H lam = g with A = P^T L U:  U^H w = g,  L^H v = w,  lam[pvec_i] = v_i.  g in registers (destroyed); lam is
+  // left in the vector slot.
+  __device__ __forceinline__ void solve_adj(unsigned pvec, float2 (&g)[NP]) const {
+#pragma unroll
     for (int i = 0; i < NP; ++i) {
-      float2 acc = vec(i);
-#pragma unroll 1
-      for (int j = 0; j < i; ++j) acc = cnmaj2(acc, at(j, i), vec(j));
+#pragma unroll
+      for (int j = 0; j < i; ++j) g[i] = cnmaj2(g[i], at(j, i), g[j]);
       const float2 di = at(i, i);
-      vec(i) = cmul2(acc, f2(di.x, -di.y));
+      g[i] = cmul2(g[i], f2(di.x, -di.y));
     }
-#pragma unroll 1
-    for (int k = NP - 1; k >= 0; --k) {
-      float2 acc = vec(k);
-#pragma unroll 1
-      for (int r = k + 1; r < NP; ++r) acc = cnmaj2(acc, at(r, k), vec(r));
-      const int pr = (int)((perm >> (3 * k)) & 7u);
-      const float2 t = vec(pr);  // pr >= k; for pr == k this is the stale value and is overwritten below
-      vec(pr) = acc;
-      if (pr != k) vec(k) = t;
-    }
+#pragma unroll
+    for (int i = NP - 2; i >= 0; --i)
+#pragma unroll
+      for (int j = i + 1; j < NP; ++j) g[i] = cnmaj2(g[i], at(j, i), g[j]);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) vec((int)((pvec >> (3 * i)) & 7u)) = g[i];
   }
 };
 
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(TPC_BLOCK, 6) fsweep_tpc_kernel(const __grid_c
         mat.at(m, j) = f2((m == j ? 1.f : 0.f) - d.x * w, -d.y * w);
       }
     }
-    const unsigned perm = mat.factor();
+    const unsigned pvec = mat.factor();
 
     for (int q = 0; q < ncols_total; ++q) {
       const int b = (A.cols == 1) ? q : q / A.cols, cc = q - b * A.cols;
@@ -216,12 +221,11 @@ __global__ void __launch_bounds__(TPC_BLOCK, 6) fsweep_tpc_kernel(const __grid_c
       const cx<float> xv = ld_cx(x + (size_t)b * A.xbs + (size_t)bl * A.cols + cc);
 #pragma unroll
       for (int m = 0; m < NP; ++m) mat.vec(m) = cmul2(D[m], f2(wpre[m] * xv.x, wpre[m] * xv.y));
-      mat.solve(perm);
       float2 y[NP];
+      mat.solve(pvec, y);
       float ox = 0.f, oy = 0.f;
 #pragma unroll
       for (int m = 0; m < NP; ++m) {
-        y[m] = mat.vec(m);
         ox = fmaf(wpost[m], y[m].x, ox);
         oy = fmaf(wpost[m], y[m].y, oy);
       }
@@ -259,12 +263,13 @@ __global__ void __launch_bounds__(TPC_BLOCK, 6) fsweep_tpc_kernel(const __grid_c
           }
         }
         // ---- through the output gain: lam0 = w_post go, dw_post = Re(go conj(y))
+        float2 g0[NP];
 #pragma unroll
         for (int m = 0; m < NP; ++m) {
-          mat.vec(m) = f2(wpost[m] * gox, wpost[m] * goy);
+          g0[m] = f2(wpost[m] * gox, wpost[m] * goy);
           gpost[m] = fmaf(gox, y[m].x, fmaf(goy, y[m].y, gpost[m]));
         }
-        mat.solve_adj(perm);
+        mat.solve_adj(pvec, g0);
         // ---- lam, g_u = conj(D) lam, u = s + W y; dW_fb = Re(g_u y^H); diagonal op; input gain
         float gxr = 0.f, gxi = 0.f;
 #pragma unroll
@@ -301,43 +306,52 @@ __global__ void __launch_bounds__(TPC_BLOCK, 6) fsweep_tpc_kernel(const __grid_c
   }
 
   if constexpr (BWD) {
-    // ---- block reduction of the register accumulators through the (now idle) matrix storage:
-    //      stage[slot * TPC_BLOCK + tid], slot = flat accumulator index op.acc_off + row*row_len + e
+    // ---- block reduction of the register accumulators through the (now idle) matrix storage.  Staging layout is
+    //      static (slot s at stage[s * TPC_BLOCK + tid]): s = m*NP + j for dW_fb[m][j], then NP slots each for
+    //      dw_pre, dw_post and the diagonal op — every store has a constant offset.
+    constexpr int S_PRE = NP * NP, S_POST = NP * NP + NP, S_DIAG = NP * NP + 2 * NP, S_TOTAL = NP * NP + 3 * NP;
+    static_assert(S_TOTAL <= 2 * (NP * NP + NP), "staging does not fit the matrix storage");
     __syncthreads();
-    float* stage = reinterpret_cast<float*>(tsm);  // 2 * (NP*NP + NP) floats per thread >= NP*NP + 3*NP slots
+    float* stage = reinterpret_cast<float*>(tsm) + tid;
+#pragma unroll
+    for (int m = 0; m < NP; ++m) {
+#pragma unroll
+      for (int j = 0; j < NP; ++j) stage[(m * NP + j) * TPC_BLOCK] = gwfb[m][j];
+      stage[(S_PRE + m) * TPC_BLOCK] = gpre[m];
+      stage[(S_POST + m) * TPC_BLOCK] = gpost[m];
+      stage[(S_DIAG + m) * TPC_BLOCK] = gdiag[m];
+    }
+    __syncthreads();
     const OpK& fbop = P.ops[L.fb];
     const OpK& preop = P.ops[L.pre];
     const OpK& postop = P.ops[L.post];
-    if (fbop.acc_mode == ACC_SMEM) {
-#pragma unroll
-      for (int m = 0; m < NP; ++m)
-#pragma unroll
-        for (int j = 0; j < NP; ++j)
-          if (m < fbop.n_out && j < fbop.n_in) stage[(fbop.acc_off + m * fbop.row_len + j) * TPC_BLOCK + tid] = gwfb[m][j];
-    }
-#pragma unroll
-    for (int m = 0; m < NP; ++m) {
-      if (m < N) {
-        if (preop.acc_mode == ACC_SMEM) stage[(preop.acc_off + m) * TPC_BLOCK + tid] = gpre[m];     // N x 1: row m
-        if (postop.acc_mode == ACC_SMEM) stage[(postop.acc_off + m) * TPC_BLOCK + tid] = gpost[m];  // 1 x N: entry m
-        if (want_ff) stage[(ffop.acc_off + m) * TPC_BLOCK + tid] = gdiag[m];
-      }
-    }
-    __syncthreads();
     float* partial = reinterpret_cast<float*>(A.partial) + (size_t)blockIdx.x * P.acc_per_lane * G;
-    for (int e = tid; e < P.acc_per_lane * G; e += TPC_BLOCK) partial[e] = 0.f;
-    __syncthreads();
-    for (int opi = 0; opi < P.n_ops; ++opi) {
-      const OpK& op = P.ops[opi];
-      if (op.acc_mode != ACC_SMEM) continue;
-      const int total = op.n_out * op.row_len;
-      for (int e = tid; e < total; e += TPC_BLOCK) {
-        const int row = e / op.row_len, i = e - row * op.row_len;
-        const float* col = stage + (size_t)(op.acc_off + e) * TPC_BLOCK;
-        float sum = 0.f;
-        for (int j = 0; j < TPC_BLOCK; ++j) sum += col[(j + tid) & (TPC_BLOCK - 1)];  // rotated: conflict-free
-        partial[(op.row_off + i) * G + row] = sum;
+    // partial[(op.row_off + i) * G + row] for entry i of row `row` (the layout fsweep_finalize_kernel reads; entries
+    // outside the live shapes are never read, so they are not written either)
+    for (int sidx = tid; sidx < S_TOTAL; sidx += TPC_BLOCK) {
+      int dst = -1;
+      if (sidx < S_PRE) {
+        const int m = sidx / NP, j = sidx - m * NP;
+        if (fbop.acc_mode == ACC_SMEM && m < N && j < N) dst = (fbop.row_off + j) * G + m;
+      } else if (sidx < S_POST) {
+        const int m = sidx - S_PRE;  // N x 1: row m, entry 0
+        if (preop.acc_mode == ACC_SMEM && m < N) dst = preop.row_off * G + m;
+      } else if (sidx < S_DIAG) {
+        const int m = sidx - S_POST;  // 1 x N: row 0, entry m
+        if (postop.acc_mode == ACC_SMEM && m < N) dst = (postop.row_off + m) * G;
+      } else {
+        const int m = sidx - S_DIAG;  // diagonal op: row m, entry 0
+        if (want_ff && m < N) dst = ffop.row_off * G + m;
       }
+      if (dst < 0) continue;
+      const float* col = reinterpret_cast<const float*>(tsm) + (size_t)sidx * TPC_BLOCK;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < TPC_BLOCK; j += 2) {  // rotated start: conflict-free
+        s0 += col[(j + tid) & (TPC_BLOCK - 1)];
+        s1 += col[(j + 1 + tid) & (TPC_BLOCK - 1)];
+      }
+      partial[dst] = s0 + s1;
     }
   }
   if (epi_fused(A.epilogue)) block_loss_store<float>(lacc, A.loss_partial);

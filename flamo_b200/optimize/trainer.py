@@ -112,39 +112,62 @@ class Trainer:
         return None
 
     def _predict(self, inputs, targets):
-        """Returns (est, fused): the network output for the criteria, or — when exactly ONE registered criterion
-        consumes the prediction and it is an MSE the kernels can fuse with the |.| output layer — est = None and
-        fused = (criterion index, loss tensor) computed without materialising the prediction."""
+        """Returns (est, done): the network output for the criteria and a dict {criterion index: loss tensor} of
+        criteria already evaluated.  When exactly ONE registered criterion consumes the prediction and it is an MSE
+        the kernels can fuse with the |.| output layer, est is None: that criterion comes out of the sweep itself,
+        and the model-only criteria are evaluated first (they share the memoised parameter maps with the sweep)."""
         users = [i for i, c in enumerate(self.criterion) if getattr(c, "uses_prediction", True)]
         if self.fuse_criterion and len(users) == 1 and hasattr(self.net, "forward_loss"):
             i = users[0]
             kind = self._fused_kind(self.criterion[i])
             key = (i, tuple(inputs.shape), tuple(targets.shape))
             if kind is not None and not self.requires_model[i] and key not in self._unfusable:
-                loss = self.net.forward_loss(inputs, targets, kind)
+                inval = getattr(self.net, "_invalidate_caches", None)
+                if inval is not None:
+                    inval()
+                done = {j: (c(None, targets, self.net) if self.requires_model[j] else c(None, targets))
+                        for j, c in enumerate(self.criterion) if j != i}
+                loss = self.net.forward_loss(inputs, targets, kind, keep_caches=True)
                 if loss is not None:
-                    return None, (i, loss)
+                    done[i] = loss
+                    return None, done
                 self._unfusable.add(key)
-        return self.net(inputs), None
+                return self.net(inputs), done
+        return self.net(inputs), {}
 
-    def _criteria(self, est, fused, targets, weight=None):
-        parts, total = [], None
-        for i, (alpha, crit, needs_model) in enumerate(zip(self.alpha, self.criterion, self.requires_model)):
-            if fused is not None and fused[0] == i:
-                t = fused[1]
+    def _criteria(self, est, done, targets, weight=None):
+        """Evaluate the remaining criteria and combine: returns the vector [part_0, ..., part_{n-1}, total] with
+        total = sum_i alpha_i part_i (reference trainer.py:184-188).  `weight[i]` (multi-GPU shard weights) scales
+        part_i.  On CUDA the combination is one kernel (sweep.WeightedTotal)."""
+        from .. import sweep
+
+        parts = []
+        for i, (crit, needs_model) in enumerate(zip(self.criterion, self.requires_model)):
+            if i in done:
+                t = done[i]
             else:
                 t = crit(est, targets, self.net) if needs_model else crit(est, targets)
-            if weight is not None:
-                t = weight(i, t)
             parts.append(t)
-            term = t if alpha == 1 else alpha * t
+        scales = [1.0] * len(parts) if weight is None else [float(w) for w in weight]
+        if sweep.WeightedTotal.supported(parts):
+            return sweep.WeightedTotal.apply(tuple(self.alpha), tuple(scales), *parts)
+        total = None
+        for i, t in enumerate(parts):
+            if scales[i] != 1.0:
+                t = parts[i] = t * scales[i]
+            term = t if self.alpha[i] == 1 else self.alpha[i] * t
             total = term if total is None else total + term
-        return total, parts
+        return torch.stack([p.reshape(()) for p in parts] + [total.reshape(())])
+
+    def _loss_vector(self, inputs, targets):
+        """Forward + criteria: [per-criterion values ..., weighted total] as one tensor (differentiable)."""
+        est, done = self._predict(inputs, targets)
+        return self._criteria(est, done, targets)
 
     def _losses(self, inputs, targets):
-        """Forward + criteria: returns (total, [per-criterion tensors])."""
-        est, fused = self._predict(inputs, targets)
-        return self._criteria(est, fused, targets)
+        """(total, [per-criterion tensors]) — kept for callers of the earlier interface."""
+        vals = self._loss_vector(inputs, targets)
+        return vals[-1], list(vals[:-1].unbind(0))
 
     # -- one optimisation step, as a pure device-side function (captured or eager) --------------------
     def _zero_grad(self):
@@ -155,10 +178,13 @@ class Trainer:
         return vals
 
     def _train_core(self, inputs, targets):
-        loss, parts = self._losses(inputs, targets)
-        loss.backward()
-        vals = torch.stack([p.detach().reshape(()) for p in parts] + [loss.detach().reshape(())])
-        vals = self._sync(vals)
+        from .. import sweep
+
+        vals = self._loss_vector(inputs, targets)
+        # d total / d .: seed the backward pass on the vector itself with a constant one-hot (no select / fill kernels)
+        seed = sweep._const_tensor((0.0,) * (vals.numel() - 1) + (1.0,), vals.dtype, vals.device)
+        torch.autograd.backward(vals, grad_tensors=seed)
+        vals = self._sync(vals.detach())
         self.optimizer.step()
         return vals
 
@@ -227,8 +253,7 @@ class Trainer:
         inputs, targets = data
         inputs = self.move_to_device(inputs)
         targets = self.move_to_device(targets)
-        loss, parts = self._losses(inputs, targets)
-        vals = torch.stack([p.reshape(()) for p in parts] + [loss.reshape(())]).tolist()
+        vals = self._loss_vector(inputs, targets).tolist()
         self._log(self.valid_loss_log, vals[:-1])
         return vals[-1]
 

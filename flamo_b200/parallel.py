@@ -59,16 +59,16 @@ class DataParallelTrainer(Trainer):
     def _zero_grad_captured(self):
         self._flat.zero_()
 
-    def _losses(self, inputs, targets):
+    def _loss_vector(self, inputs, targets):
         if self.shard == "batch" or self.world == 1:
-            return super()._losses(inputs, targets)
+            return super()._loss_vector(inputs, targets)
         M = self.net.nfft // 2 + 1
         b0, b1 = bin_range(M, self.rank, self.world)
         with sweep.bin_shard(b0, b1):
-            est, fused = self._predict(inputs, targets)  # a fused criterion slices the target itself
+            est, done = self._predict(inputs, targets)  # a fused criterion slices the target itself
         tg = targets[:, b0:b1] if targets.shape[1] == M else targets
-        return self._criteria(est, fused, tg, weight=lambda i, t: t / self.world if self.requires_model[i]
-                              else t * ((b1 - b0) / M))
+        weight = [1.0 / self.world if self.requires_model[i] else (b1 - b0) / M for i in range(len(self.criterion))]
+        return self._criteria(est, done, tg, weight=weight)
 
     def _sync(self, vals):
         if self.world == 1:

@@ -362,22 +362,34 @@ class Shell(nn.Module):
             if f is not None:
                 f()
 
-    def forward(self, x, ext_param=None):
-        self._invalidate_caches()  # memoised maps live for one forward (+ its criteria) only
-        x = self.__input_layer(x)
-        core, out = self.__core, self.__output_layer
-        if hasattr(core, "_lower") and torch.is_tensor(x) and x.is_complex():
+    def _input_and_program(self, x, ext_param):
+        """Input layer, then lowering of the core into a sweep program (None if the core cannot be lowered or the
+        input layer did not produce a bin-domain tensor).  Running the input-layer FFT on a side stream, concurrently
+        with the parameter maps, was measured and dropped: the cross-stream edges cost a captured step 9 us
+        (profiles/r01_notes.md)."""
+        core = self.__core
+        X = self.__input_layer(x)
+        prog = None
+        if hasattr(core, "_lower") and torch.is_tensor(X) and X.is_complex():
             if hasattr(core, "check_input_shape"):
-                core.check_input_shape(x)
-            prog = sweep.Program(self.nfft, _alias_of(core), x.dtype, x.device)
+                core.check_input_shape(X)
+            prog = sweep.Program(self.nfft, _alias_of(core), X.dtype, X.device)
             core._lower(prog, ext_param)
+        return X, prog
+
+    def forward(self, x, ext_param=None, keep_caches: bool = False):
+        if not keep_caches:
+            self._invalidate_caches()  # memoised maps live for one forward (+ its criteria) only
+        core, out = self.__core, self.__output_layer
+        x, prog = self._input_and_program(x, ext_param)
+        if prog is not None:
             if self.fuse_output and _is_abs_layer(out):
                 return prog.run(x, epilogue=EPI_ABS)
             return out(prog.run(x, epilogue=EPI_NONE))
         x = core(x, ext_param) if ext_param is not None else core(x)
         return out(x)
 
-    def forward_loss(self, x, target, kind: int, ext_param=None):
+    def forward_loss(self, x, target, kind: int, ext_param=None, keep_caches: bool = False):
         """criterion(self(x), target) with the |.| output layer and the criterion fused into the sweep kernel
         (sweep.SweepLossFunction; kind = _lib.CRIT_MSE | CRIT_MSE_CHSUM).  Returns None when this Shell cannot be
         fused (output layer is not |.|, core is not a single sweep launch, unexpected shapes): the caller then
@@ -385,14 +397,11 @@ class Shell(nn.Module):
         core, out = self.__core, self.__output_layer
         if not (self.fuse_output and _is_abs_layer(out) and hasattr(core, "_lower")):
             return None
-        self._invalidate_caches()
-        x = self.__input_layer(x)
-        if not (torch.is_tensor(x) and x.is_complex()):
+        if not keep_caches:
+            self._invalidate_caches()
+        x, prog = self._input_and_program(x, ext_param)
+        if prog is None:
             return None
-        if hasattr(core, "check_input_shape"):
-            core.check_input_shape(x)
-        prog = sweep.Program(self.nfft, _alias_of(core), x.dtype, x.device)
-        core._lower(prog, ext_param)
         return prog.run_loss(x, target, kind)
 
     # -- accessors -------------------------------------------------------------------------------

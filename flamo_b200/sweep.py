@@ -10,6 +10,7 @@ C-ABI calls.  Gradients come back w.r.t. the coefficients and autograd chains th
 """
 from __future__ import annotations
 
+import os
 import threading
 from typing import List, Optional, Sequence, Tuple
 
@@ -434,6 +435,68 @@ class SparsityFunction(torch.autograd.Function):
                                                         torch.cuda.current_stream(g.device).cuda_stream))
         launch_count += 1
         return gA
+
+
+class WeightedTotal(torch.autograd.Function):
+    """vals = [s_0 part_0, ..., s_{n-1} part_{n-1}, sum_i alpha_i s_i part_i] in one launch (libfsweep
+    fsweep_weighted_total): the Trainer's `loss += alpha * criterion` accumulation (reference trainer.py:184-188)
+    and the vector it reads back once per step.  Backward is one elementwise kernel."""
+
+    MAX = 8
+
+    @staticmethod
+    def supported(parts) -> bool:
+        p0 = parts[0]
+        if os.environ.get("FLAMO_B200_WEIGHTED_TOTAL", "1") == "0":
+            return False
+        return (_BACKEND.name == "cuda" and 1 <= len(parts) <= WeightedTotal.MAX and torch.is_tensor(p0) and p0.is_cuda
+                and p0.dtype in (torch.float32, torch.float64)
+                and all(torch.is_tensor(p) and p.is_cuda and p.dtype == p0.dtype and p.numel() == 1
+                        and p.device == p0.device for p in parts))
+
+    @staticmethod
+    def forward(ctx, alphas, scales, *parts):
+        global launch_count
+        import ctypes as C
+
+        n = len(parts)
+        parts = [p.detach().reshape(1).contiguous() for p in parts]
+        vals = torch.empty(n + 1, dtype=parts[0].dtype, device=parts[0].device)
+        pp = (C.c_void_p * n)(*[p.data_ptr() for p in parts])
+        aa = (C.c_double * n)(*[float(a) for a in alphas])
+        ss = (C.c_double * n)(*[float(a) for a in scales])
+        _lib.check(_lib.lib().fsweep_weighted_total(pp, aa, ss, n, _real_code(vals.dtype), vals.data_ptr(),
+                                                     torch.cuda.current_stream(vals.device).cuda_stream))
+        launch_count += 1
+        ctx.coef = (tuple(float(a) * float(c) for a, c in zip(alphas, scales)), tuple(float(c) for c in scales))
+        for c in ctx.coef:  # created here, outside any later capture of the backward
+            _const_tensor(c, vals.dtype, vals.device)
+        ctx.shapes = [p.shape for p in parts]
+        return vals
+
+    @staticmethod
+    def backward(ctx, g):
+        n = len(ctx.coef[0])
+        a_s = _const_tensor(ctx.coef[0], g.dtype, g.device)
+        sc = _const_tensor(ctx.coef[1], g.dtype, g.device)
+        if all(c == 1.0 for c in ctx.coef[1]):
+            gp = torch.addcmul(g[:n], a_s, g[n:n + 1].expand(n))  # g_i + alpha_i g_total: one kernel
+        else:
+            gp = torch.addcmul(sc * g[:n], a_s, g[n:n + 1].expand(n))
+        return (None, None, *[gp[i].reshape(()) for i in range(n)])
+
+
+_CONST_TENSORS = {}
+
+
+def _const_tensor(values, dtype, device):
+    """Small constant tensors are created once per (values, dtype, device): creating a tensor from host data is
+    not allowed inside CUDA-graph capture."""
+    key = (values, dtype, str(device))
+    t = _CONST_TENSORS.get(key)
+    if t is None:
+        t = _CONST_TENSORS[key] = torch.tensor(values, dtype=dtype, device=device)
+    return t
 
 
 def pack_sections(b: torch.Tensor, a: torch.Tensor, parallel: bool, real: torch.dtype) -> torch.Tensor:

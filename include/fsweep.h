@@ -137,6 +137,10 @@ FSWEEP_API int fsweep_plan_num_coeffs(const fsweep_plan_t* plan);
  * given the total bin count M (only TABLE kinds depend on M). */
 FSWEEP_API int64_t fsweep_plan_coeff_numel(const fsweep_plan_t* plan, int slot, int64_t M);
 
+/* name of the kernel family a forward (backward != 0: backward) call over n_bins bins will launch for this plan
+ * (bench / profile bookkeeping; static string) */
+FSWEEP_API const char* fsweep_plan_kernel_family(const fsweep_plan_t* plan, int64_t n_bins, int backward);
+
 /* scratch the caller must provide to fsweep_backward / fsweep_*_loss (fsweep_forward needs none) */
 FSWEEP_API size_t fsweep_workspace_bytes(const fsweep_plan_t* plan, int64_t batch, int64_t cols, int64_t n_bins);
 
@@ -205,6 +209,13 @@ FSWEEP_API int fsweep_expm_backward(const void* P, const void* G, void* gP, int 
 FSWEEP_API int fsweep_sparsity_forward(const void* A, int n_mats, int n, int dtype, void* loss, void* stream);
 FSWEEP_API int fsweep_sparsity_backward(const void* A, const void* gloss, int n_mats, int n, int dtype, void* gA,
                                         void* stream);
+
+/* Weighted total of the step's criteria (reference optimize/trainer.py:184-188): parts[i] are device real[1];
+ * vals (device real[n+1]) receives vals[i] = scales[i] * part_i (i < n) followed by sum_i alphas[i] * vals[i].
+ * One launch. */
+#define FSWEEP_MAX_CRITERIA 8
+FSWEEP_API int fsweep_weighted_total(const void* const* parts, const double* alphas, const double* scales, int n,
+                                     int dtype, void* vals, void* stream);
 
 /* number of kernels the last forward / backward call of this thread enqueued (bench bookkeeping) */
 FSWEEP_API int fsweep_last_launch_count(void);
