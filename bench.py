@@ -44,8 +44,12 @@ METRIC = "freq-bins*channels/sec (Trainer.train_step)"
 UNIT = "bins*ch/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of the backward sweep kernel, one launch, from the committed
 # `ncu --set full` capture (profiles/r01e_ncu_full_sweep_kernels.md)
-NCU_TRAFFIC_BYTES = 661504
-NCU_TRAFFIC_SOURCE = "profiles/r01e_ncu_full_sweep_kernels.md (ncu --set full, fsweep_loop_bwd_kernel<float,8>)"
+NCU_TRAFFIC_BYTES = 642816
+NCU_TRAFFIC_SOURCE = "profiles/r01g_ncu_full_tpc_bwd.md (ncu --set full, fsweep_tpc_kernel<8,bwd>)"
+# real flops of one fused backward launch (~3.7 kflop per bin forward + backward for the 8x8 loop:
+# LU 8/3 N^3 + build 6 N^2 + forward solve 8 N^2 + adjoint solve 8 N^2 + gradient contractions 14 N^2 + 8 delays)
+FLOPS_PER_BIN = 8 / 3 * 512 + (6 + 8 + 8 + 14) * 64 + 8 * 40
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FMA lanes x 2 flop x 1.965 GHz = 74.4 (nominal)
 WORKLOAD = "cfg2: e8_colorless_fdn 8x8 FDN (Gain->Recursion(parallelDelay,Matrix orthogonal)->Gain), nfft=96000, B=1"
 
 
@@ -382,8 +386,12 @@ def kernel_roofline(model, x_dev, flush, reps=30):
             "forward_kernel": {"kernel": plan.kernel_family(M, False) + " (validation / inference only; not in the training step)",
                                "us_per_launch": t_fwd * 1e6,
                                "achieved": bytes_per_launch / t_fwd / 1e9, "frac": bytes_per_launch / t_fwd / 1e9 / peak},
-            "note": "config 2 moves 0.58 MB per launch and does ~2-4 kflop per bin: it is instruction-issue / latency "
-                    "bound, not HBM bound (SURVEY.md §8d; profiles/); the HBM fraction is reported as the contract asks"}
+            "fp32": {"flops_per_launch": FLOPS_PER_BIN * M, "achieved_tflops": FLOPS_PER_BIN * M / t_bwd / 1e12,
+                     "nominal_peak_tflops": FP32_PEAK_TFLOPS, "frac": FLOPS_PER_BIN * M / t_bwd / 1e12 / FP32_PEAK_TFLOPS},
+            "note": "config 2 moves 0.58 MB per launch and does ~3.7 kflop per bin: it is dependent-issue latency "
+                    "bound (one bin per thread, 2.4 warps per scheduler), not HBM bound (SURVEY.md §8d; profiles/"
+                    "r01g_ncu_full_tpc_bwd.md); the HBM fraction is reported as the contract asks, the FP32 fraction "
+                    "beside it"}
 
 
 def main():

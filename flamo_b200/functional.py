@@ -43,6 +43,37 @@ def skew_matrix(X: torch.Tensor) -> torch.Tensor:
     return U - U.mT
 
 
+def expm_capturable(S: torch.Tensor, max_squarings: int = 20) -> torch.Tensor:
+    """exp(S) for square matrices too large for the one-CTA device kernel (libfsweep fsweep_expm_*, n <= 28),
+    written so that it never reads anything back to the host and can therefore be captured in a CUDA graph
+    (torch.matrix_exp copies the matrix norm to the host to choose its Pade degree).  Scaling and squaring in
+    float64: X = S / 2^s with ||X||_1 <= 1/4 (s computed on the device), degree-12 Taylor polynomial evaluated
+    Paterson-Stockmeyer style (7 products, remainder 0.25^13/13! ~ 2e-18), then `max_squarings` squarings of which
+    the first s are kept (the rest are masked out).  Plain differentiable PyTorch: autograd gives the exact
+    derivative of the approximant."""
+    dt = S.dtype
+    X = S.to(torch.float64)
+    n = X.shape[-1]
+    norm = X.abs().sum(dim=-2).amax(dim=-1)
+    s = torch.clamp(torch.ceil(torch.log2(torch.clamp(norm, min=1e-300) * 4.0)), min=0.0, max=float(max_squarings))
+    X = X * torch.exp2(-s)[..., None, None]
+    I = torch.eye(n, dtype=torch.float64, device=S.device)
+    X2 = X @ X
+    X3 = X2 @ X
+    X4 = X2 @ X2
+    X5 = X3 @ X2
+    X6 = X3 @ X3
+    c = [1.0]
+    for k in range(1, 13):
+        c.append(c[-1] / k)
+    B0 = c[0] * I + c[1] * X + c[2] * X2 + c[3] * X3 + c[4] * X4 + c[5] * X5
+    B1 = c[6] * I + c[7] * X + c[8] * X2 + c[9] * X3 + c[10] * X4 + c[11] * X5
+    E = B0 + X6 @ (B1 + c[12] * X6)
+    for i in range(max_squarings):
+        E = torch.where((s > i)[..., None, None], E @ E, E)
+    return E.to(dt)
+
+
 def _as_tensor(v, like=None, dtype=None, device=None):
     if isinstance(v, torch.Tensor):
         return v

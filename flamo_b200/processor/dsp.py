@@ -25,8 +25,8 @@ import torch.nn.functional as F
 from .. import sweep
 from .._lib import OP_DELAY, OP_GAIN, OP_PDELAY, OP_PGAIN, OP_PSOS, OP_PTABLE, OP_SOS, OP_TABLE
 from ..auxiliary.eq import eq_freqs, geq
-from ..functional import (HadamardMatrix, RotationMatrix, bandpass_filter, highpass_filter, lowpass_filter,
-                          skew_matrix)
+from ..functional import (HadamardMatrix, RotationMatrix, bandpass_filter, expm_capturable, highpass_filter,
+                          lowpass_filter, skew_matrix)
 from ..utils import to_complex
 
 # ======================================================================================= transforms
@@ -309,21 +309,24 @@ class Matrix(Gain):
         """matrix_exp(skew(x)).  On CUDA the library's capture-safe kernel is used; the result is
         memoised per parameter version so that the sweep and parameter-only criteria (sparsity_loss
         calls map(param) again, reference loss.py:41-42) share one evaluation per step."""
-        if not sweep.OrthogonalMap.supported(x):
+        if not x.is_cuda:
             return torch.matrix_exp(skew_matrix(x))
         key = (x._version, torch.is_grad_enabled() and x.requires_grad)
         if x is self.param:
             hit = self._expm_cache
             if hit is not None and hit[0] == key:
                 return hit[1]
-        out = sweep.OrthogonalMap.apply(x)
+        if sweep.OrthogonalMap.supported(x):
+            out = sweep.OrthogonalMap.apply(x)
+        else:  # wider than the one-CTA kernel: capture-safe PyTorch scaling-and-squaring (float64 inside)
+            out = expm_capturable(skew_matrix(x))
         if x is self.param:
             self._expm_cache = (key, out)
         return out
 
     def _up(self, param):
         # the orthogonal map upcasts internally; handing it `param` itself lets the memo above hit
-        if self.matrix_type == "orthogonal" and sweep.OrthogonalMap.supported(param):
+        if self.matrix_type == "orthogonal" and param.is_cuda:
             return param
         return super()._up(param)
 
