@@ -342,6 +342,37 @@ class Matrix(Gain):
         self.get_freq_convolve()
 
 
+class HouseholderMatrix(Gain):
+    """U = I - 2 u u^T with u = param / ||param||, param (N, 1) (reference dsp.py:679-782).  The reference applies it
+    as two vector products; here it is lowered as a dense GAIN whose N x N matrix is formed from u in the map's
+    precision (O(N^2), differentiable), so it fuses with its neighbours like any other gain."""
+
+    def __init__(self, size: tuple = (1, 1), nfft: int = 2 ** 11, requires_grad: bool = False,
+                 alias_decay_db: float = 0.0, device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        assert size[0] == size[1], "Matrix must be square"
+        super().__init__(size=(size[0], 1), nfft=nfft, map=lambda x: to_complex(x) / torch.norm(x, dim=0, keepdim=True),
+                         requires_grad=requires_grad, alias_decay_db=alias_decay_db, device=device, dtype=dtype)
+
+    def check_input_shape(self, x):
+        if self.size[0] != x.shape[2]:
+            raise ValueError(f"parameter shape = {self.size} not compatible with input signal of shape = ({x.shape}).")
+
+    def get_io(self):
+        self.input_channels = self.size[0]
+        self.output_channels = self.size[0]
+
+    def _matrix(self, param):
+        u = self.map(param)
+        u = u.real if u.is_complex() else u
+        return torch.eye(u.shape[0], dtype=u.dtype, device=u.device) - 2 * (u @ u.mT)
+
+    def _emit(self, prog, param):
+        prog.leaf(OP_GAIN, self.output_channels, self.input_channels, self._matrix(self._up(param)))
+
+    def probe(self, z):
+        return to_complex(self._matrix(self.param))
+
+
 # ========================================================================================== filters
 
 
@@ -537,6 +568,64 @@ class parallelBiquad(Biquad):
 
     def check_param_shape(self):
         assert len(self.size) == 3, "Parameter size must be 3D, for 3D sapce use Biquad module."
+
+
+class SOSFilter(_SectionFilter):
+    """Cascade of second-order sections given directly by their coefficients: param (K, 6, N_out, N_in) ordered
+    [b0, b1, b2, a0, a1, a2]; the map optionally normalises every section by a0 (reference dsp.py:1767-1975).
+    Lowered as the same SOS op as Biquad / SVF / GEQ."""
+
+    def __init__(self, size: tuple = (1, 1), n_sections: int = 1, nfft: int = 2 ** 11, fs: int = 48000,
+                 alias_decay_db: float = 0.0, device: Optional[str] = None, dtype: torch.dtype = torch.float32,
+                 normalize_a0: bool = True):
+        self.n_sections, self.fs, self.device, self.dtype, self.normalize_a0 = n_sections, fs, device, dtype, normalize_a0
+        self.alias_envelope_dcy = _alias_envelope(nfft, alias_decay_db, device, dtype)[:3].reciprocal()
+        self.get_map()
+        DSP.__init__(self, size=(n_sections, *self.get_size(), *size), nfft=nfft, map=self.map, requires_grad=False,
+                     alias_decay_db=alias_decay_db, device=device, dtype=dtype)
+        self.initialize_class()
+
+    def get_size(self):
+        return (6,)
+
+    def get_map(self):
+        self.map = self._normalise
+
+    def _normalise(self, x):
+        if not self.normalize_a0:
+            return x
+        a0 = x[:, 3:4]
+        eps = torch.finfo(x.dtype).eps
+        safe = torch.where(torch.abs(a0) > eps, a0, torch.full_like(a0, eps))
+        y = x / safe
+        return torch.cat((y[:, :3], torch.ones_like(a0), y[:, 4:]), dim=1)
+
+    def init_param(self):
+        with torch.no_grad():
+            self.param.zero_()
+            self.param[:, 0] = 1.0
+            self.param[:, 3] = 1.0
+
+    def check_param_shape(self):
+        assert len(self.size) == 4, "Parameter size must be 4D, expected (K, 6, N_out, N_in)."
+        assert self.size[1] == 6, "Second dimension must be 6: [b0,b1,b2,a0,a1,a2]."
+
+    def _taps(self, mapped):
+        return (torch.stack((mapped[:, 0], mapped[:, 1], mapped[:, 2]), dim=0),
+                torch.stack((mapped[:, 3], mapped[:, 4], mapped[:, 5]), dim=0))
+
+
+class parallelSOSFilter(SOSFilter):
+    """param (K, 6, N) (reference dsp.py:1978-2073)."""
+
+    _parallel = True
+
+    def __init__(self, size: tuple = (1,), **kwargs):
+        super().__init__(size=size, **kwargs)
+
+    def check_param_shape(self):
+        assert len(self.size) == 3, "Parameter size must be 3D, expected (K, 6, N)."
+        assert self.size[1] == 6, "Second dimension must be 6: [b0,b1,b2,a0,a1,a2]."
 
 
 class SVF(_SectionFilter):
@@ -747,3 +836,120 @@ class parallelDelay(Delay):
 
     def check_param_shape(self):
         assert len(self.size) == 1, "delays must be 1D, for 2D delays use Delay module."
+
+
+class GainDelay(DSP):
+    """Gain and delay per channel pair: H[m][n] = map_gain(g)[m][n] gamma^d exp(-j omega d), d = map_delay(param[1])
+    * fs / unit samples; param (2, N_out, N_in) (reference dsp.py:3554-3724).  The dense variant is an elementwise
+    (not a matrix) product of a gain and a delay matrix, so it is lowered as a streamed response table built in
+    float64 with exact integer phases; the parallel variant is a PGAIN followed by a PDELAY."""
+
+    def __init__(self, size: tuple = (1, 1), max_len: int = 2000, isint: bool = False, unit: int = 100,
+                 nfft: int = 2 ** 11, fs: int = 48000, map_gain: Optional[callable] = None,
+                 map_delay: Optional[callable] = None, requires_grad: bool = False, alias_decay_db: float = 0.0,
+                 device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        self.fs, self.max_len, self.unit, self.isint = fs, max_len, unit, isint
+        self._custom_gain_map, self._custom_delay_map = map_gain is not None, map_delay is not None
+        self.map_gain = map_gain if map_gain is not None else _identity
+        self.map_delay = map_delay if map_delay is not None else _identity
+        super().__init__(size=(2, *size), nfft=nfft, requires_grad=requires_grad, alias_decay_db=alias_decay_db,
+                         device=device, dtype=dtype)
+        self.initialize_class()
+
+    def init_param(self):
+        shape = self.size[1:]
+        with torch.no_grad():
+            nn.init.ones_(self.param[0])
+            if self.isint:
+                d = torch.randint(1, self.max_len, shape, device=self.device, dtype=torch.int64).to(self.param.dtype)
+            else:
+                d = torch.rand(shape, device=self.device, dtype=self.dtype) * self.max_len
+            self.param[1].copy_(self.sample2s(d))
+        self.order = int(torch.ceil(d).max().item()) + 1
+
+    def s2sample(self, delay):
+        return delay * self.fs / self.unit
+
+    def sample2s(self, delay):
+        return delay / self.fs * self.unit
+
+    def check_input_shape(self, x):
+        if (int(self.nfft / 2 + 1), self.input_channels) != (x.shape[1], x.shape[2]):
+            raise ValueError(
+                f"parameter shape = {self.param.shape} not compatible with input signal of shape = ({x.shape}).")
+
+    def check_param_shape(self):
+        assert len(self.size) == 3 and self.size[0] == 2, "GainDelay parameters must have shape (2, N_out, N_in)."
+
+    def get_io(self):
+        self.input_channels = self.size[-1]
+        self.output_channels = self.size[-1] if self._parallel else self.size[-2]
+
+    def get_gains(self):
+        return lambda param: to_complex(self.map_gain(param[0]))
+
+    def get_delays(self):
+        return lambda param: self.s2sample(self.map_delay(param[1]))
+
+    def initialize_class(self):
+        self.check_param_shape()
+        self.get_io()
+        if self.requires_grad and not self._custom_delay_map:
+            self.map_delay = lambda x: F.softplus(x)
+        self.omega = self._omega(self.dtype, self.device).unsqueeze(1)
+        self.get_freq_response()
+        self.get_freq_convolve()
+
+    def get_freq_response(self):
+        self.freq_response = self._response
+
+    def _response(self, param):
+        """(M, N_out, N_in) | (M, N) response; integer delays take their phase index k*d mod nfft in integers."""
+        g = self.map_gain(param[0])
+        d = self.s2sample(self.map_delay(param[1])).to(g.dtype)
+        k = torch.arange(0, self.nfft // 2 + 1, device=d.device).view(-1, *([1] * d.dim()))
+        if self.isint:
+            d = d.round()
+            idx = torch.remainder(k * d.detach().to(torch.int64).unsqueeze(0), self.nfft).to(d.dtype)
+            ph = (2 * math.pi / self.nfft) * idx
+        else:
+            ph = (2 * math.pi / self.nfft) * k.to(d.dtype) * d.unsqueeze(0)
+        mag = (g * (10 ** (-abs(self._alias_db) / self.nfft / 20)) ** d).unsqueeze(0)
+        if mag.is_complex():  # a custom map_gain may return complex gains
+            return mag * torch.exp(-1j * ph)
+        return torch.complex(mag * torch.cos(ph), -mag * torch.sin(ph))
+
+    def get_freq_convolve(self):
+        self.freq_convolve = lambda x, param: self._sweep(x, param)
+
+    def _emit(self, prog, param):
+        p = self._up(param)
+        if self._parallel:
+            g = self.map_gain(p[0])
+            prog.leaf(OP_PGAIN, self.output_channels, self.input_channels, g.reshape(-1))
+            prog.leaf(OP_PDELAY, self.output_channels, self.input_channels, self.s2sample(self.map_delay(p[1])).reshape(-1),
+                      isint=self.isint)
+            return
+        H = self._response(p)
+        prog.leaf(OP_TABLE, self.output_channels, self.input_channels, H)
+
+    def probe(self, z):
+        g = to_complex(self.map_gain(self.param[0]))
+        m = self.s2sample(self.map_delay(self.param[1]))
+        if self.isint:
+            m = m.round()
+        H = g * (self.gamma ** m) * (1.0 / z) ** m
+        return torch.diag_embed(H) if self._parallel else H
+
+
+class parallelGainDelay(GainDelay):
+    """param (2, N) (reference dsp.py:3727-3778)."""
+
+    _parallel = True
+
+    def __init__(self, size: tuple = (1,), **kwargs):
+        super().__init__(size=size, **kwargs)
+
+    def check_param_shape(self):
+        assert len(self.size) == 2 and self.size[0] == 2, (
+            "parallelGainDelay parameters must have shape (2, N), for MIMO use GainDelay module.")

@@ -283,6 +283,81 @@ class Recursion(nn.Module):
         return torch.eye(Fm.shape[0], dtype=Fm.dtype, device=Fm.device) - Fm @ Bm
 
 
+# ========================================================================================== parallel
+
+
+class Parallel(nn.Module):
+    """Two branches fed with the same input; outputs summed or concatenated along the channel axis (reference
+    system.py:570-772).  Each branch is lowered and launched as its own fused sweep program; the sum / concatenation
+    is the only PyTorch op.  Inside a Series it is therefore a launch boundary; inside a Recursion path it is
+    not supported (FSWEEP_E_UNSUPPORTED)."""
+
+    def __init__(self, brA, brB, sum_output: bool = True):
+        super().__init__()
+        self.branchA = self._as_branch(brA, "A")
+        self.branchB = self._as_branch(brB, "B")
+        self.sum_output = sum_output
+        self.nfft = self._shared("nfft")
+        self.alias_decay_db = self._shared("alias_decay_db")
+        self.dtype = self._shared("dtype")
+        self.input_channels, self.output_channels = self._check_io()
+
+    @staticmethod
+    def _as_branch(b, name):
+        if isinstance(b, (nn.Sequential, OrderedDict)) and not isinstance(b, Series):
+            warnings.warn(f"Branch {name} has been converted to a Series class instance.")
+            return Series(b)
+        return b
+
+    def _shared(self, attr):
+        a, b = getattr(self.branchA, attr, None), getattr(self.branchB, attr, None)
+        if a is None:
+            warnings.warn(f"The feedforward pass does not possess the attribute {attr}.")
+        if b is None:
+            warnings.warn(f"The feedback pass does not possess the attribute {attr}.")
+        if a is not None and b is not None:
+            assert a == b, (f"Branch A has {attr} = {a} and branch B has {attr} = {b}. They must have the same value.")
+        return a if a is not None else b
+
+    def _check_io(self):
+        io = {}
+        for name, br in (("A", self.branchA), ("B", self.branchB)):
+            for side in ("input_channels", "output_channels"):
+                v = getattr(br, side, None)
+                if v is None:
+                    raise ValueError(f"Branch {name} does not possess the attribute {side}.")
+                io[name, side] = v
+        assert io["A", "input_channels"] == io["B", "input_channels"], (
+            f"Branch A has {io['A', 'input_channels']} input channels, but branch B has "
+            f"{io['B', 'input_channels']} input channels. They must be the same.")
+        if self.sum_output:
+            assert io["A", "output_channels"] == io["B", "output_channels"], (
+                f"Branch A has {io['A', 'output_channels']} output channels, but branch B has "
+                f"{io['B', 'output_channels']} output channels. They must be the same if their output is being summed.")
+            return io["A", "input_channels"], io["A", "output_channels"]
+        return io["A", "input_channels"], io["A", "output_channels"] + io["B", "output_channels"]
+
+    def forward(self, X, ext_param: dict = None):
+        ext_a = ext_b = None
+        if ext_param is not None:
+            for key, p in ext_param.items():
+                if "branchA" in key:
+                    ext_a = p
+                elif "branchB" in key:
+                    ext_b = p
+        YA = self.branchA(X, ext_a) if ext_a is not None else self.branchA(X)
+        YB = self.branchB(X, ext_b) if ext_b is not None else self.branchB(X)
+        return YA + YB if self.sum_output else torch.cat((YA, YB), dim=2)
+
+    def probe(self, z):
+        HA, HB = self.branchA.probe(z), self.branchB.probe(z)
+        return HA + HB if self.sum_output else torch.cat([HA, HB], dim=0)
+
+    def probe_w(self, w):
+        HA, HB = self.branchA.probe_w(w), self.branchB.probe_w(w)
+        return HA + HB if self.sum_output else torch.cat([HA, HB], dim=0)
+
+
 # ============================================================================================= shell
 
 

@@ -4,7 +4,8 @@ A description is plain data:
 
     ("Series", [desc, ...], [key, ...] | None)
     ("Recursion", ff_desc, fb_desc)
-    (ClassName, ctor_kwargs [, post])        post: {"delay_samples": [...]} | {"assign": tensor}
+    ("Parallel", a_desc, b_desc [, sum_output])
+    (ClassName, ctor_kwargs [, post])        post: {"delay_samples": [...]} | {"assign": tensor} | {"requires_grad": True}
 
 `build(desc, dsp, system, ...)` instantiates it with any library exposing the flamo class
 API — this package's `processor.dsp/system`, or the reference's own modules (used only by
@@ -32,6 +33,10 @@ def build(desc, dsp, system, nfft, alias_decay_db, dtype=torch.float32, device=N
         ff = build(desc[1], dsp, system, nfft, alias_decay_db, dtype, device)
         fb = build(desc[2], dsp, system, nfft, alias_decay_db, dtype, device)
         return system.Recursion(fF=ff, fB=fb)
+    if name == "Parallel":
+        a = build(desc[1], dsp, system, nfft, alias_decay_db, dtype, device)
+        b = build(desc[2], dsp, system, nfft, alias_decay_db, dtype, device)
+        return system.Parallel(a, b, sum_output=desc[3] if len(desc) > 3 else True)
     kwargs = dict(desc[1])
     mod = getattr(dsp, name)(nfft=nfft, alias_decay_db=alias_decay_db, dtype=dtype, device=device, **kwargs)
     post = desc[2] if len(desc) > 2 else None
@@ -41,6 +46,8 @@ def build(desc, dsp, system, nfft, alias_decay_db, dtype=torch.float32, device=N
             mod.assign_value(mod.sample2s(d))
         if "assign" in post:
             mod.assign_value(torch.as_tensor(post["assign"], dtype=dtype, device=device))
+        if post.get("requires_grad"):  # modules whose constructor has no requires_grad argument (SOSFilter)
+            mod.param.requires_grad_(True)
     return mod
 
 

@@ -4,6 +4,8 @@ Each case = a model description (flamo_b200.workloads format) + nfft, alias deca
 trailing columns and the seed under which the REFERENCE constructors drew the raw parameters
 (the drawn values are stored in the golden file; nothing here depends on RNG streams).
 """
+import math
+
 import numpy as np
 import torch
 
@@ -69,6 +71,17 @@ def _case(desc, nfft, alias=30.0, B=1, C=None, seed=0, grads=True):
 
 def _svf(ft, size=(3, 2), K=2):
     return ("SVF", dict(size=size, n_sections=K, filter_type=ft, fs=FS, requires_grad=True))
+
+
+def _sos_coeffs(K, shape, seed):
+    """Deterministic stable second-order sections [b0,b1,b2,a0,a1,a2] of shape (K, 6, *shape)."""
+    g = torch.Generator().manual_seed(seed)
+    b = torch.rand(K, 3, *shape, generator=g, dtype=torch.float64) * 2 - 1
+    a0 = 0.8 + 0.7 * torch.rand(K, 1, *shape, generator=g, dtype=torch.float64)
+    r = 0.3 + 0.6 * torch.rand(K, 1, *shape, generator=g, dtype=torch.float64)  # pole radius
+    th = math.pi * torch.rand(K, 1, *shape, generator=g, dtype=torch.float64)
+    a = torch.cat((a0, -2 * r * torch.cos(th) * a0, r * r * a0), dim=1)
+    return torch.cat((b, a), dim=1).tolist()
 
 
 CASES = {
@@ -142,6 +155,46 @@ CASES = {
                                              {"assign": [0.7, 0.65, 0.6, 0.55]})]),
                                 ("Matrix", dict(size=(4, 4), matrix_type="orthogonal", requires_grad=True),
                                  )), 4096, seed=28),
+    # --- SOSFilter, HouseholderMatrix, GainDelay, Parallel ---------------
+    "sosfilter": _case(("SOSFilter", dict(size=(2, 3), n_sections=2, fs=FS),
+                        {"assign": _sos_coeffs(2, (2, 3), 31)}), 4096, seed=31, grads=False),  # the reference's a0
+    # normalisation map writes in place: its own autograd cannot differentiate it (dsp.py:1857-1862)
+    "psosfilter_raw_a0": _case(("parallelSOSFilter", dict(size=(4,), n_sections=3, fs=FS, normalize_a0=False),
+                                {"assign": _sos_coeffs(3, (4,), 32), "requires_grad": True}), 2048, B=2, seed=32),
+    "householder_series": _case(("Series", [
+        ("Gain", dict(size=(4, 2), requires_grad=True)),
+        ("HouseholderMatrix", dict(size=(4, 4), requires_grad=True)),
+        ("Gain", dict(size=(3, 4), requires_grad=True)),
+    ]), 2048, B=2, seed=33),
+    "fdn4_householder": _case(("Series", [
+        ("Gain", dict(size=(4, 1), requires_grad=True)),
+        ("Recursion",
+         ("Series", [("parallelDelay", dict(size=(4,), max_len=700, isint=True, fs=FS, requires_grad=False),
+                      {"delay_samples": [241, 331, 419, 547]}),
+                     ("parallelGain", dict(size=(4,), requires_grad=True), {"assign": [0.9, 0.88, 0.86, 0.84]})]),
+         ("HouseholderMatrix", dict(size=(4, 4), requires_grad=True))),
+        ("Gain", dict(size=(1, 4), requires_grad=True)),
+    ], ["input_gain", "feedback_loop", "output_gain"]), 4096, seed=34),
+    "gaindelay_frac": _case(("GainDelay", dict(size=(3, 2), max_len=900, isint=False, fs=FS, requires_grad=True)),
+                            4096, seed=35),
+    "gaindelay_int": _case(("GainDelay", dict(size=(2, 3), max_len=900, isint=True, fs=FS, requires_grad=False)),
+                           2048, seed=36, grads=False),
+    "pgaindelay_frac": _case(("parallelGainDelay", dict(size=(4,), max_len=600, isint=False, fs=FS,
+                                                       requires_grad=True)), 2048, B=2, seed=37),
+    "parallel_sum": _case(("Parallel",
+                           ("Series", [("Gain", dict(size=(3, 2), requires_grad=True)),
+                                       ("parallelDelay", dict(size=(3,), max_len=300, isint=True, fs=FS,
+                                                              requires_grad=False))]),
+                           ("Biquad", dict(size=(3, 2), n_sections=1, filter_type="lowpass", fs=FS, requires_grad=True)),
+                           True), 2048, B=2, seed=38),
+    "parallel_cat_in_series": _case(("Series", [
+        ("Gain", dict(size=(2, 2), requires_grad=True)),
+        ("Parallel",
+         ("Gain", dict(size=(2, 2), requires_grad=True)),
+         ("Series", [("Gain", dict(size=(3, 2), requires_grad=True)), ("parallelGain", dict(size=(3,), requires_grad=True))]),
+         False),
+        ("Gain", dict(size=(1, 5), requires_grad=True)),
+    ]), 2048, seed=39),
     "fir_filter": _case(("Filter", dict(size=(24, 2, 3), requires_grad=True)), 2048, seed=29),
     "pfir_filter": _case(("parallelFilter", dict(size=(40, 3), requires_grad=True)), 2048, seed=30),
 }

@@ -14,7 +14,8 @@ from helpers import build_case, grad_err
 
 pytestmark = pytest.mark.gpu
 
-NAMES = [n for n, c in C.CASES.items() if c["C"] is None and c["grads"]]
+# (a Parallel node is a launch boundary: such programs decline the fused path, see test_unfusable_programs_decline)
+NAMES = [n for n, c in C.CASES.items() if c["C"] is None and c["grads"] and not n.startswith("parallel_")]
 
 
 def target_for(kind, B, M, n_out, dtype):
@@ -125,5 +126,9 @@ def test_unfusable_programs_decline():
     assert shell.forward_loss(X, torch.ones(2, M, 2, 3, device="cuda"), _lib.CRIT_MSE) is None  # trailing columns
     X3 = C.make_input(2, M, core.input_channels, None).to(torch.complex64).cuda()
     assert shell.forward_loss(X3, torch.ones(2, M, 5, device="cuda"), _lib.CRIT_MSE) is None  # wrong target shape
+    case, g, pcore = build_case("parallel_sum", torch.float32, "cuda")
+    pshell = system.Shell(pcore, output_layer=dsp.Transform(lambda x: torch.abs(x)))
+    Xp = C.make_input(2, case["nfft"] // 2 + 1, 2, None).to(torch.complex64).cuda()
+    assert pshell.forward_loss(Xp, torch.ones(2, case["nfft"] // 2 + 1, 3, device="cuda"), _lib.CRIT_MSE) is None
     shell2 = system.Shell(core, output_layer=dsp.Transform(lambda x: x))
     assert shell2.forward_loss(X3, torch.ones(2, M, 2, device="cuda"), _lib.CRIT_MSE) is None  # no |.| output layer

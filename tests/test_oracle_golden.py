@@ -69,7 +69,7 @@ def _n_in(desc):
     name = desc[0]
     if name == "Series":
         return _n_in(desc[1][0])
-    if name == "Recursion":
+    if name in ("Recursion", "Parallel"):
         return _n_in(desc[1])
     size = desc[1]["size"]
     return size[-1]
