@@ -200,6 +200,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
     if (o.kind == FSWEEP_OP_SOS || o.kind == FSWEEP_OP_PSOS) P.needs_ctx = 1;
     k.acc_off = acc_total;
     k.row_off = 0;
+    k.def_off = -1;
     k.acc_mode = ACC_NONE;
     if (o.flags & FSWEEP_F_GRAD) {
       if (kind_is_table(o.kind)) {
@@ -222,6 +223,18 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
       }
     if ((size_t)acc_per_lane * BLOCK * real_sz <= SMEM_ACC_BUDGET || big < 0) break;
     P.ops[big].acc_mode = ACC_GLOBAL;
+  }
+  // section cascades too large for shared memory: defer their coefficient gradient to fsweep_sos_defer_kernel
+  // (FSWEEP_DISABLE_DEFER=1, tests: keep the in-kernel global atomics)
+  P.def_stride = 0;
+  {
+    const char* no_defer = getenv("FSWEEP_DISABLE_DEFER");
+    if (!(no_defer && no_defer[0] == '1'))
+      for (int s = 0; s < P.n_ops; ++s)
+        if (P.ops[s].acc_mode == ACC_GLOBAL && (P.ops[s].kind == FSWEEP_OP_SOS || P.ops[s].kind == FSWEEP_OP_PSOS)) {
+          P.ops[s].def_off = P.def_stride;
+          P.def_stride += P.ops[s].n_in + P.ops[s].n_out;
+        }
   }
   for (int s = 0; s < P.n_ops; ++s) {
     if (P.ops[s].acc_mode == ACC_GLOBAL) p->any_global = true;
@@ -451,15 +464,24 @@ extern "C" const char* fsweep_plan_kernel_family(const fsweep_plan_t* plan, int6
   return backward ? "fsweep_bwd_kernel" : "fsweep_fwd_kernel";
 }
 
-extern "C" size_t fsweep_workspace_bytes(const fsweep_plan_t* plan, int64_t batch, int64_t cols, int64_t n_bins) {
-  (void)batch;
-  (void)cols;
-  if (!plan) return 0;
+namespace {
+// [per-block partial sums][flat global accumulator][pad][loss partials] — then the deferral buffer
+size_t ws_base_bytes(const fsweep_plan* plan, int64_t n_bins) {
   const size_t rs = plan->dtype == FSWEEP_C64 ? 4 : 8;
   const size_t grid = (size_t)grid_cap(n_bins, plan->G);
   size_t partial = grid * (size_t)plan->prog.acc_per_lane * plan->G * rs;
   size_t gacc = (size_t)plan->prog.acc_total * rs;
   return ((partial + 255) / 256) * 256 + ((gacc + 255) / 256) * 256 + 256 + LOSS_PARTIAL_BYTES;
+}
+size_t ws_defer_bytes(const fsweep_plan* plan, int64_t batch, int64_t cols, int64_t n_bins) {
+  const size_t rs = plan->dtype == FSWEEP_C64 ? 4 : 8;
+  return (size_t)plan->prog.def_stride * (size_t)(batch * cols) * (size_t)n_bins * 2 * rs;
+}
+}  // namespace
+
+extern "C" size_t fsweep_workspace_bytes(const fsweep_plan_t* plan, int64_t batch, int64_t cols, int64_t n_bins) {
+  if (!plan) return 0;
+  return ws_base_bytes(plan, n_bins) + ws_defer_bytes(plan, batch, cols, n_bins);
 }
 
 namespace {
@@ -471,7 +493,7 @@ int setup_criterion(const fsweep_plan* plan, const fsweep_criterion_t* crit, int
   if (crit->kind != FSWEEP_CRIT_MSE && crit->kind != FSWEEP_CRIT_MSE_CHSUM)
     return fail(FSWEEP_E_BADARG, "bad criterion kind %d", crit->kind);
   if (!crit->target || !crit->loss) return fail(FSWEEP_E_BADARG, "criterion: null target / loss");
-  const size_t need = fsweep_workspace_bytes(plan, 1, 1, n_bins);
+  const size_t need = ws_base_bytes(plan, n_bins);
   if (!workspace || workspace_bytes < need)
     return fail(FSWEEP_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
   *epi = crit->kind == FSWEEP_CRIT_MSE ? EPI_ABS_MSE : EPI_ABSSUM_MSE;
@@ -615,7 +637,10 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   if (r) return r;
   if (!grad_y && !crit) return fail(FSWEEP_E_BADARG, "null grad_y");
   if (n_bins == 0) return fail(FSWEEP_E_BADARG, "empty bin range in backward");
-  const size_t need = fsweep_workspace_bytes(plan, batch, cols, n_bins);
+  bool any_deferred = false;
+  for (int s = 0; s < plan->n_coeffs; ++s)
+    if (plan->prog.ops[s].def_off >= 0 && grad_coeffs && grad_coeffs[s]) any_deferred = true;
+  const size_t need = ws_base_bytes(plan, n_bins) + (any_deferred ? ws_defer_bytes(plan, batch, cols, n_bins) : 0);
   if (need > 256 + LOSS_PARTIAL_BYTES && (!workspace || workspace_bytes < need))
     return fail(FSWEEP_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
@@ -631,6 +656,7 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
       if (!gp) P.ops[s].acc_mode = ACC_NONE;
     } else if (P.ops[s].acc_mode != ACC_NONE) {
       if (gp) any_acc_wanted = true;
+      if (!gp) P.ops[s].def_off = -1;  // nobody wants this gradient: nothing to park either
     }
   }
   if (grad_x && plan->first_pre_rstep >= 0) P.rsteps[plan->first_pre_rstep].flags |= RS_NEED_GIN;
@@ -665,6 +691,7 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   A.epilogue = epilogue;
   A.partial = partial;
   A.gacc = gacc;
+  A.defer = any_deferred ? ws + ws_base_bytes(plan, n_bins) : nullptr;
   if (crit && (r = setup_criterion(plan, crit, n_bins, workspace, workspace_bytes, A, &A.epilogue))) return r;
 
   int launches = 0;
@@ -690,6 +717,38 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   }
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "backward launch: %s", cudaGetErrorString(e));
   ++launches;
+
+  if (any_deferred) {
+    // absolute bins k with 4k <= nfft use Taylor block 0
+    const int64_t k_last_plus = P.nfft / 4;
+    const int64_t n_plus = std::max<int64_t>(0, std::min<int64_t>(n_bins, k_last_plus - bin_begin + 1));
+    for (int s = 0; s < P.n_ops; ++s) {
+      if (P.ops[s].def_off < 0) continue;
+      DeferArgs D;
+      memset(&D, 0, sizeof(D));
+      D.defer = A.defer;
+      D.gacc = gacc;
+      D.n_bins = n_bins;
+      D.bin_begin = bin_begin;
+      D.n_plus = n_plus;
+      D.ncols_total = (int)(batch * cols);
+      D.opi = s;
+      const int pairs = P.ops[s].kind == FSWEEP_OP_PSOS ? P.ops[s].n_out : P.ops[s].n_out * P.ops[s].n_in;
+      if (dtype == FSWEEP_C64) {
+        const int ch = DEF_BLOCK * DeferCfg<float>::BPT;
+        D.chunks_plus = (int)((n_plus + ch - 1) / ch);
+        const int chunks = D.chunks_plus + (int)((n_bins - n_plus + ch - 1) / ch);
+        fsweep_sos_defer_kernel<float><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(P, D);
+      } else {
+        const int ch = DEF_BLOCK * DeferCfg<double>::BPT;
+        D.chunks_plus = (int)((n_plus + ch - 1) / ch);
+        const int chunks = D.chunks_plus + (int)((n_bins - n_plus + ch - 1) / ch);
+        fsweep_sos_defer_kernel<double><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(P, D);
+      }
+      if ((e = cudaGetLastError()) != cudaSuccess) return fail(FSWEEP_E_CUDA, "deferred gradient launch: %s", cudaGetErrorString(e));
+      ++launches;
+    }
+  }
 
   if (any_acc_wanted) {
     FinalizeArgs F;

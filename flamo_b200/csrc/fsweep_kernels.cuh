@@ -61,6 +61,9 @@ struct OpK {
   int row_len;  // accumulators per row (per lane)
   int acc_off;  // offset of this op in the flat accumulator / partial buffers (row-major [row][row_len])
   int h_off;    // offset (complex elements per thread) of this op's response row in the per-thread cache
+  int def_off;  // >= 0: DEFERRED gradient — the backward kernel only records this op's input state and output
+                // gradient per bin (offset, in complex elements, inside one record of the deferral buffer) and
+                // fsweep_sos_defer_kernel forms the coefficient gradient afterwards; -1 otherwise
   const void* coef;
   void* gtab;  // ACC_TABLE: gradient table
 };
@@ -95,6 +98,7 @@ struct ProgK {
   int n_fsteps, n_msteps, n_bsteps, n_rsteps;
   int h_total;     // complex elements per thread in the response cache
   int needs_ctx;   // some op is a section cascade: the Taylor context (v, v^2) is needed
+  int def_stride;  // complex elements per (column, bin) record of the deferral buffer (0: nothing deferred)
   long long nfft;
   double lng;   // ln(gamma)
   double inv_nfft;
@@ -170,6 +174,19 @@ __device__ __forceinline__ cx<T> crcp_exact(cx<T> a) {  // correctly rounded rec
 template <typename T>
 __device__ __forceinline__ bool czero(cx<T> a) {
   return a.x == T(0) && a.y == T(0);
+}
+
+__device__ __forceinline__ cx<float> ld_cx(const cx<float>* p) {
+  float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return mk<float>(v.x, v.y);
+}
+__device__ __forceinline__ cx<double> ld_cx(const cx<double>* p) {
+  double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return mk<double>(v.x, v.y);
+}
+__device__ __forceinline__ void st_cx(cx<float>* p, cx<float> v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+__device__ __forceinline__ void st_cx(cx<double>* p, cx<double> v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
 }
 
 // ---- group exchange.  G <= 32: warp shuffles.  G == 64: the group is two warps of the same CTA (threads
@@ -443,6 +460,10 @@ struct Acc {
   T* gacc;   // global flat accumulator (ACC_GLOBAL ops)
   int tid;
   bool valid;  // this group holds a real bin
+  // deferred gradients: record (q, bin) at defer[((q * n_bins + bl) * def_stride) ...]
+  cx<T>* defer;
+  long long bl, n_bins;
+  int q0, ncols_total, def_stride;
   __device__ __forceinline__ void add(const OpK& op, int row, int e, T v) const {
     if (!valid) return;
     if (op.acc_mode == ACC_SMEM) {
@@ -607,8 +628,24 @@ template <typename T, int G, int NC>
 __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, int lane, const cx<T> (&Sin)[NC],
                                             cx<T> (&g)[NC], bool need_gin, const Acc<T>& acc, bool first_chunk,
                                             const cx<T>* hc, unsigned gmask, int tid) {
-  const bool want = op.acc_mode != ACC_NONE;
+  bool want = op.acc_mode != ACC_NONE;
   const cx<T>* hrow = hc + (size_t)op.h_off * BLOCK + tid;
+  if (want && op.def_off >= 0) {
+    // deferred: lane r parks S_in[r] and g_out[r] of every live column; the per-section gradient work happens
+    // in fsweep_sos_defer_kernel, parallel over (channel pair, bin) instead of serial per lane
+    if (acc.valid) {
+      static_for<0, NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const int q = acc.q0 + c;
+        if (q < acc.ncols_total) {
+          cx<T>* rec = acc.defer + ((size_t)q * acc.n_bins + acc.bl) * acc.def_stride + op.def_off;
+          if (lane < op.n_in) st_cx(rec + lane, Sin[c]);
+          if (lane < op.n_out) st_cx(rec + op.n_in + lane, g[c]);
+        }
+      });
+    }
+    want = false;
+  }
   if (is_dense(op.kind)) {
     if (want) {
       for (int n = 0; n < op.n_in; ++n) {
@@ -912,6 +949,7 @@ struct SweepArgs {
   int epilogue;
   void* partial;  // backward: [grid][acc_per_lane * G]
   void* gacc;     // backward: [acc_total] (ACC_GLOBAL ops), zeroed by the host wrapper
+  void* defer;    // backward: deferral buffer [batch*cols][n_bins][def_stride] cplx (ops with def_off >= 0)
   // fused criterion (epilogue EPI_ABS_MSE / EPI_ABSSUM_MSE, cols == 1): y / gy are unused, dL/d|Y| is formed in
   // the kernel from the target and the squared errors are summed per block
   const void* tgt;       // real (batch, n_bins, out_ch) or (batch, n_bins); first processed bin
@@ -956,19 +994,6 @@ __device__ __forceinline__ void block_loss_store(double lacc, double* loss_parti
     for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) s += red[w];
     loss_partial[blockIdx.x] = s;
   }
-}
-
-__device__ __forceinline__ cx<float> ld_cx(const cx<float>* p) {
-  float2 v = __ldg(reinterpret_cast<const float2*>(p));
-  return mk<float>(v.x, v.y);
-}
-__device__ __forceinline__ cx<double> ld_cx(const cx<double>* p) {
-  double2 v = __ldg(reinterpret_cast<const double2*>(p));
-  return mk<double>(v.x, v.y);
-}
-__device__ __forceinline__ void st_cx(cx<float>* p, cx<float> v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
-__device__ __forceinline__ void st_cx(cx<double>* p, cx<double> v) {
-  *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
 }
 
 template <typename T, int G, int CC>
@@ -1074,6 +1099,10 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
   acc.sacc = sacc;
   acc.gacc = reinterpret_cast<T*>(A.gacc);
   acc.tid = tid;
+  acc.defer = reinterpret_cast<cx<T>*>(A.defer);
+  acc.n_bins = A.n_bins;
+  acc.ncols_total = ncols_total;
+  acc.def_stride = P.def_stride;
 
   auto put = [&](int slot, const cx<T>(&S)[CC]) {
 #pragma unroll
@@ -1093,6 +1122,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
     const bool valid = bl < A.n_bins;
     if (!valid) bl = A.n_bins - 1;
     acc.valid = valid;
+    acc.bl = bl;
     const Ctx<T> ctx = make_ctx<T>(P, A.bin_begin + bl);
     stage_ops<T>(P, ctx, lane, hc, gmask, tid, false);
     LU<T, G> lu;
@@ -1100,6 +1130,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
 
     for (int q0 = 0; q0 < ncols_total; q0 += CC) {
       const bool first_chunk = q0 == 0;
+      acc.q0 = q0;
       cx<T> S[CC];
       load_cols<T, G, CC>(x, A.xbs, bl, P.in_ch, A.cols, q0, ncols_total, lane, S);
       int slot = 0;
@@ -1254,6 +1285,149 @@ __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_const
       reinterpret_cast<double*>(op.grad)[o] = s;
     else
       reinterpret_cast<T*>(op.grad)[o] = (T)s;
+  }
+}
+
+// ------------------------------------------------------------------------------------ deferred SOS gradients
+// Coefficient gradient of a section-cascade op whose accumulators do not fit shared memory (e.g. the 16 x 16 x 30
+// sections of BASELINE config 3: 122 880 accumulators).  The backward kernel parked S_in and g_out per (column,
+// bin); here ONE BLOCK OWNS ONE CHANNEL PAIR (m, n) and its threads own bins, so the per-section gradient sums stay
+// in registers across bins and leave the block as one reduced atomicAdd per coefficient and chunk (the in-kernel
+// path did six global atomics per section, pair and bin: 4.4e9 for config 3).
+//   gh = sum_q g_out[m] conj(S_in[n]);  dL/dB_s = Re(gh conj(H / B_s) ...) as in sos_grad above.
+// Bins of one block lie in one half of the spectrum (one Taylor block); a bin whose rounded cos(w) disagrees with
+// the geometric split (at most the boundary bin) takes the slow atomic path.
+template <typename T>
+struct DeferCfg {
+  static constexpr int BPT = sizeof(T) == 4 ? 8 : 4;  // bins per thread
+  static constexpr int KC = sizeof(T) == 4 ? 10 : 5;  // sections per register chunk
+};
+constexpr int DEF_BLOCK = 128;
+
+struct DeferArgs {
+  const void* defer;
+  void* gacc;
+  long long n_bins, bin_begin, n_plus;  // n_plus: processed bins [0, n_plus) have 4k <= nfft
+  int ncols_total, chunks_plus, opi;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_defer_kernel(const __grid_constant__ ProgK P, const DeferArgs D) {
+  constexpr int BPT = DeferCfg<T>::BPT, KC = DeferCfg<T>::KC;
+  constexpr int CH = DEF_BLOCK * BPT;
+  __shared__ T red[DEF_BLOCK / 32][KC * 6];
+  const OpK& op = P.ops[D.opi];
+  const bool par = op.kind == FSWEEP_OP_PSOS;
+  const int pair = blockIdx.x;
+  const int m = par ? pair : pair / op.n_in, n = par ? pair : pair - m * op.n_in;
+  const bool plus = (int)blockIdx.y < D.chunks_plus;
+  const long long base = plus ? (long long)blockIdx.y * CH : D.n_plus + (long long)((int)blockIdx.y - D.chunks_plus) * CH;
+  const long long lim = plus ? D.n_plus : D.n_bins;
+  const int tid = threadIdx.x;
+  const int K = op.K;
+  const T* coef = reinterpret_cast<const T*>(op.coef) + (par ? (size_t)n * 16 : ((size_t)n * op.n_out + m) * 16);
+  const long stride = par ? (long)op.n_out * 16 : (long)op.n_in * op.n_out * 16;
+  const int sec_stride = op.row_len / K;  // accumulator slots per section in this op's row
+  T* gdst = reinterpret_cast<T*>(D.gacc) + op.acc_off + (size_t)m * op.row_len + (par ? 0 : n * 16);
+  const cx<T>* defer = reinterpret_cast<const cx<T>*>(D.defer);
+
+  cx<T> H[BPT], gh[BPT], u1[BPT], u2[BPT];
+  int state[BPT];  // 0: nothing to do, 1: fast path (bin in this block's half), 2: slow path
+#pragma unroll
+  for (int i = 0; i < BPT; ++i) {
+    const long long bl = base + (long long)i * DEF_BLOCK + tid;
+    state[i] = 0;
+    H[i] = gh[i] = u1[i] = u2[i] = mk<T>(0, 0);
+    if (bl < lim) {
+      const Ctx<T> ctx = make_ctx<T>(P, D.bin_begin + bl);
+      bool guarded;
+      H[i] = sos_eval<T>(coef, K, stride, ctx, guarded);
+      u1[i] = ctx.u1;
+      u2[i] = ctx.u2;
+      cx<T> acc = mk<T>(0, 0);
+      for (int q = 0; q < D.ncols_total; ++q) {
+        const cx<T>* rec = defer + ((size_t)q * D.n_bins + bl) * P.def_stride + op.def_off;
+        cfmac(acc, ld_cx(rec + op.n_in + m), ld_cx(rec + n));  // g_out[m] conj(S_in[n])
+      }
+      gh[i] = acc;
+      state[i] = guarded ? 0 : (ctx.plus == plus ? 1 : 2);
+    }
+  }
+
+  for (int c0 = 0; c0 < K; c0 += KC) {
+    T a[KC][6];
+#pragma unroll
+    for (int j = 0; j < KC; ++j)
+#pragma unroll
+      for (int e = 0; e < 6; ++e) a[j][e] = T(0);
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+      if (state[i] == 0) continue;
+      const bool bplus = state[i] == 1 ? plus : !plus;
+      const T* p = coef + (size_t)c0 * stride + (bplus ? 0 : 8);
+#pragma unroll
+      for (int j = 0; j < KC; ++j) {
+        if (c0 + j < K) {
+          T c[8];
+          load8<T>(p + (size_t)j * stride, c);
+          Ctx<T> cx_;
+          cx_.u1 = u1[i];
+          cx_.u2 = u2[i];
+          cx<T> Bv, Av;
+          section_eval<T>(c, cx_, Bv, Av);
+          cx<T> qb;
+          if (czero(Bv)) {
+            Ctx<T> full = make_ctx<T>(P, D.bin_begin + base + (long long)i * DEF_BLOCK + tid);
+            qb = cmul(sos_eval_without<T>(coef, K, stride, full, c0 + j), crcp_exact(Av));
+          } else {
+            qb = cmul(H[i], crcp_exact(Bv));
+          }
+          cx<T> qa = cmul(H[i], crcp_exact(Av));
+          qa.x = -qa.x;
+          qa.y = -qa.y;
+          const cx<T> rb = cmulc(gh[i], qb), ra = cmulc(gh[i], qa);
+          const T v0 = rb.x, v1 = rb.x * u1[i].x + rb.y * u1[i].y, v2 = rb.x * u2[i].x + rb.y * u2[i].y;
+          const T v4 = ra.x, v5 = ra.x * u1[i].x + ra.y * u1[i].y, v6 = ra.x * u2[i].x + ra.y * u2[i].y;
+          if (state[i] == 1) {
+            a[j][0] += v0;
+            a[j][1] += v1;
+            a[j][2] += v2;
+            a[j][3] += v4;
+            a[j][4] += v5;
+            a[j][5] += v6;
+          } else {  // the boundary bin: straight to the other Taylor block
+            T* g = gdst + (size_t)(c0 + j) * sec_stride + (bplus ? 0 : 8);
+            atomicAdd(g + 0, v0);
+            atomicAdd(g + 1, v1);
+            atomicAdd(g + 2, v2);
+            atomicAdd(g + 4, v4);
+            atomicAdd(g + 5, v5);
+            atomicAdd(g + 6, v6);
+          }
+        }
+      }
+    }
+    // block reduction of the chunk: warp shuffles, then one atomicAdd per coefficient
+#pragma unroll
+    for (int j = 0; j < KC; ++j)
+#pragma unroll
+      for (int e = 0; e < 6; ++e) {
+        T v = a[j][e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if ((tid & 31) == 0) red[tid >> 5][j * 6 + e] = v;
+      }
+    __syncthreads();
+    if (tid < KC * 6) {
+      const int j = tid / 6, e = tid - j * 6;
+      if (c0 + j < K) {
+        T v = T(0);
+#pragma unroll
+        for (int w = 0; w < DEF_BLOCK / 32; ++w) v += red[w][tid];
+        atomicAdd(gdst + (size_t)(c0 + j) * sec_stride + (plus ? 0 : 8) + (e < 3 ? e : e + 1), v);
+      }
+    }
+    __syncthreads();
   }
 }
 

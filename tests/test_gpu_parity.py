@@ -131,3 +131,41 @@ def test_alternative_kernel_paths_on_fdn_cases(name, dtype, path, monkeypatch):
         assert run_case.mag_err <= 1e-4 and all(e <= 1e-3 for e in gerrs.values())
     else:
         assert ferr <= 1e-9 and all(e <= 1e-6 for e in gerrs.values())
+
+
+@pytest.mark.parametrize("name", ["cfg3_geq16_small", "geq_oct3", "pgeq_oct1", "cfg4_active_full"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_deferred_sos_gradients_match_in_kernel_atomics(name, dtype, monkeypatch):
+    """Section cascades whose accumulators exceed shared memory get their coefficient gradient from
+    fsweep_sos_defer_kernel (one block per channel pair, registers across bins).  It must reproduce the in-kernel
+    global-atomic path (FSWEEP_DISABLE_DEFER=1) — on the whole spectrum, on bin shards that straddle the
+    cos(w) = 0 boundary between the two Taylor blocks, and with several batch items."""
+    def grads(disable, shard=None, B=None):
+        if disable:
+            monkeypatch.setenv("FSWEEP_DISABLE_DEFER", "1")
+        else:
+            monkeypatch.delenv("FSWEEP_DISABLE_DEFER", raising=False)
+        saved = dict(sweep._PLANS)
+        sweep._PLANS.clear()
+        try:
+            case, g, model = build_case(name, dtype, "cuda")
+            M = case["nfft"] // 2 + 1
+            cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
+            X = C.make_input(B or case["B"], M, model.input_channels, None).to(cdt).cuda()
+            ps = [p for p in model.parameters() if p.requires_grad]
+            if shard is None:
+                out = torch.autograd.grad(C.golden_loss(model(X)), ps)
+            else:
+                with sweep.bin_shard(*shard):
+                    out = torch.autograd.grad(C.golden_loss(model(X)), ps)
+            return [t.cpu().numpy() for t in out]
+        finally:
+            sweep._PLANS.clear()
+            sweep._PLANS.update(saved)
+
+    M = C.CASES[name]["nfft"] // 2 + 1
+    tol = 2e-4 if dtype == torch.float32 else 1e-10
+    for shard, B in ((None, None), ((M // 4 - 37, M // 2 + 501), 3), ((M // 2 + 3, M), None)):
+        a, b = grads(False, shard, B), grads(True, shard, B)
+        for u, v in zip(a, b):
+            assert grad_err(u, v) <= tol, (shard, B)
