@@ -231,7 +231,8 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
     const char* no_defer = getenv("FSWEEP_DISABLE_DEFER");
     if (!(no_defer && no_defer[0] == '1'))
       for (int s = 0; s < P.n_ops; ++s)
-        if (P.ops[s].acc_mode == ACC_GLOBAL && (P.ops[s].kind == FSWEEP_OP_SOS || P.ops[s].kind == FSWEEP_OP_PSOS)) {
+        if (P.ops[s].acc_mode == ACC_GLOBAL && (P.ops[s].kind == FSWEEP_OP_SOS || P.ops[s].kind == FSWEEP_OP_PSOS) &&
+            P.ops[s].K <= DEF_MAX_K) {
           P.ops[s].def_off = P.def_stride;
           P.def_stride += P.ops[s].n_in + P.ops[s].n_out;
         }
@@ -734,17 +735,13 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
       D.ncols_total = (int)(batch * cols);
       D.opi = s;
       const int pairs = P.ops[s].kind == FSWEEP_OP_PSOS ? P.ops[s].n_out : P.ops[s].n_out * P.ops[s].n_in;
-      if (dtype == FSWEEP_C64) {
-        const int ch = DEF_BLOCK * DeferCfg<float>::BPT;
-        D.chunks_plus = (int)((n_plus + ch - 1) / ch);
-        const int chunks = D.chunks_plus + (int)((n_bins - n_plus + ch - 1) / ch);
+      const int ch = DEF_BLOCK * DEF_TILES;
+      D.chunks_plus = (int)((n_plus + ch - 1) / ch);
+      const int chunks = D.chunks_plus + (int)((n_bins - n_plus + ch - 1) / ch);
+      if (dtype == FSWEEP_C64)
         fsweep_sos_defer_kernel<float><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(P, D);
-      } else {
-        const int ch = DEF_BLOCK * DeferCfg<double>::BPT;
-        D.chunks_plus = (int)((n_plus + ch - 1) / ch);
-        const int chunks = D.chunks_plus + (int)((n_bins - n_plus + ch - 1) / ch);
+      else
         fsweep_sos_defer_kernel<double><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(P, D);
-      }
       if ((e = cudaGetLastError()) != cudaSuccess) return fail(FSWEEP_E_CUDA, "deferred gradient launch: %s", cudaGetErrorString(e));
       ++launches;
     }

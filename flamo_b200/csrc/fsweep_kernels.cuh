@@ -1291,18 +1291,19 @@ __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_const
 // ------------------------------------------------------------------------------------ deferred SOS gradients
 // Coefficient gradient of a section-cascade op whose accumulators do not fit shared memory (e.g. the 16 x 16 x 30
 // sections of BASELINE config 3: 122 880 accumulators).  The backward kernel parked S_in and g_out per (column,
-// bin); here ONE BLOCK OWNS ONE CHANNEL PAIR (m, n) and its threads own bins, so the per-section gradient sums stay
-// in registers across bins and leave the block as one reduced atomicAdd per coefficient and chunk (the in-kernel
-// path did six global atomics per section, pair and bin: 4.4e9 for config 3).
-//   gh = sum_q g_out[m] conj(S_in[n]);  dL/dB_s = Re(gh conj(H / B_s) ...) as in sos_grad above.
+// bin); here ONE BLOCK OWNS ONE CHANNEL PAIR (m, n) and a range of bins, and works tile by tile (128 bins):
+//   phase 1  thread t evaluates the whole cascade H of bin t and gh = sum_q g_out[m] conj(S_in[n]), and leaves
+//            (H, gh, v, v^2) of its bin in shared memory;
+//   phase 2  thread t = (section s, bin lane l) keeps the six coefficients of ITS section in registers, walks the
+//            tile's bins l, l + TS, ... and adds dL/d{B(w0), B'(w0), b2, A(w0), A'(w0), a2} into six registers.
+// The sums stay in registers across all tiles of the block and leave it as one atomicAdd per coefficient (the
+// in-kernel path did six global atomics per section, pair and bin: 4.4e9 for config 3).  Small loop bodies: the
+// first version of this kernel unrolled bins x sections into 0.8 MB of SASS and ran at instruction-fetch speed.
 // Bins of one block lie in one half of the spectrum (one Taylor block); a bin whose rounded cos(w) disagrees with
-// the geometric split (at most the boundary bin) takes the slow atomic path.
-template <typename T>
-struct DeferCfg {
-  static constexpr int BPT = sizeof(T) == 4 ? 8 : 4;  // bins per thread
-  static constexpr int KC = sizeof(T) == 4 ? 10 : 5;  // sections per register chunk
-};
+// the geometric split (at most the boundary bin) takes a slow atomic path.
 constexpr int DEF_BLOCK = 128;
+constexpr int DEF_TILES = 8;       // tiles of DEF_BLOCK bins per block
+constexpr int DEF_MAX_K = DEF_BLOCK;  // one thread per section at least
 
 struct DeferArgs {
   const void* defer;
@@ -1313,9 +1314,9 @@ struct DeferArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_defer_kernel(const __grid_constant__ ProgK P, const DeferArgs D) {
-  constexpr int BPT = DeferCfg<T>::BPT, KC = DeferCfg<T>::KC;
-  constexpr int CH = DEF_BLOCK * BPT;
-  __shared__ T red[DEF_BLOCK / 32][KC * 6];
+  constexpr int CH = DEF_BLOCK * DEF_TILES;
+  __shared__ T sH[2][DEF_BLOCK], sG[2][DEF_BLOCK], sU1[2][DEF_BLOCK], sU2[2][DEF_BLOCK];
+  __shared__ int sState[DEF_BLOCK];
   const OpK& op = P.ops[D.opi];
   const bool par = op.kind == FSWEEP_OP_PSOS;
   const int pair = blockIdx.x;
@@ -1331,103 +1332,103 @@ __global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_defer_kernel(const __gri
   T* gdst = reinterpret_cast<T*>(D.gacc) + op.acc_off + (size_t)m * op.row_len + (par ? 0 : n * 16);
   const cx<T>* defer = reinterpret_cast<const cx<T>*>(D.defer);
 
-  cx<T> H[BPT], gh[BPT], u1[BPT], u2[BPT];
-  int state[BPT];  // 0: nothing to do, 1: fast path (bin in this block's half), 2: slow path
+  // phase-2 role: section s, bin lane l of TS
+  const int TS = DEF_BLOCK / K;
+  const int s = tid / TS, l = tid - s * TS;
+  const bool worker = s < K;
+  T c[8];
 #pragma unroll
-  for (int i = 0; i < BPT; ++i) {
-    const long long bl = base + (long long)i * DEF_BLOCK + tid;
-    state[i] = 0;
-    H[i] = gh[i] = u1[i] = u2[i] = mk<T>(0, 0);
+  for (int i = 0; i < 8; ++i) c[i] = T(0);
+  if (worker) load8<T>(coef + (size_t)s * stride + (plus ? 0 : 8), c);
+  T a0 = T(0), a1 = T(0), a2 = T(0), a4 = T(0), a5 = T(0), a6 = T(0);
+
+  for (int tile = 0; tile < DEF_TILES; ++tile) {
+    const long long bl = base + (long long)tile * DEF_BLOCK + tid;
+    if (base + (long long)tile * DEF_BLOCK >= lim) break;  // uniform
+    // ---- phase 1: this thread's bin
+    int st = 0;
+    cx<T> H = mk<T>(0, 0), gh = mk<T>(0, 0), u1 = mk<T>(0, 0), u2 = mk<T>(0, 0);
     if (bl < lim) {
       const Ctx<T> ctx = make_ctx<T>(P, D.bin_begin + bl);
       bool guarded;
-      H[i] = sos_eval<T>(coef, K, stride, ctx, guarded);
-      u1[i] = ctx.u1;
-      u2[i] = ctx.u2;
-      cx<T> acc = mk<T>(0, 0);
+      H = sos_eval<T>(coef, K, stride, ctx, guarded);
+      u1 = ctx.u1;
+      u2 = ctx.u2;
       for (int q = 0; q < D.ncols_total; ++q) {
         const cx<T>* rec = defer + ((size_t)q * D.n_bins + bl) * P.def_stride + op.def_off;
-        cfmac(acc, ld_cx(rec + op.n_in + m), ld_cx(rec + n));  // g_out[m] conj(S_in[n])
+        cfmac(gh, ld_cx(rec + op.n_in + m), ld_cx(rec + n));  // g_out[m] conj(S_in[n])
       }
-      gh[i] = acc;
-      state[i] = guarded ? 0 : (ctx.plus == plus ? 1 : 2);
+      st = guarded ? 0 : (ctx.plus == plus ? 1 : 2);
     }
-  }
-
-  for (int c0 = 0; c0 < K; c0 += KC) {
-    T a[KC][6];
-#pragma unroll
-    for (int j = 0; j < KC; ++j)
-#pragma unroll
-      for (int e = 0; e < 6; ++e) a[j][e] = T(0);
-#pragma unroll
-    for (int i = 0; i < BPT; ++i) {
-      if (state[i] == 0) continue;
-      const bool bplus = state[i] == 1 ? plus : !plus;
-      const T* p = coef + (size_t)c0 * stride + (bplus ? 0 : 8);
-#pragma unroll
-      for (int j = 0; j < KC; ++j) {
-        if (c0 + j < K) {
-          T c[8];
-          load8<T>(p + (size_t)j * stride, c);
-          Ctx<T> cx_;
-          cx_.u1 = u1[i];
-          cx_.u2 = u2[i];
-          cx<T> Bv, Av;
-          section_eval<T>(c, cx_, Bv, Av);
-          cx<T> qb;
-          if (czero(Bv)) {
-            Ctx<T> full = make_ctx<T>(P, D.bin_begin + base + (long long)i * DEF_BLOCK + tid);
-            qb = cmul(sos_eval_without<T>(coef, K, stride, full, c0 + j), crcp_exact(Av));
-          } else {
-            qb = cmul(H[i], crcp_exact(Bv));
-          }
-          cx<T> qa = cmul(H[i], crcp_exact(Av));
-          qa.x = -qa.x;
-          qa.y = -qa.y;
-          const cx<T> rb = cmulc(gh[i], qb), ra = cmulc(gh[i], qa);
-          const T v0 = rb.x, v1 = rb.x * u1[i].x + rb.y * u1[i].y, v2 = rb.x * u2[i].x + rb.y * u2[i].y;
-          const T v4 = ra.x, v5 = ra.x * u1[i].x + ra.y * u1[i].y, v6 = ra.x * u2[i].x + ra.y * u2[i].y;
-          if (state[i] == 1) {
-            a[j][0] += v0;
-            a[j][1] += v1;
-            a[j][2] += v2;
-            a[j][3] += v4;
-            a[j][4] += v5;
-            a[j][5] += v6;
-          } else {  // the boundary bin: straight to the other Taylor block
-            T* g = gdst + (size_t)(c0 + j) * sec_stride + (bplus ? 0 : 8);
-            atomicAdd(g + 0, v0);
-            atomicAdd(g + 1, v1);
-            atomicAdd(g + 2, v2);
-            atomicAdd(g + 4, v4);
-            atomicAdd(g + 5, v5);
-            atomicAdd(g + 6, v6);
-          }
+    if (st == 2) {
+      // the boundary bin (rounded cos(w) on the other side of the split): its own thread, straight atomics
+      const Ctx<T> ctx = make_ctx<T>(P, D.bin_begin + bl);
+      const T* p = coef + (ctx.plus ? 0 : 8);
+      for (int ss = 0; ss < K; ++ss) {
+        T cc[8];
+        load8<T>(p + (size_t)ss * stride, cc);
+        cx<T> Bv, Av;
+        section_eval<T>(cc, ctx, Bv, Av);
+        const cx<T> qb = czero(Bv) ? cmul(sos_eval_without<T>(coef, K, stride, ctx, ss), crcp_exact(Av)) : cmul(H, crcp_exact(Bv));
+        cx<T> qa = cmul(H, crcp_exact(Av));
+        const cx<T> rb = cmulc(gh, qb), ra = cmulc(gh, mk<T>(-qa.x, -qa.y));
+        T* g = gdst + (size_t)ss * sec_stride + (ctx.plus ? 0 : 8);
+        atomicAdd(g + 0, rb.x);
+        atomicAdd(g + 1, rb.x * u1.x + rb.y * u1.y);
+        atomicAdd(g + 2, rb.x * u2.x + rb.y * u2.y);
+        atomicAdd(g + 4, ra.x);
+        atomicAdd(g + 5, ra.x * u1.x + ra.y * u1.y);
+        atomicAdd(g + 6, ra.x * u2.x + ra.y * u2.y);
+      }
+      st = 0;
+    }
+    sH[0][tid] = H.x;
+    sH[1][tid] = H.y;
+    sG[0][tid] = gh.x;
+    sG[1][tid] = gh.y;
+    sU1[0][tid] = u1.x;
+    sU1[1][tid] = u1.y;
+    sU2[0][tid] = u2.x;
+    sU2[1][tid] = u2.y;
+    sState[tid] = st;
+    __syncthreads();
+    // ---- phase 2: my section over the tile's bins
+    if (worker) {
+      for (int b = l; b < DEF_BLOCK; b += TS) {
+        if (sState[b] == 0) continue;
+        Ctx<T> cx_;
+        cx_.u1 = mk<T>(sU1[0][b], sU1[1][b]);
+        cx_.u2 = mk<T>(sU2[0][b], sU2[1][b]);
+        const cx<T> Hb = mk<T>(sH[0][b], sH[1][b]), gb = mk<T>(sG[0][b], sG[1][b]);
+        cx<T> Bv, Av;
+        section_eval<T>(c, cx_, Bv, Av);
+        cx<T> qb;
+        if (czero(Bv)) {  // rare: this numerator section vanishes at this bin (H itself is 0 there)
+          const Ctx<T> full = make_ctx<T>(P, D.bin_begin + base + (long long)tile * DEF_BLOCK + b);
+          qb = cmul(sos_eval_without<T>(coef, K, stride, full, s), crcp_exact(Av));
+        } else {
+          qb = cmul(Hb, crcp(Bv));
         }
-      }
-    }
-    // block reduction of the chunk: warp shuffles, then one atomicAdd per coefficient
-#pragma unroll
-    for (int j = 0; j < KC; ++j)
-#pragma unroll
-      for (int e = 0; e < 6; ++e) {
-        T v = a[j][e];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if ((tid & 31) == 0) red[tid >> 5][j * 6 + e] = v;
-      }
-    __syncthreads();
-    if (tid < KC * 6) {
-      const int j = tid / 6, e = tid - j * 6;
-      if (c0 + j < K) {
-        T v = T(0);
-#pragma unroll
-        for (int w = 0; w < DEF_BLOCK / 32; ++w) v += red[w][tid];
-        atomicAdd(gdst + (size_t)(c0 + j) * sec_stride + (plus ? 0 : 8) + (e < 3 ? e : e + 1), v);
+        const cx<T> qa = cmul(Hb, crcp(Av));
+        const cx<T> rb = cmulc(gb, qb), ra = cmulc(gb, mk<T>(-qa.x, -qa.y));
+        a0 += rb.x;
+        a1 = fma(rb.x, cx_.u1.x, fma(rb.y, cx_.u1.y, a1));
+        a2 = fma(rb.x, cx_.u2.x, fma(rb.y, cx_.u2.y, a2));
+        a4 += ra.x;
+        a5 = fma(ra.x, cx_.u1.x, fma(ra.y, cx_.u1.y, a5));
+        a6 = fma(ra.x, cx_.u2.x, fma(ra.y, cx_.u2.y, a6));
       }
     }
     __syncthreads();
+  }
+  if (worker) {
+    T* g = gdst + (size_t)s * sec_stride + (plus ? 0 : 8);
+    atomicAdd(g + 0, a0);
+    atomicAdd(g + 1, a1);
+    atomicAdd(g + 2, a2);
+    atomicAdd(g + 4, a4);
+    atomicAdd(g + 5, a5);
+    atomicAdd(g + 6, a6);
   }
 }
 
