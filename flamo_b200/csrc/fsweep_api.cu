@@ -474,9 +474,17 @@ size_t ws_base_bytes(const fsweep_plan* plan, int64_t n_bins) {
   size_t gacc = (size_t)plan->prog.acc_total * rs;
   return ((partial + 255) / 256) * 256 + ((gacc + 255) / 256) * 256 + 256 + LOSS_PARTIAL_BYTES;
 }
+// deferral records, then one response table per deferred op
 size_t ws_defer_bytes(const fsweep_plan* plan, int64_t batch, int64_t cols, int64_t n_bins) {
   const size_t rs = plan->dtype == FSWEEP_C64 ? 4 : 8;
-  return (size_t)plan->prog.def_stride * (size_t)(batch * cols) * (size_t)n_bins * 2 * rs;
+  size_t b = (((size_t)plan->prog.def_stride * (size_t)(batch * cols) * (size_t)n_bins * 2 * rs + 255) / 256) * 256;
+  for (int s = 0; s < plan->prog.n_ops; ++s) {
+    const OpK& o = plan->prog.ops[s];
+    if (o.def_off < 0) continue;
+    const size_t row = o.kind == FSWEEP_OP_PSOS ? (size_t)o.n_out : (size_t)o.n_out * o.n_in;
+    b += ((row * (size_t)n_bins * 2 * rs + 255) / 256) * 256;
+  }
+  return b;
 }
 }  // namespace
 
@@ -701,6 +709,40 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "memset: %s", cudaGetErrorString(e));
     ++launches;
   }
+  // deferred section cascades: build their response tables first (the sweep kernel reads them as TABLE ops)
+  ProgK Pdef = P;  // the program as the table / gradient kernels see it: original op kinds + table pointers
+  if (any_deferred) {
+    char* tabp = ws + ws_base_bytes(plan, n_bins) +
+                 (((size_t)P.def_stride * (size_t)(batch * cols) * (size_t)n_bins * 2 * rs + 255) / 256) * 256;
+    for (int s = 0; s < P.n_ops; ++s) {
+      if (plan->prog.ops[s].def_off < 0) continue;
+      const bool par = P.ops[s].kind == FSWEEP_OP_PSOS;
+      const size_t row = par ? (size_t)P.ops[s].n_out : (size_t)P.ops[s].n_out * P.ops[s].n_in;
+      const size_t bytes = ((row * (size_t)n_bins * 2 * rs + 255) / 256) * 256;
+      if (P.ops[s].def_off >= 0) {
+        // table indexed by absolute bin: shift the base by -bin_begin rows (never dereferenced below bin_begin)
+        char* tbase = tabp - (size_t)bin_begin * row * 2 * rs;
+        Pdef.ops[s].gtab = tbase;
+        DeferArgs D;
+        memset(&D, 0, sizeof(D));
+        D.n_bins = n_bins;
+        D.bin_begin = bin_begin;
+        D.opi = s;
+        const int pairs = (int)row;
+        const int chunks = (int)((n_bins + DEF_BLOCK * DEF_TILES - 1) / (DEF_BLOCK * DEF_TILES));
+        if (plan->dtype == FSWEEP_C64)
+          fsweep_sos_table_kernel<float><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(Pdef, D);
+        else
+          fsweep_sos_table_kernel<double><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(Pdef, D);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) return fail(FSWEEP_E_CUDA, "response table launch: %s", cudaGetErrorString(e2));
+        ++launches;
+        P.ops[s].kind = par ? FSWEEP_OP_PTABLE : FSWEEP_OP_TABLE;
+        P.ops[s].coef = tbase;
+      }
+      tabp += bytes;
+    }
+  }
   const int dtype = plan->dtype;
   if (use_tpc(plan, n_bins)) {
     cfg.grid = tpc_grid(n_bins);
@@ -723,8 +765,8 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     // absolute bins k with 4k <= nfft use Taylor block 0
     const int64_t k_last_plus = P.nfft / 4;
     const int64_t n_plus = std::max<int64_t>(0, std::min<int64_t>(n_bins, k_last_plus - bin_begin + 1));
-    for (int s = 0; s < P.n_ops; ++s) {
-      if (P.ops[s].def_off < 0) continue;
+    for (int s = 0; s < Pdef.n_ops; ++s) {
+      if (Pdef.ops[s].def_off < 0) continue;
       DeferArgs D;
       memset(&D, 0, sizeof(D));
       D.defer = A.defer;
@@ -734,14 +776,14 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
       D.n_plus = n_plus;
       D.ncols_total = (int)(batch * cols);
       D.opi = s;
-      const int pairs = P.ops[s].kind == FSWEEP_OP_PSOS ? P.ops[s].n_out : P.ops[s].n_out * P.ops[s].n_in;
+      const int pairs = Pdef.ops[s].kind == FSWEEP_OP_PSOS ? Pdef.ops[s].n_out : Pdef.ops[s].n_out * Pdef.ops[s].n_in;
       const int ch = DEF_BLOCK * DEF_TILES;
       D.chunks_plus = (int)((n_plus + ch - 1) / ch);
       const int chunks = D.chunks_plus + (int)((n_bins - n_plus + ch - 1) / ch);
       if (dtype == FSWEEP_C64)
-        fsweep_sos_defer_kernel<float><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(P, D);
+        fsweep_sos_defer_kernel<float><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(Pdef, D);
       else
-        fsweep_sos_defer_kernel<double><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(P, D);
+        fsweep_sos_defer_kernel<double><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(Pdef, D);
       if ((e = cudaGetLastError()) != cudaSuccess) return fail(FSWEEP_E_CUDA, "deferred gradient launch: %s", cudaGetErrorString(e));
       ++launches;
     }
@@ -764,7 +806,7 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     int max_total = 1;
     for (int s = 0; s < P.n_ops; ++s) {
       FinalizeOp& o = F.ops[s];
-      o.kind = P.ops[s].kind;
+      o.kind = Pdef.ops[s].kind;  // (the sweep kernel may have seen a deferred cascade as a TABLE)
       o.n_out = P.ops[s].n_out;
       o.n_in = P.ops[s].n_in;
       o.K = P.ops[s].K;

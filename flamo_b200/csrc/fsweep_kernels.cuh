@@ -1312,6 +1312,33 @@ struct DeferArgs {
   int ncols_total, chunks_plus, opi;
 };
 
+// Response table of a deferred section-cascade op for the processed bins: tab[k][m][n] (PSOS: tab[k][n]), indexed by
+// ABSOLUTE bin like a TABLE op (the pointer handed in is already offset by -bin_begin rows).  One block per channel
+// pair, a bin per thread: the pair's coefficients are uniform loads that stay in L1, where the row-distributed
+// backward kernel streamed the whole coefficient set (491 KB for config 3) from L2 once per bin.  The backward
+// kernel then reads the op as a TABLE, and the gradient kernel below takes H from here instead of re-evaluating it.
+template <typename T>
+__global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_table_kernel(const __grid_constant__ ProgK P, const DeferArgs D) {
+  const OpK& op = P.ops[D.opi];
+  const bool par = op.kind == FSWEEP_OP_PSOS;
+  const int pair = blockIdx.x;
+  const int m = par ? pair : pair / op.n_in, n = par ? pair : pair - m * op.n_in;
+  const int K = op.K;
+  const T* coef = reinterpret_cast<const T*>(op.coef) + (par ? (size_t)n * 16 : ((size_t)n * op.n_out + m) * 16);
+  const long stride = par ? (long)op.n_out * 16 : (long)op.n_in * op.n_out * 16;
+  const size_t row = par ? (size_t)op.n_out : (size_t)op.n_out * op.n_in;
+  cx<T>* tab = reinterpret_cast<cx<T>*>(op.gtab);
+  const long long base = (long long)blockIdx.y * DEF_BLOCK * DEF_TILES;
+  for (int tile = 0; tile < DEF_TILES; ++tile) {
+    const long long bl = base + (long long)tile * DEF_BLOCK + threadIdx.x;
+    if (bl >= D.n_bins) break;
+    const Ctx<T> ctx = make_ctx<T>(P, D.bin_begin + bl);
+    bool guarded;
+    const cx<T> H = sos_eval<T>(coef, K, stride, ctx, guarded);
+    st_cx(tab + (size_t)ctx.k * row + pair, H);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_defer_kernel(const __grid_constant__ ProgK P, const DeferArgs D) {
   constexpr int CH = DEF_BLOCK * DEF_TILES;
@@ -1350,8 +1377,14 @@ __global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_defer_kernel(const __gri
     cx<T> H = mk<T>(0, 0), gh = mk<T>(0, 0), u1 = mk<T>(0, 0), u2 = mk<T>(0, 0);
     if (bl < lim) {
       const Ctx<T> ctx = make_ctx<T>(P, D.bin_begin + bl);
-      bool guarded;
-      H = sos_eval<T>(coef, K, stride, ctx, guarded);
+      bool guarded = false;
+      if (op.gtab != nullptr) {
+        // the response table built for the backward kernel; (eps, 0) may be the reference's zero guard: re-check
+        H = ld_cx(reinterpret_cast<const cx<T>*>(op.gtab) + (size_t)ctx.k * (par ? (size_t)op.n_out : (size_t)op.n_out * op.n_in) + pair);
+        if (H.x == eps_of<T>() && H.y == T(0)) H = sos_eval<T>(coef, K, stride, ctx, guarded);
+      } else {
+        H = sos_eval<T>(coef, K, stride, ctx, guarded);
+      }
       u1 = ctx.u1;
       u2 = ctx.u2;
       for (int q = 0; q < D.ncols_total; ++q) {
