@@ -11,7 +11,7 @@
 #include <type_traits>
 #include <vector>
 
-#include "fsweep_tpc.cuh"
+#include "fsweep_cta.cuh"
 
 using namespace fsweep;
 
@@ -69,6 +69,8 @@ struct fsweep_plan {
   LoopInfo loop;
   int tpb_np = 0;  // 4 / 8: additionally small enough for the thread-per-bin kernels of fsweep_tpb.cuh
   bool tpb_force = false;  // FSWEEP_FORCE_TPB=1 (tests): use them regardless of the bin count
+  bool cta = false;  // wide flagship shape (32 < N <= 64, float32): CTA-per-bin kernels, fsweep_cta.cuh
+  int cta_blocks_per_sm[2] = {0, 0};
   int tpc_np = 0;  // 4 / 8: the flagship shape (N x 1 gain, loop width <= 8, 1 x N gain) -> compact kernels, fsweep_tpc.cuh
   bool tpc_force = false;  // FSWEEP_FORCE_TPC=1 (tests)
   // lazily filled launch geometry: [cc index 0:1, 1:4, 2:loop kernels][fwd, bwd]
@@ -211,7 +213,27 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
       }
     }
   }
-  // shared-memory accumulator budget: spill the largest rows to global atomics until it fits
+  // ---- wide flagship shape -> CTA-per-bin kernels: [GAIN N x 1] RECURSION(diagonal, no gradients ; GAIN N x N) [GAIN 1 x N]
+  {
+    const char* no_cta = getenv("FSWEEP_DISABLE_CTA");
+    bool ok = !(no_cta && no_cta[0] == '1') && dtype == FSWEEP_C64 && width > 32 && width <= 64 && rec >= 0 &&
+              pre.size() == 1 && post.size() == 1 && fb.size() == 1 && ops[fb[0]].kind == FSWEEP_OP_GAIN &&
+              ops[pre[0]].kind == FSWEEP_OP_GAIN && ops[post[0]].kind == FSWEEP_OP_GAIN && ops[pre[0]].n_in == 1 &&
+              ops[post[0]].n_out == 1 && ops[pre[0]].n_out == rec_n && ops[post[0]].n_in == rec_n && rec_in == rec_n &&
+              ff.size() <= 8;
+    for (int i : ff) ok = ok && kind_is_diag(ops[i].kind) && !(ops[i].flags & FSWEEP_F_GRAD);
+    if (ok) {
+      p->cta = true;
+      memset(&p->loop, 0, sizeof(p->loop));
+      p->loop.pre = slot_of[pre[0]];
+      p->loop.ff_begin = slot_of[ff[0]];
+      p->loop.n_ff = (int)ff.size();
+      p->loop.fb = slot_of[fb[0]];
+      p->loop.post = slot_of[post[0]];
+    }
+  }
+  // shared-memory accumulator budget: spill the largest rows to global atomics until it fits (the CTA kernels keep
+  // every accumulator in registers: nothing to spill)
   for (;;) {
     acc_per_lane = 0;
     int big = -1;
@@ -221,7 +243,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
         acc_per_lane += P.ops[s].row_len;
         if (big < 0 || P.ops[s].row_len > P.ops[big].row_len) big = s;
       }
-    if ((size_t)acc_per_lane * BLOCK * real_sz <= SMEM_ACC_BUDGET || big < 0) break;
+    if (p->cta || (size_t)acc_per_lane * BLOCK * real_sz <= SMEM_ACC_BUDGET || big < 0) break;
     P.ops[big].acc_mode = ACC_GLOBAL;
   }
   // section cascades too large for shared memory: defer their coefficient gradient to fsweep_sos_defer_kernel
@@ -399,6 +421,27 @@ int grid_cap(int64_t n_bins, int G) {
   return (int)std::min<int64_t>(need, MAX_GRID);
 }
 
+int cta_grid(fsweep_plan* p, bool bwd, int64_t n_bins, cudaError_t* err) {
+  *err = cudaSuccess;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (p->num_sms == 0) {
+    int dev = 0;
+    if ((*err = cudaGetDevice(&dev)) != cudaSuccess) return 0;
+    if ((*err = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return 0;
+  }
+  if (p->cta_blocks_per_sm[bwd] == 0) {
+    int n = 0;
+    if ((*err = occupancy_cta(bwd, &n)) != cudaSuccess) return 0;
+    if (n < 1) {
+      *err = cudaErrorLaunchOutOfResources;
+      return 0;
+    }
+    p->cta_blocks_per_sm[bwd] = n;
+  }
+  const int64_t resident = (int64_t)p->cta_blocks_per_sm[bwd] * p->num_sms;
+  return (int)std::min<int64_t>(std::min<int64_t>(resident, n_bins), grid_cap(n_bins, p->G));
+}
+
 template <typename F>
 cudaError_t by_group(int G, F&& f) {
   switch (G) {
@@ -459,6 +502,7 @@ int check_common(const fsweep_plan* plan, const void* const* coeffs, const void*
 
 extern "C" const char* fsweep_plan_kernel_family(const fsweep_plan_t* plan, int64_t n_bins, int backward) {
   if (!plan) return "";
+  if (plan->cta) return backward ? "fsweep_cta_kernel<bwd>" : "fsweep_cta_kernel<fwd>";
   if (use_tpc(plan, n_bins)) return backward ? "fsweep_tpc_kernel<NP,bwd>" : "fsweep_tpc_kernel<NP,fwd>";
   if (use_tpb(plan, n_bins, backward != 0)) return backward ? "fsweep_tpb_bwd_kernel" : "fsweep_tpb_fwd_kernel";
   if (plan->loop_fast) return backward ? "fsweep_loop_bwd_kernel" : "fsweep_loop_fwd_kernel";
@@ -578,14 +622,17 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
   const int cc = cc_of(batch * cols);
   const bool loop = plan->loop_fast;
   LaunchCfg cfg;
-  cfg.smem = smem_fwd(plan);
+  cfg.smem = plan->cta ? 0 : smem_fwd(plan);
   if (cfg.smem > 220 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "forward needs %zu bytes of shared memory", cfg.smem);
   cfg.stream = (cudaStream_t)stream;
-  cudaError_t e;
-  cfg.grid = pick_grid(plan, cc, false, cfg.smem, n_bins, &e, loop);
+  cudaError_t e = cudaSuccess;
+  cfg.grid = plan->cta ? 0 : pick_grid(plan, cc, false, cfg.smem, n_bins, &e, loop);
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
   const int dtype = plan->dtype;
-  if (use_tpc(plan, n_bins)) {
+  if (plan->cta) {
+    cfg.grid = cta_grid(plan, false, n_bins, &e);
+    if (e == cudaSuccess) e = launch_cta(false, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
+  } else if (use_tpc(plan, n_bins)) {
     cfg.grid = tpc_grid(n_bins);
     e = launch_tpc(plan->tpc_np, false, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
   } else if (use_tpb(plan, n_bins, false)) {
@@ -673,11 +720,11 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   const bool loop = plan->loop_fast;
   const int cc = loop ? 1 : cc_of(batch * cols);
   LaunchCfg cfg;
-  cfg.smem = smem_bwd(plan, cc);
+  cfg.smem = plan->cta ? 0 : smem_bwd(plan, cc);
   if (cfg.smem > 220 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "backward needs %zu bytes of shared memory", cfg.smem);
   cfg.stream = st;
-  cudaError_t e;
-  cfg.grid = pick_grid(plan, cc, true, cfg.smem, n_bins, &e, loop);
+  cudaError_t e = cudaSuccess;
+  cfg.grid = plan->cta ? 0 : pick_grid(plan, cc, true, cfg.smem, n_bins, &e, loop);
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
 
   const size_t partial_bytes = (((size_t)grid_cap(n_bins, plan->G) * P.acc_per_lane * plan->G * rs + 255) / 256) * 256;
@@ -744,7 +791,10 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     }
   }
   const int dtype = plan->dtype;
-  if (use_tpc(plan, n_bins)) {
+  if (plan->cta) {
+    cfg.grid = cta_grid(plan, true, n_bins, &e);
+    if (e == cudaSuccess) e = launch_cta(true, cfg.grid, st, P, plan->loop, A, plan->G);
+  } else if (use_tpc(plan, n_bins)) {
     cfg.grid = tpc_grid(n_bins);
     e = launch_tpc(plan->tpc_np, true, cfg.grid, st, P, plan->loop, A, plan->G);
   } else if (use_tpb(plan, n_bins, true)) {

@@ -984,7 +984,7 @@ __device__ __forceinline__ T crit_rowdist(const SweepArgs& A, T mag, bool live, 
 
 template <typename T>
 __device__ __forceinline__ void block_loss_store(double lacc, double* loss_partial) {
-  __shared__ double red[BLOCK / 32];
+  __shared__ double red[32];  // up to 1024 threads per block
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lacc += __shfl_xor_sync(FULL, lacc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lacc;

@@ -169,3 +169,55 @@ def test_deferred_sos_gradients_match_in_kernel_atomics(name, dtype, monkeypatch
         a, b = grads(False, shard, B), grads(True, shard, B)
         for u, v in zip(a, b):
             assert grad_err(u, v) <= tol, (shard, B)
+
+
+@pytest.mark.parametrize("N,B", [(40, 1), (64, 3), (48, 35)])
+def test_cta_per_bin_kernels_on_wide_fdn(N, B, monkeypatch):
+    """Wide FDN loops (32 < N <= 64, float32) run on the CTA-per-bin kernels (fsweep_cta.cuh): against the oracle,
+    and against the row-distributed two-warps-per-bin path (FSWEEP_DISABLE_CTA=1) — forward, input gradient and
+    parameter gradients, with a padded width (N < 64) and more than one pass of 32 right-hand sides (B = 35)."""
+    from flamo_b200 import workloads as W
+    from flamo_b200.processor import dsp, system
+
+    nfft, alias = 1024, 30.0
+    M = nfft // 2 + 1
+    delays = [601 + 37 * i for i in range(N)]
+    desc = W.fdn(N, delays=delays)
+
+    def run(disable):
+        if disable:
+            monkeypatch.setenv("FSWEEP_DISABLE_CTA", "1")
+        else:
+            monkeypatch.delenv("FSWEEP_DISABLE_CTA", raising=False)
+        saved = dict(sweep._PLANS)
+        sweep._PLANS.clear()
+        try:
+            torch.manual_seed(11)
+            model = W.build(desc, dsp, system, nfft, alias, dtype=torch.float32, device="cuda")
+            X = C.make_input(B, M, 1, None).to(torch.complex64).cuda().requires_grad_(True)
+            Y = model(X)
+            ps = [p for p in model.parameters() if p.requires_grad]
+            gs = torch.autograd.grad(C.golden_loss(Y), ps + [X])
+            plan = next(iter(sweep._PLANS.values()))
+            fam = plan.kernel_family(M, True)
+            return model, Y.detach(), [g.detach() for g in gs], fam
+        finally:
+            sweep._PLANS.clear()
+            sweep._PLANS.update(saved)
+
+    model, Ya, ga, fam_a = run(False)
+    _, Yb, gb, fam_b = run(True)
+    assert "cta" in fam_a and "cta" not in fam_b
+    assert rel_err(Ya.cpu().numpy(), Yb.cpu().numpy()) <= 2e-5
+    for u, v in zip(ga[:-1], gb[:-1]):
+        assert grad_err(u.cpu().numpy(), v.cpu().numpy()) <= 2e-4
+    gxa, gxb = ga[-1].cpu().numpy(), gb[-1].cpu().numpy()  # complex input gradient
+    assert np.abs(gxa - gxb).max() <= 2e-4 * np.abs(gxb).max()
+    # oracle (float64) on the same rounded parameters
+    params64 = [p.detach().cpu().double().requires_grad_(p.requires_grad) for p in model.parameters()]
+    X64 = C.make_input(B, M, 1, None)
+    Yo = O.forward(O.from_desc(desc), X64.to(torch.complex64).to(torch.complex128), params64, nfft, alias)
+    go = torch.autograd.grad(C.golden_loss(Yo), [p for p in params64 if p.requires_grad])
+    assert rel_err(np.abs(Ya.cpu().numpy()), np.abs(Yo.detach().numpy())) <= 1e-4
+    for u, v in zip(ga[:-1], go):
+        assert grad_err(u.cpu().numpy(), v.numpy()) <= 1e-3
