@@ -525,14 +525,15 @@ class Biquad(_SectionFilter):
 
     def _bounded_map(self, x):
         """clamp([fc..., 20 log10 |g|]) to [0,1] / [-60,60] dB (reference dsp.py:1528-1563)."""
-        gain_db = 20 * torch.log10(torch.abs(x[:, -1]))
+        cols = x.unbind(1)  # one UnbindBackward instead of a select_backward (zeros + copy + add) per column
+        gain_db = 20 * torch.log10(torch.abs(cols[-1]))
         tail = (1,) * (x.dim() - 2)
         if self.filter_type == "bandpass":
             e = torch.finfo(self.dtype).eps
-            v = torch.stack((x[:, 0], x[:, 1], gain_db), dim=1)
+            v = torch.stack((cols[0], cols[1], gain_db), dim=1)
             lo, hi = [e, e, -60.0], [1 - e, 1 - e, 60.0]
         else:
-            v = torch.stack((x[:, 0], gain_db), dim=1)
+            v = torch.stack((cols[0], gain_db), dim=1)
             lo, hi = [0.0, -60.0], [1.0, 60.0]
         lo = self._const("lo", lo, x).view(-1, *tail)
         hi = self._const("hi", hi, x).view(-1, *tail)
@@ -551,11 +552,12 @@ class Biquad(_SectionFilter):
     def _taps(self, p):
         half_fs = self.fs / 2  # rad2hertz(param * pi)
         kw = dict(fs=self.fs, device=p.device, dtype=p.dtype)
+        c = p.unbind(1)
         if self.filter_type == "lowpass":
-            return lowpass_filter(fc=p[:, 0] * half_fs, gain=p[:, 1], **kw)
+            return lowpass_filter(fc=c[0] * half_fs, gain=c[1], **kw)
         if self.filter_type == "highpass":
-            return highpass_filter(fc=p[:, 0] * half_fs, gain=p[:, 1], **kw)
-        return bandpass_filter(fc1=p[:, 0] * half_fs, fc2=p[:, 1] * half_fs, gain=p[:, 2], **kw)
+            return highpass_filter(fc=c[0] * half_fs, gain=c[1], **kw)
+        return bandpass_filter(fc1=c[0] * half_fs, fc2=c[1] * half_fs, gain=c[2], **kw)
 
 
 class parallelBiquad(Biquad):
@@ -611,8 +613,8 @@ class SOSFilter(_SectionFilter):
         assert self.size[1] == 6, "Second dimension must be 6: [b0,b1,b2,a0,a1,a2]."
 
     def _taps(self, mapped):
-        return (torch.stack((mapped[:, 0], mapped[:, 1], mapped[:, 2]), dim=0),
-                torch.stack((mapped[:, 3], mapped[:, 4], mapped[:, 5]), dim=0))
+        c = mapped.unbind(1)
+        return torch.stack(c[:3], dim=0), torch.stack(c[3:], dim=0)
 
 
 class parallelSOSFilter(SOSFilter):
@@ -655,9 +657,15 @@ class SVF(_SectionFilter):
         return F.softplus(param) / math.log(2.0)
 
     def param2mix(self, param, R=None):
-        G = 10 ** (-F.softplus(param[0]))
-        one, zero = torch.ones_like(G), torch.zeros_like(G)
+        return torch.stack(self._mix(param.unbind(0), R), dim=0)
+
+    def _mix(self, p, R):
+        """(mLP, mBP, mHP) from the three raw mix parameters p = (p0, p1, p2)."""
         t = self.filter_type
+        if t is None:
+            return (p[0] + 1, p[1] + 2, p[2] + 1)
+        G = 10 ** (-F.softplus(p[0]))
+        one, zero = torch.ones_like(G), torch.zeros_like(G)
         if t == "lowpass":
             m = (one, zero, zero)
         elif t == "highpass":
@@ -670,15 +678,14 @@ class SVF(_SectionFilter):
             m = (G, 2 * R * torch.sqrt(G), one)
         elif t in ("peaking", "notch"):
             m = (one, 2 * R * torch.sqrt(G), one)
-        else:
-            m = (param[0] + 1, param[1] + 2, param[2] + 1)
-        return torch.stack(m, dim=0)
+        return m
 
     def map_param2svf(self, param):
-        f = self.param2freq(param[0])
-        r = self.param2R(param[1])
+        p = param.unbind(0)  # one UnbindBackward (a stack) instead of five select_backward (zeros + copy + add)
+        f = self.param2freq(p[0])
+        r = self.param2R(p[1])
         R = 1 / r if self.filter_type == "peaking" else r
-        m = self.param2mix(param[2:], r)
+        m = self._mix(p[2:], r)
         return f, R, m[0], m[1], m[2]
 
     def _taps(self, mapped):

@@ -499,15 +499,27 @@ def _const_tensor(values, dtype, device):
     return t
 
 
+# rows: {B(w0), B'(w0), b2, 0, A(w0), A'(w0), a2, 0} for w0 = +1 then w0 = -1; columns: (b0, b1, b2, a0, a1, a2)
+_PACK_MATRIX = (
+    (1, 1, 1, 0, 0, 0), (0, 1, 2, 0, 0, 0), (0, 0, 1, 0, 0, 0), (0, 0, 0, 0, 0, 0),
+    (0, 0, 0, 1, 1, 1), (0, 0, 0, 0, 1, 2), (0, 0, 0, 0, 0, 1), (0, 0, 0, 0, 0, 0),
+    (1, -1, 1, 0, 0, 0), (0, 1, -2, 0, 0, 0), (0, 0, 1, 0, 0, 0), (0, 0, 0, 0, 0, 0),
+    (0, 0, 0, 1, -1, 1), (0, 0, 0, 0, 1, -2), (0, 0, 0, 0, 0, 1), (0, 0, 0, 0, 0, 0),
+)
+
+
 def pack_sections(b: torch.Tensor, a: torch.Tensor, parallel: bool, real: torch.dtype) -> torch.Tensor:
     """(3, K, N_out, N_in) taps (or (3, K, N) for parallel) -> kernel layout [K][N_in][N_out][2][8]
     ([K][N][2][8]): per section the Taylor coefficients of B and A around w0 = +1 and w0 = -1
-    (include/fsweep.h, FSWEEP_OP_SOS).  Formed in the taps' own (float64) precision, then cast;
-    differentiable, so autograd maps the kernel's packed gradient back onto (b, a)."""
-    z = torch.zeros_like(b[0])
-    plus = torch.stack((b[0] + b[1] + b[2], b[1] + 2 * b[2], b[2], z, a[0] + a[1] + a[2], a[1] + 2 * a[2], a[2], z), -1)
-    minus = torch.stack((b[0] - b[1] + b[2], b[1] - 2 * b[2], b[2], z, a[0] - a[1] + a[2], a[1] - 2 * a[2], a[2], z), -1)
-    packed = torch.stack((plus, minus), dim=-2)  # (K, ..., 2, 8)
-    if not parallel:
-        packed = packed.permute(0, 2, 1, 3, 4)  # (K, N_out, N_in, 2, 8) -> (K, N_in, N_out, 2, 8)
+    (include/fsweep.h, FSWEEP_OP_SOS).  The packing is linear in the taps: ONE contraction with a constant 16 x 6
+    matrix in the taps' own (float64) precision, then a cast — a handful of launches forward and backward instead of
+    one per tap combination.  Differentiable, so autograd maps the kernel's packed gradient back onto (b, a)."""
+    taps = torch.cat((b, a), dim=0)  # (6, K, ...)
+    T = _const_tensor(_PACK_MATRIX, taps.dtype, taps.device)  # (16, 6)
+    packed = torch.tensordot(T, taps, dims=([1], [0]))  # (16, K, ...)
+    packed = packed.reshape(2, 8, *taps.shape[1:])
+    if parallel:
+        packed = packed.permute(2, 3, 0, 1)  # (K, N, 2, 8)
+    else:
+        packed = packed.permute(2, 4, 3, 0, 1)  # (2, 8, K, N_out, N_in) -> (K, N_in, N_out, 2, 8)
     return packed.to(real).contiguous()
