@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
                                                             const __grid_constant__ LoopInfo L, const SweepArgs A, int G) {
   extern __shared__ __align__(16) float2 csm[];
   float2* sA = csm;                 // [CN][CLD]   L\U in place, 1/U_kk on the diagonal
-  float2* sY = sA + CN * CLD;       // [CN][CYLD]  right-hand sides / solutions of the current pass
+  float2* sY = sA + CN * CLD;       // [2][CQ]     pivot-entry broadcast of the substitutions (rest: spare)
   float2* sD = sY + CN * CYLD;      // [CN]  diagonal chain response
   float2* sV = sD + CN;             // [CN]  adjoint vector v, then vd = conj(D) v
   float2* sT = sV + CN;             // [CN]  T[j] = sum_b g_b conj(y_b[j])
@@ -215,42 +215,61 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
         sX[t] = xv;
       }
       __syncthreads();
-      // right-hand side, already row-permuted: Y'[i][b] = D[p_i] w_pre[p_i] x_b
-      for (int e = t; e < CN * CQ; e += CTA_T) {
-        const int i = e >> 5, b = e & 31;
-        const int src = sPiv[i];
-        const float2 d = sD[src];
-        const float w = sWpre[src];
-        sY[i * CYLD + b] = cmul2(f2(d.x * w, d.y * w), sX[b]);
-      }
-      __syncthreads();
-      const int ty = warp, b = lane;  // a warp owns rows ty, ty + 8, ...; a lane owns one right-hand side
-      // forward substitution (unit lower)
-      for (int k = 0; k < CN - 1; ++k) {
-        const float2 yk = sY[k * CYLD + b];
-        for (int r = k + 1 + ty; r < CN; r += 8) sY[r * CYLD + b] = cnma2(sY[r * CYLD + b], sA[r * CLD + k], yk);
-        __syncthreads();
-      }
-      // backward substitution (upper, reciprocal diagonal); row r is scaled right after its last update
-      if (ty == 0) sY[(CN - 1) * CYLD + b] = cmul2(sY[(CN - 1) * CYLD + b], sA[(CN - 1) * CLD + CN - 1]);
-      __syncthreads();
-      for (int k = CN - 1; k >= 1; --k) {
-        const float2 xk = sY[k * CYLD + b];
-        for (int r = ty; r < k; r += 8) {
-          float2 v = cnma2(sY[r * CYLD + b], sA[r * CLD + k], xk);
-          if (r == k - 1) v = cmul2(v, sA[r * CLD + r]);
-          sY[r * CYLD + b] = v;
+      // A warp owns rows ty, ty + 8, ..., ty + 56 and a lane one right-hand side: the thread's eight entries of the
+      // solution block stay in REGISTERS through both substitutions; only the pivot entry of each step crosses
+      // shared memory (double buffered: one barrier per step).
+      const int ty = warp, b = lane;
+      float2 yr[8];
+      {
+        const float2 xb = sX[b];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // right-hand side, already row-permuted: Y'[r][b] = D[p_r] w_pre[p_r] x_b
+          const int src = sPiv[ty + 8 * i];
+          const float2 d = sD[src];
+          const float w = sWpre[src];
+          yr[i] = cmul2(f2(d.x * w, d.y * w), xb);
         }
-        __syncthreads();
+      }
+      float2* sBk = sY;  // [2][CQ] pivot-entry broadcast
+      // forward substitution (unit lower): step k = 8p + kk is owned by warp kk, register p
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+#pragma unroll 1
+        for (int kk = 0; kk < 8; ++kk) {
+          const int k = 8 * p + kk;
+          if (ty == kk) sBk[(k & 1) * CQ + b] = yr[p];
+          __syncthreads();
+          const float2 yk = sBk[(k & 1) * CQ + b];
+          if (ty > kk) yr[p] = cnma2(yr[p], sA[(ty + 8 * p) * CLD + k], yk);
+#pragma unroll
+          for (int i = p + 1; i < 8; ++i) yr[i] = cnma2(yr[i], sA[(ty + 8 * i) * CLD + k], yk);
+        }
+      }
+      // backward substitution (upper, reciprocal diagonal)
+#pragma unroll
+      for (int p = 7; p >= 0; --p) {
+#pragma unroll 1
+        for (int kk = 7; kk >= 0; --kk) {
+          const int k = 8 * p + kk;
+          if (ty == kk) {  // (buffer parity flipped w.r.t. the forward pass: its last step used buffer 1)
+            yr[p] = cmul2(yr[p], sA[k * CLD + k]);
+            sBk[((k + 1) & 1) * CQ + b] = yr[p];
+          }
+          __syncthreads();
+          const float2 xk = sBk[((k + 1) & 1) * CQ + b];
+          if (ty < kk) yr[p] = cnma2(yr[p], sA[(ty + 8 * p) * CLD + k], xk);
+#pragma unroll
+          for (int i = 0; i < p; ++i) yr[i] = cnma2(yr[i], sA[(ty + 8 * i) * CLD + k], xk);
+        }
       }
       // ---- output o_b = w_post . y_b
       {
         float ox = 0.f, oy = 0.f;
-        for (int m = ty; m < CN; m += 8) {
-          const float w = sWpost[m];
-          const float2 y = sY[m * CYLD + b];
-          ox = fmaf(w, y.x, ox);
-          oy = fmaf(w, y.y, oy);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float w = sWpost[ty + 8 * i];
+          ox = fmaf(w, yr[i].x, ox);
+          oy = fmaf(w, yr[i].y, oy);
         }
         sRed[ty * CQ + b] = f2(ox, oy);
       }
@@ -302,8 +321,10 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
       if constexpr (BWD) {
         // T[j] += sum_b g_b conj(y_b[j]);  xbar += sum_b g_b conj(x_b);  g_x = g_b * sum_m w_pre[m] vd[m]
         const float2 go = sGo[b];
-        for (int j = ty; j < CN; j += 8) {
-          const float2 y = sY[j * CYLD + b];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = ty + 8 * i;
+          const float2 y = yr[i];
           float vx = go.x * y.x + go.y * y.y, vy = go.y * y.x - go.x * y.y;  // g conj(y)
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
