@@ -1,12 +1,16 @@
-// fsweep_expm.cu — E = exp(S), S = triu(P,1) - triu(P,1)^T (or S = P), and its adjoint, for the
-// orthogonal map of dsp.Matrix (reference flamo/processor/dsp.py:649, functional.py:42-56).
+// fsweep_params.cu — the PARAMETER-SIZED kernels of a training step: everything here works on O(#params) data and
+// costs one launch, which is what matters inside a captured step (a step of the headline config is 17 launches).
 //
-// torch.matrix_exp copies the matrix norm to the host to pick its Pade degree, which synchronises
-// and cannot be captured in a CUDA graph.  This kernel does the whole thing on the device: one CTA,
-// float64, scaling-and-squaring with a degree-12 Taylor polynomial (Paterson-Stockmeyer, 7 products) on
-// X = S / 2^s with ||X||_1 <= 1/4 (remainder 0.25^13/13! ~ 2e-18), matrices resident in shared memory.
-// The adjoint uses the block-triangular identity  exp([[S^T, G], [0, S^T]]) = [[E^T, dS], [0, E^T]]
-// (the same Frechet-derivative formula torch.autograd uses), then folds dS through the skew map.
+//  * E = exp(S), S = triu(P,1) - triu(P,1)^T (or S = P), and its adjoint, for the orthogonal map of dsp.Matrix
+//    (reference flamo/processor/dsp.py:649, functional.py:42-56).  torch.matrix_exp copies the matrix norm to the
+//    host to pick its Pade degree, which synchronises and cannot be captured in a CUDA graph.  This kernel does the
+//    whole thing on the device: one CTA, float64, scaling-and-squaring with a degree-12 Taylor polynomial
+//    (Paterson-Stockmeyer, 7 products) on X = S / 2^s with ||X||_1 <= 1/4 (remainder 0.25^13/13! ~ 2e-18), matrices
+//    resident in shared memory.  The adjoint uses the block-triangular identity
+//    exp([[S^T, G], [0, S^T]]) = [[E^T, dS], [0, E^T]] (the same Frechet-derivative formula torch.autograd uses),
+//    then folds dS through the skew map.
+//  * sparsity_loss of the mapped feedback matrix (reference flamo/optimize/loss.py:36-63), forward and backward.
+//  * the weighted total of the step's criteria (reference flamo/optimize/trainer.py:184-188).
 #include <cuda_runtime.h>
 
 #include "../../include/fsweep.h"
