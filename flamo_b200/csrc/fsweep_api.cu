@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fsweep_cta.cuh"
+#include "fsweep_stream.cuh"
 
 using namespace fsweep;
 
@@ -69,6 +70,8 @@ struct fsweep_plan {
   LoopInfo loop;
   int tpb_np = 0;  // 4 / 8: additionally small enough for the thread-per-bin kernels of fsweep_tpb.cuh
   bool tpb_force = false;  // FSWEEP_FORCE_TPB=1 (tests): use them regardless of the bin count
+  bool stream = false;  // TABLE-heavy program without recursion: streaming kernels, fsweep_stream.cuh
+  StreamInfo sinfo;     // everything but tb / qc / threads (chosen per call from batch*cols)
   bool cta = false;  // wide flagship shape (32 < N <= 64, float32): CTA-per-bin kernels, fsweep_cta.cuh
   int cta_blocks_per_sm[2] = {0, 0};
   int tpc_np = 0;  // 4 / 8: the flagship shape (N x 1 gain, loop width <= 8, 1 x N gain) -> compact kernels, fsweep_tpc.cuh
@@ -351,6 +354,48 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
     }
   }
 
+  // ---- TABLE-heavy program without recursion -> streaming kernels
+  {
+    const char* no_stream = getenv("FSWEEP_DISABLE_STREAM");
+    bool ok = !(no_stream && no_stream[0] == '1') && dtype == FSWEEP_C64 && rec < 0 && width <= SW;
+    bool any_table = false;
+    for (int s2 = 0; s2 < P.n_ops && ok; ++s2) {
+      const OpK& o = P.ops[s2];
+      const bool tabk = o.kind == FSWEEP_OP_TABLE || o.kind == FSWEEP_OP_PTABLE;
+      any_table |= tabk;
+      ok = tabk || o.kind == FSWEEP_OP_PGAIN || (o.kind == FSWEEP_OP_GAIN && o.acc_mode == ACC_NONE);
+      ok = ok && o.acc_mode != ACC_GLOBAL;
+    }
+    if (ok && any_table) {
+      StreamInfo& S = p->sinfo;
+      memset(&S, 0, sizeof(S));
+      S.n_ops = P.n_ops;
+      int off = 0, st = 0, pg = 0;
+      for (int s2 = 0; s2 < P.n_ops; ++s2) {
+        const OpK& o = P.ops[s2];
+        S.tab_off[s2] = -1;
+        S.pg_off[s2] = -1;
+        S.row_bytes[s2] = 0;
+        if (o.kind == FSWEEP_OP_TABLE || o.kind == FSWEEP_OP_PTABLE) {
+          S.row_bytes[s2] = (o.kind == FSWEEP_OP_TABLE ? o.n_out * o.n_in : o.n_out) * 8;
+          S.tab_off[s2] = off;  // in units of ONE bin; scaled by tb at launch
+          off += S.row_bytes[s2];
+        }
+        if (o.kind == FSWEEP_OP_PGAIN && o.acc_mode == ACC_SMEM) {
+          S.pg_off[s2] = pg;
+          pg += o.n_out;
+        }
+        S.st_off[s2] = st;
+        st += o.n_in;
+      }
+      S.st_off[P.n_ops] = st;
+      S.st_total = st + P.out_ch;
+      S.bytes_per_bin = off;
+      S.n_pgain_acc = pg;
+      p->stream = S.st_total <= S_MAXST;
+    }
+  }
+
   *out = p;
   return FSWEEP_OK;
 }
@@ -442,6 +487,21 @@ int cta_grid(fsweep_plan* p, bool bwd, int64_t n_bins, cudaError_t* err) {
   return (int)std::min<int64_t>(std::min<int64_t>(resident, n_bins), grid_cap(n_bins, p->G));
 }
 
+// per-call geometry of the streaming kernels; returns false when this call cannot use them
+bool stream_setup(const fsweep_plan* p, int64_t q, bool bwd, StreamInfo* S, size_t* smem) {
+  if (!p->stream || q < 1 || q > 16 || (q & (q - 1)) != 0) return false;
+  *S = p->sinfo;
+  S->qc = (int)q;
+  S->tb = 512 / (SW * (int)q);
+  S->threads = S->tb * SW * (int)q;
+  for (int i = 0; i < S->n_ops; ++i)
+    if (S->tab_off[i] >= 0) S->tab_off[i] *= S->tb;  // blocks of tb rows per op inside a stage
+  const size_t stage = (size_t)S->tb * S->bytes_per_bin;
+  *smem = S_STAGES * stage + (size_t)S->tb * q * S->st_total * 8 + (size_t)2 * S->tb * q * SW * 8 +
+          (bwd ? stage + (size_t)S->n_pgain_acc * 4 : 0) + 16;
+  return *smem <= 200 * 1024;
+}
+
 template <typename F>
 cudaError_t by_group(int G, F&& f) {
   switch (G) {
@@ -503,6 +563,7 @@ int check_common(const fsweep_plan* plan, const void* const* coeffs, const void*
 extern "C" const char* fsweep_plan_kernel_family(const fsweep_plan_t* plan, int64_t n_bins, int backward) {
   if (!plan) return "";
   if (plan->cta) return backward ? "fsweep_cta_kernel<bwd>" : "fsweep_cta_kernel<fwd>";
+  if (plan->stream) return backward ? "fsweep_stream_kernel<bwd> (batch*cols a power of two <= 16)" : "fsweep_stream_kernel<fwd> (batch*cols a power of two <= 16)";
   if (use_tpc(plan, n_bins)) return backward ? "fsweep_tpc_kernel<NP,bwd>" : "fsweep_tpc_kernel<NP,fwd>";
   if (use_tpb(plan, n_bins, backward != 0)) return backward ? "fsweep_tpb_bwd_kernel" : "fsweep_tpb_fwd_kernel";
   if (plan->loop_fast) return backward ? "fsweep_loop_bwd_kernel" : "fsweep_loop_fwd_kernel";
@@ -629,9 +690,19 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
   cfg.grid = plan->cta ? 0 : pick_grid(plan, cc, false, cfg.smem, n_bins, &e, loop);
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
   const int dtype = plan->dtype;
+  StreamInfo SI;
+  size_t ssmem = 0;
   if (plan->cta) {
     cfg.grid = cta_grid(plan, false, n_bins, &e);
     if (e == cudaSuccess) e = launch_cta(false, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
+  } else if (!crit && stream_setup(plan, batch * cols, false, &SI, &ssmem)) {
+    int bps = 0;
+    e = occupancy_stream(false, SI.threads, ssmem, &bps);
+    if (e == cudaSuccess) {
+      const int64_t tiles = (n_bins + SI.tb - 1) / SI.tb;
+      cfg.grid = (int)std::min<int64_t>(tiles, (int64_t)std::max(1, bps) * std::max(1, plan->num_sms ? plan->num_sms : 148));
+      e = launch_stream(false, cfg.grid, ssmem, cfg.stream, P, SI, A, plan->G);
+    }
   } else if (use_tpc(plan, n_bins)) {
     cfg.grid = tpc_grid(n_bins);
     e = launch_tpc(plan->tpc_np, false, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
@@ -791,9 +862,20 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     }
   }
   const int dtype = plan->dtype;
+  StreamInfo SI;
+  size_t ssmem = 0;
   if (plan->cta) {
     cfg.grid = cta_grid(plan, true, n_bins, &e);
     if (e == cudaSuccess) e = launch_cta(true, cfg.grid, st, P, plan->loop, A, plan->G);
+  } else if (!crit && stream_setup(plan, batch * cols, true, &SI, &ssmem)) {
+    int bps = 0;
+    e = occupancy_stream(true, SI.threads, ssmem, &bps);
+    if (e == cudaSuccess) {
+      const int64_t tiles = (n_bins + SI.tb - 1) / SI.tb;
+      cfg.grid = (int)std::min<int64_t>(std::min<int64_t>(tiles, (int64_t)std::max(1, bps) * std::max(1, plan->num_sms ? plan->num_sms : 148)),
+                                        grid_cap(n_bins, plan->G));
+      e = launch_stream(true, cfg.grid, ssmem, st, P, SI, A, plan->G);
+    }
   } else if (use_tpc(plan, n_bins)) {
     cfg.grid = tpc_grid(n_bins);
     e = launch_tpc(plan->tpc_np, true, cfg.grid, st, P, plan->loop, A, plan->G);

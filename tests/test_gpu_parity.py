@@ -221,3 +221,68 @@ def test_cta_per_bin_kernels_on_wide_fdn(N, B, monkeypatch):
     assert rel_err(np.abs(Ya.cpu().numpy()), np.abs(Yo.detach().numpy())) <= 1e-4
     for u, v in zip(ga[:-1], go):
         assert grad_err(u.cpu().numpy(), v.numpy()) <= 1e-3
+
+
+@pytest.mark.parametrize("B,cols", [(1, None), (1, 4), (2, 2), (3, None)])
+def test_streaming_table_kernels(B, cols, monkeypatch):
+    """TABLE-heavy programs without recursion (FIR filter banks + gains, the shape of the real
+    examples/e8_active_acoustics.py path) run on the streaming kernels (fsweep_stream.cuh) when batch*cols is a power of
+    two <= 16: against the generic interpreter (FSWEEP_DISABLE_STREAM=1) and the oracle — outputs, table / gain
+    gradients, input gradient, whole spectrum and a bin shard."""
+    from flamo_b200 import workloads as W
+    from flamo_b200.processor import dsp, system
+
+    nfft, alias = 2048, 30.0
+    M = nfft // 2 + 1
+    desc = ("Series", [
+        ("Filter", dict(size=(20, 5, 3), requires_grad=True)),
+        ("parallelFilter", dict(size=(33, 5), requires_grad=True)),
+        ("parallelGain", dict(size=(5,), requires_grad=True)),
+        ("Gain", dict(size=(4, 5), requires_grad=False)),
+        ("Filter", dict(size=(12, 2, 4), requires_grad=True)),
+    ])
+
+    def run(disable, shard=None):
+        if disable:
+            monkeypatch.setenv("FSWEEP_DISABLE_STREAM", "1")
+        else:
+            monkeypatch.delenv("FSWEEP_DISABLE_STREAM", raising=False)
+        saved = dict(sweep._PLANS)
+        sweep._PLANS.clear()
+        try:
+            torch.manual_seed(21)
+            model = W.build(desc, dsp, system, nfft, alias, dtype=torch.float32, device="cuda")
+            X = C.make_input(B, M, 3, cols).to(torch.complex64).cuda().requires_grad_(True)
+            ps = [p for p in model.parameters() if p.requires_grad]
+            if shard is None:
+                Y = model(X)
+            else:
+                with sweep.bin_shard(*shard):
+                    Y = model(X)
+            gs = torch.autograd.grad((Y.abs() ** 2).mean(), ps + [X])
+            fam = [pl.kernel_family(M, True) for pl in sweep._PLANS.values()]
+            return model, Y.detach(), [g.detach() for g in gs], fam
+        finally:
+            sweep._PLANS.clear()
+            sweep._PLANS.update(saved)
+
+    q = B * (cols or 1)
+    streamable = q & (q - 1) == 0
+    for shard in (None, (301, 777)):
+        model, Ya, ga, fam_a = run(False, shard)
+        _, Yb, gb, fam_b = run(True, shard)
+        assert any("stream" in f for f in fam_a) and not any("stream" in f for f in fam_b)
+        assert np.abs(Ya.cpu().numpy() - Yb.cpu().numpy()).max() <= 2e-6 * np.abs(Yb.cpu().numpy()).max()
+        for u, v in zip(ga, gb):
+            u, v = u.cpu().numpy(), v.cpu().numpy()
+            assert np.abs(u - v).max() <= 2e-5 * np.abs(v).max(), (shard, streamable)
+    # oracle on the whole spectrum
+    model, Ya, ga, _ = run(False)
+    params64 = [p.detach().cpu().double().requires_grad_(p.requires_grad) for p in model.parameters()]
+    X64 = C.make_input(B, M, 3, cols).to(torch.complex64).to(torch.complex128).requires_grad_(True)
+    Yo = O.forward(O.from_desc(desc), X64, params64, nfft, alias)
+    go = torch.autograd.grad((Yo.abs() ** 2).mean(), [p for p in params64 if p.requires_grad] + [X64])
+    assert rel_err(Ya.cpu().numpy(), Yo.detach().numpy()) <= 1e-4
+    for u, v in zip(ga, go):
+        u, v = u.cpu().numpy(), v.numpy()
+        assert np.abs(u - v).max() <= 1e-3 * np.abs(v).max()
