@@ -70,6 +70,8 @@ struct fsweep_plan {
   LoopInfo loop;
   int tpb_np = 0;  // 4 / 8: additionally small enough for the thread-per-bin kernels of fsweep_tpb.cuh
   bool tpb_force = false;  // FSWEEP_FORCE_TPB=1 (tests): use them regardless of the bin count
+  int stream_bps[2] = {0, 0};       // cached occupancy of the streaming kernels ...
+  size_t stream_bps_smem[2] = {0, 0};  // ... for this dynamic shared memory size
   bool stream = false;  // TABLE-heavy program without recursion: streaming kernels, fsweep_stream.cuh
   StreamInfo sinfo;     // everything but tb / qc / threads (chosen per call from batch*cols)
   bool cta = false;  // wide flagship shape (32 < N <= 64, float32): CTA-per-bin kernels, fsweep_cta.cuh
@@ -492,13 +494,14 @@ bool stream_setup(const fsweep_plan* p, int64_t q, bool bwd, StreamInfo* S, size
   if (!p->stream || q < 1 || q > 16 || (q & (q - 1)) != 0) return false;
   *S = p->sinfo;
   S->qc = (int)q;
-  S->tb = 512 / (SW * (int)q);
-  S->threads = S->tb * SW * (int)q;
+  S->threads = bwd ? 32 : 32;  // one thread per (bin, column); small blocks: shared memory per bin bounds the warps per SM
+  S->tb = S->threads / (int)q;
   for (int i = 0; i < S->n_ops; ++i)
     if (S->tab_off[i] >= 0) S->tab_off[i] *= S->tb;  // blocks of tb rows per op inside a stage
   const size_t stage = (size_t)S->tb * S->bytes_per_bin;
-  *smem = S_STAGES * stage + (size_t)S->tb * q * S->st_total * 8 + (size_t)2 * S->tb * q * SW * 8 +
-          (bwd ? stage + (size_t)S->n_pgain_acc * 4 : 0) + 16;
+  const size_t n_state = bwd ? (size_t)S->st_total : 2 * SW;
+  *smem = S_STAGES * stage + n_state * S->threads * 8 +
+          (bwd ? (size_t)2 * SW * S->threads * 8 + stage + (size_t)S->n_pgain_acc * 4 : 0) + 16;
   return *smem <= 200 * 1024;
 }
 
@@ -696,8 +699,14 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
     cfg.grid = cta_grid(plan, false, n_bins, &e);
     if (e == cudaSuccess) e = launch_cta(false, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
   } else if (!crit && stream_setup(plan, batch * cols, false, &SI, &ssmem)) {
-    int bps = 0;
-    e = occupancy_stream(false, SI.threads, ssmem, &bps);
+    int bps = plan->stream_bps_smem[0] == ssmem ? plan->stream_bps[0] : 0;
+    if (bps == 0) {
+      e = occupancy_stream(false, SI.threads, ssmem, &bps);
+      if (e == cudaSuccess) {
+        plan->stream_bps[0] = bps;
+        plan->stream_bps_smem[0] = ssmem;
+      }
+    }
     if (e == cudaSuccess) {
       const int64_t tiles = (n_bins + SI.tb - 1) / SI.tb;
       cfg.grid = (int)std::min<int64_t>(tiles, (int64_t)std::max(1, bps) * std::max(1, plan->num_sms ? plan->num_sms : 148));
@@ -868,8 +877,14 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     cfg.grid = cta_grid(plan, true, n_bins, &e);
     if (e == cudaSuccess) e = launch_cta(true, cfg.grid, st, P, plan->loop, A, plan->G);
   } else if (!crit && stream_setup(plan, batch * cols, true, &SI, &ssmem)) {
-    int bps = 0;
-    e = occupancy_stream(true, SI.threads, ssmem, &bps);
+    int bps = plan->stream_bps_smem[1] == ssmem ? plan->stream_bps[1] : 0;
+    if (bps == 0) {
+      e = occupancy_stream(true, SI.threads, ssmem, &bps);
+      if (e == cudaSuccess) {
+        plan->stream_bps[1] = bps;
+        plan->stream_bps_smem[1] = ssmem;
+      }
+    }
     if (e == cudaSuccess) {
       const int64_t tiles = (n_bins + SI.tb - 1) / SI.tb;
       cfg.grid = (int)std::min<int64_t>(std::min<int64_t>(tiles, (int64_t)std::max(1, bps) * std::max(1, plan->num_sms ? plan->num_sms : 148)),
