@@ -195,20 +195,23 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
         if (op.kind == FSWEEP_OP_TABLE) {
           const float2* H = reinterpret_cast<const float2*>(tab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
           if (op.acc_mode == ACC_TABLE) {  // dL/dH[m][n] = sum over the bin's columns of g[m] conj(v[n])
+            // the qc threads of a bin split the entries among themselves and each sums over ALL columns, reading
+            // the neighbours' (thread-private) g and v columns: no shuffle chain per entry
             float2* gt = reinterpret_cast<float2*>(sGTab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
-            for (int m = 0; m < n_out; ++m) {
-              const float2 gm = go[(size_t)m * T];
-#pragma unroll 2
-              for (int n = 0; n < n_in; ++n) {
-                const float2 vn = v[(size_t)n * T];
-                float vx = gm.x * vn.x + gm.y * vn.y, vy = gm.y * vn.x - gm.x * vn.y;
-                for (int o = qc >> 1; o > 0; o >>= 1) {
-                  vx += __shfl_xor_sync(FULL, vx, o);
-                  vy += __shfl_xor_sync(FULL, vy, o);
-                }
-                if (c == 0) gt[m * n_in + n] = f2(vx, vy);
+            __syncwarp();
+            const float2* go0 = go - c;  // column 0 of this bin
+            const float2* v0 = v - c;
+            for (int e = c; e < n_out * n_in; e += qc) {
+              const int m = e / n_in, n = e - m * n_in;
+              float vx = 0.f, vy = 0.f;
+              for (int cq = 0; cq < qc; ++cq) {
+                const float2 gm = go0[(size_t)m * T + cq], vn = v0[(size_t)n * T + cq];
+                vx = fmaf(gm.x, vn.x, fmaf(gm.y, vn.y, vx));
+                vy = fmaf(gm.y, vn.x, fmaf(-gm.x, vn.y, vy));
               }
+              gt[e] = f2(vx, vy);
             }
+            __syncwarp();  // nobody overwrites a gradient column while a neighbour still reads it
           }
           for (int n = 0; n < n_in; ++n) {  // g_in[n] = sum_m conj(H[m][n]) g[m]
             float ax = 0.f, ay = 0.f;
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
                 vy += __shfl_xor_sync(FULL, vy, o);
               }
               if (c == 0) gt[m] = f2(vx, vy);
-            }
+            }  // (diagonal tables: n entries only, the shuffle sum is cheap)
             gi[(size_t)m * T] = f2(h.x * gm.x + h.y * gm.y, h.x * gm.y - h.y * gm.x);
           }
         } else if (op.kind == FSWEEP_OP_GAIN) {
