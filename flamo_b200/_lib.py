@@ -26,6 +26,7 @@ EXPORTS = [
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward",
     "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total",
+    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n",
 ]
 
 
@@ -105,6 +106,9 @@ def lib():
     L.fsweep_sparsity_forward.argtypes = [vp, i32, i32, i32, vp, vp]
     L.fsweep_sparsity_backward.restype = i32
     L.fsweep_sparsity_backward.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.fsweep_allreduce_p2p_max_n.restype = i32
+    L.fsweep_allreduce_p2p.restype = i32
+    L.fsweep_allreduce_p2p.argtypes = [vp, vp, i32, i32, i32, C.c_double, vp, vp]
     L.fsweep_weighted_total.restype = i32
     L.fsweep_weighted_total.argtypes = [C.POINTER(vp), C.POINTER(C.c_double), C.POINTER(C.c_double), i32, i32, vp, vp]
     _lib = L

@@ -309,3 +309,78 @@ extern "C" FSWEEP_API int fsweep_weighted_total(const void* const* parts, const 
     return FSWEEP_E_BADARG;
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// One-shot all-reduce of the (small) flat gradient buffer over NVLink peer memory: the one exchange of a multi-GPU
+// training step (80 - 4224 floats, pure latency).  Every rank's buffer lives in symmetric memory
+// (torch.distributed._symmetric_memory provides the allocation and the peer pointers — plumbing); ONE kernel per
+// rank does the whole collective: announce "my gradients are final" in every peer's signal pad (release), wait for
+// every peer's announcement (acquire), read ALL peers' buffers with P2P loads and sum them in rank order (every rank
+// gets bit-identical sums), announce "done reading", wait for everyone, then overwrite its own buffer with
+// scale * sum.  Epochs increase monotonically in device memory, so the launch can be replayed inside a CUDA graph.
+// A bounded spin (about a second) turns a missing peer into garbage instead of a hung GPU.
+namespace {
+constexpr int AR_THREADS = 1024;
+constexpr int AR_PER = 8;          // values per thread: n <= 8192
+constexpr int AR_PAD_OFF = 256;    // uint32 offset of our flags inside the signal pad (torch's own barriers use the head)
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(AR_THREADS) allreduce_p2p_kernel(float* const* __restrict__ bufs,
+                                                                  unsigned* const* __restrict__ pads, int rank, int world,
+                                                                  int n, float scale, unsigned* epoch_ctr) {
+  __shared__ unsigned s_epoch;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_epoch = *epoch_ctr + 1u;
+  __syncthreads();
+  const unsigned epoch = s_epoch;
+  auto barrier = [&](int phase) {
+    if (tid < world) {
+      __threadfence_system();
+      st_release_sys(pads[tid] + AR_PAD_OFF + phase * 64 + rank, epoch);
+      const unsigned* mine = pads[rank] + AR_PAD_OFF + phase * 64 + tid;
+      unsigned spins = 0;
+      while ((int)(ld_acquire_sys(mine) - epoch) < 0 && ++spins < (1u << 26)) {
+      }
+    }
+    __syncthreads();
+  };
+  barrier(0);  // every rank's gradients are final and visible
+  float acc[AR_PER];
+#pragma unroll
+  for (int i = 0; i < AR_PER; ++i) {
+    const int idx = tid + i * AR_THREADS;
+    float s = 0.f;
+    if (idx < n)
+      for (int r = 0; r < world; ++r) s += __ldcv(bufs[r] + idx);  // fixed rank order: identical on every rank
+    acc[i] = s;
+  }
+  barrier(1);  // everyone has read everyone: the buffers may be overwritten
+#pragma unroll
+  for (int i = 0; i < AR_PER; ++i) {
+    const int idx = tid + i * AR_THREADS;
+    if (idx < n) bufs[rank][idx] = acc[i] * scale;
+  }
+  if (tid == 0) *epoch_ctr = epoch;
+}
+}  // namespace
+
+extern "C" FSWEEP_API int fsweep_allreduce_p2p_max_n(void) { return AR_THREADS * AR_PER; }
+
+extern "C" FSWEEP_API int fsweep_allreduce_p2p(void* const* peer_buffers, void* const* peer_signal_pads, int rank,
+                                               int world, int n, double scale, void* epoch_counter, void* stream) {
+  if (!peer_buffers || !peer_signal_pads || !epoch_counter || world < 1 || world > 64 || rank < 0 || rank >= world ||
+      n < 1 || n > AR_THREADS * AR_PER)
+    return FSWEEP_E_BADARG;
+  allreduce_p2p_kernel<<<1, AR_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float* const*>(peer_buffers), reinterpret_cast<unsigned* const*>(peer_signal_pads), rank, world, n,
+      (float)scale, reinterpret_cast<unsigned*>(epoch_counter));
+  return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}

@@ -3,7 +3,10 @@
 The reference has no multi-device path.  Bins and batch items are independent units,
 so the path shards with no data-path collective; the only exchange is ONE all-reduce per step of the
 flat parameter-gradient buffer (a few hundred bytes to a few KB) with the per-criterion losses riding
-in its tail.  Two sharding modes:
+in its tail.  On GPUs that buffer lives in symmetric (peer-mapped) memory and the all-reduce is ONE
+hand-written kernel per rank over NVLink (libfsweep fsweep_allreduce_p2p: signal, read every peer's
+buffer, sum in rank order, scale, write back — bit-identical on every rank, capture safe); NCCL is
+the fallback.  Two sharding modes:
 
   shard="batch"  every rank sweeps all bins of its own batch items (weak scaling: per-GPU work fixed);
                  gradients are averaged.
@@ -40,11 +43,47 @@ class DataParallelTrainer(Trainer):
         self._flat = None
 
     # gradients live in one flat buffer so that a step needs exactly one collective
+    def _p2p_buffer(self, numel, dtype, device):
+        """The flat buffer in symmetric (peer-mapped) memory + what libfsweep's one-shot all-reduce kernel needs, or
+        None (not CUDA + NCCL / not float32 / too large / symmetric memory unavailable / FLAMO_B200_P2P_ALLREDUCE=0): the
+        collective is then NCCL's.  Measured (profiles/r01_notes.md): inside the captured step the one-shot kernel
+        (scale fused, latency flat in the number of ranks) beats NCCL by 6 us on 2 GPUs and 33 us on 4."""
+        import os
+
+        from . import _lib
+
+        if (self.world == 1 or device.type != "cuda" or dtype != torch.float32 or dist.get_backend(self.pg) != "nccl"
+                or os.environ.get("FLAMO_B200_P2P_ALLREDUCE", "1") == "0"):
+            return None
+        try:
+            if numel > _lib.lib().fsweep_allreduce_p2p_max_n():
+                return None
+            import torch.distributed._symmetric_memory as symm_mem
+
+            buf = symm_mem.empty(numel, dtype=dtype, device=device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, self.pg if self.pg is not None else dist.group.WORLD)
+            if hdl.signal_pad_size < 2048 or hdl.world_size != self.world:
+                return None
+            self._p2p = (hdl, torch.zeros(1, dtype=torch.int32, device=device))
+            torch.cuda.synchronize(device)
+            dist.barrier(self.pg)
+            return buf
+        except Exception as e:  # pragma: no cover - depends on the box
+            import warnings
+
+            warnings.warn(f"peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
+            self._p2p = None
+            return None
+
     def _setup_flat(self, n_vals):
         ps = [p for p in self.net.parameters() if p.requires_grad]
         total = sum(p.numel() for p in ps)
         dt = ps[0].dtype
-        self._flat = torch.zeros(total + n_vals, dtype=dt, device=ps[0].device)
+        self._p2p = None
+        self._flat = self._p2p_buffer(total + n_vals, dt, ps[0].device)
+        if self._flat is None:
+            self._flat = torch.zeros(total + n_vals, dtype=dt, device=ps[0].device)
         off = 0
         for p in ps:
             p.grad = self._flat[off:off + p.numel()].view_as(p)
@@ -74,7 +113,18 @@ class DataParallelTrainer(Trainer):
         if self.world == 1:
             return vals
         self._flat[self._n_grad:] = vals.to(self._flat.dtype)
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
-        if self.shard == "batch":
-            self._flat.div_(self.world)
+        scale = 1.0 / self.world if self.shard == "batch" else 1.0
+        if self._p2p is not None:
+            # ONE kernel per rank over NVLink peer memory: signal, read every peer's buffer, sum, scale, write back
+            from . import _lib
+
+            hdl, epoch = self._p2p
+            _lib.check(_lib.lib().fsweep_allreduce_p2p(hdl.buffer_ptrs_dev, hdl.signal_pad_ptrs_dev, hdl.rank,
+                                                        hdl.world_size, self._flat.numel(), scale, epoch.data_ptr(),
+                                                        torch.cuda.current_stream(self._flat.device).cuda_stream))
+            sweep.launch_count += 1
+        else:
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
+            if self.shard == "batch":
+                self._flat.div_(self.world)
         return self._flat[self._n_grad:].to(vals.dtype)

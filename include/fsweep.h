@@ -217,6 +217,17 @@ FSWEEP_API int fsweep_sparsity_backward(const void* A, const void* gloss, int n_
 FSWEEP_API int fsweep_weighted_total(const void* const* parts, const double* alphas, const double* scales, int n,
                                      int dtype, void* vals, void* stream);
 
+/* One-shot all-reduce (sum, then * scale) of a small float32 buffer that lives in symmetric / peer-mapped memory on
+ * every rank of one node — the single exchange of a multi-GPU training step (flamo has no multi-device path; this
+ * replaces the NCCL all-reduce of flamo_b200/parallel.py).  peer_buffers / peer_signal_pads: DEVICE arrays of `world`
+ * device pointers (rank r's buffer / signal pad, as torch.distributed._symmetric_memory hands them out; the pads must
+ * be zero before the first call and at least 2 KiB).  epoch_counter: device uint32, zero before the first call, private
+ * to this communicator.  One kernel, in place, capture safe, bit-identical results on every rank.
+ * n <= fsweep_allreduce_p2p_max_n(). */
+FSWEEP_API int fsweep_allreduce_p2p_max_n(void);
+FSWEEP_API int fsweep_allreduce_p2p(void* const* peer_buffers, void* const* peer_signal_pads, int rank, int world, int n,
+                                    double scale, void* epoch_counter, void* stream);
+
 /* number of kernels the last forward / backward call of this thread enqueued (bench bookkeeping) */
 FSWEEP_API int fsweep_last_launch_count(void);
 
