@@ -68,3 +68,45 @@ def test_trainer_fused_criterion_equals_unfused(crit_kind):
         assert torch.allclose(a, b, rtol=1e-9, atol=1e-12)
     assert nf < nu  # the fused step makes fewer sweep launches (no forward sweep)
     assert np.allclose(list(trf.train_loss_log.values())[0], list(tru.train_loss_log.values())[0], rtol=1e-10)
+
+
+@pytest.mark.parametrize("n,scale", [(6, 1.0), (40, 1.0), (64, 4.0), (33, 1e-3)])
+def test_capture_safe_expm_matches_matrix_exp(n, scale):
+    """functional.expm_capturable (the orthogonal map of matrices wider than the one-CTA device kernel) against
+    torch.matrix_exp and its autograd, float64 and float32 inputs."""
+    from flamo_b200.functional import expm_capturable, skew_matrix
+
+    torch.manual_seed(n)
+    P = (torch.randn(n, n, dtype=torch.float64) * scale).requires_grad_(True)
+    w = torch.randn(n, n, dtype=torch.float64)
+    E, R = expm_capturable(skew_matrix(P)), torch.matrix_exp(skew_matrix(P))
+    assert torch.allclose(E, R, rtol=1e-12, atol=1e-12)
+    (g1,) = torch.autograd.grad((E * w).sum(), P)
+    (g2,) = torch.autograd.grad((R * w).sum(), P)
+    assert float((g1 - g2).abs().max()) <= 1e-9 * float(g2.abs().max())
+    assert torch.allclose(E.T @ E, torch.eye(n, dtype=torch.float64), atol=1e-11)  # orthogonal
+    E32 = expm_capturable(skew_matrix(P.detach().float()))
+    assert E32.dtype == torch.float32 and torch.allclose(E32.double(), R.detach(), atol=5e-6)
+
+
+def test_pack_sections_matches_definition():
+    """sweep.pack_sections (one contraction with a constant 16 x 6 matrix) against the layout include/fsweep.h
+    defines: per section {B(w0), B'(w0), b2, 0, A(w0), A'(w0), a2, 0} for w0 = +1 and w0 = -1."""
+    from flamo_b200 import sweep
+
+    torch.manual_seed(0)
+    b, a = torch.randn(3, 2, 4, 3, dtype=torch.float64), torch.randn(3, 2, 4, 3, dtype=torch.float64)
+    p = sweep.pack_sections(b, a, False, torch.float64)  # (K, N_in, N_out, 2, 8)
+    assert p.shape == (2, 3, 4, 2, 8)
+    for s in range(2):
+        for m in range(4):
+            for n in range(3):
+                for blk, sg in ((0, 1.0), (1, -1.0)):
+                    for off, t in ((0, b), (4, a)):
+                        c0, c1, c2 = (float(t[i, s, m, n]) for i in range(3))
+                        want = [c0 + sg * c1 + c2, c1 + 2 * sg * c2, c2, 0.0]
+                        got = p[s, n, m, blk, off:off + 4].tolist()
+                        assert np.allclose(got, want, rtol=1e-13, atol=1e-13)
+    pp = sweep.pack_sections(b[..., 0], a[..., 0], True, torch.float32)  # parallel: (K, N, 2, 8)
+    assert pp.shape == (2, 4, 2, 8) and pp.dtype == torch.float32
+    assert np.allclose(pp.double().numpy(), p[:, 0].numpy(), rtol=1e-6, atol=1e-6)
