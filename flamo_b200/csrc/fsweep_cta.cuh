@@ -147,10 +147,19 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
       __syncthreads();
       if (t == 0) sA[k * CLD + k] = inv;  // nobody reads the diagonal during the update
       {
+        // trailing update: thread (ty, tx) owns rows k+1+ty+16i and columns k+1+tx+16jj; its (up to four) pivot-row
+        // entries are loaded once per step
         const int ty = t >> 4, tx = t & 15;
+        const int j0 = k + 1 + tx;
+        float2 u[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) u[jj] = (j0 + 16 * jj < CN) ? sA[k * CLD + j0 + 16 * jj] : f2(0.f, 0.f);
         for (int r = k + 1 + ty; r < CN; r += 16) {
           const float2 l = sA[r * CLD + k];
-          for (int j = k + 1 + tx; j < CN; j += 16) sA[r * CLD + j] = cnma2(sA[r * CLD + j], l, sA[k * CLD + j]);
+          float2* row = sA + r * CLD + j0;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            if (j0 + 16 * jj < CN) row[16 * jj] = cnma2(row[16 * jj], l, u[jj]);
         }
       }
       __syncthreads();
