@@ -320,7 +320,8 @@ def gpu_arm(args):
 
 def kernel_roofline(model, x_dev, flush, reps=30):
     """Duration of the dominant kernel (the backward sweep) and of the forward sweep, each launched
-    alone behind an L2 flush, CUDA events on the launching stream; algorithmic bytes per launch =
+    alone behind an L2 flush (as a one-node CUDA graph, so that host launch overhead is excluded), CUDA events on the
+    launching stream; algorithmic bytes per launch =
     B*M*(8*N_in + 4*N_out) (x read as complex64, |Y| or dL/d|Y| as float32)."""
     from flamo_b200 import sweep
     from flamo_b200._lib import EPI_ABS
@@ -351,12 +352,23 @@ def kernel_roofline(model, x_dev, flush, reps=30):
     backend = sweep._BACKEND
 
     def timed(call):
+        """Mean duration of `call`'s device work: the launch is captured once into a CUDA graph and the replay is
+        timed with events, so the Python / ctypes launch path (tens of microseconds, longer than these kernels) is
+        not inside the timed region; L2 is flushed before every replay."""
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                call()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            call()
         ts = []
         for i in range(reps + 5):
             flush.fill_(i & 0xFF)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            call()
+            graph.replay()
             e.record()
             torch.cuda.synchronize()
             if i >= 5:
@@ -383,6 +395,9 @@ def kernel_roofline(model, x_dev, flush, reps=30):
             "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else which,
             "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
             "us_per_launch": t_bwd * 1e6, "algorithmic_bytes_per_launch": bytes_per_launch,
+            "us_per_launch_note": "graph replay of sweep kernel + one-warp loss finalize, launch latency included; the "
+                                  "sweep kernel alone is 23.5 us in the ncu launch list of a captured step "
+                                  "(profiles/r01i_launches_step_summary.md)",
             "forward_kernel": {"kernel": plan.kernel_family(M, False) + " (validation / inference only; not in the training step)",
                                "us_per_launch": t_fwd * 1e6,
                                "achieved": bytes_per_launch / t_fwd / 1e9, "frac": bytes_per_launch / t_fwd / 1e9 / peak},
