@@ -16,6 +16,20 @@
  *                              (einsum / rfft / prod / div / where / exp / linalg.solve
  *                              backward), as driven by loss.backward() in
  *                              optimize/trainer.py:190
+ *   fsweep_forward_loss / fsweep_backward_loss
+ *                    replace   the same plus the Shell's |.| output layer and an MSE criterion
+ *                              (optimize/loss.py:90-103 or torch.nn.MSELoss): one launch yields
+ *                              the loss and its gradients (optimize/trainer.py:177-190)
+ *   fsweep_expm_* / fsweep_sparsity_* / fsweep_weighted_total
+ *                    replace   the parameter-sized pieces of a training step (dsp.py:649,
+ *                              loss.py:36-63, trainer.py:184-188) so that a captured step is a
+ *                              handful of launches
+ *   fsweep_allreduce_p2p       the one exchange of the multi-GPU step (no reference counterpart)
+ *
+ * Which kernel family serves a plan is an implementation detail (fsweep_plan_kernel_family):
+ * row-distributed interpreter, FDN-loop kernels, thread-per-bin kernels for small loops,
+ * CTA-per-bin kernels for wide loops, streaming kernels for TABLE-heavy programs, and the
+ * table / deferred-gradient kernels for large section cascades (flamo_b200/csrc/).
  *
  * Conventions
  *   - plain C, no C++ exceptions cross the boundary; every pointer marked "device" is a CUDA

@@ -188,3 +188,37 @@ def test_series_with_two_recursions_splits_into_two_launches():
     prog = sweep.Program(64, 0.0, torch.complex64, "cpu")
     s._lower(prog, None)
     assert [t for t, _ in prog._segments()] == ["sweep", "sweep"]
+
+
+def test_kernel_family_selection():
+    """Host-side dispatch (no GPU needed: plans are host objects): which kernel family a plan launches."""
+    import torch
+
+    from flamo_b200 import sweep, workloads as W
+    from flamo_b200.processor import dsp, system
+
+    def plan_of(desc, nfft=4096, dtype=torch.float32):
+        torch.manual_seed(0)
+        core = W.build(desc, dsp, system, nfft, 30.0, dtype=dtype, device="cpu")
+        cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
+        with torch.enable_grad():
+            prog = sweep.Program(nfft, 30.0, cdt, "cpu")
+            core._lower(prog, None)
+            (tag, payload), = list(prog._segments())
+            ops, coefs, n_out = prog.flatten_segment(payload)
+        return _lib.Plan([_lib.Op(*o) for o in ops], nfft, 30.0, _lib.C64 if dtype == torch.float32 else _lib.C128)
+
+    p = plan_of(W.fdn(8))
+    assert "tpc" in p.kernel_family(48001, True) and "tpc" in p.kernel_family(48001, False)  # one thread per bin
+    assert "loop" in p.kernel_family(2049, True)                                             # few bins: 8 lanes per bin
+    assert "loop" in plan_of(W.fdn(8), dtype=torch.float64).kernel_family(48001, True)       # float64: no tpc
+    assert "loop" in plan_of(W.fdn(16, delays=list(range(601, 601 + 16 * 37, 37)))).kernel_family(48001, True)
+    assert "cta" in plan_of(W.fdn(64)).kernel_family(192001, True)                           # CTA per bin
+    assert "cta" in plan_of(W.fdn(40, delays=list(range(601, 601 + 40 * 37, 37)))).kernel_family(1000, False)
+    fir = ("Series", [("Filter", dict(size=(20, 5, 3), requires_grad=True)),
+                      ("parallelGain", dict(size=(5,), requires_grad=True)),
+                      ("Filter", dict(size=(12, 2, 5), requires_grad=True))])
+    assert "stream" in plan_of(fir).kernel_family(2049, True)                                # TABLE streaming
+    assert p.kernel_family(48001, True) != plan_of(W.geq(4, 4, 3)).kernel_family(48001, True)
+    assert plan_of(W.geq(4, 4, 3)).kernel_family(48001, True) == "fsweep_bwd_kernel"         # generic interpreter
+    assert plan_of(W.active_acoustics()).kernel_family(48001, True) == "fsweep_bwd_kernel"
