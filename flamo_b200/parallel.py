@@ -84,19 +84,20 @@ class DataParallelTrainer(Trainer):
         self._flat = self._p2p_buffer(total + n_vals, dt, ps[0].device)
         if self._flat is None:
             self._flat = torch.zeros(total + n_vals, dtype=dt, device=ps[0].device)
-        off = 0
-        for p in ps:
-            p.grad = self._flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self._ps = ps
         self._n_grad = total
 
+    # backward writes ordinary per-parameter gradients; ONE cat packs them (and the loss values) into the flat
+    # buffer right before the collective, and the parameters' .grad then become views of the reduced buffer
     def _zero_grad(self):
         if self._flat is None:
             self._setup_flat(self.n_loss + 1)
-        self._flat.zero_()
+        for p in self._ps:
+            p.grad = None
 
     def _zero_grad_captured(self):
-        self._flat.zero_()
+        for p in self._ps:
+            p.grad = None
 
     def _loss_vector(self, inputs, targets):
         if self.shard == "batch" or self.world == 1:
@@ -112,7 +113,13 @@ class DataParallelTrainer(Trainer):
     def _sync(self, vals):
         if self.world == 1:
             return vals
-        self._flat[self._n_grad:] = vals.to(self._flat.dtype)
+        dt = self._flat.dtype
+        pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(dt) for p in self._ps]
+        torch.cat(pieces + [vals.to(dt)], out=self._flat)
+        off = 0
+        for p in self._ps:
+            p.grad = self._flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
         scale = 1.0 / self.world if self.shard == "batch" else 1.0
         if self._p2p is not None:
             # ONE kernel per rank over NVLink peer memory: signal, read every peer's buffer, sum, scale, write back
