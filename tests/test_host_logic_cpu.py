@@ -110,3 +110,56 @@ def test_pack_sections_matches_definition():
     pp = sweep.pack_sections(b[..., 0], a[..., 0], True, torch.float32)  # parallel: (K, N, 2, 8)
     assert pp.shape == (2, 4, 2, 8) and pp.dtype == torch.float32
     assert np.allclose(pp.double().numpy(), p[:, 0].numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_trainer_chooses_fused_path_only_when_it_is_safe():
+    """The fused criterion is taken iff exactly ONE criterion consumes the prediction and it is an MSE; anything else
+    (two consumers, a custom criterion, fuse_criterion=False, a Shell without |.| output) evaluates the prediction."""
+    from flamo_b200 import workloads as W
+    from flamo_b200.optimize.loss import mse_loss, sparsity_loss
+    from flamo_b200.optimize.trainer import Trainer
+    from flamo_b200.processor import dsp, system
+
+    nfft, M = 256, 129
+
+    def shell(abs_out=True):
+        torch.manual_seed(3)
+        core = W.build(W.fdn(4, delays=[7, 11, 13, 17]), dsp, system, nfft, 30.0, dtype=torch.float64, device="cpu")
+        fn = (lambda x: torch.abs(x)) if abs_out else (lambda x: torch.abs(x) ** 2)
+        out = dsp.Transform(fn, dtype=torch.float64)
+        return system.Shell(core, dsp.FFT(nfft, dtype=torch.float64), out)
+
+    x = torch.zeros(1, nfft, 1, dtype=torch.float64)
+    x[:, 0] = 1
+    tgt = torch.ones(1, M, 1, dtype=torch.float64)
+
+    class Custom(torch.nn.Module):
+        def forward(self, y_pred, y_true):
+            return (y_pred - y_true).abs().mean()
+
+    def fused(tr):
+        est, done = tr._predict(x, tgt)
+        return est is None
+
+    t = Trainer(shell(), log=False, device="cpu")
+    t.register_criterion(mse_loss(nfft=nfft), 1)
+    t.register_criterion(sparsity_loss(), 0.2, requires_model=True)
+    assert fused(t)
+    t2 = Trainer(shell(), log=False, device="cpu")
+    t2.register_criterion(mse_loss(nfft=nfft), 1)
+    t2.register_criterion(Custom(), 1)  # a second consumer of the prediction
+    assert not fused(t2)
+    t3 = Trainer(shell(), log=False, device="cpu")
+    t3.register_criterion(Custom(), 1)  # not an MSE the kernels know
+    assert not fused(t3)
+    t4 = Trainer(shell(), log=False, device="cpu", fuse_criterion=False)
+    t4.register_criterion(mse_loss(nfft=nfft), 1)
+    assert not fused(t4)
+    t5 = Trainer(shell(abs_out=False), log=False, device="cpu")  # output layer is not |.|: declined, remembered
+    t5.register_criterion(mse_loss(nfft=nfft), 1)
+    assert not fused(t5) and len(t5._unfusable) == 1
+    # every variant still trains
+    for tr in (t, t2, t3, t4, t5):
+        a = tr.train_step((x, tgt))
+        b = tr.train_step((x, tgt))
+        assert np.isfinite(a) and np.isfinite(b)
