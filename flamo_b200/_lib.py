@@ -26,7 +26,7 @@ EXPORTS = [
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward",
     "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total",
-    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n",
+    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_adam_step",
 ]
 
 
@@ -44,6 +44,15 @@ class Criterion(C.Structure):
         ("kind", C.c_int32), ("reserved", C.c_int32), ("target", C.c_void_p), ("target_batch_stride", C.c_int64),
         ("scale", C.c_double), ("loss", C.c_void_p),
     ]
+
+
+class AdamTensor(C.Structure):
+    """fsweep_adam_tensor_t"""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("step", C.c_void_p), ("numel", C.c_int64)]
+
+
+ADAM_MAX_TENSORS = 32
 
 
 class SweepError(RuntimeError):
@@ -109,6 +118,8 @@ def lib():
     L.fsweep_allreduce_p2p_max_n.restype = i32
     L.fsweep_allreduce_p2p.restype = i32
     L.fsweep_allreduce_p2p.argtypes = [vp, vp, i32, i32, i32, C.c_double, vp, vp]
+    L.fsweep_adam_step.restype = i32
+    L.fsweep_adam_step.argtypes = [C.POINTER(AdamTensor), i32, i32, vp, C.c_double, C.c_double, C.c_double, vp]
     L.fsweep_weighted_total.restype = i32
     L.fsweep_weighted_total.argtypes = [C.POINTER(vp), C.POINTER(C.c_double), C.POINTER(C.c_double), i32, i32, vp, vp]
     _lib = L

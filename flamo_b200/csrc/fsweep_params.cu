@@ -384,3 +384,68 @@ extern "C" FSWEEP_API int fsweep_allreduce_p2p(void* const* peer_buffers, void* 
       (float)scale, reinterpret_cast<unsigned*>(epoch_counter));
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam's update, reference optimize/trainer.py:42: the Trainer's optimizer) for ALL parameters of a
+// model in ONE launch: one block per parameter tensor, its step counter in device memory (read, used, written back by
+// that block only), learning rate read from device memory (schedulers fill it in place).  torch's capturable fused
+// Adam is two launches (a foreach add on the step counters, then the update).
+//   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+namespace {
+struct AdamArgs {
+  fsweep_adam_tensor_t t[FSWEEP_ADAM_MAX_TENSORS];
+  int n;
+  double beta1, beta2, eps;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) adam_step_kernel(const __grid_constant__ AdamArgs a, const float* __restrict__ lr) {
+  const fsweep_adam_tensor_t& q = a.t[blockIdx.x];
+  __shared__ float s_step;
+  float* step = reinterpret_cast<float*>(q.step);
+  if (threadIdx.x == 0) s_step = *step + 1.0f;
+  __syncthreads();
+  const double t = (double)s_step;
+  const double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
+  const double step_size = (double)*lr / bc1, bc2_sqrt = sqrt(bc2);
+  T* p = reinterpret_cast<T*>(q.param);
+  const T* g = reinterpret_cast<const T*>(q.grad);
+  T* m = reinterpret_cast<T*>(q.exp_avg);
+  T* v = reinterpret_cast<T*>(q.exp_avg_sq);
+  const T b1 = (T)a.beta1, b2 = (T)a.beta2;
+  for (long long i = threadIdx.x; i < q.numel; i += blockDim.x) {
+    const T gi = g[i];
+    const T mi = m[i] + (gi - m[i]) * (T(1) - b1);      // lerp, as torch does
+    const T vi = b2 * v[i] + (T(1) - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const T denom = (T)(sqrt((double)vi) / bc2_sqrt) + (T)a.eps;
+    p[i] = p[i] - (T)step_size * (mi / denom);
+  }
+  if (threadIdx.x == 0) *step = s_step;
+}
+}  // namespace
+
+extern "C" FSWEEP_API int fsweep_adam_step(const fsweep_adam_tensor_t* tensors, int n, int dtype, const void* lr,
+                                           double beta1, double beta2, double eps, void* stream) {
+  if (!tensors || !lr || n < 1 || n > FSWEEP_ADAM_MAX_TENSORS) return FSWEEP_E_BADARG;
+  AdamArgs a;
+  a.n = n;
+  a.beta1 = beta1;
+  a.beta2 = beta2;
+  a.eps = eps;
+  for (int i = 0; i < n; ++i) {
+    if (!tensors[i].param || !tensors[i].grad || !tensors[i].exp_avg || !tensors[i].exp_avg_sq || !tensors[i].step ||
+        tensors[i].numel < 1)
+      return FSWEEP_E_BADARG;
+    a.t[i] = tensors[i];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSWEEP_C64)
+    adam_step_kernel<float><<<n, 256, 0, st>>>(a, (const float*)lr);
+  else if (dtype == FSWEEP_C128)
+    adam_step_kernel<double><<<n, 256, 0, st>>>(a, (const float*)lr);
+  else
+    return FSWEEP_E_BADARG;
+  return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}

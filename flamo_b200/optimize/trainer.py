@@ -40,10 +40,17 @@ class Trainer:
         self.use_graph = on_cuda if graph is None else (graph and on_cuda)
         params = list(self.net.parameters())
         if self.use_graph:
-            # capturable Adam keeps `step` and `lr` on the device so a captured step can be replayed
-            # and `fused` folds the whole update into one multi-tensor kernel (same arithmetic)
-            self.optimizer = torch.optim.Adam(params, lr=torch.tensor(float(lr), device=device, dtype=torch.float32),
-                                              capturable=True, fused=True)
+            # a captured step needs `step` and `lr` on the device: torch's capturable fused Adam (two launches: a
+            # foreach add on the step counters, then the multi-tensor update).  FLAMO_B200_SWEEP_ADAM=1 selects
+            # optimize/adam.py instead (the update of ALL parameters as one libfsweep launch, same arithmetic) —
+            # opt-in until tests/test_gpu_adam.py has been run on a B200
+            from .adam import SweepAdam
+
+            lr_t = torch.tensor(float(lr), device=device, dtype=torch.float32)
+            if os.environ.get("FLAMO_B200_SWEEP_ADAM", "0") == "1" and SweepAdam.supported(params):
+                self.optimizer = SweepAdam([p for p in params], lr=lr_t)
+            else:
+                self.optimizer = torch.optim.Adam(params, lr=lr_t, capturable=True, fused=True)
         else:
             self.optimizer = torch.optim.Adam(params, lr=self.lr)
         self.n_loss = 0

@@ -231,6 +231,22 @@ FSWEEP_API int fsweep_sparsity_backward(const void* A, const void* gloss, int n_
 FSWEEP_API int fsweep_weighted_total(const void* const* parts, const double* alphas, const double* scales, int n,
                                      int dtype, void* vals, void* stream);
 
+/* torch.optim.Adam's update (the Trainer's optimizer, reference optimize/trainer.py:42; no weight decay, no amsgrad)
+ * for up to FSWEEP_ADAM_MAX_TENSORS parameter tensors in ONE launch.  All pointers are device pointers; param / grad /
+ * exp_avg / exp_avg_sq are real[numel] (float for FSWEEP_C64, double for FSWEEP_C128), step is a float32[1] counter
+ * private to the tensor (incremented by the call), lr a float32[1].  Capture safe. */
+#define FSWEEP_ADAM_MAX_TENSORS 32
+typedef struct fsweep_adam_tensor {
+  void* param;
+  const void* grad;
+  void* exp_avg;
+  void* exp_avg_sq;
+  void* step;
+  int64_t numel;
+} fsweep_adam_tensor_t;
+FSWEEP_API int fsweep_adam_step(const fsweep_adam_tensor_t* tensors, int n, int dtype, const void* lr, double beta1,
+                                double beta2, double eps, void* stream);
+
 /* One-shot all-reduce (sum, then * scale) of a small float32 buffer that lives in symmetric / peer-mapped memory on
  * every rank of one node — the single exchange of a multi-GPU training step (flamo has no multi-device path; this
  * replaces the NCCL all-reduce of flamo_b200/parallel.py).  peer_buffers / peer_signal_pads: DEVICE arrays of `world`
