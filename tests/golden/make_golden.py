@@ -126,6 +126,49 @@ def checkpoints():
     print("checkpoint keys:", sorted({k.split('|')[2] for k in out}))
 
 
+def checkpoint_responses():
+    """SURVEY §8c fixtures: every shipped checkpoint (notebooks/output/ex_fdn: 20 epochs of the 6-line colourless FDN,
+    notebooks/e8_colorless_fdn.ipynb, nfft = 2**16, alias 30 dB; notebooks/output/ex_biquad: 8 epochs of the 2-section
+    1 -> 2 bandpass Biquad, notebooks/e7_biquad.ipynb, alias 0 dB) is loaded into the reference model (float64 modules)
+    and the reference's Shell.get_freq_response / get_time_response (system.py:1012-1153) are recorded."""
+    base = "/root/reference/notebooks/output"
+    nfft = 2 ** 16
+    M = nfft // 2 + 1
+    bins = C.select_bins(M)
+    taps = np.unique(np.concatenate([np.arange(0, 2200), np.arange(2200, nfft, 499)]))
+    out = {"bins": bins, "taps": taps}
+
+    def shell(core):
+        return rsystem.Shell(core=core, input_layer=rdsp.FFT(nfft, dtype=torch.float64),
+                             output_layer=rdsp.Transform(lambda x: torch.abs(x), dtype=torch.float64))
+
+    fdn = shell(W.build(W.fdn(6), rdsp, rsystem, nfft, 30, dtype=torch.float64))
+    bq = shell(W.build(W.biquad(2, 1, 2, "bandpass"), rdsp, rsystem, nfft, 0, dtype=torch.float64))
+    for tag, model, sub, n in (("fdn", fdn, "ex_fdn", 20), ("biquad", bq, "ex_biquad", 8)):
+        for e in range(n):
+            sd = torch.load(os.path.join(base, sub, "checkpoints", f"model_e{e}.pt"), map_location="cpu",
+                            weights_only=True)
+            model.load_state_dict(sd)
+            for i, q in enumerate(model.parameters()):
+                out[f"{tag}|e{e}|param_{i}"] = q.detach().numpy().copy()  # copy: load_state_dict writes in place
+            H = model.get_freq_response(identity=False)
+            assert H.shape[:2] == (1, M)
+            out[f"{tag}|e{e}|H"] = H[0, bins].numpy()
+            if e in (0, n - 1):  # impulse responses of the first and the last epoch only (size)
+                h = model.get_time_response(identity=False)
+                assert h.shape[:2] == (1, nfft)
+                out[f"{tag}|e{e}|h"] = h[0, taps].numpy()
+            out[f"{tag}|e{e}|mag"] = model(signal_impulse(nfft, model.input_channels))[0, bins].detach().numpy()
+        print(f"checkpoint responses: {tag} x {n}")
+    np.savez_compressed(os.path.join(HERE, "reference_checkpoint_responses.npz"), **out)
+
+
+def signal_impulse(nfft, n):
+    x = torch.zeros(1, nfft, n, dtype=torch.float64)
+    x[:, 0, :] = 1
+    return x
+
+
 def train_trace():
     """Three Trainer.train_step calls of the reference on a reduced config 2 (N=8, nfft=4096),
     float64, Adam lr=1e-3, mse_loss + 0.2*sparsity_loss (examples/e8_colorless_fdn.py:128-138)."""
@@ -162,6 +205,9 @@ def train_trace():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
+    if only == ["checkpoint_responses"]:
+        checkpoint_responses()
+        sys.exit(0)
     worst = 0.0
     for name, case in C.CASES.items():
         if only and name not in only:
@@ -170,4 +216,5 @@ if __name__ == "__main__":
     if not only:
         probe_kat()
         checkpoints()
+        checkpoint_responses()
         train_trace()

@@ -163,3 +163,13 @@ def test_trainer_chooses_fused_path_only_when_it_is_safe():
         a = tr.train_step((x, tgt))
         b = tr.train_step((x, tgt))
         assert np.isfinite(a) and np.isfinite(b)
+
+
+@pytest.mark.parametrize("tag,epoch", [("fdn", 0), ("fdn", 19), ("biquad", 0), ("biquad", 7)])
+def test_shipped_checkpoints_load_and_respond(tag, epoch):
+    """SURVEY §8c fixtures through the host side (load_state_dict with the reference's keys, Shell.get_freq_response /
+    get_time_response layer swapping) and the ABI emulator; all 28 checkpoints run on the GPU
+    (tests/test_gpu_zz_checkpoints.py)."""
+    from helpers import check_checkpoint
+
+    check_checkpoint(tag, epoch, torch.float64, "cpu", tol_mag=1e-9, tol_resp=1e-9)

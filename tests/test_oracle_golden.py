@@ -113,3 +113,38 @@ def test_train_trace():
     assert np.allclose(losses, g["losses"], rtol=1e-10, atol=0)
     for i, p in enumerate(params):
         assert np.allclose(p.detach().numpy(), g[f"param3_{i}"], rtol=1e-9, atol=1e-12)
+
+
+CHECKPOINTS = [("fdn", e) for e in range(20)] + [("biquad", e) for e in range(8)]
+
+
+def checkpoint_model(tag):
+    """(description, nfft, alias, n_in) of the two notebook models whose checkpoints the reference ships."""
+    from flamo_b200 import workloads as W
+
+    return (W.fdn(6), 2 ** 16, 30.0, 1) if tag == "fdn" else (W.biquad(2, 1, 2, "bandpass"), 2 ** 16, 0.0, 1)
+
+
+@pytest.mark.parametrize("tag,epoch", CHECKPOINTS)
+def test_shipped_checkpoint_responses(tag, epoch):
+    """SURVEY §8c fixtures: the reference's get_freq_response / get_time_response / forward of every checkpoint under
+    notebooks/output (recorded by make_golden.checkpoint_responses) reproduced by the oracle."""
+    g = load("reference_checkpoint_responses")
+    desc, nfft, alias, n_in = checkpoint_model(tag)
+    node = O.from_desc(desc)
+    params, i = [], 0
+    while f"{tag}|e{epoch}|param_{i}" in g:
+        params.append(torch.tensor(g[f"{tag}|e{epoch}|param_{i}"]))
+        i += 1
+    with torch.no_grad():
+        H = O.freq_response(node, params, nfft, alias, n_in)[0, g["bins"]].numpy()
+        ref = g[f"{tag}|e{epoch}|H"]
+        assert np.abs(H - ref).max() <= 1e-10 * np.abs(ref).max()
+        x = torch.zeros(1, nfft, n_in, dtype=torch.float64)
+        x[:, 0, :] = 1
+        mag = O.shell_forward(node, x, params, nfft, alias)[0, g["bins"]].numpy()
+        assert rel_err(mag, g[f"{tag}|e{epoch}|mag"]) < 1e-11
+        if f"{tag}|e{epoch}|h" in g:
+            h = O.time_response(node, params, nfft, alias, n_in)[0, g["taps"]].numpy()
+            ref = g[f"{tag}|e{epoch}|h"]
+            assert np.abs(h - ref).max() <= 1e-11 * np.abs(ref).max()
