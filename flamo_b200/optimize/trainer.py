@@ -42,8 +42,8 @@ class Trainer:
         if self.use_graph:
             # a captured step needs `step` and `lr` on the device: torch's capturable fused Adam (two launches: a
             # foreach add on the step counters, then the multi-tensor update).  FLAMO_B200_SWEEP_ADAM=1 selects
-            # optimize/adam.py instead (the update of ALL parameters as one libfsweep launch, same arithmetic) —
-            # opt-in until tests/test_gpu_adam.py has been run on a B200
+            # optimize/adam.py instead (the update of ALL parameters as one libfsweep launch, same arithmetic,
+            # tests/test_gpu_adam.py) — opt-in because it measured neutral on the step time (profiles/r01_notes.md)
             from .adam import SweepAdam
 
             lr_t = torch.tensor(float(lr), device=device, dtype=torch.float32)
