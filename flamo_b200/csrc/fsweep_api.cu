@@ -967,7 +967,14 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     }
     // 4 warps per block, 1 warp per element; row n_ops of the grid sums the fused criterion's loss
     dim3 grid((unsigned)std::min(1024, (max_total + 3) / 4), (unsigned)P.n_ops + (crit ? 1u : 0u));
-    if (dtype == FSWEEP_C64)
+    const char* v2 = getenv("FSWEEP_FINALIZE_V2");  // experimental coalesced variant, off unless asked for
+    if (v2 && v2[0] == '1') {
+      dim3 grid2((unsigned)std::min(256, (max_total + 31) / 32), grid.y);
+      if (dtype == FSWEEP_C64)
+        fsweep_finalize_v2_kernel<float><<<grid2, 32 * FIN2_WARPS, 0, st>>>(F);
+      else
+        fsweep_finalize_v2_kernel<double><<<grid2, 32 * FIN2_WARPS, 0, st>>>(F);
+    } else if (dtype == FSWEEP_C64)
       fsweep_finalize_kernel<float><<<grid, 128, 0, st>>>(F);
     else
       fsweep_finalize_kernel<double><<<grid, 128, 0, st>>>(F);

@@ -1288,6 +1288,81 @@ __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_const
   }
 }
 
+// EXPERIMENTAL (FSWEEP_FINALIZE_V2=1, not the default: written after the round's GPU budget was spent, never run).
+// Same sums as fsweep_finalize_kernel with coalesced reads: the 32 lanes of a warp own 32 CONSECUTIVE accumulators of
+// one partial row (row index fastest, which is how the rows are laid out), the block's warps split the per-block rows,
+// and the cross-warp sum runs in a fixed order through shared memory (deterministic).  The first version gives every
+// lane of a warp a different block's row: n_blocks scattered 4-byte loads per gradient element.
+constexpr int FIN2_WARPS = 16;
+
+template <typename T>
+__device__ __forceinline__ void finalize_store(const FinalizeOp& op, int row, int i, double s) {
+  const bool diag = !(op.kind == FSWEEP_OP_GAIN || op.kind == FSWEEP_OP_SOS || op.kind == FSWEEP_OP_DELAY);
+  size_t o;
+  if (op.kind == FSWEEP_OP_SOS || op.kind == FSWEEP_OP_PSOS) {
+    const int slot = i & 15, sn = i >> 4;  // i = (section [* n_in + n]) * 16 + slot
+    o = ((size_t)sn * op.n_out + row) * 16 + slot;
+  } else if (diag) {
+    o = row;
+  } else {
+    o = (size_t)row * op.n_in + i;
+  }
+  if (op.kind == FSWEEP_OP_DELAY || op.kind == FSWEEP_OP_PDELAY)
+    reinterpret_cast<double*>(op.grad)[o] = s;
+  else
+    reinterpret_cast<T*>(op.grad)[o] = (T)s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * FIN2_WARPS) fsweep_finalize_v2_kernel(const __grid_constant__ FinalizeArgs F) {
+  __shared__ double red[FIN2_WARPS][33];
+  const int opi = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (opi == F.n_ops) {  // fused criterion: sum of the per-block squared-error sums
+    if (F.loss == nullptr || blockIdx.x != 0) return;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < F.n_blocks; b += 32 * FIN2_WARPS) s += F.loss_partial[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp][0] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < FIN2_WARPS; ++w) t += red[w][0];
+      *reinterpret_cast<T*>(F.loss) = (T)(F.crit_scale * t);
+    }
+    return;
+  }
+  const FinalizeOp& op = F.ops[opi];
+  if (op.grad == nullptr || (op.acc_mode != ACC_SMEM && op.acc_mode != ACC_GLOBAL)) return;  // uniform in the block
+  const int total = op.n_out * op.row_len;
+  const size_t stride = (size_t)F.acc_per_lane * F.G;
+  for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {  // uniform trip count
+    const int e = base + lane;  // e = i * n_out + row: consecutive lanes, consecutive rows of accumulator i
+    const bool live = e < total;
+    const int i = live ? e / op.n_out : 0, row = live ? e - i * op.n_out : 0;
+    double s = 0.0;
+    if (op.acc_mode == ACC_SMEM) {
+      if (live) {
+        const T* p = reinterpret_cast<const T*>(F.partial) + (size_t)(op.row_off + i) * F.G + row;
+#pragma unroll 4
+        for (int b = warp; b < F.n_blocks; b += FIN2_WARPS) s += (double)p[(size_t)b * stride];
+      }
+      red[warp][lane] = s;
+      __syncthreads();
+      if (warp == 0) {
+        s = 0.0;
+#pragma unroll
+        for (int w = 0; w < FIN2_WARPS; ++w) s += red[w][lane];
+      }
+      __syncthreads();  // red is reused by the next trip
+    } else if (live) {
+      s = (double)reinterpret_cast<const T*>(F.gacc)[op.acc_off + (size_t)row * op.row_len + i];
+    }
+    if (warp == 0 && live) finalize_store<T>(op, row, i, s);
+  }
+}
+
 // ------------------------------------------------------------------------------------ deferred SOS gradients
 // Coefficient gradient of a section-cascade op whose accumulators do not fit shared memory (e.g. the 16 x 16 x 30
 // sections of BASELINE config 3: 122 880 accumulators).  The backward kernel parked S_in and g_out per (column,
