@@ -100,6 +100,21 @@ def _chain_io(modules):
     return first_in, prev_out
 
 
+def _entry_check(module, x):
+    """check_input_shape of the FIRST leaf the signal meets (a Series hands it to its first module, a Recursion to its
+    feedforward path): the reference raises there (dsp.py:441-444, 880-883), before anything is evaluated."""
+    while module is not None:
+        if hasattr(module, "check_input_shape"):
+            module.check_input_shape(x)
+            return
+        if isinstance(module, Series):
+            module = module[0] if len(module) else None
+        elif isinstance(module, Recursion):
+            module = module.feedforward
+        else:
+            return
+
+
 def _alias_of(module) -> float:
     a = getattr(module, "_alias_db", None)
     if a is None:
@@ -165,10 +180,7 @@ class Series(nn.Sequential):
                 else:
                     input = module(input)
             return input
-        for m in self:
-            if hasattr(m, "check_input_shape"):
-                m.check_input_shape(input)
-                break
+        _entry_check(self, input)
         prog = sweep.Program(self.nfft, self._alias_db, input.dtype, input.device)
         self._lower(prog, ext_param)
         return prog.run(input)
@@ -265,6 +277,7 @@ class Recursion(nn.Module):
         prog.recursion(lambda: self.feedforward._lower(prog, ext_ff), lambda: self.feedback._lower(prog, ext_fb))
 
     def forward(self, X, ext_param=None):
+        _entry_check(self, X)
         prog = sweep.Program(self.nfft, self._alias_db, X.dtype, X.device)
         self._lower(prog, ext_param)
         return prog.run(X)
@@ -446,8 +459,7 @@ class Shell(nn.Module):
         X = self.__input_layer(x)
         prog = None
         if hasattr(core, "_lower") and torch.is_tensor(X) and X.is_complex():
-            if hasattr(core, "check_input_shape"):
-                core.check_input_shape(X)
+            _entry_check(core, X)
             prog = sweep.Program(self.nfft, _alias_of(core), X.dtype, X.device)
             core._lower(prog, ext_param)
         return X, prog

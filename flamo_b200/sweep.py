@@ -290,6 +290,16 @@ class Program:
         cdtype = cdtype or self.cdtype
         return _get_plan(ops, self.nfft, self.alias_decay_db, _lib.C64 if cdtype == torch.complex64 else _lib.C128)
 
+    def _check_signal(self, ops, x4, bin_begin):
+        """Backstop in front of every launch (the kernels trust the plan's widths): the signal must carry the channels
+        the program's first op reads and only bins that exist."""
+        if x4.shape[2] != ops[0][2]:
+            raise ValueError(f"the sweep program expects {ops[0][2]} input channels, got a signal of shape "
+                             f"{tuple(x4.shape)} (batch, bins, channels, columns)")
+        if bin_begin < 0 or bin_begin + x4.shape[1] > self.nfft // 2 + 1:
+            raise ValueError(f"bins [{bin_begin}, {bin_begin + x4.shape[1]}) outside the {self.nfft // 2 + 1} bins of "
+                             f"nfft = {self.nfft}")
+
     def run(self, x: torch.Tensor, epilogue: int = EPI_NONE) -> torch.Tensor:
         if not x.is_complex():
             raise TypeError("sweep input must be complex (bin-domain) — put a dsp.FFT input layer in front")
@@ -317,6 +327,7 @@ class Program:
                 x4 = payload(x4.reshape(x4.shape[:3] + trail)).reshape(x4.shape[0], x4.shape[1], -1, cols)
                 continue
             ops, coefs, n_out = self.flatten_segment(payload)
+            self._check_signal(ops, x4, bin_begin)
             epi = epilogue if si == len(segs) - 1 else EPI_NONE
             plan = _get_plan(ops, self.nfft, self.alias_decay_db, dtype)
             x4 = SweepFunction.apply(x4, plan, ops, epi, bin_begin, n_out, *coefs)
@@ -359,8 +370,8 @@ class Program:
             bin_begin = shard[0]
             x4, tgt = x4[:, shard[0]:shard[1]], tgt[:, shard[0]:shard[1]]
             scale = 1.0 / tgt.numel()  # mean over the shard, as the unfused path computes it
-        if x4.shape[1] == 0:
-            return None
+        if x4.shape[1] == 0 or x4.shape[2] != ops[0][2] or bin_begin + x4.shape[1] > self.nfft // 2 + 1:
+            return None  # (the unfused path raises the proper error)
         plan = _get_plan(ops, self.nfft, self.alias_decay_db, _lib.C64 if x.dtype == torch.complex64 else _lib.C128)
         return SweepLossFunction.apply(x4, tgt, plan, ops, kind, scale, bin_begin, *coefs)
 

@@ -173,3 +173,27 @@ def test_shipped_checkpoints_load_and_respond(tag, epoch):
     from helpers import check_checkpoint
 
     check_checkpoint(tag, epoch, torch.float64, "cpu", tol_mag=1e-9, tol_resp=1e-9)
+
+
+def test_entry_shape_check_follows_the_first_leaf():
+    """Found by tests/test_random_trees_cpu.py: a Series that STARTS with a Recursion checked the input against the
+    next module that owns check_input_shape (a later one, with other widths).  The check belongs to the first leaf the
+    signal meets; wrong widths are rejected before any launch, also for a bare Recursion."""
+    from flamo_b200.processor import dsp, system
+
+    kw = dict(nfft=64, dtype=torch.float64)
+    rec = system.Recursion(fF=dsp.Gain(size=(2, 1), **kw),
+                           fB=system.Series(dsp.Gain(size=(1, 2), **kw), dsp.parallelGain(size=(1,), **kw)))
+    rec.feedback[1].assign_value(torch.tensor([0.02], dtype=torch.float64))
+    s = system.Series(rec, dsp.Delay(size=(1, 2), max_len=5, **kw))
+    X = C.make_input(1, 33, 1, None)
+    assert s(X).shape == (1, 33, 1)
+    with pytest.raises(ValueError):
+        s(C.make_input(1, 33, 2, None))      # the Recursion's feedforward Gain reads ONE channel
+    with pytest.raises(ValueError):
+        rec(C.make_input(1, 33, 3, None))
+    with pytest.raises(ValueError):
+        rec(C.make_input(1, 40, 1, None))    # more bins than nfft // 2 + 1
+    shell = system.Shell(s)
+    with pytest.raises(ValueError):
+        shell(C.make_input(1, 33, 2, None))

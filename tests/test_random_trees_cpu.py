@@ -1,0 +1,132 @@
+"""CPU: randomly composed module trees (hypothesis) through this package's host side (constructors, maps, lowering,
+coefficient packing, autograd seams; float64, ABI emulator) against the oracle on the same raw parameters — forward
+response and every parameter gradient.  Complements the fixed case list of tests/cases.py with compositions nobody
+wrote down: nested Series inside Recursion paths, rectangular loops, trailing columns, mixed filter kinds."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import cases as C
+from flamo_b200 import workloads as W
+from flamo_b200.processor import dsp, system
+from helpers import grad_err, rel_err
+from oracle import flamo_oracle as O
+
+pytestmark = pytest.mark.usefixtures("emulated_backend")
+FS = W.FS
+NFFT = 256
+
+
+@st.composite
+def leaf(draw, n_in, n_out=None, allow_delay=True):
+    """One dsp module description with n_in inputs (and n_out outputs if given, else drawn)."""
+    square = n_out is not None and n_out == n_in
+    kinds = ["Gain", "Biquad", "SVF", "GEQ", "Filter", "GainDelay"]
+    if allow_delay:
+        kinds.append("Delay")
+    if n_out is None or square:
+        kinds += ["parallelGain", "parallelBiquad", "parallelSVF", "parallelFilter", "parallelGainDelay"]
+        if allow_delay:
+            kinds.append("parallelDelay")
+        if n_in > 1:
+            kinds += ["Matrix", "HouseholderMatrix"]
+    kind = draw(st.sampled_from(kinds))
+    rg = draw(st.booleans()) or kind in ("Gain", "parallelGain")
+    if kind.startswith("parallel") or kind in ("Matrix", "HouseholderMatrix"):
+        m = n_in
+    else:
+        m = n_out if n_out is not None else draw(st.integers(1, 4))
+    size = (m,) if kind.startswith("parallel") else (m, n_in)
+    kw = dict(size=size, requires_grad=rg)
+    if kind in ("Biquad", "parallelBiquad"):
+        kw.update(n_sections=draw(st.integers(1, 3)), filter_type=draw(st.sampled_from(["lowpass", "highpass", "bandpass"])),
+                  fs=FS)
+    elif kind in ("SVF", "parallelSVF"):
+        kw.update(n_sections=draw(st.integers(1, 2)), fs=FS,
+                  filter_type=draw(st.sampled_from([None, "lowpass", "highpass", "bandpass", "lowshelf", "highshelf",
+                                                    "peaking", "notch"])))
+    elif kind == "GEQ":
+        kw.update(octave_interval=1, fs=FS)
+    elif kind in ("Filter", "parallelFilter"):
+        kw["size"] = (draw(st.integers(1, 9)),) + size
+    elif kind in ("Delay", "parallelDelay", "GainDelay", "parallelGainDelay"):
+        kw.update(max_len=draw(st.integers(5, 60)), isint=draw(st.booleans()), fs=FS)
+        if kw["isint"] and kind in ("Delay", "parallelDelay"):
+            kw["requires_grad"] = False
+    elif kind == "Matrix":
+        kw["matrix_type"] = draw(st.sampled_from(["orthogonal", "random"]))
+    elif kind == "HouseholderMatrix":
+        pass
+    return (kind, kw), m
+
+
+@st.composite
+def chain(draw, n_in, n_out=None, max_len=3, allow_delay=True):
+    n = draw(st.integers(1, max_len))
+    descs, cur = [], n_in
+    for j in range(n):
+        last = j == n - 1
+        d, cur = draw(leaf(cur, n_out if last else None, allow_delay))
+        descs.append(d)
+    if n_out is not None and cur != n_out:  # a diagonal / square kind came last: close with a Gain
+        descs.append(("Gain", dict(size=(n_out, cur), requires_grad=True)))
+        cur = n_out
+    return (descs[0] if len(descs) == 1 and draw(st.booleans()) else ("Series", descs)), cur
+
+
+@st.composite
+def tree(draw):
+    n_in = draw(st.integers(1, 3))
+    parts, cur = [], n_in
+    if draw(st.booleans()):
+        d, cur = draw(chain(cur, None, 2))
+        parts.append(d)
+    if draw(st.booleans()):
+        N = draw(st.integers(1, 5))
+        ff, _ = draw(chain(cur, N, 2))
+        fb, _ = draw(chain(N, cur, 2))
+        # keep the loop gain small so that I - F Fb is well conditioned whatever the random parameters are
+        damp = ("parallelGain", dict(size=(cur,), requires_grad=True), {"assign": [0.02] * cur})
+        fb = ("Series", (list(fb[1]) if fb[0] == "Series" else [fb]) + [damp])
+        parts.append(("Recursion", ff, fb))
+        cur = N
+    if draw(st.booleans()) or not parts:
+        d, cur = draw(chain(cur, None, 2))
+        parts.append(d)
+    desc = parts[0] if len(parts) == 1 and parts[0][0] != "Recursion" and draw(st.booleans()) else ("Series", parts)
+    return desc, n_in, draw(st.integers(1, 2)), draw(st.sampled_from([None, None, 2])), draw(st.integers(0, 10 ** 6)), \
+        draw(st.sampled_from([0.0, 30.0]))
+
+
+@settings(max_examples=250, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree())
+def test_random_tree_matches_oracle(t):
+    desc, n_in, B, cols, seed, alias = t
+    torch.manual_seed(seed)
+    model = W.build(desc, dsp, system, NFFT, alias, dtype=torch.float64, device="cpu")
+    assert model.input_channels == n_in
+    M = NFFT // 2 + 1
+    X = C.make_input(B, M, n_in, cols)
+    params = list(model.parameters())
+    Y = model(X)
+    ps = [p.detach().clone().requires_grad_(p.requires_grad) for p in params]
+    Yo = O.forward(O.from_desc(desc), X, ps, NFFT, alias)
+    assert Y.shape == Yo.shape
+    assert rel_err(Y.detach().numpy(), Yo.detach().numpy()) <= 1e-8, desc
+    gp = [p for p in ps if p.requires_grad]
+    if gp:
+        C.golden_loss(Y).backward()
+        go = torch.autograd.grad(C.golden_loss(Yo), gp, allow_unused=True)
+        k = 0
+        for p, q in zip(params, ps):
+            if not q.requires_grad:
+                continue
+            ref = go[k]
+            k += 1
+            if ref is None or float(ref.abs().max()) == 0.0:
+                assert p.grad is None or float(p.grad.abs().max()) <= 1e-12, desc
+                continue
+            assert p.grad is not None, desc
+            scale = max(float(g.abs().max()) for g in go if g is not None)
+            assert float((p.grad - ref).abs().max()) <= 1e-7 * scale, desc
