@@ -208,7 +208,12 @@ class DSP(nn.Module):
         return 2 * math.pi * torch.arange(0, self.nfft // 2 + 1, dtype=dtype, device=device) / self.nfft
 
     def _bins_ok(self, x):
-        return x.shape[1] == int(self.nfft / 2 + 1)
+        """All nfft // 2 + 1 bins — or, inside sweep.bin_shard, a signal an earlier launch of the same Series already
+        restricted to the shard (a Parallel node or any other eager module after the first sweep)."""
+        if x.shape[1] == int(self.nfft / 2 + 1):
+            return True
+        shard = sweep.current_shard()
+        return shard is not None and x.shape[1] == shard[1] - shard[0]
 
     def probe(self, z):
         raise NotImplementedError(f"probe() not implemented for {self.__class__.__name__}")
@@ -401,7 +406,7 @@ class Filter(DSP):
         assert len(self.size) == 3, "Filter must be 3D, for 2D (parallel) filters use ParallelFilter module."
 
     def check_input_shape(self, x):
-        if (int(self.nfft / 2 + 1), self.input_channels) != (x.shape[1], x.shape[2]):
+        if not self._bins_ok(x) or self.input_channels != x.shape[2]:
             raise ValueError(f"parameter shape not compatible with input signal of shape = ({x.shape}).")
 
     def get_io(self):
@@ -791,7 +796,7 @@ class Delay(DSP):
         assert len(self.size) == 2, "delay must be 2D, for 1D (parallel) delay use parallelDelay module."
 
     def check_input_shape(self, x):
-        if (int(self.nfft / 2 + 1), self.input_channels) != (x.shape[1], x.shape[2]):
+        if not self._bins_ok(x) or self.input_channels != x.shape[2]:
             raise ValueError(
                 f"parameter shape = {self.param.shape} not compatible with input signal of shape = ({x.shape}).")
 
@@ -881,7 +886,7 @@ class GainDelay(DSP):
         return delay / self.fs * self.unit
 
     def check_input_shape(self, x):
-        if (int(self.nfft / 2 + 1), self.input_channels) != (x.shape[1], x.shape[2]):
+        if not self._bins_ok(x) or self.input_channels != x.shape[2]:
             raise ValueError(
                 f"parameter shape = {self.param.shape} not compatible with input signal of shape = ({x.shape}).")
 

@@ -91,15 +91,28 @@ def tree(draw):
         fb = ("Series", (list(fb[1]) if fb[0] == "Series" else [fb]) + [damp])
         parts.append(("Recursion", ff, fb))
         cur = N
+    if draw(st.integers(0, 3)) == 0:  # a Parallel node: two branches on the same input, summed or concatenated
+        total = draw(st.booleans())
+        a, na = draw(chain(cur, None, 2))
+        b, nb = draw(chain(cur, na if total else None, 2))
+        parts.append(("Parallel", a, b, total))
+        cur = na if total else na + nb
+    if draw(st.integers(0, 4)) == 0:  # a second loop: the series splits into two launches
+        N = draw(st.integers(1, 3))
+        damp = ("parallelGain", dict(size=(cur,), requires_grad=True), {"assign": [0.03] * cur})
+        parts.append(("Recursion", ("Gain", dict(size=(N, cur), requires_grad=True)),
+                      ("Series", [("Gain", dict(size=(cur, N), requires_grad=True)), damp])))
+        cur = N
     if draw(st.booleans()) or not parts:
         d, cur = draw(chain(cur, None, 2))
         parts.append(d)
-    desc = parts[0] if len(parts) == 1 and parts[0][0] != "Recursion" and draw(st.booleans()) else ("Series", parts)
+    desc = parts[0] if len(parts) == 1 and parts[0][0] not in ("Recursion", "Parallel") and draw(st.booleans()) \
+        else ("Series", parts)
     return desc, n_in, draw(st.integers(1, 2)), draw(st.sampled_from([None, None, 2])), draw(st.integers(0, 10 ** 6)), \
         draw(st.sampled_from([0.0, 30.0]))
 
 
-@settings(max_examples=250, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
 @given(tree())
 def test_random_tree_matches_oracle(t):
     desc, n_in, B, cols, seed, alias = t
@@ -130,3 +143,25 @@ def test_random_tree_matches_oracle(t):
             assert p.grad is not None, desc
             scale = max(float(g.abs().max()) for g in go if g is not None)
             assert float((p.grad - ref).abs().max()) <= 1e-7 * scale, desc
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree(), st.integers(1, NFFT // 2 - 1))
+def test_random_tree_is_bin_shard_invariant(t, cut):
+    """Evaluating two bin ranges separately (what the bin-sharded multi-GPU step does) and concatenating
+    equals the full sweep, whatever the tree: launch boundaries (Parallel nodes, second loops) included."""
+    from flamo_b200 import sweep
+
+    desc, n_in, B, cols, seed, alias = t
+    torch.manual_seed(seed)
+    model = W.build(desc, dsp, system, NFFT, alias, dtype=torch.float64, device="cpu")
+    M = NFFT // 2 + 1
+    X = C.make_input(B, M, n_in, cols)
+    with torch.no_grad():
+        full = model(X)
+        with sweep.bin_shard(0, cut):
+            lo = model(X)
+        with sweep.bin_shard(cut, M):
+            hi = model(X)
+    assert lo.shape[1] == cut and hi.shape[1] == M - cut
+    assert torch.allclose(torch.cat((lo, hi), dim=1), full, rtol=1e-12, atol=1e-12 * float(full.abs().max()))
