@@ -165,3 +165,64 @@ def test_random_tree_is_bin_shard_invariant(t, cut):
             hi = model(X)
     assert lo.shape[1] == cut and hi.shape[1] == M - cut
     assert torch.allclose(torch.cat((lo, hi), dim=1), full, rtol=1e-12, atol=1e-12 * float(full.abs().max()))
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree(), st.sampled_from(["mse_loss", "MSELoss"]))
+def test_random_tree_trainer_fused_equals_unfused(t, crit_kind):
+    """Trainer.train_step on a random Shell(FFT, tree, |.|): the fused-criterion route (one backward_loss call, or its
+    fallback when the tree is more than one launch) takes exactly the steps of the unfused route."""
+    from flamo_b200.optimize.loss import mse_loss
+    from flamo_b200.optimize.trainer import Trainer
+
+    desc, n_in, B, cols, seed, alias = t
+    M = NFFT // 2 + 1
+
+    def run(fuse):
+        torch.manual_seed(seed)
+        core = W.build(desc, dsp, system, NFFT, alias, dtype=torch.float64, device="cpu")
+        model = system.Shell(core, dsp.FFT(NFFT, dtype=torch.float64),
+                             dsp.Transform(lambda x: torch.abs(x), dtype=torch.float64))
+        tr = Trainer(model, max_epochs=1, lr=1e-2, log=False, device="cpu", fuse_criterion=fuse)
+        n_out = core.output_channels
+        if crit_kind == "mse_loss":
+            tr.register_criterion(mse_loss(nfft=NFFT), 1)
+            tgt = torch.full((B, M, 1), 0.7, dtype=torch.float64)
+        else:
+            tr.register_criterion(torch.nn.MSELoss(), 0.5)
+            tgt = torch.full((B, M, n_out), 0.3, dtype=torch.float64)
+        x = torch.zeros(B, NFFT, n_in, dtype=torch.float64)
+        x[:, 0] = 1
+        x[:, 5] = -0.25
+        losses = [tr.train_step((x, tgt)) for _ in range(2)]
+        return losses, [p.detach().clone() for p in model.parameters()]
+
+    if not any(p.requires_grad for p in W.build(desc, dsp, system, NFFT, alias, dtype=torch.float64).parameters()):
+        return
+    lf, pf = run(True)
+    lu, pu = run(False)
+    assert np.allclose(lf, lu, rtol=1e-9, atol=1e-14), desc
+    for a, b in zip(pf, pu):
+        assert torch.allclose(a, b, rtol=1e-8, atol=1e-11), desc
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree())
+def test_random_tree_responses_match_oracle(t):
+    """Shell.get_time_response / get_freq_response (layer swapping, rising envelope; reference system.py:1012-1153) on
+    random trees against the oracle's restatement (itself pinned on the shipped checkpoints)."""
+    desc, n_in, B, cols, seed, alias = t
+    torch.manual_seed(seed)
+    core = W.build(desc, dsp, system, NFFT, alias, dtype=torch.float64, device="cpu")
+    out_layer = dsp.Transform(lambda x: torch.abs(x), dtype=torch.float64)
+    model = system.Shell(core, dsp.FFT(NFFT, dtype=torch.float64), out_layer)
+    ps = [p.detach().clone() for p in model.parameters()]
+    node = O.from_desc(desc)
+    with torch.no_grad():
+        h, H = model.get_time_response(), model.get_freq_response()
+        ho = O.time_response(node, ps, NFFT, alias, n_in)
+        Ho = O.freq_response(node, ps, NFFT, alias, n_in)
+    assert h.shape == ho.shape and H.shape == Ho.shape
+    assert float((h - ho).abs().max()) <= 1e-9 * float(ho.abs().max() + 1e-300)
+    assert float((H - Ho).abs().max()) <= 1e-9 * float(Ho.abs().max() + 1e-300)
+    assert model.get_outputLayer() is out_layer  # layers restored
