@@ -150,6 +150,10 @@ class SweepFunction(torch.autograd.Function):
             else:
                 grads.append(None)
         gx = torch.empty_like(x, memory_format=torch.contiguous_format) if need[0] else None
+        if gx is None and all(g is None for g in grads):
+            # nothing to compute: e.g. an external integer-delay tensor that requires grad (its gradient through
+            # `round` is zero; the reference returns zeros, autograd treats None the same way)
+            return (None,) * (6 + len(coefs))
         if nb > 0:
             launch_count += _BACKEND.backward(ctx.plan, ctx.ops, coefs, x, gy, grads, gx, cols, ctx.bin_begin,
                                               ctx.epilogue) or 0

@@ -95,3 +95,87 @@ def test_random_tree_matches_the_reference_itself(t):
                 continue
             assert b.grad is not None, desc
             assert float((b.grad - g).abs().max()) <= 1e-7 * scale, desc
+
+
+def _make_ext(ref_mod, rsystem, gen, p_use=0.6):
+    """Nested ext_param structure for a REFERENCE module tree (hyper-conditioning, reference dsp.py:415-432,
+    system.py:279-301, 397-411): tensors for leaves, {key: ...} for a Series, {"feedforward" / "feedback": ...} for a
+    Recursion, {"branchA" / "branchB": ...} for a Parallel.  New values = stored parameter + a small perturbation."""
+    if isinstance(ref_mod, rsystem.Series):
+        d = {}
+        for key, child in ref_mod._modules.items():
+            e = _make_ext(child, rsystem, gen, p_use)
+            if e is not None:
+                d[key] = e
+        return d or None
+    if isinstance(ref_mod, rsystem.Recursion):
+        d = {}
+        for name in ("feedforward", "feedback"):
+            e = _make_ext(getattr(ref_mod, name), rsystem, gen, p_use)
+            if e is not None:
+                d[name] = e
+        return d or None
+    if isinstance(ref_mod, rsystem.Parallel):
+        d = {}
+        for name in ("branchA", "branchB"):
+            e = _make_ext(getattr(ref_mod, name), rsystem, gen, p_use)
+            if e is not None:
+                d[name] = e
+        return d or None
+    if torch.rand((), generator=gen).item() > p_use:
+        return None
+    p = ref_mod.param.detach()
+    return (p + 0.01 * torch.randn(p.shape, generator=gen, dtype=p.dtype)).requires_grad_(True)
+
+
+def _ext_tensors(e, out):
+    if torch.is_tensor(e):
+        out.append(e)
+    elif e is not None:
+        for v in e.values():
+            _ext_tensors(v, out)
+    return out
+
+
+def _clone_ext(e):
+    if torch.is_tensor(e):
+        return e.detach().clone().requires_grad_(True)
+    return None if e is None else {k: _clone_ext(v) for k, v in e.items()}
+
+
+@settings(max_examples=80, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree())
+def test_random_tree_ext_param_routing_matches_the_reference(t):
+    rdsp, rsystem = reference_modules()
+    desc, n_in, B, cols, seed, alias = t
+    kinds = kinds_of(desc, set())
+    assume(not kinds & {"SVF", "parallelSVF", "GEQ", "parallelGEQ"})  # float32 internals: covered above
+    X = C.make_input(B, NFFT // 2 + 1, n_in, cols)
+    torch.manual_seed(seed)
+    try:
+        ref = W.build(desc, rdsp, rsystem, NFFT, alias, dtype=torch.float64)
+        ext_r = _make_ext(ref, rsystem, torch.Generator().manual_seed(seed))
+        assume(ext_r is not None)
+        Yr = ref(X, ext_r)
+    except Exception as e:
+        if isinstance(e, (AssertionError,)) and "Unsatisfied" in type(e).__name__:
+            raise
+        assume(False)
+    torch.manual_seed(seed)
+    model = W.build(desc, dsp, system, NFFT, alias, dtype=torch.float64, device="cpu")
+    ext_m = _clone_ext(ext_r)
+    Y = model(X, ext_m)
+    assert rel_err(Y.detach().numpy(), Yr.detach().numpy()) <= 1e-8, desc
+    for a, b in zip(ref.parameters(), model.parameters()):  # the external values were logged into the modules
+        assert torch.equal(a.detach(), b.detach()), desc
+    tr, tm = _ext_tensors(ext_r, []), _ext_tensors(ext_m, [])
+    gr = torch.autograd.grad(C.golden_loss(Yr), tr, allow_unused=True)
+    gm = torch.autograd.grad(C.golden_loss(Y), tm, allow_unused=True) if Y.requires_grad else [None] * len(tm)
+    assume(all(g is None or bool(torch.isfinite(g).all()) for g in gr))  # the reference's own gradient is NaN for some
+    # draws (clamped Biquad maps): nothing to compare with
+    scale = max([float(g.abs().max()) for g in gr if g is not None] + [1e-300])
+    for a, b in zip(gr, gm):
+        if a is None or float(a.abs().max()) == 0.0:
+            assert b is None or float(b.abs().max()) <= 1e-12 * scale, desc
+        else:
+            assert b is not None and float((a - b).abs().max()) <= 1e-7 * scale, desc
