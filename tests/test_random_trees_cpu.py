@@ -226,3 +226,24 @@ def test_random_tree_responses_match_oracle(t):
     assert float((h - ho).abs().max()) <= 1e-9 * float(ho.abs().max() + 1e-300)
     assert float((H - Ho).abs().max()) <= 1e-9 * float(Ho.abs().max() + 1e-300)
     assert model.get_outputLayer() is out_layer  # layers restored
+
+
+@settings(max_examples=100, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree())
+def test_random_tree_float32_modules_stay_within_the_float32_bar(t):
+    """float32 modules (the bench dtype): raw parameters, maps evaluated in float64 and cast once, coefficient
+    packing (Taylor blocks of the sections, float64 delays) — everything the host hands the float32 kernels — against
+    the float64 oracle on the same (float32-representable) parameters, at BASELINE.md's bar: 1e-4 relative on the
+    response, denominator floored at 1e-3 of the peak.  (The emulator computes in float64 from these float32
+    coefficients: what is measured is the error the HOST side contributes to the bar.)"""
+    desc, n_in, B, cols, seed, alias = t
+    torch.manual_seed(seed)
+    model = W.build(desc, dsp, system, NFFT, alias, dtype=torch.float32, device="cpu")
+    M = NFFT // 2 + 1
+    X = C.make_input(B, M, n_in, cols).to(torch.complex64)
+    with torch.no_grad():
+        Y = model(X)
+        ps = [p.detach().double() for p in model.parameters()]
+        Yo = O.forward(O.from_desc(desc), X.to(torch.complex128), ps, NFFT, alias)
+    assert Y.dtype == torch.complex64
+    assert rel_err(Y.numpy().astype(np.complex128), Yo.numpy()) <= 1e-4, desc

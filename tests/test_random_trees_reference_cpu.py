@@ -179,3 +179,49 @@ def test_random_tree_ext_param_routing_matches_the_reference(t):
             assert b is None or float(b.abs().max()) <= 1e-12 * scale, desc
         else:
             assert b is not None and float((a - b).abs().max()) <= 1e-7 * scale, desc
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree())
+def test_random_tree_train_steps_match_the_reference_trainer(t):
+    """Two Trainer.train_step calls (reference optimize/trainer.py:155-192: zero_grad, forward, weighted criteria,
+    backward, Adam) of the reference Trainer on the reference model vs this package's Trainer on its model."""
+    import numpy as np
+
+    rdsp, rsystem = reference_modules()
+    from flamo.optimize.loss import mse_loss as r_mse_loss
+    from flamo.optimize.trainer import Trainer as RTrainer
+
+    from flamo_b200.optimize.loss import mse_loss
+    from flamo_b200.optimize.trainer import Trainer
+
+    desc, n_in, B, cols, seed, alias = t
+    assume(not kinds_of(desc, set()) & {"SVF", "parallelSVF", "GEQ", "parallelGEQ"})
+    M = NFFT // 2 + 1
+    x = torch.zeros(B, NFFT, n_in, dtype=torch.float64)
+    x[:, 0] = 1
+    x[:, 7] = 0.5
+    tgt = torch.full((B, M, 1), 0.6, dtype=torch.float64)
+
+    def run(dsp_, system_, trainer_cls, crit):
+        torch.manual_seed(seed)
+        core = W.build(desc, dsp_, system_, NFFT, alias, dtype=torch.float64)
+        model = system_.Shell(core, dsp_.FFT(NFFT, dtype=torch.float64),
+                              dsp_.Transform(lambda v: torch.abs(v), dtype=torch.float64))
+        if not any(p.requires_grad for p in model.parameters()):
+            return None
+        tr = trainer_cls(model, max_epochs=1, lr=1e-2, log=False, device="cpu")
+        tr.register_criterion(crit, 1)
+        tr.train_loss_log = {crit.__class__.__name__: []}
+        losses = [tr.train_step((x, tgt)) for _ in range(2)]
+        return losses, [p.detach().clone() for p in model.parameters()]
+
+    try:
+        r = run(rdsp, rsystem, RTrainer, r_mse_loss(nfft=NFFT, device="cpu"))
+    except Exception:
+        assume(False)
+    assume(r is not None and all(np.isfinite(r[0])) and all(bool(torch.isfinite(p).all()) for p in r[1]))
+    m = run(dsp, system, Trainer, mse_loss(nfft=NFFT))
+    assert np.allclose(m[0], r[0], rtol=1e-8, atol=1e-13), desc
+    for a, b in zip(m[1], r[1]):
+        assert torch.allclose(a, b, rtol=1e-7, atol=1e-9), desc
