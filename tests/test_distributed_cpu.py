@@ -23,13 +23,34 @@ def _free_port():
     return p
 
 
-def _build(batch):
+FS = 48000
+# a tree with launch boundaries inside the Series: a loop, a Parallel node (eager sum of two launches), a second loop
+BOUNDARIES = ("Series", [
+    ("Gain", dict(size=(3, 1), requires_grad=True)),
+    ("Recursion", ("parallelDelay", dict(size=(3,), max_len=300, isint=True, requires_grad=False),
+                   {"delay_samples": [101, 157, 211]}),
+     ("Series", [("Gain", dict(size=(3, 3), requires_grad=True)),
+                 ("parallelGain", dict(size=(3,), requires_grad=True), {"assign": [0.1, 0.1, 0.1]})])),
+    ("Parallel",
+     ("Series", [("Biquad", dict(size=(2, 3), n_sections=1, filter_type="lowpass", fs=FS, requires_grad=True))]),
+     ("Series", [("Delay", dict(size=(2, 3), max_len=40, isint=False, fs=FS, requires_grad=True))]), True),
+    ("Recursion", ("Gain", dict(size=(2, 2), requires_grad=True)),
+     ("Series", [("parallelDelay", dict(size=(2,), max_len=50, isint=False, fs=FS, requires_grad=True)),
+                 ("parallelGain", dict(size=(2,), requires_grad=True), {"assign": [0.05, 0.05]})])),
+    ("Gain", dict(size=(1, 2), requires_grad=True)),
+])
+
+
+def _build(batch, kind="fdn"):
     from flamo_b200 import workloads as W
     from flamo_b200.optimize.loss import mse_loss, sparsity_loss
     from flamo_b200.processor import dsp, system
 
     torch.manual_seed(7)
-    core = W.build(W.fdn(N, delays=[101, 157, 211, 263]), dsp, system, NFFT, 30.0, dtype=torch.float64)
+    desc = W.fdn(N, delays=[101, 157, 211, 263]) if kind == "fdn" else BOUNDARIES
+    if kind != "fdn":
+        sparsity_loss = None
+    core = W.build(desc, dsp, system, NFFT, 30.0, dtype=torch.float64)
     model = system.Shell(core, dsp.FFT(NFFT, dtype=torch.float64),
                          dsp.Transform(lambda x: torch.abs(x), dtype=torch.float64))
     M = NFFT // 2 + 1
@@ -43,12 +64,13 @@ def _build(batch):
 def _train(trainer_cls, model, x, y, mse_loss, sparsity_loss, **kw):
     tr = trainer_cls(model, max_epochs=1, lr=1e-2, log=False, device="cpu", **kw)
     tr.register_criterion(mse_loss(nfft=NFFT), 1)
-    tr.register_criterion(sparsity_loss(), 0.2, requires_model=True)
+    if sparsity_loss is not None:
+        tr.register_criterion(sparsity_loss(), 0.2, requires_model=True)
     losses = [tr.train_step((x, y)) for _ in range(STEPS)]
     return losses, [p.detach().clone() for p in model.parameters()]
 
 
-def _worker(rank, world, port, shard, out):
+def _worker(rank, world, port, shard, out, kind="fdn"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import cpu_emulator
@@ -57,7 +79,7 @@ def _worker(rank, world, port, shard, out):
     cpu_emulator.install()
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        model, x, y, mse_loss, sparsity_loss = _build(batch=2)
+        model, x, y, mse_loss, sparsity_loss = _build(2, kind)
         if shard == "batch":
             x, y = x[rank:rank + 1], y[rank:rank + 1]  # each rank trains its own item
         losses, params = _train(DataParallelTrainer, model, x, y, mse_loss, sparsity_loss, shard=shard)
@@ -75,6 +97,21 @@ def test_two_ranks_match_single_process(shard, tmp_path, emulated_backend):
     ref_losses, ref_params = _train(Trainer, model, x, y, mse_loss, sparsity_loss)
     out = str(tmp_path / "rank0.pt")
     mp.spawn(_worker, args=(2, _free_port(), shard, out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert np.allclose(got["losses"], ref_losses, rtol=1e-9), (got["losses"], ref_losses)
+    for a, b in zip(got["params"], ref_params):
+        assert torch.allclose(a, b, rtol=1e-8, atol=1e-10)
+
+
+def test_two_ranks_bin_shards_across_launch_boundaries(tmp_path, emulated_backend):
+    """Bin-sharded step of a Series with launch boundaries (two loops, a Parallel node): the modules behind the first
+    launch see a signal already restricted to the rank's bins (found by tests/test_random_trees_cpu.py)."""
+    from flamo_b200.optimize.trainer import Trainer
+
+    model, x, y, mse_loss, sparsity_loss = _build(2, "boundaries")
+    ref_losses, ref_params = _train(Trainer, model, x, y, mse_loss, sparsity_loss)
+    out = str(tmp_path / "rank0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), "bins", out, "boundaries"), nprocs=2, join=True)
     got = torch.load(out)
     assert np.allclose(got["losses"], ref_losses, rtol=1e-9), (got["losses"], ref_losses)
     for a, b in zip(got["params"], ref_params):
