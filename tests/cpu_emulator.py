@@ -49,8 +49,13 @@ def _response(op, coef, k, nfft, lng):
     # SOS / PSOS: packed sections [K][n_in][n_out][2][8] / [K][n][2][8]
     c = coef.double()
     g = math.exp(lng)
-    w = g * torch.exp(-1j * om)
-    plus = torch.cos(om) >= 0
+    # z^-1 = exp(-j 2 pi k / nfft) with EXACT values at the quarter points, as the kernels' sincospi gives them
+    # (torch.exp(-1j * pi) has a 1.2e-16 imaginary part, which matters where a section's zero and pole cancel at Nyquist)
+    x = 2.0 * k.double() / nfft                                   # omega / pi in [0, 1]
+    sinpi = torch.sin(math.pi * torch.minimum(x, 1.0 - x))
+    cospi = torch.where(x <= 0.5, torch.sin(math.pi * (0.5 - x)), -torch.sin(math.pi * (x - 0.5)))
+    w = g * torch.complex(cospi, -sinpi)
+    plus = cospi >= 0
     v = torch.where(plus, w - 1, w + 1)
     shape = (-1,) + (1,) * (c.dim() - 2)
     v, plus = v.view(shape), plus.view(shape)

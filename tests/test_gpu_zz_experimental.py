@@ -100,3 +100,37 @@ def test_random_tree_on_the_kernels(t):
                 continue
             assert p.grad is not None, desc
             assert float((p.grad.cpu() - ref).abs().max()) <= 1e-6 * scale, desc
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("ft", ["lowpass", "highpass", "bandpass"])
+def test_biquad_cutoff_clamped_at_nyquist(ft, dtype):
+    """Raw cutoff parameters beyond 1 are clamped to Nyquist by the Biquad map (reference dsp.py:1528-1563): with
+    alias_decay_db = 0 the low-pass section's double zero and its poles then cancel AT the Nyquist bin (B = 0 and
+    A = -1.1e-16 there; the reference returns 0).  The kernels form z^-1 with sincospi, i.e. exactly -1 at that bin, and
+    must return ~0 too — the float64 emulator did not until it was given exact quarter-point phases (found by
+    tests/test_random_trees_reference_cpu.py::test_random_tree_far_from_the_initial_parameters)."""
+    import numpy as np
+
+    from flamo_b200 import workloads as W
+    from flamo_b200.processor import dsp, system
+    from helpers import rel_err
+    from oracle import flamo_oracle as O
+
+    nfft = 256
+    desc = ("Biquad", dict(size=(2, 1), n_sections=1, filter_type=ft, fs=48000, requires_grad=False))
+    torch.manual_seed(0)
+    model = W.build(desc, dsp, system, nfft, 0.0, dtype=dtype, device="cuda")
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(4.0)
+        cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
+        X = C.make_input(1, nfft // 2 + 1, 1, None).to(cdt).cuda()
+        Y = model(X).cpu().numpy().astype(np.complex128)
+        ps = [p.detach().cpu().double() for p in model.parameters()]
+        Yo = O.forward(O.from_desc(desc), X.cpu().to(torch.complex128), ps, nfft, 0.0).numpy()
+    peak = np.abs(Yo).max()
+    if peak < 1e-9:  # high-pass / band-pass at Nyquist: an all-stop filter
+        assert np.abs(Y).max() < 1e-6
+    else:
+        assert rel_err(Y, Yo) <= (1e-4 if dtype == torch.float32 else 1e-8)
