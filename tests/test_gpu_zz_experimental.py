@@ -134,3 +134,48 @@ def test_biquad_cutoff_clamped_at_nyquist(ft, dtype):
         assert np.abs(Y).max() < 1e-6
     else:
         assert rel_err(Y, Yo) <= (1e-4 if dtype == torch.float32 else 1e-8)
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree())
+def test_random_tree_captured_step_equals_eager(t):
+    """Trainer.train_step replayed from a CUDA graph vs stepped eagerly, on random trees (float32): same losses, same
+    parameters, and the capture itself must not have fallen back (maps that build tensors from host data, eager
+    Parallel segments, multi-launch series are all legal inside a capture or the Trainer has a bug)."""
+    import warnings
+
+    import numpy as np
+
+    from flamo_b200 import workloads as W
+    from flamo_b200.optimize.loss import mse_loss
+    from flamo_b200.optimize.trainer import Trainer
+    from flamo_b200.processor import dsp, system
+
+    desc, n_in, B, cols, seed, alias = t
+    M = NFFT // 2 + 1
+    x = torch.zeros(B, NFFT, n_in, device="cuda")
+    x[:, 0] = 1
+    x[:, 9] = 0.5
+    tgt = torch.full((B, M, 1), 0.6, device="cuda")
+
+    def run(graph):
+        torch.manual_seed(seed)
+        core = W.build(desc, dsp, system, NFFT, alias, dtype=torch.float32, device="cuda")
+        model = system.Shell(core, dsp.FFT(NFFT), dsp.Transform(lambda v: torch.abs(v)))
+        if not any(p.requires_grad for p in model.parameters()):
+            return None
+        tr = Trainer(model, max_epochs=1, lr=1e-3, log=False, device="cuda", graph=graph)
+        tr.register_criterion(mse_loss(nfft=NFFT, device="cuda"), 1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")  # a capture that falls back warns: make it an error here
+            losses = [tr.train_step((x, tgt)) for _ in range(7)]  # 3 eager warm-ups, capture, 3 replays
+        assert tr.use_graph == graph
+        return losses, [p.detach().clone() for p in model.parameters()]
+
+    e = run(False)
+    if e is None:
+        return
+    g = run(True)
+    assert np.allclose(g[0], e[0], rtol=2e-4, atol=1e-7), desc
+    for a, b in zip(g[1], e[1]):
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5), desc
