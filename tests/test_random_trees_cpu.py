@@ -120,17 +120,19 @@ def test_random_tree_matches_oracle(t):
     model = W.build(desc, dsp, system, NFFT, alias, dtype=torch.float64, device="cpu")
     assert model.input_channels == n_in
     M = NFFT // 2 + 1
-    X = C.make_input(B, M, n_in, cols)
+    X = C.make_input(B, M, n_in, cols).requires_grad_(True)  # the gradient w.r.t. the input signal is checked too
+    Xo = X.detach().clone().requires_grad_(True)
     params = list(model.parameters())
     Y = model(X)
     ps = [p.detach().clone().requires_grad_(p.requires_grad) for p in params]
-    Yo = O.forward(O.from_desc(desc), X, ps, NFFT, alias)
+    Yo = O.forward(O.from_desc(desc), Xo, ps, NFFT, alias)
     assert Y.shape == Yo.shape
     assert rel_err(Y.detach().numpy(), Yo.detach().numpy()) <= 1e-8, desc
     gp = [p for p in ps if p.requires_grad]
+    C.golden_loss(Y).backward()
+    *go, gxo = torch.autograd.grad(C.golden_loss(Yo), gp + [Xo], allow_unused=True)
+    assert X.grad is not None and float((X.grad - gxo).abs().max()) <= 1e-8 * float(gxo.abs().max() + 1e-300), desc
     if gp:
-        C.golden_loss(Y).backward()
-        go = torch.autograd.grad(C.golden_loss(Yo), gp, allow_unused=True)
         k = 0
         for p, q in zip(params, ps):
             if not q.requires_grad:
