@@ -18,11 +18,20 @@ FS = W.FS
 NFFT = 256
 
 
+EXTRA = False  # set by tree(extra=True): kinds the oracle does not restate (compared with the reference itself only)
+
+
 @st.composite
 def leaf(draw, n_in, n_out=None, allow_delay=True):
     """One dsp module description with n_in inputs (and n_out outputs if given, else drawn)."""
     square = n_out is not None and n_out == n_in
     kinds = ["Gain", "Biquad", "SVF", "GEQ", "Filter", "GainDelay"]
+    if EXTRA:
+        kinds.append("SOSFilter")
+        if n_out is None or square:
+            kinds.append("parallelSOSFilter")
+            if n_in in (2, 4):
+                kinds += ["Matrix:hadamard", "Matrix:rotation"]
     if allow_delay:
         kinds.append("Delay")
     if n_out is None or square:
@@ -33,6 +42,8 @@ def leaf(draw, n_in, n_out=None, allow_delay=True):
             kinds += ["Matrix", "HouseholderMatrix"]
     kind = draw(st.sampled_from(kinds))
     rg = draw(st.booleans()) or kind in ("Gain", "parallelGain")
+    if kind.startswith("Matrix:"):
+        return ("Matrix", dict(size=(n_in, n_in), matrix_type=kind.split(":")[1], requires_grad=rg)), n_in
     if kind.startswith("parallel") or kind in ("Matrix", "HouseholderMatrix"):
         m = n_in
     else:
@@ -54,6 +65,11 @@ def leaf(draw, n_in, n_out=None, allow_delay=True):
         kw.update(max_len=draw(st.integers(5, 60)), isint=draw(st.booleans()), fs=FS)
         if kw["isint"] and kind in ("Delay", "parallelDelay"):
             kw["requires_grad"] = False
+    elif kind in ("SOSFilter", "parallelSOSFilter"):
+        K = draw(st.integers(1, 3))
+        kw = dict(size=size, n_sections=K, fs=FS)  # (no requires_grad argument; the a0-normalising map of the reference
+        # writes in place and cannot be differentiated, dsp.py:1857-1862)
+        return (kind, kw, {"assign": C._sos_coeffs(K, size, draw(st.integers(0, 999)))}), m
     elif kind == "Matrix":
         kw["matrix_type"] = draw(st.sampled_from(["orthogonal", "random"]))
     elif kind == "HouseholderMatrix":
@@ -76,7 +92,17 @@ def chain(draw, n_in, n_out=None, max_len=3, allow_delay=True):
 
 
 @st.composite
-def tree(draw):
+def tree(draw, extra=False):
+    global EXTRA
+    EXTRA = extra
+    try:
+        return draw(_tree())
+    finally:
+        EXTRA = False
+
+
+@st.composite
+def _tree(draw):
     n_in = draw(st.integers(1, 3))
     parts, cur = [], n_in
     if draw(st.booleans()):

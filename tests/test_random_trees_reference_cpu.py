@@ -76,8 +76,8 @@ def assert_matches_reference(desc, X, model, Y, Yr, alias, tol_full=1e-8):
     assert rel_err(Y.detach().numpy(), Yo.numpy()) <= tol_full, desc
 
 
-@settings(max_examples=100, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
-@given(tree())
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree(extra=True))  # + SOSFilter / parallelSOSFilter, Matrix "hadamard" / "rotation" (no oracle restatement)
 def test_random_tree_matches_the_reference_itself(t):
     rdsp, rsystem = reference_modules()
     desc, n_in, B, cols, seed, alias = t
