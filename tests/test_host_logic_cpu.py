@@ -197,3 +197,45 @@ def test_entry_shape_check_follows_the_first_leaf():
     shell = system.Shell(s)
     with pytest.raises(ValueError):
         shell(C.make_input(1, 33, 2, None))
+
+
+def test_long_series_splits_into_launches_of_at_most_24_ops():
+    """A Series of 30 leaves exceeds the kernels' step table (24 ops per launch, include/fsweep.h): the lowering
+    splits it into two launches; response and gradients equal the oracle's."""
+    from flamo_b200 import sweep, workloads as W
+    from flamo_b200.processor import dsp, system
+    from oracle import flamo_oracle as O
+
+    nfft = 128
+    leaves = []
+    for i in range(30):
+        if i % 3 == 0:
+            leaves.append(("Gain", dict(size=(2, 2), requires_grad=True)))
+        elif i % 3 == 1:
+            leaves.append(("parallelDelay", dict(size=(2,), max_len=20, isint=bool(i % 2), fs=48000,
+                                                 requires_grad=not bool(i % 2))))
+        else:
+            leaves.append(("parallelGain", dict(size=(2,), requires_grad=True)))
+    desc = ("Series", leaves)
+    torch.manual_seed(3)
+    model = W.build(desc, dsp, system, nfft, 30.0, dtype=torch.float64, device="cpu")
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 2:
+                p.copy_(torch.eye(2, dtype=torch.float64) + 0.1 * p)  # keep the 10 dense gains well scaled
+    prog = sweep.Program(nfft, 30.0, torch.complex128, "cpu")
+    model._lower(prog, None)
+    segs = list(prog._segments())
+    assert [t for t, _ in segs] == ["sweep", "sweep"] and all(len(p) <= sweep.MAX_OPS_PER_LAUNCH for _, p in segs)
+    X = C.make_input(2, nfft // 2 + 1, 2, None)
+    Y = model(X)
+    ps = [p.detach().clone().requires_grad_(p.requires_grad) for p in model.parameters()]
+    Yo = O.forward(O.from_desc(desc), X, ps, nfft, 30.0)
+    assert rel_err(Y.detach().numpy(), Yo.detach().numpy()) <= 1e-9
+    C.golden_loss(Y).backward()
+    gp = [p for p in ps if p.requires_grad]
+    go = torch.autograd.grad(C.golden_loss(Yo), gp)
+    mine = [p.grad for p in model.parameters() if p.requires_grad]
+    scale = max(float(g.abs().max()) for g in go)
+    for a, b in zip(mine, go):
+        assert float((a - b).abs().max()) <= 1e-8 * scale
