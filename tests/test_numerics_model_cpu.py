@@ -73,3 +73,39 @@ def test_integer_phase_is_exact_where_float32_omega_times_delay_is_not():
     exact = (np.cos(np.pi * fr.astype(f64)) - 1j * np.sin(np.pi * fr.astype(f64)))
     assert np.abs(naive - truth).max() > 3e-4
     assert np.abs(exact - truth).max() < 5e-7
+
+
+def test_product_of_ratios_survives_where_separate_products_underflow():
+    """30 third-octave peak sections (config 3's GEQ): near DC every B_s and A_s is a ~1e-5 ... 1e-1 remainder, so
+    prod B and prod A taken separately (the reference's formula, dsp.py:2587-2593) underflow float32 and give 0 / 0,
+    while the product of the per-section ratios B_s / A_s — what the kernels accumulate — stays O(1)."""
+    fs, nfft, alias = 48000, 192000, 30.0
+    gamma = 10 ** (-alias / nfft / 20)
+    fcs = 31.25 * 2.0 ** (np.arange(30) / 3.0)
+    fcs = fcs[fcs < 0.45 * fs]
+    k = np.arange(0, 40, dtype=f64)
+    B64 = np.ones((len(k),), dtype=np.complex128)
+    A64 = np.ones_like(B64)
+    num32 = np.ones((len(k),), dtype=np.complex64)
+    den32 = np.ones_like(num32)
+    ratio32 = np.ones_like(num32)
+    for i, fc in enumerate(fcs):
+        g = 10 ** ((3.0 if i % 2 else -3.0) / 20)
+        b, a = peak_filter(torch.tensor(fc, dtype=torch.float64), torch.tensor(g, dtype=torch.float64),
+                           torch.tensor(4.3, dtype=torch.float64), fs=fs, dtype=torch.float64)
+        b, a = b.reshape(3).numpy(), a.reshape(3).numpy()
+        w = gamma * np.exp(-2j * np.pi * k / nfft)
+        B64 *= b[0] + b[1] * w + b[2] * w * w
+        A64 *= a[0] + a[1] * w + a[2] * w * w
+        packed = sweep.pack_sections(torch.tensor(b).view(3, 1, 1), torch.tensor(a).view(3, 1, 1), True,
+                                     torch.float32)[0, 0].numpy()
+        Bs, As = _taylor_eval_f32(packed, k, nfft, gamma)
+        num32 = (num32 * Bs).astype(np.complex64)
+        den32 = (den32 * As).astype(np.complex64)
+        ratio32 = (ratio32 * (Bs / As)).astype(np.complex64)
+    H = B64 / A64
+    assert np.abs(A64).min() < 1e-45  # float64 holds it; float32 (tiny = 1.2e-38, denormals to 1.4e-45) cannot
+    with np.errstate(all="ignore"):
+        separate = num32 / den32
+    assert not np.isfinite(separate).all() or np.abs(separate - H).max() > 0.1 * np.abs(H).max()
+    assert np.abs(ratio32 - H).max() <= 2e-5 * np.abs(H).max()
