@@ -222,3 +222,31 @@ def test_kernel_family_selection():
     assert p.kernel_family(48001, True) != plan_of(W.geq(4, 4, 3)).kernel_family(48001, True)
     assert plan_of(W.geq(4, 4, 3)).kernel_family(48001, True) == "fsweep_bwd_kernel"         # generic interpreter
     assert plan_of(W.active_acoustics()).kernel_family(48001, True) == "fsweep_bwd_kernel"
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """include/fsweep.h is the reference-facing seam: it must compile as strict C99 (no C++, no torch types) and a C
+    program must link and call into libfsweep.so with nothing but that header (what a cgo / ctypes / FFI binding does)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "fsweep.h"\n'
+                   "int main(void) {\n"
+                   "  fsweep_op_t op = {FSWEEP_OP_GAIN, 2, 2, 0, FSWEEP_F_GRAD, 0, 0, 0};\n"
+                   "  fsweep_plan_t* plan = 0;\n"
+                   "  if (fsweep_version() != FSWEEP_VERSION) return 1;\n"
+                   "  if (fsweep_plan_create(&op, 1, 64, 0.0, FSWEEP_C64, &plan) != FSWEEP_OK) return 2;\n"
+                   "  if (fsweep_plan_num_coeffs(plan) != 1 || fsweep_plan_coeff_numel(plan, 0, 33) != 4) return 3;\n"
+                   "  if (fsweep_forward(plan, 0, 0, 0, 0, 0, 1, 1, 0, 33, FSWEEP_EPI_NONE, 0) != FSWEEP_E_BADARG) return 4;\n"
+                   "  if (!fsweep_last_error()[0]) return 5;\n"
+                   "  return fsweep_plan_destroy(plan) == FSWEEP_OK ? 0 : 6;\n"
+                   "}\n")
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH),
+                    "-Wl,-rpath," + libdir], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
