@@ -250,3 +250,21 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
                     str(src), "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH),
                     "-Wl,-rpath," + libdir], check=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_integration_md_stub_matches_the_real_binding():
+    """The ctypes stub INTEGRATION.md shows a flamo maintainer is executable and declares the same argument lists as
+    the binding this package ships (flamo_b200/_lib.py)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = next(b.split("```")[0] for b in text.split("```python")[1:] if "flamo/_fsweep.py" in b)
+    assert "flamo/_fsweep.py" in block
+    stub = block.split("class Sweep")[0].replace('C.CDLL("libfsweep.so")', f'C.CDLL({_lib.LIB_PATH!r})')
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    real = _lib.lib()
+    for name in ("fsweep_plan_create", "fsweep_forward", "fsweep_backward"):
+        shown, shipped = getattr(ns["L"], name).argtypes, getattr(real, name).argtypes
+        assert len(shown) == len(shipped), name
+        for a, b in zip(shown, shipped):
+            assert ctypes.sizeof(a) == ctypes.sizeof(b), (name, a, b)
+    assert ctypes.sizeof(ns["Op"]) == ctypes.sizeof(_lib.Op) == 32
