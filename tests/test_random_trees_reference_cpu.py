@@ -289,3 +289,32 @@ def test_random_tree_far_from_the_initial_parameters(t, scale):
     # then a 1e-12 remainder of O(1) taps and ANY float64 evaluation from the taps (the reference's rfft, the
     # oracle's, this package's Taylor blocks) is only good to ~1e-4 there: the full-precision step is held to 1e-3
     assert_matches_reference(desc, X, model, Y, Yr, alias, tol_full=1e-3 if scale in (-3.0, 4.0, 40.0) else 1e-8)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree(), st.booleans())
+def test_random_tree_shell_responses_match_the_reference(t, identity):
+    """Shell.get_time_response / get_freq_response (reference system.py:1012-1153), input-to-output and input-free
+    (`identity=True`: a diagonal of impulses, one column per input channel) against the reference's own."""
+    rdsp, rsystem = reference_modules()
+    desc, n_in, B, cols, seed, alias = t
+    assume(not kinds_of(desc, set()) & {"SVF", "parallelSVF", "GEQ", "parallelGEQ"})
+
+    def shell(dsp_, system_):
+        torch.manual_seed(seed)
+        core = W.build(desc, dsp_, system_, NFFT, alias, dtype=torch.float64)
+        return system_.Shell(core, dsp_.FFT(NFFT, dtype=torch.float64),
+                             dsp_.Transform(lambda v: torch.abs(v), dtype=torch.float64))
+
+    try:
+        ref = shell(rdsp, rsystem)
+        hr = ref.get_time_response(identity=identity)
+        Hr = ref.get_freq_response(identity=identity)
+    except Exception:
+        assume(False)
+    assume(bool(torch.isfinite(hr).all()) and float(hr.abs().max()) > 1e-9)
+    model = shell(dsp, system)
+    h, H = model.get_time_response(identity=identity), model.get_freq_response(identity=identity)
+    assert h.shape == hr.shape and H.shape == Hr.shape
+    assert float((h - hr).abs().max()) <= 1e-9 * float(hr.abs().max()), desc
+    assert float((H - Hr).abs().max()) <= 1e-9 * float(Hr.abs().max()), desc
