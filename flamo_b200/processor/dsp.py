@@ -15,7 +15,6 @@ callers that want the response tensor itself (plots, probes, subclasses); they a
 from __future__ import annotations
 
 import math
-import warnings
 from typing import Optional
 
 import torch

@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (CRIT_MSE, CRIT_MSE_CHSUM, EPI_ABS, EPI_NONE, F_GRAD, F_ISINT, OP_DELAY, OP_GAIN, OP_PDELAY, OP_PGAIN, OP_PSOS, OP_PTABLE,
+from ._lib import (CRIT_MSE_CHSUM, EPI_ABS, EPI_NONE, F_GRAD, F_ISINT, OP_DELAY, OP_GAIN, OP_PDELAY, OP_PGAIN, OP_PSOS, OP_PTABLE,
                    OP_RECURSION, OP_SOS, OP_TABLE, Op, Plan)
 
 MAX_OPS_PER_LAUNCH = 24

@@ -5,7 +5,6 @@ queries consistently.  Argument checks of the launch entry points are covered wi
 (they must be rejected before anything is enqueued, so no GPU is needed)."""
 import ctypes as C
 
-import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
 
 from flamo_b200 import _lib

@@ -10,7 +10,7 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 import cases as C
 from flamo_b200 import workloads as W
 from flamo_b200.processor import dsp, system
-from helpers import grad_err, rel_err
+from helpers import rel_err
 from oracle import flamo_oracle as O
 
 pytestmark = pytest.mark.usefixtures("emulated_backend")

@@ -4,7 +4,6 @@ Usage: python tools/static_resource_usage.py [> profiles/<name>.md]"""
 import os
 import re
 import subprocess
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "flamo_b200", "libfsweep.so")
