@@ -318,3 +318,50 @@ def test_random_tree_shell_responses_match_the_reference(t, identity):
     assert h.shape == hr.shape and H.shape == Hr.shape
     assert float((h - hr).abs().max()) <= 1e-9 * float(hr.abs().max()), desc
     assert float((H - Hr).abs().max()) <= 1e-9 * float(Hr.abs().max()), desc
+
+
+def test_full_training_loop_matches_the_reference(tmp_path):
+    """Trainer.train (reference optimize/trainer.py:106-153: epochs over a DataLoader, StepLR, validation, checkpoint
+    per epoch, early stopping) with the colourless-FDN criteria of examples/e8_colorless_fdn.py on a 4-line FDN: same
+    train / validation loss curves, same per-criterion logs, same checkpoint files as the reference Trainer."""
+    import numpy as np
+
+    rdsp, rsystem = reference_modules()
+    from flamo.optimize import dataset as rdataset, loss as rloss, trainer as rtrainer
+
+    from flamo_b200.optimize import dataset, loss, trainer
+
+    nfft = 512
+    desc = W.fdn(4, delays=[11, 17, 23, 31])
+
+    def run(dsp_, system_, ds_, loss_, tr_, out):
+        torch.manual_seed(11)
+        core = W.build(desc, dsp_, system_, nfft, 30.0, dtype=torch.float64)
+        model = system_.Shell(core, dsp_.FFT(nfft, dtype=torch.float64),
+                              dsp_.Transform(lambda v: torch.abs(v), dtype=torch.float64))
+        data = ds_.DatasetColorless(input_shape=(1, nfft // 2 + 1, 1), target_shape=(1, nfft // 2 + 1, 1), expand=10,
+                                    device="cpu", dtype=torch.float64)
+        train_loader, valid_loader = ds_.load_dataset(data, batch_size=2, split=0.8, shuffle=False, device="cpu")
+        os.makedirs(out)
+        tr = tr_.Trainer(model, max_epochs=3, lr=1e-2, step_size=2, train_dir=str(out), device="cpu")
+        tr.register_criterion(loss_.mse_loss(nfft=nfft, device="cpu"), 1)
+        tr.register_criterion(loss_.sparsity_loss(), 0.2, requires_model=True)
+        tr.train(train_loader, valid_loader)
+        return tr, model
+
+    rt, rm = run(rdsp, rsystem, rdataset, rloss, rtrainer, tmp_path / "ref")
+    mt, mm = run(dsp, system, dataset, loss, trainer, tmp_path / "mine")
+    assert np.allclose(mt.train_loss, rt.train_loss, rtol=1e-9) and np.allclose(mt.valid_loss, rt.valid_loss, rtol=1e-9)
+    assert mt.train_loss_log.keys() == rt.train_loss_log.keys()
+    for k in rt.train_loss_log:
+        assert np.allclose(mt.train_loss_log[k], rt.train_loss_log[k], rtol=1e-9), k
+        assert np.allclose(mt.valid_loss_log[k], rt.valid_loss_log[k], rtol=1e-9), k
+    for a, b in zip(mm.parameters(), rm.parameters()):
+        assert torch.allclose(a, b, rtol=1e-8, atol=1e-11)
+    files = sorted(os.listdir(tmp_path / "ref" / "checkpoints"))
+    assert files == sorted(os.listdir(tmp_path / "mine" / "checkpoints")) and len(files) == 3
+    sd_r = torch.load(tmp_path / "ref" / "checkpoints" / files[-1], weights_only=True)
+    sd_m = torch.load(tmp_path / "mine" / "checkpoints" / files[-1], weights_only=True)
+    assert sd_r.keys() == sd_m.keys()
+    for k in sd_r:
+        assert torch.allclose(sd_r[k], sd_m[k], rtol=1e-8, atol=1e-11), k
