@@ -365,3 +365,42 @@ def test_full_training_loop_matches_the_reference(tmp_path):
     assert sd_r.keys() == sd_m.keys()
     for k in sd_r:
         assert torch.allclose(sd_r[k], sd_m[k], rtol=1e-8, atol=1e-11), k
+
+
+def _outcome(fn):
+    try:
+        fn()
+        return "ok"
+    except Exception as e:  # noqa: BLE001 - the exception TYPE is the thing compared
+        return type(e).__name__
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(st.integers(1, 4), st.integers(1, 4), st.integers(1, 4), st.integers(1, 4), st.integers(1, 4),
+       st.sampled_from(["series", "recursion", "input", "param_rank", "assign", "nfft"]))
+def test_error_behaviour_matches_the_reference(a, b, c, d, n_x, what):
+    """error types are part of the interface — mismatched channel chains (AssertionError), wrong input
+    widths (ValueError), wrong parameter ranks (AssertionError), wrong assign_value shapes, mixed nfft (ValueError):
+    whatever the reference does for a construction (including accepting it), this package does too."""
+    rdsp, rsystem = reference_modules()
+    kw = dict(nfft=64, dtype=torch.float64)
+
+    def attempt(dsp_, system_):
+        if what == "series":  # Gain (a <- b) then Gain (c <- d): valid iff a == d
+            return _outcome(lambda: system_.Series(dsp_.Gain(size=(a, b), **kw), dsp_.Gain(size=(c, d), **kw)))
+        if what == "recursion":  # fF: b -> a, fB: d -> c: valid iff a == d and c == b
+            return _outcome(lambda: system_.Recursion(fF=dsp_.Gain(size=(a, b), **kw), fB=dsp_.Gain(size=(c, d), **kw)))
+        if what == "input":
+            m = dsp_.Delay(size=(a, b), max_len=20, **kw) if c % 2 else dsp_.Gain(size=(a, b), **kw)
+            x = C.make_input(1, 33, n_x, None)
+            return _outcome(lambda: m(x))
+        if what == "param_rank":
+            cls = [dsp_.Gain, dsp_.parallelGain, dsp_.Delay, dsp_.parallelDelay][c % 4]
+            size = (a, b) if d % 2 else (a,)
+            return _outcome(lambda: cls(size=size, **kw))
+        if what == "assign":
+            m = dsp_.Gain(size=(a, b), **kw)
+            return _outcome(lambda: m.assign_value(torch.zeros(c, d, dtype=torch.float64)))
+        return _outcome(lambda: system_.Series(dsp_.Gain(size=(a, b), nfft=64), dsp_.Gain(size=(c, a), nfft=64 * d)))
+
+    assert attempt(dsp, system) == attempt(rdsp, rsystem), (what, a, b, c, d, n_x)
