@@ -404,3 +404,28 @@ def test_error_behaviour_matches_the_reference(a, b, c, d, n_x, what):
         return _outcome(lambda: system_.Series(dsp_.Gain(size=(a, b), nfft=64), dsp_.Gain(size=(c, a), nfft=64 * d)))
 
     assert attempt(dsp, system) == attempt(rdsp, rsystem), (what, a, b, c, d, n_x)
+
+
+CLASSES = ["Gain", "parallelGain", "Matrix", "HouseholderMatrix", "Filter", "parallelFilter", "Biquad", "parallelBiquad",
+           "SVF", "parallelSVF", "GEQ", "parallelGEQ", "Delay", "parallelDelay", "GainDelay", "parallelGainDelay",
+           "SOSFilter", "parallelSOSFilter"]
+
+
+@settings(max_examples=200, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(st.sampled_from(CLASSES), st.lists(st.integers(1, 4), min_size=1, max_size=3))
+def test_constructor_size_checks_match_the_reference(cls, size):
+    """Every module class with every rank of `size` (1 to 3 entries): accepted or rejected exactly like the
+    reference, with the same exception type; when accepted, the same parameter shape and channel counts."""
+    rdsp, rsystem = reference_modules()
+    kw = dict(nfft=64, dtype=torch.float64)
+
+    def build(dsp_):
+        torch.manual_seed(0)
+        return getattr(dsp_, cls)(size=tuple(size), **kw)
+
+    mine, ref = _outcome(lambda: build(dsp)), _outcome(lambda: build(rdsp))
+    assert mine == ref, (cls, size)
+    if ref == "ok":
+        m, r = build(dsp), build(rdsp)
+        assert tuple(m.param.shape) == tuple(r.param.shape), (cls, size)
+        assert (m.input_channels, m.output_channels) == (r.input_channels, r.output_channels), (cls, size)
