@@ -169,18 +169,26 @@ class HadamardMatrix:
 
 
 class RotationMatrix:
-    """Kronecker power of a 2x2 rotation by angle theta: size N = 2^k (flamo/functional.py)."""
+    """Rotation matrix built from ONE angle by Kronecker squaring, with the reference's semantics
+    (flamo/functional.py:96-158): the angle is clamped to [min_angle, max_angle] (default [0, pi/4]) and the 2 x 2
+    rotation is squared `iter` times with torch.kron (iter = log2(N) - 1 when None), i.e. the result is N x N only for
+    N = 2 and N = 4.  Unlike the reference's (fill_diagonal_ with a tensor) this one is differentiable."""
 
-    def __init__(self, N, iter=1, device=None, dtype=torch.float32):
-        self.N, self.device, self.dtype = int(N), device, dtype
+    def __init__(self, N, min_angle=0, max_angle=math.pi / 4, iter=None, device=None, dtype=torch.float32):
+        self.N, self.min_angle, self.max_angle, self.iter = int(N), min_angle, max_angle, iter
+        self.device, self.dtype = device, dtype
 
     def __call__(self, theta):
         th = theta[0] if isinstance(theta, (list, tuple)) else theta
+        if self.min_angle is not None and self.min_angle > self.max_angle:
+            th = torch.full_like(th, self.max_angle)  # torch.clamp with min > max returns max
+        else:
+            th = torch.clamp(th, self.min_angle, self.max_angle)
         c, s = torch.cos(th), torch.sin(th)
-        R = torch.stack((torch.stack((c, s)), torch.stack((-s, c))))
-        out = R
-        while out.shape[0] < self.N:
-            out = torch.kron(out, R)
+        out = torch.stack((torch.stack((c, s)), torch.stack((-s, c))))
+        iters = self.iter if self.iter is not None else int(math.log2(self.N)) - 1
+        for _ in range(iters):
+            out = torch.kron(out, out)
         return out
 
 

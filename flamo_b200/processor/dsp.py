@@ -305,6 +305,8 @@ class Matrix(Gain):
         elif t == "rotation":
             assert N == self.size[1], "Matrix must be square to be a rotation matrix"
             assert N % 2 == 0, "Matrix must have even dimensions to be a rotation matrix"
+            # (the reference passes `iter` in RotationMatrix's SECOND positional slot, which is min_angle, dsp.py:665:
+            #  the number of Kronecker squarings is therefore always log2(N) - 1 and `iter` bounds the angle from below)
             self.map = lambda x: RotationMatrix(N, self.iter, device=x.device, dtype=x.dtype)([x[0][0]])
         else:
             raise ValueError(f"unknown matrix_type {t}")

@@ -51,7 +51,7 @@ def kinds_of(desc, out):
     return out
 
 
-def assert_matches_reference(desc, X, model, Y, Yr, alias, tol_full=1e-8):
+def assert_matches_reference(desc, X, model, Y, Yr, alias, tol_full=1e-8, nfft=NFFT):
     """Response parity with the reference.  Trees without SVF / GEQ: directly, 1e-8.  Trees with them: the reference
     keeps those modules' tap buffers (and eq.geq's frequency terms) in float32 whatever the module dtype (SURVEY.md §8c
     caveat), which costs it up to 1.4e-1 — so parity is shown as an exact chain instead of a loose tolerance:
@@ -66,10 +66,10 @@ def assert_matches_reference(desc, X, model, Y, Yr, alias, tol_full=1e-8):
     ps = [p.detach().clone() for p in model.parameters()]
     node = O.from_desc(desc)
     with torch.no_grad():
-        Yo = O.forward(node, X, ps, NFFT, alias)
+        Yo = O.forward(node, X, ps, nfft, alias)
         O.REF_FP32_INTERNALS = True
         try:
-            Yo32 = O.forward(node, X, ps, NFFT, alias)
+            Yo32 = O.forward(node, X, ps, nfft, alias)
         finally:
             O.REF_FP32_INTERNALS = False
     assert rel_err(Yo32.numpy(), Yr.detach().numpy()) <= 1e-10, desc
@@ -429,3 +429,45 @@ def test_constructor_size_checks_match_the_reference(cls, size):
         m, r = build(dsp), build(rdsp)
         assert tuple(m.param.shape) == tuple(r.param.shape), (cls, size)
         assert (m.input_channels, m.output_channels) == (r.input_channels, r.output_channels), (cls, size)
+
+
+@pytest.mark.parametrize("name,kwargs", [
+    ("Delay", dict(size=(2, 3), max_len=500, isint=False, unit=1, fs=44100)),
+    ("Delay", dict(size=(2, 3), max_len=500, isint=True, unit=1000, fs=48000)),
+    ("parallelDelay", dict(size=(3,), max_len=123, isint=True, unit=10, fs=8000)),
+    ("parallelDelay", dict(size=(3,), max_len=50, isint=False, unit=100, fs=48000, requires_grad=True)),
+    ("GainDelay", dict(size=(2, 2), max_len=77, isint=False, unit=1, fs=16000)),
+    ("parallelGainDelay", dict(size=(3,), max_len=77, isint=True, unit=100, fs=48000)),
+    ("GEQ", dict(size=(1, 2), octave_interval=3, fs=48000)),
+    ("parallelGEQ", dict(size=(2,), octave_interval=3, fs=44100)),
+    ("Biquad", dict(size=(2, 1), n_sections=3, filter_type="highpass", fs=22050)),
+    ("parallelSVF", dict(size=(2,), n_sections=2, filter_type="peaking", fs=96000)),
+    ("Matrix", dict(size=(4, 4), matrix_type="rotation", iter=2)),   # (the reference hands `iter` to RotationMatrix's
+    ("Matrix", dict(size=(4, 4), matrix_type="rotation")),           #  min_angle slot, dsp.py:665: with the default
+    ("Matrix", dict(size=(2, 2), matrix_type="rotation", iter=0)),   #  iter = 1 > pi/4 the angle is ALWAYS pi/4;
+    ("Matrix", dict(size=(4, 4), matrix_type="rotation", iter=None)),  # iter = 0 / None let the parameter through)
+    ("Matrix", dict(size=(4, 4), matrix_type="hadamard")),
+    ("Filter", dict(size=(7, 2, 2))),
+])
+def test_constructor_keywords_match_the_reference(name, kwargs):
+    """Less common constructor keywords (delay `unit` / `fs` / `max_len`, third-octave GEQ, sampling rates, matrix
+    types): same parameter draw from the same seed and the same response as the reference."""
+    rdsp, rsystem = reference_modules()
+    nfft = 128
+
+    def build(dsp_):
+        torch.manual_seed(5)
+        return getattr(dsp_, name)(nfft=nfft, alias_decay_db=20.0, dtype=torch.float64, **kwargs)
+
+    try:
+        r = build(rdsp)
+        X = C.make_input(1, nfft // 2 + 1, r.input_channels, None)
+        Yr = r(X)
+    except Exception as e:
+        pytest.skip(f"the reference itself fails here: {type(e).__name__}: {e}")
+    m = build(dsp)
+    assert torch.equal(m.param.detach(), r.param.detach())
+    for attr in ("fs", "unit", "max_len", "n_sections", "n_gains"):
+        if hasattr(r, attr):
+            assert getattr(m, attr) == getattr(r, attr), attr
+    assert_matches_reference((name, dict(kwargs)), X, m, m(X), Yr, 20.0, nfft=nfft)
