@@ -448,6 +448,27 @@ def test_constructor_size_checks_match_the_reference(cls, size):
     ("Matrix", dict(size=(4, 4), matrix_type="rotation", iter=None)),  # iter = 0 / None let the parameter through)
     ("Matrix", dict(size=(4, 4), matrix_type="hadamard")),
     ("Filter", dict(size=(7, 2, 2))),
+    ("Filter", dict(size=(5, 1, 3), requires_grad=True)),
+    ("parallelFilter", dict(size=(9, 3))),
+    ("Delay", dict(size=(2, 2), max_len=300, isint=False, requires_grad=True)),          # learnable: softplus map
+    ("Delay", dict(size=(2, 2), max_len=300, isint=True, requires_grad=True)),
+    ("parallelDelay", dict(size=(4,), max_len=2000, isint=True)),
+    ("GainDelay", dict(size=(3, 1), max_len=40, isint=True, requires_grad=True)),
+    ("parallelGainDelay", dict(size=(2,), max_len=40, isint=False, requires_grad=True)),
+    ("Gain", dict(size=(2, 3), map=lambda x: torch.tanh(x) * 2, requires_grad=True)),
+    ("parallelGain", dict(size=(3,), map=lambda x: x ** 2)),
+    ("HouseholderMatrix", dict(size=(4, 4), requires_grad=True)),
+    ("HouseholderMatrix", dict(size=(2, 2))),
+    ("Matrix", dict(size=(3, 3), matrix_type="orthogonal", requires_grad=True)),
+    ("Matrix", dict(size=(2, 5), matrix_type="random")),
+    ("Biquad", dict(size=(1, 2), n_sections=2, filter_type="bandpass", fs=48000, requires_grad=True)),
+    ("parallelBiquad", dict(size=(3,), n_sections=1, filter_type="highpass", fs=32000)),
+    ("SVF", dict(size=(2, 2), n_sections=1, filter_type="notch", fs=48000)),
+    ("SVF", dict(size=(1, 1), n_sections=3, filter_type="lowshelf", fs=44100, requires_grad=True)),
+    ("parallelSVF", dict(size=(3,), n_sections=2, filter_type="highshelf", fs=48000)),
+    ("GEQ", dict(size=(2, 1), octave_interval=1, fs=44100, requires_grad=True)),
+    ("SOSFilter", dict(size=(2, 2), n_sections=2)),
+    ("parallelSOSFilter", dict(size=(3,), n_sections=1)),
 ])
 def test_constructor_keywords_match_the_reference(name, kwargs):
     """Less common constructor keywords (delay `unit` / `fs` / `max_len`, third-octave GEQ, sampling rates, matrix
