@@ -492,3 +492,57 @@ def test_constructor_keywords_match_the_reference(name, kwargs):
         if hasattr(r, attr):
             assert getattr(m, attr) == getattr(r, attr), attr
     assert_matches_reference((name, dict(kwargs)), X, m, m(X), Yr, 20.0, nfft=nfft)
+
+
+def _io(desc):
+    """(input channels, output channels) of a description."""
+    if desc[0] == "Series":
+        return _io(desc[1][0])[0], _io(desc[1][-1])[1]
+    if desc[0] == "Recursion":
+        return _io(desc[1])
+    if desc[0] == "Parallel":
+        a, b = _io(desc[1]), _io(desc[2])
+        return a[0], (a[1] if (len(desc) < 4 or desc[3]) else a[1] + b[1])
+    size = desc[1]["size"]
+    return (size[-1], size[-1]) if desc[0].startswith("parallel") else (size[-1], size[-2])
+
+
+def _rect_loop(desc):
+    if desc[0] == "Series":
+        return any(_rect_loop(d) for d in desc[1])
+    if desc[0] == "Recursion":
+        a, b = _io(desc[1])
+        return a != b
+    if desc[0] == "Parallel":
+        return _rect_loop(desc[1]) or _rect_loop(desc[2])
+    return False
+
+
+@settings(max_examples=80, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tree(), st.floats(0.05, 3.0), st.floats(0.8, 1.2))
+def test_random_tree_probe_matches_the_reference(t, angle, radius):
+    """probe(z): the transfer matrix at an arbitrary point of the z plane (reference examples/e10_probe.py; the
+    per-module probe methods of dsp.py / system.py) on random trees."""
+    rdsp, rsystem = reference_modules()
+    desc, n_in, B, cols, seed, alias = t
+    # kinds whose probe the reference defines (dsp.py:487, 563, 945, 1032, 3436, 3539): the section filters and
+    # GainDelay inherit the FIR probe, which reads their parameter as taps, and Recursion.probe sizes its identity
+    # with F.shape[-1] (system.py:530), which is only right for square loops — neither says anything about parity
+    assume(kinds_of(desc, set()) <= {"Gain", "parallelGain", "Matrix", "HouseholderMatrix", "Filter", "parallelFilter",
+                                     "Delay", "parallelDelay"})
+    assume(not _rect_loop(desc) and not _has(desc, "Parallel"))
+    z = torch.polar(torch.tensor(radius, dtype=torch.float64), torch.tensor(angle, dtype=torch.float64))
+    torch.manual_seed(seed)
+    try:
+        ref = W.build(desc, rdsp, rsystem, NFFT, alias, dtype=torch.float64)
+        with torch.no_grad():
+            Hr = ref.probe(z)
+    except Exception:
+        assume(False)
+    assume(Hr is not None and bool(torch.isfinite(torch.view_as_real(Hr)).all()))
+    torch.manual_seed(seed)
+    model = W.build(desc, dsp, system, NFFT, alias, dtype=torch.float64, device="cpu")
+    with torch.no_grad():
+        H = model.probe(z)
+    assert H.shape == Hr.shape, desc
+    assert float((H - Hr).abs().max()) <= 1e-9 * float(Hr.abs().max() + 1e-300), desc
