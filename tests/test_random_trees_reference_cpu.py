@@ -546,3 +546,43 @@ def test_random_tree_probe_matches_the_reference(t, angle, radius):
         H = model.probe(z)
     assert H.shape == Hr.shape, desc
     assert float((H - Hr).abs().max()) <= 1e-9 * float(Hr.abs().max() + 1e-300), desc
+
+
+@settings(max_examples=100, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(st.sampled_from(["lowpass", "highpass", "bandpass", "shelving_low", "shelving_high", "peak"]),
+       st.lists(st.floats(20.0, 20000.0), min_size=1, max_size=4), st.floats(-24.0, 24.0), st.floats(0.3, 8.0),
+       st.sampled_from([8000, 44100, 48000, 96000]), st.sampled_from([torch.float32, torch.float64]))
+def test_filter_designers_match_the_reference(kind, fcs, gain, Q, fs, dtype):
+    """functional.{lowpass, highpass, bandpass, shelving, peak}_filter (reference functional.py:376-675): same taps,
+    same shapes, same dtypes for random cutoffs / gains / Q / sampling rates."""
+    reference_modules()
+    import flamo.functional as RF
+
+    from flamo_b200 import functional as MF
+
+    fc = torch.tensor(fcs, dtype=dtype).clamp(max=0.45 * fs)
+    if kind.startswith("shelving") or kind == "peak":
+        fc = fc[0]  # the reference's shelving / peak designers are scalar (eq.geq loops over bands and channel pairs in
+        # Python, eq.py:57-111); this package's accept tensors — compared on what the reference can do
+    g = torch.full_like(fc, gain)
+
+    def call(F):
+        if kind == "lowpass":
+            return F.lowpass_filter(fc=fc, gain=g, fs=fs, dtype=dtype)
+        if kind == "highpass":
+            return F.highpass_filter(fc=fc, gain=g, fs=fs, dtype=dtype)
+        if kind == "bandpass":
+            return F.bandpass_filter(fc1=fc, fc2=(fc * 1.7).clamp(max=0.49 * fs), gain=g, fs=fs, dtype=dtype)
+        if kind.startswith("shelving"):
+            return F.shelving_filter(fc=fc, gain=10 ** (g / 20), type=kind.split("_")[1], fs=fs, dtype=dtype)
+        return F.peak_filter(fc=fc, gain=10 ** (g / 20), Q=torch.full_like(fc, Q), fs=fs, dtype=dtype)
+
+    try:
+        br, ar = call(RF)
+    except Exception:
+        assume(False)
+    b, a = call(MF)
+    tol = 1e-12 if dtype == torch.float64 else 2e-6
+    for mine, ref in ((b, br), (a, ar)):
+        assert mine.shape == ref.shape and mine.dtype == ref.dtype, kind
+        assert float((mine - ref).abs().max()) <= tol * float(ref.abs().max() + 1e-30), kind
