@@ -208,6 +208,13 @@ def signal_gallery(batch_size: int, n_samples: int, n: int, signal_type: str = "
     if signal_type == "exp":
         t = torch.arange(n_samples, dtype=dtype, device=device)
         return torch.exp(-rate * t / fs).unsqueeze(-1).expand(batch_size, n_samples, n)
+    if signal_type == "sweep":
+        # linear chirp 20 Hz -> 20 kHz over the whole signal: scipy.signal.chirp(t, 20, t[-1], 20000) with phi = 0,
+        # evaluated in `dtype` in scipy's operation order (the reference hands it a `dtype` time axis)
+        t = torch.linspace(0, n_samples / fs - 1 / fs, n_samples, dtype=dtype)
+        beta = (20000.0 - 20.0) / t[-1]
+        x = torch.cos(2 * np.pi * (20.0 * t + 0.5 * beta * t * t))
+        return x.to(device).unsqueeze(-1).expand(batch_size, n_samples, n)
     if signal_type == "reference":
         return torch.as_tensor(reference, dtype=dtype, device=device).expand(batch_size, n_samples, n)
     raise ValueError(f"Signal type {signal_type} not recognized.")

@@ -586,3 +586,25 @@ def test_filter_designers_match_the_reference(kind, fcs, gain, Q, fs, dtype):
     for mine, ref in ((b, br), (a, ar)):
         assert mine.shape == ref.shape and mine.dtype == ref.dtype, kind
         assert float((mine - ref).abs().max()) <= tol * float(ref.abs().max() + 1e-30), kind
+
+
+@pytest.mark.parametrize("signal_type", ["impulse", "sine", "sweep", "wgn", "exp", "noise", "reference", "foo"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_signal_gallery_matches_the_reference(signal_type, dtype):
+    """functional.signal_gallery (reference functional.py:164-270): same signals (seeded for the noise types), same
+    errors for an unknown type / a missing reference."""
+    reference_modules()
+    import flamo.functional as RF
+
+    from flamo_b200 import functional as MF
+
+    def call(F):
+        torch.manual_seed(3)
+        return F.signal_gallery(2, 480, 3, signal_type=signal_type, fs=48000, rate=5.0, dtype=dtype)
+
+    ref, mine = _outcome(lambda: call(RF)), _outcome(lambda: call(MF))
+    assert ref == mine
+    if ref == "ok":
+        r, m = call(RF), call(MF)
+        assert r.shape == m.shape and r.dtype == m.dtype
+        assert float((r - m).abs().max()) <= (1e-12 if dtype == torch.float64 else 1e-5)
