@@ -608,3 +608,34 @@ def test_signal_gallery_matches_the_reference(signal_type, dtype):
         r, m = call(RF), call(MF)
         assert r.shape == m.shape and r.dtype == m.dtype
         assert float((r - m).abs().max()) <= (1e-12 if dtype == torch.float64 else 1e-5)
+
+
+def test_small_helpers_match_the_reference():
+    """functional.{hertz2rad, rad2hertz, db2mag, mag2db, get_magnitude, skew_matrix}, utils.to_complex, eq.eq_freqs:
+    same values, shapes and dtypes as the reference (functional.py:42-56, 306-353; utils.py:12-22; eq.py:8-54)."""
+    reference_modules()
+    import flamo.functional as RF
+    import importlib
+
+    RU = importlib.import_module("flamo.utils")  # (the package attribute `flamo.utils` is shadowed by optimize.utils)
+    REQ = importlib.import_module("flamo.auxiliary.eq")
+
+    from flamo_b200 import functional as MF, utils as MU
+    from flamo_b200.auxiliary import eq as MEQ
+
+    g = torch.Generator().manual_seed(0)
+    for dtype in (torch.float32, torch.float64):
+        x = torch.rand(4, 3, generator=g, dtype=dtype) * 100 + 0.1
+        for name, args in (("hertz2rad", (x, 48000)), ("rad2hertz", (x / 100, 44100)), ("db2mag", (x - 50,)),
+                           ("mag2db", (x,)), ("skew_matrix", (torch.randn(5, 5, generator=g, dtype=dtype),))):
+            r, m = getattr(RF, name)(*args), getattr(MF, name)(*args)
+            assert r.shape == m.shape and r.dtype == m.dtype, name
+            assert torch.allclose(r, m, rtol=1e-6 if dtype == torch.float32 else 1e-13, atol=0), name
+        z = torch.complex(x, x.flip(0))
+        assert torch.equal(RF.get_magnitude(z), MF.get_magnitude(z))
+        rc, mc = RU.to_complex(x), MU.to_complex(x)
+        assert rc.dtype == mc.dtype and torch.equal(rc, mc)
+    for interval in (1, 3):
+        rf, mf = REQ.eq_freqs(interval=interval), MEQ.eq_freqs(interval=interval)
+        rf, mf = (rf[0] if isinstance(rf, tuple) else rf), (mf[0] if isinstance(mf, tuple) else mf)
+        assert torch.allclose(torch.as_tensor(rf).double(), torch.as_tensor(mf).double(), rtol=1e-6)
