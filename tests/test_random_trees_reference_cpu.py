@@ -639,3 +639,39 @@ def test_small_helpers_match_the_reference():
         rf, mf = REQ.eq_freqs(interval=interval), MEQ.eq_freqs(interval=interval)
         rf, mf = (rf[0] if isinstance(rf, tuple) else rf), (mf[0] if isinstance(mf, tuple) else mf)
         assert torch.allclose(torch.as_tensor(rf).double(), torch.as_tensor(mf).double(), rtol=1e-6)
+
+
+@settings(max_examples=100, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(st.lists(st.tuples(st.sampled_from(["append", "prepend", "insert"]), st.integers(-4, 4),
+                          st.sampled_from([None, "a", "b", "7", "gain"]), st.booleans()), min_size=1, max_size=5))
+def test_series_editing_matches_the_reference(edits):
+    """Series.append / prepend / insert with plain modules, keyed OrderedDicts and nested Series (reference
+    system.py:33-125): the same keys in the same order, the same channel counts, the same exceptions."""
+    from collections import OrderedDict
+
+    rdsp, rsystem = reference_modules()
+    kw = dict(size=(2,), nfft=64, dtype=torch.float64)
+
+    def play(dsp_, system_):
+        s = system_.Series(OrderedDict({"first": dsp_.parallelGain(**kw)}), dsp_.parallelGain(**kw))
+        log = []
+        for op, idx, key, nested in edits:
+            new = dsp_.parallelGain(**kw)
+            if nested:
+                new = system_.Series(new, dsp_.parallelGain(**kw))
+            if key is not None:
+                new = OrderedDict({key: new})
+            if op == "append":
+                log.append(_outcome(lambda: s.append(new)))
+            elif op == "prepend":
+                log.append(_outcome(lambda: s.prepend(new)))
+            else:
+                log.append(_outcome(lambda: s.insert(idx, new)))
+            log.append(tuple(s._modules.keys()))
+        return log, (s.input_channels, s.output_channels), len(s)
+
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert play(dsp, system) == play(rdsp, rsystem)
