@@ -675,3 +675,40 @@ def test_series_editing_matches_the_reference(edits):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         assert play(dsp, system) == play(rdsp, rsystem)
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(st.tuples(st.integers(1, 3), st.integers(1, 3)), st.one_of(st.none(), st.tuples(st.integers(1, 3), st.integers(1, 3))),
+       st.one_of(st.none(), st.tuples(st.integers(1, 3), st.integers(1, 3))), st.sampled_from([64, 128]),
+       st.sampled_from([64, 128]), st.sampled_from(["plain", "sequential", "ordered"]))
+def test_shell_construction_checks_match_the_reference(core, inp, out, nfft_core, nfft_layer, wrap):
+    """Shell.__init__ (reference system.py:800-976): channel / nfft consistency checks between the core and the input
+    / output layers, conversion of nn.Sequential / OrderedDict cores to Series, resulting channel counts."""
+    from collections import OrderedDict
+
+    import torch.nn as nn
+
+    rdsp, rsystem = reference_modules()
+
+    def build(dsp_, system_):
+        c = dsp_.Gain(size=core, nfft=nfft_core, dtype=torch.float64)
+        if wrap == "sequential":
+            c = nn.Sequential(c)
+        elif wrap == "ordered":
+            c = OrderedDict({"g": c})
+        i = dsp_.FFT(nfft_layer, dtype=torch.float64) if inp is None else dsp_.Gain(size=inp, nfft=nfft_layer,
+                                                                                      dtype=torch.float64)
+        o = dsp_.iFFT(nfft_layer, dtype=torch.float64) if out is None else dsp_.Gain(size=out, nfft=nfft_layer,
+                                                                                       dtype=torch.float64)
+        s = system_.Shell(core=c, input_layer=i, output_layer=o)
+        return (s.input_channels, s.output_channels, s.nfft, type(s.get_core()).__name__,
+                tuple(s.state_dict().keys()))
+
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mine, ref = _outcome(lambda: build(dsp, system)), _outcome(lambda: build(rdsp, rsystem))
+        assert mine == ref, (core, inp, out, nfft_core, nfft_layer, wrap)
+        if ref == "ok":
+            assert build(dsp, system) == build(rdsp, rsystem)
