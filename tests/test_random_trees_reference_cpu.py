@@ -712,3 +712,39 @@ def test_shell_construction_checks_match_the_reference(core, inp, out, nfft_core
         assert mine == ref, (core, inp, out, nfft_core, nfft_layer, wrap)
         if ref == "ok":
             assert build(dsp, system) == build(rdsp, rsystem)
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(st.sampled_from(["Recursion", "Parallel_sum", "Parallel_cat"]), st.tuples(st.integers(1, 3), st.integers(1, 3)),
+       st.tuples(st.integers(1, 3), st.integers(1, 3)), st.sampled_from([64, 128]), st.sampled_from([64, 128]),
+       st.sampled_from(["plain", "sequential", "ordered"]))
+def test_recursion_and_parallel_construction_match_the_reference(kind, sa, sb, nfft_a, nfft_b, wrap):
+    """Recursion.__init__ / Parallel.__init__ (reference system.py:363-395, 473-515, 600-738): path conversion to
+    Series, nfft / channel consistency assertions, resulting channel counts and state_dict keys."""
+    from collections import OrderedDict
+
+    import torch.nn as nn
+
+    rdsp, rsystem = reference_modules()
+
+    def build(dsp_, system_):
+        a = dsp_.Gain(size=sa, nfft=nfft_a, dtype=torch.float64)
+        b = dsp_.Gain(size=sb, nfft=nfft_b, dtype=torch.float64)
+        if wrap == "sequential":
+            a = nn.Sequential(a)
+        elif wrap == "ordered":
+            b = OrderedDict({"g": b})
+        if kind == "Recursion":
+            m = system_.Recursion(fF=a, fB=b)
+        else:
+            m = system_.Parallel(a, b, sum_output=kind.endswith("sum"))
+        return m.input_channels, m.output_channels, m.nfft, tuple(m.state_dict().keys())
+
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mine, ref = _outcome(lambda: build(dsp, system)), _outcome(lambda: build(rdsp, rsystem))
+        assert mine == ref, (kind, sa, sb, nfft_a, nfft_b, wrap)
+        if ref == "ok":
+            assert build(dsp, system) == build(rdsp, rsystem)
