@@ -748,3 +748,32 @@ def test_recursion_and_parallel_construction_match_the_reference(kind, sa, sb, n
         assert mine == ref, (kind, sa, sb, nfft_a, nfft_b, wrap)
         if ref == "ok":
             assert build(dsp, system) == build(rdsp, rsystem)
+
+
+@settings(max_examples=80, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(st.sampled_from(["FFT", "iFFT", "FFTAntiAlias", "iFFTAntiAlias"]), st.sampled_from(["backward", "ortho", "forward"]),
+       st.sampled_from([64, 96]), st.sampled_from([0.0, 20.0, -35.0]), st.integers(1, 3), st.integers(1, 3),
+       st.sampled_from([torch.float32, torch.float64]), st.booleans())
+def test_transform_layers_match_the_reference(cls, norm, nfft, alias, B, N, dtype, short):
+    """dsp.FFT / iFFT / FFTAntiAlias / iFFTAntiAlias (reference dsp.py:45-160): same values, shapes and dtypes for
+    inputs shorter than or equal to nfft, every norm, with and without the anti-aliasing envelope."""
+    rdsp, rsystem = reference_modules()
+    g = torch.Generator().manual_seed(nfft + B + 10 * N)
+    if cls.startswith("i"):
+        x = torch.randn(B, nfft // 2 + 1, N, generator=g, dtype=dtype) + 1j * torch.randn(B, nfft // 2 + 1, N, generator=g,
+                                                                                         dtype=dtype)
+    else:
+        x = torch.randn(B, nfft // 2 + 3 if short else nfft, N, generator=g, dtype=dtype)
+
+    def run(dsp_):
+        kw = dict(nfft=nfft, norm=norm, dtype=dtype)
+        if "AntiAlias" in cls:
+            kw["alias_decay_db"] = alias
+        return getattr(dsp_, cls)(**kw)(x)
+
+    ref = _outcome(lambda: run(rdsp))
+    assert _outcome(lambda: run(dsp)) == ref
+    if ref == "ok":
+        r, m = run(rdsp), run(dsp)
+        assert r.shape == m.shape and r.dtype == m.dtype
+        assert float((r - m).abs().max()) <= (1e-4 if dtype == torch.float32 else 1e-11) * float(r.abs().max() + 1e-30)
