@@ -777,3 +777,42 @@ def test_transform_layers_match_the_reference(cls, norm, nfft, alias, B, N, dtyp
         r, m = run(rdsp), run(dsp)
         assert r.shape == m.shape and r.dtype == m.dtype
         assert float((r - m).abs().max()) <= (1e-4 if dtype == torch.float32 else 1e-11) * float(r.abs().max() + 1e-30)
+
+
+@pytest.mark.parametrize("name,kwargs,tol", [
+    ("Biquad", dict(size=(2, 3), n_sections=2, filter_type="lowpass"), 1e-10),
+    ("Biquad", dict(size=(1, 2), n_sections=3, filter_type="bandpass"), 1e-10),
+    ("parallelBiquad", dict(size=(3,), n_sections=2, filter_type="highpass"), 1e-10),
+    ("SVF", dict(size=(2, 2), n_sections=2, filter_type=None), 5e-3),            # float32 tap buffers in the reference
+    ("parallelSVF", dict(size=(3,), n_sections=1, filter_type="peaking"), 5e-3),
+    ("GEQ", dict(size=(1, 2), octave_interval=1), 0.2),                          # float32 eq.geq in the reference
+    ("parallelGEQ", dict(size=(2,), octave_interval=1), 0.2),
+    ("SOSFilter", dict(size=(2, 2), n_sections=2), 1e-10),
+])
+def test_public_module_methods_match_the_reference(name, kwargs, tol):
+    """The methods other flamo code calls on a section filter: get_poly_coeff(map(param)) -> (H, B, A),
+    freq_response(param), assign_value with an index, s2sample / sample2s of the delays."""
+    rdsp, rsystem = reference_modules()
+    nfft = 128
+
+    def build(dsp_):
+        torch.manual_seed(9)
+        return getattr(dsp_, name)(nfft=nfft, alias_decay_db=10.0, dtype=torch.float64, fs=48000, **kwargs)
+
+    r, m = build(rdsp), build(dsp)
+    with torch.no_grad():
+        outs_r, outs_m = r.get_poly_coeff(r.map(r.param)), m.get_poly_coeff(m.map(m.param))
+        assert len(outs_r) == len(outs_m) == 3
+        for a, b in zip(outs_r, outs_m):
+            assert a.shape == b.shape and a.dtype == b.dtype, name
+            assert float((a - b).abs().max()) <= tol * float(a.abs().max()), name
+        Hr, Hm = r.freq_response(r.param), m.freq_response(m.param)
+        assert Hr.shape == Hm.shape and float((Hr - Hm).abs().max()) <= tol * float(Hr.abs().max())
+    new = torch.full_like(r.param[0], 0.25)
+    r.assign_value(new, (0,))
+    m.assign_value(new, (0,))
+    assert torch.equal(r.param.detach(), m.param.detach()) and m.new_value == r.new_value
+    d_r = rdsp.parallelDelay(size=(3,), max_len=500, unit=10, fs=44100, nfft=nfft, dtype=torch.float64)
+    d_m = dsp.parallelDelay(size=(3,), max_len=500, unit=10, fs=44100, nfft=nfft, dtype=torch.float64)
+    v = torch.tensor([1.0, 12.5, 499.0], dtype=torch.float64)
+    assert torch.equal(d_r.sample2s(v), d_m.sample2s(v)) and torch.equal(d_r.s2sample(v), d_m.s2sample(v))
