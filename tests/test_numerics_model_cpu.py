@@ -109,3 +109,43 @@ def test_product_of_ratios_survives_where_separate_products_underflow():
         separate = num32 / den32
     assert not np.isfinite(separate).all() or np.abs(separate - H).max() > 0.1 * np.abs(H).max()
     assert np.abs(ratio32 - H).max() <= 2e-5 * np.abs(H).max()
+
+
+def test_float32_loop_solve_meets_the_bar_only_with_exact_phases():
+    """Config 2 (8 x 8 FDN, nfft = 96000, alias 30 dB) modelled in numpy: H = c^T (I - D W)^-1 D b per bin with a
+    float32 LU (LAPACK complex64, partial pivoting — the arithmetic of the loop kernels).  With the delay phases formed
+    exactly (integer k * m mod nfft) the magnitude response is within the 1e-4 bar of the float64 truth; with the
+    reference's float32 omega * m it is not — the phase error, not the float32 LU, is what breaks float32 parity."""
+    from flamo_b200 import workloads as W
+
+    nfft, N, alias = 96000, 8, 30.0
+    m = np.array(W.fdn_delays(N), dtype=np.int64)
+    rng = np.random.default_rng(130709)
+    P = rng.standard_normal((N, N))
+    S = np.triu(P, 1) - np.triu(P, 1).T
+    Wm = torch.matrix_exp(torch.tensor(S)).numpy()  # orthogonal feedback matrix
+    b, c = rng.standard_normal((N, 1)), rng.standard_normal((1, N))
+    gamma = 10 ** (-alias / nfft / 20)
+    k = np.arange(0, nfft // 2 + 1, dtype=np.int64)[::7]  # every 7th bin: 6858 systems
+    gm = gamma ** m.astype(f64)
+
+    def response(D, dtype):
+        A = np.eye(N, dtype=dtype)[None] - D[:, :, None].astype(dtype) * Wm.astype(dtype)[None]
+        rhs = (D.astype(dtype) * b[:, 0].astype(dtype)[None])[:, :, None]
+        y = np.linalg.solve(A, rhs)[:, :, 0]
+        return np.abs((y * c[0].astype(dtype)[None]).sum(-1))
+
+    D_true = gm[None] * np.exp(-2j * np.pi * ((k[:, None] * m[None]) % nfft) / nfft)
+    truth = response(D_true, np.complex128)
+    fr = (2.0 * ((k[:, None] * m[None]) % nfft) / nfft).astype(f32).astype(f64)
+    D_exact = (gm.astype(f32)[None] * (np.cos(np.pi * fr) - 1j * np.sin(np.pi * fr))).astype(np.complex64)
+    omega32 = (f32(2) * f32(np.pi) * k.astype(f32) / f32(nfft)).astype(f32)
+    ph32 = (omega32[:, None] * m.astype(f32)[None]).astype(f32).astype(f64)
+    D_naive = (gm.astype(f32)[None] * (np.cos(ph32) - 1j * np.sin(ph32))).astype(np.complex64)
+
+    def rel(a):
+        return float((np.abs(a - truth) / np.maximum(truth, 1e-3 * truth.max())).max())
+
+    err_exact, err_naive = rel(response(D_exact, np.complex64)), rel(response(D_naive, np.complex64))
+    assert err_exact < 1e-4, err_exact
+    assert err_naive > 10 * err_exact and err_naive > 1e-4, (err_naive, err_exact)
