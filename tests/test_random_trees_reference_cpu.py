@@ -816,3 +816,39 @@ def test_public_module_methods_match_the_reference(name, kwargs, tol):
     d_m = dsp.parallelDelay(size=(3,), max_len=500, unit=10, fs=44100, nfft=nfft, dtype=torch.float64)
     v = torch.tensor([1.0, 12.5, 499.0], dtype=torch.float64)
     assert torch.equal(d_r.sample2s(v), d_m.sample2s(v)) and torch.equal(d_r.s2sample(v), d_m.s2sample(v))
+
+
+def test_datasets_and_criteria_match_the_reference():
+    """optimize.dataset.{Dataset, DatasetColorless, load_dataset} and optimize.loss.{mse_loss, sparsity_loss}
+    (reference dataset.py:9-174, loss.py:12-103): same items, same loader lengths, same loss values and gradients."""
+    rdsp, rsystem = reference_modules()
+    from flamo.optimize import dataset as RD, loss as RL
+
+    from flamo_b200.optimize import dataset as MD, loss as ML
+
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(1, 33, 2, generator=g), torch.rand(1, 33, 1, generator=g)
+    for D in (RD, MD):
+        ds = D.Dataset(input=x, target=y, expand=7, device="cpu", dtype=torch.float64)
+        assert len(ds) == 7 and ds[3][0].dtype == torch.float64 and torch.equal(ds[3][0], x[0].double())
+        tr, va = D.load_dataset(ds, batch_size=2, split=0.7, shuffle=False, device="cpu")
+        assert (len(tr), len(va)) == (2, 1)  # int(7 * 0.7) = 4 -> 2 batches; 3 -> 1 batch (drop_last)
+        dc = D.DatasetColorless(input_shape=(1, 17, 3), target_shape=(1, 17, 1), expand=4, device="cpu")
+        assert dc.input.shape == (4, 17, 3) and float(dc.input[:, 0].min()) == 1 and float(dc.input[:, 1:].abs().max()) == 0
+        assert dc.target.shape == (4, 17, 1) and float(dc.target.min()) == 1
+    pred = torch.rand(3, 33, 4, generator=g, dtype=torch.float64, requires_grad=True)
+    tgt = torch.rand(3, 33, 1, generator=g, dtype=torch.float64)
+    lr, lm = RL.mse_loss(nfft=64, device="cpu")(pred, tgt), ML.mse_loss(nfft=64, device="cpu")(pred, tgt)
+    assert torch.equal(lr, lm)
+    assert torch.equal(torch.autograd.grad(lr, pred)[0], torch.autograd.grad(lm, pred)[0])
+    for N in (4, 6):
+        def fdn(dsp_, system_):
+            torch.manual_seed(N)
+            core = W.build(W.fdn(N, delays=list(range(11, 11 + 2 * N, 2))), dsp_, system_, 64, 30.0, dtype=torch.float64)
+            return system_.Shell(core, dsp_.FFT(64, dtype=torch.float64))
+        mr, mm = fdn(rdsp, rsystem), fdn(dsp, system)
+        sr, sm = RL.sparsity_loss()(None, None, mr), ML.sparsity_loss()(None, None, mm)
+        assert abs(float(sr) - float(sm)) <= 1e-12
+        gr = torch.autograd.grad(sr, mr.get_core().feedback_loop.feedback.param)[0]
+        gm = torch.autograd.grad(sm, mm.get_core().feedback_loop.feedback.param)[0]
+        assert torch.allclose(gr, gm, rtol=1e-9, atol=1e-12)
