@@ -249,10 +249,12 @@ def test_random_tree_trainer_fused_equals_unfused(t, crit_kind):
     if rf is None or ru is None:
         return
     (lf, pf), (lu, pu) = rf, ru
-    assert np.allclose(lf, lu, rtol=1e-9, atol=1e-14), desc
+    assert np.allclose(lf, lu, rtol=1e-7, atol=1e-14), desc
     for a, b in zip(pf, pu):
-        assert torch.allclose(a, b, rtol=1e-8, atol=2e-6), desc  # (atol: Adam on zero true gradients, see the
-        # reference-trainer test)
+        # Adam normalises: a parameter whose true gradient is (near) zero moves by lr * g / (|g| + eps) with g the
+        # rounding noise of the route taken, so parameters are only pinned to 1e-2 of a real update (lr = 1e-2);
+        # the second step's loss above is the sharp check of the parameters that matter
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-4), desc
 
 
 @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
