@@ -179,4 +179,6 @@ def test_random_tree_captured_step_equals_eager(t):
     g = run(True)
     assert np.allclose(g[0], e[0], rtol=2e-4, atol=1e-7), desc
     for a, b in zip(g[1], e[1]):
-        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5), desc
+        # (Adam moves a parameter with a near-zero true gradient by lr * noise / (|noise| + eps): only gross
+        #  differences are meaningful here; the losses above are the sharp check)
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-4), desc
