@@ -967,8 +967,8 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     }
     // 4 warps per block, 1 warp per element; row n_ops of the grid sums the fused criterion's loss
     dim3 grid((unsigned)std::min(1024, (max_total + 3) / 4), (unsigned)P.n_ops + (crit ? 1u : 0u));
-    const char* v2 = getenv("FSWEEP_FINALIZE_V2");  // experimental coalesced variant, off unless asked for
-    if (v2 && v2[0] == '1') {
+    const char* v2 = getenv("FSWEEP_FINALIZE_V2");  // coalesced kernel (default); "0" selects the round-1 kernel
+    if (!(v2 && v2[0] == '0')) {
       dim3 grid2((unsigned)std::min(256, (max_total + 31) / 32), grid.y);
       if (dtype == FSWEEP_C64)
         fsweep_finalize_v2_kernel<float><<<grid2, 32 * FIN2_WARPS, 0, st>>>(F);

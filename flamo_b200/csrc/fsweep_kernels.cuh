@@ -1288,8 +1288,8 @@ __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_const
   }
 }
 
-// EXPERIMENTAL (FSWEEP_FINALIZE_V2=1, not the default: written after the round's GPU budget was spent, never run).
-// Same sums as fsweep_finalize_kernel with coalesced reads: the 32 lanes of a warp own 32 CONSECUTIVE accumulators of
+// The default gradient finalize since round 2 (FSWEEP_FINALIZE_V2=0 selects fsweep_finalize_kernel above; parity of the
+// two on every case: tests/test_gpu_random_trees.py).  Same sums as fsweep_finalize_kernel with coalesced reads: the 32 lanes of a warp own 32 CONSECUTIVE accumulators of
 // one partial row (row index fastest, which is how the rows are laid out), the block's warps split the per-block rows,
 // and the cross-warp sum runs in a fixed order through shared memory (deterministic).  The first version gives every
 // lane of a warp a different block's row: n_blocks scattered 4-byte loads per gradient element.

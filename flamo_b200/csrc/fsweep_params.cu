@@ -318,7 +318,8 @@ extern "C" FSWEEP_API int fsweep_weighted_total(const void* const* parts, const 
 // every peer's announcement (acquire), read ALL peers' buffers with P2P loads and sum them in rank order (every rank
 // gets bit-identical sums), announce "done reading", wait for everyone, then overwrite its own buffer with
 // scale * sum.  Epochs increase monotonically in device memory, so the launch can be replayed inside a CUDA graph.
-// A bounded spin (about a second) turns a missing peer into garbage instead of a hung GPU.
+// A bounded spin (about a second) turns a missing peer into an ERROR FLAG (epoch_ctr[1] = 1 + the missing rank, sticky;
+// the host checks it, flamo_b200/parallel.py) instead of a hung GPU.
 namespace {
 constexpr int AR_THREADS = 1024;
 constexpr int AR_PER = 8;          // values per thread: n <= 8192
@@ -342,6 +343,10 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_p2p_kernel(float* const*
   __syncthreads();
   const unsigned epoch = s_epoch;
   auto barrier = [&](int phase) {
+    // every thread's peer loads / stores of the preceding phase must have completed before ANY thread of this block
+    // releases its flag: without this, a peer could pass the barrier and overwrite a buffer that slower warps of
+    // this block are still reading
+    __syncthreads();
     if (tid < world) {
       __threadfence_system();
       st_release_sys(pads[tid] + AR_PAD_OFF + phase * 64 + rank, epoch);
@@ -349,6 +354,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_p2p_kernel(float* const*
       unsigned spins = 0;
       while ((int)(ld_acquire_sys(mine) - epoch) < 0 && ++spins < (1u << 26)) {
       }
+      if ((int)(ld_acquire_sys(mine) - epoch) < 0) atomicExch(epoch_ctr + 1, 1u + (unsigned)tid);  // sticky: peer `tid` never arrived
     }
     __syncthreads();
   };

@@ -53,8 +53,10 @@ class SweepAdam(torch.optim.Optimizer):
             arr = (_lib.AdamTensor * len(entries))(*entries)
             lr = group["lr"]
             b1, b2 = group["betas"]
-            _lib.check(_lib.lib().fsweep_adam_step(arr, len(entries), _lib.C64 if dtype == torch.float32 else _lib.C128,
-                                                   lr.data_ptr(), float(b1), float(b2), float(group["eps"]),
-                                                   torch.cuda.current_stream(lr.device).cuda_stream))
+            with torch.cuda.device(lr.device):
+                _lib.check(_lib.lib().fsweep_adam_step(arr, len(entries),
+                                                       _lib.C64 if dtype == torch.float32 else _lib.C128,
+                                                       lr.data_ptr(), float(b1), float(b2), float(group["eps"]),
+                                                       torch.cuda.current_stream(lr.device).cuda_stream))
             sweep.launch_count += 1
         return loss

@@ -25,6 +25,10 @@ class sparsity_loss(nn.Module):
                 continue
         if mm is None:
             raise AttributeError("sparsity_loss: could not locate the feedback mixing matrix in the model")
+        from ..processor.dsp import HouseholderMatrix
+
+        if isinstance(mm, HouseholderMatrix):  # the parameter is the unit vector u: A = I - 2 u u^T (loss.py:53-55)
+            A = mm._matrix(mm.param)
         N = A.shape[-1]
         from .. import sweep
 

@@ -39,6 +39,7 @@ class Trainer:
         on_cuda = torch.device(device).type == "cuda"
         self.use_graph = on_cuda if graph is None else (graph and on_cuda)
         params = list(self.net.parameters())
+        self._all_params = params
         if self.use_graph:
             # a captured step needs `step` and `lr` on the device: torch's capturable fused Adam (two launches: a
             # foreach add on the step counters, then the multi-tensor update).  FLAMO_B200_SWEEP_ADAM=1 selects
@@ -202,8 +203,15 @@ class Trainer:
         return vals[-1]
 
     # -- captured step (CUDA) --------------------------------------------------------------------
+    def _graph_key(self, inputs, targets):
+        """Shapes + the version counters of the FROZEN parameters: their mapped coefficients are baked into a captured
+        step (DSP._coef_cache), so assign_value / load_state_dict on a frozen module must lead to a new capture.
+        (Trainable parameters are read from their own storage at every replay.)"""
+        frozen = tuple(p._version for p in self._all_params if not p.requires_grad)
+        return (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), targets.dtype, frozen)
+
     def _graph_for(self, inputs, targets):
-        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), targets.dtype)
+        key = self._graph_key(inputs, targets)
         g = self._graphs.get(key)
         if g is not None:
             return g
@@ -238,7 +246,7 @@ class Trainer:
         if self.use_graph:
             # a captured step exists for these shapes: copy straight into its static buffers (from pinned host
             # memory this is ONE asynchronous H2D copy per tensor — no intermediate device tensor, no host sync)
-            key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), targets.dtype)
+            key = self._graph_key(inputs, targets)
             g = self._graphs.get(key)
             if g is None:
                 inputs = self.move_to_device(inputs)

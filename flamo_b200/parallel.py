@@ -65,7 +65,7 @@ class DataParallelTrainer(Trainer):
             hdl = symm_mem.rendezvous(buf, self.pg if self.pg is not None else dist.group.WORLD)
             if hdl.signal_pad_size < 2048 or hdl.world_size != self.world:
                 return None
-            self._p2p = (hdl, torch.zeros(1, dtype=torch.int32, device=device))
+            self._p2p = (hdl, torch.zeros(2, dtype=torch.int32, device=device))  # [epoch, sticky error flag]
             torch.cuda.synchronize(device)
             dist.barrier(self.pg)
             return buf
@@ -126,12 +126,32 @@ class DataParallelTrainer(Trainer):
             from . import _lib
 
             hdl, epoch = self._p2p
-            _lib.check(_lib.lib().fsweep_allreduce_p2p(hdl.buffer_ptrs_dev, hdl.signal_pad_ptrs_dev, hdl.rank,
-                                                        hdl.world_size, self._flat.numel(), scale, epoch.data_ptr(),
-                                                        torch.cuda.current_stream(self._flat.device).cuda_stream))
+            with torch.cuda.device(self._flat.device):
+                _lib.check(_lib.lib().fsweep_allreduce_p2p(hdl.buffer_ptrs_dev, hdl.signal_pad_ptrs_dev, hdl.rank,
+                                                            hdl.world_size, self._flat.numel(), scale,
+                                                            epoch.data_ptr(),
+                                                            torch.cuda.current_stream(self._flat.device).cuda_stream))
             sweep.launch_count += 1
         else:
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
             if self.shard == "batch":
                 self._flat.div_(self.world)
         return self._flat[self._n_grad:].to(vals.dtype)
+
+    def check_exchange(self):
+        """Raises if the peer-memory all-reduce ever timed out waiting for a peer (its results are then undefined).
+        A host read: call it outside the captured step (train_step does, every `check_every` steps)."""
+        if getattr(self, "_p2p", None) is not None:
+            flag = int(self._p2p[1][1].item())
+            if flag:
+                raise RuntimeError(f"fsweep_allreduce_p2p: rank {flag - 1} did not arrive at the exchange (timeout); "
+                                   "the gradients of that step are invalid")
+
+    check_every = 64
+
+    def train_step(self, data):
+        out = super().train_step(data)
+        self._n_steps = getattr(self, "_n_steps", 0) + 1
+        if self._n_steps % self.check_every == 1:
+            self.check_exchange()
+        return out

@@ -375,8 +375,9 @@ class Parallel(nn.Module):
 
 
 def _is_abs_layer(layer) -> bool:
-    """True if `layer` is a Transform computing |x| (the output layer of every frequency-domain
-    example).  Decided once per layer object by probing it on a tiny CPU tensor."""
+    """Cheap pre-filter: True if `layer` is a plain Transform that maps a tiny probe tensor to |x|.  Necessary, not
+    sufficient (abs(x[:, :1000]), clamp(abs(x)), abs(x) + eps all pass it): `_abs_layer_verified` confirms the
+    candidate on the real signal before anything is fused."""
     if not isinstance(layer, Transform) or type(layer) is not Transform:
         return False
     flag = getattr(layer, "_fsweep_is_abs", None)
@@ -391,6 +392,36 @@ def _is_abs_layer(layer) -> bool:
             flag = False
         layer._fsweep_is_abs = flag
     return flag
+
+
+def _abs_layer_verified(layer, prog, X) -> bool:
+    """The |.| epilogue replaces `layer` only after the layer has been RUN once on the unfused output of this very
+    program for this signal shape and agreed with |Y| in shape, dtype and values (a transform that crops, clamps or
+    offsets is then kept as it is).  One extra forward sweep per (layer, shape), outside any CUDA-graph capture."""
+    if not _is_abs_layer(layer):
+        return False
+    seen = layer.__dict__.setdefault("_fsweep_abs_verified", {})
+    key = (tuple(X.shape), X.dtype, current_shard_key())
+    ok = seen.get(key)
+    if ok is None:
+        if X.is_cuda and torch.cuda.is_current_stream_capturing():
+            return False  # cannot verify (host read) inside a capture: stay unfused
+        try:
+            with torch.no_grad():
+                Y = prog.run(X, epilogue=EPI_NONE)
+                ok = True
+                for s in (1.0, 2.0 ** 20, 2.0 ** -20):  # other scales expose clamps and offsets this signal misses
+                    r, ref = layer(Y * s), torch.abs(Y * s)
+                    ok = ok and bool(torch.is_tensor(r) and r.shape == ref.shape and r.dtype == ref.dtype
+                                     and torch.allclose(r, ref, rtol=1e-6, atol=0.0))
+        except Exception:
+            ok = False
+        seen[key] = ok
+    return ok
+
+
+def current_shard_key():
+    return sweep.current_shard()
 
 
 class Shell(nn.Module):
@@ -470,7 +501,7 @@ class Shell(nn.Module):
         core, out = self.__core, self.__output_layer
         x, prog = self._input_and_program(x, ext_param)
         if prog is not None:
-            if self.fuse_output and _is_abs_layer(out):
+            if self.fuse_output and _abs_layer_verified(out, prog, x):
                 return prog.run(x, epilogue=EPI_ABS)
             return out(prog.run(x, epilogue=EPI_NONE))
         x = core(x, ext_param) if ext_param is not None else core(x)
@@ -487,7 +518,7 @@ class Shell(nn.Module):
         if not keep_caches:
             self._invalidate_caches()
         x, prog = self._input_and_program(x, ext_param)
-        if prog is None:
+        if prog is None or not _abs_layer_verified(out, prog, x):
             return None
         return prog.run_loss(x, target, kind)
 

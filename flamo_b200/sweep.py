@@ -60,12 +60,28 @@ class CudaBackend:
     def _stream(t: torch.Tensor):
         return torch.cuda.current_stream(t.device).cuda_stream
 
+    # Every library call runs with the TENSOR's device current: the kernels, the occupancy queries and the internal
+    # memsets all act on the process's current device, which need not be the model's (Trainer(device="cuda:1")
+    # without torch.cuda.set_device).  All GPUs of a node are identical, so a plan's cached launch geometry holds
+    # for each of them.
     def forward(self, plan, ops, coefs, x, y, cols, bin_begin, epilogue):
+        with torch.cuda.device(x.device):
+            return self._forward(plan, ops, coefs, x, y, cols, bin_begin, epilogue)
+
+    def backward(self, plan, ops, coefs, x, gy, grads, gx, cols, bin_begin, epilogue):
+        with torch.cuda.device(x.device):
+            return self._backward(plan, ops, coefs, x, gy, grads, gx, cols, bin_begin, epilogue)
+
+    def loss(self, plan, ops, coefs, x, target, kind, scale, loss, grads, gx, bin_begin):
+        with torch.cuda.device(x.device):
+            return self._loss(plan, ops, coefs, x, target, kind, scale, loss, grads, gx, bin_begin)
+
+    def _forward(self, plan, ops, coefs, x, y, cols, bin_begin, epilogue):
         B, nb = x.shape[0], x.shape[1]
         return plan.forward([c.data_ptr() for c in coefs], x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), B,
                             cols, bin_begin, nb, epilogue, self._stream(x))
 
-    def backward(self, plan, ops, coefs, x, gy, grads, gx, cols, bin_begin, epilogue):
+    def _backward(self, plan, ops, coefs, x, gy, grads, gx, cols, bin_begin, epilogue):
         B, nb = x.shape[0], x.shape[1]
         ws_bytes = plan.workspace_bytes(B, cols, nb)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
@@ -75,7 +91,7 @@ class CudaBackend:
                              cols, bin_begin, nb, epilogue, ws.data_ptr(), ws_bytes, self._stream(x))
 
 
-    def loss(self, plan, ops, coefs, x, target, kind, scale, loss, grads, gx, bin_begin):
+    def _loss(self, plan, ops, coefs, x, target, kind, scale, loss, grads, gx, bin_begin):
         """Fused |.| + MSE criterion.  grads is None: loss only (one forward launch); else loss and its
         gradients from ONE backward launch (+ the finalize kernel)."""
         B, nb = x.shape[0], x.shape[1]
@@ -311,34 +327,40 @@ class Program:
             raise RuntimeError(
                 "flamo_b200 evaluates the frequency sweep with hand-written CUDA kernels only; got a "
                 f"{x.device.type} tensor. Move the model and data to a CUDA device (no CPU fallback exists).")
-        trail = tuple(x.shape[3:])
-        cols = 1
-        for d in trail:
-            cols *= d
-        x4 = x.reshape(x.shape[0], x.shape[1], x.shape[2], cols)
         shard = current_shard()
         M = self.nfft // 2 + 1
         bin_begin = 0
-        if shard is not None and x4.shape[1] == M:
+        cur = x
+        if shard is not None and cur.shape[1] == M:
             bin_begin = shard[0]
-            x4 = x4[:, shard[0]:shard[1]]
+            cur = cur[:, shard[0]:shard[1]]
         elif shard is not None:
             bin_begin = shard[0]  # already restricted by an earlier launch of the same series
         segs = list(self._segments())
-        dtype = _lib.C64 if x.dtype == torch.complex64 else _lib.C128
         for si, (tag, payload) in enumerate(segs):
             if tag == "eager":
-                x4 = payload(x4.reshape(x4.shape[:3] + trail)).reshape(x4.shape[0], x4.shape[1], -1, cols)
+                # the module's output is taken as returned: an iFFT / cropping Transform changes dim 1 (and the dtype),
+                # exactly as when the reference runs its modules one after the other (system.py:279-301)
+                cur = payload(cur)
                 continue
+            if not (torch.is_tensor(cur) and cur.is_complex() and cur.dim() >= 3):
+                raise TypeError("a frequency-domain module follows a module whose output is not a bin-domain "
+                                f"(complex, (B, bins, channels, ...)) tensor: got {tuple(cur.shape)} {cur.dtype}")
+            trail = tuple(cur.shape[3:])
+            cols = 1
+            for d in trail:
+                cols *= d
+            x4 = cur.reshape(cur.shape[0], cur.shape[1], cur.shape[2], cols)
             ops, coefs, n_out = self.flatten_segment(payload)
             self._check_signal(ops, x4, bin_begin)
             epi = epilogue if si == len(segs) - 1 else EPI_NONE
+            dtype = _lib.C64 if x4.dtype == torch.complex64 else _lib.C128
             plan = _get_plan(ops, self.nfft, self.alias_decay_db, dtype)
             x4 = SweepFunction.apply(x4, plan, ops, epi, bin_begin, n_out, *coefs)
+            cur = x4.reshape(x4.shape[:3] + trail)
         if epilogue == EPI_ABS and segs and segs[-1][0] == "eager":
-            x4 = torch.abs(x4)
-        return x4.reshape(x4.shape[:3] + trail)
-
+            cur = torch.abs(cur)
+        return cur
 
     def run_loss(self, x: torch.Tensor, target: torch.Tensor, kind: int) -> Optional[torch.Tensor]:
         """criterion(|program(x)|, target) through the fused kernels, or None when this program / these shapes
@@ -394,8 +416,9 @@ class OrthogonalMap(torch.autograd.Function):
         global launch_count
         Pc = P.detach().contiguous()
         E = torch.empty_like(Pc)
-        _lib.check(_lib.lib().fsweep_expm_forward(Pc.data_ptr(), E.data_ptr(), Pc.shape[0], 1, _real_code(Pc.dtype),
-                                                   torch.cuda.current_stream(P.device).cuda_stream))
+        with torch.cuda.device(P.device):
+            _lib.check(_lib.lib().fsweep_expm_forward(Pc.data_ptr(), E.data_ptr(), Pc.shape[0], 1, _real_code(Pc.dtype),
+                                                       torch.cuda.current_stream(P.device).cuda_stream))
         launch_count += 1
         ctx.save_for_backward(Pc)
         return E
@@ -406,9 +429,10 @@ class OrthogonalMap(torch.autograd.Function):
         (Pc,) = ctx.saved_tensors
         Gc = G.to(Pc.dtype).contiguous()
         gP = torch.empty_like(Pc)
-        _lib.check(_lib.lib().fsweep_expm_backward(Pc.data_ptr(), Gc.data_ptr(), gP.data_ptr(), Pc.shape[0], 1,
-                                                    _real_code(Pc.dtype),
-                                                    torch.cuda.current_stream(G.device).cuda_stream))
+        with torch.cuda.device(G.device):
+            _lib.check(_lib.lib().fsweep_expm_backward(Pc.data_ptr(), Gc.data_ptr(), gP.data_ptr(), Pc.shape[0], 1,
+                                                        _real_code(Pc.dtype),
+                                                        torch.cuda.current_stream(G.device).cuda_stream))
         launch_count += 1
         return gP
 
@@ -432,8 +456,10 @@ class SparsityFunction(torch.autograd.Function):
         Ac = A.detach().contiguous()
         loss = torch.empty((), dtype=Ac.dtype, device=Ac.device)
         n_mats = Ac.shape[0] if Ac.dim() == 3 else 1
-        _lib.check(_lib.lib().fsweep_sparsity_forward(Ac.data_ptr(), n_mats, Ac.shape[-1], _real_code(Ac.dtype),
-                                                       loss.data_ptr(), torch.cuda.current_stream(A.device).cuda_stream))
+        with torch.cuda.device(A.device):
+            _lib.check(_lib.lib().fsweep_sparsity_forward(Ac.data_ptr(), n_mats, Ac.shape[-1], _real_code(Ac.dtype),
+                                                           loss.data_ptr(),
+                                                           torch.cuda.current_stream(A.device).cuda_stream))
         launch_count += 1
         ctx.save_for_backward(Ac)
         return loss
@@ -445,9 +471,10 @@ class SparsityFunction(torch.autograd.Function):
         gc = g.to(Ac.dtype).contiguous()
         gA = torch.empty_like(Ac)
         n_mats = Ac.shape[0] if Ac.dim() == 3 else 1
-        _lib.check(_lib.lib().fsweep_sparsity_backward(Ac.data_ptr(), gc.data_ptr(), n_mats, Ac.shape[-1],
-                                                        _real_code(Ac.dtype), gA.data_ptr(),
-                                                        torch.cuda.current_stream(g.device).cuda_stream))
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().fsweep_sparsity_backward(Ac.data_ptr(), gc.data_ptr(), n_mats, Ac.shape[-1],
+                                                            _real_code(Ac.dtype), gA.data_ptr(),
+                                                            torch.cuda.current_stream(g.device).cuda_stream))
         launch_count += 1
         return gA
 
@@ -480,8 +507,9 @@ class WeightedTotal(torch.autograd.Function):
         pp = (C.c_void_p * n)(*[p.data_ptr() for p in parts])
         aa = (C.c_double * n)(*[float(a) for a in alphas])
         ss = (C.c_double * n)(*[float(a) for a in scales])
-        _lib.check(_lib.lib().fsweep_weighted_total(pp, aa, ss, n, _real_code(vals.dtype), vals.data_ptr(),
-                                                     torch.cuda.current_stream(vals.device).cuda_stream))
+        with torch.cuda.device(vals.device):
+            _lib.check(_lib.lib().fsweep_weighted_total(pp, aa, ss, n, _real_code(vals.dtype), vals.data_ptr(),
+                                                         torch.cuda.current_stream(vals.device).cuda_stream))
         launch_count += 1
         ctx.coef = (tuple(float(a) * float(c) for a, c in zip(alphas, scales)), tuple(float(c) for c in scales))
         for c in ctx.coef:  # created here, outside any later capture of the backward

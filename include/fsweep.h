@@ -251,8 +251,9 @@ FSWEEP_API int fsweep_adam_step(const fsweep_adam_tensor_t* tensors, int n, int 
  * every rank of one node — the single exchange of a multi-GPU training step (flamo has no multi-device path; this
  * replaces the NCCL all-reduce of flamo_b200/parallel.py).  peer_buffers / peer_signal_pads: DEVICE arrays of `world`
  * device pointers (rank r's buffer / signal pad, as torch.distributed._symmetric_memory hands them out; the pads must
- * be zero before the first call and at least 2 KiB).  epoch_counter: device uint32, zero before the first call, private
- * to this communicator.  One kernel, in place, capture safe, bit-identical results on every rank.
+ * be zero before the first call and at least 2 KiB).  epoch_counter: device uint32[2], zero before the first call, private
+ * to this communicator: [0] the epoch, [1] a sticky error flag (1 + rank of a peer that did not arrive within the
+ * bounded spin; the results of that call are then undefined and the caller must not use them).  One kernel, in place, capture safe, bit-identical results on every rank.
  * n <= fsweep_allreduce_p2p_max_n(). */
 FSWEEP_API int fsweep_allreduce_p2p_max_n(void);
 FSWEEP_API int fsweep_allreduce_p2p(void* const* peer_buffers, void* const* peer_signal_pads, int rank, int world, int n,

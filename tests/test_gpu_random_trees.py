@@ -1,11 +1,8 @@
-"""GPU, OPT-IN (FLAMO_B200_EXPERIMENTAL=1): kernels written after round 1's GPU budget was spent and therefore never
-run on a B200.  They are compiled into libfsweep.so but not dispatched unless their own environment switch is set; this
-file is what to run first in the next round:
-
-    FLAMO_B200_EXPERIMENTAL=1 python -m pytest tests/test_gpu_zz_experimental.py -q
-
-* FSWEEP_FINALIZE_V2=1 — fsweep_finalize_v2_kernel (coalesced per-block partial sums): every gradient of every parity
-  case must equal the default finalize kernel's to float rounding (both sum in float64; only the order differs)."""
+"""GPU: (1) the coalesced gradient finalize kernel (fsweep_finalize_v2_kernel, the default since round 2) against the
+round-1 kernel (FSWEEP_FINALIZE_V2=0) on every parity case; (2) the random module trees of
+tests/test_random_trees_cpu.py on the REAL kernels: float64 kernels at 1e-8 / gradients 1e-6, float32 kernels at the
+1e-4 bar; (3) captured vs eager training steps on random trees.  First run green on a B200 in round 2
+(gpurun_out/r02_experimental_all.log: 89 passed; the two failures were test tolerances, see below)."""
 import os
 
 import pytest
@@ -14,13 +11,11 @@ import torch
 import cases as C
 from helpers import build_case
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FLAMO_B200_EXPERIMENTAL", "0") != "1",
-                                 reason="experimental kernels are opt-in (FLAMO_B200_EXPERIMENTAL=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _grads(name, dtype, variant):
-    os.environ["FSWEEP_FINALIZE_V2"] = variant  # read by libfsweep at every backward call
+    os.environ["FSWEEP_FINALIZE_V2"] = variant  # read by libfsweep at every backward call ("0": the round-1 kernel)
     try:
         case, g, model = build_case(name, dtype, "cuda")
         M = case["nfft"] // 2 + 1
@@ -45,16 +40,18 @@ def test_finalize_v2_equals_default(name, dtype):
     if a is None:
         pytest.skip("no trainable parameter")
     b = _grads(name, dtype, "1")
-    eps = 1e-6 if dtype == torch.float32 else 1e-14
+    # both kernels sum the per-block partials in float64; programs whose accumulators overflow shared memory add
+    # float atomics in a flat buffer whose order differs from run to run (cfg4: 1.4e-6 between two runs of the SAME
+    # kernel), hence 5e-6 rather than one ulp
+    eps = 5e-6 if dtype == torch.float32 else 1e-13
     for ga, gb in zip(a, b):
         assert torch.isfinite(gb).all()
         assert float((ga - gb).abs().max()) <= eps * float(ga.abs().max() + 1e-30)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# The random module trees of tests/test_random_trees_cpu.py on the REAL kernels (written after the GPU budget was
-# spent; opt-in until it has been seen green once): float64 kernels at 1e-8 / gradients 1e-6, float32 kernels at the
-# 1e-4 bar (loops are damped by the generator, so conditioning is benign).
+# The random module trees of tests/test_random_trees_cpu.py on the REAL kernels: float64 kernels at 1e-8 / gradients
+# 1e-6, float32 kernels at the 1e-4 bar (loops are damped by the generator, so conditioning is benign).
 from hypothesis import HealthCheck, given, settings  # noqa: E402
 
 from test_random_trees_cpu import NFFT, tree  # noqa: E402
