@@ -495,7 +495,7 @@ class _SectionFilter(Filter):
             self._emit_table(prog, param, upcast=False)
             return
         b, a = self._taps(self.map(self._up(param)))
-        coef = sweep.pack_sections(b, a, self._parallel, prog.real)
+        coef = sweep.pack_sections(b, a, self._parallel, None)
         prog.leaf(OP_PSOS if self._parallel else OP_SOS, self.output_channels, self.input_channels, coef,
                   K=b.shape[1])
 

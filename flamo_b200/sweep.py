@@ -220,6 +220,44 @@ class SweepLossFunction(torch.autograd.Function):
         return (pick(ctx.gx), None, None, None, None, None, None, *[pick(t) for t in ctx.grads])
 
 
+def _cast(coef: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Coefficient in the dtype a launch reads.  Frozen coefficients (no autograd history: DSP._coef_cache keeps
+    them across steps) remember their casts, so a frozen module still costs no launch per step."""
+    if coef.dtype == dtype:
+        return coef
+    if coef.requires_grad:
+        return coef.to(dtype)
+    memo = coef.__dict__.setdefault("_fsweep_cast", {})
+    t = memo.get(dtype)
+    if t is None:
+        t = memo[dtype] = coef.to(dtype)
+    return t
+
+
+def _wants_f64(ops) -> bool:
+    """float32 models whose response float32 ARITHMETIC cannot hold to the 1e-4 magnitude bar are
+    swept by the float64 kernels, with the signal converted on the way in and out (the coefficients come out of the
+    maps in float64 anyway).  Two shapes qualify, both measured (tests/test_numerics_model_cpu.py):
+      * a closed loop wider than 8 channels (and <= 32, the float64 kernels' limit): the output is a sum of > 8
+        solved channels that cancel down to the metric's floor (config 4: 1.3e-4 in float32);
+      * a dense cascade of many second-order sections feeding a wide sum (config 3: 16 x 30 sections per output):
+        the float32 rounding of the packed section coefficients ALONE is 1.1e-4 of the floor there.
+    FLAMO_B200_PRECISION=float32 keeps float32 arithmetic everywhere, =float64 promotes every launch."""
+    mode = os.environ.get("FLAMO_B200_PRECISION", "auto")
+    if mode == "float32":
+        return False
+    if mode == "float64":
+        return all(o[1] <= 32 and o[2] <= 32 for o in ops)
+    if any(o[1] > 32 or o[2] > 32 for o in ops):
+        return False
+    for o in ops:
+        if o[0] == OP_RECURSION and o[1] > 8:
+            return True
+        if o[0] == OP_SOS and o[2] >= 8 and o[2] * o[3] >= 128:
+            return True
+    return False
+
+
 # ---------------------------------------------------------------------------------------------
 class Program:
     """Flat sweep program under construction.  Leaves are (kind, n_out, n_in, K, flags, 0, 0, 0) tuples
@@ -237,12 +275,10 @@ class Program:
     def leaf(self, kind: int, n_out: int, n_in: int, coef: torch.Tensor, K: int = 0, isint: bool = False):
         want = kind in (OP_GAIN, OP_PGAIN, OP_SOS, OP_PSOS, OP_TABLE, OP_PTABLE) or not isint
         flags = (F_ISINT if isint else 0) | (F_GRAD if (coef.requires_grad and torch.is_grad_enabled() and want) else 0)
+        # coefficients stay in the precision their map produced (float64 for every non-identity map); the cast to
+        # the arithmetic type of the launch happens in flatten_segment, once that type is known (_wants_f64)
         if kind in (OP_DELAY, OP_PDELAY):
             coef = coef.to(torch.float64)
-        elif kind in _TABLE:
-            coef = coef.to(self.cdtype)
-        else:
-            coef = coef.to(self.real)
         item = ("leaf", (kind, int(n_out), int(n_in), int(K), flags, 0, 0, 0), coef)
         (self._chain if self._chain is not None else self.items).append(item)
 
@@ -289,8 +325,10 @@ class Program:
             yield ("sweep", seg)
 
     @staticmethod
-    def flatten_segment(payload):
-        """One launch worth of items -> (flat op tuples, coefficient tensors in slot order, n_out)."""
+    def flatten_segment(payload, cdtype=None):
+        """One launch worth of items -> (flat op tuples, coefficient tensors in slot order, n_out).  With `cdtype`
+        (the complex arithmetic type of the launch) the coefficients are cast to what the kernels of that type read:
+        real / complex of that precision, delays float64."""
         ops, coefs = [], []
         for it in payload:
             if it[0] == "leaf":
@@ -304,6 +342,11 @@ class Program:
                     coefs.append(l[2])
         last = payload[-1]
         n_out = last[1][1] if last[0] == "leaf" else last[1]
+        if cdtype is not None:
+            real = torch.float32 if cdtype == torch.complex64 else torch.float64
+            leaf_ops = [o for o in ops if o[0] != OP_RECURSION]
+            coefs = [c if o[0] in (OP_DELAY, OP_PDELAY) else _cast(c, cdtype if o[0] in _TABLE else real)
+                     for o, c in zip(leaf_ops, coefs)]
         return tuple(ops), coefs, n_out
 
     def plan_for(self, ops, cdtype=None):
@@ -354,9 +397,13 @@ class Program:
             ops, coefs, n_out = self.flatten_segment(payload)
             self._check_signal(ops, x4, bin_begin)
             epi = epilogue if si == len(segs) - 1 else EPI_NONE
-            dtype = _lib.C64 if x4.dtype == torch.complex64 else _lib.C128
-            plan = _get_plan(ops, self.nfft, self.alias_decay_db, dtype)
-            x4 = SweepFunction.apply(x4, plan, ops, epi, bin_begin, n_out, *coefs)
+            io_dtype = x4.dtype
+            ex = torch.complex128 if (io_dtype == torch.complex128 or _wants_f64(ops)) else torch.complex64
+            _, coefs, _ = self.flatten_segment(payload, ex)
+            plan = _get_plan(ops, self.nfft, self.alias_decay_db, _lib.C64 if ex == torch.complex64 else _lib.C128)
+            x4 = SweepFunction.apply(x4.to(ex), plan, ops, epi, bin_begin, n_out, *coefs)
+            if ex != io_dtype:  # float32 signal, float64 arithmetic: hand back what a float32 model returns
+                x4 = x4.to(torch.float32 if epi == EPI_ABS else io_dtype)
             cur = x4.reshape(x4.shape[:3] + trail)
         if epilogue == EPI_ABS and segs and segs[-1][0] == "eager":
             cur = torch.abs(cur)
@@ -373,7 +420,9 @@ class Program:
         segs = list(self._segments())
         if len(segs) != 1 or segs[0][0] != "sweep":
             return None
-        ops, coefs, n_out = self.flatten_segment(segs[0][1])
+        ops, _, n_out = self.flatten_segment(segs[0][1])
+        ex = torch.complex128 if (x.dtype == torch.complex128 or _wants_f64(ops)) else torch.complex64
+        _, coefs, _ = self.flatten_segment(segs[0][1], ex)
         B, M = x.shape[0], x.shape[1]
         real = torch.float32 if x.dtype == torch.complex64 else torch.float64
         if kind == CRIT_MSE_CHSUM:  # mse_loss: MSE(sum_r |Y_r|, target.squeeze(-1))
@@ -398,7 +447,10 @@ class Program:
             scale = 1.0 / tgt.numel()  # mean over the shard, as the unfused path computes it
         if x4.shape[1] == 0 or x4.shape[2] != ops[0][2] or bin_begin + x4.shape[1] > self.nfft // 2 + 1:
             return None  # (the unfused path raises the proper error)
-        plan = _get_plan(ops, self.nfft, self.alias_decay_db, _lib.C64 if x.dtype == torch.complex64 else _lib.C128)
+        plan = _get_plan(ops, self.nfft, self.alias_decay_db, _lib.C64 if ex == torch.complex64 else _lib.C128)
+        if ex != x.dtype:  # float32 model, float64 arithmetic (_wants_f64)
+            return SweepLossFunction.apply(x4.to(ex), tgt.to(torch.float64), plan, ops, kind, scale, bin_begin,
+                                           *coefs).to(real)
         return SweepLossFunction.apply(x4, tgt, plan, ops, kind, scale, bin_begin, *coefs)
 
 
@@ -565,4 +617,4 @@ def pack_sections(b: torch.Tensor, a: torch.Tensor, parallel: bool, real: torch.
         packed = packed.permute(2, 3, 0, 1)  # (K, N, 2, 8)
     else:
         packed = packed.permute(2, 4, 3, 0, 1)  # (2, 8, K, N_out, N_in) -> (K, N_in, N_out, 2, 8)
-    return packed.to(real).contiguous()
+    return (packed if real is None else packed.to(real)).contiguous()

@@ -172,7 +172,7 @@ def test_lowering_produces_one_fused_program():
     core._lower(prog, None)
     segs = list(prog._segments())
     assert len(segs) == 1
-    ops, coefs, n_out = prog.flatten_segment(segs[0][1])
+    ops, coefs, n_out = prog.flatten_segment(segs[0][1], torch.complex64)
     kinds = [o[0] for o in ops]
     assert kinds == [_lib.OP_GAIN, _lib.OP_RECURSION, _lib.OP_SOS, _lib.OP_PDELAY, _lib.OP_PGAIN, _lib.OP_DELAY,
                      _lib.OP_PGAIN, _lib.OP_GAIN]

@@ -170,9 +170,8 @@ def test_full_size_properties(name):
         y32 = m32(X.to(torch.complex64))
         y64 = m64(X)
         a32, a64 = np.abs(y32.cpu().numpy()), np.abs(y64.cpu().numpy())
-        # floored relative metric: 1e-4, except where |Y| is a 13/16-term sum cancelling down to the floor
-        # (cfg3, cfg4: float32 rounding of the terms, ~1e-7 of the peak, reads as ~2e-4 of the floor)
-        assert rel_err(a32, a64) < (2.5e-4 if name in ("cfg3_geq16", "cfg4_active") else 1e-4)
+        # floored relative metric over ALL bins (configs 3 and 4 run float64 arithmetic inside: sweep._wants_f64)
+        assert rel_err(a32, a64) < 1e-4
         assert np.abs(a32 - a64).max() / a64.max() < 2e-6
         # linearity: f(a x1 + b x2) = a f(x1) + b f(x2)
         X2 = torch.flip(X, dims=[1]) * (0.3 - 0.8j)
@@ -216,3 +215,49 @@ def test_config5_full_size_properties():
         with sweep.bin_shard(half, M):
             p1 = model(X[:2])
         assert torch.equal(torch.cat((p0, p1), dim=1), y[:2])
+
+
+def _subset(M, n):
+    stride = max(1, M // n)
+    idx = np.unique(np.concatenate([np.arange(min(M, 16)), np.arange(0, M, stride), [M - 1]]))
+    return torch.as_tensor(idx.astype(np.int64))
+
+
+FULL_SIZE_REPORT = {}
+
+
+@pytest.mark.parametrize("name,n_sub", [("cfg1_biquad", 509), ("cfg2_fdn8", 509), ("cfg3_geq16", 509),
+                                         ("cfg4_active", 509), ("cfg5_fdn64", 127)])
+def test_full_size_vs_oracle_bin_subset(name, n_sub):
+    """All five BASELINE.json configs AT FULL SIZE (config 3: nfft 192000, config 5: nfft 384000 / batch 32 / 64 x 64),
+    float32 kernels, against the float64 oracle evaluated in its per-bin closed form on a subset of the bins
+    (oracle.forward(..., bins=idx); the full-M oracle needs 11.8 GB / 201 GB per intermediate for configs 3 / 5):
+    magnitude response within 1e-4 on the floored metric, parameter gradients of
+    mean((sum_ch |Y| - 1)^2) over the subset bins within 1e-3."""
+    desc, nfft, B, seed, _ = W.CONFIGS[name]
+    M = nfft // 2 + 1
+    torch.manual_seed(seed)
+    model = W.build(desc, dsp, system, nfft, W.ALIAS_DECAY_DB, dtype=torch.float32, device=DEV)
+    X = C.make_input(B, M, model.input_channels, None).to(torch.complex64).to(DEV)
+    idx = _subset(M, n_sub)
+    Y = model(X)
+    Ys = Y[:, idx.to(DEV)]
+    params = list(model.parameters())
+    C.golden_loss(Ys).backward()
+    torch.cuda.synchronize()
+    ps = [p.detach().cpu().double().requires_grad_(p.requires_grad) for p in params]
+    Yo = O.forward(O.from_desc(desc), X[:, idx.to(DEV)].cpu().to(torch.complex128), ps, nfft, W.ALIAS_DECAY_DB, bins=idx)
+    go = torch.autograd.grad(C.golden_loss(Yo), [p for p in ps if p.requires_grad])
+    a, ao = np.abs(Ys.detach().cpu().numpy()), np.abs(Yo.detach().numpy())
+    ferr = rel_err(a, ao)
+    gerr, k = 0.0, 0
+    for p in params:
+        if p.requires_grad:
+            assert p.grad is not None
+            ref = go[k].numpy()
+            gerr = max(gerr, float(np.abs(p.grad.cpu().numpy() - ref).max() / (np.abs(ref).max() + 1e-300)))
+            k += 1
+    FULL_SIZE_REPORT[name] = (ferr, gerr)
+    print(f"[full-size parity] {name}: |Y| floored rel err {ferr:.3e}, grad err {gerr:.3e}, bins {len(idx)}")
+    assert ferr <= 1e-4, f"{name}: magnitude rel err {ferr:.3e}"
+    assert gerr <= 1e-3, f"{name}: gradient rel err {gerr:.3e}"

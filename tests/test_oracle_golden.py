@@ -148,3 +148,34 @@ def test_shipped_checkpoint_responses(tag, epoch):
             h = O.time_response(node, params, nfft, alias, n_in)[0, g["taps"]].numpy()
             ref = g[f"{tag}|e{epoch}|h"]
             assert np.abs(h - ref).max() <= 1e-11 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name", ["cfg1_biquad_full", "cfg2_fdn8_full", "cfg3_geq16_small", "cfg4_active_full",
+                                  "cfg5_fdn64_small", "svf_general", "geq_oct3", "delay_mimo_frac", "fir_filter",
+                                  "gaindelay_frac", "recursion_rect"])
+def test_bin_subset_mode_equals_full_sweep(name):
+    """oracle.forward(..., bins=idx) — the per-bin closed form used to check the BASELINE-size configs on a few
+    hundred bins — is the full-M oracle restricted to those bins (response and parameter gradients)."""
+    if name not in C.CASES:
+        pytest.skip("case not in this build")
+    case, g = C.CASES[name], load(name)
+    node = O.from_desc(case["desc"])
+    M = case["nfft"] // 2 + 1
+    X = C.make_input(case["B"], M, _n_in(case["desc"]), case["C"])
+    idx = torch.as_tensor(C.select_bins(M)[::3].copy())
+
+    def run(bins):
+        ps = [p.requires_grad_(f"grad_{i}" in g) for i, p in enumerate(params_of(g))]
+        if bins is None:
+            Y = O.forward(node, X, ps, case["nfft"], case["alias"])[:, idx]
+        else:
+            Y = O.forward(node, X[:, idx], ps, case["nfft"], case["alias"], bins=idx)
+        gp = [p for p in ps if p.requires_grad]
+        gr = torch.autograd.grad(C.golden_loss(Y), gp) if gp else ()
+        return Y.detach().numpy(), [t.numpy() for t in gr]
+
+    Yf, gf = run(None)
+    Ys, gs = run(idx)
+    assert rel_err(Ys, Yf) < 1e-10
+    for a, b in zip(gs, gf):
+        assert np.abs(a - b).max() <= 1e-9 * (np.abs(b).max() + 1e-30)
