@@ -8,7 +8,7 @@ static cudaError_t configure() {
   static bool done = false;  // per instantiation; benign if two host threads race (same values)
   if (done) return cudaSuccess;
   auto k = fsweep_cta_kernel<BWD>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem_bytes());
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem_bytes(BWD));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
@@ -20,17 +20,17 @@ cudaError_t launch_cta(bool bwd, int grid, cudaStream_t st, const ProgK& P, cons
   cudaError_t e = bwd ? configure<true>() : configure<false>();
   if (e != cudaSuccess) return e;
   if (bwd)
-    fsweep_cta_kernel<true><<<grid, CTA_T, cta_smem_bytes(), st>>>(P, L, A, G);
+    fsweep_cta_kernel<true><<<grid, CTA_T, cta_smem_bytes(true), st>>>(P, L, A, G);
   else
-    fsweep_cta_kernel<false><<<grid, CTA_T, cta_smem_bytes(), st>>>(P, L, A, G);
+    fsweep_cta_kernel<false><<<grid, CTA_T, cta_smem_bytes(false), st>>>(P, L, A, G);
   return cudaGetLastError();
 }
 
 cudaError_t occupancy_cta(bool bwd, int* blocks_per_sm) {
   cudaError_t e = bwd ? configure<true>() : configure<false>();
   if (e != cudaSuccess) return e;
-  if (bwd) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fsweep_cta_kernel<true>, CTA_T, cta_smem_bytes());
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fsweep_cta_kernel<false>, CTA_T, cta_smem_bytes());
+  if (bwd) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fsweep_cta_kernel<true>, CTA_T, cta_smem_bytes(true));
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fsweep_cta_kernel<false>, CTA_T, cta_smem_bytes(false));
 }
 
 }  // namespace fsweep

@@ -5,18 +5,20 @@
 // but one thread BLOCK (256 threads) owns one frequency bin, with the per-bin matrix A = I - D(w) W and up to 32
 // right-hand sides resident in shared memory (33 KB + 17 KB), the way a batched small-matrix LAPACK would do it:
 //   * P A = L U: right-looking, the (63-k)^2 trailing update of step k spread over all 256 threads;
-//   * all batch items of the bin are solved TOGETHER (forward / backward substitution on a 64 x 32 block), where the
-//     row-distributed path (two warps per bin, fsweep_kernels.cuh with G = 64) solved them four at a time with two
-//     named barriers per substitution step;
-//   * the output has ONE channel, so the adjoint solve is shared by the whole batch: lambda_b = g_b v with
-//     v = A^-H w_post solved once per bin, and the feedback-matrix gradient collapses to ONE outer product per bin,
-//         dW = Re( (conj(D) v) (sum_b g_b conj(y_b))^T ),
+//   * the loop has ONE input channel, so every right-hand side of a bin is a multiple of one vector: y_b = x_b z with
+//     z = A^-1 (D w_pre) solved once per bin whatever the batch (the reference, system.py:417-425, likewise solves for
+//     the closed-loop response once and applies it to the batch with an einsum); o_b = (w_post . z) x_b;
+//   * the output has ONE channel, so the adjoint solve is shared by the whole batch too: lambda_b = g_b v with
+//     v = A^-H w_post, and the feedback-matrix gradient collapses to ONE outer product per bin,
+//         dW = Re( (conj(D) v) (xbar conj(z))^T ),   xbar = sum_b g_b conj(x_b),
 //     accumulated in 16 registers per thread across all bins of the block: no atomics at all (the row-distributed
 //     path issued 4096 global atomics per bin and batch chunk — 2.5e10 per step of config 5);
 //   * gradients leave the block once, in the `partial` layout fsweep_finalize_kernel sums in float64.
 // Gradients of the diagonal chain (learnable delays / gains inside the loop) are not formed here: such plans stay on
 // the row-distributed kernels (host-checked, plan->cta).
 #pragma once
+#include <type_traits>
+
 #include "fsweep_tpc.cuh"
 
 namespace fsweep {
@@ -24,16 +26,14 @@ namespace fsweep {
 constexpr int CTA_T = 256;    // threads per block
 constexpr int CN = 64;        // padded loop width
 constexpr int CLD = CN + 1;   // row stride of A in float2 (odd: column walks are conflict-free)
-constexpr int CQ = 32;        // right-hand sides per pass
-constexpr int CYLD = CQ + 1;  // row stride of Y
 
 __device__ __forceinline__ float2 cmulj2(float2 a, float2 b) {  // conj(a) * b
   return f2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
 }
 
-constexpr size_t cta_smem_bytes() {
-  return (size_t)(CN * CLD + CN * CYLD + 4 * CN + 2 * CQ + 8 * CQ) * sizeof(float2) + (size_t)(2 * CN) * sizeof(float) +
-         (size_t)(CN + 8) * sizeof(int);
+constexpr size_t cta_smem_bytes(bool bwd) {
+  return (size_t)(CN * CLD + 7 * CN + 16) * sizeof(float2) + (size_t)(2 * CN) * sizeof(float) +
+         (size_t)(2 * CN + 8) * sizeof(int) + (bwd ? (size_t)(CN * CN) * sizeof(float) : 0);
 }
 
 template <bool BWD>
@@ -41,18 +41,18 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
                                                             const __grid_constant__ LoopInfo L, const SweepArgs A, int G) {
   extern __shared__ __align__(16) float2 csm[];
   float2* sA = csm;                 // [CN][CLD]   L\U in place, 1/U_kk on the diagonal
-  float2* sY = sA + CN * CLD;       // [2][CQ]     pivot-entry broadcast of the substitutions (rest: spare)
-  float2* sD = sY + CN * CYLD;      // [CN]  diagonal chain response
+  float2* sD = sA + CN * CLD;       // [CN]  diagonal chain response
   float2* sV = sD + CN;             // [CN]  adjoint vector v, then vd = conj(D) v
-  float2* sT = sV + CN;             // [CN]  T[j] = sum_b g_b conj(y_b[j])
-  float2* sW = sT + CN;             // [CN]  scratch of the adjoint solve
-  float2* sGo = sW + CN;            // [CQ]  output gradients g_b of the pass
-  float2* sX = sGo + CQ;            // [CQ]  inputs x_b of the pass
-  float2* sRed = sX + CQ;           // [8][CQ] cross-warp partial sums
-  float* sWpre = reinterpret_cast<float*>(sRed + 8 * CQ);  // [CN]
+  float2* sZ = sV + CN;             // [CN]  z = A^-1 (D w_pre): every y_b = x_b z
+  float2* sW = sZ + CN;             // [CN]  scratch of the adjoint solve
+  float2* sRed = sW + CN;           // [16] h, S, per-warp partial sums of xbar
+  float2* sL = sRed + 16;           // [2][CN] multipliers of the current elimination step (double buffered)
+  float2* sInv = sL + 2 * CN;       // [CN] reciprocal pivots
+  float* sWpre = reinterpret_cast<float*>(sInv + CN);  // [CN]
   float* sWpost = sWpre + CN;                               // [CN]
   int* sPiv = reinterpret_cast<int*>(sWpost + CN);          // [CN] row map of P A; [CN..]: scalars
-  int* sScalar = sPiv + CN;
+  int* sPos = sPiv + CN;                                    // [CN] inverse row map
+  int* sScalar = sPos + CN;
 
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
@@ -66,11 +66,13 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
   const int Q = A.batch * A.cols;
   const cx<float>* x = reinterpret_cast<const cx<float>*>(A.x);
   double lacc = 0.0;
-  float gw[BWD ? 16 : 1];  // dW_fb entries e = t + 256 i  (m = e >> 6, j = e & 63)
+  // dW_fb entries e = t + 256 i (m = e >> 6, j = e & 63) accumulate across the bins of this block in shared memory
+  // (BWD): the elimination wants every register for the matrix tile
+  float* sGw = reinterpret_cast<float*>(sScalar + 8);  // [CN * CN], BWD only
   float gpre = 0.f, gpost = 0.f;
   if constexpr (BWD) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) gw[i] = 0.f;
+    for (int i = 0; i < 16; ++i) sGw[t + CTA_T * i] = 0.f;
   }
   __syncthreads();
 
@@ -84,316 +86,284 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
         d = cmul(d, op_diag<float>(P.ops[L.ff_begin + i], ctx, t, gd));
       }
       sD[t] = f2(d.x, d.y);
-      sPiv[t] = t;
     }
     __syncthreads();
-    // ---- 2. A = I - D W (rows / columns >= N: identity)
-    for (int e = t; e < CN * CN; e += CTA_T) {
-      const int m = e >> 6, j = e & 63;
-      const float w = (m < N && j < N) ? __ldg(Wfb + m * N + j) : 0.f;
-      const float2 d = sD[m];
-      sA[m * CLD + j] = f2((m == j ? 1.f : 0.f) - d.x * w, -d.y * w);
-    }
-    __syncthreads();
-    // ---- 3. P A = L U
-    for (int k = 0; k < CN; ++k) {
-      if (warp == 0) {  // pivot search in column k, rows k .. 63
-        float best = -1.f;
-        int pr = k;
+    // ---- 2. A = I - D W in REGISTERS (rows / columns >= N: identity).  Warp w owns the columns w + 8 j (j < 8), lane l
+    //         the rows l and l + 32: a 2 x 8 tile per thread.
+    float2 a[2][8];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int r = k + lane + 32 * h;
-          if (r < CN) {
-            const float2 c = sA[r * CLD + k];
-            const float mg = c.x * c.x + c.y * c.y;
-            if (mg > best) {
-              best = mg;
-              pr = r;
+    for (int i = 0; i < 2; ++i) {
+      const int m = lane + 32 * i;
+      const float2 d = sD[m];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = warp + 8 * j;
+        const float w = (m < N && c < N) ? __ldg(Wfb + m * N + c) : 0.f;
+        a[i][j] = f2((m == c ? 1.f : 0.f) - d.x * w, -d.y * w);
+      }
+    }
+    // ---- 3. P A = L U with IMPLICIT partial pivoting, as a producer / consumer pipeline over the warps.  Column k
+    //         belongs to warp k & 7 (slot k >> 3).  Its owner finds the pivot among the rows that have not been pivots
+    //         yet (one REDUX over a packed |.|^2 / row key), scales the column and publishes {pivot row, multipliers
+    //         l[0..63]} (l = 0 for finished rows) with bar.arrive; the other warps bar.sync on it, fetch the pivot
+    //         row's entries of their own columns with a shuffle (that row lives in lane pr & 31 of EVERY warp) and
+    //         update their tiles.  Look-ahead: the owner of column k + 1 updates that column first, factors it and
+    //         publishes before touching its other columns, so the next step's multipliers are normally waiting when
+    //         the consumers arrive.  Nothing but the multipliers crosses shared memory; no CTA-wide barrier.
+    unsigned act = 3u;  // bit i: row lane + 32 i has not been a pivot row yet
+    int pr = 0;
+    float2 l0 = f2(0.f, 0.f), l1 = f2(0.f, 0.f);
+    auto upd = [&](int pr_, float2 la, float2 lb, float2& r0, float2& r1) {
+      float2 u = (pr_ & 32) ? r1 : r0;
+      u.x = __shfl_sync(FULL, u.x, pr_ & 31);
+      u.y = __shfl_sync(FULL, u.y, pr_ & 31);
+      r0 = cnma2(r0, la, u);
+      r1 = cnma2(r1, lb, u);
+    };
+    auto factor = [&](int k, float2& c0, float2& c1, int& pr_, float2& la, float2& lb) {
+      const float m0 = c0.x * c0.x + c0.y * c0.y, m1 = c1.x * c1.x + c1.y * c1.y;
+      // |c|^2 >= 0: its bit pattern orders like an unsigned; the low 6 bits carry the row (ties: lowest row)
+      const unsigned k0 = (act & 1u) ? ((__float_as_uint(m0) & ~63u) | (unsigned)(63 - lane)) + 64u : 0u;
+      const unsigned k1 = (act & 2u) ? ((__float_as_uint(m1) & ~63u) | (unsigned)(31 - lane)) + 64u : 0u;
+      const unsigned key = __reduce_max_sync(FULL, max(k0, k1));
+      pr_ = 63 - (int)(key & 63u);
+      float2 pv = (pr_ & 32) ? c1 : c0;
+      pv.x = __shfl_sync(FULL, pv.x, pr_ & 31);
+      pv.y = __shfl_sync(FULL, pv.y, pr_ & 31);
+      const float id = rcp_t(pv.x * pv.x + pv.y * pv.y);
+      const float2 inv = f2(pv.x * id, -pv.y * id);
+      la = f2(0.f, 0.f);
+      lb = f2(0.f, 0.f);
+      if ((act & 1u) && lane != pr_) c0 = la = cmul2(c0, inv);  // L is kept in place
+      if ((act & 2u) && lane + 32 != pr_) c1 = lb = cmul2(c1, inv);
+      float2* bufL = sL + (k & 1) * CN;
+      bufL[lane] = la;
+      bufL[lane + 32] = lb;
+      if (lane == 0) {
+        sScalar[k & 1] = pr_;
+        sPiv[k] = pr_;  // position k of P A holds original row pr
+        sPos[pr_] = k;
+        sInv[k] = inv;
+      }
+      asm volatile("bar.arrive %0, 256;" ::"r"(3 + (k & 1)) : "memory");
+    };
+    if (warp == 0) factor(0, a[0][0], a[1][0], pr, l0, l1);
+    // One elimination step for this warp.  JK = k >> 3 is static (unrolled), kk = k & 7 a runtime loop index; LAST
+    // says kk == 7 (the next column then lives in slot JK + 1 of warp 0).  Slots > JK are always right of column k;
+    // slot JK only for the warps > kk.
+    auto step = [&](auto JKc, auto LASTc, int kk) {
+      constexpr int JK = decltype(JKc)::value;
+      constexpr bool LAST = decltype(LASTc)::value;
+      const int k = 8 * JK + kk;
+      if (warp != kk) {  // consumer of l_k (its owner kept them in registers)
+        asm volatile("bar.sync %0, 256;" ::"r"(3 + (k & 1)) : "memory");
+        const float2* bufL = sL + (k & 1) * CN;
+        pr = sScalar[k & 1];
+        l0 = bufL[lane];
+        l1 = bufL[lane + 32];
+      }
+      if ((pr & 31) == lane) act &= ~(1u << (pr >> 5));
+      const int opr = pr;
+      const float2 ol0 = l0, ol1 = l1;
+      if constexpr (!LAST) {
+        if (warp > kk) {
+          upd(opr, ol0, ol1, a[0][JK], a[1][JK]);
+          if (warp == kk + 1) factor(k + 1, a[0][JK], a[1][JK], pr, l0, l1);  // look-ahead
+        }
+#pragma unroll
+        for (int j = JK + 1; j < 8; ++j) upd(opr, ol0, ol1, a[0][j], a[1][j]);
+      } else if constexpr (JK < 7) {
+        upd(opr, ol0, ol1, a[0][JK + 1], a[1][JK + 1]);
+        if (warp == 0) factor(k + 1, a[0][JK + 1], a[1][JK + 1], pr, l0, l1);  // look-ahead
+#pragma unroll
+        for (int j = JK + 2; j < 8; ++j) upd(opr, ol0, ol1, a[0][j], a[1][j]);
+      }
+    };
+    auto phase = [&](auto JKc) {
+#pragma unroll 1
+      for (int kk = 0; kk < 7; ++kk) step(JKc, std::false_type{}, kk);
+      step(JKc, std::true_type{}, 7);
+    };
+    phase(std::integral_constant<int, 0>{});
+    phase(std::integral_constant<int, 1>{});
+    phase(std::integral_constant<int, 2>{});
+    phase(std::integral_constant<int, 3>{});
+    phase(std::integral_constant<int, 4>{});
+    phase(std::integral_constant<int, 5>{});
+    phase(std::integral_constant<int, 6>{});
+    phase(std::integral_constant<int, 7>{});
+    // L\U -> shared memory in pivot order (row pos[r] of P A is original row r), reciprocal pivots on the diagonal
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float2* row = sA + sPos[lane + 32 * i] * CLD + warp;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) row[8 * j] = a[i][j];
+    }
+    __syncthreads();
+    if (t < CN) sA[t * CLD + t] = sInv[t];
+    __syncthreads();
+
+    // ---- 4. The loop has ONE input and ONE output channel, so every right-hand side of the bin is a multiple of the
+    //         same vector: y_b = x_b z with z = A^-1 (D w_pre), o_b = h x_b with h = w_post . z — one forward and (BWD)
+    //         one adjoint substitution per bin, whatever the batch.  They run side by side: threads 0..63 solve for z
+    //         (named barrier 1), threads 64..127 for v = A^-H w_post (named barrier 2).
+    if (t < CN) {
+      // L U z = P r,  r = D w_pre:  row i of P r is r[piv[i]]
+      const int src = sPiv[t];
+      const float2 dsrc = sD[src];
+      const float wsrc = sWpre[src];
+      float2 g = f2(dsrc.x * wsrc, dsrc.y * wsrc);
+      const float2* rowA = sA + t * CLD;
+      for (int i = 0; i < CN; ++i) {  // L c = P r (unit lower, column oriented)
+        if (t == i) sZ[i] = g;
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (t > i) g = cnma2(g, rowA[i], sZ[i]);
+      }
+      for (int i = CN - 1; i >= 0; --i) {  // U z = c (reciprocal diagonal stored)
+        if (t == i) {
+          g = cmul2(g, rowA[i]);
+          sZ[i] = g;
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (t < i) g = cnma2(g, rowA[i], sZ[i]);
+      }
+    } else if (BWD && t < 2 * CN) {
+      // v = A^-H w_post:  A^H = U^H L^H P
+      const int tt = t - CN;
+      float2 g = f2(sWpost[tt], 0.f);
+      // U^H w = g  (lower triangular, column-oriented: after w_i is final, g_j -= conj(U[i][j]) w_i for j > i)
+      for (int i = 0; i < CN; ++i) {
+        if (tt == i) {
+          const float2 di = sA[i * CLD + i];
+          g = cmul2(g, f2(di.x, -di.y));
+          sW[i] = g;
+        }
+        asm volatile("bar.sync 2, 64;" ::: "memory");
+        if (tt > i) {
+          const float2 u = sA[i * CLD + tt];
+          const float2 wi = sW[i];
+          g.x -= u.x * wi.x + u.y * wi.y;  // conj(u) * wi
+          g.y -= u.x * wi.y - u.y * wi.x;
+        }
+      }
+      // L^H z = w  (unit upper triangular): z_i final when all j > i are done; z_j -= conj(L[i][j]) z_i for j < i
+      for (int i = CN - 1; i >= 0; --i) {
+        if (tt == i) sW[i] = g;
+        asm volatile("bar.sync 2, 64;" ::: "memory");
+        if (tt < i) {
+          const float2 l = sA[i * CLD + tt];
+          const float2 zi = sW[i];
+          g.x -= l.x * zi.x + l.y * zi.y;
+          g.y -= l.x * zi.y - l.y * zi.x;
+        }
+      }
+      // v[piv[i]] = z_i ; vd = conj(D) v
+      sV[sPiv[tt]] = g;
+      asm volatile("bar.sync 2, 64;" ::: "memory");
+      const float2 v = sV[tt];
+      const float2 dd = sD[tt];
+      asm volatile("bar.sync 2, 64;" ::: "memory");
+      sV[tt] = f2(dd.x * v.x + dd.y * v.y, dd.x * v.y - dd.y * v.x);
+    }
+    __syncthreads();
+    // ---- 5. h = w_post . z (warp 0);  S = sum_m w_pre[m] vd[m] (warp 1, BWD: g_x = g_b S)
+    if (warp < (BWD ? 2 : 1)) {
+      const float* wv = warp == 0 ? sWpost : sWpre;
+      const float2* vec = warp == 0 ? sZ : sV;
+      float sx = 0.f, sy = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float w = wv[lane + 32 * h];
+        sx = fmaf(w, vec[lane + 32 * h].x, sx);
+        sy = fmaf(w, vec[lane + 32 * h].y, sy);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(FULL, sx, o);
+        sy += __shfl_xor_sync(FULL, sy, o);
+      }
+      if (lane == 0) sRed[warp] = f2(sx, sy);
+    }
+    __syncthreads();
+    // ---- 6. the batch: o_b = h x_b, criterion / output gradient g_b, xbar = sum_b g_b conj(x_b)
+    {
+      const float2 hh = sRed[0];
+      const float2 S = BWD ? sRed[1] : f2(0.f, 0.f);
+      float xbx = 0.f, xby = 0.f;
+      for (int q = t; q < Q; q += CTA_T) {
+        const int bb = (A.cols == 1) ? q : q / A.cols, cc = q - bb * A.cols;
+        const size_t ooff = (size_t)bl * A.cols + cc;
+        const cx<float> xv = ld_cx(x + (size_t)bb * A.xbs + ooff);
+        const float ox = hh.x * xv.x - hh.y * xv.y, oy = hh.x * xv.y + hh.y * xv.x;
+        if constexpr (!BWD) {
+          if (epi_fused(A.epilogue)) {
+            const float e = abs_t(ox, oy) - __ldg(reinterpret_cast<const float*>(A.tgt) + (size_t)bb * A.tbs + bl);
+            lacc += (double)e * (double)e;
+          } else if (A.epilogue == FSWEEP_EPI_ABS) {
+            reinterpret_cast<float*>(A.y)[(size_t)bb * A.ybs + ooff] = abs_t(ox, oy);
+          } else {
+            st_cx(reinterpret_cast<cx<float>*>(A.y) + (size_t)bb * A.ybs + ooff, mk<float>(ox, oy));
+          }
+        } else {
+          float2 go = f2(0.f, 0.f);
+          if (A.epilogue == FSWEEP_EPI_NONE) {
+            const cx<float> g = ld_cx(reinterpret_cast<const cx<float>*>(A.gy) + (size_t)bb * A.gybs + ooff);
+            go = f2(g.x, g.y);
+          } else {
+            const float mag = abs_t(ox, oy);
+            float gabs;
+            if (epi_fused(A.epilogue)) {
+              const float e = mag - __ldg(reinterpret_cast<const float*>(A.tgt) + (size_t)bb * A.tbs + bl);
+              lacc += (double)e * (double)e;
+              gabs = (float)(2.0 * A.crit_scale) * e;
+            } else {
+              gabs = __ldg(reinterpret_cast<const float*>(A.gy) + (size_t)bb * A.gybs + ooff);
+            }
+            if (mag > 0.f) {
+              const float s = gabs * rcp_t(mag);
+              go = f2(s * ox, s * oy);
             }
           }
+          xbx += go.x * xv.x + go.y * xv.y;  // g conj(x)
+          xby += go.y * xv.x - go.x * xv.y;
+          if (A.gx != nullptr)
+            st_cx(reinterpret_cast<cx<float>*>(A.gx) + (size_t)bb * A.gxbs + ooff,
+                  mk<float>(go.x * S.x - go.y * S.y, go.x * S.y + go.y * S.x));
         }
+      }
+      if constexpr (BWD) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          const float ob = __shfl_xor_sync(FULL, best, o);
-          const int op_ = __shfl_xor_sync(FULL, pr, o);
-          if (ob > best || (ob == best && op_ < pr)) {
-            best = ob;
-            pr = op_;
-          }
+          xbx += __shfl_xor_sync(FULL, xbx, o);
+          xby += __shfl_xor_sync(FULL, xby, o);
         }
-        if (lane == 0) sScalar[0] = pr;
+        if (lane == 0) sRed[2 + warp] = f2(xbx, xby);
       }
-      __syncthreads();
-      const int pr = sScalar[0];
-      if (pr != k) {  // uniform
-        if (t < CN) {
-          const float2 a = sA[k * CLD + t];
-          sA[k * CLD + t] = sA[pr * CLD + t];
-          sA[pr * CLD + t] = a;
-        } else if (t == CN) {
-          const int a = sPiv[k];
-          sPiv[k] = sPiv[pr];
-          sPiv[pr] = a;
-        }
-        __syncthreads();
-      }
-      const float2 d = sA[k * CLD + k];
-      const float id = rcp_t(d.x * d.x + d.y * d.y);
-      const float2 inv = f2(d.x * id, -d.y * id);
-      if (t < CN - 1 - k) {
-        const int r = k + 1 + t;
-        sA[r * CLD + k] = cmul2(sA[r * CLD + k], inv);
-      }
-      __syncthreads();
-      if (t == 0) sA[k * CLD + k] = inv;  // nobody reads the diagonal during the update
-      {
-        // trailing update: thread (ty, tx) owns rows k+1+ty+16i and columns k+1+tx+16jj; its (up to four) pivot-row
-        // entries are loaded once per step
-        const int ty = t >> 4, tx = t & 15;
-        const int j0 = k + 1 + tx;
-        float2 u[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) u[jj] = (j0 + 16 * jj < CN) ? sA[k * CLD + j0 + 16 * jj] : f2(0.f, 0.f);
-        for (int r = k + 1 + ty; r < CN; r += 16) {
-          const float2 l = sA[r * CLD + k];
-          float2* row = sA + r * CLD + j0;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            if (j0 + 16 * jj < CN) row[16 * jj] = cnma2(row[16 * jj], l, u[jj]);
-        }
-      }
-      __syncthreads();
     }
-
     if constexpr (BWD) {
-      // ---- 4. v = A^-H w_post, once per bin (threads 0..63, named barrier 1): A^H = U^H L^H P
-      if (t < CN) {
-        float2 g = f2(sWpost[t], 0.f);
-        // U^H w = g  (lower triangular, column-oriented: after w_i is final, g_j -= conj(U[i][j]) w_i for j > i)
-        for (int i = 0; i < CN; ++i) {
-          if (t == i) {
-            const float2 di = sA[i * CLD + i];
-            g = cmul2(g, f2(di.x, -di.y));
-            sW[i] = g;
-          }
-          asm volatile("bar.sync 1, 64;" ::: "memory");
-          if (t > i) {
-            const float2 u = sA[i * CLD + t];
-            const float2 wi = sW[i];
-            g.x -= u.x * wi.x + u.y * wi.y;  // conj(u) * wi
-            g.y -= u.x * wi.y - u.y * wi.x;
-          }
-        }
-        // L^H z = w  (unit upper triangular): z_i final when all j > i are done; z_j -= conj(L[i][j]) z_i for j < i
-        for (int i = CN - 1; i >= 0; --i) {
-          if (t == i) sW[i] = g;
-          asm volatile("bar.sync 1, 64;" ::: "memory");
-          if (t < i) {
-            const float2 l = sA[i * CLD + t];
-            const float2 zi = sW[i];
-            g.x -= l.x * zi.x + l.y * zi.y;
-            g.y -= l.x * zi.y - l.y * zi.x;
-          }
-        }
-        // v[piv[i]] = z_i ; vd = conj(D) v
-        sV[sPiv[t]] = g;
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        const float2 v = sV[t];
-        const float2 dd = sD[t];
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        sV[t] = f2(dd.x * v.x + dd.y * v.y, dd.x * v.y - dd.y * v.x);
-        sT[t] = f2(0.f, 0.f);
-      }
-      if (t == 0) {
-        sRed[0] = f2(0.f, 0.f);  // unused here; keeps the scratch initialised
-      }
       __syncthreads();
-    }
-    float2 xbar = f2(0.f, 0.f);  // sum_b g_b conj(x_b) (thread 0)
-
-    // ---- passes of up to CQ right-hand sides
-    for (int q0 = 0; q0 < Q; q0 += CQ) {
-      const int nq = min(CQ, Q - q0);
-      if (t < CQ) {
-        float2 xv = f2(0.f, 0.f);
-        if (t < nq) {
-          const int q = q0 + t, b = (A.cols == 1) ? q : q / A.cols, cc = q - b * A.cols;
-          const cx<float> v = ld_cx(x + (size_t)b * A.xbs + (size_t)bl * A.cols + cc);
-          xv = f2(v.x, v.y);
-        }
-        sX[t] = xv;
+      // ---- 7. this bin's gradient contributions, with T[j] = sum_b g_b conj(y_b[j]) = conj(z_j) xbar:
+      //         dW[m][j] += Re(vd[m] T[j]),  dw_post[m] += Re T[m],  dw_pre[m] += Re(vd[m] xbar)
+      float2 xb = f2(0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < CTA_T / 32; ++w) {
+        xb.x += sRed[2 + w].x;
+        xb.y += sRed[2 + w].y;
       }
-      __syncthreads();
-      // A warp owns rows ty, ty + 8, ..., ty + 56 and a lane one right-hand side: the thread's eight entries of the
-      // solution block stay in REGISTERS through both substitutions; only the pivot entry of each step crosses
-      // shared memory (double buffered: one barrier per step).
-      const int ty = warp, b = lane;
-      float2 yr[8];
-      {
-        const float2 xb = sX[b];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {  // right-hand side, already row-permuted: Y'[r][b] = D[p_r] w_pre[p_r] x_b
-          const int src = sPiv[ty + 8 * i];
-          const float2 d = sD[src];
-          const float w = sWpre[src];
-          yr[i] = cmul2(f2(d.x * w, d.y * w), xb);
-        }
-      }
-      float2* sBk = sY;  // [2][CQ] pivot-entry broadcast
-      // forward substitution (unit lower): step k = 8p + kk is owned by warp kk, register p
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-#pragma unroll 1
-        for (int kk = 0; kk < 8; ++kk) {
-          const int k = 8 * p + kk;
-          if (ty == kk) sBk[(k & 1) * CQ + b] = yr[p];
-          __syncthreads();
-          const float2 yk = sBk[(k & 1) * CQ + b];
-          if (ty > kk) yr[p] = cnma2(yr[p], sA[(ty + 8 * p) * CLD + k], yk);
-#pragma unroll
-          for (int i = p + 1; i < 8; ++i) yr[i] = cnma2(yr[i], sA[(ty + 8 * i) * CLD + k], yk);
-        }
-      }
-      // backward substitution (upper, reciprocal diagonal)
-#pragma unroll
-      for (int p = 7; p >= 0; --p) {
-#pragma unroll 1
-        for (int kk = 7; kk >= 0; --kk) {
-          const int k = 8 * p + kk;
-          if (ty == kk) {  // (buffer parity flipped w.r.t. the forward pass: its last step used buffer 1)
-            yr[p] = cmul2(yr[p], sA[k * CLD + k]);
-            sBk[((k + 1) & 1) * CQ + b] = yr[p];
-          }
-          __syncthreads();
-          const float2 xk = sBk[((k + 1) & 1) * CQ + b];
-          if (ty < kk) yr[p] = cnma2(yr[p], sA[(ty + 8 * p) * CLD + k], xk);
-#pragma unroll
-          for (int i = 0; i < p; ++i) yr[i] = cnma2(yr[i], sA[(ty + 8 * i) * CLD + k], xk);
-        }
-      }
-      // ---- output o_b = w_post . y_b
-      {
-        float ox = 0.f, oy = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float w = sWpost[ty + 8 * i];
-          ox = fmaf(w, yr[i].x, ox);
-          oy = fmaf(w, yr[i].y, oy);
-        }
-        sRed[ty * CQ + b] = f2(ox, oy);
-      }
-      __syncthreads();
-      if (t < CQ) {
-        float ox = 0.f, oy = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          ox += sRed[w * CQ + t].x;
-          oy += sRed[w * CQ + t].y;
-        }
-        float2 go = f2(0.f, 0.f);
-        if (t < nq) {
-          const int q = q0 + t, bb = (A.cols == 1) ? q : q / A.cols, cc = q - bb * A.cols;
-          const size_t ooff = (size_t)bl * A.cols + cc;
-          if constexpr (!BWD) {
-            if (epi_fused(A.epilogue)) {
-              const float e = abs_t(ox, oy) - __ldg(reinterpret_cast<const float*>(A.tgt) + (size_t)bb * A.tbs + bl);
-              lacc += (double)e * (double)e;
-            } else if (A.epilogue == FSWEEP_EPI_ABS) {
-              reinterpret_cast<float*>(A.y)[(size_t)bb * A.ybs + ooff] = abs_t(ox, oy);
-            } else {
-              st_cx(reinterpret_cast<cx<float>*>(A.y) + (size_t)bb * A.ybs + ooff, mk<float>(ox, oy));
-            }
-          } else {
-            if (A.epilogue == FSWEEP_EPI_NONE) {
-              const cx<float> g = ld_cx(reinterpret_cast<const cx<float>*>(A.gy) + (size_t)bb * A.gybs + ooff);
-              go = f2(g.x, g.y);
-            } else {
-              const float mag = abs_t(ox, oy);
-              float gabs;
-              if (epi_fused(A.epilogue)) {
-                const float e = mag - __ldg(reinterpret_cast<const float*>(A.tgt) + (size_t)bb * A.tbs + bl);
-                lacc += (double)e * (double)e;
-                gabs = (float)(2.0 * A.crit_scale) * e;
-              } else {
-                gabs = __ldg(reinterpret_cast<const float*>(A.gy) + (size_t)bb * A.gybs + ooff);
-              }
-              if (mag > 0.f) {
-                const float s = gabs * rcp_t(mag);
-                go = f2(s * ox, s * oy);
-              }
-            }
-          }
-        }
-        sGo[t] = go;
-      }
-      __syncthreads();
-      if constexpr (BWD) {
-        // T[j] += sum_b g_b conj(y_b[j]);  xbar += sum_b g_b conj(x_b);  g_x = g_b * sum_m w_pre[m] vd[m]
-        const float2 go = sGo[b];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = ty + 8 * i;
-          const float2 y = yr[i];
-          float vx = go.x * y.x + go.y * y.y, vy = go.y * y.x - go.x * y.y;  // g conj(y)
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            vx += __shfl_xor_sync(FULL, vx, o);
-            vy += __shfl_xor_sync(FULL, vy, o);
-          }
-          if (lane == 0) {
-            float2 acc = sT[j];
-            acc.x += vx;
-            acc.y += vy;
-            sT[j] = acc;  // row j belongs to warp j & 7 only
-          }
-        }
-        if (warp == 0) {
-          const float2 xv = sX[b];
-          float vx = go.x * xv.x + go.y * xv.y, vy = go.y * xv.x - go.x * xv.y;
-          float sx = 0.f, sy = 0.f;  // S = sum_m w_pre[m] vd[m], two rows per lane
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float w = sWpre[lane + 32 * h];
-            sx = fmaf(w, sV[lane + 32 * h].x, sx);
-            sy = fmaf(w, sV[lane + 32 * h].y, sy);
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            vx += __shfl_xor_sync(FULL, vx, o);
-            vy += __shfl_xor_sync(FULL, vy, o);
-            sx += __shfl_xor_sync(FULL, sx, o);
-            sy += __shfl_xor_sync(FULL, sy, o);
-          }
-          xbar.x += vx;
-          xbar.y += vy;
-          if (A.gx != nullptr && lane < nq) {
-            const int q = q0 + lane, bb = (A.cols == 1) ? q : q / A.cols, cc = q - bb * A.cols;
-            st_cx(reinterpret_cast<cx<float>*>(A.gx) + (size_t)bb * A.gxbs + (size_t)bl * A.cols + cc,
-                  mk<float>(go.x * sx - go.y * sy, go.x * sy + go.y * sx));
-          }
-        }
-        __syncthreads();
-      }
-    }
-
-    if constexpr (BWD) {
-      // ---- 5. this bin's gradient contributions:  dW[m][j] += Re(vd[m] T[j]),  dw_post[m] += Re T[m],
-      //         dw_pre[m] += Re(vd[m] xbar)
-      if (t == 0) sRed[0] = xbar;
-      __syncthreads();
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int e = t + CTA_T * i, m = e >> 6, j = e & 63;
-        const float2 vd = sV[m], tj = sT[j];
-        gw[i] = fmaf(vd.x, tj.x, fmaf(-vd.y, tj.y, gw[i]));
+        const float2 vd = sV[m], tj = cmulj2(sZ[j], xb);
+        sGw[e] = fmaf(vd.x, tj.x, fmaf(-vd.y, tj.y, sGw[e]));
       }
       if (t < CN) {
-        const float2 vd = sV[t], xb = sRed[0];
-        gpost += sT[t].x;
+        const float2 vd = sV[t], tj = cmulj2(sZ[t], xb);
+        gpost += tj.x;
         gpre = fmaf(vd.x, xb.x, fmaf(-vd.y, xb.y, gpre));
       }
-      __syncthreads();
     }
+    __syncthreads();
   }
 
   if constexpr (BWD) {
@@ -405,7 +375,7 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int e = t + CTA_T * i, m = e >> 6, j = e & 63;
-        if (m < N && j < N) partial[(fbop.row_off + j) * G + m] = gw[i];
+        if (m < N && j < N) partial[(fbop.row_off + j) * G + m] = sGw[e];
       }
     }
     if (t < N) {
