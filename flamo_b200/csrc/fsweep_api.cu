@@ -12,6 +12,10 @@
 #include <vector>
 
 #include "fsweep_cta.cuh"
+
+#ifndef FSWEEP_CTA_TC_DEFAULT
+#define FSWEEP_CTA_TC_DEFAULT false  // FSWEEP_CTA_TC=1 selects the tensor-core elimination per plan
+#endif
 #include "fsweep_stream.cuh"
 
 using namespace fsweep;
@@ -75,6 +79,7 @@ struct fsweep_plan {
   bool stream = false;  // TABLE-heavy program without recursion: streaming kernels, fsweep_stream.cuh
   StreamInfo sinfo;     // everything but tb / qc / threads (chosen per call from batch*cols)
   bool cta = false;  // wide flagship shape (32 < N <= 64, float32): CTA-per-bin kernels, fsweep_cta.cuh
+  bool cta_tc = false;  // ... with the tensor-core elimination (fsweep_tc.cuh) instead of the SIMT one
   int cta_blocks_per_sm[2] = {0, 0};
   int tpc_np = 0;  // 4 / 8: the flagship shape (N x 1 gain, loop width <= 8, 1 x N gain) -> compact kernels, fsweep_tpc.cuh
   bool tpc_force = false;  // FSWEEP_FORCE_TPC=1 (tests)
@@ -229,6 +234,8 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
     for (int i : ff) ok = ok && kind_is_diag(ops[i].kind) && !(ops[i].flags & FSWEEP_F_GRAD);
     if (ok) {
       p->cta = true;
+      const char* tc_env = getenv("FSWEEP_CTA_TC");
+      p->cta_tc = tc_env ? tc_env[0] == '1' : FSWEEP_CTA_TC_DEFAULT;
       memset(&p->loop, 0, sizeof(p->loop));
       p->loop.pre = slot_of[pre[0]];
       p->loop.ff_begin = slot_of[ff[0]];
@@ -478,7 +485,7 @@ int cta_grid(fsweep_plan* p, bool bwd, int64_t n_bins, cudaError_t* err) {
   }
   if (p->cta_blocks_per_sm[bwd] == 0) {
     int n = 0;
-    if ((*err = occupancy_cta(bwd, &n)) != cudaSuccess) return 0;
+    if ((*err = occupancy_cta(bwd, p->cta_tc, &n)) != cudaSuccess) return 0;
     if (n < 1) {
       *err = cudaErrorLaunchOutOfResources;
       return 0;
@@ -565,6 +572,7 @@ int check_common(const fsweep_plan* plan, const void* const* coeffs, const void*
 
 extern "C" const char* fsweep_plan_kernel_family(const fsweep_plan_t* plan, int64_t n_bins, int backward) {
   if (!plan) return "";
+  if (plan->cta && plan->cta_tc) return backward ? "fsweep_cta_kernel<bwd,tc> (tcgen05 LU)" : "fsweep_cta_kernel<fwd,tc> (tcgen05 LU)";
   if (plan->cta) return backward ? "fsweep_cta_kernel<bwd>" : "fsweep_cta_kernel<fwd>";
   if (plan->stream) return backward ? "fsweep_stream_kernel<bwd> (batch*cols a power of two <= 16)" : "fsweep_stream_kernel<fwd> (batch*cols a power of two <= 16)";
   if (use_tpc(plan, n_bins)) return backward ? "fsweep_tpc_kernel<NP,bwd>" : "fsweep_tpc_kernel<NP,fwd>";
@@ -697,7 +705,7 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
   size_t ssmem = 0;
   if (plan->cta) {
     cfg.grid = cta_grid(plan, false, n_bins, &e);
-    if (e == cudaSuccess) e = launch_cta(false, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
+    if (e == cudaSuccess) e = launch_cta(false, plan->cta_tc, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
   } else if (!crit && stream_setup(plan, batch * cols, false, &SI, &ssmem)) {
     int bps = plan->stream_bps_smem[0] == ssmem ? plan->stream_bps[0] : 0;
     if (bps == 0) {
@@ -875,7 +883,7 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   size_t ssmem = 0;
   if (plan->cta) {
     cfg.grid = cta_grid(plan, true, n_bins, &e);
-    if (e == cudaSuccess) e = launch_cta(true, cfg.grid, st, P, plan->loop, A, plan->G);
+    if (e == cudaSuccess) e = launch_cta(true, plan->cta_tc, cfg.grid, st, P, plan->loop, A, plan->G);
   } else if (!crit && stream_setup(plan, batch * cols, true, &SI, &ssmem)) {
     int bps = plan->stream_bps_smem[1] == ssmem ? plan->stream_bps[1] : 0;
     if (bps == 0) {

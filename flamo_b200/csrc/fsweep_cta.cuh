@@ -20,6 +20,7 @@
 #include <type_traits>
 
 #include "fsweep_tpc.cuh"
+#include "fsweep_tc.cuh"
 
 namespace fsweep {
 
@@ -31,13 +32,15 @@ __device__ __forceinline__ float2 cmulj2(float2 a, float2 b) {  // conj(a) * b
   return f2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
 }
 
-constexpr size_t cta_smem_bytes(bool bwd) {
+constexpr size_t cta_smem_bytes(bool bwd, bool tc) {
   return (size_t)(CN * CLD + 7 * CN + 16) * sizeof(float2) + (size_t)(2 * CN) * sizeof(float) +
-         (size_t)(2 * CN + 8) * sizeof(int) + (bwd ? (size_t)(CN * CN) * sizeof(float) : 0);
+         (size_t)(2 * CN + 8) * sizeof(int) +
+         (tc ? (size_t)CN * sizeof(int) + 16 : (bwd ? (size_t)(CN * CN) * sizeof(float) : 0));
 }
+static_assert(tc::scratch_bytes() <= (size_t)CN * CLD * sizeof(float2), "tensor-core scratch must fit in the L\\U area");
 
-template <bool BWD>
-__global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_constant__ ProgK P,
+template <bool BWD, bool TC>
+__global__ void __launch_bounds__(TC ? tc::T : CTA_T, TC ? 5 : 4) fsweep_cta_kernel(const __grid_constant__ ProgK P,
                                                             const __grid_constant__ LoopInfo L, const SweepArgs A, int G) {
   extern __shared__ __align__(16) float2 csm[];
   float2* sA = csm;                 // [CN][CLD]   L\U in place, 1/U_kk on the diagonal
@@ -66,13 +69,26 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
   const int Q = A.batch * A.cols;
   const cx<float>* x = reinterpret_cast<const cx<float>*>(A.x);
   double lacc = 0.0;
-  // dW_fb entries e = t + 256 i (m = e >> 6, j = e & 63) accumulate across the bins of this block in shared memory
-  // (BWD): the elimination wants every register for the matrix tile
-  float* sGw = reinterpret_cast<float*>(sScalar + 8);  // [CN * CN], BWD only
+  constexpr int NT = TC ? tc::T : CTA_T;  // threads per block
+  constexpr int NGW = CN * CN / NT;       // dW_fb entries per thread: e = t + NT i (m = e >> 6, j = e & 63)
+  // SIMT elimination: the dW_fb accumulators live in shared memory across the bins of this block (the elimination
+  // wants every register for the matrix tile); tensor-core elimination: the matrix is in TMEM, so they are registers
+  float* sGw = reinterpret_cast<float*>(sScalar + 8);  // [CN * CN], BWD && !TC only
+  int* sFin = sScalar + 8;                              // [CN], TC only
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(sFin + CN);  // TC only (8-byte aligned: every array above is)
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1);
+  float gwr[(BWD && TC) ? NGW : 1];
+  tc::State TS;
+  if constexpr (TC) tc::setup(TS, sTmem, sBar);
   float gpre = 0.f, gpost = 0.f;
   if constexpr (BWD) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sGw[t + CTA_T * i] = 0.f;
+    for (int i = 0; i < NGW; ++i) {
+      if constexpr (TC)
+        gwr[i] = 0.f;
+      else
+        sGw[t + NT * i] = 0.f;
+    }
   }
   __syncthreads();
 
@@ -88,6 +104,10 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
       sD[t] = f2(d.x, d.y);
     }
     __syncthreads();
+    if constexpr (TC) {
+      // ---- 2 + 3 on the tensor cores: the matrix lives in TMEM, rank-8 updates as 3 x TF32 tcgen05.mma (fsweep_tc.cuh)
+      tc::lu<CLD>(TS, sA, sD, Wfb, N, sPiv, sPos, sFin, sInv);
+    } else {
     // ---- 2. A = I - D W in REGISTERS (rows / columns >= N: identity).  Warp w owns the columns w + 8 j (j < 8), lane l
     //         the rows l and l + 32: a 2 x 8 tile per thread.
     float2 a[2][8];
@@ -203,6 +223,7 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
     __syncthreads();
     if (t < CN) sA[t * CLD + t] = sInv[t];
     __syncthreads();
+    }
 
     // ---- 4. The loop has ONE input and ONE output channel, so every right-hand side of the bin is a multiple of the
     //         same vector: y_b = x_b z with z = A^-1 (D w_pre), o_b = h x_b with h = w_post . z — one forward and (BWD)
@@ -291,7 +312,7 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
       const float2 hh = sRed[0];
       const float2 S = BWD ? sRed[1] : f2(0.f, 0.f);
       float xbx = 0.f, xby = 0.f;
-      for (int q = t; q < Q; q += CTA_T) {
+      for (int q = t; q < Q; q += NT) {
         const int bb = (A.cols == 1) ? q : q / A.cols, cc = q - bb * A.cols;
         const size_t ooff = (size_t)bl * A.cols + cc;
         const cx<float> xv = ld_cx(x + (size_t)bb * A.xbs + ooff);
@@ -347,15 +368,18 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
       //         dW[m][j] += Re(vd[m] T[j]),  dw_post[m] += Re T[m],  dw_pre[m] += Re(vd[m] xbar)
       float2 xb = f2(0.f, 0.f);
 #pragma unroll
-      for (int w = 0; w < CTA_T / 32; ++w) {
+      for (int w = 0; w < NT / 32; ++w) {
         xb.x += sRed[2 + w].x;
         xb.y += sRed[2 + w].y;
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int e = t + CTA_T * i, m = e >> 6, j = e & 63;
+      for (int i = 0; i < NGW; ++i) {
+        const int e = t + NT * i, m = e >> 6, j = e & 63;
         const float2 vd = sV[m], tj = cmulj2(sZ[j], xb);
-        sGw[e] = fmaf(vd.x, tj.x, fmaf(-vd.y, tj.y, sGw[e]));
+        if constexpr (TC)
+          gwr[i] = fmaf(vd.x, tj.x, fmaf(-vd.y, tj.y, gwr[i]));
+        else
+          sGw[e] = fmaf(vd.x, tj.x, fmaf(-vd.y, tj.y, sGw[e]));
       }
       if (t < CN) {
         const float2 vd = sV[t], tj = cmulj2(sZ[t], xb);
@@ -373,9 +397,9 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
     const OpK& postop = P.ops[L.post];
     if (fbop.acc_mode == ACC_SMEM) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int e = t + CTA_T * i, m = e >> 6, j = e & 63;
-        if (m < N && j < N) partial[(fbop.row_off + j) * G + m] = sGw[e];
+      for (int i = 0; i < NGW; ++i) {
+        const int e = t + NT * i, m = e >> 6, j = e & 63;
+        if (m < N && j < N) partial[(fbop.row_off + j) * G + m] = TC ? gwr[i] : sGw[e];
       }
     }
     if (t < N) {
@@ -384,9 +408,10 @@ __global__ void __launch_bounds__(CTA_T, 4) fsweep_cta_kernel(const __grid_const
     }
   }
   if (epi_fused(A.epilogue)) block_loss_store<float>(lacc, A.loss_partial);
+  if constexpr (TC) tc::teardown(TS);
 }
 
-cudaError_t launch_cta(bool bwd, int grid, cudaStream_t st, const ProgK& P, const LoopInfo& L, const SweepArgs& A, int G);
-cudaError_t occupancy_cta(bool bwd, int* blocks_per_sm);
+cudaError_t launch_cta(bool bwd, bool tc, int grid, cudaStream_t st, const ProgK& P, const LoopInfo& L, const SweepArgs& A, int G);
+cudaError_t occupancy_cta(bool bwd, bool tc, int* blocks_per_sm);
 
 }  // namespace fsweep

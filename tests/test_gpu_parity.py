@@ -179,8 +179,9 @@ def test_deferred_sos_gradients_match_in_kernel_atomics(name, dtype, monkeypatch
             assert grad_err(u, v) <= tol, (shard, B)
 
 
+@pytest.mark.parametrize("tc", [False, True], ids=["simt", "tcgen05"])
 @pytest.mark.parametrize("N,B", [(40, 1), (64, 3), (48, 35)])
-def test_cta_per_bin_kernels_on_wide_fdn(N, B, monkeypatch):
+def test_cta_per_bin_kernels_on_wide_fdn(N, B, tc, monkeypatch):
     """Wide FDN loops (32 < N <= 64, float32) run on the CTA-per-bin kernels (fsweep_cta.cuh): against the oracle,
     and against the row-distributed two-warps-per-bin path (FSWEEP_DISABLE_CTA=1) — forward, input gradient and
     parameter gradients, with a padded width (N < 64) and more than one pass of 32 right-hand sides (B = 35)."""
@@ -191,6 +192,8 @@ def test_cta_per_bin_kernels_on_wide_fdn(N, B, monkeypatch):
     M = nfft // 2 + 1
     delays = [601 + 37 * i for i in range(N)]
     desc = W.fdn(N, delays=delays)
+
+    monkeypatch.setenv("FSWEEP_CTA_TC", "1" if tc else "0")  # tensor-core (fsweep_tc.cuh) or SIMT elimination
 
     def run(disable):
         if disable:
@@ -215,7 +218,7 @@ def test_cta_per_bin_kernels_on_wide_fdn(N, B, monkeypatch):
 
     model, Ya, ga, fam_a = run(False)
     _, Yb, gb, fam_b = run(True)
-    assert "cta" in fam_a and "cta" not in fam_b
+    assert "cta" in fam_a and "cta" not in fam_b and ("tcgen05" in fam_a) == tc
     e_ab = rel_err(Ya.cpu().numpy(), Yb.cpu().numpy())
     assert e_ab <= 5e-5, f"cta vs row-distributed: {e_ab:.3e}"  # two float32 paths, each held to 1e-4 below
     for u, v in zip(ga[:-1], gb[:-1]):
