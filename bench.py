@@ -13,7 +13,13 @@ workload configs[1]: examples/e8_colorless_fdn.py restated with N = 8 delay line
     python bench.py --impl reference [...]                         the reference algorithm on the host CPU
     torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU (weak scaling: every
                                                                    rank trains its own batch item, gradients
-                                                                   are all-reduced over NCCL each step)
+                                                                   are all-reduced each step)
+
+Before anything is timed the bench model's first-step loss and parameter gradients are checked against the CPU
+oracle ("correctness gate before any number counts"); the line carries the errors under "parity".
+Besides the headline the line carries, under "configs", a device-timed Trainer.train_step of ALL FIVE BASELINE.json
+configs with the roofline that bounds each (HBM for the small loops, the MEASURED FP32 FMA rate for the
+compute-bound ones), and under --gpus N > 1 the bin-sharded (strong-scaling) step of config 5.
 
 The reference is pure Python and cannot travel to the GPU box, so the reference arm times
 oracle/flamo_oracle.py — the bit-exact restatement of the reference's algorithm and cost structure
@@ -42,15 +48,16 @@ ALIAS_DB = 30.0
 SEED = 130709
 METRIC = "freq-bins*channels/sec (Trainer.train_step)"
 UNIT = "bins*ch/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of the backward sweep kernel, one launch, from the committed
-# `ncu --set full` capture (profiles/r01e_ncu_full_sweep_kernels.md)
-NCU_TRAFFIC_BYTES = 642816
-NCU_TRAFFIC_SOURCE = "profiles/r01g_ncu_full_tpc_bwd.md (ncu --set full, fsweep_tpc_kernel<8,bwd>)"
 # real flops of one fused backward launch (~3.7 kflop per bin forward + backward for the 8x8 loop:
 # LU 8/3 N^3 + build 6 N^2 + forward solve 8 N^2 + adjoint solve 8 N^2 + gradient contractions 14 N^2 + 8 delays)
 FLOPS_PER_BIN = 8 / 3 * 512 + (6 + 8 + 8 + 14) * 64 + 8 * 40
-FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FMA lanes x 2 flop x 1.965 GHz = 74.4 (nominal)
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FMA lanes x 2 flop x 1.965 GHz = 74.4
 WORKLOAD = "cfg2: e8_colorless_fdn 8x8 FDN (Gain->Recursion(parallelDelay,Matrix orthogonal)->Gain), nfft=96000, B=1"
+# real flops of one training step of the two compute-bound configs:
+#   config 5: per bin one complex 64 x 64 LU (8/3 N^3) + one forward and one adjoint pair of substitutions (2 * 8 N^2)
+#             + forming A (2 N^2) + the dW outer product (4 N^2)
+#   config 3: 7680 second-order sections per bin, ~85 flops each forward + gradient (63 GFLOP per step)
+STEP_FLOPS = {"cfg5_fdn64": 192001 * (8 / 3 * 64 ** 3 + (16 + 2 + 4) * 64 ** 2), "cfg3_geq16": 63e9}
 
 
 def dist_env():
@@ -58,6 +65,14 @@ def dist_env():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     return rank, world, local
+
+
+def config_dict(world, cuda_graph, l2, final_loss, device):
+    """The SAME keys in both arms (the driver compares the two `config` objects)."""
+    M = NFFT // 2 + 1
+    return {"workload": WORKLOAD, "global_batch": world * BATCH, "nfft": NFFT, "bins": M, "channels": N_DELAYS,
+            "parallelism": f"dp{world}" if world > 1 else "single", "cuda_graph": cuda_graph, "l2": l2,
+            "final_loss": final_loss, "device": device}
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -135,15 +150,17 @@ def build_gpu_model(device, dtype=torch.float32):
     return model, ds, Trainer, mse_loss, sparsity_loss
 
 
-def cpu_reference_trainer(dtype=torch.float32):
-    """The reference algorithm (oracle port) for the same workload, float32 like the GPU arm."""
+def cpu_reference_trainer(dtype=torch.float32, params=None):
+    """The reference algorithm (oracle port) for the same workload, float32 like the GPU arm.  `params`: raw parameter
+    values to start from (the parity gate hands over the GPU model's), else the seeded draw."""
     from flamo_b200 import workloads as W
     from flamo_b200.processor import dsp, system
     from oracle import flamo_oracle as O
 
-    torch.manual_seed(SEED)
-    core = W.build(W.fdn(N_DELAYS), dsp, system, NFFT, ALIAS_DB, dtype=dtype, device="cpu")
-    params = [p.detach().clone().requires_grad_(p.requires_grad) for p in core.parameters()]
+    if params is None:
+        torch.manual_seed(SEED)
+        core = W.build(W.fdn(N_DELAYS), dsp, system, NFFT, ALIAS_DB, dtype=dtype, device="cpu")
+        params = [p.detach().clone().requires_grad_(p.requires_grad) for p in core.parameters()]
     node = O.from_desc(W.fdn(N_DELAYS))
     fb = node.children[1].children[1]
     crit = [(1, lambda est, tgt, ps: O.mse_loss(est, tgt)),
@@ -159,16 +176,17 @@ def cpu_reference_trainer(dtype=torch.float32):
 def time_cpu_reference(steps: int, warmup: int):
     torch.set_num_threads(os.cpu_count())
     tr, x, y = cpu_reference_trainer()
+    loss = None
     for _ in range(warmup):
         tr.train_step(x, y)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        tr.train_step(x, y)
+        loss = tr.train_step(x, y)
         ts.append(time.perf_counter() - t0)
     t = sum(ts) / len(ts)
     M = NFFT // 2 + 1
-    return BATCH * M * N_DELAYS / t, t
+    return BATCH * M * N_DELAYS / t, t, statistics.median(ts), loss
 
 
 def reference_arm(args):
@@ -177,18 +195,174 @@ def reference_arm(args):
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     steps = min(steps, 100)  # ~150 ms per step on 8 cores: keep the run within a few minutes
-    value, t = time_cpu_reference(steps, min(warmup, 10))
+    value, t, t_med, loss = time_cpu_reference(steps, min(warmup, 10))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(warmup, 10), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "device": "host cpu"},
+        "warmup": min(warmup, 10), "ms_per_step": t * 1e3, "ms_per_step_median": t_med * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(1, False, "n/a (host CPU)", loss, "host cpu"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"{steps} full train_step calls of the whole workload (oracle port of the "
                                    "reference algorithm, torch CPU, all host threads)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ parity gate
+def parity_gate(device):
+    """First-step loss and parameter gradients of the bench model (fresh, seeded) against the CPU oracle evaluated in
+    float64 on the same float32 parameter values: loss within 1e-4, every gradient within 1e-3 of its largest entry
+    (BASELINE.md §2).  Raises on a mismatch: no number is printed for a wrong kernel."""
+    from flamo_b200.optimize.loss import mse_loss, sparsity_loss
+
+    model, ds, _, _, _ = build_gpu_model(device)
+    x, y = ds.input[:BATCH].to(device), ds.target[:BATCH].to(device)
+    crit_a, crit_b = mse_loss(nfft=NFFT, device=device), sparsity_loss()
+    est = model(x)
+    loss = crit_a(est, y) + 0.2 * crit_b(est, y, model)
+    loss.backward()
+    torch.cuda.synchronize()
+    params = [p for p in model.parameters()]
+    p64 = [p.detach().cpu().double().requires_grad_(p.requires_grad) for p in model.get_core().parameters()]
+    tr, xo, yo = cpu_reference_trainer(torch.float64, p64)
+    lo, _ = tr.loss(xo, yo)
+    go = torch.autograd.grad(lo, [p for p in p64 if p.requires_grad])
+    loss, lo = loss.detach(), lo.detach()
+    loss_err = abs(float(loss) - float(lo)) / abs(float(lo))
+    gerr, k = 0.0, 0
+    core_params = [p for p in model.get_core().parameters()]
+    for p in core_params:
+        if p.requires_grad:
+            ref = go[k]
+            gerr = max(gerr, float((p.grad.detach().cpu().double() - ref).abs().max() / (ref.abs().max() + 1e-300)))
+            k += 1
+    out = {"loss": float(loss), "oracle_loss": float(lo), "loss_rel_err": loss_err, "grad_rel_err": gerr,
+           "bounds": {"loss": 1e-4, "grad": 1e-3}, "against": "oracle/flamo_oracle.py (CPU, float64, same parameters)"}
+    if not (loss_err <= 1e-4 and gerr <= 1e-3):
+        raise SystemExit(f"parity gate failed, nothing timed: {json.dumps(out)}")
+    del params
+    return out
+
+
+# ------------------------------------------------------------------------------------ all five configs
+def build_config_trainer(name, device, world=1, shard=None):
+    """Trainer + data for one BASELINE.json config (SURVEY.md §8d restatements, as tools/measure_configs.py)."""
+    from flamo_b200 import workloads as W
+    from flamo_b200.optimize.loss import mse_loss, sparsity_loss
+    from flamo_b200.optimize.trainer import Trainer
+    from flamo_b200.processor import dsp, system
+
+    desc, nfft, B, seed, n_ch = W.CONFIGS[name]
+    M = nfft // 2 + 1
+    torch.manual_seed(seed)
+    core = W.build(desc, dsp, system, nfft, W.ALIAS_DECAY_DB, dtype=torch.float32, device=device)
+    model = system.Shell(core, dsp.FFT(nfft), dsp.Transform(lambda x: torch.abs(x)))
+    n_in = model.input_channels
+    if name in ("cfg1_biquad", "cfg3_geq16"):
+        x = torch.zeros(B, nfft, n_in, device=device)
+        x[:, 0, :] = 1
+        torch.manual_seed(seed + 1)
+        tcore = W.build(desc, dsp, system, nfft, W.ALIAS_DECAY_DB, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            tgt = system.Shell(tcore, dsp.FFT(nfft), dsp.Transform(lambda x: torch.abs(x)))(x).clone()
+        crits = [(torch.nn.MSELoss(), 1, False)]
+    else:
+        x = torch.zeros(B, M, n_in, device=device)
+        x[:, 0, :] = 1
+        tgt = torch.ones(B, M, 1, device=device)
+        crits = [(mse_loss(nfft=nfft, device=device), 1, False)]
+        if name in ("cfg2_fdn8", "cfg5_fdn64"):
+            crits.append((sparsity_loss(), 0.2, True))
+    if world > 1:
+        from flamo_b200.parallel import DataParallelTrainer
+
+        tr = DataParallelTrainer(model, max_epochs=1, lr=1e-3, log=False, device=device, shard=shard)
+    else:
+        tr = Trainer(model, max_epochs=1, lr=1e-3, log=False, device=device)
+    for c, a, rm in crits:
+        tr.register_criterion(c, a, requires_model=rm)
+    return tr, x, tgt, B, M, n_ch, n_in, model.output_channels
+
+
+def time_trainer(tr, data, steps, flush, world=1, device="cuda"):
+    """Median and mean device time of `steps` train_step calls (CUDA events on the launching stream, L2 flushed before
+    every step, max over ranks)."""
+    for _ in range(6):  # lazy state + graph capture
+        tr.train_step(data)
+    ts = []
+    for i in range(steps):
+        flush.fill_(i & 0xFF)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        tr.train_step(data)
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    med, mean = statistics.median(ts), statistics.mean(ts)
+    if world > 1:
+        import torch.distributed as dist
+
+        v = torch.tensor([med, mean], device=device, dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        med, mean = float(v[0]), float(v[1])
+    return med, mean
+
+
+def measure_fma_peak(device):
+    """FP32 FMA rate of this GPU, measured (SURVEY.md §8d "derive + measure"): libfsweep's probe kernel, 16 blocks of
+    256 threads per SM, 64 independent FFMAs per thread and round; best of 5 launches timed with CUDA events."""
+    from flamo_b200 import _lib
+
+    L = _lib.lib()
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    blocks, iters = sms * 16, 4096
+    out = torch.zeros(1, dtype=torch.float32, device=device)
+    st = torch.cuda.current_stream(device).cuda_stream
+    best = None
+    for i in range(7):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        _lib.check(L.fsweep_fma_probe(out.data_ptr(), blocks, iters, st))
+        e.record()
+        torch.cuda.synchronize()
+        t = s.elapsed_time(e) * 1e-3
+        if i >= 2:
+            best = t if best is None else min(best, t)
+    return L.fsweep_fma_probe_flops(blocks, iters) / best / 1e12
+
+
+def all_configs(device, flush, steps, peaks, fma_tflops, rank):
+    """Device-timed Trainer.train_step of the five BASELINE.json configs on ONE GPU, each with the roofline that bounds
+    it: HBM (algorithmic bytes of the sweep, x in + |Y| or target in, per step) for the small loops, the measured FP32
+    FMA rate for the two compute-bound ones."""
+    from flamo_b200 import workloads as W
+
+    out = {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    for name in W.CONFIGS:
+        try:
+            tr, x, tgt, B, M, n_ch, n_in, n_out = build_config_trainer(name, device)
+            med, mean = time_trainer(tr, (x, tgt), steps, flush)
+            rec = {"ms_per_step": med, "ms_per_step_mean": mean, "value": B * M * n_ch / (med * 1e-3), "unit": UNIT,
+                   "bins": M, "batch": B, "channels": n_ch, "steps": steps, "cuda_graph": bool(tr.use_graph and tr._graphs)}
+            if name in STEP_FLOPS:
+                ach = STEP_FLOPS[name] / (med * 1e-3) / 1e12
+                rec["roofline"] = {"bound": "fp32", "achieved": ach, "peak": fma_tflops, "unit": "TFLOP/s",
+                                   "frac": ach / fma_tflops, "peak_source": "measured (fsweep_fma_probe on this GPU)",
+                                   "flops_per_step": STEP_FLOPS[name]}
+            else:
+                byts = B * M * (8 * n_in + 4 * n_out)
+                ach = byts / (med * 1e-3) / 1e9
+                rec["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                                   "algorithmic_bytes_per_step": byts,
+                                   "note": "launch / latency bound: the whole captured step is timed, not one kernel"}
+            del tr
+        except Exception as ex:  # one config failing must not hide the others
+            rec = {"error": f"{type(ex).__name__}: {ex}"}
+        out[name] = rec
+        torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -205,6 +379,8 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     from flamo_b200 import sweep
+
+    parity = parity_gate(device) if (rank == 0 and not args.no_parity_gate) else None
 
     model, ds, Trainer, mse_loss, sparsity_loss = build_gpu_model(device)
     if world > 1:
@@ -230,7 +406,7 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(steps, data, timed=True):
+    def run(steps, data):
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         loss = None
@@ -240,7 +416,8 @@ def gpu_arm(args):
             loss = trainer.train_step(data)
             ends[i].record()
         torch.cuda.synchronize()
-        return sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3, loss
+        ts = [s.elapsed_time(e) * 1e-3 for s, e in zip(starts, ends)]
+        return sum(ts), statistics.median(ts), loss
 
     # lazy state + graph capture happen in the first few calls; they are not part of W
     for _ in range(6):
@@ -252,7 +429,7 @@ def gpu_arm(args):
     barrier()
     launches0 = sweep.launch_count
     sampler.start()
-    t_dev, loss = run(args.steps, (x_dev, y_dev))
+    t_dev, med_dev, loss = run(args.steps, (x_dev, y_dev))
     barrier()
     launches = sweep.launch_count - launches0
     # keep the GPU under the same load long enough for a few clock samples; a FIXED number of steps,
@@ -263,47 +440,74 @@ def gpu_arm(args):
     # end to end: inputs in pinned host memory, H2D inside the timed region, loss read back
     run(warmup, (x_host, y_host))
     barrier()
-    t_e2e, _ = run(args.steps, (x_host, y_host))
+    t_e2e, med_e2e, _ = run(args.steps, (x_host, y_host))
     barrier()
 
-    def reduce_max(t):
+    def reduce_max(*ts):
         if world == 1:
-            return t
+            return ts
         import torch.distributed as dist
 
-        v = torch.tensor([t], device=device, dtype=torch.float64)
+        v = torch.tensor(list(ts), device=device, dtype=torch.float64)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        return float(v.item())
+        return tuple(float(a) for a in v)
 
-    t_dev, t_e2e = reduce_max(t_dev), reduce_max(t_e2e)
+    t_dev, t_e2e, med_dev, med_e2e = reduce_max(t_dev, t_e2e, med_dev, med_e2e)
     units_per_step = world * BATCH * M * N_DELAYS
     value = units_per_step * args.steps / t_dev
     e2e_value = units_per_step * args.steps / t_e2e
 
-    roof = kernel_roofline(model, x_dev, flush) if rank == 0 else None
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    fma_tflops = measure_fma_peak(device) if rank == 0 else None
+    roof = kernel_roofline(model, x_dev, flush, peaks, fma_tflops) if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, t = time_cpu_reference(steps=40, warmup=3)
+        v, t, t_med, _ = time_cpu_reference(steps=40, warmup=3)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": "40 full train_step calls of the whole workload (oracle port of the reference "
                          f"algorithm, torch CPU float32, all host threads): {t * 1e3:.1f} ms/step"}
+
+    # the multi-GPU step of the bench model holds NCCL / peer-memory state: release its graphs before other trainers run
+    extra = {}
+    if world == 1 and rank == 0 and not args.no_configs:
+        extra["configs"] = all_configs(device, flush, args.config_steps, peaks, fma_tflops, rank)
+    if world > 1 and not args.no_configs:
+        # BASELINE.json configs[4] as north_star describes it: bin ranges sharded over the GPUs of the node, one
+        # all-reduce of the gradients per step (strong scaling: the total work is fixed)
+        try:
+            tr5, x5, t5, B5, M5, n5, _, _ = build_config_trainer("cfg5_fdn64", device, world, "bins")
+            med5, mean5 = time_trainer(tr5, (x5, t5), args.config_steps, flush, world, device)
+            extra["cfg5_bins_sharded"] = {"ms_per_step": med5, "ms_per_step_mean": mean5, "n_gpus": world,
+                                          "value": B5 * M5 * n5 / (med5 * 1e-3), "unit": UNIT, "scaling": "strong",
+                                          "bins_per_rank": M5 // world, "batch": B5, "steps": args.config_steps}
+            tr5._graphs.clear()
+        except Exception as ex:
+            extra["cfg5_bins_sharded"] = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": t_dev / args.steps * 1e3, "ms_per_step_median": med_dev * 1e3,
+            "value_median": units_per_step / med_dev, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "nfft": NFFT, "bins": M,
-                       "channels": N_DELAYS, "parallelism": f"dp{world}" if world > 1 else "single",
-                       "cuda_graph": bool(trainer.use_graph), "l2": "flushed between timed steps (192 MB fill)",
-                       "final_loss": loss},
+            "config": config_dict(world, bool(trainer.use_graph), "flushed between timed steps (192 MB fill)", loss,
+                                  "B200"),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": t_e2e / args.steps * 1e3,
+                    "ms_per_step_median": med_e2e * 1e3,
                     "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),
                     "d2h_bytes_per_step": 4 * (trainer.n_loss + 1)},
             "gpu_launches": launches,
             "clocks": clocks,
+            "parity": parity,
             "roofline": roof,
             "cpu_baseline": cpu,
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         # a captured graph that contains NCCL work keeps the communicator busy: ProcessGroupNCCL's teardown
@@ -318,7 +522,7 @@ def gpu_arm(args):
         os._exit(0)
 
 
-def kernel_roofline(model, x_dev, flush, reps=30):
+def kernel_roofline(model, x_dev, flush, peaks, fma_tflops, reps=30):
     """Duration of the dominant kernel (the backward sweep) and of the forward sweep, each launched
     alone behind an L2 flush (as a one-node CUDA graph, so that host launch overhead is excluded), CUDA events on the
     launching stream; algorithmic bytes per launch =
@@ -326,13 +530,15 @@ def kernel_roofline(model, x_dev, flush, reps=30):
     from flamo_b200 import sweep
     from flamo_b200._lib import EPI_ABS
 
-    peaks = {}
+    peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from THIS round's `ncu --set full` capture
+    traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except Exception:
         pass
-    peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
     core = model.get_core()
     with torch.enable_grad():  # lowered with grad enabled so the ops carry FSWEEP_F_GRAD like a real step
@@ -341,18 +547,17 @@ def kernel_roofline(model, x_dev, flush, reps=30):
         core._lower(prog, None)
         segs = list(prog._segments())
         assert len(segs) == 1 and segs[0][0] == "sweep"
-        ops, coefs, n_out = prog.flatten_segment(segs[0][1])
+        ops, coefs, n_out = prog.flatten_segment(segs[0][1], X.dtype)
     coefs = [c.detach().contiguous() for c in coefs]
     plan = prog.plan_for(ops)
     x4 = X.detach().reshape(X.shape[0], X.shape[1], X.shape[2], 1).contiguous()
     y = torch.empty((x4.shape[0], x4.shape[1], n_out, 1), dtype=torch.float32, device=X.device)
-    gy = torch.ones_like(y)
     M = X.shape[1]
     bytes_per_launch = BATCH * M * (8 * 1 + 4 * 1)
     backend = sweep._BACKEND
 
     def timed(call):
-        """Mean duration of `call`'s device work: the launch is captured once into a CUDA graph and the replay is
+        """Median duration of `call`'s device work: the launch is captured once into a CUDA graph and the replay is
         timed with events, so the Python / ctypes launch path (tens of microseconds, longer than these kernels) is
         not inside the timed region; L2 is flushed before every replay."""
         side = torch.cuda.Stream()
@@ -373,7 +578,7 @@ def kernel_roofline(model, x_dev, flush, reps=30):
             torch.cuda.synchronize()
             if i >= 5:
                 ts.append(s.elapsed_time(e) * 1e-3)
-        return statistics.mean(ts)
+        return statistics.median(ts)
 
     t_fwd = timed(lambda: backend.forward(plan, ops, coefs, x4, y, 1, 0, EPI_ABS))
 
@@ -393,20 +598,20 @@ def kernel_roofline(model, x_dev, flush, reps=30):
     return {"bound": "hbm", "kernel": plan.kernel_family(M, True) + " (fused |.|+MSE criterion)", "achieved": ach,
             "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else which,
-            "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
+            "traffic": traffic, "traffic_source": traffic_src,
             "us_per_launch": t_bwd * 1e6, "algorithmic_bytes_per_launch": bytes_per_launch,
-            "us_per_launch_note": "graph replay of sweep kernel + one-warp loss finalize, launch latency included; the "
-                                  "sweep kernel alone is 23.5 us in the ncu launch list of a captured step "
-                                  "(profiles/r01i_launches_step_summary.md)",
+            "us_per_launch_note": "median over graph replays of the sweep kernel + one-warp loss finalize, launch "
+                                  "latency included",
             "forward_kernel": {"kernel": plan.kernel_family(M, False) + " (validation / inference only; not in the training step)",
                                "us_per_launch": t_fwd * 1e6,
                                "achieved": bytes_per_launch / t_fwd / 1e9, "frac": bytes_per_launch / t_fwd / 1e9 / peak},
             "fp32": {"flops_per_launch": FLOPS_PER_BIN * M, "achieved_tflops": FLOPS_PER_BIN * M / t_bwd / 1e12,
-                     "nominal_peak_tflops": FP32_PEAK_TFLOPS, "frac": FLOPS_PER_BIN * M / t_bwd / 1e12 / FP32_PEAK_TFLOPS},
+                     "measured_peak_tflops": fma_tflops, "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
+                     "frac": FLOPS_PER_BIN * M / t_bwd / 1e12 / (fma_tflops or FP32_NOMINAL_TFLOPS),
+                     "peak_source": "measured (fsweep_fma_probe on this GPU)" if fma_tflops else "nominal"},
             "note": "config 2 moves 0.58 MB per launch and does ~3.7 kflop per bin: it is dependent-issue latency "
-                    "bound (one bin per thread, 2.4 warps per scheduler), not HBM bound (SURVEY.md §8d; profiles/"
-                    "r01g_ncu_full_tpc_bwd.md); the HBM fraction is reported as the contract asks, the FP32 fraction "
-                    "beside it"}
+                    "bound (one bin per thread), not HBM bound (SURVEY.md §8d); the HBM fraction is reported as the "
+                    "contract asks, the FP32 fraction (of the measured FMA rate) beside it"}
 
 
 def main():
@@ -417,6 +622,9 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-graph", action="store_true", help="run train_step eagerly (profiling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-gate", action="store_true", help="skip the oracle check before timing (profiling)")
+    ap.add_argument("--no-configs", action="store_true", help="headline only: skip the per-config sub-records")
+    ap.add_argument("--config-steps", type=int, default=30, help="timed steps per config in the sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -26,7 +26,7 @@ EXPORTS = [
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward",
     "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total",
-    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_adam_step",
+    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_adam_step", "fsweep_fma_probe", "fsweep_fma_probe_flops",
 ]
 
 
@@ -120,6 +120,10 @@ def lib():
     L.fsweep_allreduce_p2p.argtypes = [vp, vp, i32, i32, i32, C.c_double, vp, vp]
     L.fsweep_adam_step.restype = i32
     L.fsweep_adam_step.argtypes = [C.POINTER(AdamTensor), i32, i32, vp, C.c_double, C.c_double, C.c_double, vp]
+    L.fsweep_fma_probe.restype = i32
+    L.fsweep_fma_probe.argtypes = [vp, i32, i32, vp]
+    L.fsweep_fma_probe_flops.restype = C.c_double
+    L.fsweep_fma_probe_flops.argtypes = [i32, i32]
     L.fsweep_weighted_total.restype = i32
     L.fsweep_weighted_total.argtypes = [C.POINTER(vp), C.POINTER(C.c_double), C.POINTER(C.c_double), i32, i32, vp, vp]
     _lib = L

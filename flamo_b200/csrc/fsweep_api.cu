@@ -14,7 +14,7 @@
 #include "fsweep_cta.cuh"
 
 #ifndef FSWEEP_CTA_TC_DEFAULT
-#define FSWEEP_CTA_TC_DEFAULT false  // FSWEEP_CTA_TC=1 selects the tensor-core elimination per plan
+#define FSWEEP_CTA_TC_DEFAULT true  // FSWEEP_CTA_TC=0 selects the SIMT elimination instead of the tensor-core one
 #endif
 #include "fsweep_stream.cuh"
 
@@ -490,7 +490,12 @@ int cta_grid(fsweep_plan* p, bool bwd, int64_t n_bins, cudaError_t* err) {
       *err = cudaErrorLaunchOutOfResources;
       return 0;
     }
+    // The occupancy calculator answers 1 for a kernel that allocates tensor memory, but blocks do share an SM as long
+    // as their TMEM columns fit (64 of 512 each here): registers and shared memory allow 5 (__launch_bounds__).  A
+    // block that finds no room simply starts later; the bin loop is grid-strided either way.
+    if (p->cta_tc) n = std::max(n, tc::BLOCKS_PER_SM);
     p->cta_blocks_per_sm[bwd] = n;
+    if (getenv("FSWEEP_DEBUG")) fprintf(stderr, "[fsweep] cta kernel bwd=%d tc=%d: %d blocks per SM, %d SMs\n", (int)bwd, (int)p->cta_tc, n, p->num_sms);
   }
   const int64_t resident = (int64_t)p->cta_blocks_per_sm[bwd] * p->num_sms;
   return (int)std::min<int64_t>(std::min<int64_t>(resident, n_bins), grid_cap(n_bins, p->G));

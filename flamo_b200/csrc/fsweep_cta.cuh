@@ -33,24 +33,23 @@ __device__ __forceinline__ float2 cmulj2(float2 a, float2 b) {  // conj(a) * b
 }
 
 constexpr size_t cta_smem_bytes(bool bwd, bool tc) {
-  return (size_t)(CN * CLD + 7 * CN + 16) * sizeof(float2) + (size_t)(2 * CN) * sizeof(float) +
+  return (size_t)(CN * CLD + (tc ? 4 : 6) * CN + 16) * sizeof(float2) + (size_t)(2 * CN) * sizeof(float) +
          (size_t)(2 * CN + 8) * sizeof(int) +
          (tc ? (size_t)CN * sizeof(int) + 16 : (bwd ? (size_t)(CN * CN) * sizeof(float) : 0));
 }
 static_assert(tc::scratch_bytes() <= (size_t)CN * CLD * sizeof(float2), "tensor-core scratch must fit in the L\\U area");
 
 template <bool BWD, bool TC>
-__global__ void __launch_bounds__(TC ? tc::T : CTA_T, TC ? 5 : 4) fsweep_cta_kernel(const __grid_constant__ ProgK P,
+__global__ void __launch_bounds__(TC ? tc::T : CTA_T, TC ? tc::BLOCKS_PER_SM : 4) fsweep_cta_kernel(const __grid_constant__ ProgK P,
                                                             const __grid_constant__ LoopInfo L, const SweepArgs A, int G) {
   extern __shared__ __align__(16) float2 csm[];
   float2* sA = csm;                 // [CN][CLD]   L\U in place, 1/U_kk on the diagonal
   float2* sD = sA + CN * CLD;       // [CN]  diagonal chain response
   float2* sV = sD + CN;             // [CN]  adjoint vector v, then vd = conj(D) v
   float2* sZ = sV + CN;             // [CN]  z = A^-1 (D w_pre): every y_b = x_b z
-  float2* sW = sZ + CN;             // [CN]  scratch of the adjoint solve
-  float2* sRed = sW + CN;           // [16] h, S, per-warp partial sums of xbar
-  float2* sL = sRed + 16;           // [2][CN] multipliers of the current elimination step (double buffered)
-  float2* sInv = sL + 2 * CN;       // [CN] reciprocal pivots
+  float2* sRed = sZ + CN;           // [16] h, S, per-warp partial sums of xbar
+  float2* sL = sRed + 16;           // [2][CN] multipliers of the current elimination step (SIMT elimination only)
+  float2* sInv = sL + (TC ? 0 : 2 * CN);  // [CN] reciprocal pivots
   float* sWpre = reinterpret_cast<float*>(sInv + CN);  // [CN]
   float* sWpost = sWpre + CN;                               // [CN]
   int* sPiv = reinterpret_cast<int*>(sWpost + CN);          // [CN] row map of P A; [CN..]: scalars
@@ -227,65 +226,98 @@ __global__ void __launch_bounds__(TC ? tc::T : CTA_T, TC ? 5 : 4) fsweep_cta_ker
 
     // ---- 4. The loop has ONE input and ONE output channel, so every right-hand side of the bin is a multiple of the
     //         same vector: y_b = x_b z with z = A^-1 (D w_pre), o_b = h x_b with h = w_post . z — one forward and (BWD)
-    //         one adjoint substitution per bin, whatever the batch.  They run side by side: threads 0..63 solve for z
-    //         (named barrier 1), threads 64..127 for v = A^-H w_post (named barrier 2).
-    if (t < CN) {
+    //         one adjoint substitution per bin, whatever the batch.  They run side by side, each inside ONE warp (lane l
+    //         owns entries l and l + 32; the entry that becomes final in a step is broadcast with a shuffle: no barrier,
+    //         no shared-memory round trip on the dependent chain): warp 0 solves for z, warp 1 for v = A^-H w_post.
+    if (warp == 0) {
       // L U z = P r,  r = D w_pre:  row i of P r is r[piv[i]]
-      const int src = sPiv[t];
-      const float2 dsrc = sD[src];
-      const float wsrc = sWpre[src];
-      float2 g = f2(dsrc.x * wsrc, dsrc.y * wsrc);
-      const float2* rowA = sA + t * CLD;
-      for (int i = 0; i < CN; ++i) {  // L c = P r (unit lower, column oriented)
-        if (t == i) sZ[i] = g;
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        if (t > i) g = cnma2(g, rowA[i], sZ[i]);
+      float2 g0, g1;
+      {
+        const int s0 = sPiv[lane], s1 = sPiv[lane + 32];
+        const float2 d0 = sD[s0], d1 = sD[s1];
+        const float w0 = sWpre[s0], w1 = sWpre[s1];
+        g0 = f2(d0.x * w0, d0.y * w0);
+        g1 = f2(d1.x * w1, d1.y * w1);
       }
-      for (int i = CN - 1; i >= 0; --i) {  // U z = c (reciprocal diagonal stored)
-        if (t == i) {
-          g = cmul2(g, rowA[i]);
-          sZ[i] = g;
-        }
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        if (t < i) g = cnma2(g, rowA[i], sZ[i]);
+      const float2* row0 = sA + lane * CLD;
+      const float2* row1 = sA + (lane + 32) * CLD;
+      // L c = P r (unit lower, column oriented)
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const float2 ci = f2(__shfl_sync(FULL, g0.x, i), __shfl_sync(FULL, g0.y, i));
+        if (lane > i) g0 = cnma2(g0, row0[i], ci);
+        g1 = cnma2(g1, row1[i], ci);
       }
-    } else if (BWD && t < 2 * CN) {
+#pragma unroll 4
+      for (int i = 32; i < CN - 1; ++i) {
+        const float2 ci = f2(__shfl_sync(FULL, g1.x, i - 32), __shfl_sync(FULL, g1.y, i - 32));
+        if (lane + 32 > i) g1 = cnma2(g1, row1[i], ci);
+      }
+      // U z = c (reciprocal diagonal stored)
+#pragma unroll 4
+      for (int i = CN - 1; i >= 32; --i) {
+        if (lane + 32 == i) g1 = cmul2(g1, row1[i]);
+        const float2 zi = f2(__shfl_sync(FULL, g1.x, i - 32), __shfl_sync(FULL, g1.y, i - 32));
+        if (lane + 32 < i) g1 = cnma2(g1, row1[i], zi);
+        g0 = cnma2(g0, row0[i], zi);
+      }
+#pragma unroll 4
+      for (int i = 31; i >= 0; --i) {
+        if (lane == i) g0 = cmul2(g0, row0[i]);
+        const float2 zi = f2(__shfl_sync(FULL, g0.x, i), __shfl_sync(FULL, g0.y, i));
+        if (lane < i) g0 = cnma2(g0, row0[i], zi);
+      }
+      sZ[lane] = g0;
+      sZ[lane + 32] = g1;
+    } else if (BWD && warp == 1) {
       // v = A^-H w_post:  A^H = U^H L^H P
-      const int tt = t - CN;
-      float2 g = f2(sWpost[tt], 0.f);
-      // U^H w = g  (lower triangular, column-oriented: after w_i is final, g_j -= conj(U[i][j]) w_i for j > i)
-      for (int i = 0; i < CN; ++i) {
-        if (tt == i) {
-          const float2 di = sA[i * CLD + i];
-          g = cmul2(g, f2(di.x, -di.y));
-          sW[i] = g;
+      float2 g0 = f2(sWpost[lane], 0.f), g1 = f2(sWpost[lane + 32], 0.f);
+      const float2* col0 = sA + lane;       // entry [i][lane]
+      const float2* col1 = sA + lane + 32;  // entry [i][lane + 32]
+      auto cjnma = [](float2 acc, float2 a, float2 b) {  // acc - conj(a) b
+        acc.x -= a.x * b.x + a.y * b.y;
+        acc.y -= a.x * b.y - a.y * b.x;
+        return acc;
+      };
+      // U^H w = g  (lower triangular, column oriented: once w_i is final, g_j -= conj(U[i][j]) w_i for j > i)
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        if (lane == i) {
+          const float2 di = col0[i * CLD];
+          g0 = cmul2(g0, f2(di.x, -di.y));
         }
-        asm volatile("bar.sync 2, 64;" ::: "memory");
-        if (tt > i) {
-          const float2 u = sA[i * CLD + tt];
-          const float2 wi = sW[i];
-          g.x -= u.x * wi.x + u.y * wi.y;  // conj(u) * wi
-          g.y -= u.x * wi.y - u.y * wi.x;
-        }
+        const float2 wi = f2(__shfl_sync(FULL, g0.x, i), __shfl_sync(FULL, g0.y, i));
+        if (lane > i) g0 = cjnma(g0, col0[i * CLD], wi);
+        g1 = cjnma(g1, col1[i * CLD], wi);
       }
-      // L^H z = w  (unit upper triangular): z_i final when all j > i are done; z_j -= conj(L[i][j]) z_i for j < i
-      for (int i = CN - 1; i >= 0; --i) {
-        if (tt == i) sW[i] = g;
-        asm volatile("bar.sync 2, 64;" ::: "memory");
-        if (tt < i) {
-          const float2 l = sA[i * CLD + tt];
-          const float2 zi = sW[i];
-          g.x -= l.x * zi.x + l.y * zi.y;
-          g.y -= l.x * zi.y - l.y * zi.x;
+#pragma unroll 4
+      for (int i = 32; i < CN; ++i) {
+        if (lane + 32 == i) {
+          const float2 di = col1[i * CLD];
+          g1 = cmul2(g1, f2(di.x, -di.y));
         }
+        const float2 wi = f2(__shfl_sync(FULL, g1.x, i - 32), __shfl_sync(FULL, g1.y, i - 32));
+        if (lane + 32 > i) g1 = cjnma(g1, col1[i * CLD], wi);
+      }
+      // L^H z = w  (unit upper triangular): z_i is final when all j > i are done; z_j -= conj(L[i][j]) z_i for j < i
+#pragma unroll 4
+      for (int i = CN - 1; i >= 32; --i) {
+        const float2 zi = f2(__shfl_sync(FULL, g1.x, i - 32), __shfl_sync(FULL, g1.y, i - 32));
+        if (lane + 32 < i) g1 = cjnma(g1, col1[i * CLD], zi);
+        g0 = cjnma(g0, col0[i * CLD], zi);
+      }
+#pragma unroll 4
+      for (int i = 31; i > 0; --i) {
+        const float2 zi = f2(__shfl_sync(FULL, g0.x, i), __shfl_sync(FULL, g0.y, i));
+        if (lane < i) g0 = cjnma(g0, col0[i * CLD], zi);
       }
       // v[piv[i]] = z_i ; vd = conj(D) v
-      sV[sPiv[tt]] = g;
-      asm volatile("bar.sync 2, 64;" ::: "memory");
-      const float2 v = sV[tt];
-      const float2 dd = sD[tt];
-      asm volatile("bar.sync 2, 64;" ::: "memory");
-      sV[tt] = f2(dd.x * v.x + dd.y * v.y, dd.x * v.y - dd.y * v.x);
+      {
+        const int p0 = sPiv[lane], p1 = sPiv[lane + 32];
+        const float2 d0 = sD[p0], d1 = sD[p1];
+        sV[p0] = f2(d0.x * g0.x + d0.y * g0.y, d0.x * g0.y - d0.y * g0.x);
+        sV[p1] = f2(d1.x * g1.x + d1.y * g1.y, d1.x * g1.y - d1.y * g1.x);
+      }
     }
     __syncthreads();
     // ---- 5. h = w_post . z (warp 0);  S = sum_m w_pre[m] vd[m] (warp 1, BWD: g_x = g_b S)

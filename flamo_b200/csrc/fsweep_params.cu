@@ -455,3 +455,34 @@ extern "C" FSWEEP_API int fsweep_adam_step(const fsweep_adam_tensor_t* tensors, 
     return FSWEEP_E_BADARG;
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
+
+// ---------------------------------------------------------------------------------------------- FP32 FMA peak probe
+// The roofline denominator for the compute-bound sweeps ("derive + measure"): every thread runs 16
+// independent FFMA chains for `iters` rounds; the caller times the launch with CUDA events and divides
+// fsweep_fma_probe_flops() by the duration.  Not part of the product path.
+namespace {
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters, float x, float y) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], x, y);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;  // keeps the chains alive
+}
+}  // namespace
+
+extern "C" FSWEEP_API double fsweep_fma_probe_flops(int blocks, int iters) { return 2.0 * 16 * 4 * (double)iters * 256.0 * blocks; }
+
+extern "C" FSWEEP_API int fsweep_fma_probe(void* out, int blocks, int iters, void* stream) {
+  if (!out || blocks < 1 || iters < 1) return FSWEEP_E_BADARG;
+  fma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float*>(out), iters, 0.999f, 1e-4f);
+  return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}

@@ -30,6 +30,7 @@ namespace tc {
 
 constexpr int T = 128;         // threads per block = TMEM lanes
 constexpr int NB = 8;          // panel width
+constexpr int BLOCKS_PER_SM = 5;  // register / shared-memory budget the kernel is compiled for (TMEM allows 8)
 constexpr int NCOL = 64;       // TMEM columns (= loop width, padded)
 constexpr int PLD = NB + 1;    // row stride of the panel buffer (floats)
 constexpr int ULD = 64;        // row stride of the pivot-row buffer (floats)
@@ -72,6 +73,23 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 8-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld8x2(uint32_t taddr, float* v, bool second) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  if (second)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr + 8)
+                 : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
                "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
@@ -90,7 +108,11 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-__device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
+// nearest TF32 value, ties away from zero (the tensor core truncates the 13 low mantissa bits of what it is given:
+// round first).  Two integer instructions; cvt.rna.tf32.f32 measured 12 % of the kernel's instructions.
+__device__ __forceinline__ float tf32_hi(float a) {
+  return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u);
+}
 
 // Block-level state that lives across bins.
 struct State {
@@ -152,12 +174,17 @@ __device__ __forceinline__ void lu(State& S, float2* scratch, const float2* sD, 
 #pragma unroll 1
     for (int c0 = 0; c0 < NCOL; c0 += 8) {
       float v[8];
+      float w8[8];
+      if (N == NCOL) {  // full width: the row is 64 contiguous, 16-byte aligned floats
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(Wfb + r * NCOL + c0));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(Wfb + r * NCOL + c0 + 4));
+        w8[0] = wa.x, w8[1] = wa.y, w8[2] = wa.z, w8[3] = wa.w, w8[4] = wb.x, w8[5] = wb.y, w8[6] = wb.z, w8[7] = wb.w;
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i;
-        const float w = (r < N && c < N) ? __ldg(Wfb + r * N + c) : 0.f;
-        v[i] = ((part == 0 && c == r) ? 1.f : 0.f) - dv * w;
+        for (int i = 0; i < 8; ++i) w8[i] = (r < N && c0 + i < N) ? __ldg(Wfb + r * N + c0 + i) : 0.f;
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ((part == 0 && c0 + i == r) ? 1.f : 0.f) - dv * w8[i];
       tmem_st8(tlane + c0, v);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
@@ -196,13 +223,15 @@ __device__ __forceinline__ void lu(State& S, float2* scratch, const float2* sD, 
         const float m1 = c[1][j].x * c[1][j].x + c[1][j].y * c[1][j].y;
         const unsigned k0 = (act & 1u) ? ((__float_as_uint(m0) & ~63u) | (unsigned)(63 - lane)) + 64u : 0u;
         const unsigned k1 = (act & 2u) ? ((__float_as_uint(m1) & ~63u) | (unsigned)(31 - lane)) + 64u : 0u;
+        // every lane forms the reciprocals of its own two candidates while the REDUX is in flight; the pivot's one is
+        // then a select + shuffle away (no MUFU on the dependent chain)
+        const float r0 = rcp_t(m0), r1 = rcp_t(m1);
+        const float2 ic0 = f2(c[0][j].x * r0, -c[0][j].y * r0), ic1 = f2(c[1][j].x * r1, -c[1][j].y * r1);
         const unsigned key = __reduce_max_sync(FULL, max(k0, k1));
         const int pr = 63 - (int)(key & 63u);
-        float2 pv = (pr & 32) ? c[1][j] : c[0][j];
-        pv.x = __shfl_sync(FULL, pv.x, pr & 31);
-        pv.y = __shfl_sync(FULL, pv.y, pr & 31);
-        const float id = rcp_t(pv.x * pv.x + pv.y * pv.y);
-        const float2 inv = f2(pv.x * id, -pv.y * id);
+        float2 inv = (pr & 32) ? ic1 : ic0;
+        inv.x = __shfl_sync(FULL, inv.x, pr & 31);
+        inv.y = __shfl_sync(FULL, inv.y, pr & 31);
         float2 l0 = f2(0.f, 0.f), l1 = f2(0.f, 0.f);
         if ((act & 1u) && lane != pr) c[0][j] = l0 = cmul2(c[0][j], inv);
         if ((act & 2u) && lane + 32 != pr) c[1][j] = l1 = cmul2(c[1][j], inv);
@@ -269,10 +298,10 @@ __device__ __forceinline__ void lu(State& S, float2* scratch, const float2* sD, 
           hi.y = tf32_hi(a16[4 * q + 1]);
           hi.z = tf32_hi(a16[4 * q + 2]);
           hi.w = tf32_hi(a16[4 * q + 3]);
-          lo.x = a16[4 * q + 0] - hi.x;
-          lo.y = a16[4 * q + 1] - hi.y;
-          lo.z = a16[4 * q + 2] - hi.z;
-          lo.w = a16[4 * q + 3] - hi.w;
+          lo.x = tf32_hi(a16[4 * q + 0] - hi.x);
+          lo.y = tf32_hi(a16[4 * q + 1] - hi.y);
+          lo.z = tf32_hi(a16[4 * q + 2] - hi.z);
+          lo.w = tf32_hi(a16[4 * q + 3] - hi.w);
           *reinterpret_cast<float4*>(sAhi + q * (128 * 4) + t * 4) = hi;
           *reinterpret_cast<float4*>(sAlo + q * (128 * 4) + t * 4) = lo;
         }
@@ -281,12 +310,17 @@ __device__ __forceinline__ void lu(State& S, float2* scratch, const float2* sD, 
       const bool is_piv = pos >= c0 && pos < c0 + NB;
       float* urow = sU + (part * NB + (pos - c0)) * ULD;
 #pragma unroll 1
-      for (int cc = c0 + NB; cc < NCOL; cc += 8) {
-        float v[8];
-        tmem_ld8(tlane + cc, v);
+      for (int cc = c0 + NB; cc < NCOL; cc += 16) {
+        float v[16];
+        const bool two = cc + 8 < NCOL;  // (block-uniform)
+        tmem_ld8x2(tlane + cc, v, two);
         if (is_piv) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) urow[cc + i] = v[i];
+          if (two) {
+#pragma unroll
+            for (int i = 8; i < 16; ++i) urow[cc + i] = v[i];
+          }
         }
       }
     }
@@ -321,10 +355,10 @@ __device__ __forceinline__ void lu(State& S, float2* scratch, const float2* sD, 
           hi[q].y = tf32_hi(b16[4 * q + 1]);
           hi[q].z = tf32_hi(b16[4 * q + 2]);
           hi[q].w = tf32_hi(b16[4 * q + 3]);
-          lo[q].x = b16[4 * q + 0] - hi[q].x;
-          lo[q].y = b16[4 * q + 1] - hi[q].y;
-          lo[q].z = b16[4 * q + 2] - hi[q].z;
-          lo[q].w = b16[4 * q + 3] - hi[q].w;
+          lo[q].x = tf32_hi(b16[4 * q + 0] - hi[q].x);
+          lo[q].y = tf32_hi(b16[4 * q + 1] - hi[q].y);
+          lo[q].z = tf32_hi(b16[4 * q + 2] - hi[q].z);
+          lo[q].w = tf32_hi(b16[4 * q + 3] - hi[q].w);
         }
       } else {
 #pragma unroll

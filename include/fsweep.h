@@ -259,6 +259,12 @@ FSWEEP_API int fsweep_allreduce_p2p_max_n(void);
 FSWEEP_API int fsweep_allreduce_p2p(void* const* peer_buffers, void* const* peer_signal_pads, int rank, int world, int n,
                                     double scale, void* epoch_counter, void* stream);
 
+/* FP32 FMA peak probe (bench.py's roofline denominator for the compute-bound sweeps; SURVEY.md section 8d "derive +
+ * measure"): `blocks` blocks of 256 threads, 64 independent FFMAs per thread and round; fsweep_fma_probe_flops gives the
+ * flop count of one launch, the caller times it with CUDA events.  out: device float[1] (never written in practice). */
+FSWEEP_API int fsweep_fma_probe(void* out, int blocks, int iters, void* stream);
+FSWEEP_API double fsweep_fma_probe_flops(int blocks, int iters);
+
 /* number of kernels the last forward / backward call of this thread enqueued (bench bookkeeping) */
 FSWEEP_API int fsweep_last_launch_count(void);
 
