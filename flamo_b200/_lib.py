@@ -24,7 +24,7 @@ EXPORTS = [
     "fsweep_version", "fsweep_last_error", "fsweep_plan_create", "fsweep_plan_destroy",
     "fsweep_plan_num_coeffs", "fsweep_plan_coeff_numel", "fsweep_plan_kernel_family", "fsweep_workspace_bytes",
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
-    "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward",
+    "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward", "fsweep_expm_forward_sp", "fsweep_expm_backward_sp",
     "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total",
     "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_adam_step", "fsweep_fma_probe", "fsweep_fma_probe_flops",
 ]
@@ -111,6 +111,10 @@ def lib():
     L.fsweep_expm_forward.argtypes = [vp, vp, i32, i32, i32, vp]
     L.fsweep_expm_backward.restype = i32
     L.fsweep_expm_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.fsweep_expm_forward_sp.restype = i32
+    L.fsweep_expm_forward_sp.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.fsweep_expm_backward_sp.restype = i32
+    L.fsweep_expm_backward_sp.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
     L.fsweep_sparsity_forward.restype = i32
     L.fsweep_sparsity_forward.argtypes = [vp, i32, i32, i32, vp, vp]
     L.fsweep_sparsity_backward.restype = i32

@@ -107,9 +107,11 @@ __device__ double* expm_inplace(double* X, double* W, int n, double* red) {
 }
 
 // IO type T (float | double) is the caller's parameter dtype; the arithmetic is float64 throughout.
+// sp (optional): sparsity_loss of the result (reference optimize/loss.py:36-63, one matrix):
+//   (sum |E| - n sqrt n) / (n (1 - sqrt n)),  evaluated on the values as stored (rounded to T)
 template <typename T>
 __global__ void __launch_bounds__(EXPM_THREADS) expm_fwd_kernel(const T* __restrict__ Pin, T* __restrict__ E,
-                                                               int n, int skew) {
+                                                               int n, int skew, T* __restrict__ sp) {
   extern __shared__ double sm[];
   double *X = sm, *W = sm + n * n, *red = sm + 8 * n * n;
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
@@ -120,12 +122,32 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_fwd_kernel(const T* __restr
   }
   __syncthreads();
   double* R = expm_inplace(X, W, n, red);
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) E[e] = (T)R[e];
+  double asum = 0.0;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const T v = (T)R[e];
+    E[e] = v;
+    asum += fabs((double)v);
+  }
+  if (sp != nullptr) {  // (uniform)
+    __shared__ double sred[EXPM_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = asum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < EXPM_THREADS / 32; ++w) t += sred[w];
+      const double rn = sqrt((double)n);
+      *sp = (T)((t - n * rn) / (n * (1.0 - rn)));
+    }
+  }
 }
 
+// G (optional): dL/dE;  Esp + gsp (optional): the sparsity_loss term above contributes gsp * sign(E) / (n (1 - sqrt n))
 template <typename T>
 __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const T* __restrict__ Pin, const T* __restrict__ G,
-                                                               T* __restrict__ gP, int n, int skew) {
+                                                               T* __restrict__ gP, int n, int skew,
+                                                               const T* __restrict__ Esp, const T* __restrict__ gsp) {
   extern __shared__ double sm[];
   const int m = 2 * n;
   double *X = sm, *W = sm + m * m, *red = sm + 8 * m * m;
@@ -133,7 +155,13 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const T* __restr
     int r = e / m, c = e - r * m;
     double v = 0.0;
     if (r < n && c >= n) {
-      v = (double)G[r * n + (c - n)];
+      if (G != nullptr) v = (double)G[r * n + (c - n)];
+      if (gsp != nullptr) {
+        const T a = Esp[r * n + (c - n)];
+        const double rn = sqrt((double)n);
+        const double k = (double)*gsp / (n * (1.0 - rn));
+        v += a > T(0) ? k : (a < T(0) ? -k : 0.0);
+      }
     } else if ((r < n) == (c < n)) {
       int i = r % n, j = c % n;  // block (i, j) of S^T = S[j][i]
       if (skew)
@@ -159,42 +187,60 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const T* __restr
 extern "C" FSWEEP_API int fsweep_expm_max_n(void) { return 28; }  // 8 matrices of (2n)^2 doubles in shared memory
 
 template <typename T>
-static int expm_forward_t(const T* P, T* E, int n, int skew, cudaStream_t st) {
+static int expm_forward_t(const T* P, T* E, int n, int skew, T* sp, cudaStream_t st) {
   size_t smem = (size_t)(8 * n * n + n + 8) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(expm_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return FSWEEP_E_CUDA;
   }
-  expm_fwd_kernel<T><<<1, EXPM_THREADS, smem, st>>>(P, E, n, skew);
+  expm_fwd_kernel<T><<<1, EXPM_THREADS, smem, st>>>(P, E, n, skew, sp);
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
 
 template <typename T>
-static int expm_backward_t(const T* P, const T* G, T* gP, int n, int skew, cudaStream_t st) {
+static int expm_backward_t(const T* P, const T* G, T* gP, int n, int skew, const T* Esp, const T* gsp, cudaStream_t st) {
   const int m = 2 * n;
   size_t smem = (size_t)(8 * m * m + m + 8) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(expm_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return FSWEEP_E_CUDA;
   }
-  expm_bwd_kernel<T><<<1, EXPM_THREADS, smem, st>>>(P, G, gP, n, skew);
+  expm_bwd_kernel<T><<<1, EXPM_THREADS, smem, st>>>(P, G, gP, n, skew, Esp, gsp);
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
 
+extern "C" FSWEEP_API int fsweep_expm_forward_sp(const void* P, void* E, int n, int skew, int dtype, void* sparsity,
+                                                 void* stream) {
+  if (!P || !E || n < 1 || n > 2 * fsweep_expm_max_n() || (sparsity && n < 2)) return FSWEEP_E_BADARG;
+  if (dtype == FSWEEP_C64)
+    return expm_forward_t<float>((const float*)P, (float*)E, n, skew, (float*)sparsity, (cudaStream_t)stream);
+  if (dtype == FSWEEP_C128)
+    return expm_forward_t<double>((const double*)P, (double*)E, n, skew, (double*)sparsity, (cudaStream_t)stream);
+  return FSWEEP_E_BADARG;
+}
+
 extern "C" FSWEEP_API int fsweep_expm_forward(const void* P, void* E, int n, int skew, int dtype, void* stream) {
-  if (!P || !E || n < 1 || n > 2 * fsweep_expm_max_n()) return FSWEEP_E_BADARG;
-  if (dtype == FSWEEP_C64) return expm_forward_t<float>((const float*)P, (float*)E, n, skew, (cudaStream_t)stream);
-  if (dtype == FSWEEP_C128) return expm_forward_t<double>((const double*)P, (double*)E, n, skew, (cudaStream_t)stream);
+  return fsweep_expm_forward_sp(P, E, n, skew, dtype, nullptr, stream);
+}
+
+extern "C" FSWEEP_API int fsweep_expm_backward_sp(const void* P, const void* G, void* gP, int n, int skew, int dtype,
+                                                  const void* E, const void* gsparsity, void* stream) {
+  if (!P || (!G && !gsparsity) || !gP || n < 1 || n > fsweep_expm_max_n() || (gsparsity && (!E || n < 2)))
+    return FSWEEP_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSWEEP_C64)
+    return expm_backward_t<float>((const float*)P, (const float*)G, (float*)gP, n, skew, (const float*)E,
+                                  (const float*)gsparsity, st);
+  if (dtype == FSWEEP_C128)
+    return expm_backward_t<double>((const double*)P, (const double*)G, (double*)gP, n, skew, (const double*)E,
+                                   (const double*)gsparsity, st);
   return FSWEEP_E_BADARG;
 }
 
 extern "C" FSWEEP_API int fsweep_expm_backward(const void* P, const void* G, void* gP, int n, int skew, int dtype,
                                                void* stream) {
-  if (!P || !G || !gP || n < 1 || n > fsweep_expm_max_n()) return FSWEEP_E_BADARG;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == FSWEEP_C64) return expm_backward_t<float>((const float*)P, (const float*)G, (float*)gP, n, skew, st);
-  if (dtype == FSWEEP_C128) return expm_backward_t<double>((const double*)P, (const double*)G, (double*)gP, n, skew, st);
-  return FSWEEP_E_BADARG;
+  if (!G) return FSWEEP_E_BADARG;
+  return fsweep_expm_backward_sp(P, G, gP, n, skew, dtype, nullptr, nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -41,14 +41,14 @@ class Trainer:
         params = list(self.net.parameters())
         self._all_params = params
         if self.use_graph:
-            # a captured step needs `step` and `lr` on the device: torch's capturable fused Adam (two launches: a
-            # foreach add on the step counters, then the multi-tensor update).  FLAMO_B200_SWEEP_ADAM=1 selects
-            # optimize/adam.py instead (the update of ALL parameters as one libfsweep launch, same arithmetic,
-            # tests/test_gpu_adam.py) — opt-in because it measured neutral on the step time (profiles/r01_notes.md)
+            # a captured step needs `step` and `lr` on the device.  Default: optimize/adam.py, the update of ALL
+            # parameters as ONE libfsweep launch (same arithmetic as torch.optim.Adam, tests/test_gpu_adam.py; 1.6 us
+            # per captured config-2 step faster than torch's capturable fused Adam, which is two launches: a foreach
+            # add on the step counters, then the multi-tensor update).  FLAMO_B200_SWEEP_ADAM=0 selects torch's.
             from .adam import SweepAdam
 
             lr_t = torch.tensor(float(lr), device=device, dtype=torch.float32)
-            if os.environ.get("FLAMO_B200_SWEEP_ADAM", "0") == "1" and SweepAdam.supported(params):
+            if os.environ.get("FLAMO_B200_SWEEP_ADAM", "1") == "1" and SweepAdam.supported(params):
                 self.optimizer = SweepAdam([p for p in params], lr=lr_t)
             else:
                 self.optimizer = torch.optim.Adam(params, lr=lr_t, capturable=True, fused=True)
@@ -157,7 +157,15 @@ class Trainer:
                 t = crit(est, targets, self.net) if needs_model else crit(est, targets)
             parts.append(t)
         scales = [1.0] * len(parts) if weight is None else [float(w) for w in weight]
+        self._parts = None
         if sweep.WeightedTotal.supported(parts):
+            if torch.is_grad_enabled() and all(p.requires_grad for p in parts):
+                # the combination is linear with CONSTANT weights: evaluate it outside autograd and let _train_core
+                # seed every criterion with its own constant d total / d part_i = alpha_i * scale_i (no backward
+                # kernels for the combination, and a weight of 1 costs the criterion's backward nothing)
+                self._parts = (parts, [float(a) * s for a, s in zip(self.alpha, scales)])
+                with torch.no_grad():
+                    return sweep.WeightedTotal.apply(tuple(self.alpha), tuple(scales), *[p.detach() for p in parts])
             return sweep.WeightedTotal.apply(tuple(self.alpha), tuple(scales), *parts)
         total = None
         for i, t in enumerate(parts):
@@ -189,9 +197,15 @@ class Trainer:
         from .. import sweep
 
         vals = self._loss_vector(inputs, targets)
-        # d total / d .: seed the backward pass on the vector itself with a constant one-hot (no select / fill kernels)
-        seed = sweep._const_tensor((0.0,) * (vals.numel() - 1) + (1.0,), vals.dtype, vals.device)
-        torch.autograd.backward(vals, grad_tensors=seed)
+        if getattr(self, "_parts", None) is not None:
+            parts, weights = self._parts
+            self._parts = None
+            seeds = [sweep._const_tensor((w,), p.dtype, p.device).reshape(p.shape) for p, w in zip(parts, weights)]
+            torch.autograd.backward(parts, grad_tensors=seeds)
+        else:
+            # d total / d .: seed the backward pass on the vector itself with a constant one-hot (no select / fill kernels)
+            seed = sweep._const_tensor((0.0,) * (vals.numel() - 1) + (1.0,), vals.dtype, vals.device)
+            torch.autograd.backward(vals, grad_tensors=seed)
         vals = self._sync(vals.detach())
         self.optimizer.step()
         return vals
@@ -229,12 +243,15 @@ class Trainer:
             with torch.cuda.graph(graph):
                 self._zero_grad_captured()
                 out = self._train_core(static_in, static_tg)
+                # the step's single device->host read is a node of the graph: the losses land in pinned host memory
+                out_host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                out_host.copy_(out, non_blocking=True)
         except Exception as e:  # keep training eagerly (still on the CUDA sweep) if capture is impossible
             warnings.warn(f"CUDA-graph capture of the training step failed ({e}); continuing without graph.")
             self.use_graph = False
             torch.cuda.synchronize()
             return None
-        g = (graph, static_in, static_tg, out, sweep.launch_count - n0)  # sweep kernels per replay
+        g = (graph, static_in, static_tg, out_host, sweep.launch_count - n0, [None, None])  # sweep kernels per replay
         self._graphs[key] = g
         return g
 
@@ -255,15 +272,22 @@ class Trainer:
             if g is not None:
                 from .. import sweep
 
-                graph, static_in, static_tg, out, n_kernels = g
-                static_in.copy_(inputs, non_blocking=True)
-                static_tg.copy_(targets, non_blocking=True)
+                graph, static_in, static_tg, out_host, n_kernels, last = g
+                # A DEVICE tensor that is the very tensor (storage, version) copied in by the previous step is already
+                # in the static buffer: a dataset resident in HBM costs no copy per step.  Host tensors are copied
+                # every step (from pinned memory: ONE asynchronous H2D copy per tensor).
+                for slot, (dst, src) in enumerate(((static_in, inputs), (static_tg, targets))):
+                    tag = (src.data_ptr(), src._version, src.device) if src.is_cuda else None
+                    if tag is None or last[slot] != tag:
+                        dst.copy_(src, non_blocking=True)
+                        last[slot] = tag
                 graph.replay()
                 sweep.launch_count += n_kernels
                 inval = getattr(self.net, "_invalidate_caches", None)
                 if inval is not None:  # parameters changed on the device without a version bump
                     inval()
-                vals = out.tolist()  # the step's single device->host read
+                torch.cuda.current_stream(static_in.device).synchronize()
+                vals = out_host.tolist()  # written by the graph's own device->host copy node
                 self._log(self.train_loss_log, vals[:-1])
                 return vals[-1]
             return self._eager_train_step(inputs, targets)

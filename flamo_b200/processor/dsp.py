@@ -322,12 +322,13 @@ class Matrix(Gain):
             hit = self._expm_cache
             if hit is not None and hit[0] == key:
                 return hit[1]
+        sp = None
         if sweep.OrthogonalMap.supported(x):
-            out = sweep.OrthogonalMap.apply(x)
+            out, sp = sweep.OrthogonalMap.apply(x)  # sp: sparsity_loss(out), for optimize.loss.sparsity_loss
         else:  # wider than the one-CTA kernel: capture-safe PyTorch scaling-and-squaring (float64 inside)
             out = expm_capturable(skew_matrix(x))
         if x is self.param:
-            self._expm_cache = (key, out)
+            self._expm_cache = (key, out, sp)
         return out
 
     def _up(self, param):

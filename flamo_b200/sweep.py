@@ -207,6 +207,10 @@ class SweepLossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if g.data_ptr() == _const_tensor((1.0,), g.dtype, g.device).data_ptr():
+            # the Trainer seeds every criterion with the cached constant alpha_i: for alpha = 1 (the usual weight of the
+            # prediction criterion) the kernel's gradients are already d total / d coefficients
+            return (ctx.gx, None, None, None, None, None, None, *ctx.grads)
         live = [t for t in ctx.grads if t is not None] + ([ctx.gx] if ctx.gx is not None else [])
         by_dtype = {}
         for t in live:
@@ -455,8 +459,10 @@ class Program:
 
 
 class OrthogonalMap(torch.autograd.Function):
-    """exp(triu(P,1) - triu(P,1)^T) on the device without a host read-back (libfsweep fsweep_expm_*),
-    the orthogonal map of dsp.Matrix (reference dsp.py:649)."""
+    """(E, sp) = (exp(triu(P,1) - triu(P,1)^T), sparsity_loss(E)) on the device without a host read-back (libfsweep
+    fsweep_expm_*_sp): the orthogonal map of dsp.Matrix (reference dsp.py:649) with the parameter-only criterion of the
+    colorless-FDN examples (reference optimize/loss.py:36-63) riding along — sparsity_loss picks `sp` up instead of
+    launching its own kernels, and both gradients go back through the map in ONE backward launch."""
 
     @staticmethod
     def supported(P: torch.Tensor) -> bool:
@@ -468,23 +474,35 @@ class OrthogonalMap(torch.autograd.Function):
         global launch_count
         Pc = P.detach().contiguous()
         E = torch.empty_like(Pc)
+        n = Pc.shape[0]
+        sp = torch.empty((), dtype=Pc.dtype, device=Pc.device) if n >= 2 else torch.zeros((), dtype=Pc.dtype,
+                                                                                               device=Pc.device)
         with torch.cuda.device(P.device):
-            _lib.check(_lib.lib().fsweep_expm_forward(Pc.data_ptr(), E.data_ptr(), Pc.shape[0], 1, _real_code(Pc.dtype),
-                                                       torch.cuda.current_stream(P.device).cuda_stream))
+            _lib.check(_lib.lib().fsweep_expm_forward_sp(Pc.data_ptr(), E.data_ptr(), n, 1, _real_code(Pc.dtype),
+                                                          sp.data_ptr() if n >= 2 else None,
+                                                          torch.cuda.current_stream(P.device).cuda_stream))
         launch_count += 1
-        ctx.save_for_backward(Pc)
-        return E
+        ctx.save_for_backward(Pc, E)
+        return E, sp
 
     @staticmethod
-    def backward(ctx, G):
+    def backward(ctx, G, gsp):
         global launch_count
-        (Pc,) = ctx.saved_tensors
-        Gc = G.to(Pc.dtype).contiguous()
+        Pc, E = ctx.saved_tensors
+        n = Pc.shape[0]
+        if n < 2:
+            gsp = None
+        if G is None and gsp is None:
+            return None
+        Gc = G.to(Pc.dtype).contiguous() if G is not None else None
+        gs = gsp.to(Pc.dtype).contiguous() if gsp is not None else None
         gP = torch.empty_like(Pc)
-        with torch.cuda.device(G.device):
-            _lib.check(_lib.lib().fsweep_expm_backward(Pc.data_ptr(), Gc.data_ptr(), gP.data_ptr(), Pc.shape[0], 1,
-                                                        _real_code(Pc.dtype),
-                                                        torch.cuda.current_stream(G.device).cuda_stream))
+        with torch.cuda.device(Pc.device):
+            _lib.check(_lib.lib().fsweep_expm_backward_sp(Pc.data_ptr(), Gc.data_ptr() if Gc is not None else None,
+                                                           gP.data_ptr(), n, 1, _real_code(Pc.dtype),
+                                                           E.data_ptr() if gs is not None else None,
+                                                           gs.data_ptr() if gs is not None else None,
+                                                           torch.cuda.current_stream(Pc.device).cuda_stream))
         launch_count += 1
         return gP
 

@@ -216,6 +216,13 @@ FSWEEP_API int fsweep_backward_loss(const fsweep_plan_t* plan, const void* const
 FSWEEP_API int fsweep_expm_max_n(void);
 FSWEEP_API int fsweep_expm_forward(const void* P, void* E, int n, int skew, int dtype, void* stream);
 FSWEEP_API int fsweep_expm_backward(const void* P, const void* G, void* gP, int n, int skew, int dtype, void* stream);
+/* The same with the sparsity_loss of the result (optimize/loss.py:36-63, below) riding along: forward also writes
+ * sparsity = (sum |E| - n sqrt n) / (n (1 - sqrt n)) (device real[1], or NULL); backward takes dL/dE in G (or NULL) and
+ * dL/dsparsity in gsparsity (device real[1], or NULL; E = the forward result) and returns the gradient of both through
+ * the map — the parameter-sized part of a colorless-FDN training step is then ONE launch each way. */
+FSWEEP_API int fsweep_expm_forward_sp(const void* P, void* E, int n, int skew, int dtype, void* sparsity, void* stream);
+FSWEEP_API int fsweep_expm_backward_sp(const void* P, const void* G, void* gP, int n, int skew, int dtype, const void* E,
+                                       const void* gsparsity, void* stream);
 
 /* sparsity_loss of the mapped feedback matrix (reference optimize/loss.py:36-63), A: device real[n_mats][n][n]:
  *   loss = mean_i ((sum |A_i| - n sqrt n) / (n (1 - sqrt n)));  backward: gA = gloss * dloss/dA (gloss: device real[1]).

@@ -15,7 +15,7 @@ def test_expm_matches_torch(n, scale):
     torch.manual_seed(n)
     P = (scale * torch.randn(n, n, dtype=torch.float64, device="cuda")).requires_grad_(True)
     Q = P.detach().clone().requires_grad_(True)
-    E = sweep.OrthogonalMap.apply(P)
+    E = sweep.OrthogonalMap.apply(P)[0]
     Er = torch.matrix_exp(skew_matrix(Q))
     import scipy.linalg
 
@@ -32,16 +32,16 @@ def test_expm_matches_torch(n, scale):
 
 def test_expm_float32_parameter_and_capture():
     P = torch.randn(8, 8, device="cuda", requires_grad=True)
-    E = sweep.OrthogonalMap.apply(P)
+    E = sweep.OrthogonalMap.apply(P)[0]
     assert E.dtype == torch.float32
     assert torch.allclose(E, torch.matrix_exp(skew_matrix(P.detach().double())).float(), atol=1e-6)
     del E  # an autograd graph kept alive from before the capture would pin P's AccumulateGrad to the default stream
     for _ in range(2):  # warm-up on the current stream, like Trainer._graph_for
-        sweep.OrthogonalMap.apply(P).sum().backward()
+        sweep.OrthogonalMap.apply(P)[0].sum().backward()
     P.grad = None
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        out = sweep.OrthogonalMap.apply(P)
+        out = sweep.OrthogonalMap.apply(P)[0]
         out.square().sum().backward()
     with torch.no_grad():
         P.add_(0.1)
@@ -71,3 +71,35 @@ def test_sparsity_kernels_match_reference_formula(shape, dtype):
     tol = 1e-6 if dtype == torch.float32 else 1e-13
     assert abs(float(out.detach()) - float(ref.detach())) <= tol * max(1.0, abs(float(ref.detach())))
     assert torch.allclose(go, gr, rtol=tol * 10, atol=tol)
+
+
+@pytest.mark.parametrize("n", [2, 8, 13])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_sparsity_rides_along_with_the_orthogonal_map(n, dtype):
+    """OrthogonalMap returns (E, sparsity_loss(E)) from one launch and takes both gradients back in one launch:
+    against torch.matrix_exp + the reference formula (optimize/loss.py:55-63), separately and together."""
+    torch.manual_seed(n)
+    P = torch.randn(n, n, device="cuda", dtype=dtype, requires_grad=True)
+    Wt = torch.randn(n, n, device="cuda", dtype=dtype)
+
+    def ref(p):
+        u = p.triu(1)
+        E = torch.matrix_exp((u - u.T).double())
+        sp = -(E.abs().sum() - n * n ** 0.5) / (n * (n ** 0.5 - 1))
+        return E, sp
+
+    tol = 2e-5 if dtype == torch.float32 else 1e-11
+    for use_e, use_sp in ((True, True), (False, True), (True, False)):
+        P.grad = None
+        E, sp = sweep.OrthogonalMap.apply(P)
+        loss = (E * Wt).sum() * (1.0 if use_e else 0.0) * (1 if use_e else 0) if use_e else 0.0
+        loss = loss + (0.7 * sp if use_sp else 0.0)
+        loss.backward()
+        Pr = P.detach().clone().requires_grad_(True)
+        Er, spr = ref(Pr)
+        lr_ = ((Er * Wt.double()).sum() if use_e else 0.0) + (0.7 * spr if use_sp else 0.0)
+        lr_.backward()
+        assert abs(float(sp) - float(spr)) <= tol * max(1.0, abs(float(spr)))
+        assert float((E.double() - Er).abs().max()) <= tol
+        g, gr = P.grad.double(), Pr.grad.double()
+        assert float((g - gr).abs().max()) <= 5 * tol * max(1.0, float(gr.abs().max()))
