@@ -502,18 +502,45 @@ int cta_grid(fsweep_plan* p, bool bwd, int64_t n_bins, cudaError_t* err) {
 }
 
 // per-call geometry of the streaming kernels; returns false when this call cannot use them
-bool stream_setup(const fsweep_plan* p, int64_t q, bool bwd, StreamInfo* S, size_t* smem) {
+// TMA (bulk-copy) variant of the streaming kernels: every table block (and table-gradient block) of the call must start
+// on a 16-byte boundary — true for whole tables, not for every bin shard.  OPT-IN (FSWEEP_STREAM_TMA=1): measured on a
+// B200 it is 6 - 30 % SLOWER than the cp.async path (profiles/r02_notes.md) — the ring of three tile buffers costs
+// shared memory, shared memory per bin is what bounds the bins in flight per SM, and the kernel is bound by the
+// LDS -> FMA latency of the bins in flight, not by the DRAM latency the ring hides.
+bool stream_tma_ok(const ProgK& P, const StreamInfo& S, int64_t bin_begin, bool bwd) {
+  const char* env = getenv("FSWEEP_STREAM_TMA");  // read per call: tests toggle it
+  if (!(env && env[0] == '1')) return false;
+  for (int i = 0; i < S.n_ops; ++i) {
+    if (S.row_bytes[i] <= 0 || P.ops[i].coef == nullptr) continue;
+    if ((reinterpret_cast<uintptr_t>(P.ops[i].coef) + (uintptr_t)bin_begin * S.row_bytes[i]) % 16) return false;
+    if (bwd && P.ops[i].acc_mode == ACC_TABLE &&
+        (reinterpret_cast<uintptr_t>(P.ops[i].gtab) + (uintptr_t)bin_begin * S.row_bytes[i]) % 16)
+      return false;
+  }
+  return true;
+}
+
+bool stream_setup(const fsweep_plan* p, int64_t q, bool bwd, bool tma, StreamInfo* S, size_t* smem) {
   if (!p->stream || q < 1 || q > 16 || (q & (q - 1)) != 0) return false;
   *S = p->sinfo;
   S->qc = (int)q;
-  S->threads = bwd ? 32 : 32;  // one thread per (bin, column); small blocks: shared memory per bin bounds the warps per SM
+  // one thread per (bin, column).  cp.async path: small blocks (shared memory per bin bounds the warps per SM); TMA
+  // path: tiles of >= 16 bins so that one bulk copy moves a few KB
+  static const int tma_threads = [] {
+    const char* e = getenv("FSWEEP_STREAM_TMA_THREADS");
+    const int v = e ? atoi(e) : 64;
+    return (v == 32 || v == 64 || v == 128) ? v : 64;
+  }();
+  S->threads = tma ? std::max(tma_threads, 2 * (int)q) : 32;
   S->tb = S->threads / (int)q;
+  if (tma && (S->tb & 1)) return false;  // block sizes must be multiples of 16 bytes (rows are multiples of 8)
   for (int i = 0; i < S->n_ops; ++i)
     if (S->tab_off[i] >= 0) S->tab_off[i] *= S->tb;  // blocks of tb rows per op inside a stage
   const size_t stage = (size_t)S->tb * S->bytes_per_bin;
   const size_t n_state = bwd ? (size_t)S->st_total : 2 * SW;
-  *smem = S_STAGES * stage + n_state * S->threads * 8 +
-          (bwd ? (size_t)2 * SW * S->threads * 8 + stage + (size_t)S->n_pgain_acc * 4 : 0) + 16;
+  *smem = (tma ? S_TMA_STAGES : S_STAGES) * stage + n_state * S->threads * 8 +
+          (bwd ? (size_t)2 * SW * S->threads * 8 + stage + (size_t)S->n_pgain_acc * 4 : 0) + 16 +
+          (tma ? 16 + 8 * S_TMA_STAGES : 0);
   return *smem <= 200 * 1024;
 }
 
@@ -708,13 +735,16 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
   const int dtype = plan->dtype;
   StreamInfo SI;
   size_t ssmem = 0;
+  bool stream_tma = false;
   if (plan->cta) {
     cfg.grid = cta_grid(plan, false, n_bins, &e);
     if (e == cudaSuccess) e = launch_cta(false, plan->cta_tc, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
-  } else if (!crit && stream_setup(plan, batch * cols, false, &SI, &ssmem)) {
+  } else if (!crit && ((stream_tma = plan->stream && stream_tma_ok(P, plan->sinfo, bin_begin, false) &&
+                                     stream_setup(plan, batch * cols, false, true, &SI, &ssmem)) ||
+                       stream_setup(plan, batch * cols, false, false, &SI, &ssmem))) {
     int bps = plan->stream_bps_smem[0] == ssmem ? plan->stream_bps[0] : 0;
     if (bps == 0) {
-      e = occupancy_stream(false, SI.threads, ssmem, &bps);
+      e = occupancy_stream(false, stream_tma, SI.threads, ssmem, &bps);
       if (e == cudaSuccess) {
         plan->stream_bps[0] = bps;
         plan->stream_bps_smem[0] = ssmem;
@@ -723,7 +753,7 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
     if (e == cudaSuccess) {
       const int64_t tiles = (n_bins + SI.tb - 1) / SI.tb;
       cfg.grid = (int)std::min<int64_t>(tiles, (int64_t)std::max(1, bps) * std::max(1, plan->num_sms ? plan->num_sms : 148));
-      e = launch_stream(false, cfg.grid, ssmem, cfg.stream, P, SI, A, plan->G);
+      e = launch_stream(false, stream_tma, cfg.grid, ssmem, cfg.stream, P, SI, A, plan->G);
     }
   } else if (use_tpc(plan, n_bins)) {
     cfg.grid = tpc_grid(n_bins);
@@ -886,13 +916,16 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   const int dtype = plan->dtype;
   StreamInfo SI;
   size_t ssmem = 0;
+  bool stream_tma = false;
   if (plan->cta) {
     cfg.grid = cta_grid(plan, true, n_bins, &e);
     if (e == cudaSuccess) e = launch_cta(true, plan->cta_tc, cfg.grid, st, P, plan->loop, A, plan->G);
-  } else if (!crit && stream_setup(plan, batch * cols, true, &SI, &ssmem)) {
+  } else if (!crit && ((stream_tma = plan->stream && stream_tma_ok(P, plan->sinfo, bin_begin, true) &&
+                                     stream_setup(plan, batch * cols, true, true, &SI, &ssmem)) ||
+                       stream_setup(plan, batch * cols, true, false, &SI, &ssmem))) {
     int bps = plan->stream_bps_smem[1] == ssmem ? plan->stream_bps[1] : 0;
     if (bps == 0) {
-      e = occupancy_stream(true, SI.threads, ssmem, &bps);
+      e = occupancy_stream(true, stream_tma, SI.threads, ssmem, &bps);
       if (e == cudaSuccess) {
         plan->stream_bps[1] = bps;
         plan->stream_bps_smem[1] = ssmem;
@@ -902,7 +935,7 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
       const int64_t tiles = (n_bins + SI.tb - 1) / SI.tb;
       cfg.grid = (int)std::min<int64_t>(std::min<int64_t>(tiles, (int64_t)std::max(1, bps) * std::max(1, plan->num_sms ? plan->num_sms : 148)),
                                         grid_cap(n_bins, plan->G));
-      e = launch_stream(true, cfg.grid, ssmem, st, P, SI, A, plan->G);
+      e = launch_stream(true, stream_tma, cfg.grid, ssmem, st, P, SI, A, plan->G);
     }
   } else if (use_tpc(plan, n_bins)) {
     cfg.grid = tpc_grid(n_bins);

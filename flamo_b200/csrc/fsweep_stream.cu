@@ -3,32 +3,42 @@
 
 namespace fsweep {
 
-template <bool BWD>
+template <bool BWD, bool TMA>
 static cudaError_t configure(size_t smem) {
   static size_t configured = 0;  // per instantiation: largest dynamic shared memory size opted into so far
   if (smem <= configured) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(fsweep_stream_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e =
+      cudaFuncSetAttribute(fsweep_stream_kernel<BWD, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   configured = smem;
   return cudaSuccess;
 }
 
-cudaError_t launch_stream(bool bwd, int grid, size_t smem, cudaStream_t st, const ProgK& P, const StreamInfo& S,
-                          const SweepArgs& A, int G) {
-  cudaError_t e = bwd ? configure<true>(smem) : configure<false>(smem);
+template <bool BWD, bool TMA>
+static cudaError_t launch(int grid, size_t smem, cudaStream_t st, const ProgK& P, const StreamInfo& S, const SweepArgs& A,
+                          int G) {
+  cudaError_t e = configure<BWD, TMA>(smem);
   if (e != cudaSuccess) return e;
-  if (bwd)
-    fsweep_stream_kernel<true><<<grid, S.threads, smem, st>>>(P, S, A, G);
-  else
-    fsweep_stream_kernel<false><<<grid, S.threads, smem, st>>>(P, S, A, G);
+  fsweep_stream_kernel<BWD, TMA><<<grid, S.threads, smem, st>>>(P, S, A, G);
   return cudaGetLastError();
 }
 
-cudaError_t occupancy_stream(bool bwd, int threads, size_t smem, int* blocks_per_sm) {
-  cudaError_t e = bwd ? configure<true>(smem) : configure<false>(smem);
+template <bool BWD, bool TMA>
+static cudaError_t occupancy(int threads, size_t smem, int* blocks_per_sm) {
+  cudaError_t e = configure<BWD, TMA>(smem);
   if (e != cudaSuccess) return e;
-  if (bwd) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fsweep_stream_kernel<true>, threads, smem);
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fsweep_stream_kernel<false>, threads, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fsweep_stream_kernel<BWD, TMA>, threads, smem);
+}
+
+cudaError_t launch_stream(bool bwd, bool tma, int grid, size_t smem, cudaStream_t st, const ProgK& P, const StreamInfo& S,
+                          const SweepArgs& A, int G) {
+  if (tma) return bwd ? launch<true, true>(grid, smem, st, P, S, A, G) : launch<false, true>(grid, smem, st, P, S, A, G);
+  return bwd ? launch<true, false>(grid, smem, st, P, S, A, G) : launch<false, false>(grid, smem, st, P, S, A, G);
+}
+
+cudaError_t occupancy_stream(bool bwd, bool tma, int threads, size_t smem, int* blocks_per_sm) {
+  if (tma) return bwd ? occupancy<true, true>(threads, smem, blocks_per_sm) : occupancy<false, true>(threads, smem, blocks_per_sm);
+  return bwd ? occupancy<true, false>(threads, smem, blocks_per_sm) : occupancy<false, false>(threads, smem, blocks_per_sm);
 }
 
 }  // namespace fsweep

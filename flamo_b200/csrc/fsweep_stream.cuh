@@ -11,6 +11,14 @@
 // one contiguous, fully coalesced block per op and tile.  (A first version with one thread per (bin, output row,
 // column) and a barrier per op issued 1019 warp instructions per bin and was issue bound: profiles/r01l.)
 //
+// Two ways of bringing a tile in.  TMA (opt-in, FSWEEP_STREAM_TMA=1, when every table block of the call is 16-byte aligned): persistent
+// blocks, a ring of S_TMA_STAGES tile buffers filled by the bulk-copy engine — ONE elected thread issues one
+// cp.async.bulk per table op and tile (SASS: UBLKCP) against an mbarrier with the expected byte count, S_TMA_STAGES - 1
+// tiles ahead of the arithmetic — and table gradients leave the block the same way (cp.async.bulk shared -> global,
+// bulk_group).  Nobody spends an instruction on moving table bytes and the DRAM latency is hidden by the ring rather
+// than by occupancy.  Default: every thread copies 8-byte granules with cp.async, one tile per small block — measured
+// faster, because shared memory per bin (not DRAM latency) bounds this kernel (fsweep_api.cu, stream_tma_ok).
+//
 // Supported programs (host-checked, plan->stream): float32; no recursion; ops in {TABLE, PTABLE, GAIN, PGAIN};
 // widths <= 16; batch*cols a power of two <= 16; coefficient gradients for TABLE / PTABLE (written per bin) and PGAIN
 // (accumulated); dense GAIN only without gradient.  Everything else stays on the generic kernels.
@@ -24,6 +32,7 @@ namespace fsweep {
 constexpr int SW = 16;        // row slots per (bin, column)
 constexpr int S_STAGES = 1;   // tiles in flight per block: shared memory per bin bounds the warps per SM, and more resident blocks hide more latency than a deeper pipeline
 constexpr int S_MAXST = 96;   // saved-state entries per (bin, column): sum of op input widths + last output width
+constexpr int S_TMA_STAGES = 3;  // TMA path: tile buffers in the ring
 
 struct StreamInfo {
   int n_ops;
@@ -41,17 +50,115 @@ struct StreamInfo {
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) { __pipeline_memcpy_async(smem, gmem, 8); }
 
+// ---- TMA bulk copies + mbarrier (inline PTX; sm_90+)
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(s_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+// global -> shared, completion counted in bytes on `bar`; src, dst 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   s_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(s_u32(bar))
+               : "memory");
+}
+// shared -> global, tracked by the thread's bulk async-group
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+
+// ---- width-specialised inner loops.  The op chain is runtime data, but its widths are <= 16: one instantiation per
+// width keeps the vector an op consumes in REGISTERS and unrolls the dot products — no index arithmetic, one LDS
+// (the table entry) per complex multiply-add.  (The generic loops ran 13.9 M warp instructions for 4.8 M of use.)
+template <int NIN>
+__device__ __forceinline__ void table_rows(const float2* __restrict__ H, const float2* vin, float2* vout, int n_out,
+                                           int T) {  // vout[m] = sum_n H[m][n] vin[n]
+  float2 v[NIN];
+#pragma unroll
+  for (int n = 0; n < NIN; ++n) v[n] = vin[(size_t)n * T];
+  // (rows are independent accumulation chains: four of them in flight per thread)
+#pragma unroll 4
+  for (int m = 0; m < n_out; ++m) {
+    const float2* h = H + m * NIN;
+    float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;
+#pragma unroll
+    for (int n = 0; n < NIN; ++n) {
+      const float2 hh = h[n];
+      ax = fmaf(hh.x, v[n].x, ax);
+      bx = fmaf(-hh.y, v[n].y, bx);
+      ay = fmaf(hh.x, v[n].y, ay);
+      by = fmaf(hh.y, v[n].x, by);
+    }
+    vout[(size_t)m * T] = f2(ax + bx, ay + by);
+  }
+}
+template <int NOUT>
+__device__ __forceinline__ void table_cols(const float2* __restrict__ H, const float2* go, float2* gi, int n_in,
+                                           int T) {  // gi[n] = sum_m conj(H[m][n]) go[m]
+  float2 g[NOUT];
+#pragma unroll
+  for (int m = 0; m < NOUT; ++m) g[m] = go[(size_t)m * T];
+#pragma unroll 4
+  for (int n = 0; n < n_in; ++n) {
+    const float2* h = H + n;
+    float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;
+#pragma unroll
+    for (int m = 0; m < NOUT; ++m) {
+      const float2 hh = h[m * n_in];
+      ax = fmaf(hh.x, g[m].x, ax);
+      bx = fmaf(hh.y, g[m].y, bx);
+      ay = fmaf(hh.x, g[m].y, ay);
+      by = fmaf(-hh.y, g[m].x, by);
+    }
+    gi[(size_t)n * T] = f2(ax + bx, ay + by);
+  }
+}
+#define FSWEEP_WIDTH_SWITCH(W, CALL)                                                      \
+  switch (W) {                                                                            \
+    case 1: { constexpr int WW = 1; CALL; } break;                                        \
+    case 2: { constexpr int WW = 2; CALL; } break;                                        \
+    case 3: { constexpr int WW = 3; CALL; } break;                                        \
+    case 4: { constexpr int WW = 4; CALL; } break;                                        \
+    case 5: { constexpr int WW = 5; CALL; } break;                                        \
+    case 6: { constexpr int WW = 6; CALL; } break;                                        \
+    case 7: { constexpr int WW = 7; CALL; } break;                                        \
+    case 8: { constexpr int WW = 8; CALL; } break;                                        \
+    case 9: { constexpr int WW = 9; CALL; } break;                                        \
+    case 10: { constexpr int WW = 10; CALL; } break;                                      \
+    case 11: { constexpr int WW = 11; CALL; } break;                                      \
+    case 12: { constexpr int WW = 12; CALL; } break;                                      \
+    case 13: { constexpr int WW = 13; CALL; } break;                                      \
+    case 14: { constexpr int WW = 14; CALL; } break;                                      \
+    case 15: { constexpr int WW = 15; CALL; } break;                                      \
+    default: { constexpr int WW = 16; CALL; } break;                                      \
+  }
+
 // shared memory: [S_STAGES][tb * bytes_per_bin] tables | state columns [n_state][T] | (BWD) gradient columns [2][SW][T] |
 //                (BWD) [tb * bytes_per_bin] table-gradient staging | (BWD) [n_pgain_acc] block accumulators
 // where n_state = st_total (BWD: every op input is kept for its gradient) or 2*SW (forward: ping-pong).
 // ONE THREAD PER (bin, column): the whole op chain runs privately on thread-private shared-memory columns
 // (element i of thread t at [i*T + t]: conflict-free), so there is no barrier between ops and no idle row slot; the
 // only exchange is the sum over the columns of a bin in the table gradients (adjacent lanes, shuffles).
-template <bool BWD>
+template <bool BWD, bool TMA>
 __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constant__ ProgK P,
                                                             const __grid_constant__ StreamInfo S, const SweepArgs A,
                                                             int G) {
-  extern __shared__ __align__(16) unsigned char ssm[];
+  extern __shared__ __align__(128) unsigned char ssm[];
+  constexpr int NST = TMA ? S_TMA_STAGES : S_STAGES;
   const int tid = threadIdx.x, T = blockDim.x;
   const int qc = S.qc, tb = S.tb;
   const int c = tid & (qc - 1);  // column (fastest: the lanes of one bin are adjacent)
@@ -59,10 +166,12 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
   const size_t stage_bytes = (size_t)tb * S.bytes_per_bin;
   const int n_state = BWD ? S.st_total : 2 * SW;
   unsigned char* sTab = ssm;
-  float2* sState = reinterpret_cast<float2*>(ssm + S_STAGES * stage_bytes) + tid;  // element i: sState[i * T]
+  float2* sState = reinterpret_cast<float2*>(ssm + NST * stage_bytes) + tid;  // element i: sState[i * T]
   float2* sGrad = sState + (size_t)n_state * T;                                      // [2][SW] columns (BWD)
   unsigned char* sGTab = reinterpret_cast<unsigned char*>(sGrad - tid + (BWD ? (size_t)2 * SW * T : 0));
   float* sAcc = reinterpret_cast<float*>(sGTab + (BWD ? stage_bytes : 0));
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sAcc) +
+                                               (((BWD ? (size_t)S.n_pgain_acc * 4 : 0) + 15) / 16) * 16);  // [NST], TMA
 
   const long long n_tiles = (A.n_bins + tb - 1) / tb;
   const cx<float>* x = reinterpret_cast<const cx<float>*>(A.x);
@@ -72,6 +181,31 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
     for (int i = tid; i < S.n_pgain_acc; i += T) sAcc[i] = 0.f;
   }
 
+  if constexpr (TMA) {
+    if (tid == 0) {
+      for (int i = 0; i < NST; ++i) mbar_init(sBar + i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  // a tile is "full" when all tb bins exist: only full tiles go through the bulk-copy engine (sizes in multiples of 16)
+  auto is_full = [&](long long tile) { return (tile + 1) * tb <= A.n_bins; };
+  // ---- TMA tile loader: ONE thread, one bulk copy per table op, completion on the stage's mbarrier
+  auto issue_tma = [&](long long tile, int stage) {
+    if (tile < n_tiles && is_full(tile)) {
+      unsigned char* dst = sTab + (size_t)stage * stage_bytes;
+      uint32_t total = 0;
+      for (int i = 0; i < n_ops; ++i)
+        if (S.tab_off[i] >= 0) total += (uint32_t)(tb * S.row_bytes[i]);
+      mbar_expect_tx(sBar + stage, total);
+      for (int i = 0; i < n_ops; ++i) {
+        if (S.tab_off[i] < 0) continue;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.ops[i].coef) +
+                                   (size_t)(A.bin_begin + tile * tb) * S.row_bytes[i];
+        tma_load_1d(dst + S.tab_off[i], src, (uint32_t)(tb * S.row_bytes[i]), sBar + stage);
+      }
+    }
+  };
   // ---- asynchronous tile loader: every thread copies 8-byte granules of the tile's contiguous table blocks
   auto issue = [&](long long tile, int stage) {
     if (tile < n_tiles) {
@@ -90,12 +224,44 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
   };
 
   long long tile = blockIdx.x;
-  for (int s = 0; s < S_STAGES - 1; ++s) issue(tile + (long long)s * gridDim.x, s);
+  if constexpr (TMA) {
+    if (tid == 0)
+      for (int s = 0; s < NST - 1; ++s) issue_tma(tile + (long long)s * gridDim.x, s);
+  } else {
+    for (int s = 0; s < NST - 1; ++s) issue(tile + (long long)s * gridDim.x, s);
+  }
   int stage = 0;
+  uint32_t phases = 0;  // TMA: bit s = parity the next wait on stage s expects
   for (; tile < n_tiles; tile += gridDim.x) {
-    issue(tile + (long long)(S_STAGES - 1) * gridDim.x, (stage + S_STAGES - 1) % S_STAGES);
-    __pipeline_wait_prior(S_STAGES - 1);
-    __syncthreads();
+    if constexpr (TMA) {
+      // the stage refilled here was consumed in the previous iteration (its closing __syncthreads is behind us)
+      if (tid == 0) {
+        issue_tma(tile + (long long)(NST - 1) * gridDim.x, (stage + NST - 1) % NST);
+        // the previous tile's gradient blocks have left the staging buffer before anyone writes it again (the
+        // __syncthreads in front of the reverse sweep publishes this)
+        if (BWD) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      if (is_full(tile)) {
+        mbar_wait(sBar + stage, (phases >> stage) & 1u);
+        phases ^= 1u << stage;
+      } else {  // the one partial tile at the end of the range: plain loads
+        const int nb = (int)(A.n_bins - tile * tb);
+        unsigned char* dst = sTab + (size_t)stage * stage_bytes;
+        for (int i = 0; i < n_ops; ++i) {
+          if (S.tab_off[i] < 0) continue;
+          const float2* src = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(P.ops[i].coef) +
+                                                             (size_t)(A.bin_begin + tile * tb) * S.row_bytes[i]);
+          float2* d2 = reinterpret_cast<float2*>(dst + S.tab_off[i]);
+          const int n8 = nb * S.row_bytes[i] / 8;
+          for (int e = tid; e < n8; e += T) d2[e] = __ldg(src + e);
+        }
+        __syncthreads();
+      }
+    } else {
+      issue(tile + (long long)(NST - 1) * gridDim.x, (stage + NST - 1) % NST);
+      __pipeline_wait_prior(NST - 1);
+      __syncthreads();
+    }
     const unsigned char* tab = sTab + (size_t)stage * stage_bytes;
     const long long bl = tile * tb + bi;
     const bool live = bl < A.n_bins;
@@ -113,16 +279,7 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
       const int n_in = op.n_in, n_out = op.n_out;
       if (op.kind == FSWEEP_OP_TABLE) {
         const float2* H = reinterpret_cast<const float2*>(tab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
-        for (int m = 0; m < n_out; ++m) {
-          float ax = 0.f, ay = 0.f;
-#pragma unroll 4
-          for (int n = 0; n < n_in; ++n) {
-            const float2 h = H[m * n_in + n], v = vin[(size_t)n * T];
-            ax = fmaf(h.x, v.x, fmaf(-h.y, v.y, ax));
-            ay = fmaf(h.x, v.y, fmaf(h.y, v.x, ay));
-          }
-          vout[(size_t)m * T] = f2(ax, ay);
-        }
+        FSWEEP_WIDTH_SWITCH(n_in, table_rows<WW>(H, vin, vout, n_out, T))
       } else if (op.kind == FSWEEP_OP_PTABLE) {
         const float2* H = reinterpret_cast<const float2*>(tab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
         for (int m = 0; m < n_out; ++m) {
@@ -184,6 +341,7 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
         }
         gout[(size_t)m * T] = g;
       }
+      if constexpr (TMA) __syncthreads();  // thread 0 has seen the last bulk stores read the staging buffer
       // ---- reverse sweep
       int buf = 0;
       for (int i = n_ops - 1; i >= 0; --i) {
@@ -201,8 +359,12 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
             __syncwarp();
             const float2* go0 = go - c;  // column 0 of this bin
             const float2* v0 = v - c;
-            for (int e = c; e < n_out * n_in; e += qc) {
-              const int m = e / n_in, n = e - m * n_in;
+            int m = c / n_in, n = c - m * n_in;  // (m, n) walk along with e: no division per entry
+            for (int e = c; e < n_out * n_in; e += qc, n += qc) {
+              while (n >= n_in) {
+                n -= n_in;
+                ++m;
+              }
               float vx = 0.f, vy = 0.f;
               for (int cq = 0; cq < qc; ++cq) {
                 const float2 gm = go0[(size_t)m * T + cq], vn = v0[(size_t)n * T + cq];
@@ -213,16 +375,8 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
             }
             __syncwarp();  // nobody overwrites a gradient column while a neighbour still reads it
           }
-          for (int n = 0; n < n_in; ++n) {  // g_in[n] = sum_m conj(H[m][n]) g[m]
-            float ax = 0.f, ay = 0.f;
-#pragma unroll 4
-            for (int m = 0; m < n_out; ++m) {
-              const float2 h = H[m * n_in + n], gm = go[(size_t)m * T];
-              ax = fmaf(h.x, gm.x, fmaf(h.y, gm.y, ax));
-              ay = fmaf(h.x, gm.y, fmaf(-h.y, gm.x, ay));
-            }
-            gi[(size_t)n * T] = f2(ax, ay);
-          }
+          // g_in[n] = sum_m conj(H[m][n]) g[m]
+          FSWEEP_WIDTH_SWITCH(n_out, table_cols<WW>(H, go, gi, n_in, T))
         } else if (op.kind == FSWEEP_OP_PTABLE) {
           const float2* H = reinterpret_cast<const float2*>(tab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
           float2* gt = reinterpret_cast<float2*>(sGTab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
@@ -274,26 +428,37 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
                 mk<float>(gv.x, gv.y));
         }
       }
+      if constexpr (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging -> async proxy
       __syncthreads();
-      // ---- table gradients of the tile: contiguous blocks, coalesced 8-byte stores
+      // ---- table gradients of the tile: contiguous blocks (TMA: one bulk store per op; else coalesced 8-byte stores)
       {
         const long long b0 = tile * tb;
         const int nb = (int)min((long long)tb, A.n_bins - b0);
+        const bool bulk = TMA && nb == tb;
         for (int i = 0; i < n_ops; ++i) {
           const OpK& op = P.ops[i];
           if (op.acc_mode != ACC_TABLE || S.tab_off[i] < 0) continue;
-          float2* dst = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(op.gtab) +
-                                                  (size_t)(A.bin_begin + b0) * S.row_bytes[i]);
-          const float2* src = reinterpret_cast<const float2*>(sGTab + S.tab_off[i]);
-          const int n8 = nb * S.row_bytes[i] / 8;
-          for (int e = tid; e < n8; e += T) dst[e] = src[e];
+          unsigned char* gdst = reinterpret_cast<unsigned char*>(op.gtab) + (size_t)(A.bin_begin + b0) * S.row_bytes[i];
+          if (bulk) {
+            if (tid == 0) tma_store_1d(gdst, sGTab + S.tab_off[i], (uint32_t)(tb * S.row_bytes[i]));
+          } else {
+            float2* dst = reinterpret_cast<float2*>(gdst);
+            const float2* src = reinterpret_cast<const float2*>(sGTab + S.tab_off[i]);
+            const int n8 = nb * S.row_bytes[i] / 8;
+            for (int e = tid; e < n8; e += T) dst[e] = src[e];
+          }
         }
+        if (bulk && tid == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
     __syncthreads();  // everyone is done with this stage (and the staging buffer) before they are refilled
-    stage = (stage + 1) % S_STAGES;
+    stage = (stage + 1) % NST;
   }
-  __pipeline_wait_prior(0);
+  if constexpr (TMA) {
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    __pipeline_wait_prior(0);
+  }
 
   if constexpr (BWD) {
     // PGAIN accumulators -> partial[(row_off + 0) * G + row]
@@ -307,8 +472,8 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
   }
 }
 
-cudaError_t launch_stream(bool bwd, int grid, size_t smem, cudaStream_t st, const ProgK& P, const StreamInfo& S,
+cudaError_t launch_stream(bool bwd, bool tma, int grid, size_t smem, cudaStream_t st, const ProgK& P, const StreamInfo& S,
                           const SweepArgs& A, int G);
-cudaError_t occupancy_stream(bool bwd, int threads, size_t smem, int* blocks_per_sm);
+cudaError_t occupancy_stream(bool bwd, bool tma, int threads, size_t smem, int* blocks_per_sm);
 
 }  // namespace fsweep

@@ -236,7 +236,8 @@ def test_cta_per_bin_kernels_on_wide_fdn(N, B, tc, monkeypatch):
 
 
 @pytest.mark.parametrize("B,cols", [(1, None), (1, 4), (2, 2), (3, None)])
-def test_streaming_table_kernels(B, cols, monkeypatch):
+@pytest.mark.parametrize("tma", [False, True], ids=["cp.async", "tma"])
+def test_streaming_table_kernels(B, cols, tma, monkeypatch):
     """TABLE-heavy programs without recursion (FIR filter banks + gains, the shape of the real
     examples/e8_active_acoustics.py path) run on the streaming kernels (fsweep_stream.cuh) when batch*cols is a power of
     two <= 16: against the generic interpreter (FSWEEP_DISABLE_STREAM=1) and the oracle — outputs, table / gain
@@ -244,6 +245,7 @@ def test_streaming_table_kernels(B, cols, monkeypatch):
     from flamo_b200 import workloads as W
     from flamo_b200.processor import dsp, system
 
+    monkeypatch.setenv("FSWEEP_STREAM_TMA", "1" if tma else "0")  # bulk-copy ring (UBLKCP + mbarrier) or cp.async tiles
     nfft, alias = 2048, 30.0
     M = nfft // 2 + 1
     desc = ("Series", [

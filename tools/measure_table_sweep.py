@@ -36,7 +36,7 @@ def main():
         prog = sweep.Program(nfft, alias, X.dtype, X.device)
         core._lower(prog, None)
         (tag, payload), = list(prog._segments())
-        ops, coefs, n_out = prog.flatten_segment(payload)
+        ops, coefs, n_out = prog.flatten_segment(payload, X.dtype)
     coefs = [c.detach().contiguous() for c in coefs]
     plan = prog.plan_for(ops)
     cols = n_M
