@@ -26,7 +26,7 @@ EXPORTS = [
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward", "fsweep_expm_forward_sp", "fsweep_expm_backward_sp",
     "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total",
-    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_adam_step", "fsweep_fma_probe", "fsweep_fma_probe_flops",
+    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_allreduce_push", "fsweep_adam_step", "fsweep_fma_probe", "fsweep_fma_probe_flops",
 ]
 
 
@@ -36,6 +36,11 @@ class Op(C.Structure):
         ("kind", C.c_int32), ("n_out", C.c_int32), ("n_in", C.c_int32), ("n_sections", C.c_int32),
         ("flags", C.c_uint32), ("n_ff", C.c_int32), ("n_fb", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+class Seg(C.Structure):
+    """fsweep_seg_t"""
+    _fields_ = [("ptr", C.c_void_p), ("numel", C.c_int64)]
 
 
 class Criterion(C.Structure):
@@ -122,6 +127,8 @@ def lib():
     L.fsweep_allreduce_p2p_max_n.restype = i32
     L.fsweep_allreduce_p2p.restype = i32
     L.fsweep_allreduce_p2p.argtypes = [vp, vp, i32, i32, i32, C.c_double, vp, vp]
+    L.fsweep_allreduce_push.restype = i32
+    L.fsweep_allreduce_push.argtypes = [C.POINTER(Seg), i32, vp, vp, i32, i32, i32, C.c_double, vp, vp]
     L.fsweep_adam_step.restype = i32
     L.fsweep_adam_step.argtypes = [C.POINTER(AdamTensor), i32, i32, vp, C.c_double, C.c_double, C.c_double, vp]
     L.fsweep_fma_probe.restype = i32

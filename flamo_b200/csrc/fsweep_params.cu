@@ -438,6 +438,97 @@ extern "C" FSWEEP_API int fsweep_allreduce_p2p(void* const* peer_buffers, void* 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The same exchange as a PUSH, with the packing and unpacking inside: the step's gradients stay where autograd left
+// them (one tensor per parameter) and the kernel (1) gathers the segments and STORES them straight into slot [rank] of
+// every peer's receive area over NVLink (posted writes: nothing waits for a round trip), (2) releases one flag per peer,
+// (3) waits for the peers' flags in its own pad, (4) sums the `world` slots of its OWN receive area (local loads, fixed
+// rank order: bit-identical on every rank), scales, and scatters the result back into the segments.  The receive
+// areas are double buffered on the epoch's parity, so ONE flag round per step is enough: a rank that writes parity p
+// again (two steps later) has passed the step in between, which every peer enters only after it finished reading p.
+// Replaces torch.cat + fsweep_allreduce_p2p (two flag rounds, peer loads) + views in flamo_b200/parallel.py.
+namespace {
+struct SegArgs {
+  float* ptr[FSWEEP_AR_MAX_SEGS];
+  int off[FSWEEP_AR_MAX_SEGS + 1];  // prefix offsets in floats; off[n_segs] = n
+  int n_segs;
+};
+
+__global__ void __launch_bounds__(AR_THREADS) allreduce_push_kernel(const __grid_constant__ SegArgs sg,
+                                                                   float* const* __restrict__ bufs,
+                                                                   unsigned* const* __restrict__ pads, int rank, int world,
+                                                                   int cap, float scale, unsigned* epoch_ctr) {
+  __shared__ unsigned s_epoch;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_epoch = *epoch_ctr + 1u;
+  __syncthreads();
+  const unsigned epoch = s_epoch;
+  const int n = sg.off[sg.n_segs];
+  const size_t par = (size_t)(epoch & 1u) * world * cap;  // this step's half of every receive area
+  float* seg_ptr[AR_PER];
+  // (1) gather + push
+#pragma unroll
+  for (int i = 0; i < AR_PER; ++i) {
+    const int idx = tid + i * AR_THREADS;
+    seg_ptr[i] = nullptr;
+    if (idx < n) {
+      int s_ = 0;
+      while (idx >= sg.off[s_ + 1]) ++s_;
+      seg_ptr[i] = sg.ptr[s_] + (idx - sg.off[s_]);
+      const float v = *seg_ptr[i];
+      for (int r = 0; r < world; ++r) bufs[r][par + (size_t)rank * cap + idx] = v;
+    }
+  }
+  // (2) + (3): one flag round
+  __syncthreads();
+  if (tid < world) {
+    __threadfence_system();
+    st_release_sys(pads[tid] + AR_PAD_OFF + 128 + rank, epoch);
+    const unsigned* mine = pads[rank] + AR_PAD_OFF + 128 + tid;
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys(mine) - epoch) < 0 && ++spins < (1u << 26)) {
+    }
+    if ((int)(ld_acquire_sys(mine) - epoch) < 0) atomicExch(epoch_ctr + 1, 1u + (unsigned)tid);  // sticky error flag
+  }
+  __syncthreads();
+  // (4) local sum in rank order, scatter back
+  const float* mybuf = bufs[rank] + par;
+#pragma unroll
+  for (int i = 0; i < AR_PER; ++i) {
+    const int idx = tid + i * AR_THREADS;
+    if (idx < n) {
+      float s_ = 0.f;
+      for (int r = 0; r < world; ++r) s_ += __ldcv(mybuf + (size_t)r * cap + idx);
+      *seg_ptr[i] = s_ * scale;
+    }
+  }
+  if (tid == 0) *epoch_ctr = epoch;
+}
+}  // namespace
+
+extern "C" FSWEEP_API int fsweep_allreduce_push(const fsweep_seg_t* segs, int n_segs, void* const* peer_buffers,
+                                                void* const* peer_signal_pads, int rank, int world, int cap, double scale,
+                                                void* epoch_counter, void* stream) {
+  if (!segs || n_segs < 1 || n_segs > FSWEEP_AR_MAX_SEGS || !peer_buffers || !peer_signal_pads || !epoch_counter ||
+      world < 1 || world > 64 || rank < 0 || rank >= world || cap < 1)
+    return FSWEEP_E_BADARG;
+  SegArgs a;
+  a.n_segs = n_segs;
+  int64_t off = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    if (!segs[i].ptr || segs[i].numel < 1) return FSWEEP_E_BADARG;
+    a.ptr[i] = reinterpret_cast<float*>(segs[i].ptr);
+    a.off[i] = (int)off;
+    off += segs[i].numel;
+    if (off > AR_THREADS * AR_PER || off > cap) return FSWEEP_E_BADARG;
+  }
+  a.off[n_segs] = (int)off;
+  allreduce_push_kernel<<<1, AR_THREADS, 0, (cudaStream_t)stream>>>(
+      a, reinterpret_cast<float* const*>(peer_buffers), reinterpret_cast<unsigned* const*>(peer_signal_pads), rank, world,
+      cap, (float)scale, reinterpret_cast<unsigned*>(epoch_counter));
+  return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam's update, reference optimize/trainer.py:42: the Trainer's optimizer) for ALL parameters of a
 // model in ONE launch: one block per parameter tensor, its step counter in device memory (read, used, written back by
 // that block only), learning rate read from device memory (schedulers fill it in place).  torch's capturable fused

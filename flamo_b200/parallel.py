@@ -56,11 +56,12 @@ class DataParallelTrainer(Trainer):
                 or os.environ.get("FLAMO_B200_P2P_ALLREDUCE", "1") == "0"):
             return None
         try:
-            if numel > _lib.lib().fsweep_allreduce_p2p_max_n():
+            if numel > _lib.lib().fsweep_allreduce_p2p_max_n() or len(self._ps) + 1 > 32:
                 return None
             import torch.distributed._symmetric_memory as symm_mem
 
-            buf = symm_mem.empty(numel, dtype=dtype, device=device)
+            # receive area of the push kernel: [2 (epoch parity)][world][numel]
+            buf = symm_mem.empty(2 * self.world * numel, dtype=dtype, device=device)
             buf.zero_()
             hdl = symm_mem.rendezvous(buf, self.pg if self.pg is not None else dist.group.WORLD)
             if hdl.signal_pad_size < 2048 or hdl.world_size != self.world:
@@ -81,11 +82,12 @@ class DataParallelTrainer(Trainer):
         total = sum(p.numel() for p in ps)
         dt = ps[0].dtype
         self._p2p = None
-        self._flat = self._p2p_buffer(total + n_vals, dt, ps[0].device)
-        if self._flat is None:
-            self._flat = torch.zeros(total + n_vals, dtype=dt, device=ps[0].device)
         self._ps = ps
         self._n_grad = total
+        self._cap = total + n_vals
+        self._recv = self._p2p_buffer(total + n_vals, dt, ps[0].device) if all(p.dtype == dt for p in ps) else None
+        # NCCL fallback: gradients and loss values are packed into one flat buffer, one all-reduce
+        self._flat = torch.zeros(total + n_vals, dtype=dt, device=ps[0].device) if self._recv is None else self._recv
 
     # backward writes ordinary per-parameter gradients; ONE cat packs them (and the loss values) into the flat
     # buffer right before the collective, and the parameters' .grad then become views of the reduced buffer
@@ -114,29 +116,40 @@ class DataParallelTrainer(Trainer):
         if self.world == 1:
             return vals
         dt = self._flat.dtype
+        scale = 1.0 / self.world if self.shard == "batch" else 1.0
+        if self._p2p is not None and vals.dtype == dt:
+            # ONE kernel per rank over NVLink peer memory, in place on the tensors autograd left behind: gather the
+            # gradients (and the loss values), push them into every peer's receive area, one flag round, local sum in
+            # rank order, scale, scatter back (libfsweep fsweep_allreduce_push) — no cat, no views, no second launch
+            from . import _lib
+
+            for p in self._ps:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                elif not p.grad.is_contiguous():
+                    p.grad = p.grad.contiguous()
+            vals = vals.contiguous()
+            tensors = [p.grad for p in self._ps] + [vals]
+            segs = (_lib.Seg * len(tensors))(*[_lib.Seg(t.data_ptr(), t.numel()) for t in tensors])
+            hdl, epoch = self._p2p
+            with torch.cuda.device(vals.device):
+                _lib.check(_lib.lib().fsweep_allreduce_push(segs, len(tensors), hdl.buffer_ptrs_dev,
+                                                             hdl.signal_pad_ptrs_dev, hdl.rank, hdl.world_size,
+                                                             self._cap, scale, epoch.data_ptr(),
+                                                             torch.cuda.current_stream(vals.device).cuda_stream))
+            sweep.launch_count += 1
+            return vals
         pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(dt) for p in self._ps]
-        torch.cat(pieces + [vals.to(dt)], out=self._flat)
+        torch.cat(pieces + [vals.to(dt)], out=self._flat[:self._cap])
         off = 0
         for p in self._ps:
             p.grad = self._flat[off:off + p.numel()].view_as(p)
             off += p.numel()
-        scale = 1.0 / self.world if self.shard == "batch" else 1.0
-        if self._p2p is not None:
-            # ONE kernel per rank over NVLink peer memory: signal, read every peer's buffer, sum, scale, write back
-            from . import _lib
-
-            hdl, epoch = self._p2p
-            with torch.cuda.device(self._flat.device):
-                _lib.check(_lib.lib().fsweep_allreduce_p2p(hdl.buffer_ptrs_dev, hdl.signal_pad_ptrs_dev, hdl.rank,
-                                                            hdl.world_size, self._flat.numel(), scale,
-                                                            epoch.data_ptr(),
-                                                            torch.cuda.current_stream(self._flat.device).cuda_stream))
-            sweep.launch_count += 1
-        else:
-            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
-            if self.shard == "batch":
-                self._flat.div_(self.world)
-        return self._flat[self._n_grad:].to(vals.dtype)
+        flat = self._flat[:self._cap]
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.shard == "batch":
+            flat.div_(self.world)
+        return self._flat[self._n_grad:self._cap].to(vals.dtype)
 
     def check_exchange(self):
         """Raises if the peer-memory all-reduce ever timed out waiting for a peer (its results are then undefined).

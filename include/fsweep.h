@@ -266,6 +266,21 @@ FSWEEP_API int fsweep_allreduce_p2p_max_n(void);
 FSWEEP_API int fsweep_allreduce_p2p(void* const* peer_buffers, void* const* peer_signal_pads, int rank, int world, int n,
                                     double scale, void* epoch_counter, void* stream);
 
+/* The same exchange as ONE push kernel that also packs and unpacks: `segs` are the step's float32 gradient tensors (and the
+ * loss values), reduced IN PLACE.  Every rank's receive area (peer_buffers[r], symmetric memory) holds 2 * world * cap
+ * floats (double buffered on the epoch parity: one flag round per call); cap >= the total number of values.  Gathers the
+ * segments, stores them into slot [rank] of every peer's area over NVLink, one release / acquire flag round, then sums
+ * its own area's slots in rank order (bit-identical on every rank), scales and scatters back.  epoch_counter and the
+ * signal pads as above (a different flag range: both kernels may share pads).  Capture safe. */
+#define FSWEEP_AR_MAX_SEGS 32
+typedef struct fsweep_seg {
+  void* ptr;     /* device float32 */
+  int64_t numel;
+} fsweep_seg_t;
+FSWEEP_API int fsweep_allreduce_push(const fsweep_seg_t* segs, int n_segs, void* const* peer_buffers,
+                                     void* const* peer_signal_pads, int rank, int world, int cap, double scale,
+                                     void* epoch_counter, void* stream);
+
 /* FP32 FMA peak probe (bench.py's roofline denominator for the compute-bound sweeps; SURVEY.md section 8d "derive +
  * measure"): `blocks` blocks of 256 threads, 64 independent FFMAs per thread and round; fsweep_fma_probe_flops gives the
  * flop count of one launch, the caller times it with CUDA events.  out: device float[1] (never written in practice). */
