@@ -106,9 +106,22 @@ def test_c128_vs_oracle_and_golden(name):
 FDN_CASES = ["cfg2_fdn8_full", "fdn6_example", "fdn8_batch3", "fdn16", "fdn32", "fdn8_fracdelay", "recursion_filters"]
 
 
-@pytest.mark.parametrize("name", FDN_CASES)
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("path", ["generic", "loop", "tpb", "tpc"])
+def _family_combos():
+    """(case, dtype, kernel family) combinations that exist: the thread-per-bin families are float32, width <= 8, and
+    the compact one needs the N x 1 / 1 x N gains around the loop."""
+    out = []
+    for name in FDN_CASES:
+        for dtype in (torch.float32, torch.float64):
+            for path in ("generic", "loop", "tpb", "tpc"):
+                if path in ("tpb", "tpc") and (dtype != torch.float32 or name in ("fdn16", "fdn32")):
+                    continue
+                if path == "tpc" and name == "recursion_filters":
+                    continue
+                out.append(pytest.param(name, dtype, path, id=f"{path}-{str(dtype).split('.')[-1]}-{name}"))
+    return out
+
+
+@pytest.mark.parametrize("name,dtype,path", _family_combos())
 def test_alternative_kernel_paths_on_fdn_cases(name, dtype, path, monkeypatch):
     """FDN-shaped programs can run on four kernel families: the generic step-table interpreter
     (fsweep_kernels.cuh), the row-distributed loop kernels (fsweep_loop.cuh) and, for widths <= 8 in float32 and
@@ -116,10 +129,6 @@ def test_alternative_kernel_paths_on_fdn_cases(name, dtype, path, monkeypatch):
     family is forced here in turn; all must agree with the oracle."""
     monkeypatch.setenv("FLAMO_B200_PRECISION", "float32")  # the float32 kernels themselves, width 16 / 32 included
     if path in ("tpb", "tpc"):
-        if dtype != torch.float32 or name in ("fdn16", "fdn32"):
-            pytest.skip("thread-per-bin kernels: float32, width <= 8")
-        if path == "tpc" and name == "recursion_filters":
-            pytest.skip("compact thread-per-bin kernels: N x 1 and 1 x N gains around the loop only")
         monkeypatch.setenv("FSWEEP_FORCE_TPB" if path == "tpb" else "FSWEEP_FORCE_TPC", "1")
     else:
         monkeypatch.setenv("FSWEEP_DISABLE_TPB", "1")
