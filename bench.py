@@ -365,6 +365,63 @@ def all_configs(device, flush, steps, peaks, fma_tflops, rank):
     return out
 
 
+def table_sweep_record(device, flush, peaks, reps=30):
+    """The HBM-bound case (the shape of the real examples/e8_active_acoustics.py path): a Series of
+    generic FIR filters whose per-bin response tables are streamed from HBM — Filter(100 x 13 x 4) -> parallelFilter(72000
+    x 13) -> parallelGain(13) -> Filter(15000 x 4 x 13), nfft = 96000, 4 columns.  Forward and backward sweep launches
+    alone (the cuFFT that builds the tables excluded), median of CUDA-event times behind an L2 flush, against the
+    measured copy bandwidth.  Algorithmic bytes: tables + x + y forward; tables read + table gradients written + x +
+    dL/dy backward."""
+    from flamo_b200 import sweep
+    from flamo_b200._lib import EPI_NONE
+    from flamo_b200.processor import dsp, system
+
+    nfft, alias, n_M, n_L = 96000, 30.0, 4, 13
+    M = nfft // 2 + 1
+    torch.manual_seed(0)
+    kw = dict(nfft=nfft, alias_decay_db=alias, device=device, requires_grad=True)
+    core = system.Series(dsp.Filter(size=(100, n_L, n_M), **kw), dsp.parallelFilter(size=(72000, n_L), **kw),
+                         dsp.parallelGain(size=(n_L,), **kw), dsp.Filter(size=(15000, n_M, n_L), **kw))
+    X = torch.eye(n_M, dtype=torch.complex64, device=device).expand(1, M, n_M, n_M).contiguous()
+    with torch.enable_grad():
+        prog = sweep.Program(nfft, alias, X.dtype, X.device)
+        core._lower(prog, None)
+        (tag, payload), = list(prog._segments())
+        ops, coefs, n_out = prog.flatten_segment(payload, X.dtype)
+    coefs = [c.detach().contiguous() for c in coefs]
+    plan = prog.plan_for(ops)
+    y = torch.empty((1, M, n_out, n_M), dtype=torch.complex64, device=device)
+    gy = torch.ones_like(y)
+    grads = [torch.empty_like(c) for c in coefs]
+    be = sweep._BACKEND
+
+    def timed(fn):
+        ts = []
+        for i in range(reps + 5):
+            flush.fill_(i & 0xFF)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            if i >= 5:
+                ts.append(s.elapsed_time(e) * 1e-3)
+        return statistics.median(ts)
+
+    t_f = timed(lambda: be.forward(plan, ops, coefs, X, y, n_M, 0, EPI_NONE))
+    t_b = timed(lambda: be.backward(plan, ops, coefs, X, gy, grads, None, n_M, 0, EPI_NONE))
+    tab = sum(c.numel() * c.element_size() for c in coefs if c.is_complex())
+    io = X.numel() * 8 + y.numel() * 8
+    peak = peaks.get("hbm_gbs", 6650.0)
+    rec = {"workload": "FIR Series 13x4 -> 13 -> 13 -> 4x13 (generic Filter tables streamed from HBM), nfft=96000, 4 columns",
+           "kernel": plan.kernel_family(M, True), "table_bytes": tab}
+    for name, t, byts in (("forward", t_f, tab + io), ("backward", t_b, 2 * tab + io)):
+        rec[name] = {"us_per_launch": t * 1e6, "algorithmic_bytes": byts,
+                     "roofline": {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": byts / t / 1e9 / peak}}
+    return rec
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def gpu_arm(args):
     rank, world, local = dist_env()
@@ -476,6 +533,10 @@ def gpu_arm(args):
     extra = {}
     if world == 1 and rank == 0 and not args.no_configs:
         extra["configs"] = all_configs(device, flush, args.config_steps, peaks, fma_tflops, rank)
+        try:
+            extra["table_sweep"] = table_sweep_record(device, flush, peaks)
+        except Exception as ex:
+            extra["table_sweep"] = {"error": f"{type(ex).__name__}: {ex}"}
     if world > 1 and not args.no_configs:
         # BASELINE.json configs[4] as north_star describes it: bin ranges sharded over the GPUs of the node, one
         # all-reduce of the gradients per step (strong scaling: the total work is fixed)
