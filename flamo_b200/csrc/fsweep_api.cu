@@ -78,6 +78,7 @@ struct fsweep_plan {
   size_t stream_bps_smem[2] = {0, 0};  // ... for this dynamic shared memory size
   bool stream = false;  // TABLE-heavy program without recursion: streaming kernels, fsweep_stream.cuh
   StreamInfo sinfo;     // everything but tb / qc / threads (chosen per call from batch*cols)
+  bool grad32 = false;  // FSWEEP_DT_GRAD32: float64 plan of a float32 model, deferred cascade gradients in float32 arithmetic
   bool cta = false;  // wide flagship shape (32 < N <= 64, float32): CTA-per-bin kernels, fsweep_cta.cuh
   bool cta_tc = false;  // ... with the tensor-core elimination (fsweep_tc.cuh) instead of the SIMT one
   int cta_blocks_per_sm[2] = {0, 0};
@@ -96,6 +97,8 @@ extern "C" int fsweep_last_launch_count(void) { return g_launches; }
 extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nfft, double alias_decay_db, int dtype,
                                   fsweep_plan_t** out) {
   if (!ops || !out || n_ops <= 0) return fail(FSWEEP_E_BADARG, "null or empty program");
+  const bool grad32 = (dtype & FSWEEP_DT_GRAD32) != 0;
+  dtype &= ~FSWEEP_DT_GRAD32;
   if (dtype != FSWEEP_C64 && dtype != FSWEEP_C128) return fail(FSWEEP_E_BADARG, "bad dtype %d", dtype);
   if (nfft < 2) return fail(FSWEEP_E_BADARG, "bad nfft %lld", (long long)nfft);
 
@@ -170,6 +173,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   fsweep_plan* p = new (std::nothrow) fsweep_plan();
   if (!p) return fail(FSWEEP_E_BADARG, "out of host memory");
   p->dtype = dtype;
+  p->grad32 = grad32 && dtype == FSWEEP_C128;
   int G = 1;
   while (G < width) G <<= 1;
   p->G = G;
@@ -975,6 +979,8 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
       const int chunks = D.chunks_plus + (int)((n_bins - n_plus + ch - 1) / ch);
       if (dtype == FSWEEP_C64)
         fsweep_sos_defer_kernel<float><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(Pdef, D);
+      else if (plan->grad32)
+        fsweep_sos_defer_kernel<double, float><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(Pdef, D);
       else
         fsweep_sos_defer_kernel<double><<<dim3((unsigned)pairs, (unsigned)chunks), DEF_BLOCK, 0, st>>>(Pdef, D);
       if ((e = cudaGetLastError()) != cudaSuccess) return fail(FSWEEP_E_CUDA, "deferred gradient launch: %s", cudaGetErrorString(e));

@@ -372,6 +372,15 @@ __device__ __forceinline__ void load8<double>(const double* p, double (&c)[8]) {
   }
 }
 
+// eight coefficients stored as TS, used as T (mixed precision: float64 coefficients, float32 gradient arithmetic)
+template <typename T, typename TS>
+__device__ __forceinline__ void load8_as(const TS* p, T (&c)[8]) {
+  TS t[8];
+  load8<TS>(p, t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i] = (T)t[i];
+}
+
 // one packed section block {B(w0), B'(w0), b2, -, A(w0), A'(w0), a2, -} -> B(w), A(w) with
 // B(w) = B(w0) + B'(w0) v + b2 v^2, v = w - w0, w0 = +1 | -1: no cancellation between large terms
 template <typename T>
@@ -398,6 +407,27 @@ __device__ __forceinline__ cx<T> sos_eval(const T* p, int K, long stride, const 
   }
   if (guarded) return mk<T>(eps_of<T>(), T(0));
   return H;
+}
+
+// float64 only, K <= 64: numerator and denominator products separately and ONE division (the range of float64 holds
+// 64 sections; float32 needs the product of ratios above).  Half the FP64 instructions of sos_eval: the response-table
+// kernel of a float32 model swept in float64 arithmetic (sweep._wants_f64) is FP64-pipe bound.
+__device__ __forceinline__ cx<double> sos_eval_numden(const double* p, int K, long stride, const Ctx<double>& ctx,
+                                                       bool& guarded) {
+  cx<double> num = mk<double>(1, 0), den = mk<double>(1, 0);
+  guarded = false;
+  p += ctx.plus ? 0 : 8;
+  for (int s = 0; s < K; ++s, p += stride) {
+    double c[8];
+    load8<double>(p, c);
+    cx<double> Bv, Av;
+    section_eval<double>(c, ctx, Bv, Av);
+    guarded |= czero(Av);
+    num = cmul(num, Bv);
+    den = cmul(den, Av);
+  }
+  if (guarded) return mk<double>(eps_of<double>(), 0.0);
+  return cmul(num, crcp_exact(den));
 }
 
 // cascade with section `skip` left out (rare path: a numerator section is exactly zero at this bin)
@@ -1409,15 +1439,24 @@ __global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_table_kernel(const __gri
     if (bl >= D.n_bins) break;
     const Ctx<T> ctx = make_ctx<T>(P, D.bin_begin + bl);
     bool guarded;
-    const cx<T> H = sos_eval<T>(coef, K, stride, ctx, guarded);
+    cx<T> H;
+    if constexpr (sizeof(T) == 8) {
+      H = K <= 64 ? sos_eval_numden(coef, K, stride, ctx, guarded) : sos_eval<T>(coef, K, stride, ctx, guarded);
+    } else {
+      H = sos_eval<T>(coef, K, stride, ctx, guarded);
+    }
     st_cx(tab + (size_t)ctx.k * row + pair, H);
   }
 }
 
-template <typename T>
+// T: type of the buffers (coefficients, response table, parked vectors, accumulators); TC: arithmetic type.  TC = float
+// with T = double serves float32 models swept in float64 arithmetic (plan flag FSWEEP_DT_GRAD32): their gradients are
+// held to 1e-3 and the float64 version of this kernel is FP64-pipe bound (4.3 ms of config 3's 6.8 ms step).
+template <typename T, typename TC = T>
 __global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_defer_kernel(const __grid_constant__ ProgK P, const DeferArgs D) {
   constexpr int CH = DEF_BLOCK * DEF_TILES;
-  __shared__ T sH[2][DEF_BLOCK], sG[2][DEF_BLOCK], sU1[2][DEF_BLOCK], sU2[2][DEF_BLOCK];
+  __shared__ TC sH[2][DEF_BLOCK], sG[2][DEF_BLOCK], sU1[2][DEF_BLOCK], sU2[2][DEF_BLOCK];
+  auto cvt = [](cx<T> v) { return mk<TC>((TC)v.x, (TC)v.y); };
   __shared__ int sState[DEF_BLOCK];
   const OpK& op = P.ops[D.opi];
   const bool par = op.kind == FSWEEP_OP_PSOS;
@@ -1438,33 +1477,35 @@ __global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_defer_kernel(const __gri
   const int TS = DEF_BLOCK / K;
   const int s = tid / TS, l = tid - s * TS;
   const bool worker = s < K;
-  T c[8];
+  TC c[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) c[i] = T(0);
-  if (worker) load8<T>(coef + (size_t)s * stride + (plus ? 0 : 8), c);
-  T a0 = T(0), a1 = T(0), a2 = T(0), a4 = T(0), a5 = T(0), a6 = T(0);
+  for (int i = 0; i < 8; ++i) c[i] = TC(0);
+  if (worker) load8_as<TC, T>(coef + (size_t)s * stride + (plus ? 0 : 8), c);
+  TC a0 = TC(0), a1 = TC(0), a2 = TC(0), a4 = TC(0), a5 = TC(0), a6 = TC(0);
 
   for (int tile = 0; tile < DEF_TILES; ++tile) {
     const long long bl = base + (long long)tile * DEF_BLOCK + tid;
     if (base + (long long)tile * DEF_BLOCK >= lim) break;  // uniform
     // ---- phase 1: this thread's bin
     int st = 0;
-    cx<T> H = mk<T>(0, 0), gh = mk<T>(0, 0), u1 = mk<T>(0, 0), u2 = mk<T>(0, 0);
+    cx<TC> H = mk<TC>(0, 0), gh = mk<TC>(0, 0), u1 = mk<TC>(0, 0), u2 = mk<TC>(0, 0);
     if (bl < lim) {
       const Ctx<T> ctx = make_ctx<T>(P, D.bin_begin + bl);
       bool guarded = false;
+      cx<T> Hs;
       if (op.gtab != nullptr) {
         // the response table built for the backward kernel; (eps, 0) may be the reference's zero guard: re-check
-        H = ld_cx(reinterpret_cast<const cx<T>*>(op.gtab) + (size_t)ctx.k * (par ? (size_t)op.n_out : (size_t)op.n_out * op.n_in) + pair);
-        if (H.x == eps_of<T>() && H.y == T(0)) H = sos_eval<T>(coef, K, stride, ctx, guarded);
+        Hs = ld_cx(reinterpret_cast<const cx<T>*>(op.gtab) + (size_t)ctx.k * (par ? (size_t)op.n_out : (size_t)op.n_out * op.n_in) + pair);
+        if (Hs.x == eps_of<T>() && Hs.y == T(0)) Hs = sos_eval<T>(coef, K, stride, ctx, guarded);
       } else {
-        H = sos_eval<T>(coef, K, stride, ctx, guarded);
+        Hs = sos_eval<T>(coef, K, stride, ctx, guarded);
       }
-      u1 = ctx.u1;
-      u2 = ctx.u2;
+      H = cvt(Hs);
+      u1 = cvt(ctx.u1);
+      u2 = cvt(ctx.u2);
       for (int q = 0; q < D.ncols_total; ++q) {
         const cx<T>* rec = defer + ((size_t)q * D.n_bins + bl) * P.def_stride + op.def_off;
-        cfmac(gh, ld_cx(rec + op.n_in + m), ld_cx(rec + n));  // g_out[m] conj(S_in[n])
+        cfmac(gh, cvt(ld_cx(rec + op.n_in + m)), cvt(ld_cx(rec + n)));  // g_out[m] conj(S_in[n])
       }
       st = guarded ? 0 : (ctx.plus == plus ? 1 : 2);
     }
@@ -1472,21 +1513,22 @@ __global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_defer_kernel(const __gri
       // the boundary bin (rounded cos(w) on the other side of the split): its own thread, straight atomics
       const Ctx<T> ctx = make_ctx<T>(P, D.bin_begin + bl);
       const T* p = coef + (ctx.plus ? 0 : 8);
+      const cx<T> Hs = mk<T>((T)H.x, (T)H.y), ghs = mk<T>((T)gh.x, (T)gh.y);
       for (int ss = 0; ss < K; ++ss) {
         T cc[8];
         load8<T>(p + (size_t)ss * stride, cc);
         cx<T> Bv, Av;
         section_eval<T>(cc, ctx, Bv, Av);
-        const cx<T> qb = czero(Bv) ? cmul(sos_eval_without<T>(coef, K, stride, ctx, ss), crcp_exact(Av)) : cmul(H, crcp_exact(Bv));
-        cx<T> qa = cmul(H, crcp_exact(Av));
-        const cx<T> rb = cmulc(gh, qb), ra = cmulc(gh, mk<T>(-qa.x, -qa.y));
+        const cx<T> qb = czero(Bv) ? cmul(sos_eval_without<T>(coef, K, stride, ctx, ss), crcp_exact(Av)) : cmul(Hs, crcp_exact(Bv));
+        cx<T> qa = cmul(Hs, crcp_exact(Av));
+        const cx<T> rb = cmulc(ghs, qb), ra = cmulc(ghs, mk<T>(-qa.x, -qa.y));
         T* g = gdst + (size_t)ss * sec_stride + (ctx.plus ? 0 : 8);
         atomicAdd(g + 0, rb.x);
-        atomicAdd(g + 1, rb.x * u1.x + rb.y * u1.y);
-        atomicAdd(g + 2, rb.x * u2.x + rb.y * u2.y);
+        atomicAdd(g + 1, rb.x * ctx.u1.x + rb.y * ctx.u1.y);
+        atomicAdd(g + 2, rb.x * ctx.u2.x + rb.y * ctx.u2.y);
         atomicAdd(g + 4, ra.x);
-        atomicAdd(g + 5, ra.x * u1.x + ra.y * u1.y);
-        atomicAdd(g + 6, ra.x * u2.x + ra.y * u2.y);
+        atomicAdd(g + 5, ra.x * ctx.u1.x + ra.y * ctx.u1.y);
+        atomicAdd(g + 6, ra.x * ctx.u2.x + ra.y * ctx.u2.y);
       }
       st = 0;
     }
@@ -1504,21 +1546,21 @@ __global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_defer_kernel(const __gri
     if (worker) {
       for (int b = l; b < DEF_BLOCK; b += TS) {
         if (sState[b] == 0) continue;
-        Ctx<T> cx_;
-        cx_.u1 = mk<T>(sU1[0][b], sU1[1][b]);
-        cx_.u2 = mk<T>(sU2[0][b], sU2[1][b]);
-        const cx<T> Hb = mk<T>(sH[0][b], sH[1][b]), gb = mk<T>(sG[0][b], sG[1][b]);
-        cx<T> Bv, Av;
-        section_eval<T>(c, cx_, Bv, Av);
-        cx<T> qb;
+        Ctx<TC> cx_;
+        cx_.u1 = mk<TC>(sU1[0][b], sU1[1][b]);
+        cx_.u2 = mk<TC>(sU2[0][b], sU2[1][b]);
+        const cx<TC> Hb = mk<TC>(sH[0][b], sH[1][b]), gb = mk<TC>(sG[0][b], sG[1][b]);
+        cx<TC> Bv, Av;
+        section_eval<TC>(c, cx_, Bv, Av);
+        cx<TC> qb;
         if (czero(Bv)) {  // rare: this numerator section vanishes at this bin (H itself is 0 there)
           const Ctx<T> full = make_ctx<T>(P, D.bin_begin + base + (long long)tile * DEF_BLOCK + b);
-          qb = cmul(sos_eval_without<T>(coef, K, stride, full, s), crcp_exact(Av));
+          qb = cmul(cvt(sos_eval_without<T>(coef, K, stride, full, s)), crcp_exact(Av));
         } else {
           qb = cmul(Hb, crcp(Bv));
         }
-        const cx<T> qa = cmul(Hb, crcp(Av));
-        const cx<T> rb = cmulc(gb, qb), ra = cmulc(gb, mk<T>(-qa.x, -qa.y));
+        const cx<TC> qa = cmul(Hb, crcp(Av));
+        const cx<TC> rb = cmulc(gb, qb), ra = cmulc(gb, mk<TC>(-qa.x, -qa.y));
         a0 += rb.x;
         a1 = fma(rb.x, cx_.u1.x, fma(rb.y, cx_.u1.y, a1));
         a2 = fma(rb.x, cx_.u2.x, fma(rb.y, cx_.u2.y, a2));
@@ -1531,12 +1573,12 @@ __global__ void __launch_bounds__(DEF_BLOCK) fsweep_sos_defer_kernel(const __gri
   }
   if (worker) {
     T* g = gdst + (size_t)s * sec_stride + (plus ? 0 : 8);
-    atomicAdd(g + 0, a0);
-    atomicAdd(g + 1, a1);
-    atomicAdd(g + 2, a2);
-    atomicAdd(g + 4, a4);
-    atomicAdd(g + 5, a5);
-    atomicAdd(g + 6, a6);
+    atomicAdd(g + 0, (T)a0);
+    atomicAdd(g + 1, (T)a1);
+    atomicAdd(g + 2, (T)a2);
+    atomicAdd(g + 4, (T)a4);
+    atomicAdd(g + 5, (T)a5);
+    atomicAdd(g + 6, (T)a6);
   }
 }
 

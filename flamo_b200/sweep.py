@@ -404,7 +404,8 @@ class Program:
             io_dtype = x4.dtype
             ex = torch.complex128 if (io_dtype == torch.complex128 or _wants_f64(ops)) else torch.complex64
             _, coefs, _ = self.flatten_segment(payload, ex)
-            plan = _get_plan(ops, self.nfft, self.alias_decay_db, _lib.C64 if ex == torch.complex64 else _lib.C128)
+            code = _lib.C64 if ex == torch.complex64 else (_lib.C128 | (_lib.DT_GRAD32 if ex != io_dtype else 0))
+            plan = _get_plan(ops, self.nfft, self.alias_decay_db, code)
             x4 = SweepFunction.apply(x4.to(ex), plan, ops, epi, bin_begin, n_out, *coefs)
             if ex != io_dtype:  # float32 signal, float64 arithmetic: hand back what a float32 model returns
                 x4 = x4.to(torch.float32 if epi == EPI_ABS else io_dtype)
@@ -451,7 +452,8 @@ class Program:
             scale = 1.0 / tgt.numel()  # mean over the shard, as the unfused path computes it
         if x4.shape[1] == 0 or x4.shape[2] != ops[0][2] or bin_begin + x4.shape[1] > self.nfft // 2 + 1:
             return None  # (the unfused path raises the proper error)
-        plan = _get_plan(ops, self.nfft, self.alias_decay_db, _lib.C64 if ex == torch.complex64 else _lib.C128)
+        code = _lib.C64 if ex == torch.complex64 else (_lib.C128 | (_lib.DT_GRAD32 if ex != x.dtype else 0))
+        plan = _get_plan(ops, self.nfft, self.alias_decay_db, code)
         if ex != x.dtype:  # float32 model, float64 arithmetic (_wants_f64)
             return SweepLossFunction.apply(x4.to(ex), tgt.to(torch.float64), plan, ops, kind, scale, bin_begin,
                                            *coefs).to(real)

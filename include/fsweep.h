@@ -73,6 +73,10 @@ extern "C" {
 /* dtypes */
 #define FSWEEP_C64 0
 #define FSWEEP_C128 1
+/* may be OR-ed into FSWEEP_C128 at plan creation: the caller's PARAMETERS are float32 (a float32 model swept in float64
+ * arithmetic because float32 arithmetic misses the 1e-4 bar), so coefficient gradients of deferred section cascades may
+ * be accumulated in float32 arithmetic (buffers stay float64) */
+#define FSWEEP_DT_GRAD32 256
 
 /* epilogues (output layer fused into the sweep) */
 #define FSWEEP_EPI_NONE 0 /* y = Y                      (cplx out)                           */

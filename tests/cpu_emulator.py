@@ -20,7 +20,7 @@ class _EmuPlan:
         # validate with the real library's host-side planner when it is built
         self.real = None
         try:
-            self.real = _lib.Plan([_lib.Op(*o) for o in ops], nfft, alias_decay_db, dtype)
+            self.real = _lib.Plan([_lib.Op(*o) for o in ops], nfft, alias_decay_db, dtype)  # (flags like DT_GRAD32 included)
         except _lib.Unsupported:
             pass  # e.g. loop width > 32: the emulator itself has no such limit
         except RuntimeError as e:
