@@ -1323,7 +1323,7 @@ __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_const
 // one partial row (row index fastest, which is how the rows are laid out), the block's warps split the per-block rows,
 // and the cross-warp sum runs in a fixed order through shared memory (deterministic).  The first version gives every
 // lane of a warp a different block's row: n_blocks scattered 4-byte loads per gradient element.
-constexpr int FIN2_WARPS = 16;
+constexpr int FIN2_WARPS = 32;  // 24 independent loads per lane for 751 partial rows: three batches of 8 in flight
 
 template <typename T>
 __device__ __forceinline__ void finalize_store(const FinalizeOp& op, int row, int i, double s) {
@@ -1375,7 +1375,7 @@ __global__ void __launch_bounds__(32 * FIN2_WARPS) fsweep_finalize_v2_kernel(con
     if (op.acc_mode == ACC_SMEM) {
       if (live) {
         const T* p = reinterpret_cast<const T*>(F.partial) + (size_t)(op.row_off + i) * F.G + row;
-#pragma unroll 4
+#pragma unroll 8
         for (int b = warp; b < F.n_blocks; b += FIN2_WARPS) s += (double)p[(size_t)b * stride];
       }
       red[warp][lane] = s;

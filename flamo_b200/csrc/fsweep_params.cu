@@ -172,12 +172,39 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const T* __restr
     X[e] = v;
   }
   __syncthreads();
+  // The Frechet derivative is LINEAR in G: normalise the G block to unit 1-norm and scale the result back, so that
+  // the number of squarings depends on ||S|| only (a large loss gradient used to add one 16 x 16 product per factor
+  // of two of its norm: this kernel was 12 us of a 101 us config-2 step).
+  __shared__ double s_gn;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    double cs = 0.0;
+    for (int r = 0; r < n; ++r) cs += fabs(X[r * m + n + c]);
+    red[c] = cs;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double g = 0.0;
+    for (int c = 0; c < n; ++c) g = fmax(g, red[c]);
+    s_gn = g;
+  }
+  __syncthreads();
+  const double gn = s_gn;
+  if (gn > 0.0 && isfinite(gn)) {
+    const double ign = 1.0 / gn;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      int r = e / n, c = e - r * n;
+      X[r * m + n + c] *= ign;
+    }
+  }
+  __syncthreads();
+  const double back = (gn > 0.0 && isfinite(gn)) ? gn : 1.0;
   double* R = expm_inplace(X, W, m, red);
   // dS = top-right block; skew map: gP[i][j] = dS[i][j] - dS[j][i] for i < j, else 0
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     int i = e / n, j = e - i * n;
     double d = R[i * m + n + j];
     if (skew) d = (i < j) ? d - R[j * m + n + i] : 0.0;
+    d *= back;
     gP[e] = (T)d;
   }
 }
