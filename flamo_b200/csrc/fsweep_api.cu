@@ -165,8 +165,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   }
   if (width > 64)
     return fail(FSWEEP_E_UNSUPPORTED, "channel width %d > 64: not supported by the register-resident sweep", width);
-  if (width > 32 && dtype != FSWEEP_C64)
-    return fail(FSWEEP_E_UNSUPPORTED, "channel width %d > 32 is float32-only (complex128 rows exceed the register file)", width);
+  const bool wide64 = width > 32 && dtype != FSWEEP_C64;  // float64 beyond 32 channels: the CTA-per-bin kernels only (below)
   const int n_leaf = (int)(pre.size() + ff.size() + fb.size() + post.size());
   if (n_leaf > MAX_OPS) return fail(FSWEEP_E_UNSUPPORTED, "program has %d ops (max %d): split the series", n_leaf, MAX_OPS);
 
@@ -230,7 +229,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   // ---- wide flagship shape -> CTA-per-bin kernels: [GAIN N x 1] RECURSION(diagonal, no gradients ; GAIN N x N) [GAIN 1 x N]
   {
     const char* no_cta = getenv("FSWEEP_DISABLE_CTA");
-    bool ok = !(no_cta && no_cta[0] == '1') && dtype == FSWEEP_C64 && width > 32 && width <= 64 && rec >= 0 &&
+    bool ok = (dtype == FSWEEP_C128 || !(no_cta && no_cta[0] == '1')) && width > 32 && width <= 64 && rec >= 0 &&
               pre.size() == 1 && post.size() == 1 && fb.size() == 1 && ops[fb[0]].kind == FSWEEP_OP_GAIN &&
               ops[pre[0]].kind == FSWEEP_OP_GAIN && ops[post[0]].kind == FSWEEP_OP_GAIN && ops[pre[0]].n_in == 1 &&
               ops[post[0]].n_out == 1 && ops[pre[0]].n_out == rec_n && ops[post[0]].n_in == rec_n && rec_in == rec_n &&
@@ -239,7 +238,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
     if (ok) {
       p->cta = true;
       const char* tc_env = getenv("FSWEEP_CTA_TC");
-      p->cta_tc = tc_env ? tc_env[0] == '1' : FSWEEP_CTA_TC_DEFAULT;
+      p->cta_tc = dtype == FSWEEP_C64 && (tc_env ? tc_env[0] == '1' : FSWEEP_CTA_TC_DEFAULT);
       memset(&p->loop, 0, sizeof(p->loop));
       p->loop.pre = slot_of[pre[0]];
       p->loop.ff_begin = slot_of[ff[0]];
@@ -247,6 +246,13 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
       p->loop.fb = slot_of[fb[0]];
       p->loop.post = slot_of[post[0]];
     }
+  }
+  if (wide64 && !p->cta) {
+    delete p;
+    return fail(FSWEEP_E_UNSUPPORTED,
+                "channel width %d > 32 in float64 is supported for the FDN shape only ([Gain N x 1] Recursion(diagonal "
+                "chain without gradients ; N x N matrix) [Gain 1 x N]): complex128 rows exceed the register file of the "
+                "row-distributed kernels", width);
   }
   // shared-memory accumulator budget: spill the largest rows to global atomics until it fits (the CTA kernels keep
   // every accumulator in registers: nothing to spill)
@@ -489,7 +495,7 @@ int cta_grid(fsweep_plan* p, bool bwd, int64_t n_bins, cudaError_t* err) {
   }
   if (p->cta_blocks_per_sm[bwd] == 0) {
     int n = 0;
-    if ((*err = occupancy_cta(bwd, p->cta_tc, &n)) != cudaSuccess) return 0;
+    if ((*err = occupancy_cta(p->dtype, bwd, p->cta_tc, &n)) != cudaSuccess) return 0;
     if (n < 1) {
       *err = cudaErrorLaunchOutOfResources;
       return 0;
@@ -742,7 +748,7 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
   bool stream_tma = false;
   if (plan->cta) {
     cfg.grid = cta_grid(plan, false, n_bins, &e);
-    if (e == cudaSuccess) e = launch_cta(false, plan->cta_tc, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
+    if (e == cudaSuccess) e = launch_cta(plan->dtype, false, plan->cta_tc, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
   } else if (!crit && ((stream_tma = plan->stream && stream_tma_ok(P, plan->sinfo, bin_begin, false) &&
                                      stream_setup(plan, batch * cols, false, true, &SI, &ssmem)) ||
                        stream_setup(plan, batch * cols, false, false, &SI, &ssmem))) {
@@ -923,7 +929,7 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   bool stream_tma = false;
   if (plan->cta) {
     cfg.grid = cta_grid(plan, true, n_bins, &e);
-    if (e == cudaSuccess) e = launch_cta(true, plan->cta_tc, cfg.grid, st, P, plan->loop, A, plan->G);
+    if (e == cudaSuccess) e = launch_cta(plan->dtype, true, plan->cta_tc, cfg.grid, st, P, plan->loop, A, plan->G);
   } else if (!crit && ((stream_tma = plan->stream && stream_tma_ok(P, plan->sinfo, bin_begin, true) &&
                                      stream_setup(plan, batch * cols, true, true, &SI, &ssmem)) ||
                        stream_setup(plan, batch * cols, true, false, &SI, &ssmem))) {

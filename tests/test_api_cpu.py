@@ -44,7 +44,7 @@ def test_plan_validation():
     with pytest.raises(_lib.Unsupported, match="width"):
         P([_op(_lib.OP_GAIN, 65, 65)])
     assert P([_op(_lib.OP_GAIN, 64, 64)]).n_coeffs == 1  # two warps per bin
-    with pytest.raises(_lib.Unsupported, match="float32-only"):
+    with pytest.raises(_lib.Unsupported, match="FDN shape only"):
         _lib.Plan([_lib.Op(*_op(_lib.OP_GAIN, 64, 64))], 1024, 30.0, _lib.C128)
     with pytest.raises(_lib.Unsupported, match="more than one"):
         P([_op(_lib.OP_RECURSION, 2, 2, n_ff=1, n_fb=1), _op(_lib.OP_PGAIN, 2, 2), _op(_lib.OP_PGAIN, 2, 2),

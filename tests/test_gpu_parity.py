@@ -16,7 +16,6 @@ from oracle import flamo_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-WIDE = {"cfg5_fdn64_small"}  # loop width 64 > 32: two warps per bin, float32 kernels only
 
 
 def oracle_on(case, params64, X64):
@@ -90,8 +89,6 @@ def test_pure_float32_arithmetic_on_promoted_shapes(name, monkeypatch):
 
 @pytest.mark.parametrize("name", [n for n in C.CASES])
 def test_c128_vs_oracle_and_golden(name):
-    if name in WIDE:
-        pytest.xfail("loop width > 32 is float32-only: a row of 64 complex128 exceeds the register file")
     case, g, Y, ferr, gerrs, missing = run_case(name, torch.float64)
     tol = 1e-6 if case["alias"] == 0.0 else 1e-9
     assert not missing
@@ -186,6 +183,34 @@ def test_deferred_sos_gradients_match_in_kernel_atomics(name, dtype, monkeypatch
         a, b = grads(False, shard, B), grads(True, shard, B)
         for u, v in zip(a, b):
             assert grad_err(u, v) <= tol, (shard, B)
+
+
+@pytest.mark.parametrize("N,B", [(40, 1), (64, 3), (48, 35)])
+def test_wide_fdn_in_float64(N, B):
+    """float64 models with a 33..64-wide FDN loop (the reference's examples default to float64) run on the float64
+    instantiation of the CTA-per-bin kernels: response and gradients against the oracle at float64 resolution."""
+    from flamo_b200 import workloads as W
+    from flamo_b200.processor import dsp, system
+
+    nfft, alias = 1024, 30.0
+    M = nfft // 2 + 1
+    desc = W.fdn(N, delays=[601 + 37 * i for i in range(N)])
+    torch.manual_seed(11)
+    model = W.build(desc, dsp, system, nfft, alias, dtype=torch.float64, device="cuda")
+    X = C.make_input(B, M, 1, None).cuda().requires_grad_(True)
+    Y = model(X)
+    ps = [p for p in model.parameters() if p.requires_grad]
+    gs = torch.autograd.grad(C.golden_loss(Y), ps + [X])
+    fam = next(iter(pl.kernel_family(M, True) for pl in sweep._PLANS.values() if pl.dtype == 1 and "cta" in pl.kernel_family(M, True)), None)
+    assert fam is not None and "tcgen05" not in fam
+    params64 = [p.detach().cpu().double().requires_grad_(p.requires_grad) for p in model.parameters()]
+    Xo = C.make_input(B, M, 1, None).requires_grad_(True)
+    Yo = O.forward(O.from_desc(desc), Xo, params64, nfft, alias)
+    go = torch.autograd.grad(C.golden_loss(Yo), [p for p in params64 if p.requires_grad] + [Xo])
+    assert rel_err(Y.detach().cpu().numpy(), Yo.detach().numpy()) <= 1e-9
+    for u, v in zip(gs, go):
+        assert grad_err(u.detach().cpu().numpy().view(np.float64) if u.is_complex() else u.cpu().numpy(),
+                        v.detach().numpy().view(np.float64) if v.is_complex() else v.numpy()) <= 1e-6
 
 
 @pytest.mark.parametrize("tc", [False, True], ids=["simt", "tcgen05"])

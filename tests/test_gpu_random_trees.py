@@ -34,11 +34,9 @@ def _grads(name, dtype, variant):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("name", list(C.CASES))
 def test_finalize_v2_equals_default(name, dtype):
-    if dtype == torch.float64 and name == "cfg5_fdn64_small":
-        pytest.skip("no float64 kernels at loop width 64")
     a = _grads(name, dtype, "0")
     if a is None:
-        pytest.skip("no trainable parameter")
+        return  # (cases without a trainable parameter have no gradient to finalize)
     b = _grads(name, dtype, "1")
     # both kernels sum the per-block partials in float64; programs whose accumulators overflow shared memory add
     # float atomics in a flat buffer whose order differs from run to run (cfg4: 1.4e-6 between two runs of the SAME
