@@ -166,6 +166,8 @@ class Series(nn.Sequential):
             ext = ext_param[key] if (ext_param is not None and key in ext_param) else None
             if hasattr(module, "_lower"):
                 module._lower(prog, ext)
+            elif prog._chain is not None and isinstance(module, Parallel):
+                prog.table_of(module, ext)  # a Parallel inside a Recursion path: its response as a streamed table
             elif ext is not None:
                 prog.eager(lambda t, m=module, e=ext: m(t, e))
             else:
@@ -270,11 +272,21 @@ class Recursion(nn.Module):
                     ext_fb = p
                 elif "feedforward" in key:
                     ext_ff = p
-        for path in (self.feedforward, self.feedback):
-            if not hasattr(path, "_lower"):
+        if prog._chain is not None:
+            # a loop nested inside another loop's path: its closed-loop response enters the outer program as a table
+            prog.table_of(self, ext_param)
+            return
+
+        def lower(path, ext):
+            if hasattr(path, "_lower"):
+                path._lower(prog, ext)
+            elif isinstance(path, Parallel):
+                prog.table_of(path, ext)
+            else:
                 raise sweep._lib.Unsupported(sweep._lib.E_UNSUPPORTED,
                                              f"{path.__class__.__name__} cannot be lowered inside a Recursion")
-        prog.recursion(lambda: self.feedforward._lower(prog, ext_ff), lambda: self.feedback._lower(prog, ext_fb))
+
+        prog.recursion(lambda: lower(self.feedforward, ext_ff), lambda: lower(self.feedback, ext_fb))
 
     def forward(self, X, ext_param=None):
         _entry_check(self, X)

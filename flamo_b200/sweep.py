@@ -290,6 +290,25 @@ class Program:
         """The list new leaves are appended to (the open recursion chain, or the top level)."""
         return self._chain if self._chain is not None else self.items
 
+    def table_of(self, module, ext_param=None):
+        """Fallback for a bin-wise LINEAR sub-system the flat program cannot express where it stands — a Recursion or a
+        Parallel inside a Recursion path (the reference nests them freely, system.py:397-425 applies the feedback path to
+        an identity signal and never looks inside).  Its response is measured the way the reference does it: the module
+        is run on the identity signal (its own sweep launch: (1, M, n_in, n_in) in, (1, M, n_out, n_in) out) and enters
+        this program as a streamed per-bin TABLE, gradients flowing back through that launch.  Costs one launch and
+        8 M n_out n_in bytes of HBM per nested system; tables are indexed by absolute bin, so it is evaluated on all
+        bins even inside a bin shard."""
+        n_in, n_out = int(module.input_channels), int(module.output_channels)
+        M = self.nfft // 2 + 1
+        eye = torch.eye(n_in, dtype=self.cdtype, device=self.device).expand(1, M, n_in, n_in)
+        prev = getattr(_tls, "shard", None)
+        _tls.shard = None
+        try:
+            H = module(eye, ext_param) if ext_param is not None else module(eye)
+        finally:
+            _tls.shard = prev
+        self.leaf(OP_TABLE, n_out, n_in, H[0])
+
     def eager(self, fn):
         """A module the sweep cannot express: run it in PyTorch between two launches."""
         if self._chain is not None:
@@ -297,7 +316,7 @@ class Program:
         self.items.append(("eager", fn))
 
     def recursion(self, lower_ff, lower_fb):
-        if self._chain is not None:
+        if self._chain is not None:  # (system.Recursion._lower routes a nested loop through table_of)
             raise _lib.Unsupported(_lib.E_UNSUPPORTED, "nested Recursion")
         self._chain = ff = []
         lower_ff()

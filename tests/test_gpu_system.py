@@ -261,3 +261,33 @@ def test_full_size_vs_oracle_bin_subset(name, n_sub):
     print(f"[full-size parity] {name}: |Y| floored rel err {ferr:.3e}, grad err {gerr:.3e}, bins {len(idx)}")
     assert ferr <= 1e-4, f"{name}: magnitude rel err {ferr:.3e}"
     assert gerr <= 1e-3, f"{name}: gradient rel err {gerr:.3e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("name", ["loop_in_feedforward", "loop_as_feedback", "parallel_in_feedback",
+                                  "parallel_cat_as_feedforward"])
+def test_nested_recursion_and_parallel_inside_a_loop(name, dtype):
+    """A Recursion or a Parallel INSIDE a Recursion path (round 1 raised): the nested system's response enters the outer
+    program as a streamed table (sweep.Program.table_of); response and gradients against the oracle on the kernels."""
+    from nested_cases import NESTED
+
+    desc = NESTED[name]
+    nfft, alias = 512, 20.0
+    M = nfft // 2 + 1
+    torch.manual_seed(3)
+    model = W.build(desc, dsp, system, nfft, alias, dtype=dtype, device=DEV)
+    cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
+    X = C.make_input(2, M, model.input_channels, None).to(cdt).to(DEV)
+    Y = model(X)
+    C.golden_loss(Y).backward()
+    ps = [p.detach().cpu().double().requires_grad_(p.requires_grad) for p in model.parameters()]
+    Yo = O.forward(O.from_desc(desc), X.cpu().to(torch.complex128), ps, nfft, alias)
+    go = torch.autograd.grad(C.golden_loss(Yo), [p for p in ps if p.requires_grad])
+    ftol, gtol = (1e-4, 1e-3) if dtype == torch.float32 else (1e-9, 1e-6)
+    assert rel_err(np.abs(Y.detach().cpu().numpy()), np.abs(Yo.detach().numpy())) <= ftol
+    k = 0
+    for p in model.parameters():
+        if p.requires_grad:
+            assert p.grad is not None
+            assert float((p.grad.cpu().double() - go[k]).abs().max()) <= gtol * float(go[k].abs().max() + 1e-30)
+            k += 1
