@@ -650,3 +650,122 @@ extern "C" FSWEEP_API int fsweep_fma_probe(void* out, int blocks, int iters, voi
   fma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float*>(out), iters, 0.999f, 1e-4f);
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
+
+// ---------------------------------------------------------------------------------------------- Biquad designer
+// dsp.Biquad / parallelBiquad with a low-pass or high-pass prototype (reference dsp.py:1494-1563 -> functional.py
+// lowpass_filter / highpass_filter, :376-470): raw parameter (K, 2, ...) -> bounded map (clamp cut-off to [0, 1],
+// 20 log10|gain| to [-60, 60] dB) -> RBJ taps (Q = 1/sqrt 2) -> the packed Taylor blocks of FSWEEP_OP_SOS, as ONE
+// launch (and one for the adjoint) instead of ~60 parameter-sized PyTorch launches: config 1's captured step was
+// nothing but those.  float64 arithmetic; the parameter is read / its gradient written in its own dtype.
+namespace {
+struct BqTaps {
+  double b[3], a[3];
+  double db0[3], da0[3];  // d taps / d x0 (raw cut-off)
+  double db1[3];          // d b / d x1 (raw gain); a does not depend on it
+};
+
+__device__ __forceinline__ BqTaps biquad_taps(double x0, double x1, int highpass) {
+  BqTaps t;
+  const bool in0 = x0 >= 0.0 && x0 <= 1.0;
+  const double v0 = fmin(fmax(x0, 0.0), 1.0);
+  const double gdb_raw = 20.0 * log10(fabs(x1));
+  const bool in1 = gdb_raw >= -60.0 && gdb_raw <= 60.0;
+  const double gdb = fmin(fmax(gdb_raw, -60.0), 60.0);
+  const double PI = 3.14159265358979323846;
+  double sw, cw;
+  sincos(PI * v0, &sw, &cw);
+  const double alpha = sw * 0.70710678118654752440;
+  const double g = pow(10.0, gdb / 20.0);
+  const double sgn = highpass ? 1.0 : -1.0;      // h = (1 + sgn c) / 2
+  const double h = 0.5 * (1.0 + sgn * cw);
+  t.b[0] = g * h;
+  t.b[1] = g * (highpass ? -(1.0 + cw) : (1.0 - cw));
+  t.b[2] = g * h;
+  t.a[0] = 1.0 + alpha;
+  t.a[1] = -2.0 * cw;
+  t.a[2] = 1.0 - alpha;
+  // derivatives (torch.clamp passes the gradient on the closed interval)
+  const double dw = in0 ? PI : 0.0;
+  const double dc = -sw * dw, dal = cw * 0.70710678118654752440 * dw;
+  const double dh = 0.5 * sgn * dc;
+  t.db0[0] = g * dh;
+  t.db0[1] = g * (highpass ? -dc : -dc);
+  t.db0[2] = g * dh;
+  t.da0[0] = dal;
+  t.da0[1] = -2.0 * dc;
+  t.da0[2] = -dal;
+  // d g / d x1 = g ln10/20 * 20 / (ln10 x1) = g / x1 inside the clamp
+  const double dg = (in1 && x1 != 0.0) ? g / x1 : 0.0;
+  t.db1[0] = dg * h;
+  t.db1[1] = dg * (highpass ? -(1.0 + cw) : (1.0 - cw));
+  t.db1[2] = dg * h;
+  return t;
+}
+
+// section e = (k, n_out index m, n_in index n) of a (K, 2, n_out, n_in) parameter (parallel: (K, 2, n), m = n)
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(128) biquad_design_kernel(const T* __restrict__ param, double* __restrict__ packed,
+                                                            const double* __restrict__ gpacked, T* __restrict__ gparam,
+                                                            int K, int n_out, int n_in, int parallel, int highpass) {
+  const int per = parallel ? n_in : n_out * n_in;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= K * per) return;
+  const int k = e / per, r = e - k * per;
+  const int m = parallel ? r : r / n_in, n = parallel ? r : r - m * n_in;
+  const double x0 = (double)param[((size_t)k * 2 + 0) * per + r], x1 = (double)param[((size_t)k * 2 + 1) * per + r];
+  const BqTaps t = biquad_taps(x0, x1, highpass);
+  // packed layout [K][n_in][n_out][2][8] (parallel: [K][n][2][8])
+  const size_t o = parallel ? ((size_t)k * n_in + n) * 16 : (((size_t)k * n_in + n) * n_out + m) * 16;
+  if constexpr (!BWD) {
+    double* q = packed + o;
+    q[0] = t.b[0] + t.b[1] + t.b[2];
+    q[1] = t.b[1] + 2.0 * t.b[2];
+    q[2] = t.b[2];
+    q[3] = 0.0;
+    q[4] = t.a[0] + t.a[1] + t.a[2];
+    q[5] = t.a[1] + 2.0 * t.a[2];
+    q[6] = t.a[2];
+    q[7] = 0.0;
+    q[8] = t.b[0] - t.b[1] + t.b[2];
+    q[9] = t.b[1] - 2.0 * t.b[2];
+    q[10] = t.b[2];
+    q[11] = 0.0;
+    q[12] = t.a[0] - t.a[1] + t.a[2];
+    q[13] = t.a[1] - 2.0 * t.a[2];
+    q[14] = t.a[2];
+    q[15] = 0.0;
+  } else {
+    const double* g = gpacked + o;
+    // adjoint of the packing: gradient w.r.t. the taps
+    const double gb0 = g[0] + g[8], gb1 = g[0] + g[1] - g[8] + g[9], gb2 = g[0] + 2.0 * g[1] + g[2] + g[8] - 2.0 * g[9] + g[10];
+    const double ga0 = g[4] + g[12], ga1 = g[4] + g[5] - g[12] + g[13], ga2 = g[4] + 2.0 * g[5] + g[6] + g[12] - 2.0 * g[13] + g[14];
+    const double d0 = gb0 * t.db0[0] + gb1 * t.db0[1] + gb2 * t.db0[2] + ga0 * t.da0[0] + ga1 * t.da0[1] + ga2 * t.da0[2];
+    const double d1 = gb0 * t.db1[0] + gb1 * t.db1[1] + gb2 * t.db1[2];
+    gparam[((size_t)k * 2 + 0) * per + r] = (T)d0;
+    gparam[((size_t)k * 2 + 1) * per + r] = (T)d1;
+  }
+}
+}  // namespace
+
+extern "C" FSWEEP_API int fsweep_biquad_design(const void* param, int K, int n_out, int n_in, int parallel, int highpass,
+                                               int dtype, void* packed, const void* gpacked, void* gparam, void* stream) {
+  if (!param || K < 1 || n_out < 1 || n_in < 1 || (!packed && !(gpacked && gparam))) return FSWEEP_E_BADARG;
+  const int total = K * (parallel ? n_in : n_out * n_in);
+  const int grid = (total + 127) / 128;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool bwd = packed == nullptr;
+  if (dtype == FSWEEP_C64) {
+    if (bwd)
+      biquad_design_kernel<float, true><<<grid, 128, 0, st>>>((const float*)param, nullptr, (const double*)gpacked, (float*)gparam, K, n_out, n_in, parallel, highpass);
+    else
+      biquad_design_kernel<float, false><<<grid, 128, 0, st>>>((const float*)param, (double*)packed, nullptr, nullptr, K, n_out, n_in, parallel, highpass);
+  } else if (dtype == FSWEEP_C128) {
+    if (bwd)
+      biquad_design_kernel<double, true><<<grid, 128, 0, st>>>((const double*)param, nullptr, (const double*)gpacked, (double*)gparam, K, n_out, n_in, parallel, highpass);
+    else
+      biquad_design_kernel<double, false><<<grid, 128, 0, st>>>((const double*)param, (double*)packed, nullptr, nullptr, K, n_out, n_in, parallel, highpass);
+  } else {
+    return FSWEEP_E_BADARG;
+  }
+  return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}

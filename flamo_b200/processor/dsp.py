@@ -15,6 +15,7 @@ callers that want the response tensor itself (plots, probes, subclasses); they a
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -487,6 +488,11 @@ class _SectionFilter(Filter):
         H = torch.where(torch.abs(den) != 0, num / den, torch.finfo(num.dtype).eps * torch.ones_like(num))
         return H, B, A
 
+    def _fused_design(self, param):
+        """Packed section coefficients straight from the raw parameter in one library launch, where one exists for this
+        module (Biquad low-/high-pass with its stock map); None otherwise."""
+        return None
+
     def _overridden(self):
         return (self.freq_response is not self._stock_freq_response
                 or type(self).get_poly_coeff is not _SectionFilter.get_poly_coeff)
@@ -495,10 +501,12 @@ class _SectionFilter(Filter):
         if self._overridden():  # user / subclass supplies its own response: stream it as a table
             self._emit_table(prog, param, upcast=False)
             return
-        b, a = self._taps(self.map(self._up(param)))
-        coef = sweep.pack_sections(b, a, self._parallel, None)
+        coef = self._fused_design(param)
+        if coef is None:
+            b, a = self._taps(self.map(self._up(param)))
+            coef = sweep.pack_sections(b, a, self._parallel, None)
         prog.leaf(OP_PSOS if self._parallel else OP_SOS, self.output_channels, self.input_channels, coef,
-                  K=b.shape[1])
+                  K=coef.shape[0])
 
     def probe(self, z):
         b, a = self._taps(self.map(self.param))
@@ -555,6 +563,15 @@ class Biquad(_SectionFilter):
 
     def check_param_shape(self):
         assert len(self.size) == 4, "Parameter size must be 4D, for 3D (parallel) biquads use parallelBiquad module."
+
+    def _fused_design(self, param):
+        stock = (getattr(self.map, "__func__", None) is Biquad._bounded_map and type(self)._taps is Biquad._taps
+                 and self.filter_type in ("lowpass", "highpass"))
+        if not (stock and param.is_cuda and param.dtype in (torch.float32, torch.float64)
+                and sweep._BACKEND.name == "cuda" and os.environ.get("FLAMO_B200_FUSED_DESIGN", "1") == "1"):
+            return None
+        return sweep.BiquadDesign.apply(param, self.output_channels, self.input_channels, self._parallel,
+                                        self.filter_type == "highpass")
 
     def _taps(self, p):
         half_fs = self.fs / 2  # rad2hertz(param * pi)

@@ -528,6 +528,42 @@ class OrthogonalMap(torch.autograd.Function):
         return gP
 
 
+class BiquadDesign(torch.autograd.Function):
+    """Raw Biquad parameter -> packed section coefficients of the SOS op in ONE launch each way (libfsweep
+    fsweep_biquad_design: bounded map, RBJ low-/high-pass taps, Taylor packing, float64 inside) instead of the ~60
+    parameter-sized PyTorch launches of map -> designer -> pack_sections (reference dsp.py:1494-1563)."""
+
+    @staticmethod
+    def forward(ctx, param, n_out, n_in, parallel, highpass):
+        global launch_count
+        p = param.detach().contiguous()
+        K = p.shape[0]
+        shape = (K, n_in, 2, 8) if parallel else (K, n_in, n_out, 2, 8)
+        packed = torch.empty(shape, dtype=torch.float64, device=p.device)
+        with torch.cuda.device(p.device):
+            _lib.check(_lib.lib().fsweep_biquad_design(p.data_ptr(), K, n_out, n_in, int(parallel), int(highpass),
+                                                        _real_code(p.dtype), packed.data_ptr(), None, None,
+                                                        torch.cuda.current_stream(p.device).cuda_stream))
+        launch_count += 1
+        ctx.save_for_backward(p)
+        ctx.meta = (n_out, n_in, parallel, highpass)
+        return packed
+
+    @staticmethod
+    def backward(ctx, g):
+        global launch_count
+        (p,) = ctx.saved_tensors
+        n_out, n_in, parallel, highpass = ctx.meta
+        gc = g.to(torch.float64).contiguous()
+        gp = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            _lib.check(_lib.lib().fsweep_biquad_design(p.data_ptr(), p.shape[0], n_out, n_in, int(parallel), int(highpass),
+                                                        _real_code(p.dtype), None, gc.data_ptr(), gp.data_ptr(),
+                                                        torch.cuda.current_stream(p.device).cuda_stream))
+        launch_count += 1
+        return gp, None, None, None, None
+
+
 def _real_code(dtype: torch.dtype) -> int:
     return _lib.C64 if dtype == torch.float32 else _lib.C128
 

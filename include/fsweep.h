@@ -228,6 +228,14 @@ FSWEEP_API int fsweep_expm_forward_sp(const void* P, void* E, int n, int skew, i
 FSWEEP_API int fsweep_expm_backward_sp(const void* P, const void* G, void* gP, int n, int skew, int dtype, const void* E,
                                        const void* gsparsity, void* stream);
 
+/* dsp.Biquad / parallelBiquad, low-pass or high-pass prototype (reference dsp.py:1494-1563, functional.py:376-470): raw
+ * parameter (K, 2, n_out, n_in) [parallel: (K, 2, n), n_out = n_in = n] -> bounded map -> RBJ taps -> packed Taylor blocks
+ * of FSWEEP_OP_SOS (layout above), float64, in ONE launch.  Forward: packed != NULL (double[K][n_in][n_out][2][8]).
+ * Adjoint: packed == NULL, gpacked = dL/dpacked (double, same layout), gparam = dL/dparam (the parameter's dtype: float
+ * for FSWEEP_C64, double for FSWEEP_C128). */
+FSWEEP_API int fsweep_biquad_design(const void* param, int K, int n_out, int n_in, int parallel, int highpass, int dtype,
+                                    void* packed, const void* gpacked, void* gparam, void* stream);
+
 /* sparsity_loss of the mapped feedback matrix (reference optimize/loss.py:36-63), A: device real[n_mats][n][n]:
  *   loss = mean_i ((sum |A_i| - n sqrt n) / (n (1 - sqrt n)));  backward: gA = gloss * dloss/dA (gloss: device real[1]).
  * One launch each way, capture safe. */

@@ -103,3 +103,40 @@ def test_sparsity_rides_along_with_the_orthogonal_map(n, dtype):
         assert float((E.double() - Er).abs().max()) <= tol
         g, gr = P.grad.double(), Pr.grad.double()
         assert float((g - gr).abs().max()) <= 5 * tol * max(1.0, float(gr.abs().max()))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("parallel", [False, True])
+@pytest.mark.parametrize("ft", ["lowpass", "highpass"])
+def test_fused_biquad_designer_equals_the_pytorch_designer(ft, parallel, dtype, monkeypatch):
+    """fsweep_biquad_design (bounded map -> RBJ taps -> Taylor packing in one launch, and its adjoint) against the
+    PyTorch map / designer / pack_sections chain it replaces: packed coefficients and parameter gradients, including
+    parameters outside the clamps (cut-off > 1, gain beyond +-60 dB) where the gradient must vanish."""
+    from flamo_b200.processor import dsp
+
+    torch.manual_seed(5)
+    kw = dict(n_sections=3, filter_type=ft, nfft=256, fs=48000, requires_grad=True, alias_decay_db=10.0, device="cuda", dtype=dtype)
+    mod = dsp.parallelBiquad(size=(4,), **kw) if parallel else dsp.Biquad(size=(3, 2), **kw)
+    with torch.no_grad():
+        mod.param[0, 0].mul_(3.0)        # some cut-offs beyond the [0, 1] clamp
+        mod.param[1, 1].mul_(5000.0)     # some gains beyond +60 dB
+        mod.param[2, 1].mul_(1e-5)       # ... and below -60 dB
+    Wt = torch.randn((3, 4, 2, 8) if parallel else (3, 2, 3, 2, 8), device="cuda", dtype=torch.float64)
+
+    def run(fused):
+        monkeypatch.setenv("FLAMO_B200_FUSED_DESIGN", "1" if fused else "0")
+        mod.param.grad = None
+        coef = mod._fused_design(mod.param)
+        assert (coef is not None) == fused
+        if coef is None:
+            b, a = mod._taps(mod.map(mod._up(mod.param)))
+            coef = sweep.pack_sections(b, a, parallel, None)
+        (coef * Wt).sum().backward()
+        return coef.detach().clone(), mod.param.grad.detach().clone()
+
+    c1, g1 = run(True)
+    c0, g0 = run(False)
+    assert float((c1 - c0).abs().max()) <= 1e-12 * float(c0.abs().max())
+    tol = 1e-5 if dtype == torch.float32 else 1e-11
+    assert float((g1 - g0).abs().max()) <= tol * float(g0.abs().max())
+    assert float(g0.abs().max()) > 0
