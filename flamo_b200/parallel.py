@@ -33,6 +33,33 @@ def bin_range(M: int, rank: int, world: int):
     return b0, b0 + base + (1 if rank < rem else 0)
 
 
+class _AllGatherBins(torch.autograd.Function):
+    """(B, M_rank, ...) on every rank -> (B, M, ...) on every rank (bin ranges of `bin_range`, concatenated in rank
+    order).  Whatever consumes the gathered spectrum (a time-domain output layer and its criterion) is evaluated
+    identically on every rank; its gradient reaches the parameters through THIS rank's bins only, times `world`,
+    because the trainer weights such a replicated criterion by 1 / world before the gradients are summed over ranks."""
+
+    @staticmethod
+    def forward(ctx, x, M, rank, world, group):
+        sizes = [bin_range(M, r, world) for r in range(world)]
+        width = max(b - a for a, b in sizes)
+        pad = x.new_zeros((x.shape[0], width) + tuple(x.shape[2:]))
+        pad[:, :x.shape[1]] = x
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        if x.is_complex():  # (gloo has no complex all_gather)
+            real = [torch.view_as_real(p) for p in parts]
+            dist.all_gather(real, torch.view_as_real(pad).contiguous(), group=group)
+        else:
+            dist.all_gather(parts, pad.contiguous(), group=group)
+        ctx.range, ctx.world = sizes[rank], world
+        return torch.cat([p[:, :b - a] for p, (a, b) in zip(parts, sizes)], dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.range
+        return g[:, a:b] * ctx.world, None, None, None, None
+
+
 class DataParallelTrainer(Trainer):
     def __init__(self, net, *args, shard: str = "batch", process_group=None, **kwargs):
         super().__init__(net, *args, **kwargs)
@@ -106,10 +133,15 @@ class DataParallelTrainer(Trainer):
             return super()._loss_vector(inputs, targets)
         M = self.net.nfft // 2 + 1
         b0, b1 = bin_range(M, self.rank, self.world)
-        with sweep.bin_shard(b0, b1):
+        gather = lambda t: _AllGatherBins.apply(t, M, self.rank, self.world, self.pg)  # noqa: E731
+        with sweep.bin_shard(b0, b1, gather=gather):
             est, done = self._predict(inputs, targets)  # a fused criterion slices the target itself
-        tg = targets[:, b0:b1] if targets.shape[1] == M else targets
-        weight = [1.0 / self.world if self.requires_model[i] else (b1 - b0) / M for i in range(len(self.criterion))]
+        # a prediction that does not hold this rank's bins went through a layer that needs the whole spectrum (iFFT:
+        # all-gathered, then evaluated identically on every rank): its criteria are replicated, weight 1 / world
+        replicated = est is not None and est.shape[1] != b1 - b0
+        tg = targets[:, b0:b1] if (targets.shape[1] == M and not replicated) else targets
+        w_pred = 1.0 / self.world if replicated else (b1 - b0) / M
+        weight = [1.0 / self.world if self.requires_model[i] else w_pred for i in range(len(self.criterion))]
         return self._criteria(est, done, tg, weight=weight)
 
     def _sync(self, vals):

@@ -68,6 +68,7 @@ class iFFT(Transform):
         super().__init__(transform=self._transform, dtype=dtype)
 
     def _transform(self, x):
+        x = sweep.gather_bins(x, self.nfft)  # inside a multi-GPU bin shard: the whole spectrum first
         return torch.fft.irfft(x, n=self.nfft, dim=1, norm=self.norm)
 
 
@@ -99,6 +100,7 @@ class iFFTAntiAlias(Transform):
         super().__init__(transform=self._transform, device=device, dtype=dtype)
 
     def _transform(self, x):
+        x = sweep.gather_bins(x, self.nfft)  # inside a multi-GPU bin shard: the whole spectrum first
         return torch.fft.irfft(x, n=self.nfft, dim=1, norm=self.norm) * self.alias_envelope.view(1, -1, 1)
 
 

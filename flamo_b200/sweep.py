@@ -31,16 +31,37 @@ _tls = threading.local()
 
 
 class bin_shard:
-    def __init__(self, begin: int, end: int):
+    """`gather` (optional): callable that turns a tensor holding this rank's bins (B, end - begin, ...) into the full
+    (B, M, ...) tensor on every rank — handed in by the multi-GPU trainer; the layers that need ALL bins (iFFT,
+    iFFTAntiAlias: SURVEY.md §8e last row) call it through `gather_bins`."""
+
+    def __init__(self, begin: int, end: int, gather=None):
         self.range = (int(begin), int(end))
+        self.gather = gather
 
     def __enter__(self):
-        self.prev = getattr(_tls, "shard", None)
-        _tls.shard = self.range
+        self.prev = (getattr(_tls, "shard", None), getattr(_tls, "gather", None))
+        _tls.shard, _tls.gather = self.range, self.gather
         return self
 
     def __exit__(self, *a):
-        _tls.shard = self.prev
+        _tls.shard, _tls.gather = self.prev
+
+
+def gather_bins(x: torch.Tensor, nfft: int) -> torch.Tensor:
+    """Inside a bin shard, a bin-domain tensor that holds only this rank's bins becomes the full spectrum (all-gather
+    over the ranks of the shard); anywhere else the tensor is returned as it is.  A layer that needs every bin and finds
+    no way to get them raises instead of transforming a fragment of the spectrum."""
+    shard = current_shard()
+    M = nfft // 2 + 1
+    if shard is None or x.shape[1] == M or x.shape[1] != shard[1] - shard[0]:
+        return x
+    gather = getattr(_tls, "gather", None)
+    if gather is None:
+        raise RuntimeError(f"a layer that needs all {M} bins (iFFT / iFFTAntiAlias) was given the {x.shape[1]} bins of "
+                           f"the bin shard {shard}: run it under flamo_b200.parallel.DataParallelTrainer(shard='bins') "
+                           "(which all-gathers the spectrum) or outside sweep.bin_shard")
+    return gather(x)
 
 
 def current_shard() -> Optional[Tuple[int, int]]:

@@ -127,3 +127,69 @@ def test_bin_range_partition():
         assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
         sizes = [b - a for a, b in cuts]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _build_time_domain(batch):
+    """Shell whose OUTPUT LAYER is time-domain (iFFTAntiAlias): under bin sharding it needs the whole spectrum."""
+    from flamo_b200 import workloads as W
+    from flamo_b200.processor import dsp, system
+
+    torch.manual_seed(7)
+    core = W.build(W.fdn(N, delays=[101, 157, 211, 263]), dsp, system, NFFT, 30.0, dtype=torch.float64)
+    model = system.Shell(core, dsp.FFT(NFFT, dtype=torch.float64),
+                         dsp.iFFTAntiAlias(NFFT, alias_decay_db=30.0, dtype=torch.float64))
+    M = NFFT // 2 + 1
+    g = torch.Generator().manual_seed(3)
+    x = torch.zeros(batch, M, 1, dtype=torch.float64)
+    x[:, 0, :] = 1.0
+    y = 0.01 * torch.randn(batch, NFFT, 1, generator=g, dtype=torch.float64)  # a time-domain target
+    return model, x, y
+
+
+def _train_td(trainer_cls, model, x, y, **kw):
+    tr = trainer_cls(model, max_epochs=1, lr=1e-2, log=False, device="cpu", **kw)
+    tr.register_criterion(torch.nn.MSELoss(), 1)
+    losses = [tr.train_step((x, y)) for _ in range(STEPS)]
+    return losses, [p.detach().clone() for p in model.parameters()]
+
+
+def _worker_td(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_emulator
+    from flamo_b200.parallel import DataParallelTrainer
+
+    cpu_emulator.install()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        model, x, y = _build_time_domain(2)
+        losses, params = _train_td(DataParallelTrainer, model, x, y, shard="bins")
+        if rank == 0:
+            torch.save({"losses": losses, "params": params}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_domain_output_layer_under_bin_sharding(tmp_path, emulated_backend):
+    """SURVEY.md §8e last row: a time-domain output layer (iFFTAntiAlias) needs all bins — under bin sharding the
+    spectrum is all-gathered before the inverse FFT, the time-domain criterion is evaluated on every rank and its
+    gradient flows back through each rank's own bins: same trajectory as one process."""
+    from flamo_b200.optimize.trainer import Trainer
+
+    model, x, y = _build_time_domain(2)
+    ref_losses, ref_params = _train_td(Trainer, model, x, y)
+    out = str(tmp_path / "rank0.pt")
+    mp.spawn(_worker_td, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert np.allclose(got["losses"], ref_losses, rtol=1e-9), (got["losses"], ref_losses)
+    for a, b in zip(got["params"], ref_params):
+        assert torch.allclose(a, b, rtol=1e-8, atol=1e-10)
+
+
+def test_time_domain_layer_refuses_a_fragment_of_the_spectrum(emulated_backend):
+    from flamo_b200 import sweep
+
+    model, x, y = _build_time_domain(1)
+    with pytest.raises(RuntimeError, match="needs all"):
+        with sweep.bin_shard(10, 200):
+            model(x)
