@@ -20,6 +20,7 @@
 // factorisation is a runtime loop, the triangular solves are fully static (vector in registers, every matrix
 // element one LDS at a constant offset: independent loads that issue back to back).
 #pragma once
+#include "fsweep_tma.cuh"
 #include "fsweep_tpb.cuh"
 
 namespace fsweep {
@@ -151,20 +152,37 @@ __global__ void __launch_bounds__(TPC_BLOCK, 6) fsweep_tpc_kernel(const __grid_c
                                                                 const __grid_constant__ LoopInfo L, const SweepArgs A,
                                                                 int G) {
   extern __shared__ __align__(16) float2 tsm[];  // [NP*NP + NP][TPC_BLOCK]
-  __shared__ float wfb[NP * NP], wpre[NP], wpost[NP];
+  __shared__ __align__(16) float wfb[NP * NP];
+  __shared__ float wpre[NP], wpost[NP];
+  __shared__ __align__(8) uint64_t wbar;
   const int tid = threadIdx.x;
   const int N = P.rec_n;
   {
+    // the block's feedback matrix W_fb enters shared memory through the TMA bulk-copy engine when it is a full,
+    // 16-byte aligned NP x NP block (the headline config: 8 x 8 = 256 B; SASS UBLKCP + an mbarrier carrying the byte
+    // count): one elected thread issues the copy, the gains are fetched meanwhile.  Smaller matrices are padded into
+    // the NP x NP layout with plain loads.
     const OpK& fb = P.ops[L.fb];
-    for (int e = tid; e < NP * NP; e += TPC_BLOCK) {
-      const int r = e / NP, c = e - r * NP;
-      wfb[e] = (r < fb.n_out && c < fb.n_in) ? __ldg(reinterpret_cast<const float*>(fb.coef) + r * fb.n_in + c) : 0.f;
+    const bool bulk = fb.n_out == NP && fb.n_in == NP && (reinterpret_cast<uintptr_t>(fb.coef) & 15) == 0;
+    if (bulk) {
+      if (tid == 0) {
+        mbar_init(&wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&wbar, (uint32_t)(NP * NP * sizeof(float)));
+        tma_load_1d(wfb, fb.coef, (uint32_t)(NP * NP * sizeof(float)), &wbar);
+      }
+    } else {
+      for (int e = tid; e < NP * NP; e += TPC_BLOCK) {
+        const int r = e / NP, c = e - r * NP;
+        wfb[e] = (r < fb.n_out && c < fb.n_in) ? __ldg(reinterpret_cast<const float*>(fb.coef) + r * fb.n_in + c) : 0.f;
+      }
     }
     if (tid < NP) {
       wpre[tid] = tid < N ? __ldg(reinterpret_cast<const float*>(P.ops[L.pre].coef) + tid) : 0.f;
       wpost[tid] = tid < N ? __ldg(reinterpret_cast<const float*>(P.ops[L.post].coef) + tid) : 0.f;
     }
-    __syncthreads();
+    __syncthreads();  // (also publishes the barrier's initialisation)
+    if (bulk) mbar_wait(&wbar, 0);
   }
   TpcMat<NP> mat;
   mat.a = tsm + tid;
