@@ -28,7 +28,7 @@ EXPORTS = [
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward", "fsweep_expm_forward_sp", "fsweep_expm_backward_sp",
     "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total",
-    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_allreduce_push", "fsweep_adam_step", "fsweep_fma_probe", "fsweep_fma_probe_flops", "fsweep_biquad_design",
+    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_allreduce_push", "fsweep_adam_step", "fsweep_fma_probe", "fsweep_fma_probe_flops", "fsweep_biquad_design", "fsweep_svf_design",
 ]
 
 
@@ -135,6 +135,8 @@ def lib():
     L.fsweep_adam_step.argtypes = [C.POINTER(AdamTensor), i32, i32, vp, C.c_double, C.c_double, C.c_double, vp]
     L.fsweep_biquad_design.restype = i32
     L.fsweep_biquad_design.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.fsweep_svf_design.restype = i32
+    L.fsweep_svf_design.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     L.fsweep_fma_probe.restype = i32
     L.fsweep_fma_probe.argtypes = [vp, i32, i32, vp]
     L.fsweep_fma_probe_flops.restype = C.c_double

@@ -769,3 +769,96 @@ extern "C" FSWEEP_API int fsweep_biquad_design(const void* param, int K, int n_o
   }
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
+
+// ---------------------------------------------------------------------------------------------- SVF designer
+// dsp.SVF / parallelSVF with the GENERAL mixing (filter_type = None; reference dsp.py:2214-2232, 2343-2347): raw
+// parameter (5, K, ...) = (f, R, mLP, mBP, mHP) before their activations
+//     f = tan(pi/2 sigmoid(p0)),  R = softplus(p1) / ln 2,  mLP = p2 + 1,  mBP = p3 + 2,  mHP = p4 + 1
+//     b = [f^2 mLP + f mBP + mHP, 2 f^2 mLP - 2 mHP, f^2 mLP - f mBP + mHP],  a = [f^2 + 2 R f + 1, 2 f^2 - 2, f^2 - 2 R f + 1]
+// -> packed Taylor blocks of FSWEEP_OP_SOS, forward and adjoint, one launch each (float64 inside).
+namespace {
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(128) svf_design_kernel(const T* __restrict__ param, double* __restrict__ packed,
+                                                         const double* __restrict__ gpacked, T* __restrict__ gparam,
+                                                         int K, int n_out, int n_in, int parallel) {
+  const int per = parallel ? n_in : n_out * n_in;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= K * per) return;
+  const int k = e / per, r = e - k * per;
+  const int m = parallel ? r : r / n_in, n = parallel ? r : r - m * n_in;
+  const size_t cs = (size_t)K * per;  // stride between the five parameter planes
+  const size_t pi_ = (size_t)k * per + r;
+  const double p0 = (double)param[pi_], p1 = (double)param[cs + pi_], p2 = (double)param[2 * cs + pi_],
+               p3 = (double)param[3 * cs + pi_], p4 = (double)param[4 * cs + pi_];
+  const double HALF_PI = 1.57079632679489661923, LN2 = 0.69314718055994530942;
+  const double sg = 1.0 / (1.0 + exp(-p0));
+  const double f = tan(HALF_PI * sg);
+  const double sp = p1 > 20.0 ? p1 : log1p(exp(p1));  // torch's softplus (threshold 20)
+  const double R = sp / LN2;
+  const double mLP = p2 + 1.0, mBP = p3 + 2.0, mHP = p4 + 1.0;
+  const double f2 = f * f;
+  const size_t o = parallel ? ((size_t)k * n_in + n) * 16 : (((size_t)k * n_in + n) * n_out + m) * 16;
+  if constexpr (!BWD) {
+    const double b0 = f2 * mLP + f * mBP + mHP, b1 = 2.0 * f2 * mLP - 2.0 * mHP, b2 = f2 * mLP - f * mBP + mHP;
+    const double a0 = f2 + 2.0 * R * f + 1.0, a1 = 2.0 * f2 - 2.0, a2 = f2 - 2.0 * R * f + 1.0;
+    double* q = packed + o;
+    q[0] = b0 + b1 + b2;
+    q[1] = b1 + 2.0 * b2;
+    q[2] = b2;
+    q[3] = 0.0;
+    q[4] = a0 + a1 + a2;
+    q[5] = a1 + 2.0 * a2;
+    q[6] = a2;
+    q[7] = 0.0;
+    q[8] = b0 - b1 + b2;
+    q[9] = b1 - 2.0 * b2;
+    q[10] = b2;
+    q[11] = 0.0;
+    q[12] = a0 - a1 + a2;
+    q[13] = a1 - 2.0 * a2;
+    q[14] = a2;
+    q[15] = 0.0;
+  } else {
+    const double* g = gpacked + o;
+    const double gb0 = g[0] + g[8], gb1 = g[0] + g[1] - g[8] + g[9], gb2 = g[0] + 2.0 * g[1] + g[2] + g[8] - 2.0 * g[9] + g[10];
+    const double ga0 = g[4] + g[12], ga1 = g[4] + g[5] - g[12] + g[13], ga2 = g[4] + 2.0 * g[5] + g[6] + g[12] - 2.0 * g[13] + g[14];
+    // d / d f, R, mLP, mBP, mHP
+    const double gf = gb0 * (2.0 * f * mLP + mBP) + gb1 * (4.0 * f * mLP) + gb2 * (2.0 * f * mLP - mBP) +
+                      ga0 * (2.0 * f + 2.0 * R) + ga1 * (4.0 * f) + ga2 * (2.0 * f - 2.0 * R);
+    const double gR = ga0 * (2.0 * f) - ga2 * (2.0 * f);
+    const double gLP = (gb0 + 2.0 * gb1 + gb2) * f2;
+    const double gBP = (gb0 - gb2) * f;
+    const double gHP = gb0 - 2.0 * gb1 + gb2;
+    const double dfdp0 = HALF_PI * sg * (1.0 - sg) * (1.0 + f2);
+    const double dRdp1 = (p1 > 20.0 ? 1.0 : 1.0 / (1.0 + exp(-p1))) / LN2;
+    gparam[pi_] = (T)(gf * dfdp0);
+    gparam[cs + pi_] = (T)(gR * dRdp1);
+    gparam[2 * cs + pi_] = (T)gLP;
+    gparam[3 * cs + pi_] = (T)gBP;
+    gparam[4 * cs + pi_] = (T)gHP;
+  }
+}
+}  // namespace
+
+extern "C" FSWEEP_API int fsweep_svf_design(const void* param, int K, int n_out, int n_in, int parallel, int dtype,
+                                            void* packed, const void* gpacked, void* gparam, void* stream) {
+  if (!param || K < 1 || n_out < 1 || n_in < 1 || (!packed && !(gpacked && gparam))) return FSWEEP_E_BADARG;
+  const int total = K * (parallel ? n_in : n_out * n_in);
+  const int grid = (total + 127) / 128;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool bwd = packed == nullptr;
+  if (dtype == FSWEEP_C64) {
+    if (bwd)
+      svf_design_kernel<float, true><<<grid, 128, 0, st>>>((const float*)param, nullptr, (const double*)gpacked, (float*)gparam, K, n_out, n_in, parallel);
+    else
+      svf_design_kernel<float, false><<<grid, 128, 0, st>>>((const float*)param, (double*)packed, nullptr, nullptr, K, n_out, n_in, parallel);
+  } else if (dtype == FSWEEP_C128) {
+    if (bwd)
+      svf_design_kernel<double, true><<<grid, 128, 0, st>>>((const double*)param, nullptr, (const double*)gpacked, (double*)gparam, K, n_out, n_in, parallel);
+    else
+      svf_design_kernel<double, false><<<grid, 128, 0, st>>>((const double*)param, (double*)packed, nullptr, nullptr, K, n_out, n_in, parallel);
+  } else {
+    return FSWEEP_E_BADARG;
+  }
+  return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}

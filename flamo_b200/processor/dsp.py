@@ -714,6 +714,15 @@ class SVF(_SectionFilter):
         m = self._mix(p[2:], r)
         return f, R, m[0], m[1], m[2]
 
+    def _fused_design(self, param):
+        stock = (getattr(self.map, "__func__", None) is SVF.map_param2svf and type(self)._taps is SVF._taps
+                 and type(self)._mix is SVF._mix and type(self).param2freq is SVF.param2freq
+                 and type(self).param2R is SVF.param2R and self.filter_type is None)
+        if not (stock and param.is_cuda and param.dtype in (torch.float32, torch.float64)
+                and sweep._BACKEND.name == "cuda" and os.environ.get("FLAMO_B200_FUSED_DESIGN", "1") == "1"):
+            return None
+        return sweep.SVFDesign.apply(param, self.output_channels, self.input_channels, self._parallel)
+
     def _taps(self, mapped):
         f, R, mLP, mBP, mHP = mapped
         f2 = f * f

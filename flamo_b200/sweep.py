@@ -585,6 +585,41 @@ class BiquadDesign(torch.autograd.Function):
         return gp, None, None, None, None
 
 
+class SVFDesign(torch.autograd.Function):
+    """Raw SVF parameter (general mixing) -> packed section coefficients in ONE launch each way (libfsweep
+    fsweep_svf_design), as BiquadDesign."""
+
+    @staticmethod
+    def forward(ctx, param, n_out, n_in, parallel):
+        global launch_count
+        p = param.detach().contiguous()
+        K = p.shape[1]
+        shape = (K, n_in, 2, 8) if parallel else (K, n_in, n_out, 2, 8)
+        packed = torch.empty(shape, dtype=torch.float64, device=p.device)
+        with torch.cuda.device(p.device):
+            _lib.check(_lib.lib().fsweep_svf_design(p.data_ptr(), K, n_out, n_in, int(parallel), _real_code(p.dtype),
+                                                     packed.data_ptr(), None, None,
+                                                     torch.cuda.current_stream(p.device).cuda_stream))
+        launch_count += 1
+        ctx.save_for_backward(p)
+        ctx.meta = (n_out, n_in, parallel)
+        return packed
+
+    @staticmethod
+    def backward(ctx, g):
+        global launch_count
+        (p,) = ctx.saved_tensors
+        n_out, n_in, parallel = ctx.meta
+        gc = g.to(torch.float64).contiguous()
+        gp = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            _lib.check(_lib.lib().fsweep_svf_design(p.data_ptr(), p.shape[1], n_out, n_in, int(parallel),
+                                                     _real_code(p.dtype), None, gc.data_ptr(), gp.data_ptr(),
+                                                     torch.cuda.current_stream(p.device).cuda_stream))
+        launch_count += 1
+        return gp, None, None, None
+
+
 def _real_code(dtype: torch.dtype) -> int:
     return _lib.C64 if dtype == torch.float32 else _lib.C128
 

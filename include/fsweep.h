@@ -236,6 +236,12 @@ FSWEEP_API int fsweep_expm_backward_sp(const void* P, const void* G, void* gP, i
 FSWEEP_API int fsweep_biquad_design(const void* param, int K, int n_out, int n_in, int parallel, int highpass, int dtype,
                                     void* packed, const void* gpacked, void* gparam, void* stream);
 
+/* dsp.SVF / parallelSVF with the general mixing (filter_type = None; reference dsp.py:2214-2232, 2234-2347): raw parameter
+ * (5, K, n_out, n_in) [parallel: (5, K, n)] -> activations -> taps -> packed Taylor blocks, float64; forward when
+ * packed != NULL, adjoint when packed == NULL (arguments as fsweep_biquad_design). */
+FSWEEP_API int fsweep_svf_design(const void* param, int K, int n_out, int n_in, int parallel, int dtype, void* packed,
+                                 const void* gpacked, void* gparam, void* stream);
+
 /* sparsity_loss of the mapped feedback matrix (reference optimize/loss.py:36-63), A: device real[n_mats][n][n]:
  *   loss = mean_i ((sum |A_i| - n sqrt n) / (n (1 - sqrt n)));  backward: gA = gloss * dloss/dA (gloss: device real[1]).
  * One launch each way, capture safe. */

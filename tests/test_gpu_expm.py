@@ -140,3 +140,39 @@ def test_fused_biquad_designer_equals_the_pytorch_designer(ft, parallel, dtype, 
     tol = 1e-5 if dtype == torch.float32 else 1e-11
     assert float((g1 - g0).abs().max()) <= tol * float(g0.abs().max())
     assert float(g0.abs().max()) > 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("parallel", [False, True])
+def test_fused_svf_designer_equals_the_pytorch_designer(parallel, dtype, monkeypatch):
+    """fsweep_svf_design (activations -> taps -> Taylor packing in one launch, and its adjoint; general mixing) against
+    the PyTorch chain it replaces: packed coefficients and parameter gradients."""
+    from flamo_b200.processor import dsp
+
+    torch.manual_seed(6)
+    kw = dict(n_sections=2, filter_type=None, nfft=256, fs=48000, requires_grad=True, alias_decay_db=10.0, device="cuda", dtype=dtype)
+    mod = dsp.parallelSVF(size=(4,), **kw) if parallel else dsp.SVF(size=(3, 2), **kw)
+    with torch.no_grad():
+        mod.param.mul_(1.7)
+        mod.param[1, 0].add_(25.0)  # softplus beyond its linear threshold
+    Wt = torch.randn((2, 4, 2, 8) if parallel else (2, 2, 3, 2, 8), device="cuda", dtype=torch.float64)
+
+    def run(fused):
+        monkeypatch.setenv("FLAMO_B200_FUSED_DESIGN", "1" if fused else "0")
+        mod.param.grad = None
+        coef = mod._fused_design(mod.param)
+        assert (coef is not None) == fused
+        if coef is None:
+            b, a = mod._taps(mod.map(mod._up(mod.param)))
+            coef = sweep.pack_sections(b, a, parallel, None)
+        (coef * Wt).sum().backward()
+        return coef.detach().clone(), mod.param.grad.detach().clone()
+
+    c1, g1 = run(True)
+    c0, g0 = run(False)
+    assert float((c1 - c0).abs().max()) <= 1e-12 * float(c0.abs().max())
+    tol = 1e-5 if dtype == torch.float32 else 1e-11
+    assert float((g1 - g0).abs().max()) <= tol * float(g0.abs().max())
+    # the typed variants (lowpass ... notch) keep the PyTorch designer
+    typed = dsp.SVF(size=(2, 2), n_sections=1, filter_type="peaking", nfft=256, device="cuda", dtype=dtype)
+    assert typed._fused_design(typed.param) is None
