@@ -36,7 +36,7 @@ class Op(C.Structure):
     """fsweep_op_t"""
     _fields_ = [
         ("kind", C.c_int32), ("n_out", C.c_int32), ("n_in", C.c_int32), ("n_sections", C.c_int32),
-        ("flags", C.c_uint32), ("n_ff", C.c_int32), ("n_fb", C.c_int32), ("reserved", C.c_int32),
+        ("flags", C.c_uint32), ("n_ff", C.c_int32), ("n_fb", C.c_int32), ("per_item", C.c_int32),
     ]
 
 

@@ -78,6 +78,7 @@ struct fsweep_plan {
   size_t stream_bps_smem[2] = {0, 0};  // ... for this dynamic shared memory size
   bool stream = false;  // TABLE-heavy program without recursion: streaming kernels, fsweep_stream.cuh
   StreamInfo sinfo;     // everything but tb / qc / threads (chosen per call from batch*cols)
+  bool items = false;   // some op carries one coefficient set PER BATCH ITEM (fsweep_op_t::per_item): generic kernels, grid.y = item
   bool grad32 = false;  // FSWEEP_DT_GRAD32: float64 plan of a float32 model, deferred cascade gradients in float32 arithmetic
   bool cta = false;  // wide flagship shape (32 < N <= 64, float32): CTA-per-bin kernels, fsweep_cta.cuh
   bool cta_tc = false;  // ... with the tensor-core elimination (fsweep_tc.cuh) instead of the SIMT one
@@ -199,6 +200,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
 
   int acc_per_lane = 0, acc_total = 0, h_total = 0;
   p->any_global = p->any_acc = false;
+  for (int i : order) p->items = p->items || ops[i].per_item != 0;
   P.needs_ctx = 0;
   for (size_t s = 0; s < order.size(); ++s) {
     const fsweep_op_t& o = ops[order[s]];
@@ -229,7 +231,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   // ---- wide flagship shape -> CTA-per-bin kernels: [GAIN N x 1] RECURSION(diagonal, no gradients ; GAIN N x N) [GAIN 1 x N]
   {
     const char* no_cta = getenv("FSWEEP_DISABLE_CTA");
-    bool ok = (dtype == FSWEEP_C128 || !(no_cta && no_cta[0] == '1')) && width > 32 && width <= 64 && rec >= 0 &&
+    bool ok = !p->items && (dtype == FSWEEP_C128 || !(no_cta && no_cta[0] == '1')) && width > 32 && width <= 64 && rec >= 0 &&
               pre.size() == 1 && post.size() == 1 && fb.size() == 1 && ops[fb[0]].kind == FSWEEP_OP_GAIN &&
               ops[pre[0]].kind == FSWEEP_OP_GAIN && ops[post[0]].kind == FSWEEP_OP_GAIN && ops[pre[0]].n_in == 1 &&
               ops[post[0]].n_out == 1 && ops[pre[0]].n_out == rec_n && ops[post[0]].n_in == rec_n && rec_in == rec_n &&
@@ -273,7 +275,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   P.def_stride = 0;
   {
     const char* no_defer = getenv("FSWEEP_DISABLE_DEFER");
-    if (!(no_defer && no_defer[0] == '1'))
+    if (!(no_defer && no_defer[0] == '1') && !p->items)
       for (int s = 0; s < P.n_ops; ++s)
         if (P.ops[s].acc_mode == ACC_GLOBAL && (P.ops[s].kind == FSWEEP_OP_SOS || P.ops[s].kind == FSWEEP_OP_PSOS) &&
             P.ops[s].K <= DEF_MAX_K) {
@@ -333,7 +335,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
 
   // ---- FDN-loop pattern: [GAIN] RECURSION(ff: diagonal ops, fb: one GAIN) [GAIN]
   const char* no_loop = getenv("FSWEEP_DISABLE_LOOP_KERNEL");  // tests: force the generic interpreter
-  if (!(no_loop && no_loop[0] == '1') && rec >= 0 && pre.size() <= 1 && post.size() <= 1 && fb.size() == 1 &&
+  if (!(no_loop && no_loop[0] == '1') && !p->items && rec >= 0 && pre.size() <= 1 && post.size() <= 1 && fb.size() == 1 &&
       ops[fb[0]].kind == FSWEEP_OP_GAIN &&
       (pre.empty() || ops[pre[0]].kind == FSWEEP_OP_GAIN) && (post.empty() || ops[post[0]].kind == FSWEEP_OP_GAIN) &&
       G <= 32 && (dtype == FSWEEP_C64 || G <= 16)) {
@@ -376,7 +378,7 @@ extern "C" int fsweep_plan_create(const fsweep_op_t* ops, int n_ops, int64_t nff
   // ---- TABLE-heavy program without recursion -> streaming kernels
   {
     const char* no_stream = getenv("FSWEEP_DISABLE_STREAM");
-    bool ok = !(no_stream && no_stream[0] == '1') && dtype == FSWEEP_C64 && rec < 0 && width <= SW;
+    bool ok = !(no_stream && no_stream[0] == '1') && !p->items && dtype == FSWEEP_C64 && rec < 0 && width <= SW;
     bool any_table = false;
     for (int s2 = 0; s2 < P.n_ops && ok; ++s2) {
       const OpK& o = P.ops[s2];
@@ -597,6 +599,28 @@ int pick_grid(fsweep_plan* p, int cc, bool bwd, size_t smem, int64_t n_bins, cud
   return (int)std::min<int64_t>(resident, grid_cap(n_bins, p->G));
 }
 
+size_t slot_bytes(const fsweep_plan* plan, int slot) {
+  const int kind = plan->leaf[slot].kind;
+  const size_t rs = plan->dtype == FSWEEP_C64 ? 4 : 8;
+  const size_t n = (size_t)fsweep_plan_coeff_numel(plan, slot, plan->prog.nfft / 2 + 1);
+  if (kind == FSWEEP_OP_DELAY || kind == FSWEEP_OP_PDELAY) return n * 8;
+  return n * (kind_is_table(kind) ? 2 * rs : rs);
+}
+
+// Per-item launches (fsweep_op_t::per_item): `batch` is the item count, the grid gets one y-slice per item and the
+// x-extent is what keeps items * grid.x near the resident block count.  Fills the item strides of P.
+int items_setup(fsweep_plan* plan, ProgK& P, int64_t batch, int* grid_x) {
+  if (batch > 65535 || batch > MAX_GRID) return fail(FSWEEP_E_UNSUPPORTED, "per-item coefficients: at most %d items per call", MAX_GRID);
+  for (int s = 0; s < plan->n_coeffs; ++s) {
+    const long long b = plan->leaf[s].per_item ? (long long)slot_bytes(plan, s) : 0;
+    P.ops[s].coef_is = b;
+    P.ops[s].gtab_is = b;
+  }
+  const int gx = std::max<int>(1, std::min<int64_t>(MAX_GRID / batch, (*grid_x + batch - 1) / batch));
+  *grid_x = std::min(*grid_x, gx);
+  return FSWEEP_OK;
+}
+
 int check_common(const fsweep_plan* plan, const void* const* coeffs, const void* x, int64_t batch, int64_t cols,
                  int64_t bin_begin, int64_t n_bins, int epilogue) {
   if (!plan || !coeffs || !x) return fail(FSWEEP_E_BADARG, "null plan / coeffs / x");
@@ -625,11 +649,11 @@ extern "C" const char* fsweep_plan_kernel_family(const fsweep_plan_t* plan, int6
 
 namespace {
 // [per-block partial sums][flat global accumulator][pad][loss partials] — then the deferral buffer
-size_t ws_base_bytes(const fsweep_plan* plan, int64_t n_bins) {
+size_t ws_base_bytes(const fsweep_plan* plan, int64_t n_bins, int64_t items = 1) {
   const size_t rs = plan->dtype == FSWEEP_C64 ? 4 : 8;
   const size_t grid = (size_t)grid_cap(n_bins, plan->G);
-  size_t partial = grid * (size_t)plan->prog.acc_per_lane * plan->G * rs;
-  size_t gacc = (size_t)plan->prog.acc_total * rs;
+  size_t partial = grid * (size_t)items * (size_t)plan->prog.acc_per_lane * plan->G * rs;  // (per-item launches: [item][block])
+  size_t gacc = (size_t)items * (size_t)plan->prog.acc_total * rs;
   return ((partial + 255) / 256) * 256 + ((gacc + 255) / 256) * 256 + 256 + LOSS_PARTIAL_BYTES;
 }
 // deferral records, then one response table per deferred op
@@ -648,19 +672,19 @@ size_t ws_defer_bytes(const fsweep_plan* plan, int64_t batch, int64_t cols, int6
 
 extern "C" size_t fsweep_workspace_bytes(const fsweep_plan_t* plan, int64_t batch, int64_t cols, int64_t n_bins) {
   if (!plan) return 0;
-  return ws_base_bytes(plan, n_bins) + ws_defer_bytes(plan, batch, cols, n_bins);
+  return ws_base_bytes(plan, n_bins, plan->items ? batch : 1) + ws_defer_bytes(plan, batch, cols, n_bins);
 }
 
 namespace {
 
 // validates a fused criterion and fills the kernel-side fields; returns the internal epilogue code in *epi
-int setup_criterion(const fsweep_plan* plan, const fsweep_criterion_t* crit, int64_t n_bins, void* workspace,
+int setup_criterion(const fsweep_plan* plan, const fsweep_criterion_t* crit, int64_t n_bins, int64_t items, void* workspace,
                     size_t workspace_bytes, SweepArgs& A, int* epi) {
   if (!crit) return fail(FSWEEP_E_BADARG, "null criterion");
   if (crit->kind != FSWEEP_CRIT_MSE && crit->kind != FSWEEP_CRIT_MSE_CHSUM)
     return fail(FSWEEP_E_BADARG, "bad criterion kind %d", crit->kind);
   if (!crit->target || !crit->loss) return fail(FSWEEP_E_BADARG, "criterion: null target / loss");
-  const size_t need = ws_base_bytes(plan, n_bins);
+  const size_t need = ws_base_bytes(plan, n_bins, items);
   if (!workspace || workspace_bytes < need)
     return fail(FSWEEP_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
   *epi = crit->kind == FSWEEP_CRIT_MSE ? EPI_ABS_MSE : EPI_ABSSUM_MSE;
@@ -671,11 +695,12 @@ int setup_criterion(const fsweep_plan* plan, const fsweep_criterion_t* crit, int
   return FSWEEP_OK;
 }
 
-void launch_loss_finalize(int dtype, int n_blocks, const SweepArgs& A, void* loss, cudaStream_t st) {
+void launch_loss_finalize(int dtype, int n_blocks, int n_items, const SweepArgs& A, void* loss, cudaStream_t st) {
   FinalizeArgs F;
   memset(&F, 0, sizeof(F));
   F.n_ops = 0;
   F.n_blocks = n_blocks;
+  F.n_items = n_items;
   F.loss_partial = A.loss_partial;
   F.loss = loss;
   F.crit_scale = A.crit_scale;
@@ -732,8 +757,9 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
   A.bin_begin = bin_begin;
   A.n_bins = n_bins;
   A.epilogue = epilogue;
-  if (crit && (r = setup_criterion(plan, crit, n_bins, workspace, workspace_bytes, A, &A.epilogue))) return r;
-  const int cc = cc_of(batch * cols);
+  const int64_t items = plan->items ? batch : 1;
+  if (crit && (r = setup_criterion(plan, crit, n_bins, items, workspace, workspace_bytes, A, &A.epilogue))) return r;
+  const int cc = cc_of(plan->items ? cols : batch * cols);
   const bool loop = plan->loop_fast;
   LaunchCfg cfg;
   cfg.smem = plan->cta ? 0 : smem_fwd(plan);
@@ -742,6 +768,8 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
   cudaError_t e = cudaSuccess;
   cfg.grid = plan->cta ? 0 : pick_grid(plan, cc, false, cfg.smem, n_bins, &e, loop);
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+  if (plan->items && (r = items_setup(plan, P, batch, &cfg.grid))) return r;
+  cfg.items = (int)items;
   const int dtype = plan->dtype;
   StreamInfo SI;
   size_t ssmem = 0;
@@ -781,7 +809,7 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "forward launch: %s", cudaGetErrorString(e));
   g_launches = 1;
   if (crit) {
-    launch_loss_finalize(dtype, cfg.grid, A, crit->loss, cfg.stream);
+    launch_loss_finalize(dtype, cfg.grid, (int)items, A, crit->loss, cfg.stream);
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(FSWEEP_E_CUDA, "loss finalize launch: %s", cudaGetErrorString(e));
     g_launches = 2;
   }
@@ -829,7 +857,8 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   bool any_deferred = false;
   for (int s = 0; s < plan->n_coeffs; ++s)
     if (plan->prog.ops[s].def_off >= 0 && grad_coeffs && grad_coeffs[s]) any_deferred = true;
-  const size_t need = ws_base_bytes(plan, n_bins) + (any_deferred ? ws_defer_bytes(plan, batch, cols, n_bins) : 0);
+  const int64_t items = plan->items ? batch : 1;
+  const size_t need = ws_base_bytes(plan, n_bins, items) + (any_deferred ? ws_defer_bytes(plan, batch, cols, n_bins) : 0);
   if (need > 256 + LOSS_PARTIAL_BYTES && (!workspace || workspace_bytes < need))
     return fail(FSWEEP_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
@@ -851,7 +880,7 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   if (grad_x && plan->first_pre_rstep >= 0) P.rsteps[plan->first_pre_rstep].flags |= RS_NEED_GIN;
 
   const bool loop = plan->loop_fast;
-  const int cc = loop ? 1 : cc_of(batch * cols);
+  const int cc = loop ? 1 : cc_of(plan->items ? cols : batch * cols);
   LaunchCfg cfg;
   cfg.smem = plan->cta ? 0 : smem_bwd(plan, cc);
   if (cfg.smem > 220 * 1024) return fail(FSWEEP_E_UNSUPPORTED, "backward needs %zu bytes of shared memory", cfg.smem);
@@ -859,8 +888,16 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   cudaError_t e = cudaSuccess;
   cfg.grid = plan->cta ? 0 : pick_grid(plan, cc, true, cfg.smem, n_bins, &e, loop);
   if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+  if (plan->items) {
+    if ((r = items_setup(plan, P, batch, &cfg.grid))) return r;
+    for (int s = 0; s < plan->n_coeffs; ++s)
+      if (P.ops[s].acc_mode == ACC_TABLE && !plan->leaf[s].per_item)
+        return fail(FSWEEP_E_UNSUPPORTED, "slot %d: the gradient of a TABLE shared by all items is not formed by a per-item launch", s);
+  }
+  cfg.items = (int)items;
 
-  const size_t partial_bytes = (((size_t)grid_cap(n_bins, plan->G) * P.acc_per_lane * plan->G * rs + 255) / 256) * 256;
+  const size_t partial_bytes =
+      (((size_t)grid_cap(n_bins, plan->G) * (size_t)items * P.acc_per_lane * plan->G * rs + 255) / 256) * 256;
   char* ws = reinterpret_cast<char*>(workspace);
   void* partial = ws;
   void* gacc = ws ? ws + partial_bytes : nullptr;
@@ -881,11 +918,11 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
   A.partial = partial;
   A.gacc = gacc;
   A.defer = any_deferred ? ws + ws_base_bytes(plan, n_bins) : nullptr;
-  if (crit && (r = setup_criterion(plan, crit, n_bins, workspace, workspace_bytes, A, &A.epilogue))) return r;
+  if (crit && (r = setup_criterion(plan, crit, n_bins, items, workspace, workspace_bytes, A, &A.epilogue))) return r;
 
   int launches = 0;
   if (plan->any_global) {
-    e = cudaMemsetAsync(gacc, 0, (size_t)P.acc_total * rs, st);
+    e = cudaMemsetAsync(gacc, 0, (size_t)items * P.acc_total * rs, st);
     if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "memset: %s", cudaGetErrorString(e));
     ++launches;
   }
@@ -1006,6 +1043,8 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     F.G = plan->G;
     F.acc_per_lane = P.acc_per_lane;
     F.n_blocks = cfg.grid;
+    F.n_items = (int)items;
+    F.acc_total = P.acc_total;
     F.partial = partial;
     F.gacc = gacc;
     int max_total = 1;
@@ -1020,14 +1059,15 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
       o.row_len = P.ops[s].row_len;
       o.acc_off = P.ops[s].acc_off;
       o.grad = grad_coeffs[s];
+      o.grad_is = plan->items && plan->leaf[s].per_item ? (long long)fsweep_plan_coeff_numel(plan, s, P.nfft / 2 + 1) : 0;
       if (o.grad && (o.acc_mode == ACC_SMEM || o.acc_mode == ACC_GLOBAL))
         max_total = std::max(max_total, o.n_out * o.row_len);
     }
     // 4 warps per block, 1 warp per element; row n_ops of the grid sums the fused criterion's loss
-    dim3 grid((unsigned)std::min(1024, (max_total + 3) / 4), (unsigned)P.n_ops + (crit ? 1u : 0u));
+    dim3 grid((unsigned)std::min(1024, (max_total + 3) / 4), (unsigned)P.n_ops + (crit ? 1u : 0u), (unsigned)items);
     const char* v2 = getenv("FSWEEP_FINALIZE_V2");  // coalesced kernel (default); "0" selects the round-1 kernel
     if (!(v2 && v2[0] == '0')) {
-      dim3 grid2((unsigned)std::min(256, (max_total + 31) / 32), grid.y);
+      dim3 grid2((unsigned)std::min(256, (max_total + 31) / 32), grid.y, grid.z);
       if (dtype == FSWEEP_C64)
         fsweep_finalize_v2_kernel<float><<<grid2, 32 * FIN2_WARPS, 0, st>>>(F);
       else
@@ -1040,7 +1080,7 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     if (e != cudaSuccess) return fail(FSWEEP_E_CUDA, "finalize launch: %s", cudaGetErrorString(e));
     ++launches;
   } else if (crit) {
-    launch_loss_finalize(dtype, cfg.grid, A, crit->loss, st);
+    launch_loss_finalize(dtype, cfg.grid, (int)items, A, crit->loss, st);
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(FSWEEP_E_CUDA, "loss finalize launch: %s", cudaGetErrorString(e));
     ++launches;
   }

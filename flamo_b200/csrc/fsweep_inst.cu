@@ -15,7 +15,7 @@ static cudaError_t launch_fwd_t(const LaunchCfg& cfg, const ProgK& P, const Swee
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
   }
-  k<<<cfg.grid, BLOCK, cfg.smem, cfg.stream>>>(P, A);
+  k<<<dim3((unsigned)cfg.grid, (unsigned)cfg.items), BLOCK, cfg.smem, cfg.stream>>>(P, A);
   return cudaGetLastError();
 }
 
@@ -26,7 +26,7 @@ static cudaError_t launch_bwd_t(const LaunchCfg& cfg, const ProgK& P, const Swee
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
   }
-  k<<<cfg.grid, BLOCK, cfg.smem, cfg.stream>>>(P, A);
+  k<<<dim3((unsigned)cfg.grid, (unsigned)cfg.items), BLOCK, cfg.smem, cfg.stream>>>(P, A);
   return cudaGetLastError();
 }
 

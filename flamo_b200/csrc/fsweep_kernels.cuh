@@ -66,6 +66,9 @@ struct OpK {
                 // fsweep_sos_defer_kernel forms the coefficient gradient afterwards; -1 otherwise
   const void* coef;
   void* gtab;  // ACC_TABLE: gradient table
+  // per-item coefficient sets (fsweep_op_t::per_item, the generic kernels only): bytes between the sets of consecutive
+  // batch items in `coef` / `gtab`; 0 when every item shares one set
+  long long coef_is, gtab_is;
 };
 
 // The host lowers the op list into small step tables so that every kernel has exactly ONE call
@@ -317,12 +320,14 @@ struct Ctx {
   long long nfft;
   double lng;
   double inv_nfft;
+  long long item;  // batch item whose coefficient set this block reads (per-item launches: blockIdx.y; else 0)
 };
 
 template <typename T>
-__device__ __forceinline__ Ctx<T> make_ctx(const ProgK& P, long long k) {
+__device__ __forceinline__ Ctx<T> make_ctx(const ProgK& P, long long k, int item = 0) {
   Ctx<T> c;
   c.k = k;
+  c.item = item;
   c.nfft = P.nfft;
   c.lng = P.lng;
   c.inv_nfft = P.inv_nfft;
@@ -351,6 +356,16 @@ __device__ __forceinline__ Ctx<T> make_ctx(const ProgK& P, long long k) {
 // ---------------------------------------------------------------------------------- op responses
 __device__ __forceinline__ bool is_dense(int kind) {
   return kind == FSWEEP_OP_GAIN || kind == FSWEEP_OP_SOS || kind == FSWEEP_OP_DELAY || kind == FSWEEP_OP_TABLE;
+}
+
+// coefficient set of the block's batch item (ctx.item is the constant 0 outside the per-item launches)
+template <typename U, typename T>
+__device__ __forceinline__ const U* coef_of(const OpK& op, const Ctx<T>& ctx) {
+  return reinterpret_cast<const U*>(reinterpret_cast<const char*>(op.coef) + ctx.item * op.coef_is);
+}
+template <typename T>
+__device__ __forceinline__ T* gtab_of(const OpK& op, const Ctx<T>& ctx) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(op.gtab) + ctx.item * op.gtab_is);
 }
 
 template <typename T>
@@ -545,14 +560,14 @@ __device__ __forceinline__ cx<T> op_entry(const OpK& op, const Ctx<T>& ctx, int 
   guard = false;
   switch (op.kind) {
     case FSWEEP_OP_GAIN:
-      return mk<T>(__ldg(reinterpret_cast<const T*>(op.coef) + m * op.n_in + n), T(0));
+      return mk<T>(__ldg(coef_of<T>(op, ctx) + m * op.n_in + n), T(0));
     case FSWEEP_OP_DELAY:
-      return delay_eval<T>(__ldg(reinterpret_cast<const double*>(op.coef) + m * op.n_in + n), op.flags, ctx);
+      return delay_eval<T>(__ldg(coef_of<double>(op, ctx) + m * op.n_in + n), op.flags, ctx);
     case FSWEEP_OP_SOS:
-      return sos_eval<T>(reinterpret_cast<const T*>(op.coef) + ((size_t)n * op.n_out + m) * 16, op.K,
+      return sos_eval<T>(coef_of<T>(op, ctx) + ((size_t)n * op.n_out + m) * 16, op.K,
                          (long)op.n_in * op.n_out * 16, ctx, guard);
     case FSWEEP_OP_TABLE: {
-      const T* t = reinterpret_cast<const T*>(op.coef) + 2 * (((size_t)ctx.k * op.n_out + m) * op.n_in + n);
+      const T* t = coef_of<T>(op, ctx) + 2 * (((size_t)ctx.k * op.n_out + m) * op.n_in + n);
       return mk<T>(__ldg(t), __ldg(t + 1));
     }
     default:
@@ -566,13 +581,13 @@ __device__ __forceinline__ cx<T> op_diag(const OpK& op, const Ctx<T>& ctx, int m
   if (m >= op.n_out) return mk<T>(0, 0);
   switch (op.kind) {
     case FSWEEP_OP_PGAIN:
-      return mk<T>(__ldg(reinterpret_cast<const T*>(op.coef) + m), T(0));
+      return mk<T>(__ldg(coef_of<T>(op, ctx) + m), T(0));
     case FSWEEP_OP_PDELAY:
-      return delay_eval<T>(__ldg(reinterpret_cast<const double*>(op.coef) + m), op.flags, ctx);
+      return delay_eval<T>(__ldg(coef_of<double>(op, ctx) + m), op.flags, ctx);
     case FSWEEP_OP_PSOS:
-      return sos_eval<T>(reinterpret_cast<const T*>(op.coef) + (size_t)m * 16, op.K, (long)op.n_out * 16, ctx, guard);
+      return sos_eval<T>(coef_of<T>(op, ctx) + (size_t)m * 16, op.K, (long)op.n_out * 16, ctx, guard);
     case FSWEEP_OP_PTABLE: {
-      const T* t = reinterpret_cast<const T*>(op.coef) + 2 * ((size_t)ctx.k * op.n_out + m);
+      const T* t = coef_of<T>(op, ctx) + 2 * ((size_t)ctx.k * op.n_out + m);
       return mk<T>(__ldg(t), __ldg(t + 1));
     }
     default:
@@ -699,12 +714,12 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
               break;
             case FSWEEP_OP_SOS:
               if (!((gmask >> n) & 1u))
-                sos_grad<T>(op, reinterpret_cast<const T*>(op.coef) + ((size_t)n * op.n_out + lane) * 16,
+                sos_grad<T>(op, coef_of<T>(op, ctx) + ((size_t)n * op.n_out + lane) * 16,
                             (long)op.n_in * op.n_out * 16, ctx, hrow[(size_t)n * BLOCK], gh, acc, lane, n * 16);
               break;
             case FSWEEP_OP_TABLE:
               if (acc.valid && op.gtab) {
-                T* t = reinterpret_cast<T*>(op.gtab) + 2 * (((size_t)ctx.k * op.n_out + lane) * op.n_in + n);
+                T* t = gtab_of<T>(op, ctx) + 2 * (((size_t)ctx.k * op.n_out + lane) * op.n_in + n);
                 if (first_chunk) {
                   t[0] = gh.x;
                   t[1] = gh.y;
@@ -760,12 +775,12 @@ __device__ __forceinline__ void backprop_op(const OpK& op, const Ctx<T>& ctx, in
           break;
         case FSWEEP_OP_PSOS:
           if (!(gmask & 1u))
-            sos_grad<T>(op, reinterpret_cast<const T*>(op.coef) + (size_t)lane * 16, (long)op.n_out * 16, ctx, h, gh,
+            sos_grad<T>(op, coef_of<T>(op, ctx) + (size_t)lane * 16, (long)op.n_out * 16, ctx, h, gh,
                         acc, lane, 0);
           break;
         case FSWEEP_OP_PTABLE:
           if (acc.valid && op.gtab) {
-            T* t = reinterpret_cast<T*>(op.gtab) + 2 * ((size_t)ctx.k * op.n_out + lane);
+            T* t = gtab_of<T>(op, ctx) + 2 * ((size_t)ctx.k * op.n_out + lane);
             if (first_chunk) {
               t[0] = gh.x;
               t[1] = gh.y;
@@ -1022,7 +1037,7 @@ __device__ __forceinline__ void block_loss_store(double lacc, double* loss_parti
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) s += red[w];
-    loss_partial[blockIdx.x] = s;
+    loss_partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
   }
 }
 
@@ -1053,19 +1068,21 @@ __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant
   const long long groups_total = (long long)gridDim.x * (BLOCK / G);
   const long long gg = (long long)blockIdx.x * (BLOCK / G) + tid / G;
   const long long n_iter = (A.n_bins + groups_total - 1) / groups_total;
-  const int ncols_total = A.batch * A.cols;
-  const cx<T>* x = reinterpret_cast<const cx<T>*>(A.x);
+  // per-item launches (fsweep_op_t::per_item): blockIdx.y is the batch item, its columns are the block's whole batch
+  const int item = blockIdx.y;
+  const int ncols_total = (gridDim.y > 1 ? 1 : A.batch) * A.cols;
+  const cx<T>* x = reinterpret_cast<const cx<T>*>(A.x) + (size_t)item * A.xbs;
   double lacc = 0.0;
 
   {
-    const Ctx<T> c0 = make_ctx<T>(P, A.bin_begin);
+    const Ctx<T> c0 = make_ctx<T>(P, A.bin_begin, item);
     stage_ops<T>(P, c0, lane, hc, gmask, tid, true);  // bin-invariant rows, once per kernel
   }
   for (long long it = 0; it < n_iter; ++it) {
     long long bl = it * groups_total + gg;
     const bool valid = bl < A.n_bins;
     if (!valid) bl = A.n_bins - 1;
-    const Ctx<T> ctx = make_ctx<T>(P, A.bin_begin + bl);
+    const Ctx<T> ctx = make_ctx<T>(P, A.bin_begin + bl, item);
     stage_ops<T>(P, ctx, lane, hc, gmask, tid, false);
     LU<T, G> lu;
     if (P.rec_n > 0) build_loop<T, G>(P, lane, lu, hc, tid);
@@ -1082,7 +1099,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant
 #pragma unroll
         for (int c = 0; c < CC; ++c) {
           const int q = q0 + c < ncols_total ? q0 + c : ncols_total - 1;
-          crit_rowdist<T, G>(A, abs_t(S[c].x, S[c].y), lane < P.out_ch, lane, P.out_ch, bl, q, lane,
+          crit_rowdist<T, G>(A, abs_t(S[c].x, S[c].y), lane < P.out_ch, lane, P.out_ch, bl, item + q, lane,
                              valid && q0 + c < ncols_total, lacc);
         }
       } else if (valid && lane < P.out_ch) {
@@ -1091,7 +1108,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_fwd_kernel(const __grid_constant
           int q = q0 + c;
           if (q < ncols_total) {
             int b = q / A.cols, cc = q - b * A.cols;
-            size_t off = (size_t)b * A.ybs + ((size_t)bl * P.out_ch + lane) * A.cols + cc;
+            size_t off = (size_t)(item + b) * A.ybs + ((size_t)bl * P.out_ch + lane) * A.cols + cc;
             if (A.epilogue == FSWEEP_EPI_ABS)
               reinterpret_cast<T*>(A.y)[off] = abs_t(S[c].x, S[c].y);
             else
@@ -1118,8 +1135,10 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
   const long long groups_total = (long long)gridDim.x * (BLOCK / G);
   const long long gg = (long long)blockIdx.x * (BLOCK / G) + tid / G;
   const long long n_iter = (A.n_bins + groups_total - 1) / groups_total;
-  const int ncols_total = A.batch * A.cols;
-  const cx<T>* x = reinterpret_cast<const cx<T>*>(A.x);
+  // per-item launches (fsweep_op_t::per_item): blockIdx.y is the batch item, its columns are the block's whole batch
+  const int item = blockIdx.y;
+  const int ncols_total = (gridDim.y > 1 ? 1 : A.batch) * A.cols;
+  const cx<T>* x = reinterpret_cast<const cx<T>*>(A.x) + (size_t)item * A.xbs;
   const int slot_x = P.n_slots - 1;
   double lacc = 0.0;
 
@@ -1127,7 +1146,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
 
   Acc<T> acc;
   acc.sacc = sacc;
-  acc.gacc = reinterpret_cast<T*>(A.gacc);
+  acc.gacc = reinterpret_cast<T*>(A.gacc) + (size_t)item * P.acc_total;
   acc.tid = tid;
   acc.defer = reinterpret_cast<cx<T>*>(A.defer);
   acc.n_bins = A.n_bins;
@@ -1144,7 +1163,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
   };
 
   {
-    const Ctx<T> c0 = make_ctx<T>(P, A.bin_begin);
+    const Ctx<T> c0 = make_ctx<T>(P, A.bin_begin, item);
     stage_ops<T>(P, c0, lane, hc, gmask, tid, true);
   }
   for (long long it = 0; it < n_iter; ++it) {
@@ -1153,7 +1172,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
     if (!valid) bl = A.n_bins - 1;
     acc.valid = valid;
     acc.bl = bl;
-    const Ctx<T> ctx = make_ctx<T>(P, A.bin_begin + bl);
+    const Ctx<T> ctx = make_ctx<T>(P, A.bin_begin + bl, item);
     stage_ops<T>(P, ctx, lane, hc, gmask, tid, false);
     LU<T, G> lu;
     if (P.rec_n > 0) build_loop<T, G>(P, lane, lu, hc, tid);
@@ -1190,7 +1209,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
         if (epi_fused(A.epilogue)) {
           const bool inr = q < ncols_total;
           const T mag = abs_t(S[c].x, S[c].y);
-          const T ga = crit_rowdist<T, G>(A, mag, lane < P.out_ch, lane, P.out_ch, bl, inr ? q : ncols_total - 1, lane,
+          const T ga = crit_rowdist<T, G>(A, mag, lane < P.out_ch, lane, P.out_ch, bl, item + (inr ? q : ncols_total - 1), lane,
                                           valid && inr, lacc);
           if (inr && lane < P.out_ch && mag > T(0)) {
             const T r = ga * rcp_t(mag);
@@ -1198,7 +1217,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
           }
         } else if (q < ncols_total && lane < P.out_ch) {
           int b = q / A.cols, cc = q - b * A.cols;
-          size_t off = (size_t)b * A.gybs + ((size_t)bl * P.out_ch + lane) * A.cols + cc;
+          size_t off = (size_t)(item + b) * A.gybs + ((size_t)bl * P.out_ch + lane) * A.cols + cc;
           if (A.epilogue == FSWEEP_EPI_ABS) {
             T ga = __ldg(reinterpret_cast<const T*>(A.gy) + off);
             T mag = abs_t(S[c].x, S[c].y);
@@ -1228,7 +1247,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
           int q = q0 + c;
           if (q < ncols_total) {
             int b = q / A.cols, cc = q - b * A.cols;
-            st_cx(reinterpret_cast<cx<T>*>(A.gx) + (size_t)b * A.gxbs + ((size_t)bl * P.in_ch + lane) * A.cols + cc,
+            st_cx(reinterpret_cast<cx<T>*>(A.gx) + (size_t)(item + b) * A.gxbs + ((size_t)bl * P.in_ch + lane) * A.cols + cc,
                   g[c]);
           }
         }
@@ -1238,7 +1257,7 @@ __global__ void __launch_bounds__(BLOCK) fsweep_bwd_kernel(const __grid_constant
 
   // ---- block reduction of the thread-private accumulator columns: partial[block][i][row]
   __syncthreads();
-  T* partial = reinterpret_cast<T*>(A.partial) + (size_t)blockIdx.x * P.acc_per_lane * G;
+  T* partial = reinterpret_cast<T*>(A.partial) + ((size_t)item * gridDim.x + blockIdx.x) * P.acc_per_lane * G;
   for (int e = tid; e < P.acc_per_lane * G; e += BLOCK) {
     int i = e / G, row = e - i * G;
     T s = T(0);
@@ -1253,9 +1272,11 @@ struct FinalizeOp {
   int kind, n_out, n_in, K;
   int acc_mode, row_off, row_len, acc_off;
   void* grad;  // caller buffer or null
+  long long grad_is;  // per-item launches: elements between the gradients of consecutive items; 0: one set, summed over the items
 };
 struct FinalizeArgs {
   int n_ops, G, acc_per_lane, n_blocks;
+  int n_items, acc_total;  // per-item launches: partial rows are [item][block], gacc is [item][acc_total]; else n_items = 1
   const void* partial;
   const void* gacc;
   // fused criterion: blockIdx.y == n_ops sums the per-block squared-error sums into *loss (real T)
@@ -1270,9 +1291,9 @@ template <typename T>
 __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_constant__ FinalizeArgs F) {
   const int opi = blockIdx.y;
   if (opi == F.n_ops) {
-    if (F.loss == nullptr || blockIdx.x != 0 || threadIdx.x >= 32) return;
+    if (F.loss == nullptr || blockIdx.x != 0 || blockIdx.z != 0 || threadIdx.x >= 32) return;
     double s = 0.0;
-    for (int b = threadIdx.x; b < F.n_blocks; b += 32) s += F.loss_partial[b];
+    for (int b = threadIdx.x; b < F.n_blocks * F.n_items; b += 32) s += F.loss_partial[b];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (threadIdx.x == 0) *reinterpret_cast<T*>(F.loss) = (T)(F.crit_scale * s);
@@ -1280,6 +1301,11 @@ __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_const
   }
   const FinalizeOp& op = F.ops[opi];
   if (op.grad == nullptr || (op.acc_mode != ACC_SMEM && op.acc_mode != ACC_GLOBAL)) return;
+  // per-item op: this z-slice sums its own item's rows; shared op: slice 0 sums the rows of every item
+  const bool own = op.grad_is != 0;
+  if (!own && blockIdx.z != 0) return;
+  const int row0 = own ? (int)blockIdx.z * F.n_blocks : 0, rows = own ? F.n_blocks : F.n_blocks * F.n_items;
+  const int it0 = own ? (int)blockIdx.z : 0, its = own ? 1 : F.n_items;
   const bool diag = !(op.kind == FSWEEP_OP_GAIN || op.kind == FSWEEP_OP_SOS || op.kind == FSWEEP_OP_DELAY);
   const int total = op.n_out * op.row_len;
   const int lane = threadIdx.x & 31;
@@ -1290,11 +1316,11 @@ __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_const
     if (op.acc_mode == ACC_SMEM) {
       const T* p = reinterpret_cast<const T*>(F.partial) + (size_t)(op.row_off + i) * F.G + row;
       const size_t stride = (size_t)F.acc_per_lane * F.G;
-      for (int b = lane; b < F.n_blocks; b += 32) s += (double)p[(size_t)b * stride];
+      for (int b = lane; b < rows; b += 32) s += (double)p[(size_t)(row0 + b) * stride];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     } else {
-      s = (double)reinterpret_cast<const T*>(F.gacc)[op.acc_off + e];
+      for (int t = 0; t < its; ++t) s += (double)reinterpret_cast<const T*>(F.gacc)[(size_t)(it0 + t) * F.acc_total + op.acc_off + e];
     }
     if (lane != 0) continue;
     // map (row, i) -> index in the caller's layout
@@ -1311,6 +1337,7 @@ __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_const
     } else {
       o = (size_t)row * op.n_in + i;
     }
+    o += (size_t)it0 * op.grad_is;
     if (op.kind == FSWEEP_OP_DELAY || op.kind == FSWEEP_OP_PDELAY)
       reinterpret_cast<double*>(op.grad)[o] = s;
     else
@@ -1326,7 +1353,7 @@ __global__ void __launch_bounds__(128) fsweep_finalize_kernel(const __grid_const
 constexpr int FIN2_WARPS = 32;  // 24 independent loads per lane for 751 partial rows: three batches of 8 in flight
 
 template <typename T>
-__device__ __forceinline__ void finalize_store(const FinalizeOp& op, int row, int i, double s) {
+__device__ __forceinline__ void finalize_store(const FinalizeOp& op, int row, int i, double s, int item) {
   const bool diag = !(op.kind == FSWEEP_OP_GAIN || op.kind == FSWEEP_OP_SOS || op.kind == FSWEEP_OP_DELAY);
   size_t o;
   if (op.kind == FSWEEP_OP_SOS || op.kind == FSWEEP_OP_PSOS) {
@@ -1337,6 +1364,7 @@ __device__ __forceinline__ void finalize_store(const FinalizeOp& op, int row, in
   } else {
     o = (size_t)row * op.n_in + i;
   }
+  o += (size_t)item * op.grad_is;
   if (op.kind == FSWEEP_OP_DELAY || op.kind == FSWEEP_OP_PDELAY)
     reinterpret_cast<double*>(op.grad)[o] = s;
   else
@@ -1349,9 +1377,9 @@ __global__ void __launch_bounds__(32 * FIN2_WARPS) fsweep_finalize_v2_kernel(con
   const int opi = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (opi == F.n_ops) {  // fused criterion: sum of the per-block squared-error sums
-    if (F.loss == nullptr || blockIdx.x != 0) return;
+    if (F.loss == nullptr || blockIdx.x != 0 || blockIdx.z != 0) return;
     double s = 0.0;
-    for (int b = threadIdx.x; b < F.n_blocks; b += 32 * FIN2_WARPS) s += F.loss_partial[b];
+    for (int b = threadIdx.x; b < F.n_blocks * F.n_items; b += 32 * FIN2_WARPS) s += F.loss_partial[b];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) red[warp][0] = s;
@@ -1365,6 +1393,11 @@ __global__ void __launch_bounds__(32 * FIN2_WARPS) fsweep_finalize_v2_kernel(con
   }
   const FinalizeOp& op = F.ops[opi];
   if (op.grad == nullptr || (op.acc_mode != ACC_SMEM && op.acc_mode != ACC_GLOBAL)) return;  // uniform in the block
+  // per-item op: this z-slice sums its own item's rows; shared op: slice 0 sums the rows of every item
+  const bool own = op.grad_is != 0;
+  if (!own && blockIdx.z != 0) return;
+  const int row0 = own ? (int)blockIdx.z * F.n_blocks : 0, rows = own ? F.n_blocks : F.n_blocks * F.n_items;
+  const int it0 = own ? (int)blockIdx.z : 0, its = own ? 1 : F.n_items;
   const int total = op.n_out * op.row_len;
   const size_t stride = (size_t)F.acc_per_lane * F.G;
   for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {  // uniform trip count
@@ -1376,7 +1409,7 @@ __global__ void __launch_bounds__(32 * FIN2_WARPS) fsweep_finalize_v2_kernel(con
       if (live) {
         const T* p = reinterpret_cast<const T*>(F.partial) + (size_t)(op.row_off + i) * F.G + row;
 #pragma unroll 8
-        for (int b = warp; b < F.n_blocks; b += FIN2_WARPS) s += (double)p[(size_t)b * stride];
+        for (int b = warp; b < rows; b += FIN2_WARPS) s += (double)p[(size_t)(row0 + b) * stride];
       }
       red[warp][lane] = s;
       __syncthreads();
@@ -1387,9 +1420,10 @@ __global__ void __launch_bounds__(32 * FIN2_WARPS) fsweep_finalize_v2_kernel(con
       }
       __syncthreads();  // red is reused by the next trip
     } else if (live) {
-      s = (double)reinterpret_cast<const T*>(F.gacc)[op.acc_off + (size_t)row * op.row_len + i];
+      for (int t = 0; t < its; ++t)
+        s += (double)reinterpret_cast<const T*>(F.gacc)[(size_t)(it0 + t) * F.acc_total + op.acc_off + (size_t)row * op.row_len + i];
     }
-    if (warp == 0 && live) finalize_store<T>(op, row, i, s);
+    if (warp == 0 && live) finalize_store<T>(op, row, i, s, it0);
   }
 }
 
@@ -1587,6 +1621,7 @@ struct LaunchCfg {
   int grid;
   size_t smem;
   cudaStream_t stream;
+  int items = 1;  // per-item launches of the generic kernels: grid.y
 };
 template <int G>
 cudaError_t launch_fwd(int dtype, int cc, const LaunchCfg& cfg, const ProgK& P, const SweepArgs& A);

@@ -173,16 +173,31 @@ class DSP(nn.Module):
         if ext_param is None:
             return self.param
         with torch.no_grad():
-            self.assign_value(ext_param)
+            # one parameter set per batch item (see _emit_items): the reference's per-item loop leaves the last one behind
+            self.assign_value(ext_param[-1] if self._per_item(ext_param) else ext_param)
         return ext_param
+
+    def _per_item(self, param) -> bool:
+        """`param` carries one parameter set PER BATCH ITEM: a leading batch axis in front of the module's own shape.
+        The reference has no such call — its NN-in-the-loop examples run the module once per item
+        (examples/e7_biquad_nn.py:149-156, e4_recursion_nn.py:243-250, "the only way to process batches larger than
+        1") — here the whole batch is ONE launch (SURVEY.md section 8f rank 3)."""
+        return (torch.is_tensor(param) and param is not self.param and param.dim() == self.param.dim() + 1
+                and tuple(param.shape[1:]) == tuple(self.param.shape))
 
     def _sweep(self, x, param):
         prog = sweep.Program(self.nfft, self._alias_db, x.dtype, x.device)
-        self._emit(prog, param)
+        if self._per_item(param):
+            self._emit_items(prog, param)
+        else:
+            self._emit(prog, param)
         return prog.run(x)
 
     def _lower(self, prog, ext_param=None):
         param = self._select_param(ext_param)
+        if self._per_item(param):
+            self._emit_items(prog, param)
+            return
         if param is self.param and not param.requires_grad:
             # frozen parameters: the mapped coefficient tensor is reused until the parameter is
             # written again (assign_value / load_state_dict bump `_version`); the optimizer never
@@ -198,6 +213,30 @@ class DSP(nn.Module):
                 self._coef_cache = (key, prog.items_target()[-1])
             return
         self._emit(prog, param)
+
+    def _emit_items(self, prog, params):
+        """Lower `params` (B, *param.shape) as ONE op whose coefficient slot holds B sets (fsweep_op_t::per_item): batch
+        item b of the signal is filtered with set b.  The generic route maps / designs the sets one after the other
+        (small parameter-sized launches) and stacks them; subclasses whose design treats its sections independently fold
+        the batch into the section axis instead (_items_folded)."""
+        if self._items_folded(prog, params):
+            return
+        tgt = prog.items_target()
+        n0 = len(tgt)
+        leaves = []
+        for i in range(params.shape[0]):
+            self._emit(prog, params[i])
+            if len(tgt) != n0 + 1 or tgt[-1][0] != "leaf":
+                raise sweep._lib.Unsupported(sweep._lib.E_UNSUPPORTED, f"{type(self).__name__} does not lower to a "
+                                             "single op: per-item parameters are not supported for it")
+            leaves.append(tgt.pop())
+        op = leaves[0][1]
+        if any(l[1][:4] != op[:4] for l in leaves):
+            raise sweep._lib.Unsupported(sweep._lib.E_UNSUPPORTED, "per-item parameters lower to different ops")
+        prog.leaf_items(op, torch.stack([l[2] for l in leaves]))
+
+    def _items_folded(self, prog, params) -> bool:
+        return False
 
     def _emit(self, prog, param):
         raise NotImplementedError
@@ -495,6 +534,32 @@ class _SectionFilter(Filter):
         module (Biquad low-/high-pass with its stock map); None otherwise."""
         return None
 
+    _fold_axis = None  # axis of the parameter that indexes the sections, for classes whose stock design treats them independently
+
+    def _stock_design(self) -> bool:
+        """The module still uses its stock map / tap formulas (subclasses that can fold per-item parameters say when)."""
+        return False
+
+    def _items_folded(self, prog, params) -> bool:
+        """Per-item parameter sets of a section cascade whose design is elementwise over the sections (Biquad, SVF with
+        their stock maps): the batch axis is folded into the section axis, so ONE design call yields the packed
+        coefficients of every item, [B*K][...] = [B][K][...]."""
+        ax = self._fold_axis
+        if ax is None or self._overridden() or not self._stock_design():
+            return False
+        B = params.shape[0]
+        moved = params.movedim(0, ax)  # (..., B, K, ...)
+        flat = moved.reshape(*moved.shape[:ax], B * moved.shape[ax + 1], *moved.shape[ax + 2:])
+        coef = self._fused_design(flat)
+        if coef is None:
+            b, a = self._taps(self.map(self._up(flat)))
+            coef = sweep.pack_sections(b, a, self._parallel, None)
+        K = coef.shape[0] // B
+        coef = coef.view(B, K, *coef.shape[1:])
+        prog.leaf_items((OP_PSOS if self._parallel else OP_SOS, int(self.output_channels), int(self.input_channels), K,
+                         0, 0, 0, 0), coef)
+        return True
+
     def _overridden(self):
         return (self.freq_response is not self._stock_freq_response
                 or type(self).get_poly_coeff is not _SectionFilter.get_poly_coeff)
@@ -566,9 +631,13 @@ class Biquad(_SectionFilter):
     def check_param_shape(self):
         assert len(self.size) == 4, "Parameter size must be 4D, for 3D (parallel) biquads use parallelBiquad module."
 
+    _fold_axis = 0
+
+    def _stock_design(self):
+        return getattr(self.map, "__func__", None) is Biquad._bounded_map and type(self)._taps is Biquad._taps
+
     def _fused_design(self, param):
-        stock = (getattr(self.map, "__func__", None) is Biquad._bounded_map and type(self)._taps is Biquad._taps
-                 and self.filter_type in ("lowpass", "highpass"))
+        stock = self._stock_design() and self.filter_type in ("lowpass", "highpass")
         if not (stock and param.is_cuda and param.dtype in (torch.float32, torch.float64)
                 and sweep._BACKEND.name == "cuda" and os.environ.get("FLAMO_B200_FUSED_DESIGN", "1") == "1"):
             return None
@@ -714,10 +783,15 @@ class SVF(_SectionFilter):
         m = self._mix(p[2:], r)
         return f, R, m[0], m[1], m[2]
 
+    _fold_axis = 1
+
+    def _stock_design(self):
+        return (getattr(self.map, "__func__", None) is SVF.map_param2svf and type(self)._taps is SVF._taps
+                and type(self)._mix is SVF._mix and type(self).param2freq is SVF.param2freq
+                and type(self).param2R is SVF.param2R)
+
     def _fused_design(self, param):
-        stock = (getattr(self.map, "__func__", None) is SVF.map_param2svf and type(self)._taps is SVF._taps
-                 and type(self)._mix is SVF._mix and type(self).param2freq is SVF.param2freq
-                 and type(self).param2R is SVF.param2R and self.filter_type is None)
+        stock = self._stock_design() and self.filter_type is None
         if not (stock and param.is_cuda and param.dtype in (torch.float32, torch.float64)
                 and sweep._BACKEND.name == "cuda" and os.environ.get("FLAMO_B200_FUSED_DESIGN", "1") == "1"):
             return None

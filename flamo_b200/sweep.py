@@ -307,6 +307,16 @@ class Program:
         item = ("leaf", (kind, int(n_out), int(n_in), int(K), flags, 0, 0, 0), coef)
         (self._chain if self._chain is not None else self.items).append(item)
 
+    def leaf_items(self, op: tuple, coefs: torch.Tensor):
+        """One op with ONE COEFFICIENT SET PER BATCH ITEM (fsweep_op_t::per_item; hyper-conditioning through a batched
+        ext_param): `op` is the tuple leaf() built for a single set, coefs is (B, *set shape).  The launch runs the
+        generic kernels with a grid slice per item; the gradient comes back per item, (B, *set shape)."""
+        kind, n_out, n_in, K, flags = op[:5]
+        want = kind in (OP_GAIN, OP_PGAIN, OP_SOS, OP_PSOS, OP_TABLE, OP_PTABLE) or not (flags & F_ISINT)
+        flags = (flags & ~F_GRAD) | (F_GRAD if (coefs.requires_grad and torch.is_grad_enabled() and want) else 0)
+        item = ("leaf", (kind, n_out, n_in, K, flags, 0, 0, 1), coefs)
+        (self._chain if self._chain is not None else self.items).append(item)
+
     def items_target(self) -> list:
         """The list new leaves are appended to (the open recursion chain, or the top level)."""
         return self._chain if self._chain is not None else self.items
@@ -397,6 +407,22 @@ class Program:
         cdtype = cdtype or self.cdtype
         return _get_plan(ops, self.nfft, self.alias_decay_db, _lib.C64 if cdtype == torch.complex64 else _lib.C128)
 
+    @staticmethod
+    def _per_item_batch(ops, coefs, x4):
+        """Per-item launches: every per-item slot must hold one set per batch item of the signal (a single-item signal
+        is shared by all sets, like the reference examples' `z[0].unsqueeze(0)`).  Returns the signal to launch on."""
+        sizes = {c.shape[0] for o, c in zip([o for o in ops if o[0] != OP_RECURSION], coefs) if o[7]}
+        if not sizes:
+            return x4
+        if len(sizes) != 1:
+            raise ValueError(f"per-item parameters with different batch sizes in one program: {sorted(sizes)}")
+        n = sizes.pop()
+        if x4.shape[0] == 1 and n > 1:
+            return x4.expand(n, *x4.shape[1:])
+        if x4.shape[0] != n:
+            raise ValueError(f"{n} per-item parameter sets for a signal with {x4.shape[0]} batch items")
+        return x4
+
     def _check_signal(self, ops, x4, bin_begin):
         """Backstop in front of every launch (the kernels trust the plan's widths): the signal must carry the channels
         the program's first op reads and only bins that exist."""
@@ -444,6 +470,7 @@ class Program:
             io_dtype = x4.dtype
             ex = torch.complex128 if (io_dtype == torch.complex128 or _wants_f64(ops)) else torch.complex64
             _, coefs, _ = self.flatten_segment(payload, ex)
+            x4 = self._per_item_batch(ops, coefs, x4)
             code = _lib.C64 if ex == torch.complex64 else (_lib.C128 | (_lib.DT_GRAD32 if ex != io_dtype else 0))
             plan = _get_plan(ops, self.nfft, self.alias_decay_db, code)
             x4 = SweepFunction.apply(x4.to(ex), plan, ops, epi, bin_begin, n_out, *coefs)
@@ -466,6 +493,8 @@ class Program:
         if len(segs) != 1 or segs[0][0] != "sweep":
             return None
         ops, _, n_out = self.flatten_segment(segs[0][1])
+        if any(o[7] for o in ops if o[0] != OP_RECURSION):
+            return None  # per-item parameter sets: the unfused path
         ex = torch.complex128 if (x.dtype == torch.complex128 or _wants_f64(ops)) else torch.complex64
         _, coefs, _ = self.flatten_segment(segs[0][1], ex)
         B, M = x.shape[0], x.shape[1]

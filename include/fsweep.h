@@ -137,7 +137,12 @@ typedef struct fsweep_op {
   uint32_t flags;
   int32_t n_ff;       /* RECURSION only                                                    */
   int32_t n_fb;       /* RECURSION only                                                    */
-  int32_t reserved;
+  int32_t per_item;   /* != 0: the slot holds ONE COEFFICIENT SET PER BATCH ITEM, [batch][numel] (hyper-conditioning:
+                         flamo's NN-in-the-loop examples call the module once per item with ext_param,
+                         examples/e7_biquad_nn.py:149-156, e4_recursion_nn.py:243-250; here item b of x meets set b
+                         inside ONE launch).  A plan with such an op runs the generic kernels with one grid slice per
+                         item; its gradient buffer is [batch][numel] as well, the gradients of the other slots are
+                         summed over the items as usual.  0: one set for the whole batch.                  */
 } fsweep_op_t;
 
 typedef struct fsweep_plan fsweep_plan_t; /* opaque, immutable after create, host memory only */

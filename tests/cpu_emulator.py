@@ -76,6 +76,12 @@ def _apply(op, H, x):
 
 
 def _run(ops, coefs, x, bin_begin, nfft, alias, epilogue):
+    leaf = [o for o in ops if o[0] != OP_RECURSION]
+    if any(o[7] for o in leaf):
+        # per-item coefficient sets (fsweep_op_t::per_item): batch item b meets set b — one plain run per item
+        plain = tuple(tuple(o[:7]) + (0,) for o in ops)
+        return torch.cat([_run(plain, [c[b] if o[7] else c for o, c in zip(leaf, coefs)], x[b:b + 1], bin_begin, nfft,
+                               alias, epilogue) for b in range(x.shape[0])])
     lng = -abs(alias) / nfft / 20.0 * math.log(10.0)
     k = torch.arange(bin_begin, bin_begin + x.shape[1])
     x = x.to(torch.complex128)
