@@ -17,6 +17,7 @@
 #define FSWEEP_CTA_TC_DEFAULT true  // FSWEEP_CTA_TC=0 selects the SIMT elimination instead of the tensor-core one
 #endif
 #include "fsweep_stream.cuh"
+#include "fsweep_tpr.cuh"
 
 using namespace fsweep;
 
@@ -469,6 +470,26 @@ bool use_tpc(const fsweep_plan* p, int64_t n_bins) {
   if (!p->tpc_np || p->tpb_force) return false;
   return p->tpc_force || n_bins >= TPC_MIN_BINS;
 }
+// Register-matrix variant (fsweep_tpr.cuh) of the compact kernels: the default for loop widths 5..8; FSWEEP_TPC_V1=1 (tests,
+// A/B measurements) keeps the shared-memory-matrix kernels of fsweep_tpc.cuh.  Read per call.
+bool use_tpr(const fsweep_plan* p) {
+  if (p->tpc_np != 8) return false;
+  const char* v1 = getenv("FSWEEP_TPC_V1");
+  return !(v1 && v1[0] == '1');
+}
+// one block of TPR_BLOCK threads per SM, all bins in one wave when they fit
+int tpr_grid(fsweep_plan* p, int64_t n_bins, cudaError_t* err) {
+  *err = cudaSuccess;
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (p->num_sms == 0) {
+      int dev = 0;
+      if ((*err = cudaGetDevice(&dev)) != cudaSuccess) return 0;
+      if ((*err = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return 0;
+    }
+  }
+  return (int)std::min<int64_t>((n_bins + TPR_BLOCK - 1) / TPR_BLOCK, p->num_sms);
+}
 int tpc_grid(int64_t n_bins) { return (int)std::min<int64_t>((n_bins + TPC_BLOCK - 1) / TPC_BLOCK, MAX_GRID); }
 
 int cc_of(int64_t ncols) { return ncols == 1 ? 1 : 4; }
@@ -641,6 +662,7 @@ extern "C" const char* fsweep_plan_kernel_family(const fsweep_plan_t* plan, int6
   if (plan->cta && plan->cta_tc) return backward ? "fsweep_cta_kernel<bwd,tc> (tcgen05 LU)" : "fsweep_cta_kernel<fwd,tc> (tcgen05 LU)";
   if (plan->cta) return backward ? "fsweep_cta_kernel<bwd>" : "fsweep_cta_kernel<fwd>";
   if (plan->stream) return backward ? "fsweep_stream_kernel<bwd> (batch*cols a power of two <= 16)" : "fsweep_stream_kernel<fwd> (batch*cols a power of two <= 16)";
+  if (use_tpc(plan, n_bins) && use_tpr(plan)) return backward ? "fsweep_tpr_kernel<bwd> (tpc family, matrix in registers)" : "fsweep_tpr_kernel<fwd> (tpc family, matrix in registers)";
   if (use_tpc(plan, n_bins)) return backward ? "fsweep_tpc_kernel<NP,bwd>" : "fsweep_tpc_kernel<NP,fwd>";
   if (use_tpb(plan, n_bins, backward != 0)) return backward ? "fsweep_tpb_bwd_kernel" : "fsweep_tpb_fwd_kernel";
   if (plan->loop_fast) return backward ? "fsweep_loop_bwd_kernel" : "fsweep_loop_fwd_kernel";
@@ -793,6 +815,9 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
       cfg.grid = (int)std::min<int64_t>(tiles, (int64_t)std::max(1, bps) * std::max(1, plan->num_sms ? plan->num_sms : 148));
       e = launch_stream(false, stream_tma, cfg.grid, ssmem, cfg.stream, P, SI, A, plan->G);
     }
+  } else if (use_tpc(plan, n_bins) && use_tpr(plan)) {
+    cfg.grid = tpr_grid(plan, n_bins, &e);
+    if (e == cudaSuccess) e = launch_tpr(plan->tpc_np, false, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
   } else if (use_tpc(plan, n_bins)) {
     cfg.grid = tpc_grid(n_bins);
     e = launch_tpc(plan->tpc_np, false, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
@@ -984,6 +1009,9 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
                                         grid_cap(n_bins, plan->G));
       e = launch_stream(true, stream_tma, cfg.grid, ssmem, st, P, SI, A, plan->G);
     }
+  } else if (use_tpc(plan, n_bins) && use_tpr(plan)) {
+    cfg.grid = tpr_grid(plan, n_bins, &e);
+    if (e == cudaSuccess) e = launch_tpr(plan->tpc_np, true, cfg.grid, st, P, plan->loop, A, plan->G);
   } else if (use_tpc(plan, n_bins)) {
     cfg.grid = tpc_grid(n_bins);
     e = launch_tpc(plan->tpc_np, true, cfg.grid, st, P, plan->loop, A, plan->G);

@@ -73,12 +73,14 @@ def test_fused_equals_unfused_c128(name, kind):
             assert grad_err(b.cpu().numpy() / 2.5, a.cpu().numpy()) <= gtol
 
 
-@pytest.mark.parametrize("path", ["generic", "loop", "tpb", "tpc"])
+@pytest.mark.parametrize("path", ["generic", "loop", "tpb", "tpc", "tpc_v1"])
 @pytest.mark.parametrize("kind", [_lib.CRIT_MSE, _lib.CRIT_MSE_CHSUM])
 @pytest.mark.parametrize("B", [1, 5])
 def test_fused_on_every_kernel_family(path, kind, B, monkeypatch):
-    if path in ("tpb", "tpc"):
+    if path in ("tpb", "tpc", "tpc_v1"):
         monkeypatch.setenv("FSWEEP_FORCE_TPB" if path == "tpb" else "FSWEEP_FORCE_TPC", "1")
+        if path == "tpc_v1":
+            monkeypatch.setenv("FSWEEP_TPC_V1", "1")
     else:
         monkeypatch.setenv("FSWEEP_DISABLE_TPB", "1")
     if path == "generic":

@@ -109,10 +109,10 @@ def _family_combos():
     out = []
     for name in FDN_CASES:
         for dtype in (torch.float32, torch.float64):
-            for path in ("generic", "loop", "tpb", "tpc"):
-                if path in ("tpb", "tpc") and (dtype != torch.float32 or name in ("fdn16", "fdn32")):
+            for path in ("generic", "loop", "tpb", "tpc", "tpc_v1"):
+                if path in ("tpb", "tpc", "tpc_v1") and (dtype != torch.float32 or name in ("fdn16", "fdn32")):
                     continue
-                if path == "tpc" and name == "recursion_filters":
+                if path in ("tpc", "tpc_v1") and name == "recursion_filters":
                     continue
                 out.append(pytest.param(name, dtype, path, id=f"{path}-{str(dtype).split('.')[-1]}-{name}"))
     return out
@@ -122,11 +122,14 @@ def _family_combos():
 def test_alternative_kernel_paths_on_fdn_cases(name, dtype, path, monkeypatch):
     """FDN-shaped programs can run on four kernel families: the generic step-table interpreter
     (fsweep_kernels.cuh), the row-distributed loop kernels (fsweep_loop.cuh) and, for widths <= 8 in float32 and
-    enough bins, the unrolled (fsweep_tpb.cuh) and the compact (fsweep_tpc.cuh) thread-per-bin kernels.  Each
-    family is forced here in turn; all must agree with the oracle."""
+    enough bins, the unrolled (fsweep_tpb.cuh) and the compact thread-per-bin kernels — "tpc": the default of that
+    family, the matrix in registers for widths 5..8 (fsweep_tpr.cuh); "tpc_v1": the matrix in shared memory
+    (fsweep_tpc.cuh, FSWEEP_TPC_V1=1).  Each family is forced here in turn; all must agree with the oracle."""
     monkeypatch.setenv("FLAMO_B200_PRECISION", "float32")  # the float32 kernels themselves, width 16 / 32 included
-    if path in ("tpb", "tpc"):
+    if path in ("tpb", "tpc", "tpc_v1"):
         monkeypatch.setenv("FSWEEP_FORCE_TPB" if path == "tpb" else "FSWEEP_FORCE_TPC", "1")
+        if path == "tpc_v1":
+            monkeypatch.setenv("FSWEEP_TPC_V1", "1")
     else:
         monkeypatch.setenv("FSWEEP_DISABLE_TPB", "1")
     if path == "generic":
@@ -334,3 +337,53 @@ def test_streaming_table_kernels(B, cols, tma, monkeypatch):
     for u, v in zip(ga, go):
         u, v = u.cpu().numpy(), v.numpy()
         assert np.abs(u - v).max() <= 1e-3 * np.abs(v).max()
+
+
+@pytest.mark.parametrize("scale", [0.3, 2.0, 6.0])
+def test_register_matrix_kernel_on_loops_that_need_row_interchanges(scale, monkeypatch):
+    """fsweep_tpr.cuh eliminates without row interchanges as long as every diagonal pivot is at least a quarter of the
+    largest candidate below it — always the case for an FDN (orthogonal feedback, |D| < 1) — and finishes a bin that
+    violates this with partial pivoting in a slow path.  A general feedback matrix with entries of size `scale` makes
+    that path run (numpy on these matrices: an interchange is wanted at > 30 % of the bins for scale >= 2, at none for
+    0.3): the results must agree with the float64 oracle as well as those of the shared-memory kernel
+    (FSWEEP_TPC_V1=1), which pivots at every step."""
+    from flamo_b200 import workloads as W
+    from flamo_b200.processor import dsp, system
+    from oracle import flamo_oracle as O
+
+    nfft, N = 65536, 8
+    g = torch.Generator().manual_seed(5)
+    Wfb = (scale * torch.randn(N, N, generator=g, dtype=torch.float64)).tolist()
+    desc = ("Series", [
+        ("Gain", dict(size=(N, 1), requires_grad=True)),
+        ("Recursion", ("parallelDelay", dict(size=(N,), max_len=3000, isint=True, requires_grad=False),
+                       {"delay_samples": [float(d) for d in W.fdn_delays(N)]}),
+         ("Gain", dict(size=(N, N), requires_grad=True), {"assign": Wfb})),
+        ("Gain", dict(size=(1, N), requires_grad=True)),
+    ])
+    monkeypatch.setenv("FSWEEP_FORCE_TPC", "1")
+    M = nfft // 2 + 1
+    X = C.make_input(2, M, 1, None)
+    errs = {}
+    for v1 in ("0", "1"):
+        monkeypatch.setenv("FSWEEP_TPC_V1", v1)
+        saved = dict(sweep._PLANS)
+        sweep._PLANS.clear()
+        try:
+            torch.manual_seed(3)
+            model = W.build(desc, dsp, system, nfft, 30.0, dtype=torch.float32, device="cuda")
+            ps = [p for p in model.parameters() if p.requires_grad]
+            Y = model(X.to(torch.complex64).cuda())
+            C.golden_loss(Y).backward()
+            torch.cuda.synchronize()
+        finally:
+            sweep._PLANS.clear()
+            sweep._PLANS.update(saved)
+        p64 = [p.detach().cpu().double().requires_grad_(p.requires_grad) for p in model.parameters()]
+        Yo = O.forward(O.from_desc(desc), X, p64, nfft, 30.0)
+        go = torch.autograd.grad(C.golden_loss(Yo), [p for p in p64 if p.requires_grad])
+        errs[v1] = (rel_err(np.abs(Y.detach().cpu().numpy()), np.abs(Yo.detach().numpy())),
+                    max(grad_err(p.grad.cpu().numpy(), r.numpy()) for p, r in zip(ps, go)))
+    # (an arbitrary loop matrix is not well conditioned at every bin: the bar is the pivot-every-step kernel's own error)
+    assert errs["0"][0] <= max(1e-4, 3 * errs["1"][0]), errs
+    assert errs["0"][1] <= max(1e-3, 3 * errs["1"][1]), errs
