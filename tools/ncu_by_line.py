@@ -23,7 +23,12 @@ def main():
     kname = rows[0][1]
     hdr = rows[1]
     ia, ism, isrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
-    sass = [(r[isrc].strip(), int(r[ia]), int(r[ism])) for r in rows[2:] if len(r) > ia and r[0].startswith("0x")]
+    body = rows[2:]
+    for i, r in enumerate(body):  # several launches matched: the report repeats the table per launch — take the first
+        if r and r[0] == "Kernel Name":
+            body = body[:i]
+            break
+    sass = [(r[isrc].strip(), int(r[ia]), int(r[ism])) for r in body if len(r) > ia and r[0].startswith("0x")]
     # line table
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=td, capture_output=True)
