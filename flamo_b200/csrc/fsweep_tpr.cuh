@@ -25,14 +25,16 @@
 namespace fsweep {
 
 constexpr int TPR_BLOCK = 352;      // 11 warps; 65536 / 352 = 186 -> 184 registers per thread
+constexpr int TPR_SS = TPR_BLOCK + 1;  // accumulator row stride (odd: a thread summing ROW s walks banks s, s + 1, ... — no rotation needed)
 constexpr float TPR_TAU2 = 0.0625f;  // interchange when |a_kk|^2 < tau^2 max_r |a_rk|^2, tau = 0.25
 
 template <int NP>
 struct TprSmem {
   static constexpr int S_PRE = NP * NP, S_POST = NP * NP + NP, S_DIAG = NP * NP + 2 * NP, S_TOTAL = NP * NP + 3 * NP;
-  // [stage: S_TOTAL][BLOCK] float | [dslot | yslot | vslot : NP][BLOCK] float2 | red [4][S_TOTAL] float
-  static constexpr size_t bytes =
-      (size_t)S_TOTAL * TPR_BLOCK * 4 + (size_t)3 * NP * TPR_BLOCK * 8 + (size_t)4 * S_TOTAL * 4;
+  // [stage: S_TOTAL][TPR_SS] float | [dslot | yslot | vslot : NP][BLOCK] float2 | red [4][S_TOTAL] float
+  static constexpr size_t stage_bytes = (size_t)S_TOTAL * TPR_SS * 4;
+  static_assert(stage_bytes % 8 == 0, "float2 arrays follow the accumulators");
+  static constexpr size_t bytes = stage_bytes + (size_t)3 * NP * TPR_BLOCK * 8 + (size_t)4 * S_TOTAL * 4;
 };
 
 // Finish P A = L U from step k0 on with full partial pivoting (same conventions as TpcMat::factor: full row interchanges,
@@ -96,10 +98,14 @@ __global__ void __launch_bounds__(TPR_BLOCK, 1) fsweep_tpr_kernel(const __grid_c
   __shared__ __align__(16) float wfb[NP * NP];
   __shared__ float wpre[NP], wpost[NP];
   __shared__ __align__(8) uint64_t wbar;
+  __shared__ int sdi[NP];     // integer-delay fast path: the delays in samples ...
+  __shared__ float smag[NP];  // ... and gamma^delay (bin-invariant)
   const int tid = threadIdx.x;
   const int N = P.rec_n;
-  float* stage = reinterpret_cast<float*>(tpr_raw) + tid;  // slot s at stage[s * TPR_BLOCK]
-  float2* dslot = reinterpret_cast<float2*>(tpr_raw + (size_t)S_TOTAL * TPR_BLOCK * 4) + tid;  // entry i at [i * TPR_BLOCK]
+  const OpK& ffop = P.ops[L.ff_begin];
+  bool fastd;
+  float* stage = reinterpret_cast<float*>(tpr_raw) + tid;  // slot s at stage[s * TPR_SS]
+  float2* dslot = reinterpret_cast<float2*>(tpr_raw + SM::stage_bytes) + tid;  // entry i at [i * TPR_BLOCK]
   float2* yslot = dslot + NP * TPR_BLOCK;
   float2* vslot = yslot + NP * TPR_BLOCK;
   {
@@ -123,21 +129,56 @@ __global__ void __launch_bounds__(TPR_BLOCK, 1) fsweep_tpr_kernel(const __grid_c
       wpre[tid] = tid < N ? __ldg(reinterpret_cast<const float*>(P.ops[L.pre].coef) + tid) : 0.f;
       wpost[tid] = tid < N ? __ldg(reinterpret_cast<const float*>(P.ops[L.post].coef) + tid) : 0.f;
     }
-    __syncthreads();
+    // The usual FDN chain is ONE parallelDelay with integer delays: gamma^d does not depend on the bin and the phase index
+    // (k d) mod nfft fits 32-bit integer arithmetic — no float64 range reduction, no expf per bin and channel.  One thread
+    // per channel prepares (d, gamma^d); the block agrees on the path with the barrier's vote.
+    int my_ok = 1;
+    if (tid >= 32 && tid < 32 + NP) {
+      const int m = tid - 32;
+      const bool base = L.n_ff == 1 && ffop.kind == FSWEEP_OP_PDELAY && (ffop.flags & FSWEEP_F_ISINT) != 0 &&
+                        P.nfft >= 1024 && P.nfft < (1 << 24);
+      double dd = 0.0;
+      if (base && m < N) dd = rint(__ldg(reinterpret_cast<const double*>(ffop.coef) + m));
+      const bool ok = base && dd >= 0.0 && dd * (double)(A.bin_begin + A.n_bins) < 2147483648.0;
+      sdi[m] = ok ? (int)dd : 0;
+      smag[m] = (ok && m < N) ? exp_t((float)(P.lng * dd)) : 0.f;
+      my_ok = ok ? 1 : 0;
+    }
+    fastd = __syncthreads_and(my_ok) != 0;  // (also publishes the shared tables and the barrier's initialisation)
     if (bulk) mbar_wait(&wbar, 0);
   }
 
   const int ncols_total = A.batch * A.cols;
   const cx<float>* x = reinterpret_cast<const cx<float>*>(A.x);
   double lacc = 0.0;
-  const OpK& ffop = P.ops[L.ff_begin];
   const bool want_ff = BWD && L.n_ff == 1 && ffop.acc_mode == ACC_SMEM;
   const bool ff_delay = ffop.kind == FSWEEP_OP_PDELAY;
   bool first = true;  // this thread's accumulators have not been written yet
 
   for (long long bl = (long long)blockIdx.x * TPR_BLOCK + tid; bl < A.n_bins; bl += (long long)gridDim.x * TPR_BLOCK) {
     const Ctx<float> ctx = make_ctx<float>(P, A.bin_begin + bl);
-    // ---- diagonal chain D (runtime loop over the channels: one copy of the response code)
+    // the first column's input (and target) are requested now: their latency hides behind the chain and the elimination
+    const cx<float> xv0 = ld_cx(x + (size_t)bl * A.cols);
+    const float tg0 = epi_fused(A.epilogue) ? __ldg(reinterpret_cast<const float*>(A.tgt) + bl) : 0.f;
+    // ---- diagonal chain D
+    if (fastd) {
+      const unsigned kk = (unsigned)(A.bin_begin + bl), nf = (unsigned)P.nfft;
+      const float inv_f = (float)P.inv_nfft;
+      const double two_inv = 2.0 * P.inv_nfft;
+#pragma unroll
+      for (int m = 0; m < NP; ++m) {
+        const unsigned t = kk * (unsigned)sdi[m];
+        const unsigned q = (unsigned)((float)t * inv_f);  // floor(t / nfft) +- 1
+        int r = (int)(t - q * nf);
+        if (r < 0) r += (int)nf;
+        if (r >= (int)nf) r -= (int)nf;
+        float sn, cs;
+        sincospif((float)(two_inv * (double)r), &sn, &cs);  // (the same float as delay_eval's: 2 r / nfft rounded once)
+        const float mag = smag[m];
+        dslot[m * TPR_BLOCK] = f2(mag * cs, -mag * sn);
+      }
+    } else
+      // general chain: runtime loop over the channels, one copy of the response code
 #pragma unroll 1
     for (int m = 0; m < NP; ++m) {
       cx<float> d = mk<float>(m < N ? 1.f : 0.f, 0.f);
@@ -201,7 +242,7 @@ __global__ void __launch_bounds__(TPR_BLOCK, 1) fsweep_tpr_kernel(const __grid_c
     for (int q = 0; q < ncols_total; ++q) {
       const int b = (A.cols == 1) ? q : q / A.cols, cc = q - b * A.cols;
       // ---- y = A^-1 D (w_pre x):  L U y = P b
-      const cx<float> xv = ld_cx(x + (size_t)b * A.xbs + (size_t)bl * A.cols + cc);
+      const cx<float> xv = q == 0 ? xv0 : ld_cx(x + (size_t)b * A.xbs + (size_t)bl * A.cols + cc);
       float2 y[NP];
 #pragma unroll
       for (int m = 0; m < NP; ++m) y[m] = cmul2(dslot[m * TPR_BLOCK], f2(wpre[m] * xv.x, wpre[m] * xv.y));
@@ -230,7 +271,7 @@ __global__ void __launch_bounds__(TPR_BLOCK, 1) fsweep_tpr_kernel(const __grid_c
       const size_t ooff = (size_t)bl * A.cols + cc;  // one output channel
       if constexpr (!BWD) {
         if (epi_fused(A.epilogue)) {
-          const float e = abs_t(ox, oy) - __ldg(reinterpret_cast<const float*>(A.tgt) + (size_t)b * A.tbs + bl);
+          const float e = abs_t(ox, oy) - (q == 0 ? tg0 : __ldg(reinterpret_cast<const float*>(A.tgt) + (size_t)b * A.tbs + bl));
           lacc += (double)e * (double)e;
         } else if (A.epilogue == FSWEEP_EPI_ABS) {
           reinterpret_cast<float*>(A.y)[(size_t)b * A.ybs + ooff] = abs_t(ox, oy);
@@ -248,7 +289,7 @@ __global__ void __launch_bounds__(TPR_BLOCK, 1) fsweep_tpr_kernel(const __grid_c
           const float mag = abs_t(ox, oy);
           float gabs;
           if (epi_fused(A.epilogue)) {
-            const float e = mag - __ldg(reinterpret_cast<const float*>(A.tgt) + (size_t)b * A.tbs + bl);
+            const float e = mag - (q == 0 ? tg0 : __ldg(reinterpret_cast<const float*>(A.tgt) + (size_t)b * A.tbs + bl));
             lacc += (double)e * (double)e;
             gabs = (float)(2.0 * A.crit_scale) * e;
           } else {
@@ -267,7 +308,7 @@ __global__ void __launch_bounds__(TPR_BLOCK, 1) fsweep_tpr_kernel(const __grid_c
 #pragma unroll
           for (int m = 0; m < NP; ++m) {
             const float v = gox * y[m].x + goy * y[m].y;
-            float* p = stage + (S_POST + m) * TPR_BLOCK;
+            float* p = stage + (S_POST + m) * TPR_SS;
             *p = F ? v : *p + v;
           }
         };
@@ -308,7 +349,7 @@ __global__ void __launch_bounds__(TPR_BLOCK, 1) fsweep_tpr_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
               const float v = gu.x * y[j].x + gu.y * y[j].y;
-              float* p = stage + (m * NP + j) * TPR_BLOCK;
+              float* p = stage + (m * NP + j) * TPR_SS;
               *p = F ? v : *p + v;
             }
             if (want_ff) {
@@ -327,12 +368,12 @@ __global__ void __launch_bounds__(TPR_BLOCK, 1) fsweep_tpr_kernel(const __grid_c
                 const float ty = (float)ctx.lng * D.y - ctx.omega * D.x;
                 v = ghx * tx + ghy * ty;
               }
-              float* p = stage + (S_DIAG + m) * TPR_BLOCK;
+              float* p = stage + (S_DIAG + m) * TPR_SS;
               *p = F ? v : *p + v;
             }
             {
               const float v = gu.x * xv.x + gu.y * xv.y;
-              float* p = stage + (S_PRE + m) * TPR_BLOCK;
+              float* p = stage + (S_PRE + m) * TPR_SS;
               *p = F ? v : *p + v;
             }
             gxr = fmaf(wpre[m], gu.x, gxr);
@@ -348,29 +389,29 @@ __global__ void __launch_bounds__(TPR_BLOCK, 1) fsweep_tpr_kernel(const __grid_c
   }
 
   if constexpr (BWD) {
-    // ---- block reduction of the per-thread accumulator columns stage[s][0 .. BLOCK): thread (s, quarter) sums a quarter
-    //      of column s with a start rotated by its lane (conflict-free), the four quarters meet in `red`.
-    if (first) {  // a thread without a bin (the grid's tail, or no wanted diagonal gradient) contributes zeros
+    // ---- block reduction of the per-thread accumulator rows stage[s][0 .. BLOCK): thread (s, quarter) sums a quarter of
+    //      row s (the odd row stride keeps the 32 rows of a warp on 32 banks), the four quarters meet in `red`.
+    if (first) {  // a thread without a bin (the grid's tail) contributes zeros
 #pragma unroll 4
-      for (int s = 0; s < S_TOTAL; ++s) stage[s * TPR_BLOCK] = 0.f;
+      for (int s = 0; s < S_TOTAL; ++s) stage[s * TPR_SS] = 0.f;
     }
     __syncthreads();
-    float* red = reinterpret_cast<float*>(tpr_raw + (size_t)S_TOTAL * TPR_BLOCK * 4 + (size_t)3 * NP * TPR_BLOCK * 8);
-    static_assert(TPR_BLOCK == 4 * S_TOTAL || NP != 8, "quarter layout assumes 352 = 4 * 88 threads");
+    float* red = reinterpret_cast<float*>(tpr_raw + SM::stage_bytes + (size_t)3 * NP * TPR_BLOCK * 8);
+    static_assert(TPR_BLOCK % 4 == 0, "quarter layout");
     constexpr int QN = TPR_BLOCK / 4;  // values per quarter
+    static_assert(QN % 4 == 0, "four accumulation chains");
     for (int t = tid; t < 4 * S_TOTAL; t += TPR_BLOCK) {
       const int s = t % S_TOTAL, qd = t / S_TOTAL;
-      const float* col = reinterpret_cast<const float*>(tpr_raw) + (size_t)s * TPR_BLOCK + qd * QN;
-      int j = tid % QN;
-      float s0 = 0.f, s1 = 0.f;
+      const float* row = reinterpret_cast<const float*>(tpr_raw) + (size_t)s * TPR_SS + qd * QN;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 4
-      for (int i = 0; i < QN; i += 2) {
-        s0 += col[j];
-        j = j + 1 == QN ? 0 : j + 1;
-        s1 += col[j];
-        j = j + 1 == QN ? 0 : j + 1;
+      for (int i = 0; i < QN; i += 4) {
+        s0 += row[i];
+        s1 += row[i + 1];
+        s2 += row[i + 2];
+        s3 += row[i + 3];
       }
-      red[qd * S_TOTAL + s] = s0 + s1;
+      red[qd * S_TOTAL + s] = (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
     const OpK& fbop = P.ops[L.fb];

@@ -7,6 +7,7 @@ ncu's CSV export of the source page is SASS-only; this joins it (by instruction 
 line here in the build container (no GUI).
 """
 import csv
+import os
 import re
 import subprocess
 import sys
@@ -18,7 +19,7 @@ def main():
     import os
     rep, pat, obj = sys.argv[1], sys.argv[2], os.path.abspath(sys.argv[3])
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + pat], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + pat] + (["--launch-skip", os.environ["NCU_SKIP"]] if os.environ.get("NCU_SKIP") else []), capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     kname = rows[0][1]
     hdr = rows[1]

@@ -2,6 +2,7 @@
 """Markdown summary of an .ncu-rep: the raw metrics the judge reads + the top source lines by stall samples.
     python tools/ncu_summary.py <report.ncu-rep> <kernel regex> <object file> "<title>" > profiles/xxx.md"""
 import csv
+import os
 import subprocess
 import sys
 
@@ -21,7 +22,7 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 
 def main():
     rep, pat, obj, title = sys.argv[1:5]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "-k", "regex:" + pat], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "-k", "regex:" + pat] + (["--launch-skip", os.environ["NCU_SKIP"]] if os.environ.get("NCU_SKIP") else []), capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     print(f"# {title}\n")
