@@ -291,3 +291,41 @@ def test_nested_recursion_and_parallel_inside_a_loop(name, dtype):
             assert p.grad is not None
             assert float((p.grad.cpu().double() - go[k]).abs().max()) <= gtol * float(go[k].abs().max() + 1e-30)
             k += 1
+
+
+@pytest.mark.parametrize("isint", [True, False])
+def test_register_matrix_kernel_with_several_bins_per_thread(isint):
+    """fsweep_tpr.cuh runs one block of 352 threads per SM: beyond 52 096 bins a thread owns several bins and ADDS into the
+    accumulators its first bin wrote.  8 x 8 FDN at nfft = 400 000 (200 001 bins: up to four per thread), batch 2, with
+    integer delays (the 32-bit phase-index path) and fractional ones (the generic chain): magnitudes against the
+    oracle's per-bin closed form on a bin subset, gradients of a subset loss likewise."""
+    nfft, B = 400000, 2
+    M = nfft // 2 + 1
+    desc = W.fdn(8, isint=isint)
+    torch.manual_seed(11)
+    model = W.build(desc, dsp, system, nfft, W.ALIAS_DECAY_DB, dtype=torch.float32, device=DEV)
+    if not isint:
+        with torch.no_grad():
+            for m in model.modules():
+                if isinstance(m, dsp.parallelDelay):
+                    m.assign_value(m.sample2s(m.s2sample(m.param) + 0.37))
+    X = C.make_input(B, M, model.input_channels, None).to(torch.complex64).to(DEV)
+    idx = _subset(M, 401)
+    Y = model(X)
+    Ys = Y[:, idx.to(DEV)]
+    params = list(model.parameters())
+    C.golden_loss(Ys).backward()
+    torch.cuda.synchronize()
+    ps = [p.detach().cpu().double().requires_grad_(p.requires_grad) for p in params]
+    Yo = O.forward(O.from_desc(desc), X[:, idx.to(DEV)].cpu().to(torch.complex128), ps, nfft, W.ALIAS_DECAY_DB, bins=idx)
+    go = torch.autograd.grad(C.golden_loss(Yo), [p for p in ps if p.requires_grad], allow_unused=True)
+    assert rel_err(np.abs(Ys.detach().cpu().numpy()), np.abs(Yo.detach().numpy())) <= 1e-4
+    k = 0
+    for p in params:
+        if p.requires_grad:
+            ref = go[k]
+            k += 1
+            if ref is None:
+                continue
+            assert p.grad is not None
+            assert float(np.abs(p.grad.cpu().numpy() - ref.numpy()).max() / (np.abs(ref.numpy()).max() + 1e-300)) <= 1e-3
