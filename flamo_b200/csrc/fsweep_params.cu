@@ -57,8 +57,12 @@ __device__ __forceinline__ void combine6(double* out, const double* X, const dou
 
 // exp(X) for X (n x n) in shared memory.  Scaling and squaring with a degree-12 Taylor polynomial evaluated
 // Paterson-Stockmeyer style: with X2..X6 (5 products), p = B0 + X6 (B1 + X6 / 12!) (2 products), B0/B1 = degree-5
-// blocks.  ||X/2^s||_1 <= 1/4 makes the remainder 0.25^13/13! ~ 2e-18.  Scratch: 7 n x n matrices; result in W[0].
-__device__ double* expm_inplace(double* X, double* W, int n, double* red) {
+// blocks.  ||X/2^s||_1 <= theta: the remainder is bounded by theta^13/13! (theta = 1/2: 2e-14, float64 results; theta = 1:
+// 1.6e-10, float32 results).  For NORMAL matrices (the skew-symmetric argument of the orthogonal map) the bound is very
+// pessimistic — numpy, 8 x 8 and 16 x 16 skew matrices with N(0, 1) .. N(0, 9) entries: 1e-14 at theta = 1/2, 3e-13 at 1,
+// 1.5e-9 at 2 — so float32 results of the skew map use theta = 2.  Every unit of log2(theta) saves one squaring, i.e. one
+// of ~13 dependent products of this latency-bound kernel.  Scratch: 7 n x n matrices; result in W[0].
+__device__ double* expm_inplace(double* X, double* W, int n, double* red, double theta) {
   const int nn = n * n;
   for (int c = threadIdx.x; c < n; c += blockDim.x) {
     double s = 0.0;
@@ -69,9 +73,9 @@ __device__ double* expm_inplace(double* X, double* W, int n, double* red) {
   double m = 0.0;
   for (int c = 0; c < n; ++c) m = fmax(m, red[c]);  // every thread: n <= 96 broadcast reads
   int s = 0;
-  if (m > 0.25) {
+  if (m > theta) {
     int ex;
-    frexp(m * 4.0, &ex);  // m*4 = f * 2^ex, f in [0.5, 1)  ->  m / 2^ex <= 1/4
+    frexp(m / theta, &ex);  // m / theta = f * 2^ex, f in [0.5, 1)  ->  m / 2^ex <= theta
     s = ex;
   }
   if (s > 60) s = 60;
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_fwd_kernel(const T* __restr
     X[e] = v;
   }
   __syncthreads();
-  double* R = expm_inplace(X, W, n, red);
+  double* R = expm_inplace(X, W, n, red, sizeof(T) == 4 ? (skew ? 2.0 : 1.0) : 0.5);
   double asum = 0.0;
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const T v = (T)R[e];
@@ -198,7 +202,8 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const T* __restr
   }
   __syncthreads();
   const double back = (gn > 0.0 && isfinite(gn)) ? gn : 1.0;
-  double* R = expm_inplace(X, W, m, red);
+  // (the block matrix is not normal: the general bound applies to the derivative block)
+  double* R = expm_inplace(X, W, m, red, sizeof(T) == 4 ? 1.0 : 0.5);
   // dS = top-right block; skew map: gP[i][j] = dS[i][j] - dS[j][i] for i < j, else 0
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     int i = e / n, j = e - i * n;

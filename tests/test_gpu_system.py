@@ -312,6 +312,8 @@ def test_register_matrix_kernel_with_several_bins_per_thread(isint):
     X = C.make_input(B, M, model.input_channels, None).to(torch.complex64).to(DEV)
     idx = _subset(M, 401)
     Y = model(X)
+    with torch.no_grad(), sweep.bin_shard(70000, 130001):  # a bin shard of the same launch family: bit-identical bins
+        assert torch.equal(model(X), Y[:, 70000:130001])
     Ys = Y[:, idx.to(DEV)]
     params = list(model.parameters())
     C.golden_loss(Ys).backward()
