@@ -176,3 +176,22 @@ def test_fused_svf_designer_equals_the_pytorch_designer(parallel, dtype, monkeyp
     # the typed variants (lowpass ... notch) keep the PyTorch designer
     typed = dsp.SVF(size=(2, 2), n_sections=1, filter_type="peaking", nfft=256, device="cuda", dtype=dtype)
     assert typed._fused_design(typed.param) is None
+
+
+@pytest.mark.parametrize("n", [2, 6, 8, 13, 16, 28])
+@pytest.mark.parametrize("scale", [0.05, 1.0, 7.0])
+def test_expm_float32_parameter_against_float64_autograd(n, scale):
+    """The orthogonal map and its adjoint for a float32 parameter (float64 arithmetic inside, the scaling threshold of
+    float32 results: theta = 2 forward for the skew map, 1 backward) against float64 autograd of torch.matrix_exp on the
+    same (float32-representable) parameter.  (float32 ARITHMETIC for the adjoint was measured: same 10.2 us inside the
+    step — the kernel is a serial instruction stream, not bound by the float64 pipe — so it stays float64.)"""
+    torch.manual_seed(n)
+    P = (scale * torch.randn(n, n, device="cuda")).requires_grad_(True)
+    Q = P.detach().double().requires_grad_(True)
+    G = torch.randn(n, n, device="cuda")
+    E = sweep.OrthogonalMap.apply(P)[0]
+    (E * G).sum().backward()
+    Er = torch.matrix_exp(skew_matrix(Q))
+    (Er * G.double()).sum().backward()
+    assert float((E.double() - Er).abs().max()) <= 2e-7
+    assert float((P.grad.double() - Q.grad).abs().max()) <= 2e-6 * float(Q.grad.abs().max())
