@@ -60,3 +60,25 @@ def test_unmodified_reference_example_runs_and_matches(script, extra, tol, tmp_p
     for f in sorted(os.listdir(ref_dir)):
         if f not in ("checkpoints",):
             assert os.path.exists(os.path.join(ours_dir, f)), f"the reference run wrote {f}, ours did not"
+
+
+def test_unmodified_nn_in_the_loop_model_matches_and_batches(tmp_path):
+    """examples/e7_biquad_nn.py's `nnBiquad` (an MLP conditioning a Biquad through ext_param, one Shell call per batch
+    item) — the class as the reference ships it — on both engines: same output, loss and gradients; and on this engine
+    the per-item loop replaced by ONE call with the batched parameter tensor gives the same numbers."""
+    res = {}
+    for engine in ("b200", "reference"):
+        out = tmp_path / f"{engine}.npz"
+        r = subprocess.run([sys.executable, os.path.join(HERE, "run_reference_nn_model.py"), engine, str(out)],
+                           capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="4"))
+        assert r.returncode == 0, f"{engine}:\n{r.stdout[-2000:]}\n{r.stderr[-4000:]}"
+        res[engine] = dict(np.load(out))
+    o, r = res["b200"], res["reference"]
+    assert abs(float(o["loss"]) - float(r["loss"])) <= 1e-9 * abs(float(r["loss"]))
+    assert np.abs(o["y"] - r["y"]).max() <= 1e-9 * np.abs(r["y"]).max()
+    assert np.array_equal(o["biquad_param"], r["biquad_param"])  # both leave the LAST item's parameters in the module
+    grads = [k for k in r if k.startswith("grad_")]
+    assert grads and sorted(grads) == sorted(k for k in o if k.startswith("grad_"))
+    for k in grads:
+        assert np.abs(o[k] - r[k]).max() <= 1e-6 * (np.abs(r[k]).max() + 1e-12), k
+    assert float(o["batched_max_diff"]) <= 1e-12 and float(o["batched_grad_diff"]) <= 1e-9
