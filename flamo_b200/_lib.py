@@ -27,8 +27,9 @@ EXPORTS = [
     "fsweep_plan_num_coeffs", "fsweep_plan_coeff_numel", "fsweep_plan_kernel_family", "fsweep_workspace_bytes",
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward", "fsweep_expm_forward_sp", "fsweep_expm_backward_sp",
-    "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total",
+    "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total", "fsweep_weighted_total_notify",
     "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_allreduce_push", "fsweep_adam_step", "fsweep_fma_probe", "fsweep_fma_probe_flops", "fsweep_biquad_design", "fsweep_svf_design",
+    "fsweep_rfft_supported", "fsweep_rfft_workspace_bytes", "fsweep_rfft_table", "fsweep_rfft",
 ]
 
 
@@ -141,8 +142,19 @@ def lib():
     L.fsweep_fma_probe.argtypes = [vp, i32, i32, vp]
     L.fsweep_fma_probe_flops.restype = C.c_double
     L.fsweep_fma_probe_flops.argtypes = [i32, i32]
+    L.fsweep_rfft_supported.restype = i32
+    L.fsweep_rfft_supported.argtypes = [i64]
+    L.fsweep_rfft_workspace_bytes.restype = C.c_size_t
+    L.fsweep_rfft_workspace_bytes.argtypes = [i64, i64]
+    L.fsweep_rfft_table.restype = i32
+    L.fsweep_rfft_table.argtypes = [vp, i64, vp]
+    L.fsweep_rfft.restype = i32
+    L.fsweep_rfft.argtypes = [vp, i64, i64, i64, i64, i64, C.c_double, vp, vp, vp, C.c_size_t, vp, vp]
     L.fsweep_weighted_total.restype = i32
     L.fsweep_weighted_total.argtypes = [C.POINTER(vp), C.POINTER(C.c_double), C.POINTER(C.c_double), i32, i32, vp, vp]
+    L.fsweep_weighted_total_notify.restype = i32
+    L.fsweep_weighted_total_notify.argtypes = [C.POINTER(vp), C.POINTER(C.c_double), C.POINTER(C.c_double), i32, i32, vp, vp,
+                                               vp, vp, vp]
     _lib = L
     return L
 

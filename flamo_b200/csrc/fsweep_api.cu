@@ -1097,9 +1097,9 @@ int backward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const 
     if (!(v2 && v2[0] == '0')) {
       dim3 grid2((unsigned)std::min(256, (max_total + 31) / 32), grid.y, grid.z);
       if (dtype == FSWEEP_C64)
-        fsweep_finalize_v2_kernel<float><<<grid2, 32 * FIN2_WARPS, 0, st>>>(F);
+        launch_pdl(fsweep_finalize_v2_kernel<float>, grid2, dim3(32 * FIN2_WARPS), 0, st, F);
       else
-        fsweep_finalize_v2_kernel<double><<<grid2, 32 * FIN2_WARPS, 0, st>>>(F);
+        launch_pdl(fsweep_finalize_v2_kernel<double>, grid2, dim3(32 * FIN2_WARPS), 0, st, F);
     } else if (dtype == FSWEEP_C64)
       fsweep_finalize_kernel<float><<<grid, 128, 0, st>>>(F);
     else

@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "../../include/fsweep.h"
+#include "fsweep_pdl.cuh"
 
 #include <type_traits>
 
@@ -1376,6 +1377,7 @@ __global__ void __launch_bounds__(32 * FIN2_WARPS) fsweep_finalize_v2_kernel(con
   __shared__ double red[FIN2_WARPS][33];
   const int opi = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_sync();
   if (opi == F.n_ops) {  // fused criterion: sum of the per-block squared-error sums
     if (F.loss == nullptr || blockIdx.x != 0 || blockIdx.z != 0) return;
     double s = 0.0;

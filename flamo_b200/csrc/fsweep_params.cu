@@ -14,6 +14,10 @@
 #include <cuda_runtime.h>
 
 #include "../../include/fsweep.h"
+#include "fsweep_pdl.cuh"
+
+using fsweep::launch_pdl;
+using fsweep::pdl_sync;
 
 namespace {
 
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_fwd_kernel(const T* __restr
                                                                int n, int skew, T* __restrict__ sp) {
   extern __shared__ double sm[];
   double *X = sm, *W = sm + n * n, *red = sm + 8 * n * n;
+  pdl_sync();
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     int r = e / n, c = e - r * n;
     double v = (double)Pin[e];
@@ -155,6 +160,7 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const T* __restr
   extern __shared__ double sm[];
   const int m = 2 * n;
   double *X = sm, *W = sm + m * m, *red = sm + 8 * m * m;
+  pdl_sync();
   for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
     int r = e / m, c = e - r * m;
     double v = 0.0;
@@ -225,7 +231,7 @@ static int expm_forward_t(const T* P, T* E, int n, int skew, T* sp, cudaStream_t
     cudaError_t e = cudaFuncSetAttribute(expm_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return FSWEEP_E_CUDA;
   }
-  expm_fwd_kernel<T><<<1, EXPM_THREADS, smem, st>>>(P, E, n, skew, sp);
+  launch_pdl(expm_fwd_kernel<T>, dim3(1), dim3(EXPM_THREADS), smem, st, P, E, n, skew, sp);
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
 
@@ -237,7 +243,7 @@ static int expm_backward_t(const T* P, const T* G, T* gP, int n, int skew, const
     cudaError_t e = cudaFuncSetAttribute(expm_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return FSWEEP_E_CUDA;
   }
-  expm_bwd_kernel<T><<<1, EXPM_THREADS, smem, st>>>(P, G, gP, n, skew, Esp, gsp);
+  launch_pdl(expm_bwd_kernel<T>, dim3(1), dim3(EXPM_THREADS), smem, st, P, G, gP, n, skew, Esp, gsp);
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
 
@@ -354,22 +360,38 @@ struct TotalArgs {
   double scale[FSWEEP_MAX_CRITERIA];
   int n;
 };
+// host_vals / host_seq (optional): the same values written straight into MAPPED PINNED host memory, then — behind a
+// system-wide fence — a launch counter: the host polls the counter and has the step's losses the moment they exist,
+// without a copy node in the graph and without waiting for the rest of the step (adjoint of the maps, optimizer).
 template <typename T>
-__global__ void weighted_total_kernel(const __grid_constant__ TotalArgs a, T* vals) {
+__global__ void weighted_total_kernel(const __grid_constant__ TotalArgs a, T* vals, volatile T* host_vals,
+                                      volatile int* host_seq, int* seq_counter) {
+  pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   T tot = T(0);
   for (int i = 0; i < a.n; ++i) {
     const T v = (T)a.scale[i] * *reinterpret_cast<const T*>(a.part[i]);
     vals[i] = v;
+    if (host_vals) host_vals[i] = v;
     tot += (T)a.alpha[i] * v;
   }
   vals[a.n] = tot;
+  if (host_vals) {
+    host_vals[a.n] = tot;
+    __threadfence_system();
+    const int s = *seq_counter + 1;
+    *seq_counter = s;
+    *host_seq = s;
+  }
 }
 }  // namespace
 
-extern "C" FSWEEP_API int fsweep_weighted_total(const void* const* parts, const double* alphas, const double* scales,
-                                                int n, int dtype, void* vals, void* stream) {
+extern "C" FSWEEP_API int fsweep_weighted_total_notify(const void* const* parts, const double* alphas,
+                                                       const double* scales, int n, int dtype, void* vals,
+                                                       void* host_vals, void* host_seq, void* seq_counter,
+                                                       void* stream) {
   if (!parts || !alphas || !scales || !vals || n < 1 || n > FSWEEP_MAX_CRITERIA) return FSWEEP_E_BADARG;
+  if (host_vals && (!host_seq || !seq_counter)) return FSWEEP_E_BADARG;
   TotalArgs a;
   a.n = n;
   for (int i = 0; i < n; ++i) {
@@ -380,12 +402,19 @@ extern "C" FSWEEP_API int fsweep_weighted_total(const void* const* parts, const 
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FSWEEP_C64)
-    weighted_total_kernel<float><<<1, 32, 0, st>>>(a, (float*)vals);
+    launch_pdl(weighted_total_kernel<float>, dim3(1), dim3(32), 0, st, a, (float*)vals, (volatile float*)host_vals,
+               (volatile int*)host_seq, (int*)seq_counter);
   else if (dtype == FSWEEP_C128)
-    weighted_total_kernel<double><<<1, 32, 0, st>>>(a, (double*)vals);
+    launch_pdl(weighted_total_kernel<double>, dim3(1), dim3(32), 0, st, a, (double*)vals, (volatile double*)host_vals,
+               (volatile int*)host_seq, (int*)seq_counter);
   else
     return FSWEEP_E_BADARG;
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}
+
+extern "C" FSWEEP_API int fsweep_weighted_total(const void* const* parts, const double* alphas, const double* scales,
+                                                int n, int dtype, void* vals, void* stream) {
+  return fsweep_weighted_total_notify(parts, alphas, scales, n, dtype, vals, nullptr, nullptr, nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -577,6 +606,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) adam_step_kernel(const __grid_constant__ AdamArgs a, const float* __restrict__ lr) {
   const fsweep_adam_tensor_t& q = a.t[blockIdx.x];
   __shared__ float s_step;
+  pdl_sync();
   float* step = reinterpret_cast<float*>(q.step);
   if (threadIdx.x == 0) s_step = *step + 1.0f;
   __syncthreads();
@@ -617,9 +647,9 @@ extern "C" FSWEEP_API int fsweep_adam_step(const fsweep_adam_tensor_t* tensors, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FSWEEP_C64)
-    adam_step_kernel<float><<<n, 256, 0, st>>>(a, (const float*)lr);
+    launch_pdl(adam_step_kernel<float>, dim3(n), dim3(256), 0, st, a, (const float*)lr);
   else if (dtype == FSWEEP_C128)
-    adam_step_kernel<double><<<n, 256, 0, st>>>(a, (const float*)lr);
+    launch_pdl(adam_step_kernel<double>, dim3(n), dim3(256), 0, st, a, (const float*)lr);
   else
     return FSWEEP_E_BADARG;
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;

@@ -13,8 +13,7 @@ static cudaError_t tpr_t(int grid, cudaStream_t st, const ProgK& P, const LoopIn
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  k<<<grid, TPR_BLOCK, smem, st>>>(P, L, A, G);
-  return cudaGetLastError();
+  return launch_pdl(k, dim3(grid), dim3(TPR_BLOCK), smem, st, P, L, A, G);
 }
 
 cudaError_t launch_tpr(int np, bool bwd, int grid, cudaStream_t st, const ProgK& P, const LoopInfo& L, const SweepArgs& A,

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(TPR_BLOCK, 1) fsweep_tpr_kernel(const __grid_c
   const int N = P.rec_n;
   const OpK& ffop = P.ops[L.ff_begin];
   bool fastd;
+  pdl_sync();  // (fsweep_pdl.cuh) the blocks were scheduled while the preceding kernel of the step was still running
   float* stage = reinterpret_cast<float*>(tpr_raw) + tid;  // slot s at stage[s * TPR_SS]
   float2* dslot = reinterpret_cast<float2*>(tpr_raw + SM::stage_bytes) + tid;  // entry i at [i * TPR_BLOCK]
   float2* yslot = dslot + NP * TPR_BLOCK;

@@ -239,21 +239,55 @@ class Trainer:
         graph = torch.cuda.CUDAGraph()
         self._zero_grad()
         n0 = sweep.launch_count
+        # Loss read-back without a host round trip at the END of the step: the criteria-total kernel of the captured
+        # step stores the losses straight into mapped pinned host memory and bumps a sequence number behind them
+        # (fsweep_weighted_total_notify); train_step polls that number and returns the loss while the adjoint of the
+        # maps and the optimizer are still running (stream-ordered for everything that follows).  Only for the plain
+        # single-process step: a trainer whose _sync exchanges the values between ranks reads them after the exchange.
+        slot = None
+        if type(self)._sync is Trainer._sync and os.environ.get("FLAMO_B200_NOTIFY", "1") != "0":
+            slot = {"host_vals": torch.zeros(8 * 16, dtype=torch.uint8, pin_memory=True),
+                    "host_seq": torch.zeros(1, dtype=torch.int32, pin_memory=True),
+                    "counter": torch.zeros(1, dtype=torch.int32, device=static_in.device), "expected": 0}
         try:
+            sweep.NOTIFY_SLOT = slot
             with torch.cuda.graph(graph):
                 self._zero_grad_captured()
                 out = self._train_core(static_in, static_tg)
-                # the step's single device->host read is a node of the graph: the losses land in pinned host memory
-                out_host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
-                out_host.copy_(out, non_blocking=True)
+                notified = slot is not None and slot.get("used") == (out.numel(), out.dtype)
+                out_host = None
+                if not notified:
+                    # the step's single device->host read is a node of the graph: the losses land in pinned host memory
+                    out_host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                    out_host.copy_(out, non_blocking=True)
         except Exception as e:  # keep training eagerly (still on the CUDA sweep) if capture is impossible
             warnings.warn(f"CUDA-graph capture of the training step failed ({e}); continuing without graph.")
             self.use_graph = False
             torch.cuda.synchronize()
             return None
-        g = (graph, static_in, static_tg, out_host, sweep.launch_count - n0, [None, None])  # sweep kernels per replay
+        finally:
+            sweep.NOTIFY_SLOT = None
+        if notified:
+            slot["seq_np"] = slot["host_seq"].numpy()
+            slot["vals_np"] = slot["host_vals"].view(out.dtype)[:out.numel()].numpy()
+        else:
+            slot = None
+        g = (graph, static_in, static_tg, out_host, sweep.launch_count - n0, [None, None], slot)  # sweep kernels per replay
         self._graphs[key] = g
         return g
+
+    def _await_losses(self, slot, device):
+        """Spin on the sequence number the captured step writes behind its losses (pinned host memory)."""
+        slot["expected"] += 1
+        want, seq = slot["expected"], slot["seq_np"]
+        spins = 0
+        while seq[0] != want:
+            spins += 1
+            if spins == 2000000:  # ~ a second: something is wrong (or a debugger holds the GPU); stop spinning blind
+                torch.cuda.current_stream(device).synchronize()
+                if seq[0] != want:
+                    raise RuntimeError(f"captured step: loss notification {int(seq[0])} != expected {want}")
+        return slot["vals_np"].tolist()
 
     def _zero_grad_captured(self):
         """Inside the captured region: nothing to do when grads are (re)allocated by backward."""
@@ -272,7 +306,7 @@ class Trainer:
             if g is not None:
                 from .. import sweep
 
-                graph, static_in, static_tg, out_host, n_kernels, last = g
+                graph, static_in, static_tg, out_host, n_kernels, last, notify = g
                 # A DEVICE tensor that is the very tensor (storage, version) copied in by the previous step is already
                 # in the static buffer: a dataset resident in HBM costs no copy per step.  Host tensors are copied
                 # every step (from pinned memory: ONE asynchronous H2D copy per tensor).
@@ -286,8 +320,11 @@ class Trainer:
                 inval = getattr(self.net, "_invalidate_caches", None)
                 if inval is not None:  # parameters changed on the device without a version bump
                     inval()
-                torch.cuda.current_stream(static_in.device).synchronize()
-                vals = out_host.tolist()  # written by the graph's own device->host copy node
+                if notify is not None:
+                    vals = self._await_losses(notify, static_in.device)  # the rest of the step is still in flight
+                else:
+                    torch.cuda.current_stream(static_in.device).synchronize()
+                    vals = out_host.tolist()  # written by the graph's own device->host copy node
                 self._log(self.train_loss_log, vals[:-1])
                 return vals[-1]
             return self._eager_train_step(inputs, targets)

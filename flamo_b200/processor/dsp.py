@@ -57,7 +57,7 @@ class FFT(Transform):
         super().__init__(transform=self._transform, dtype=dtype)
 
     def _transform(self, x):
-        return torch.fft.rfft(x, n=self.nfft, dim=1, norm=self.norm)
+        return sweep.rfft(x, self.nfft, self.norm)  # libfsweep's two-launch FFT on the GPU, torch.fft elsewhere
 
 
 class iFFT(Transform):
@@ -87,7 +87,7 @@ class FFTAntiAlias(Transform):
         super().__init__(transform=self._transform, device=device, dtype=dtype)
 
     def _transform(self, x):
-        return torch.fft.rfft(x * self.alias_envelope.view(1, -1, 1), n=self.nfft, dim=1, norm=self.norm)
+        return sweep.rfft(x, self.nfft, self.norm, envelope=self.alias_envelope)
 
 
 class iFFTAntiAlias(Transform):

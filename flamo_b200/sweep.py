@@ -653,6 +653,55 @@ def _real_code(dtype: torch.dtype) -> int:
     return _lib.C64 if dtype == torch.float32 else _lib.C128
 
 
+_RFFT_TABLES = {}
+
+
+def rfft(x: torch.Tensor, nfft: int, norm: str = "backward", envelope: torch.Tensor = None, force: bool = False):
+    """torch.fft.rfft(x [* envelope.view(1, -1, 1)], n=nfft, dim=1, norm=norm) for the excitation of a step (reference
+    dsp.py:69-93, :122-163).  A float32 (B, T, C) signal on the GPU that needs no gradient goes through libfsweep's
+    two-launch four-step FFT (fsweep_rfft; cuFFT plans nfft = 96000 as five launches); everything else — CPU tensors,
+    float64, inputs that require grad, sizes fsweep_rfft_supported refuses, and (unless `force`) the sizes where cuFFT is
+    the faster one — stays on torch.fft / cuFFT."""
+    global launch_count
+    use = (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and _BACKEND.name == "cuda"
+           and not (x.requires_grad and torch.is_grad_enabled()) and norm in ("backward", "forward", "ortho")
+           and (envelope is None or (envelope.is_cuda and envelope.dtype == torch.float32 and envelope.numel() == nfft
+                                      and x.shape[1] == nfft and not envelope.requires_grad))
+           and os.environ.get("FLAMO_B200_RFFT", "1") != "0"
+           # a LATENCY design: it wins where cuFFT needs several launches for one short job (measured on a B200: nfft
+           # 96000 8.7 vs 12.1 us warm, 192000 11.6 vs 13.7) and loses on small single-launch sizes and on big batches
+           and (force or (nfft >= 16384 and x.shape[0] * x.shape[2] * nfft <= (1 << 20)))
+           and _lib.lib().fsweep_rfft_supported(int(nfft))
+           # the twiddle table is made at the first call, which must not be a captured one
+           and ((int(nfft), x.device.index) in _RFFT_TABLES or not torch.cuda.is_current_stream_capturing()))
+    if not use:
+        if envelope is not None:
+            x = x * envelope.view(1, -1, 1)
+        return torch.fft.rfft(x, n=nfft, dim=1, norm=norm)
+    x = x.detach()
+    if x.stride(2) != 1 or x.stride(1) != x.shape[2] or (x.shape[0] > 1 and x.stride(0) < x.shape[1] * x.shape[2]):
+        x = x.contiguous()
+    B, T, Cn = x.shape
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        key = (int(nfft), x.device.index)
+        table = _RFFT_TABLES.get(key)
+        if table is None:
+            table = torch.empty(nfft, dtype=torch.complex64, device=x.device)
+            _lib.check(L.fsweep_rfft_table(table.data_ptr(), int(nfft), stream))
+            _RFFT_TABLES[key] = table
+        ws_bytes = L.fsweep_rfft_workspace_bytes(int(nfft), B * Cn)
+        ws = torch.empty(ws_bytes // 8, dtype=torch.complex64, device=x.device)
+        X = torch.empty((B, nfft // 2 + 1, Cn), dtype=torch.complex64, device=x.device)
+        scale = {"backward": 1.0, "forward": 1.0 / nfft, "ortho": nfft ** -0.5}[norm]
+        _lib.check(L.fsweep_rfft(x.data_ptr(), B, T, Cn, x.stride(0) if B > 1 else T * Cn, int(nfft), scale,
+                                 envelope.data_ptr() if envelope is not None else None, table.data_ptr(),
+                                 ws.data_ptr(), ws_bytes, X.data_ptr(), stream))
+    launch_count += 2
+    return X
+
+
 class SparsityFunction(torch.autograd.Function):
     """sparsity_loss of a mapped (N, N) or (B, N, N) matrix (reference optimize/loss.py:36-63) as one launch each
     way (libfsweep fsweep_sparsity_*) instead of half a dozen parameter-sized PyTorch kernels."""
@@ -691,6 +740,12 @@ class SparsityFunction(torch.autograd.Function):
         return gA
 
 
+# Set by Trainer._graph_for around the capture of a step: {"host_vals": pinned uint8 buffer, "host_seq": pinned int32[1],
+# "counter": device int32[1]}.  The ONE WeightedTotal launch of the captured step then also stores its values into the
+# pinned buffer and bumps the sequence number behind them (fsweep_weighted_total_notify); "used" records (count, dtype).
+NOTIFY_SLOT = None
+
+
 class WeightedTotal(torch.autograd.Function):
     """vals = [s_0 part_0, ..., s_{n-1} part_{n-1}, sum_i alpha_i s_i part_i] in one launch (libfsweep
     fsweep_weighted_total): the Trainer's `loss += alpha * criterion` accumulation (reference trainer.py:184-188)
@@ -719,9 +774,17 @@ class WeightedTotal(torch.autograd.Function):
         pp = (C.c_void_p * n)(*[p.data_ptr() for p in parts])
         aa = (C.c_double * n)(*[float(a) for a in alphas])
         ss = (C.c_double * n)(*[float(a) for a in scales])
+        slot = NOTIFY_SLOT
         with torch.cuda.device(vals.device):
-            _lib.check(_lib.lib().fsweep_weighted_total(pp, aa, ss, n, _real_code(vals.dtype), vals.data_ptr(),
-                                                         torch.cuda.current_stream(vals.device).cuda_stream))
+            stream = torch.cuda.current_stream(vals.device).cuda_stream
+            if slot is not None and slot.get("used") is None and slot["counter"].device == vals.device:
+                # the Trainer captures a step: the values also go straight to its pinned host buffer (see NOTIFY_SLOT)
+                slot["used"] = (n + 1, vals.dtype)
+                _lib.check(_lib.lib().fsweep_weighted_total_notify(
+                    pp, aa, ss, n, _real_code(vals.dtype), vals.data_ptr(), slot["host_vals"].data_ptr(),
+                    slot["host_seq"].data_ptr(), slot["counter"].data_ptr(), stream))
+            else:
+                _lib.check(_lib.lib().fsweep_weighted_total(pp, aa, ss, n, _real_code(vals.dtype), vals.data_ptr(), stream))
         launch_count += 1
         ctx.coef = (tuple(float(a) * float(c) for a, c in zip(alphas, scales)), tuple(float(c) for c in scales))
         for c in ctx.coef:  # created here, outside any later capture of the backward

@@ -260,6 +260,15 @@ FSWEEP_API int fsweep_sparsity_backward(const void* A, const void* gloss, int n_
 #define FSWEEP_MAX_CRITERIA 8
 FSWEEP_API int fsweep_weighted_total(const void* const* parts, const double* alphas, const double* scales, int n,
                                      int dtype, void* vals, void* stream);
+/* The same, and the n + 1 values are ALSO stored into host_vals — mapped pinned host memory (cudaHostAlloc /
+ * cudaHostRegister; with unified addressing the host pointer is the device pointer), real[n+1] — followed, behind a
+ * system-wide fence, by the number of this launch (1, 2, ...; seq_counter: device int32[1], zero at the start) into
+ * host_seq (mapped pinned int32[1]).  A host thread that polls host_seq has the step's losses (reference
+ * optimize/trainer.py:190 `loss.item()`) as soon as they exist: no copy node in the captured step, no wait for the
+ * kernels behind the criteria.  host_vals == NULL: plain fsweep_weighted_total. */
+FSWEEP_API int fsweep_weighted_total_notify(const void* const* parts, const double* alphas, const double* scales, int n,
+                                            int dtype, void* vals, void* host_vals, void* host_seq, void* seq_counter,
+                                            void* stream);
 
 /* torch.optim.Adam's update (the Trainer's optimizer, reference optimize/trainer.py:42; no weight decay, no amsgrad)
  * for up to FSWEEP_ADAM_MAX_TENSORS parameter tensors in ONE launch.  All pointers are device pointers; param / grad /
@@ -303,6 +312,21 @@ typedef struct fsweep_seg {
 FSWEEP_API int fsweep_allreduce_push(const fsweep_seg_t* segs, int n_segs, void* const* peer_buffers,
                                      void* const* peer_signal_pads, int rank, int world, int cap, double scale,
                                      void* epoch_counter, void* stream);
+
+/* Real-to-complex FFT of the excitation along the time axis (reference flamo/processor/dsp.py:69-93 dsp.FFT and
+ * :122-163 dsp.FFTAntiAlias: torch.fft.rfft(x [* envelope], n=nfft, dim=1)): x float32 [batch][n_time][channels]
+ * (time stride = channels, batch stride given in elements), zero padded / cropped to nfft, X complex64
+ * [batch][nfft/2 + 1][channels] = scale * DFT.  Two launches of a four-step FFT (fsweep_fft.cu) instead of cuFFT's five.
+ * `table`: nfft complex64 entries exp(-2 pi i j / nfft), filled once per (nfft, device) by fsweep_rfft_table (float64
+ * inside); `workspace`: fsweep_rfft_workspace_bytes(nfft, batch * channels); `envelope`: NULL or nfft float32 factors.
+ * fsweep_rfft_supported(nfft) == 0 (and FSWEEP_E_UNSUPPORTED from fsweep_rfft): nfft is odd, < 512, or nfft / 2 does
+ * not split into two factors <= 1024 made of radices <= 64 - the caller keeps cuFFT for those.  Capture safe. */
+FSWEEP_API int fsweep_rfft_supported(int64_t nfft);
+FSWEEP_API size_t fsweep_rfft_workspace_bytes(int64_t nfft, int64_t signals);
+FSWEEP_API int fsweep_rfft_table(void* table, int64_t nfft, void* stream);
+FSWEEP_API int fsweep_rfft(const void* x, int64_t batch, int64_t n_time, int64_t channels, int64_t x_batch_stride,
+                           int64_t nfft, double scale, const void* envelope, const void* table, void* workspace,
+                           size_t workspace_bytes, void* X, void* stream);
 
 /* FP32 FMA peak probe (bench.py's roofline denominator for the compute-bound sweeps; SURVEY.md section 8d "derive +
  * measure"): `blocks` blocks of 256 threads, 64 independent FFMAs per thread and round; fsweep_fma_probe_flops gives the
