@@ -26,9 +26,9 @@ EXPORTS = [
     "fsweep_version", "fsweep_last_error", "fsweep_plan_create", "fsweep_plan_destroy",
     "fsweep_plan_num_coeffs", "fsweep_plan_coeff_numel", "fsweep_plan_kernel_family", "fsweep_workspace_bytes",
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
-    "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward", "fsweep_expm_forward_sp", "fsweep_expm_backward_sp",
+    "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward", "fsweep_expm_forward_sp", "fsweep_expm_backward_sp", "fsweep_expm_backward_sp_total",
     "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total", "fsweep_weighted_total_notify",
-    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_allreduce_push", "fsweep_adam_step", "fsweep_fma_probe", "fsweep_fma_probe_flops", "fsweep_biquad_design", "fsweep_svf_design",
+    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_allreduce_push", "fsweep_adam_step", "fsweep_adam_step_total", "fsweep_fma_probe", "fsweep_fma_probe_flops", "fsweep_biquad_design", "fsweep_svf_design",
     "fsweep_rfft_supported", "fsweep_rfft_workspace_bytes", "fsweep_rfft_table", "fsweep_rfft",
 ]
 
@@ -61,6 +61,14 @@ class AdamTensor(C.Structure):
 
 
 ADAM_MAX_TENSORS = 32
+MAX_CRITERIA = 8
+
+
+class TotalJob(C.Structure):
+    """fsweep_total_job_t"""
+    _fields_ = [("parts", C.c_void_p * MAX_CRITERIA), ("alphas", C.c_double * MAX_CRITERIA),
+                ("scales", C.c_double * MAX_CRITERIA), ("n", C.c_int32), ("reserved", C.c_int32), ("vals", C.c_void_p),
+                ("host_vals", C.c_void_p), ("host_seq", C.c_void_p), ("seq_counter", C.c_void_p)]
 
 
 class SweepError(RuntimeError):
@@ -123,6 +131,8 @@ def lib():
     L.fsweep_expm_forward_sp.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.fsweep_expm_backward_sp.restype = i32
     L.fsweep_expm_backward_sp.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    L.fsweep_expm_backward_sp_total.restype = i32
+    L.fsweep_expm_backward_sp_total.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, C.POINTER(TotalJob), vp]
     L.fsweep_sparsity_forward.restype = i32
     L.fsweep_sparsity_forward.argtypes = [vp, i32, i32, i32, vp, vp]
     L.fsweep_sparsity_backward.restype = i32
@@ -134,6 +144,9 @@ def lib():
     L.fsweep_allreduce_push.argtypes = [C.POINTER(Seg), i32, vp, vp, i32, i32, i32, C.c_double, vp, vp]
     L.fsweep_adam_step.restype = i32
     L.fsweep_adam_step.argtypes = [C.POINTER(AdamTensor), i32, i32, vp, C.c_double, C.c_double, C.c_double, vp]
+    L.fsweep_adam_step_total.restype = i32
+    L.fsweep_adam_step_total.argtypes = [C.POINTER(AdamTensor), i32, i32, vp, C.c_double, C.c_double, C.c_double,
+                                         C.POINTER(TotalJob), vp]
     L.fsweep_biquad_design.restype = i32
     L.fsweep_biquad_design.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     L.fsweep_svf_design.restype = i32

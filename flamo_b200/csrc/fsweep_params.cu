@@ -13,6 +13,8 @@
 //  * the weighted total of the step's criteria (reference flamo/optimize/trainer.py:184-188).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "../../include/fsweep.h"
 #include "fsweep_pdl.cuh"
 
@@ -20,6 +22,88 @@ using fsweep::launch_pdl;
 using fsweep::pdl_sync;
 
 namespace {
+
+struct TotalArgs {
+  const void* part[FSWEEP_MAX_CRITERIA];
+  double alpha[FSWEEP_MAX_CRITERIA];
+  double scale[FSWEEP_MAX_CRITERIA];
+  int n;
+};
+// host_vals / host_seq (optional): the same values written straight into MAPPED PINNED host memory together with the
+// number of this launch: the host polls the counter and has the step's losses the moment they exist, without a copy
+// node in the graph and without waiting for the rest of the step.  float32: every value travels WITH the launch number
+// in one aligned 8-byte store {value, seq} — single-copy atomic, so no fence is needed and the host simply waits until
+// every pair carries the number it expects; float64: plain values, a system-wide fence, then the counter.
+template <typename T>
+__device__ __forceinline__ void total_job(const TotalArgs& a, T* vals, void* host_vals, volatile int* host_seq,
+                                          int* seq_counter) {
+  int s = 0;
+  if (host_vals) {
+    s = *seq_counter + 1;
+    *seq_counter = s;
+  }
+  T tot = T(0);
+  for (int i = 0; i <= a.n; ++i) {
+    T v = tot;
+    if (i < a.n) {
+      v = (T)a.scale[i] * *reinterpret_cast<const T*>(a.part[i]);
+      tot += (T)a.alpha[i] * v;
+    }
+    vals[i] = v;
+    if (host_vals) {
+      if (sizeof(T) == 4) {
+        const unsigned long long pair = (unsigned long long)__float_as_uint((float)v) | ((unsigned long long)(unsigned)s << 32);
+        reinterpret_cast<volatile unsigned long long*>(host_vals)[i] = pair;
+      } else {
+        reinterpret_cast<volatile double*>(host_vals)[i] = (double)v;
+      }
+    }
+  }
+  if (host_vals) {
+    if (sizeof(T) != 4) __threadfence_system();
+    *host_seq = s;
+    // push the stores out NOW: as a rider this thread shares a kernel with blocks that run for microseconds more,
+    // and without a fence its posted writes were seen by the host only around the end of the kernel
+    __threadfence_system();
+  }
+}
+
+
+// A RIDER: one extra block of a parameter-sized kernel evaluates the weighted total of the step's criteria and
+// notifies the host (fsweep_weighted_total_notify) — inside a captured step the values are only read by the host, so they
+// need no launch of their own on the critical path.
+struct RiderArgs {
+  TotalArgs total;
+  void *vals, *host_vals, *host_seq, *seq_counter;
+  int on;
+};
+template <typename T>
+__device__ __forceinline__ void run_rider(const RiderArgs& rd) {
+  if (threadIdx.x == 0)
+    total_job<T>(rd.total, reinterpret_cast<T*>(rd.vals), rd.host_vals, reinterpret_cast<volatile int*>(rd.host_seq),
+                 reinterpret_cast<int*>(rd.seq_counter));
+}
+bool fill_rider(const fsweep_total_job_t* total, RiderArgs* rd) {
+  rd->on = 0;
+  rd->vals = rd->host_vals = rd->host_seq = rd->seq_counter = nullptr;
+  rd->total.n = 0;
+  if (!total) return true;
+  if (total->n < 1 || total->n > FSWEEP_MAX_CRITERIA || !total->vals) return false;
+  if (total->host_vals && (!total->host_seq || !total->seq_counter)) return false;
+  rd->total.n = total->n;
+  for (int i = 0; i < total->n; ++i) {
+    if (!total->parts[i]) return false;
+    rd->total.part[i] = total->parts[i];
+    rd->total.alpha[i] = total->alphas[i];
+    rd->total.scale[i] = total->scales[i];
+  }
+  rd->vals = total->vals;
+  rd->host_vals = total->host_vals;
+  rd->host_seq = total->host_seq;
+  rd->seq_counter = total->seq_counter;
+  rd->on = 1;
+  return true;
+}
 
 constexpr int EXPM_THREADS = 256;
 
@@ -156,11 +240,16 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_fwd_kernel(const T* __restr
 template <typename T>
 __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const T* __restrict__ Pin, const T* __restrict__ G,
                                                                T* __restrict__ gP, int n, int skew,
-                                                               const T* __restrict__ Esp, const T* __restrict__ gsp) {
+                                                               const T* __restrict__ Esp, const T* __restrict__ gsp,
+                                                               const __grid_constant__ RiderArgs rd) {
   extern __shared__ double sm[];
   const int m = 2 * n;
   double *X = sm, *W = sm + m * m, *red = sm + 8 * m * m;
   pdl_sync();
+  if (blockIdx.x == 1) {
+    run_rider<T>(rd);
+    return;
+  }
   for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
     int r = e / m, c = e - r * m;
     double v = 0.0;
@@ -220,12 +309,222 @@ __global__ void __launch_bounds__(EXPM_THREADS) expm_bwd_kernel(const T* __restr
   }
 }
 
+
+// ---- small matrices (the headline's 8 x 8 feedback matrix): ONE THREAD PER ELEMENT of an M x M matrix (M = 8 | 16,
+// smaller problems zero padded: exp(diag(X, 0)) = diag(exp X, I)), the same degree-12 Paterson-Stockmeyer polynomial
+// and scaling rule as expm_inplace, but
+//   * the row a thread multiplies with lives in registers, the dot products are fully unrolled (no index arithmetic,
+//     no division), every thread keeps its own element of X .. X6 in registers for the elementwise combinations;
+//   * products that share their left factor run in the same phase (X3, X4 after X2; X5, X6 after X3): 4 + s
+//     dependent product phases instead of 7 + s, 7 + s block barriers instead of ~16 + s;
+//   * norms by warp shuffles instead of serial column loops.
+// The generic kernel took 7.5 / 10.3 us (forward / adjoint) of a ~50 us config-2 step.
+template <int M>
+struct SmallExpm {
+  static constexpr int NN = M * M;
+  double* buf;  // 5 matrices in shared memory
+  int r, c, t;
+
+  __device__ __forceinline__ double rowdot(const double (&a)[M], const double* B) const {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; k += 2) {
+      s0 = fma(a[k], B[k * M + c], s0);
+      s1 = fma(a[k + 1], B[(k + 1) * M + c], s1);
+    }
+    return s0 + s1;
+  }
+  __device__ __forceinline__ void loadrow(double (&a)[M], const double* A) const {
+#pragma unroll
+    for (int k = 0; k < M; ++k) a[k] = A[r * M + k];
+  }
+  // max over the block of the row sums of v (one value per thread, rows = groups of M adjacent lanes)
+  __device__ __forceinline__ double max_rowsum(double v, double* red) const {
+#pragma unroll
+    for (int o = 1; o < M; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#pragma unroll
+    for (int o = M; o < 32; o <<= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((t & 31) == 0) red[t >> 5] = v;
+    __syncthreads();
+    double m = 0.0;
+#pragma unroll
+    for (int w = 0; w < NN / 32; ++w) m = fmax(m, red[w]);
+    return m;
+  }
+
+  // x: this thread's element of X (already stored in buf[0 .. NN) and published).  Returns the buffer holding exp(X).
+  __device__ double* run(double x, double* red, double theta) {
+    double *X = buf, *X2 = buf + NN, *X3 = buf + 2 * NN, *X6 = buf + 3 * NN, *T0 = buf + 4 * NN;
+    // 1-norm: thread (r, c) takes |X[c][r]|, so the row sums of what the threads hold are the column sums of X
+    const double m = max_rowsum(fabs(X[c * M + r]), red);
+    int s = 0;
+    if (m > theta) {
+      int ex;
+      frexp(m / theta, &ex);
+      s = ex;
+    }
+    if (s > 60) s = 60;
+    x *= ldexp(1.0, -s);
+    __syncthreads();  // every thread has read X (transposed) before it is overwritten
+    X[t] = x;
+    __syncthreads();
+    double a[M];
+    loadrow(a, X);
+    const double x2 = rowdot(a, X);
+    X2[t] = x2;
+    __syncthreads();
+    loadrow(a, X2);
+    const double x3 = rowdot(a, X), x4 = rowdot(a, X2);
+    X3[t] = x3;
+    __syncthreads();
+    loadrow(a, X3);
+    const double x5 = rowdot(a, X2), x6 = rowdot(a, X3);
+    const double id = (r == c) ? 1.0 : 0.0;
+    X6[t] = x6;
+    T0[t] = id * (1.0 / 720) + x * (1.0 / 5040) + x2 * (1.0 / 40320) + x3 * (1.0 / 362880) + x4 * (1.0 / 3628800) +
+            x5 * (1.0 / 39916800) + x6 * (1.0 / 479001600);
+    __syncthreads();
+    loadrow(a, X6);
+    double e = rowdot(a, T0) + (id + x + x2 * (1.0 / 2) + x3 * (1.0 / 6) + x4 * (1.0 / 24) + x5 * (1.0 / 120));
+    double *cur = X, *other = X2;  // (both free by now)
+    cur[t] = e;
+    __syncthreads();
+    for (int i = 0; i < s; ++i) {
+      loadrow(a, cur);
+      e = rowdot(a, cur);
+      other[t] = e;
+      __syncthreads();
+      double* tmp = cur;
+      cur = other;
+      other = tmp;
+    }
+    return cur;
+  }
+};
+
+template <typename T, int M>
+__global__ void __launch_bounds__(M * M) expm_fwd_small_kernel(const T* __restrict__ Pin, T* __restrict__ E, int n,
+                                                               int skew, T* __restrict__ sp) {
+  __shared__ double buf[5 * M * M];
+  __shared__ double red[8];
+  SmallExpm<M> ex;
+  ex.buf = buf;
+  ex.t = threadIdx.x;
+  ex.r = threadIdx.x / M;
+  ex.c = threadIdx.x % M;
+  const int r = ex.r, c = ex.c;
+  pdl_sync();
+  double v = 0.0;
+  if (r < n && c < n) {
+    if (skew)
+      v = (c > r) ? (double)Pin[r * n + c] : ((c < r) ? -(double)Pin[c * n + r] : 0.0);
+    else
+      v = (double)Pin[r * n + c];
+  }
+  buf[ex.t] = v;
+  __syncthreads();
+  const double* R = ex.run(v, red, sizeof(T) == 4 ? (skew ? 2.0 : 1.0) : 0.5);
+  double asum = 0.0;
+  if (r < n && c < n) {
+    const T o = (T)R[ex.t];
+    E[r * n + c] = o;
+    asum = fabs((double)o);
+  }
+  if (sp != nullptr) {  // (uniform)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+    __syncthreads();  // red was read by every thread inside run()
+    if ((ex.t & 31) == 0) red[ex.t >> 5] = asum;
+    __syncthreads();
+    if (ex.t == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < M * M / 32; ++w) tot += red[w];
+      const double rn = sqrt((double)n);
+      *sp = (T)((tot - n * rn) / (n * (1.0 - rn)));
+    }
+  }
+}
+
+// adjoint, 2n <= 16: the block matrix [[S^T, G], [0, S^T]] on the 16 x 16 kernel (n < 8: the blocks sit at offset 0 and
+// 8, the padding rows / columns are zero)
+template <typename T>
+__global__ void __launch_bounds__(256) expm_bwd_small_kernel(const T* __restrict__ Pin, const T* __restrict__ G,
+                                                             T* __restrict__ gP, int n, int skew,
+                                                             const T* __restrict__ Esp, const T* __restrict__ gsp,
+                                                             const __grid_constant__ RiderArgs rd) {
+  constexpr int M = 16, H = 8;
+  __shared__ double buf[5 * M * M];
+  __shared__ double red[8];
+  SmallExpm<M> ex;
+  ex.buf = buf;
+  ex.t = threadIdx.x;
+  ex.r = threadIdx.x / M;
+  ex.c = threadIdx.x % M;
+  const int r = ex.r, c = ex.c;
+  const int i = r % H, j = c % H;
+  pdl_sync();
+  if (blockIdx.x == 1) {
+    run_rider<T>(rd);
+    return;
+  }
+  double v = 0.0;
+  const bool gblock = r < H && c >= H && i < n && j < n;
+  if (gblock) {
+    if (G != nullptr) v = (double)G[i * n + j];
+    if (gsp != nullptr) {
+      const T a = Esp[i * n + j];
+      const double rn = sqrt((double)n);
+      const double k = (double)*gsp / (n * (1.0 - rn));
+      v += a > T(0) ? k : (a < T(0) ? -k : 0.0);
+    }
+  } else if ((r < H) == (c < H) && i < n && j < n) {  // block (i, j) of S^T = S[j][i]
+    if (skew)
+      v = (i > j) ? (double)Pin[j * n + i] : ((i < j) ? -(double)Pin[i * n + j] : 0.0);
+    else
+      v = (double)Pin[j * n + i];
+  }
+  // The Frechet derivative is LINEAR in G: normalise the G block (here by n * max |G_ij| >= its 1-norm) and scale the
+  // result back, so that the number of squarings depends on ||S|| only.
+  double g = gblock ? fabs(v) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) g = fmax(g, __shfl_xor_sync(0xffffffffu, g, o));
+  if ((ex.t & 31) == 0) red[ex.t >> 5] = g;
+  __syncthreads();
+  double gn = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) gn = fmax(gn, red[w]);
+  gn *= (double)n;
+  const bool norm = gn > 0.0 && isfinite(gn);
+  if (norm && gblock) v *= 1.0 / gn;
+  buf[ex.t] = v;
+  __syncthreads();  // (also: everyone has read red before run() writes it again)
+  const double* R = ex.run(v, red, sizeof(T) == 4 ? 1.0 : 0.5);
+  // dS = top-right block; skew map: gP[i][j] = dS[i][j] - dS[j][i] for i < j, else 0
+  if (r < H && c >= H && i < n && j < n) {
+    double d = R[i * M + H + j];
+    if (skew) d = (i < j) ? d - R[j * M + H + i] : 0.0;
+    if (norm) d *= gn;
+    gP[i * n + j] = (T)d;
+  }
+}
+
 }  // namespace
 
 extern "C" FSWEEP_API int fsweep_expm_max_n(void) { return 28; }  // 8 matrices of (2n)^2 doubles in shared memory
 
 template <typename T>
 static int expm_forward_t(const T* P, T* E, int n, int skew, T* sp, cudaStream_t st) {
+  static const bool small_ok = [] {
+    const char* e = getenv("FSWEEP_EXPM_SMALL");
+    return !(e && e[0] == '0');
+  }();
+  if (small_ok && n <= 16) {
+    if (n <= 8)
+      launch_pdl(expm_fwd_small_kernel<T, 8>, dim3(1), dim3(64), 0, st, P, E, n, skew, sp);
+    else
+      launch_pdl(expm_fwd_small_kernel<T, 16>, dim3(1), dim3(256), 0, st, P, E, n, skew, sp);
+    return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+  }
   size_t smem = (size_t)(8 * n * n + n + 8) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(expm_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -236,14 +535,26 @@ static int expm_forward_t(const T* P, T* E, int n, int skew, T* sp, cudaStream_t
 }
 
 template <typename T>
-static int expm_backward_t(const T* P, const T* G, T* gP, int n, int skew, const T* Esp, const T* gsp, cudaStream_t st) {
+static int expm_backward_t(const T* P, const T* G, T* gP, int n, int skew, const T* Esp, const T* gsp,
+                           const fsweep_total_job_t* total, cudaStream_t st) {
+  RiderArgs rd;
+  if (!fill_rider(total, &rd)) return FSWEEP_E_BADARG;
+  const dim3 grid(rd.on ? 2 : 1);
+  static const bool small_ok = [] {
+    const char* e = getenv("FSWEEP_EXPM_SMALL");
+    return !(e && e[0] == '0');
+  }();
+  if (small_ok && n <= 8) {
+    launch_pdl(expm_bwd_small_kernel<T>, grid, dim3(256), 0, st, P, G, gP, n, skew, Esp, gsp, rd);
+    return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+  }
   const int m = 2 * n;
   size_t smem = (size_t)(8 * m * m + m + 8) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(expm_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return FSWEEP_E_CUDA;
   }
-  launch_pdl(expm_bwd_kernel<T>, dim3(1), dim3(EXPM_THREADS), smem, st, P, G, gP, n, skew, Esp, gsp);
+  launch_pdl(expm_bwd_kernel<T>, grid, dim3(EXPM_THREADS), smem, st, P, G, gP, n, skew, Esp, gsp, rd);
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
 
@@ -261,18 +572,24 @@ extern "C" FSWEEP_API int fsweep_expm_forward(const void* P, void* E, int n, int
   return fsweep_expm_forward_sp(P, E, n, skew, dtype, nullptr, stream);
 }
 
-extern "C" FSWEEP_API int fsweep_expm_backward_sp(const void* P, const void* G, void* gP, int n, int skew, int dtype,
-                                                  const void* E, const void* gsparsity, void* stream) {
+extern "C" FSWEEP_API int fsweep_expm_backward_sp_total(const void* P, const void* G, void* gP, int n, int skew,
+                                                        int dtype, const void* E, const void* gsparsity,
+                                                        const fsweep_total_job_t* total, void* stream) {
   if (!P || (!G && !gsparsity) || !gP || n < 1 || n > fsweep_expm_max_n() || (gsparsity && (!E || n < 2)))
     return FSWEEP_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FSWEEP_C64)
     return expm_backward_t<float>((const float*)P, (const float*)G, (float*)gP, n, skew, (const float*)E,
-                                  (const float*)gsparsity, st);
+                                  (const float*)gsparsity, total, st);
   if (dtype == FSWEEP_C128)
     return expm_backward_t<double>((const double*)P, (const double*)G, (double*)gP, n, skew, (const double*)E,
-                                   (const double*)gsparsity, st);
+                                   (const double*)gsparsity, total, st);
   return FSWEEP_E_BADARG;
+}
+
+extern "C" FSWEEP_API int fsweep_expm_backward_sp(const void* P, const void* G, void* gP, int n, int skew, int dtype,
+                                                  const void* E, const void* gsparsity, void* stream) {
+  return fsweep_expm_backward_sp_total(P, G, gP, n, skew, dtype, E, gsparsity, nullptr, stream);
 }
 
 extern "C" FSWEEP_API int fsweep_expm_backward(const void* P, const void* G, void* gP, int n, int skew, int dtype,
@@ -354,35 +671,12 @@ extern "C" FSWEEP_API int fsweep_sparsity_backward(const void* A, const void* gl
 // in ONE launch instead of a mul + add per criterion and a stack; the values land in the buffer the Trainer reads
 // back once per step.
 namespace {
-struct TotalArgs {
-  const void* part[FSWEEP_MAX_CRITERIA];
-  double alpha[FSWEEP_MAX_CRITERIA];
-  double scale[FSWEEP_MAX_CRITERIA];
-  int n;
-};
-// host_vals / host_seq (optional): the same values written straight into MAPPED PINNED host memory, then — behind a
-// system-wide fence — a launch counter: the host polls the counter and has the step's losses the moment they exist,
-// without a copy node in the graph and without waiting for the rest of the step (adjoint of the maps, optimizer).
 template <typename T>
-__global__ void weighted_total_kernel(const __grid_constant__ TotalArgs a, T* vals, volatile T* host_vals,
+__global__ void weighted_total_kernel(const __grid_constant__ TotalArgs a, T* vals, void* host_vals,
                                       volatile int* host_seq, int* seq_counter) {
   pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  T tot = T(0);
-  for (int i = 0; i < a.n; ++i) {
-    const T v = (T)a.scale[i] * *reinterpret_cast<const T*>(a.part[i]);
-    vals[i] = v;
-    if (host_vals) host_vals[i] = v;
-    tot += (T)a.alpha[i] * v;
-  }
-  vals[a.n] = tot;
-  if (host_vals) {
-    host_vals[a.n] = tot;
-    __threadfence_system();
-    const int s = *seq_counter + 1;
-    *seq_counter = s;
-    *host_seq = s;
-  }
+  total_job<T>(a, vals, host_vals, host_seq, seq_counter);
 }
 }  // namespace
 
@@ -402,10 +696,10 @@ extern "C" FSWEEP_API int fsweep_weighted_total_notify(const void* const* parts,
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FSWEEP_C64)
-    launch_pdl(weighted_total_kernel<float>, dim3(1), dim3(32), 0, st, a, (float*)vals, (volatile float*)host_vals,
+    launch_pdl(weighted_total_kernel<float>, dim3(1), dim3(32), 0, st, a, (float*)vals, host_vals,
                (volatile int*)host_seq, (int*)seq_counter);
   else if (dtype == FSWEEP_C128)
-    launch_pdl(weighted_total_kernel<double>, dim3(1), dim3(32), 0, st, a, (double*)vals, (volatile double*)host_vals,
+    launch_pdl(weighted_total_kernel<double>, dim3(1), dim3(32), 0, st, a, (double*)vals, host_vals,
                (volatile int*)host_seq, (int*)seq_counter);
   else
     return FSWEEP_E_BADARG;
@@ -600,13 +894,18 @@ struct AdamArgs {
   fsweep_adam_tensor_t t[FSWEEP_ADAM_MAX_TENSORS];
   int n;
   double beta1, beta2, eps;
+  RiderArgs rider;  // optional: block n of the grid
 };
 
 template <typename T>
 __global__ void __launch_bounds__(256) adam_step_kernel(const __grid_constant__ AdamArgs a, const float* __restrict__ lr) {
-  const fsweep_adam_tensor_t& q = a.t[blockIdx.x];
   __shared__ float s_step;
   pdl_sync();
+  if ((int)blockIdx.x == a.n) {
+    run_rider<T>(a.rider);
+    return;
+  }
+  const fsweep_adam_tensor_t& q = a.t[blockIdx.x];
   float* step = reinterpret_cast<float*>(q.step);
   if (threadIdx.x == 0) s_step = *step + 1.0f;
   __syncthreads();
@@ -631,11 +930,14 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const __grid_constant__ 
 }
 }  // namespace
 
-extern "C" FSWEEP_API int fsweep_adam_step(const fsweep_adam_tensor_t* tensors, int n, int dtype, const void* lr,
-                                           double beta1, double beta2, double eps, void* stream) {
+extern "C" FSWEEP_API int fsweep_adam_step_total(const fsweep_adam_tensor_t* tensors, int n, int dtype, const void* lr,
+                                                 double beta1, double beta2, double eps,
+                                                 const fsweep_total_job_t* total, void* stream) {
   if (!tensors || !lr || n < 1 || n > FSWEEP_ADAM_MAX_TENSORS) return FSWEEP_E_BADARG;
   AdamArgs a;
   a.n = n;
+  if (!fill_rider(total, &a.rider)) return FSWEEP_E_BADARG;
+  const int blocks = n + (total ? 1 : 0);
   a.beta1 = beta1;
   a.beta2 = beta2;
   a.eps = eps;
@@ -647,12 +949,17 @@ extern "C" FSWEEP_API int fsweep_adam_step(const fsweep_adam_tensor_t* tensors, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FSWEEP_C64)
-    launch_pdl(adam_step_kernel<float>, dim3(n), dim3(256), 0, st, a, (const float*)lr);
+    launch_pdl(adam_step_kernel<float>, dim3(blocks), dim3(256), 0, st, a, (const float*)lr);
   else if (dtype == FSWEEP_C128)
-    launch_pdl(adam_step_kernel<double>, dim3(n), dim3(256), 0, st, a, (const float*)lr);
+    launch_pdl(adam_step_kernel<double>, dim3(blocks), dim3(256), 0, st, a, (const float*)lr);
   else
     return FSWEEP_E_BADARG;
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}
+
+extern "C" FSWEEP_API int fsweep_adam_step(const fsweep_adam_tensor_t* tensors, int n, int dtype, const void* lr,
+                                           double beta1, double beta2, double eps, void* stream) {
+  return fsweep_adam_step_total(tensors, n, dtype, lr, beta1, beta2, eps, nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------- FP32 FMA peak probe

@@ -53,6 +53,7 @@ class SweepAdam(torch.optim.Optimizer):
             arr = (_lib.AdamTensor * len(entries))(*entries)
             lr = group["lr"]
             b1, b2 = group["betas"]
+            sweep.flush_deferred_total()  # (a captured step's criteria total that no backward kernel carried)
             with torch.cuda.device(lr.device):
                 _lib.check(_lib.lib().fsweep_adam_step(arr, len(entries),
                                                        _lib.C64 if dtype == torch.float32 else _lib.C128,

@@ -208,6 +208,7 @@ class Trainer:
             torch.autograd.backward(vals, grad_tensors=seed)
         vals = self._sync(vals.detach())
         self.optimizer.step()
+        sweep.flush_deferred_total()  # (a deferred criteria total nobody picked up)
         return vals
 
     def _eager_train_step(self, inputs, targets):
@@ -248,12 +249,17 @@ class Trainer:
         if type(self)._sync is Trainer._sync and os.environ.get("FLAMO_B200_NOTIFY", "1") != "0":
             slot = {"host_vals": torch.zeros(8 * 16, dtype=torch.uint8, pin_memory=True),
                     "host_seq": torch.zeros(1, dtype=torch.int32, pin_memory=True),
-                    "counter": torch.zeros(1, dtype=torch.int32, device=static_in.device), "expected": 0}
+                    "counter": torch.zeros(1, dtype=torch.int32, device=static_in.device), "expected": 0,
+                    "defer": os.environ.get("FLAMO_B200_DEFER_TOTAL", "0") != "0",
+                    "side": torch.cuda.Stream(static_in.device)
+                    if os.environ.get("FLAMO_B200_TOTAL_BRANCH", "0") != "0" else None}
         try:
             sweep.NOTIFY_SLOT = slot
             with torch.cuda.graph(graph):
                 self._zero_grad_captured()
                 out = self._train_core(static_in, static_tg)
+                if slot is not None and slot.get("join"):
+                    torch.cuda.current_stream(static_in.device).wait_stream(slot["side"])
                 notified = slot is not None and slot.get("used") == (out.numel(), out.dtype)
                 out_host = None
                 if not notified:
@@ -269,7 +275,12 @@ class Trainer:
             sweep.NOTIFY_SLOT = None
         if notified:
             slot["seq_np"] = slot["host_seq"].numpy()
-            slot["vals_np"] = slot["host_vals"].view(out.dtype)[:out.numel()].numpy()
+            if out.dtype == torch.float32:  # {value, launch number} pairs, see fsweep_weighted_total_notify
+                slot["vals_np"] = slot["host_vals"].view(torch.float32)[:2 * out.numel():2].numpy()
+                slot["pair_np"] = slot["host_vals"].view(torch.int32)[1:2 * out.numel():2].numpy()
+            else:
+                slot["vals_np"] = slot["host_vals"].view(out.dtype)[:out.numel()].numpy()
+                slot["pair_np"] = None
         else:
             slot = None
         g = (graph, static_in, static_tg, out_host, sweep.launch_count - n0, [None, None], slot)  # sweep kernels per replay
@@ -287,6 +298,12 @@ class Trainer:
                 torch.cuda.current_stream(device).synchronize()
                 if seq[0] != want:
                     raise RuntimeError(f"captured step: loss notification {int(seq[0])} != expected {want}")
+        pair = slot["pair_np"]
+        if pair is not None:  # float32: every value carries the launch number it belongs to (no fence on the device)
+            while not (pair == want).all():
+                spins += 1
+                if spins > 4000000:
+                    raise RuntimeError("captured step: loss values did not arrive")
         return slot["vals_np"].tolist()
 
     def _zero_grad_captured(self):

@@ -554,6 +554,8 @@ class OrthogonalMap(torch.autograd.Function):
                                                           torch.cuda.current_stream(P.device).cuda_stream))
         launch_count += 1
         ctx.save_for_backward(Pc, E)
+        if NOTIFY_SLOT is not None and ctx.needs_input_grad[0]:
+            NOTIFY_SLOT["carrier"] = True  # the adjoint of this map will run behind the criteria: it can carry their total
         return E, sp
 
     @staticmethod
@@ -568,12 +570,14 @@ class OrthogonalMap(torch.autograd.Function):
         Gc = G.to(Pc.dtype).contiguous() if G is not None else None
         gs = gsp.to(Pc.dtype).contiguous() if gsp is not None else None
         gP = torch.empty_like(Pc)
+        import ctypes as C
+
+        taken = take_deferred_total(Pc.dtype, Pc.device)  # a captured step's criteria total rides along (one extra block)
         with torch.cuda.device(Pc.device):
-            _lib.check(_lib.lib().fsweep_expm_backward_sp(Pc.data_ptr(), Gc.data_ptr() if Gc is not None else None,
-                                                           gP.data_ptr(), n, 1, _real_code(Pc.dtype),
-                                                           E.data_ptr() if gs is not None else None,
-                                                           gs.data_ptr() if gs is not None else None,
-                                                           torch.cuda.current_stream(Pc.device).cuda_stream))
+            _lib.check(_lib.lib().fsweep_expm_backward_sp_total(
+                Pc.data_ptr(), Gc.data_ptr() if Gc is not None else None, gP.data_ptr(), n, 1, _real_code(Pc.dtype),
+                E.data_ptr() if gs is not None else None, gs.data_ptr() if gs is not None else None,
+                C.byref(taken[0]) if taken is not None else None, torch.cuda.current_stream(Pc.device).cuda_stream))
         launch_count += 1
         return gP
 
@@ -746,6 +750,34 @@ class SparsityFunction(torch.autograd.Function):
 NOTIFY_SLOT = None
 
 
+def run_total_job(job, vals):
+    """Launch a criteria-total job (a _lib.TotalJob) on its own."""
+    global launch_count
+    with torch.cuda.device(vals.device):
+        _lib.check(_lib.lib().fsweep_weighted_total_notify(
+            job.parts, job.alphas, job.scales, job.n, _real_code(vals.dtype), job.vals, job.host_vals, job.host_seq,
+            job.seq_counter, torch.cuda.current_stream(vals.device).cuda_stream))
+    launch_count += 1
+
+
+def take_deferred_total(dtype=None, device=None):
+    """The pending criteria-total job of the step being captured, if any (and if it matches dtype / device)."""
+    slot = NOTIFY_SLOT
+    if slot is None or slot.get("job") is None:
+        return None
+    job, parts, vals = slot["job"]
+    if (dtype is not None and vals.dtype != dtype) or (device is not None and vals.device != device):
+        return None
+    slot["job"] = None
+    return job, parts, vals
+
+
+def flush_deferred_total():
+    taken = take_deferred_total()
+    if taken is not None:
+        run_total_job(taken[0], taken[2])
+
+
 class WeightedTotal(torch.autograd.Function):
     """vals = [s_0 part_0, ..., s_{n-1} part_{n-1}, sum_i alpha_i s_i part_i] in one launch (libfsweep
     fsweep_weighted_total): the Trainer's `loss += alpha * criterion` accumulation (reference trainer.py:184-188)
@@ -775,17 +807,35 @@ class WeightedTotal(torch.autograd.Function):
         aa = (C.c_double * n)(*[float(a) for a in alphas])
         ss = (C.c_double * n)(*[float(a) for a in scales])
         slot = NOTIFY_SLOT
-        with torch.cuda.device(vals.device):
-            stream = torch.cuda.current_stream(vals.device).cuda_stream
-            if slot is not None and slot.get("used") is None and slot["counter"].device == vals.device:
-                # the Trainer captures a step: the values also go straight to its pinned host buffer (see NOTIFY_SLOT)
-                slot["used"] = (n + 1, vals.dtype)
-                _lib.check(_lib.lib().fsweep_weighted_total_notify(
-                    pp, aa, ss, n, _real_code(vals.dtype), vals.data_ptr(), slot["host_vals"].data_ptr(),
-                    slot["host_seq"].data_ptr(), slot["counter"].data_ptr(), stream))
+        if slot is not None and slot.get("used") is None and slot["counter"].device == vals.device:
+            # the Trainer captures a step: the values also go straight to its pinned host buffer (see NOTIFY_SLOT)
+            slot["used"] = (n + 1, vals.dtype)
+            job = _lib.TotalJob()
+            for i in range(n):
+                job.parts[i], job.alphas[i], job.scales[i] = parts[i].data_ptr(), aa[i], ss[i]
+            job.n, job.vals = n, vals.data_ptr()
+            job.host_vals, job.host_seq = slot["host_vals"].data_ptr(), slot["host_seq"].data_ptr()
+            job.seq_counter = slot["counter"].data_ptr()
+            if slot.get("defer") and slot.get("carrier"):
+                # nothing on the device reads the values: they ride along with the first parameter-sized launch of
+                # the backward pass (OrthogonalMap.backward takes the job — early enough for the host to be back
+                # before the step ends; Trainer._train_core launches it on its own if nobody did)
+                slot["job"] = (job, parts, vals)
+            elif slot.get("side") is not None:
+                # on a parallel branch of the captured graph: off the critical path sweep -> adjoint maps -> optimizer
+                cur, side = torch.cuda.current_stream(vals.device), slot["side"]
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    run_total_job(job, vals)
+                vals.record_stream(side)
+                slot["join"] = True
             else:
-                _lib.check(_lib.lib().fsweep_weighted_total(pp, aa, ss, n, _real_code(vals.dtype), vals.data_ptr(), stream))
-        launch_count += 1
+                run_total_job(job, vals)
+        else:
+            with torch.cuda.device(vals.device):
+                _lib.check(_lib.lib().fsweep_weighted_total(pp, aa, ss, n, _real_code(vals.dtype), vals.data_ptr(),
+                                                             torch.cuda.current_stream(vals.device).cuda_stream))
+            launch_count += 1
         ctx.coef = (tuple(float(a) * float(c) for a, c in zip(alphas, scales)), tuple(float(c) for c in scales))
         for c in ctx.coef:  # created here, outside any later capture of the backward
             _const_tensor(c, vals.dtype, vals.device)

@@ -265,7 +265,10 @@ FSWEEP_API int fsweep_weighted_total(const void* const* parts, const double* alp
  * system-wide fence, by the number of this launch (1, 2, ...; seq_counter: device int32[1], zero at the start) into
  * host_seq (mapped pinned int32[1]).  A host thread that polls host_seq has the step's losses (reference
  * optimize/trainer.py:190 `loss.item()`) as soon as they exist: no copy node in the captured step, no wait for the
- * kernels behind the criteria.  host_vals == NULL: plain fsweep_weighted_total. */
+ * kernels behind the criteria.  host_vals == NULL: plain fsweep_weighted_total.
+ * Layout of host_vals: FSWEEP_C128 - double[n+1], published by a system-wide fence before host_seq is written;
+ * FSWEEP_C64 - (n+1) pairs {float value; int32 launch number}, each written with ONE aligned 8-byte store and no
+ * fence: the host waits until host_seq AND every pair carry the number it expects. */
 FSWEEP_API int fsweep_weighted_total_notify(const void* const* parts, const double* alphas, const double* scales, int n,
                                             int dtype, void* vals, void* host_vals, void* host_seq, void* seq_counter,
                                             void* stream);
@@ -285,6 +288,27 @@ typedef struct fsweep_adam_tensor {
 } fsweep_adam_tensor_t;
 FSWEEP_API int fsweep_adam_step(const fsweep_adam_tensor_t* tensors, int n, int dtype, const void* lr, double beta1,
                                 double beta2, double eps, void* stream);
+/* The same launch with a rider: one extra block evaluates the weighted total of the step's criteria (and notifies the
+ * host, see fsweep_weighted_total_notify) - the values are only read by the host, so inside a captured step they need
+ * no launch of their own.  total == NULL: plain fsweep_adam_step. */
+typedef struct fsweep_total_job {
+  const void* parts[FSWEEP_MAX_CRITERIA];
+  double alphas[FSWEEP_MAX_CRITERIA];
+  double scales[FSWEEP_MAX_CRITERIA];
+  int32_t n;
+  int32_t reserved;
+  void* vals;        /* device real[n+1] */
+  void* host_vals;   /* optional, with host_seq and seq_counter */
+  void* host_seq;
+  void* seq_counter;
+} fsweep_total_job_t;
+/* fsweep_expm_backward_sp with the same rider (it runs BEFORE the optimizer: the host has the losses while the adjoint of
+ * the map and the optimizer are still running). */
+FSWEEP_API int fsweep_expm_backward_sp_total(const void* P, const void* G, void* gP, int n, int skew, int dtype,
+                                             const void* E, const void* gsparsity, const fsweep_total_job_t* total,
+                                             void* stream);
+FSWEEP_API int fsweep_adam_step_total(const fsweep_adam_tensor_t* tensors, int n, int dtype, const void* lr, double beta1,
+                                      double beta2, double eps, const fsweep_total_job_t* total, void* stream);
 
 /* One-shot all-reduce (sum, then * scale) of a small float32 buffer that lives in symmetric / peer-mapped memory on
  * every rank of one node — the single exchange of a multi-GPU training step (flamo has no multi-device path; this
