@@ -28,7 +28,7 @@ EXPORTS = [
     "fsweep_forward", "fsweep_backward", "fsweep_forward_loss", "fsweep_backward_loss", "fsweep_last_launch_count",
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward", "fsweep_expm_forward_sp", "fsweep_expm_backward_sp", "fsweep_expm_backward_sp_total",
     "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total", "fsweep_weighted_total_notify",
-    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_allreduce_push", "fsweep_adam_step", "fsweep_adam_step_total", "fsweep_fma_probe", "fsweep_fma_probe_flops", "fsweep_biquad_design", "fsweep_svf_design",
+    "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_allreduce_push", "fsweep_allreduce_push_notify", "fsweep_adam_step", "fsweep_adam_step_total", "fsweep_fma_probe", "fsweep_fma_probe_flops", "fsweep_biquad_design", "fsweep_svf_design",
     "fsweep_rfft_supported", "fsweep_rfft_workspace_bytes", "fsweep_rfft_table", "fsweep_rfft",
 ]
 
@@ -142,6 +142,8 @@ def lib():
     L.fsweep_allreduce_p2p.argtypes = [vp, vp, i32, i32, i32, C.c_double, vp, vp]
     L.fsweep_allreduce_push.restype = i32
     L.fsweep_allreduce_push.argtypes = [C.POINTER(Seg), i32, vp, vp, i32, i32, i32, C.c_double, vp, vp]
+    L.fsweep_allreduce_push_notify.restype = i32
+    L.fsweep_allreduce_push_notify.argtypes = [C.POINTER(Seg), i32, vp, vp, i32, i32, i32, C.c_double, vp, vp, vp, vp, vp]
     L.fsweep_adam_step.restype = i32
     L.fsweep_adam_step.argtypes = [C.POINTER(AdamTensor), i32, i32, vp, C.c_double, C.c_double, C.c_double, vp]
     L.fsweep_adam_step_total.restype = i32

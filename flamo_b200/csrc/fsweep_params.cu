@@ -811,10 +811,20 @@ struct SegArgs {
 __global__ void __launch_bounds__(AR_THREADS) allreduce_push_kernel(const __grid_constant__ SegArgs sg,
                                                                    float* const* __restrict__ bufs,
                                                                    unsigned* const* __restrict__ pads, int rank, int world,
-                                                                   int cap, float scale, unsigned* epoch_ctr) {
+                                                                   int cap, float scale, unsigned* epoch_ctr,
+                                                                   unsigned long long* host_vals, volatile int* host_seq,
+                                                                   int* seq_counter) {
   __shared__ unsigned s_epoch;
+  __shared__ int s_seq;
   const int tid = threadIdx.x;
-  if (tid == 0) s_epoch = *epoch_ctr + 1u;
+  pdl_sync();
+  if (tid == 0) {
+    s_epoch = *epoch_ctr + 1u;
+    if (host_vals) {
+      s_seq = *seq_counter + 1;
+      *seq_counter = s_seq;
+    }
+  }
   __syncthreads();
   const unsigned epoch = s_epoch;
   const int n = sg.off[sg.n_segs];
@@ -854,15 +864,27 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_push_kernel(const __grid
       float s_ = 0.f;
       for (int r = 0; r < world; ++r) s_ += __ldcv(mybuf + (size_t)r * cap + idx);
       *seg_ptr[i] = s_ * scale;
+      // the LAST segment (the step's loss values) also goes to the host, each value with the launch number in one
+      // aligned 8-byte store (fsweep_weighted_total_notify's float32 layout): the host has the exchanged losses while
+      // the rest of this kernel and the optimizer are still running
+      if (host_vals != nullptr && idx >= sg.off[sg.n_segs - 1]) {
+        const int k = idx - sg.off[sg.n_segs - 1];
+        reinterpret_cast<volatile unsigned long long*>(host_vals)[k] =
+            (unsigned long long)__float_as_uint(s_ * scale) | ((unsigned long long)(unsigned)s_seq << 32);
+        if (idx == n - 1) *host_seq = s_seq;
+        __threadfence_system();
+      }
     }
   }
   if (tid == 0) *epoch_ctr = epoch;
 }
 }  // namespace
 
-extern "C" FSWEEP_API int fsweep_allreduce_push(const fsweep_seg_t* segs, int n_segs, void* const* peer_buffers,
-                                                void* const* peer_signal_pads, int rank, int world, int cap, double scale,
-                                                void* epoch_counter, void* stream) {
+extern "C" FSWEEP_API int fsweep_allreduce_push_notify(const fsweep_seg_t* segs, int n_segs, void* const* peer_buffers,
+                                                       void* const* peer_signal_pads, int rank, int world, int cap,
+                                                       double scale, void* epoch_counter, void* host_vals,
+                                                       void* host_seq, void* seq_counter, void* stream) {
+  if (host_vals && (!host_seq || !seq_counter)) return FSWEEP_E_BADARG;
   if (!segs || n_segs < 1 || n_segs > FSWEEP_AR_MAX_SEGS || !peer_buffers || !peer_signal_pads || !epoch_counter ||
       world < 1 || world > 64 || rank < 0 || rank >= world || cap < 1)
     return FSWEEP_E_BADARG;
@@ -877,10 +899,19 @@ extern "C" FSWEEP_API int fsweep_allreduce_push(const fsweep_seg_t* segs, int n_
     if (off > AR_THREADS * AR_PER || off > cap) return FSWEEP_E_BADARG;
   }
   a.off[n_segs] = (int)off;
-  allreduce_push_kernel<<<1, AR_THREADS, 0, (cudaStream_t)stream>>>(
-      a, reinterpret_cast<float* const*>(peer_buffers), reinterpret_cast<unsigned* const*>(peer_signal_pads), rank, world,
-      cap, (float)scale, reinterpret_cast<unsigned*>(epoch_counter));
+  launch_pdl(allreduce_push_kernel, dim3(1), dim3(AR_THREADS), 0, (cudaStream_t)stream, a,
+             reinterpret_cast<float* const*>(peer_buffers), reinterpret_cast<unsigned* const*>(peer_signal_pads), rank,
+             world, cap, (float)scale, reinterpret_cast<unsigned*>(epoch_counter),
+             reinterpret_cast<unsigned long long*>(host_vals), reinterpret_cast<volatile int*>(host_seq),
+             reinterpret_cast<int*>(seq_counter));
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
+}
+
+extern "C" FSWEEP_API int fsweep_allreduce_push(const fsweep_seg_t* segs, int n_segs, void* const* peer_buffers,
+                                                void* const* peer_signal_pads, int rank, int world, int cap, double scale,
+                                                void* epoch_counter, void* stream) {
+  return fsweep_allreduce_push_notify(segs, n_segs, peer_buffers, peer_signal_pads, rank, world, cap, scale,
+                                      epoch_counter, nullptr, nullptr, nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -53,11 +53,18 @@ class SweepAdam(torch.optim.Optimizer):
             arr = (_lib.AdamTensor * len(entries))(*entries)
             lr = group["lr"]
             b1, b2 = group["betas"]
+            import ctypes as C
+
+            taken = None
+            slot = sweep.NOTIFY_SLOT
+            if slot is not None and slot.get("adam_rider"):  # exchanged loss values of a captured multi-GPU step
+                taken = sweep.take_deferred_total(dtype, lr.device)
             sweep.flush_deferred_total()  # (a captured step's criteria total that no backward kernel carried)
             with torch.cuda.device(lr.device):
-                _lib.check(_lib.lib().fsweep_adam_step(arr, len(entries),
-                                                       _lib.C64 if dtype == torch.float32 else _lib.C128,
-                                                       lr.data_ptr(), float(b1), float(b2), float(group["eps"]),
-                                                       torch.cuda.current_stream(lr.device).cuda_stream))
+                _lib.check(_lib.lib().fsweep_adam_step_total(arr, len(entries),
+                                                             _lib.C64 if dtype == torch.float32 else _lib.C128,
+                                                             lr.data_ptr(), float(b1), float(b2), float(group["eps"]),
+                                                             C.byref(taken[0]) if taken is not None else None,
+                                                             torch.cuda.current_stream(lr.device).cuda_stream))
             sweep.launch_count += 1
         return loss

@@ -207,6 +207,8 @@ class Trainer:
             seed = sweep._const_tensor((0.0,) * (vals.numel() - 1) + (1.0,), vals.dtype, vals.device)
             torch.autograd.backward(vals, grad_tensors=seed)
         vals = self._sync(vals.detach())
+        if type(self)._sync is not Trainer._sync:
+            sweep.notify_values(vals)  # (captured multi-GPU step: the exchanged values ride with the optimizer's launch)
         self.optimizer.step()
         sweep.flush_deferred_total()  # (a deferred criteria total nobody picked up)
         return vals
@@ -241,13 +243,14 @@ class Trainer:
         self._zero_grad()
         n0 = sweep.launch_count
         # Loss read-back without a host round trip at the END of the step: the criteria-total kernel of the captured
-        # step stores the losses straight into mapped pinned host memory and bumps a sequence number behind them
+        # step stores the losses straight into mapped pinned host memory with a sequence number
         # (fsweep_weighted_total_notify); train_step polls that number and returns the loss while the adjoint of the
-        # maps and the optimizer are still running (stream-ordered for everything that follows).  Only for the plain
-        # single-process step: a trainer whose _sync exchanges the values between ranks reads them after the exchange.
+        # maps and the optimizer are still running (stream-ordered for everything that follows).  A trainer whose _sync
+        # exchanges the values between ranks gets them after the exchange, as a rider of the optimizer's launch
+        # (sweep.notify_values): no copy node and no stream synchronize there either.
         slot = None
-        if type(self)._sync is Trainer._sync and os.environ.get("FLAMO_B200_NOTIFY", "1") != "0":
-            slot = {"host_vals": torch.zeros(8 * 16, dtype=torch.uint8, pin_memory=True),
+        if os.environ.get("FLAMO_B200_NOTIFY", "1") != "0":
+            slot = {"after_sync": type(self)._sync is not Trainer._sync,"host_vals": torch.zeros(8 * 16, dtype=torch.uint8, pin_memory=True),
                     "host_seq": torch.zeros(1, dtype=torch.int32, pin_memory=True),
                     "counter": torch.zeros(1, dtype=torch.int32, device=static_in.device), "expected": 0,
                     "defer": os.environ.get("FLAMO_B200_DEFER_TOTAL", "0") != "0",

@@ -772,6 +772,28 @@ def take_deferred_total(dtype=None, device=None):
     return job, parts, vals
 
 
+def notify_values(vals):
+    """Captured multi-GPU step: `vals` (the loss values AFTER the exchange between the ranks) go to the Trainer's pinned
+    host buffer as a rider of the optimizer's launch (fsweep_adam_step_total) — no copy node, no stream synchronize."""
+    slot = NOTIFY_SLOT
+    n = vals.numel()
+    if (slot is None or slot.get("used") is not None or not slot.get("after_sync") or not vals.is_cuda
+            or vals.dtype not in (torch.float32, torch.float64) or not 1 <= n <= _lib.MAX_CRITERIA
+            or slot["counter"].device != vals.device):
+        return
+    vals = vals.contiguous()
+    scratch = torch.empty(n + 1, dtype=vals.dtype, device=vals.device)
+    job = _lib.TotalJob()
+    for i in range(n):  # identity "total": scratch[i] = host[i] = vals[i]
+        job.parts[i], job.alphas[i], job.scales[i] = vals.data_ptr() + i * vals.element_size(), 0.0, 1.0
+    job.n, job.vals = n, scratch.data_ptr()
+    job.host_vals, job.host_seq = slot["host_vals"].data_ptr(), slot["host_seq"].data_ptr()
+    job.seq_counter = slot["counter"].data_ptr()
+    slot["used"] = (n, vals.dtype)
+    slot["adam_rider"] = True
+    slot["job"] = (job, vals, scratch)
+
+
 def flush_deferred_total():
     taken = take_deferred_total()
     if taken is not None:
@@ -807,7 +829,8 @@ class WeightedTotal(torch.autograd.Function):
         aa = (C.c_double * n)(*[float(a) for a in alphas])
         ss = (C.c_double * n)(*[float(a) for a in scales])
         slot = NOTIFY_SLOT
-        if slot is not None and slot.get("used") is None and slot["counter"].device == vals.device:
+        if (slot is not None and slot.get("used") is None and not slot.get("after_sync")
+                and slot["counter"].device == vals.device):
             # the Trainer captures a step: the values also go straight to its pinned host buffer (see NOTIFY_SLOT)
             slot["used"] = (n + 1, vals.dtype)
             job = _lib.TotalJob()

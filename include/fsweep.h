@@ -336,6 +336,13 @@ typedef struct fsweep_seg {
 FSWEEP_API int fsweep_allreduce_push(const fsweep_seg_t* segs, int n_segs, void* const* peer_buffers,
                                      void* const* peer_signal_pads, int rank, int world, int cap, double scale,
                                      void* epoch_counter, void* stream);
+/* The same, and the LAST segment (the step's loss values) is also stored into mapped pinned host memory in
+ * fsweep_weighted_total_notify's float32 layout ({value, launch number} pairs, host_seq, seq_counter): the host has the
+ * exchanged losses while the optimizer is still running.  host_vals == NULL: plain fsweep_allreduce_push. */
+FSWEEP_API int fsweep_allreduce_push_notify(const fsweep_seg_t* segs, int n_segs, void* const* peer_buffers,
+                                            void* const* peer_signal_pads, int rank, int world, int cap, double scale,
+                                            void* epoch_counter, void* host_vals, void* host_seq, void* seq_counter,
+                                            void* stream);
 
 /* Real-to-complex FFT of the excitation along the time axis (reference flamo/processor/dsp.py:69-93 dsp.FFT and
  * :122-163 dsp.FFTAntiAlias: torch.fft.rfft(x [* envelope], n=nfft, dim=1)): x float32 [batch][n_time][channels]
