@@ -17,6 +17,8 @@
 #define FSWEEP_CTA_TC_DEFAULT true  // FSWEEP_CTA_TC=0 selects the SIMT elimination instead of the tensor-core one
 #endif
 #include "fsweep_stream.cuh"
+#include "fsweep_streamr.cuh"
+#include "fsweep_streamw.cuh"
 #include "fsweep_tpr.cuh"
 
 using namespace fsweep;
@@ -77,6 +79,8 @@ struct fsweep_plan {
   bool tpb_force = false;  // FSWEEP_FORCE_TPB=1 (tests): use them regardless of the bin count
   int stream_bps[2] = {0, 0};       // cached occupancy of the streaming kernels ...
   size_t stream_bps_smem[2] = {0, 0};  // ... for this dynamic shared memory size
+  int streamr_bps = 0;                 // the same for the register-state forward kernel
+  size_t streamr_bps_smem = 0;
   bool stream = false;  // TABLE-heavy program without recursion: streaming kernels, fsweep_stream.cuh
   StreamInfo sinfo;     // everything but tb / qc / threads (chosen per call from batch*cols)
   bool items = false;   // some op carries one coefficient set PER BATCH ITEM (fsweep_op_t::per_item): generic kernels, grid.y = item
@@ -577,6 +581,48 @@ bool stream_setup(const fsweep_plan* p, int64_t q, bool bwd, bool tma, StreamInf
   return *smem <= 200 * 1024;
 }
 
+// FSWEEP_STREAM_FWD selects the forward streaming kernel (read per call: tests toggle it).  Measured on a B200 on the
+// FIR chain of tools/measure_table_sweep.py (48 001 bins, 936 B of tables per bin, 4 columns; profiles/r02_notes.md):
+//   "reg"  (default) thread per (bin, column), state in registers (fsweep_streamr.cuh), cp.async tiles: 28.7 us
+//          ... with FSWEEP_STREAM_REG_TMA=1 the tiles come through the bulk-copy engine, two buffers: 32.8 us
+//   "smem" thread per (bin, column), state in shared memory (fsweep_stream.cuh): 34.8 us
+//   "warp" one warp per bin, state distributed over the lanes (fsweep_streamw.cuh): 49.1 us
+int stream_fwd_kind() {
+  const char* env = getenv("FSWEEP_STREAM_FWD");
+  if (env && env[0] == 'w') return 2;
+  if (env && env[0] == 's') return 0;
+  return 1;
+}
+
+// geometry of a call of the forward streaming kernels fsweep_streamr.cuh / fsweep_streamw.cuh
+bool streamr_setup(const fsweep_plan* p, const ProgK& P, int64_t q, int64_t bin_begin, bool warp_per_bin, StreamInfo* S,
+                   StreamRInfo* R, size_t* smem, int* w, bool* tma) {
+  if (!p->stream || q < 1 || q > 16 || (q & (q - 1)) != 0) return false;
+  *S = p->sinfo;
+  S->qc = (int)q;
+  S->threads = warp_per_bin ? SWARP_THREADS : 64;
+  S->tb = warp_per_bin ? 16 : S->threads / (int)q;
+  int width = std::max(P.in_ch, P.out_ch), units = 0;
+  // bulk copies need 16-byte aligned sources and sizes: an even number of bins per tile makes every size a multiple
+  // of 16 (rows are multiples of 8); the sources are aligned for whole tables, not for every bin shard
+  const char* want_tma = getenv("FSWEEP_STREAM_REG_TMA");
+  *tma = (warp_per_bin || (want_tma && want_tma[0] == '1')) && (S->tb % 2 == 0);
+  for (int i = 0; i < S->n_ops; ++i) {
+    width = std::max(width, std::max(P.ops[i].n_in, P.ops[i].n_out));
+    R->pad_units[i] = 0;
+    R->pad_off[i] = 0;
+    if (S->tab_off[i] < 0) continue;
+    R->pad_units[i] = S->row_bytes[i] / 8;
+    R->pad_off[i] = units;
+    units += S->tb * R->pad_units[i];
+    if ((reinterpret_cast<uintptr_t>(P.ops[i].coef) + (uintptr_t)bin_begin * S->row_bytes[i]) % 16) *tma = false;
+  }
+  R->tile_units = units;
+  *smem = (size_t)units * 8 * (*tma ? 2 : 1) + 16;
+  *w = width <= 4 ? 4 : (width <= 8 ? 8 : 16);
+  return width <= 16 && *smem <= 200 * 1024;
+}
+
 template <typename F>
 cudaError_t by_group(int G, F&& f) {
   switch (G) {
@@ -661,7 +707,7 @@ extern "C" const char* fsweep_plan_kernel_family(const fsweep_plan_t* plan, int6
   if (!plan) return "";
   if (plan->cta && plan->cta_tc) return backward ? "fsweep_cta_kernel<bwd,tc> (tcgen05 LU)" : "fsweep_cta_kernel<fwd,tc> (tcgen05 LU)";
   if (plan->cta) return backward ? "fsweep_cta_kernel<bwd>" : "fsweep_cta_kernel<fwd>";
-  if (plan->stream) return backward ? "fsweep_stream_kernel<bwd> (batch*cols a power of two <= 16)" : "fsweep_stream_kernel<fwd> (batch*cols a power of two <= 16)";
+  if (plan->stream) return backward ? "fsweep_stream_kernel<bwd> (batch*cols a power of two <= 16)" : "fsweep_streamr_kernel (fwd, state in registers; batch*cols a power of two <= 16)";
   if (use_tpc(plan, n_bins) && use_tpr(plan)) return backward ? "fsweep_tpr_kernel<bwd> (tpc family, matrix in registers)" : "fsweep_tpr_kernel<fwd> (tpc family, matrix in registers)";
   if (use_tpc(plan, n_bins)) return backward ? "fsweep_tpc_kernel<NP,bwd>" : "fsweep_tpc_kernel<NP,fwd>";
   if (use_tpb(plan, n_bins, backward != 0)) return backward ? "fsweep_tpb_bwd_kernel" : "fsweep_tpb_fwd_kernel";
@@ -794,11 +840,32 @@ int forward_impl(const fsweep_plan_t* plan_c, const void* const* coeffs, const v
   cfg.items = (int)items;
   const int dtype = plan->dtype;
   StreamInfo SI;
+  StreamRInfo RI;
   size_t ssmem = 0;
   bool stream_tma = false;
+  int rw = 0;
+  bool rtma = false;
   if (plan->cta) {
     cfg.grid = cta_grid(plan, false, n_bins, &e);
     if (e == cudaSuccess) e = launch_cta(plan->dtype, false, plan->cta_tc, cfg.grid, cfg.stream, P, plan->loop, A, plan->G);
+  } else if (!crit && stream_fwd_kind() != 0 &&
+             streamr_setup(plan, P, batch * cols, bin_begin, stream_fwd_kind() == 2, &SI, &RI, &ssmem, &rw, &rtma)) {
+    const bool wpb = stream_fwd_kind() == 2;
+    const size_t key = ssmem * 4 + (wpb ? 2 : 0) + (rtma ? 1 : 0);
+    int bps = plan->streamr_bps_smem == key ? plan->streamr_bps : 0;
+    if (bps == 0) {
+      e = wpb ? occupancy_streamw(SI.qc, rtma, ssmem, &bps) : occupancy_streamr(rw, rtma, SI.threads, ssmem, &bps);
+      if (e == cudaSuccess) {
+        plan->streamr_bps = bps;
+        plan->streamr_bps_smem = key;
+      }
+    }
+    if (e == cudaSuccess) {
+      const int64_t tiles = (n_bins + SI.tb - 1) / SI.tb;
+      cfg.grid = (int)std::min<int64_t>(tiles, (int64_t)std::max(1, bps) * std::max(1, plan->num_sms ? plan->num_sms : 148));
+      e = wpb ? launch_streamw(SI.qc, rtma, cfg.grid, ssmem, cfg.stream, P, SI, RI, A)
+              : launch_streamr(rw, rtma, cfg.grid, SI.threads, ssmem, cfg.stream, P, SI, RI, A);
+    }
   } else if (!crit && ((stream_tma = plan->stream && stream_tma_ok(P, plan->sinfo, bin_begin, false) &&
                                      stream_setup(plan, batch * cols, false, true, &SI, &ssmem)) ||
                        stream_setup(plan, batch * cols, false, false, &SI, &ssmem))) {

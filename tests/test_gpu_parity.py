@@ -273,7 +273,7 @@ def test_cta_per_bin_kernels_on_wide_fdn(N, B, tc, monkeypatch):
 
 
 @pytest.mark.parametrize("B,cols", [(1, None), (1, 4), (2, 2), (3, None)])
-@pytest.mark.parametrize("tma", [False, True], ids=["cp.async", "tma"])
+@pytest.mark.parametrize("tma", [False, True, None], ids=["cp.async", "tma", "reg"])
 def test_streaming_table_kernels(B, cols, tma, monkeypatch):
     """TABLE-heavy programs without recursion (FIR filter banks + gains, the shape of the real
     examples/e8_active_acoustics.py path) run on the streaming kernels (fsweep_stream.cuh) when batch*cols is a power of
@@ -283,6 +283,8 @@ def test_streaming_table_kernels(B, cols, tma, monkeypatch):
     from flamo_b200.processor import dsp, system
 
     monkeypatch.setenv("FSWEEP_STREAM_TMA", "1" if tma else "0")  # bulk-copy ring (UBLKCP + mbarrier) or cp.async tiles
+    # tma None: the forward pass on the register-state kernel (fsweep_streamr.cuh, the default)
+    monkeypatch.setenv("FSWEEP_STREAM_FWD", "reg" if tma is None else "smem")
     nfft, alias = 2048, 30.0
     M = nfft // 2 + 1
     desc = ("Series", [
@@ -337,6 +339,62 @@ def test_streaming_table_kernels(B, cols, tma, monkeypatch):
     for u, v in zip(ga, go):
         u, v = u.cpu().numpy(), v.numpy()
         assert np.abs(u - v).max() <= 1e-3 * np.abs(v).max()
+
+
+@pytest.mark.parametrize("widths", [(4, 13), (2, 4), (7, 8), (16, 16), (1, 3)])
+@pytest.mark.parametrize("B,cols", [(1, 4), (1, None), (2, 8)])
+def test_forward_streaming_kernels_widths(widths, B, cols, monkeypatch):
+    """The forward streaming kernels — thread per (bin, column) with register arrays of 4, 8 or 16 entries
+    (fsweep_streamr.cuh, default; tiles by cp.async and by bulk copies) and one warp per bin with the signal distributed
+    over the lanes (fsweep_streamw.cuh, opt-in) — on every width class, ragged widths, bin shards that are not tile
+    aligned and a partial tile, against the shared-memory-state kernel and the generic interpreter."""
+    from flamo_b200 import workloads as W
+    from flamo_b200.processor import dsp, system
+
+    n_m, n_l = widths
+    nfft, alias = 4096, 30.0
+    M = nfft // 2 + 1
+    desc = ("Series", [
+        ("Filter", dict(size=(10, n_l, n_m), requires_grad=False)),
+        ("parallelFilter", dict(size=(30, n_l), requires_grad=False)),
+        ("parallelGain", dict(size=(n_l,), requires_grad=False)),
+        ("Gain", dict(size=(n_l, n_l), requires_grad=False)),
+        ("Filter", dict(size=(15, n_m, n_l), requires_grad=False)),
+    ])
+
+    def run(env, shard):
+        for k in ("FSWEEP_DISABLE_STREAM", "FSWEEP_STREAM_FWD", "FSWEEP_STREAM_REG_TMA"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        saved = dict(sweep._PLANS)
+        sweep._PLANS.clear()
+        try:
+            torch.manual_seed(5)
+            model = W.build(desc, dsp, system, nfft, alias, dtype=torch.float32, device="cuda")
+            X = C.make_input(B, M, n_m, cols).to(torch.complex64).cuda()
+            with torch.no_grad():
+                if shard is None:
+                    Y = model(X)
+                else:
+                    with sweep.bin_shard(*shard):
+                        Y = model(X)
+            fam = [pl.kernel_family(M, False) for pl in sweep._PLANS.values()]
+            return Y, fam
+        finally:
+            sweep._PLANS.clear()
+            sweep._PLANS.update(saved)
+
+    for shard in (None, (3, 1999), (1030, 1041)):
+        Yw, fam_w = run({"FSWEEP_STREAM_FWD": "warp"}, shard)
+        Yr, fam_r = run({"FSWEEP_STREAM_FWD": "reg"}, shard)
+        Yt, _ = run({"FSWEEP_STREAM_FWD": "reg", "FSWEEP_STREAM_REG_TMA": "1"}, shard)
+        Ys, _ = run({"FSWEEP_STREAM_FWD": "smem"}, shard)
+        Yg, fam_g = run({"FSWEEP_DISABLE_STREAM": "1"}, shard)
+        assert any("streamr" in f for f in fam_r) and not any("stream" in f for f in fam_g)
+        ref = Yg.abs().max()
+        for Y in (Yw, Yr, Yt, Ys):
+            assert float((Y - Yg).abs().max()) <= 2e-6 * float(ref), (shard, widths)
 
 
 @pytest.mark.parametrize("scale", [0.3, 2.0, 6.0])
