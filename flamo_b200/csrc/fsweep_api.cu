@@ -600,13 +600,18 @@ bool streamr_setup(const fsweep_plan* p, const ProgK& P, int64_t q, int64_t bin_
   if (!p->stream || q < 1 || q > 16 || (q & (q - 1)) != 0) return false;
   *S = p->sinfo;
   S->qc = (int)q;
-  S->threads = warp_per_bin ? SWARP_THREADS : 64;
+  static const int r_threads = [] {
+    const char* e = getenv("FSWEEP_STREAMR_THREADS");
+    const int v = e ? atoi(e) : 64;
+    return (v == 64 || v == 128 || v == 256) ? v : 64;
+  }();
+  S->threads = warp_per_bin ? SWARP_THREADS : r_threads;
   S->tb = warp_per_bin ? 16 : S->threads / (int)q;
   int width = std::max(P.in_ch, P.out_ch), units = 0;
   // bulk copies need 16-byte aligned sources and sizes: an even number of bins per tile makes every size a multiple
   // of 16 (rows are multiples of 8); the sources are aligned for whole tables, not for every bin shard
   const char* want_tma = getenv("FSWEEP_STREAM_REG_TMA");
-  *tma = (warp_per_bin || (want_tma && want_tma[0] == '1')) && (S->tb % 2 == 0);
+  *tma = (S->tb % 2 == 0);  // (so far: "aligned")
   for (int i = 0; i < S->n_ops; ++i) {
     width = std::max(width, std::max(P.ops[i].n_in, P.ops[i].n_out));
     R->pad_units[i] = 0;
@@ -618,6 +623,8 @@ bool streamr_setup(const fsweep_plan* p, const ProgK& P, int64_t q, int64_t bin_
     if ((reinterpret_cast<uintptr_t>(P.ops[i].coef) + (uintptr_t)bin_begin * S->row_bytes[i]) % 16) *tma = false;
   }
   R->tile_units = units;
+  R->aligned16 = *tma ? 1 : 0;
+  *tma = *tma && (warp_per_bin || (want_tma && want_tma[0] == '1'));
   *smem = (size_t)units * 8 * (*tma ? 2 : 1) + 16;
   *w = width <= 4 ? 4 : (width <= 8 ? 8 : 16);
   return width <= 16 && *smem <= 200 * 1024;

@@ -25,6 +25,7 @@ struct StreamRInfo {
   int pad_units[MAX_OPS];  // row length in 8-byte units; 0: no table
   int pad_off[MAX_OPS];    // unit offset of op i's block (tb rows) inside the tile
   int tile_units;          // units per tile
+  int aligned16;           // every table block of the call starts on a 16-byte boundary: 16-byte cp.async granules
 };
 
 // Dense op body for EXACT input width NI and output-width class NO (a multiple of 4): o[m] = sum_n C[m][n] v[n] with
@@ -105,7 +106,7 @@ __device__ __forceinline__ void r_dense_op(const void* Cp, const float2 (&v)[W],
 // instruction on moving table bytes (the per-thread cp.async loop was 36 % of all issued instructions: r02t capture).
 // Otherwise: every thread copies 8-byte granules of the tile with cp.async, one buffer.
 template <int W, bool TMA>
-__global__ void __launch_bounds__(64) fsweep_streamr_kernel(const __grid_constant__ ProgK P,
+__global__ void __launch_bounds__(256) fsweep_streamr_kernel(const __grid_constant__ ProgK P,
                                                             const __grid_constant__ StreamInfo S,
                                                             const __grid_constant__ StreamRInfo R, const SweepArgs A) {
   extern __shared__ __align__(128) unsigned char rsm[];
@@ -161,7 +162,13 @@ __global__ void __launch_bounds__(64) fsweep_streamr_kernel(const __grid_constan
                                                             (size_t)(A.bin_begin + b0) * S.row_bytes[i]);
         float2* dst = sTab + R.pad_off[i];
         const int n8 = nb * R.pad_units[i];
-        for (int e = tid; e < n8; e += T) cp_async8(dst + e, src + e);
+        if (R.aligned16 && !(n8 & 1)) {
+          const float4* s4 = reinterpret_cast<const float4*>(src);
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          for (int e = tid; e < (n8 >> 1); e += T) __pipeline_memcpy_async(d4 + e, s4 + e, 16);
+        } else {
+          for (int e = tid; e < n8; e += T) cp_async8(dst + e, src + e);
+        }
       }
       __pipeline_commit();
     }

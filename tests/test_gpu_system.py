@@ -73,6 +73,34 @@ def test_graph_replay_equals_eager(dtype):
     assert la[-1] < la[0]  # it actually trains
 
 
+@pytest.mark.parametrize("env", [{}, {"FLAMO_B200_NOTIFY": "0"}, {"FLAMO_B200_DEFER_TOTAL": "1"},
+                                 {"FLAMO_B200_TOTAL_BRANCH": "1"}, {"FLAMO_B200_RFFT": "0"}],
+                         ids=["default", "copy-node", "rider", "branch", "cufft"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_captured_step_loss_delivery(env, dtype, monkeypatch):
+    """How the captured step hands its losses to the host — written into mapped pinned memory by the criteria-total
+    kernel and polled (default), as a rider block of the adjoint-map launch, on a side branch of the graph, or through a
+    copy node and a stream synchronize — and which input transform it runs (libfsweep's two-launch FFT or cuFFT) must not
+    change a single loss: every variant against the eager trainer, 12 steps, time-domain input (the FFT is inside)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    nfft = 32768
+    ma, mb = fdn_shell(8, nfft, dtype), fdn_shell(8, nfft, dtype)
+    mb.load_state_dict(ma.state_dict())
+    ta, tb = make_trainer(ma, nfft, graph=False), make_trainer(mb, nfft, graph=True)
+    x, y = colorless(nfft, dtype, B=1)
+    la = [ta.train_step((x, y)) for _ in range(12)]
+    lb = [tb.train_step((x, y)) for _ in range(12)]
+    assert tb.use_graph and len(tb._graphs) == 1, "the step was not captured"
+    (g,) = tb._graphs.values()
+    assert (g[6] is not None) == (env.get("FLAMO_B200_NOTIFY") != "0")  # the notification slot is in use
+    tol = 1e-5 if dtype == torch.float32 else 1e-6
+    assert np.allclose(la, lb, rtol=tol), (la, lb)
+    assert np.allclose(ta.train_loss_log["sparsity_loss"], tb.train_loss_log["sparsity_loss"], rtol=tol)
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        assert torch.allclose(pa, pb, rtol=tol * 10, atol=tol)
+
+
 def test_fused_abs_epilogue_equals_unfused():
     case = C.CASES["cfg4_active_full"]
     torch.manual_seed(case["seed"])
