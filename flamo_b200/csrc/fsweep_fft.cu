@@ -12,8 +12,8 @@
 //           pair a block holds — written straight into X[batch][nfft/2 + 1][channels].
 //
 // Inside a block an L-point DFT (L = a * b, radices <= 64) is two rounds of direct small DFTs in shared memory with
-// twiddles from a table of exp(-2 pi i j / nfft) that is computed once per (nfft, device) in float64 (fsweep_rfft_table):
-// no sincos in the step, every twiddle exact to float32 rounding.  Zero padding / cropping to nfft and the anti-alias
+// twiddles from tables that are computed once per (nfft, device) in float64 (fsweep_rfft_table) and laid out in the
+// order the threads read them: no sincos in the step, every twiddle exact to float32 rounding, every load coalesced.  Zero padding / cropping to nfft and the anti-alias
 // envelope gamma^-n are folded into the load.  Sizes whose half does not split into M1 * M2 with both <= 1024 and
 // radices <= 64 are refused (FSWEEP_E_UNSUPPORTED): the caller keeps cuFFT for those.
 #include <cuda_runtime.h>
@@ -70,7 +70,10 @@ bool plan_shape(int64_t nfft, FftShape* s) {
 struct FftArgs {
   const float* x;
   const float* env;  // optional envelope, nfft entries
-  const float2* T;   // exp(-2 pi i j / N), j < N
+  const float2* TA;  // [M1]          exp(-2 pi i j / M1): the radix twiddles of pass 1
+  const float2* TB;  // [M2]          exp(-2 pi i j / M2): the radix twiddles of pass 2
+  const float2* TC;  // [M2][M1]      W_M^(n2 k1(t)): the inter-pass twiddle of thread t of block n2
+  const float2* TD;  // [M1/2+1][2][M2] W_N^k of the two output bins of thread t of block k1
   float2* Y;         // [signals][M1][M2]
   float2* X;         // [batch][M + 1][C]
   long long xbs;     // batch stride of x, in elements (time stride C, channel stride 1)
@@ -141,9 +144,10 @@ __global__ void __launch_bounds__(1024) rfft_pass1_kernel(const FftArgs A) {
   float2* WL = fsm;
   float2* buf0 = fsm + L;
   float2* buf1 = buf0 + L;
-  // the twiddle table is constant: read ahead of the wait for the preceding kernel of the step (fsweep_pdl.cuh)
-  WL[t] = __ldg(A.T + (size_t)(A.s.N / L) * t);
-  const float2 tw = __ldg(A.T + 2 * (size_t)n2 * ((t / A.s.b1) + A.s.a1 * (t % A.s.b1)));  // W_M^(n2 k1), n2 k1 < M
+  // the twiddle tables are constant — read ahead of the wait for the preceding kernel of the step (fsweep_pdl.cuh) —
+  // and laid out in thread order: every load of a block is one contiguous run (the first kernels of a step run cold)
+  WL[t] = __ldg(A.TA + t);
+  const float2 tw = __ldg(A.TC + (size_t)n2 * L + t);  // W_M^(n2 k1) of the bin this thread ends up with
   pdl_sync();
   {
     const int b = sig / A.C, c = sig - b * A.C;
@@ -171,8 +175,8 @@ __global__ void __launch_bounds__(1024) rfft_pass2_kernel(const FftArgs A) {
   float2* WL = fsm;
   float2* buf0 = fsm + L;       // [2][L]
   float2* buf1 = buf0 + 2 * L;  // [2][L]
-  WL[t] = __ldg(A.T + (size_t)(A.s.N / L) * t);
-  const float2 wk0 = __ldg(A.T + k1 + M1 * t), wk1 = __ldg(A.T + k1m + M1 * t);  // W_N^k of the two output bins
+  WL[t] = __ldg(A.TB + t);
+  const float2 wk0 = __ldg(A.TD + (size_t)(2 * k1) * L + t), wk1 = __ldg(A.TD + (size_t)(2 * k1 + 1) * L + t);  // W_N^k
   pdl_sync();  // pass 1 is complete from here on
   buf0[t] = A.Y[((size_t)sig * M1 + k1) * L + t];
   buf0[L + t] = A.Y[((size_t)sig * M1 + k1m) * L + t];
@@ -201,12 +205,37 @@ __global__ void __launch_bounds__(1024) rfft_pass2_kernel(const FftArgs A) {
   }
 }
 
-__global__ void rfft_table_kernel(float2* T, int N) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
-  double s, c;
-  sincospi(2.0 * (double)j / (double)N, &s, &c);
-  T[j] = make_float2((float)c, (float)-s);
+// table sections, in this order: TA | TB | TC | TD (see FftArgs); every entry exp(-2 pi i * num / den) in float64
+__host__ __device__ inline size_t table_entries(const FftShape& s) {
+  return (size_t)s.M1 + s.M2 + (size_t)s.M + (size_t)(s.M1 / 2 + 1) * 2 * s.M2;
+}
+__global__ void rfft_table_kernel(float2* T, const FftShape sh) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= table_entries(sh)) return;
+  long long num, den;
+  size_t e = j;
+  if (e < (size_t)sh.M1) {
+    num = (long long)e;
+    den = sh.M1;
+  } else if ((e -= sh.M1) < (size_t)sh.M2) {
+    num = (long long)e;
+    den = sh.M2;
+  } else if ((e -= sh.M2) < (size_t)sh.M) {
+    const int n2 = (int)(e / sh.M1), t = (int)(e % sh.M1);
+    const int k1 = (t / sh.b1) + sh.a1 * (t % sh.b1);
+    num = (long long)n2 * k1;
+    den = sh.M;
+  } else {
+    e -= sh.M;
+    const int k1 = (int)(e / (2 * (size_t)sh.M2)), r = (int)(e % (2 * (size_t)sh.M2));
+    const int which = r / sh.M2, t = r % sh.M2;
+    const int kk1 = which ? (sh.M1 - k1) % sh.M1 : k1;
+    num = (long long)kk1 + (long long)sh.M1 * t;
+    den = sh.N;
+  }
+  double sn, cs;
+  sincospi(2.0 * (double)(num % den) / (double)den, &sn, &cs);
+  T[j] = make_float2((float)cs, (float)-sn);
 }
 
 }  // namespace
@@ -220,10 +249,16 @@ extern "C" FSWEEP_API size_t fsweep_rfft_workspace_bytes(int64_t nfft, int64_t s
   return (size_t)(nfft / 2) * (size_t)signals * sizeof(float2);
 }
 
+extern "C" FSWEEP_API int64_t fsweep_rfft_table_entries(int64_t nfft) {
+  FftShape s;
+  return plan_shape(nfft, &s) ? (int64_t)table_entries(s) : 0;
+}
+
 extern "C" FSWEEP_API int fsweep_rfft_table(void* table, int64_t nfft, void* stream) {
   FftShape s;
   if (!table || !plan_shape(nfft, &s)) return FSWEEP_E_BADARG;
-  rfft_table_kernel<<<(s.N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(table), s.N);
+  const size_t n = table_entries(s);
+  rfft_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(table), s);
   return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
 
@@ -240,7 +275,10 @@ extern "C" FSWEEP_API int fsweep_rfft(const void* x, int64_t batch, int64_t n_ti
   FftArgs A;
   A.x = reinterpret_cast<const float*>(x);
   A.env = reinterpret_cast<const float*>(envelope);
-  A.T = reinterpret_cast<const float2*>(table);
+  A.TA = reinterpret_cast<const float2*>(table);
+  A.TB = A.TA + s.M1;
+  A.TC = A.TB + s.M2;
+  A.TD = A.TC + s.M;
   A.Y = reinterpret_cast<float2*>(workspace);
   A.X = reinterpret_cast<float2*>(X);
   A.xbs = x_batch_stride;

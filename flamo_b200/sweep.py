@@ -692,8 +692,9 @@ def rfft(x: torch.Tensor, nfft: int, norm: str = "backward", envelope: torch.Ten
         key = (int(nfft), x.device.index)
         table = _RFFT_TABLES.get(key)
         if table is None:
-            table = torch.empty(nfft, dtype=torch.complex64, device=x.device)
+            table = torch.empty(L.fsweep_rfft_table_entries(int(nfft)), dtype=torch.complex64, device=x.device)
             _lib.check(L.fsweep_rfft_table(table.data_ptr(), int(nfft), stream))
+            torch.cuda.current_stream(x.device).synchronize()  # once per (nfft, device): later calls may use other streams
             _RFFT_TABLES[key] = table
         ws_bytes = L.fsweep_rfft_workspace_bytes(int(nfft), B * Cn)
         ws = torch.empty(ws_bytes // 8, dtype=torch.complex64, device=x.device)

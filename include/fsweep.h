@@ -348,12 +348,13 @@ FSWEEP_API int fsweep_allreduce_push_notify(const fsweep_seg_t* segs, int n_segs
  * :122-163 dsp.FFTAntiAlias: torch.fft.rfft(x [* envelope], n=nfft, dim=1)): x float32 [batch][n_time][channels]
  * (time stride = channels, batch stride given in elements), zero padded / cropped to nfft, X complex64
  * [batch][nfft/2 + 1][channels] = scale * DFT.  Two launches of a four-step FFT (fsweep_fft.cu) instead of cuFFT's five.
- * `table`: nfft complex64 entries exp(-2 pi i j / nfft), filled once per (nfft, device) by fsweep_rfft_table (float64
- * inside); `workspace`: fsweep_rfft_workspace_bytes(nfft, batch * channels); `envelope`: NULL or nfft float32 factors.
+ * `table`: fsweep_rfft_table_entries(nfft) complex64 twiddles, filled once per (nfft, device) by fsweep_rfft_table
+ * (float64 inside, laid out in the order the kernels' threads read them); `workspace`: fsweep_rfft_workspace_bytes(nfft, batch * channels); `envelope`: NULL or nfft float32 factors.
  * fsweep_rfft_supported(nfft) == 0 (and FSWEEP_E_UNSUPPORTED from fsweep_rfft): nfft is odd, < 512, or nfft / 2 does
  * not split into two factors <= 1024 made of radices <= 64 - the caller keeps cuFFT for those.  Capture safe. */
 FSWEEP_API int fsweep_rfft_supported(int64_t nfft);
 FSWEEP_API size_t fsweep_rfft_workspace_bytes(int64_t nfft, int64_t signals);
+FSWEEP_API int64_t fsweep_rfft_table_entries(int64_t nfft);
 FSWEEP_API int fsweep_rfft_table(void* table, int64_t nfft, void* stream);
 FSWEEP_API int fsweep_rfft(const void* x, int64_t batch, int64_t n_time, int64_t channels, int64_t x_batch_stride,
                            int64_t nfft, double scale, const void* envelope, const void* table, void* workspace,
