@@ -29,7 +29,7 @@ EXPORTS = [
     "fsweep_expm_max_n", "fsweep_expm_forward", "fsweep_expm_backward", "fsweep_expm_forward_sp", "fsweep_expm_backward_sp", "fsweep_expm_backward_sp_total",
     "fsweep_sparsity_forward", "fsweep_sparsity_backward", "fsweep_weighted_total", "fsweep_weighted_total_notify",
     "fsweep_allreduce_p2p", "fsweep_allreduce_p2p_max_n", "fsweep_allreduce_push", "fsweep_allreduce_push_notify", "fsweep_adam_step", "fsweep_adam_step_total", "fsweep_fma_probe", "fsweep_fma_probe_flops", "fsweep_biquad_design", "fsweep_svf_design",
-    "fsweep_rfft_supported", "fsweep_rfft_workspace_bytes", "fsweep_rfft_table_entries", "fsweep_rfft_table", "fsweep_rfft",
+    "fsweep_upload", "fsweep_rfft_supported", "fsweep_rfft_workspace_bytes", "fsweep_rfft_table_entries", "fsweep_rfft_table", "fsweep_rfft",
 ]
 
 
@@ -157,6 +157,8 @@ def lib():
     L.fsweep_fma_probe.argtypes = [vp, i32, i32, vp]
     L.fsweep_fma_probe_flops.restype = C.c_double
     L.fsweep_fma_probe_flops.argtypes = [i32, i32]
+    L.fsweep_upload.restype = i32
+    L.fsweep_upload.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, vp]
     L.fsweep_rfft_supported.restype = i32
     L.fsweep_rfft_supported.argtypes = [i64]
     L.fsweep_rfft_workspace_bytes.restype = C.c_size_t

@@ -13,6 +13,7 @@
 //  * the weighted total of the step's criteria (reference flamo/optimize/trainer.py:184-188).
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <cstdlib>
 
 #include "../../include/fsweep.h"
@@ -1003,6 +1004,53 @@ extern "C" FSWEEP_API int fsweep_adam_step_total(const fsweep_adam_tensor_t* ten
 extern "C" FSWEEP_API int fsweep_adam_step(const fsweep_adam_tensor_t* tensors, int n, int dtype, const void* lr,
                                            double beta1, double beta2, double eps, void* stream) {
   return fsweep_adam_step_total(tensors, n, dtype, lr, beta1, beta2, eps, nullptr, stream);
+}
+
+// ---------------------------------------------------------------------------------------------- batch upload
+// The batch of a step (reference optimize/trainer.py:176 `move_to_device`: inputs, targets) from PINNED host memory into
+// the captured step's static device buffers as ONE kernel that reads the host tensors directly over PCIe (unified
+// addressing: the pinned host pointer is a device pointer) instead of one DMA copy per tensor: the copies of the
+// headline step move 384 KB + 8 B, and each DMA is bracketed by a compute <-> copy engine switch that costs more than the
+// transfer.  All 16-byte chunks are requested at once (one per thread), cache-volatile loads (the host rewrites the
+// buffers between steps).
+namespace {
+struct UploadArgs {
+  const unsigned char* src[FSWEEP_UPLOAD_MAX];
+  unsigned char* dst[FSWEEP_UPLOAD_MAX];
+  long long bytes[FSWEEP_UPLOAD_MAX];
+  int n;
+};
+__global__ void __launch_bounds__(256) upload_kernel(const __grid_constant__ UploadArgs a) {
+  pdl_sync();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  for (int s = 0; s < a.n; ++s) {
+    const bool al = ((reinterpret_cast<uintptr_t>(a.src[s]) | reinterpret_cast<uintptr_t>(a.dst[s])) & 15) == 0;
+    const long long n16 = al ? a.bytes[s] / 16 : 0;
+    const int4* s4 = reinterpret_cast<const int4*>(a.src[s]);
+    int4* d4 = reinterpret_cast<int4*>(a.dst[s]);
+    for (long long i = tid; i < n16; i += nt) d4[i] = __ldcv(s4 + i);
+    for (long long i = n16 * 16 + tid; i < a.bytes[s]; i += nt) a.dst[s][i] = __ldcv(a.src[s] + i);
+  }
+}
+}  // namespace
+
+extern "C" FSWEEP_API int fsweep_upload(const void* const* host_src, void* const* dev_dst, const int64_t* bytes, int n,
+                                        void* stream) {
+  if (!host_src || !dev_dst || !bytes || n < 1 || n > FSWEEP_UPLOAD_MAX) return FSWEEP_E_BADARG;
+  UploadArgs a;
+  a.n = n;
+  long long most = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!host_src[i] || !dev_dst[i] || bytes[i] < 1) return FSWEEP_E_BADARG;
+    a.src[i] = reinterpret_cast<const unsigned char*>(host_src[i]);
+    a.dst[i] = reinterpret_cast<unsigned char*>(dev_dst[i]);
+    a.bytes[i] = bytes[i];
+    most = bytes[i] > most ? bytes[i] : most;
+  }
+  const long long blocks = (most / 16 + 255) / 256;
+  launch_pdl(upload_kernel, dim3((unsigned)(blocks < 1 ? 1 : (blocks > 1184 ? 1184 : blocks))), dim3(256), 0,
+             (cudaStream_t)stream, a);
+  return cudaGetLastError() == cudaSuccess ? FSWEEP_OK : FSWEEP_E_CUDA;
 }
 
 // ---------------------------------------------------------------------------------------------- FP32 FMA peak probe

@@ -290,6 +290,33 @@ class Trainer:
         self._graphs[key] = g
         return g
 
+    _UPLOAD_MAX_BYTES = 4 << 20
+
+    def _upload(self, pairs):
+        """Pinned host tensors -> the captured step's static buffers as ONE kernel reading the host memory over PCIe
+        (libfsweep fsweep_upload) instead of one DMA copy per tensor; False: the caller copies the ordinary way (pageable
+        or non-contiguous sources, dtype / shape mismatches, big batches — the DMA engine is the better mover there)."""
+        if os.environ.get("FLAMO_B200_UPLOAD_KERNEL", "1") == "0" or len(pairs) > 4:
+            return False
+        for dst, src in pairs:
+            if (src.is_cuda or not src.is_pinned() or not src.is_contiguous() or not dst.is_contiguous()
+                    or src.dtype != dst.dtype or src.shape != dst.shape
+                    or src.numel() * src.element_size() > self._UPLOAD_MAX_BYTES or src.numel() == 0):
+                return False
+        import ctypes as C
+
+        from .. import _lib, sweep
+
+        n = len(pairs)
+        srcs = (C.c_void_p * n)(*[s.data_ptr() for _, s in pairs])
+        dsts = (C.c_void_p * n)(*[d.data_ptr() for d, _ in pairs])
+        nbytes = (C.c_int64 * n)(*[s.numel() * s.element_size() for _, s in pairs])
+        dev = pairs[0][0].device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fsweep_upload(srcs, dsts, nbytes, n, torch.cuda.current_stream(dev).cuda_stream))
+        sweep.launch_count += 1
+        return True
+
     def _await_losses(self, slot, device):
         """Spin on the sequence number the captured step writes behind its losses (pinned host memory)."""
         slot["expected"] += 1
@@ -330,11 +357,15 @@ class Trainer:
                 # A DEVICE tensor that is the very tensor (storage, version) copied in by the previous step is already
                 # in the static buffer: a dataset resident in HBM costs no copy per step.  Host tensors are copied
                 # every step (from pinned memory: ONE asynchronous H2D copy per tensor).
+                pending = []
                 for slot, (dst, src) in enumerate(((static_in, inputs), (static_tg, targets))):
                     tag = (src.data_ptr(), src._version, src.device) if src.is_cuda else None
                     if tag is None or last[slot] != tag:
-                        dst.copy_(src, non_blocking=True)
+                        pending.append((dst, src))
                         last[slot] = tag
+                if pending and not self._upload(pending):
+                    for dst, src in pending:
+                        dst.copy_(src, non_blocking=True)
                 graph.replay()
                 sweep.launch_count += n_kernels
                 inval = getattr(self.net, "_invalidate_caches", None)

@@ -360,6 +360,14 @@ FSWEEP_API int fsweep_rfft(const void* x, int64_t batch, int64_t n_time, int64_t
                            int64_t nfft, double scale, const void* envelope, const void* table, void* workspace,
                            size_t workspace_bytes, void* X, void* stream);
 
+/* Upload of a step's batch (reference optimize/trainer.py:176 move_to_device: inputs and targets) from PINNED host memory
+ * (cudaHostAlloc / cudaHostRegister: with unified addressing the host pointer is a device pointer) into device buffers as
+ * ONE kernel that reads the host tensors over PCIe, instead of one DMA copy per tensor.  n <= FSWEEP_UPLOAD_MAX segments
+ * of bytes[i] bytes; the host must not rewrite a source before the stream has passed the call (as with
+ * cudaMemcpyAsync). */
+#define FSWEEP_UPLOAD_MAX 4
+FSWEEP_API int fsweep_upload(const void* const* host_src, void* const* dev_dst, const int64_t* bytes, int n, void* stream);
+
 /* FP32 FMA peak probe (bench.py's roofline denominator for the compute-bound sweeps; SURVEY.md section 8d "derive +
  * measure"): `blocks` blocks of 256 threads, 64 independent FFMAs per thread and round; fsweep_fma_probe_flops gives the
  * flop count of one launch, the caller times it with CUDA events.  out: device float[1] (never written in practice). */

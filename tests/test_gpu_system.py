@@ -101,6 +101,38 @@ def test_captured_step_loss_delivery(env, dtype, monkeypatch):
         assert torch.allclose(pa, pb, rtol=tol * 10, atol=tol)
 
 
+@pytest.mark.parametrize("kind", ["pinned", "pageable", "pinned-no-kernel"])
+def test_host_batches_reach_the_captured_step(kind, monkeypatch):
+    """Batches that live on the host (reference trainer.py:176 move_to_device): pinned ones are uploaded by ONE kernel that
+    reads them over PCIe (fsweep_upload), pageable ones by ordinary copies — every step must see the CURRENT content of
+    the host tensors (they change between steps here), odd byte counts and both tensors included."""
+    if kind == "pinned-no-kernel":
+        monkeypatch.setenv("FLAMO_B200_UPLOAD_KERNEL", "0")
+    nfft = 16384
+    ma, mb = fdn_shell(8, nfft, torch.float32), fdn_shell(8, nfft, torch.float32)
+    mb.load_state_dict(ma.state_dict())
+    ta, tb = make_trainer(ma, nfft, graph=True), make_trainer(mb, nfft, graph=True)
+    x, y = colorless(nfft, torch.float32, B=1)  # (1, 8193, 1): 32772 bytes, not a multiple of 16
+    xh, yh = x.cpu(), y.cpu()
+    if kind != "pageable":
+        xh, yh = xh.pin_memory(), yh.pin_memory()
+    n0 = sweep.launch_count
+    la, lb = [], []
+    for i in range(10):
+        scale = 1.0 + 0.1 * (i % 3)
+        xd, yd = x * scale, y * (2.0 - scale)
+        xh.copy_(xd)
+        yh.copy_(yd)
+        torch.cuda.synchronize()
+        la.append(ta.train_step((xd, yd)))
+        lb.append(tb.train_step((xh, yh)))
+        torch.cuda.synchronize()  # the host tensors are rewritten in the next iteration
+    assert tb.use_graph and len(tb._graphs) == 1
+    assert np.allclose(la, lb, rtol=1e-6), (la, lb)
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-6)
+
+
 def test_fused_abs_epilogue_equals_unfused():
     case = C.CASES["cfg4_active_full"]
     torch.manual_seed(case["seed"])
