@@ -576,7 +576,7 @@ bool stream_setup(const fsweep_plan* p, int64_t q, bool bwd, bool tma, StreamInf
   const size_t stage = (size_t)S->tb * S->bytes_per_bin;
   const size_t n_state = bwd ? (size_t)S->st_total : 2 * SW;
   *smem = (tma ? S_TMA_STAGES : S_STAGES) * stage + n_state * S->threads * 8 +
-          (bwd ? (size_t)2 * SW * S->threads * 8 + stage + (size_t)S->n_pgain_acc * 4 : 0) + 16 +
+          (bwd ? (size_t)2 * SW * S->threads * 8 + (size_t)S->n_pgain_acc * 4 : 0) + 16 +
           (tma ? 16 + 8 * S_TMA_STAGES : 0);
   return *smem <= 200 * 1024;
 }

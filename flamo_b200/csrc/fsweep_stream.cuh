@@ -118,7 +118,7 @@ __device__ __forceinline__ void table_cols(const float2* __restrict__ H, const f
   }
 
 // shared memory: [S_STAGES][tb * bytes_per_bin] tables | state columns [n_state][T] | (BWD) gradient columns [2][SW][T] |
-//                (BWD) [tb * bytes_per_bin] table-gradient staging | (BWD) [n_pgain_acc] block accumulators
+//                (BWD) [n_pgain_acc] block accumulators      (table gradients overwrite their tables in the tile)
 // where n_state = st_total (BWD: every op input is kept for its gradient) or 2*SW (forward: ping-pong).
 // ONE THREAD PER (bin, column): the whole op chain runs privately on thread-private shared-memory columns
 // (element i of thread t at [i*T + t]: conflict-free), so there is no barrier between ops and no idle row slot; the
@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
   unsigned char* sTab = ssm;
   float2* sState = reinterpret_cast<float2*>(ssm + NST * stage_bytes) + tid;  // element i: sState[i * T]
   float2* sGrad = sState + (size_t)n_state * T;                                      // [2][SW] columns (BWD)
-  unsigned char* sGTab = reinterpret_cast<unsigned char*>(sGrad - tid + (BWD ? (size_t)2 * SW * T : 0));
-  float* sAcc = reinterpret_cast<float*>(sGTab + (BWD ? stage_bytes : 0));
+  // (table gradients have no buffer of their own: dL/dH of an op overwrites H in the tile once the op's input gradient
+  // has been formed — a table is read exactly once in the reverse sweep — and leaves the block from there)
+  float* sAcc = reinterpret_cast<float*>(sGrad - tid + (BWD ? (size_t)2 * SW * T : 0));
   uint64_t* sBar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sAcc) +
                                                (((BWD ? (size_t)S.n_pgain_acc * 4 : 0) + 15) / 16) * 16);  // [NST], TMA
 
@@ -206,10 +207,10 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
     if constexpr (TMA) {
       // the stage refilled here was consumed in the previous iteration (its closing __syncthreads is behind us)
       if (tid == 0) {
-        issue_tma(tile + (long long)(NST - 1) * gridDim.x, (stage + NST - 1) % NST);
-        // the previous tile's gradient blocks have left the staging buffer before anyone writes it again (the
-        // __syncthreads in front of the reverse sweep publishes this)
+        // the stage refilled here held the previous tile, whose table gradients leave the block from that very
+        // buffer (bulk stores): they must have been READ before the bulk loads overwrite it
         if (BWD) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        issue_tma(tile + (long long)(NST - 1) * gridDim.x, (stage + NST - 1) % NST);
       }
       if (is_full(tile)) {
         mbar_wait(sBar + stage, (phases >> stage) & 1u);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
       __pipeline_wait_prior(NST - 1);
       __syncthreads();
     }
-    const unsigned char* tab = sTab + (size_t)stage * stage_bytes;
+    unsigned char* tab = sTab + (size_t)stage * stage_bytes;
     const long long bl = tile * tb + bi;
     const bool live = bl < A.n_bins;
 
@@ -322,11 +323,13 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
         const float2* v = sState + (size_t)S.st_off[i] * T;
         if (op.kind == FSWEEP_OP_TABLE) {
           const float2* H = reinterpret_cast<const float2*>(tab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
+          // g_in[n] = sum_m conj(H[m][n]) g[m]  (first: the table gradient below overwrites H)
+          FSWEEP_WIDTH_SWITCH(n_out, table_cols<WW>(H, go, gi, n_in, T))
           if (op.acc_mode == ACC_TABLE) {  // dL/dH[m][n] = sum over the bin's columns of g[m] conj(v[n])
             // the qc threads of a bin split the entries among themselves and each sums over ALL columns, reading
             // the neighbours' (thread-private) g and v columns: no shuffle chain per entry
-            float2* gt = reinterpret_cast<float2*>(sGTab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
-            __syncwarp();
+            float2* gt = reinterpret_cast<float2*>(tab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
+            __syncwarp();  // every column of the bin has read H
             const float2* go0 = go - c;  // column 0 of this bin
             const float2* v0 = v - c;
             int m = c / n_in, n = c - m * n_in;  // (m, n) walk along with e: no division per entry
@@ -345,11 +348,9 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
             }
             __syncwarp();  // nobody overwrites a gradient column while a neighbour still reads it
           }
-          // g_in[n] = sum_m conj(H[m][n]) g[m]
-          FSWEEP_WIDTH_SWITCH(n_out, table_cols<WW>(H, go, gi, n_in, T))
         } else if (op.kind == FSWEEP_OP_PTABLE) {
           const float2* H = reinterpret_cast<const float2*>(tab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
-          float2* gt = reinterpret_cast<float2*>(sGTab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
+          float2* gt = reinterpret_cast<float2*>(tab + S.tab_off[i] + (size_t)bi * S.row_bytes[i]);
           for (int m = 0; m < n_out; ++m) {
             const float2 gm = go[(size_t)m * T], vn = v[(size_t)m * T], h = H[m];
             if (op.acc_mode == ACC_TABLE) {
@@ -410,10 +411,10 @@ __global__ void __launch_bounds__(128) fsweep_stream_kernel(const __grid_constan
           if (op.acc_mode != ACC_TABLE || S.tab_off[i] < 0) continue;
           unsigned char* gdst = reinterpret_cast<unsigned char*>(op.gtab) + (size_t)(A.bin_begin + b0) * S.row_bytes[i];
           if (bulk) {
-            if (tid == 0) tma_store_1d(gdst, sGTab + S.tab_off[i], (uint32_t)(tb * S.row_bytes[i]));
+            if (tid == 0) tma_store_1d(gdst, tab + S.tab_off[i], (uint32_t)(tb * S.row_bytes[i]));
           } else {
             float2* dst = reinterpret_cast<float2*>(gdst);
-            const float2* src = reinterpret_cast<const float2*>(sGTab + S.tab_off[i]);
+            const float2* src = reinterpret_cast<const float2*>(tab + S.tab_off[i]);
             const int n8 = nb * S.row_bytes[i] / 8;
             for (int e = tid; e < n8; e += T) dst[e] = src[e];
           }
