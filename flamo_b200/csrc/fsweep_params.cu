@@ -796,11 +796,12 @@ extern "C" FSWEEP_API int fsweep_allreduce_p2p(void* const* peer_buffers, void* 
 // ---------------------------------------------------------------------------------------------------------
 // The same exchange as a PUSH, with the packing and unpacking inside: the step's gradients stay where autograd left
 // them (one tensor per parameter) and the kernel (1) gathers the segments and STORES them straight into slot [rank] of
-// every peer's receive area over NVLink (posted writes: nothing waits for a round trip), (2) releases one flag per peer,
-// (3) waits for the peers' flags in its own pad, (4) sums the `world` slots of its OWN receive area (local loads, fixed
-// rank order: bit-identical on every rank), scales, and scatters the result back into the segments.  The receive
-// areas are double buffered on the epoch's parity, so ONE flag round per step is enough: a rank that writes parity p
-// again (two steps later) has passed the step in between, which every peer enters only after it finished reading p.
+// every peer's receive area over NVLink (posted writes: nothing waits for a round trip), each value together with the
+// step's epoch in one 8-byte store, (2) polls the `world` slots of its OWN receive area (local loads) until they carry
+// the epoch, sums them in fixed rank order (bit-identical on every rank), scales, and scatters the result back into the
+// segments.  No fence, no flag round (until the end of round 2: a system fence, one flag per peer, a barrier).  The
+// receive areas are double buffered on the epoch's parity: a rank that writes parity p again (two steps later) has
+// passed the step in between, which needs every peer's values of that step — sent only after the peer finished reading p.
 // Replaces torch.cat + fsweep_allreduce_p2p (two flag rounds, peer loads) + views in flamo_b200/parallel.py.
 namespace {
 struct SegArgs {
@@ -829,6 +830,9 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_push_kernel(const __grid
   __syncthreads();
   const unsigned epoch = s_epoch;
   const int n = sg.off[sg.n_segs];
+  // Every value travels WITH the epoch in one aligned 8-byte store {value, epoch} (the "LL" protocol of the
+  // collective libraries): an 8-byte store is single-copy atomic, so a receiver that sees the epoch has the value — no
+  // system fence, no flag round, no barrier between pushing and summing.  Receive areas: 8-byte slots.
   const size_t par = (size_t)(epoch & 1u) * world * cap;  // this step's half of every receive area
   float* seg_ptr[AR_PER];
   // (1) gather + push
@@ -840,30 +844,25 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_push_kernel(const __grid
       int s_ = 0;
       while (idx >= sg.off[s_ + 1]) ++s_;
       seg_ptr[i] = sg.ptr[s_] + (idx - sg.off[s_]);
-      const float v = *seg_ptr[i];
-      for (int r = 0; r < world; ++r) bufs[r][par + (size_t)rank * cap + idx] = v;
+      const unsigned long long pk = (unsigned long long)__float_as_uint(*seg_ptr[i]) | ((unsigned long long)epoch << 32);
+      for (int r = 0; r < world; ++r)
+        reinterpret_cast<volatile unsigned long long*>(bufs[r])[par + (size_t)rank * cap + idx] = pk;
     }
   }
-  // (2) + (3): one flag round
-  __syncthreads();
-  if (tid < world) {
-    __threadfence_system();
-    st_release_sys(pads[tid] + AR_PAD_OFF + 128 + rank, epoch);
-    const unsigned* mine = pads[rank] + AR_PAD_OFF + 128 + tid;
-    unsigned spins = 0;
-    while ((int)(ld_acquire_sys(mine) - epoch) < 0 && ++spins < (1u << 26)) {
-    }
-    if ((int)(ld_acquire_sys(mine) - epoch) < 0) atomicExch(epoch_ctr + 1, 1u + (unsigned)tid);  // sticky error flag
-  }
-  __syncthreads();
-  // (4) local sum in rank order, scatter back
-  const float* mybuf = bufs[rank] + par;
+  // (2) wait for every rank's slot of the own area (local loads), sum in rank order, scatter back
+  const volatile unsigned long long* mybuf = reinterpret_cast<const volatile unsigned long long*>(bufs[rank]) + par;
 #pragma unroll
   for (int i = 0; i < AR_PER; ++i) {
     const int idx = tid + i * AR_THREADS;
     if (idx < n) {
       float s_ = 0.f;
-      for (int r = 0; r < world; ++r) s_ += __ldcv(mybuf + (size_t)r * cap + idx);
+      for (int r = 0; r < world; ++r) {
+        unsigned long long pk = mybuf[(size_t)r * cap + idx];
+        unsigned spins = 0;
+        while ((unsigned)(pk >> 32) != epoch && ++spins < (1u << 24)) pk = mybuf[(size_t)r * cap + idx];
+        if ((unsigned)(pk >> 32) != epoch) atomicExch(epoch_ctr + 1, 1u + (unsigned)r);  // sticky error flag
+        s_ += __uint_as_float((unsigned)pk);
+      }
       *seg_ptr[i] = s_ * scale;
       // the LAST segment (the step's loss values) also goes to the host, each value with the launch number in one
       // aligned 8-byte store (fsweep_weighted_total_notify's float32 layout): the host has the exchanged losses while

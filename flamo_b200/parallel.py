@@ -87,8 +87,8 @@ class DataParallelTrainer(Trainer):
                 return None
             import torch.distributed._symmetric_memory as symm_mem
 
-            # receive area of the push kernel: [2 (epoch parity)][world][numel]
-            buf = symm_mem.empty(2 * self.world * numel, dtype=dtype, device=device)
+            # receive area of the push kernel: [2 (epoch parity)][world][numel] 8-byte slots {value, epoch}
+            buf = symm_mem.empty(2 * 2 * self.world * numel, dtype=dtype, device=device)
             buf.zero_()
             hdl = symm_mem.rendezvous(buf, self.pg if self.pg is not None else dist.group.WORLD)
             if hdl.signal_pad_size < 2048 or hdl.world_size != self.world:

@@ -323,11 +323,12 @@ FSWEEP_API int fsweep_allreduce_p2p(void* const* peer_buffers, void* const* peer
                                     double scale, void* epoch_counter, void* stream);
 
 /* The same exchange as ONE push kernel that also packs and unpacks: `segs` are the step's float32 gradient tensors (and the
- * loss values), reduced IN PLACE.  Every rank's receive area (peer_buffers[r], symmetric memory) holds 2 * world * cap
- * floats (double buffered on the epoch parity: one flag round per call); cap >= the total number of values.  Gathers the
- * segments, stores them into slot [rank] of every peer's area over NVLink, one release / acquire flag round, then sums
- * its own area's slots in rank order (bit-identical on every rank), scales and scatters back.  epoch_counter and the
- * signal pads as above (a different flag range: both kernels may share pads).  Capture safe. */
+ * loss values), reduced IN PLACE.  Every rank's receive area (peer_buffers[r], symmetric memory, 8-byte aligned, zeroed
+ * once) holds 2 * world * cap 8-BYTE slots (double buffered on the epoch parity); cap >= the total number of values.
+ * Gathers the segments, stores each value together with the step's epoch ({value, epoch}, one 8-byte store) into slot
+ * [rank] of every peer's area over NVLink, polls its own area until every slot carries the epoch, sums the slots in
+ * rank order (bit-identical on every rank), scales and scatters back: no fence, no flag round.  epoch_counter as
+ * above; the signal pads are not used any more (kept in the signature).  Capture safe. */
 #define FSWEEP_AR_MAX_SEGS 32
 typedef struct fsweep_seg {
   void* ptr;     /* device float32 */

@@ -92,7 +92,7 @@ for n in (83, 4227):
 # ---- the push kernel (fsweep_allreduce_push): segments reduced in place, one flag round, double-buffered receive areas
 for sizes in ((64, 8, 8, 3), (4096, 64, 64, 3)):
     n = sum(sizes)
-    recv = symm_mem.empty(2 * world * n, dtype=torch.float32, device=dev)
+    recv = symm_mem.empty(2 * 2 * world * n, dtype=torch.float32, device=dev)  # 8-byte slots {value, epoch}
     recv.zero_()
     hdl = symm_mem.rendezvous(recv, dist.group.WORLD)
     epoch = torch.zeros(2, dtype=torch.int32, device=dev)
