@@ -16,7 +16,6 @@ LIB_PATH = os.path.join(_HERE, "libfsweep.so")
 OK, E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_CUDA = 0, -1, -2, -3, -4
 C64, C128 = 0, 1
 DT_GRAD32 = 256  # FSWEEP_DT_GRAD32: OR-ed into C128 for float32 models swept in float64 arithmetic
-DT_GRAD32 = 256  # FSWEEP_DT_GRAD32
 EPI_NONE, EPI_ABS = 0, 1
 CRIT_MSE, CRIT_MSE_CHSUM = 1, 2
 OP_GAIN, OP_PGAIN, OP_SOS, OP_PSOS, OP_DELAY, OP_PDELAY, OP_TABLE, OP_PTABLE, OP_RECURSION = range(1, 10)
