@@ -193,10 +193,14 @@ class Trainer:
         """Hook between backward and the optimizer step (multi-GPU trainers all-reduce here)."""
         return vals
 
+    def _early_vals(self, vals):
+        """Hook between the criteria and the backward pass (multi-GPU trainers may exchange the loss values here)."""
+
     def _train_core(self, inputs, targets):
         from .. import sweep
 
         vals = self._loss_vector(inputs, targets)
+        self._early_vals(vals)
         if getattr(self, "_parts", None) is not None:
             parts, weights = self._parts
             self._parts = None
@@ -255,7 +259,8 @@ class Trainer:
                     "counter": torch.zeros(1, dtype=torch.int32, device=static_in.device), "expected": 0,
                     "defer": os.environ.get("FLAMO_B200_DEFER_TOTAL", "0") != "0",
                     "side": torch.cuda.Stream(static_in.device)
-                    if os.environ.get("FLAMO_B200_TOTAL_BRANCH", "0") != "0" else None}
+                    if (os.environ.get("FLAMO_B200_TOTAL_BRANCH", "0") != "0"
+                        or type(self)._sync is not Trainer._sync) else None}
         try:
             sweep.NOTIFY_SLOT = slot
             with torch.cuda.graph(graph):

@@ -94,6 +94,13 @@ class DataParallelTrainer(Trainer):
             if hdl.signal_pad_size < 2048 or hdl.world_size != self.world:
                 return None
             self._p2p = (hdl, torch.zeros(2, dtype=torch.int32, device=device))  # [epoch, sticky error flag]
+            # a second, tiny receive area for the step's loss VALUES: they exist before the backward pass, so a
+            # captured step exchanges them early, on a side branch of its graph (_early_vals)
+            n_vals = self.n_loss + 1
+            vbuf = symm_mem.empty(2 * 2 * self.world * n_vals, dtype=dtype, device=device)
+            vbuf.zero_()
+            vhdl = symm_mem.rendezvous(vbuf, self.pg if self.pg is not None else dist.group.WORLD)
+            self._p2p_vals = (vhdl, torch.zeros(2, dtype=torch.int32, device=device), vbuf, n_vals)
             torch.cuda.synchronize(device)
             dist.barrier(self.pg)
             return buf
@@ -109,6 +116,7 @@ class DataParallelTrainer(Trainer):
         total = sum(p.numel() for p in ps)
         dt = ps[0].dtype
         self._p2p = None
+        self._p2p_vals = None
         self._ps = ps
         self._n_grad = total
         self._cap = total + n_vals
@@ -144,6 +152,40 @@ class DataParallelTrainer(Trainer):
         weight = [1.0 / self.world if self.requires_model[i] else w_pred for i in range(len(self.criterion))]
         return self._criteria(est, done, tg, weight=weight)
 
+    def _early_vals(self, vals):
+        """Captured step, peer-memory exchange available: the loss values — final before the backward pass starts — are
+        exchanged between the ranks and handed to the host (sweep.NOTIFY_SLOT) by their own launch of the push kernel
+        on a SIDE BRANCH of the graph, concurrently with the adjoint maps.  The host has them ~10 us before the step
+        ends instead of after the gradient exchange, which is what its round trip (poll -> return -> next enqueue)
+        needs to stay off the critical path; `_sync` then exchanges the gradients only."""
+        import os
+
+        from . import _lib
+
+        self._vals_exchanged = False
+        slot = sweep.NOTIFY_SLOT
+        pv = getattr(self, "_p2p_vals", None)
+        if (self.world == 1 or slot is None or not slot.get("after_sync") or slot.get("used") is not None or pv is None
+                or slot.get("side") is None or vals.dtype != torch.float32 or not vals.is_contiguous()
+                or vals.numel() != pv[3] or os.environ.get("FLAMO_B200_EARLY_VALS", "1") == "0"):
+            return
+        hdl, epoch, _, n_vals = pv
+        scale = 1.0 / self.world if self.shard == "batch" else 1.0
+        v = vals.detach()
+        segs = (_lib.Seg * 1)(_lib.Seg(v.data_ptr(), v.numel()))
+        cur, side = torch.cuda.current_stream(v.device), slot["side"]
+        side.wait_stream(cur)
+        slot["used"] = (v.numel(), v.dtype)
+        with torch.cuda.stream(side), torch.cuda.device(v.device):
+            _lib.check(_lib.lib().fsweep_allreduce_push_notify(
+                segs, 1, hdl.buffer_ptrs_dev, hdl.signal_pad_ptrs_dev, hdl.rank, hdl.world_size, n_vals, scale,
+                epoch.data_ptr(), slot["host_vals"].data_ptr(), slot["host_seq"].data_ptr(), slot["counter"].data_ptr(),
+                side.cuda_stream))
+        v.record_stream(side)
+        slot["join"] = True
+        sweep.launch_count += 1
+        self._vals_exchanged = True
+
     def _sync(self, vals):
         if self.world == 1:
             return vals
@@ -161,12 +203,14 @@ class DataParallelTrainer(Trainer):
                 elif not p.grad.is_contiguous():
                     p.grad = p.grad.contiguous()
             vals = vals.contiguous()
-            tensors = [p.grad for p in self._ps] + [vals]
+            early = getattr(self, "_vals_exchanged", False)  # the values went ahead on their own (_early_vals)
+            self._vals_exchanged = False
+            tensors = [p.grad for p in self._ps] + ([] if early else [vals])
             segs = (_lib.Seg * len(tensors))(*[_lib.Seg(t.data_ptr(), t.numel()) for t in tensors])
             hdl, epoch = self._p2p
             # captured step: the exchanged loss values go straight to the Trainer's pinned host buffer (sweep.NOTIFY_SLOT)
             slot = sweep.NOTIFY_SLOT
-            notify = (slot is not None and slot.get("used") is None and slot.get("after_sync")
+            notify = (not early and slot is not None and slot.get("used") is None and slot.get("after_sync")
                       and vals.dtype == torch.float32 and vals.numel() <= 8 and slot["counter"].device == vals.device)
             if notify:
                 slot["used"] = (vals.numel(), vals.dtype)
@@ -195,6 +239,8 @@ class DataParallelTrainer(Trainer):
         A host read: call it outside the captured step (train_step does, every `check_every` steps)."""
         if getattr(self, "_p2p", None) is not None:
             flag = int(self._p2p[1][1].item())
+            if not flag and getattr(self, "_p2p_vals", None) is not None:
+                flag = int(self._p2p_vals[1][1].item())
             if flag:
                 raise RuntimeError(f"fsweep_allreduce_p2p: rank {flag - 1} did not arrive at the exchange (timeout); "
                                    "the gradients of that step are invalid")
