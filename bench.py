@@ -179,11 +179,18 @@ def time_cpu_reference(steps: int, warmup: int):
     loss = None
     for _ in range(warmup):
         tr.train_step(x, y)
+    import gc
+
     ts = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        loss = tr.train_step(x, y)
-        ts.append(time.perf_counter() - t0)
+    gc.collect()
+    gc.disable()  # (as in the GPU arm's timed loop)
+    try:
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            loss = tr.train_step(x, y)
+            ts.append(time.perf_counter() - t0)
+    finally:
+        gc.enable()
     t = sum(ts) / len(ts)
     M = NFFT // 2 + 1
     return BATCH * M * N_DELAYS / t, t, statistics.median(ts), loss
@@ -474,16 +481,25 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     def run(steps, data):
+        import gc
+
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         loss = None
-        for i in range(steps):
-            flush.fill_(i & 0xFF)
-            starts[i].record()
-            loss = trainer.train_step(data)
-            ends[i].record()
-        torch.cuda.synchronize()
+        gc.collect()
+        gc.disable()  # a generation-0 collection in the middle of a 50 us step is a 100+ us outlier (on N ranks: N chances)
+        try:
+            for i in range(steps):
+                flush.fill_(i & 0xFF)
+                starts[i].record()
+                loss = trainer.train_step(data)
+                ends[i].record()
+            torch.cuda.synchronize()
+        finally:
+            gc.enable()
         ts = [s.elapsed_time(e) * 1e-3 for s, e in zip(starts, ends)]
+        if os.environ.get("BENCH_DUMP_STEPS"):  # per-step times (us), for looking at outliers
+            print(f"[rank {rank}] steps:", " ".join(f"{t * 1e6:.0f}" for t in ts), file=sys.stderr, flush=True)
         return sum(ts), statistics.median(ts), loss
 
     # lazy state + graph capture happen in the first few calls; they are not part of W

@@ -93,14 +93,16 @@ class DataParallelTrainer(Trainer):
             hdl = symm_mem.rendezvous(buf, self.pg if self.pg is not None else dist.group.WORLD)
             if hdl.signal_pad_size < 2048 or hdl.world_size != self.world:
                 return None
-            self._p2p = (hdl, torch.zeros(2, dtype=torch.int32, device=device))  # [epoch, sticky error flag]
+            # [epoch, sticky error flag] of the gradient exchange, then of the loss-value exchange: one tensor, one read
+            self._flags = torch.zeros(4, dtype=torch.int32, device=device)
+            self._p2p = (hdl, self._flags[0:2])
             # a second, tiny receive area for the step's loss VALUES: they exist before the backward pass, so a
             # captured step exchanges them early, on a side branch of its graph (_early_vals)
             n_vals = self.n_loss + 1
             vbuf = symm_mem.empty(2 * 2 * self.world * n_vals, dtype=dtype, device=device)
             vbuf.zero_()
             vhdl = symm_mem.rendezvous(vbuf, self.pg if self.pg is not None else dist.group.WORLD)
-            self._p2p_vals = (vhdl, torch.zeros(2, dtype=torch.int32, device=device), vbuf, n_vals)
+            self._p2p_vals = (vhdl, self._flags[2:4], vbuf, n_vals)
             torch.cuda.synchronize(device)
             dist.barrier(self.pg)
             return buf
@@ -238,18 +240,35 @@ class DataParallelTrainer(Trainer):
         """Raises if the peer-memory all-reduce ever timed out waiting for a peer (its results are then undefined).
         A host read: call it outside the captured step (train_step does, every `check_every` steps)."""
         if getattr(self, "_p2p", None) is not None:
-            flag = int(self._p2p[1][1].item())
-            if not flag and getattr(self, "_p2p_vals", None) is not None:
-                flag = int(self._p2p_vals[1][1].item())
+            f = self._flags.tolist()
+            flag = f[1] or f[3]
             if flag:
                 raise RuntimeError(f"fsweep_allreduce_p2p: rank {flag - 1} did not arrive at the exchange (timeout); "
                                    "the gradients of that step are invalid")
 
-    check_every = 64
+    check_every = 256
+
+    def _check_exchange_async(self):
+        """The sticky error flags of the exchange kernels without a synchronize: every `check_every` steps a non-blocking
+        copy brings them into pinned host memory, and the copy issued `check_every` steps EARLIER is looked at (it is
+        long complete: later steps' losses have been seen since).  A blocking read here was a 60 - 140 us outlier every 64
+        steps of a 50 us step (and two sliced copies were hardly better: the cost is host time inside train_step).  `check_exchange()` is the immediate, blocking form."""
+        if getattr(self, "_p2p", None) is None:
+            return
+        host = getattr(self, "_err_host", None)
+        if host is None:
+            host = self._err_host = torch.zeros(4, dtype=torch.int32, pin_memory=True)
+        else:
+            f = host.tolist()
+            flag = f[1] or f[3]
+            if flag:
+                raise RuntimeError(f"fsweep_allreduce_push: rank {flag - 1} did not arrive at the exchange (timeout); "
+                                   "the gradients since the previous check are invalid")
+        host.copy_(self._flags, non_blocking=True)
 
     def train_step(self, data):
         out = super().train_step(data)
         self._n_steps = getattr(self, "_n_steps", 0) + 1
         if self._n_steps % self.check_every == 1:
-            self.check_exchange()
+            self._check_exchange_async()
         return out
