@@ -486,7 +486,6 @@ def gpu_arm(args):
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         loss = None
-        gc.collect()
         gc.disable()  # a generation-0 collection in the middle of a 50 us step is a 100+ us outlier (on N ranks: N chances)
         try:
             for i in range(steps):
@@ -508,7 +507,10 @@ def gpu_arm(args):
     warmup = max(3, args.warmup)
     run(warmup, (x_dev, y_dev))
 
+    import gc
+
     sampler = ClockSampler(local)
+    gc.collect()  # (in front of the barrier: a collection behind it would skew the ranks' start by milliseconds)
     barrier()
     launches0 = sweep.launch_count
     sampler.start()
@@ -522,6 +524,7 @@ def gpu_arm(args):
 
     # end to end: inputs in pinned host memory, H2D inside the timed region, loss read back
     run(warmup, (x_host, y_host))
+    gc.collect()
     barrier()
     t_e2e, med_e2e, _ = run(args.steps, (x_host, y_host))
     barrier()
