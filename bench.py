@@ -511,9 +511,9 @@ def gpu_arm(args):
 
     sampler = ClockSampler(local)
     gc.collect()  # (in front of the barrier: a collection behind it would skew the ranks' start by milliseconds)
+    sampler.start()  # (its thread starts up in front of the barrier too: the first timed steps are not perturbed by it)
     barrier()
     launches0 = sweep.launch_count
-    sampler.start()
     t_dev, med_dev, loss = run(args.steps, (x_dev, y_dev))
     barrier()
     launches = sweep.launch_count - launches0
