@@ -48,7 +48,22 @@ bool split_radix(int L, int* a, int* b) {
   return best < (1 << 30);
 }
 
+bool plan_shape_search(int64_t nfft, FftShape* s);
+
+// (the search below walks ~1000 candidate splits: remembered per thread for the size last asked about — a model has one)
 bool plan_shape(int64_t nfft, FftShape* s) {
+  thread_local int64_t last_nfft = -1;
+  thread_local bool last_ok = false;
+  thread_local FftShape last_shape;
+  if (nfft != last_nfft) {
+    last_ok = plan_shape_search(nfft, &last_shape);
+    last_nfft = nfft;
+  }
+  if (last_ok) *s = last_shape;
+  return last_ok;
+}
+
+bool plan_shape_search(int64_t nfft, FftShape* s) {
   if (nfft < 512 || nfft > (int64_t)1 << 21 || (nfft & 1)) return false;
   const int N = (int)nfft, M = N / 2;
   int best = 1 << 30;
