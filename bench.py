@@ -480,11 +480,20 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(steps, data):
+    def make_events(steps):
+        """torch creates the CUDA event at its first record(): do that here, in front of the barrier, not inside the
+        timed loop (cudaEventCreate is a few microseconds of host time per event, and 2 * steps of them skew the ranks)."""
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(steps)] for _ in range(2)]
+        for lst in ev:
+            for e in lst:
+                e.record()
+        torch.cuda.synchronize()
+        return ev
+
+    def run(steps, data, events=None):
         import gc
 
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        starts, ends = events if events is not None else make_events(steps)
         loss = None
         gc.disable()  # a generation-0 collection in the middle of a 50 us step is a 100+ us outlier (on N ranks: N chances)
         try:
@@ -510,11 +519,12 @@ def gpu_arm(args):
     import gc
 
     sampler = ClockSampler(local)
+    ev_dev, ev_e2e = make_events(args.steps), make_events(args.steps)
     gc.collect()  # (in front of the barrier: a collection behind it would skew the ranks' start by milliseconds)
     sampler.start()  # (its thread starts up in front of the barrier too: the first timed steps are not perturbed by it)
     barrier()
     launches0 = sweep.launch_count
-    t_dev, med_dev, loss = run(args.steps, (x_dev, y_dev))
+    t_dev, med_dev, loss = run(args.steps, (x_dev, y_dev), ev_dev)
     barrier()
     launches = sweep.launch_count - launches0
     # keep the GPU under the same load long enough for a few clock samples; a FIXED number of steps,
@@ -526,7 +536,7 @@ def gpu_arm(args):
     run(warmup, (x_host, y_host))
     gc.collect()
     barrier()
-    t_e2e, med_e2e, _ = run(args.steps, (x_host, y_host))
+    t_e2e, med_e2e, _ = run(args.steps, (x_host, y_host), ev_e2e)
     barrier()
 
     def reduce_max(*ts):
